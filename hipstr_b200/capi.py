@@ -1,0 +1,344 @@
+"""ctypes view of the C-ABI in include/hipstr_b200.h (libhipstr_b200.so) and of the
+synthetic generator (libhipstr_synth.so).
+
+Python is only the test / bench driver here: the product is the shared library.  No
+fallback exists -- `load()` raises if the library was not built (run
+`__graft_entry__.build()` or `make -C hipstr_b200/csrc`), and `Context()` raises if no
+CUDA device is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhipstr_b200.so")
+SYNTH_PATH = os.path.join(_HERE, "libhipstr_synth.so")
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+c_f64p = C.POINTER(C.c_double)
+
+
+class AlignBatch(C.Structure):
+    """hipstr_align_batch_t"""
+    _fields_ = [
+        ("n_loci", C.c_int32), ("n_blocks", C.c_int32), ("n_options", C.c_int32), ("n_pools", C.c_int32),
+        ("n_haps", C.c_int64),
+        ("locus_block_off", c_i32p), ("locus_pool_off", c_i32p), ("locus_hap_off", c_i64p), ("locus_out_off", c_i64p),
+        ("block_period", c_i32p), ("block_opt_off", c_i32p), ("block_stutter", c_f64p),
+        ("opt_seq_off", c_i32p), ("opt_seq", C.c_char_p),
+        ("pool_seq_off", c_i32p), ("pool_bases", C.c_char_p), ("pool_quals", C.c_char_p), ("pool_seed", c_i32p),
+        ("realign_pool", c_u8p), ("realign_hap", c_u8p),
+    ]
+
+
+class SynthCfg(C.Structure):
+    _fields_ = [
+        ("n_loci", C.c_int32), ("n_samples", C.c_int32), ("reads_per_sample", C.c_int32), ("n_alleles", C.c_int32),
+        ("read_len", C.c_int32), ("trim", C.c_int32), ("period", C.c_int32), ("ref_copies", C.c_int32),
+        ("seed", C.c_uint64), ("stutter_rate", C.c_double), ("sub_rate", C.c_double), ("mate_rate", C.c_double),
+    ]
+
+
+class SynthView(C.Structure):
+    _fields_ = [
+        ("batch", AlignBatch), ("n_reads", C.c_int64),
+        ("locus_read_off", c_i32p), ("locus_sample_off", c_i32p), ("pool_index", c_i32p), ("sample_label", c_i32p),
+        ("second_mate", c_u8p), ("read_weight", c_i32p), ("log_p1", c_f64p), ("log_p2", c_f64p),
+        ("n_haps", c_i32p), ("haploid", c_u8p), ("true_gt", c_i32p), ("read_bp_diff", c_i32p),
+        ("read_ll_size", C.c_int64), ("post_size", C.c_int64),
+    ]
+
+
+STATUS = {0: "OK", 1: "NO_DEVICE", 2: "CUDA", 3: "BAD_ARG", 4: "UNSUPPORTED", 5: "INVALID_SEED", 6: "BAD_CIGAR"}
+
+
+class HipstrError(RuntimeError):
+    def __init__(self, status, msg=""):
+        self.status = status
+        super().__init__("hipstr status %d (%s) %s" % (status, STATUS.get(status, "?"), msg))
+
+
+def ptr(a, ty):
+    return None if a is None else a.ctypes.data_as(ty)
+
+
+def bind_align_abi(lib, prefix):
+    """Declare the entry points that take the flat batch (shared by product, oracle and reference harness)."""
+    B = C.POINTER(AlignBatch)
+    f = getattr(lib, prefix + "calc_seeds")
+    f.restype = C.c_int32
+    f.argtypes = [C.c_int32, c_i32p, c_i32p, c_i32p, C.c_char_p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p,
+                  c_i32p, c_i32p]
+    if prefix != "hipstr_":
+        f = getattr(lib, prefix + "align_batch")
+        f.restype = C.c_int32
+        f.argtypes = [B, c_f64p, c_i32p]
+        f = getattr(lib, prefix + "align_loci")
+        f.restype = C.c_int32
+        f.argtypes = [B, C.c_int32, C.c_int32, c_f64p, c_i32p]
+        f = getattr(lib, prefix + "posteriors")
+        f.restype = C.c_int32
+        f.argtypes = [C.c_int32, c_i32p, c_i32p, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p, c_i32p, c_i32p, c_f64p,
+                      c_f64p, c_i32p, c_f64p]
+    return lib
+
+
+_lib = None
+_synth = None
+
+
+def load():
+    """Load libhipstr_b200.so; fails loudly when it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    B = C.POINTER(AlignBatch)
+    vp = C.c_void_p
+    lib.hipstr_create.restype = C.c_int32
+    lib.hipstr_create.argtypes = [C.c_int32, C.POINTER(vp)]
+    lib.hipstr_destroy.restype = None
+    lib.hipstr_destroy.argtypes = [vp]
+    lib.hipstr_last_error.restype = C.c_char_p
+    lib.hipstr_last_error.argtypes = [vp]
+    lib.hipstr_version.restype = C.c_char_p
+    lib.hipstr_set_stream.restype = C.c_int32
+    lib.hipstr_set_stream.argtypes = [vp, vp]
+    bind_align_abi(lib, "hipstr_")
+    lib.hipstr_pool_reads.restype = C.c_int32
+    lib.hipstr_pool_reads.argtypes = [C.c_int32, c_i32p, C.c_char_p, C.c_char_p, c_i32p, c_i32p, c_i32p, c_i32p,
+                                      C.c_char_p, C.c_char_p]
+    lib.hipstr_align_batch_host.restype = C.c_int32
+    lib.hipstr_align_batch_host.argtypes = [vp, B, c_f64p, c_i32p]
+    lib.hipstr_upload_batch.restype = C.c_int32
+    lib.hipstr_upload_batch.argtypes = [vp, B, C.POINTER(vp)]
+    lib.hipstr_align_batch_dev.restype = C.c_int32
+    lib.hipstr_align_batch_dev.argtypes = [vp, vp, vp, vp]
+    lib.hipstr_free_batch.restype = None
+    lib.hipstr_free_batch.argtypes = [vp, vp]
+    lib.hipstr_batch_num_alignments.restype = C.c_int64
+    lib.hipstr_batch_num_alignments.argtypes = [B]
+    lib.hipstr_last_launch_count.restype = C.c_int32
+    lib.hipstr_last_launch_count.argtypes = [vp]
+    lib.hipstr_enable_timing.restype = C.c_int32
+    lib.hipstr_enable_timing.argtypes = [vp, C.c_int]
+    lib.hipstr_last_kernel_ms.restype = C.c_float
+    lib.hipstr_last_kernel_ms.argtypes = [vp]
+    lib.hipstr_scatter_pool_lls_host.restype = C.c_int32
+    lib.hipstr_scatter_pool_lls_host.argtypes = [vp, C.c_int32, C.c_int32, c_f64p, c_i32p, c_i32p, c_u8p, c_u8p,
+                                                 c_u8p, c_f64p, c_i32p]
+    lib.hipstr_posteriors_host.restype = C.c_int32
+    lib.hipstr_posteriors_host.argtypes = [vp, C.c_int32, c_i32p, c_i32p, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p,
+                                           c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_f64p]
+    _lib = lib
+    return lib
+
+
+def load_synth():
+    global _synth
+    if _synth is not None:
+        return _synth
+    if not os.path.exists(SYNTH_PATH):
+        raise ImportError("%s missing: build it with `make -C hipstr_b200/csrc`" % SYNTH_PATH)
+    lib = C.CDLL(SYNTH_PATH)
+    lib.hipstr_synth_create.restype = C.c_void_p
+    lib.hipstr_synth_create.argtypes = [C.POINTER(SynthCfg)]
+    lib.hipstr_synth_view.restype = C.POINTER(SynthView)
+    lib.hipstr_synth_view.argtypes = [C.c_void_p]
+    lib.hipstr_synth_destroy.restype = None
+    lib.hipstr_synth_destroy.argtypes = [C.c_void_p]
+    _synth = lib
+    return lib
+
+
+def _np(p, n, dtype):
+    if n == 0 or not p:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(p, shape=(n,)).view(dtype)
+
+
+class Synth:
+    """A batch of synthetic loci owned by libhipstr_synth.so."""
+
+    def __init__(self, n_loci, n_samples, reads_per_sample, n_alleles, read_len, seed=1, trim=1, period=4,
+                 ref_copies=12, stutter_rate=0.05, sub_rate=1.0 / 200, mate_rate=0.0):
+        lib = load_synth()
+        self.cfg = SynthCfg(n_loci, n_samples, reads_per_sample, n_alleles, read_len, trim, period, ref_copies, seed,
+                            stutter_rate, sub_rate, mate_rate)
+        self._h = lib.hipstr_synth_create(C.byref(self.cfg))
+        self.view = lib.hipstr_synth_view(self._h).contents
+        v, b = self.view, self.view.batch
+        self.batch = b
+        self.n_loci = b.n_loci
+        self.n_pools = b.n_pools
+        self.n_reads = v.n_reads
+        L = b.n_loci
+        self.locus_pool_off = _np(b.locus_pool_off, L + 1, np.int32)
+        self.locus_out_off = _np(b.locus_out_off, L + 1, np.int64)
+        self.locus_hap_off = _np(b.locus_hap_off, L + 1, np.int64)
+        self.pool_seq_off = _np(b.pool_seq_off, b.n_pools + 1, np.int32)
+        self.pool_seed = _np(b.pool_seed, b.n_pools, np.int32)
+        self.locus_read_off = _np(v.locus_read_off, L + 1, np.int32)
+        self.locus_sample_off = _np(v.locus_sample_off, L + 1, np.int32)
+        self.pool_index = _np(v.pool_index, v.n_reads, np.int32)
+        self.sample_label = _np(v.sample_label, v.n_reads, np.int32)
+        self.second_mate = _np(v.second_mate, v.n_reads, np.uint8)
+        self.read_weight = _np(v.read_weight, v.n_reads, np.int32)
+        self.log_p1 = _np(v.log_p1, v.n_reads, np.float64)
+        self.log_p2 = _np(v.log_p2, v.n_reads, np.float64)
+        self.n_haps = _np(v.n_haps, L, np.int32)
+        self.haploid = _np(v.haploid, L, np.uint8)
+        self.n_out = int(self.locus_out_off[-1])
+        self.read_ll_size = v.read_ll_size
+        self.post_size = v.post_size
+
+    def close(self):
+        if self._h:
+            load_synth().hipstr_synth_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchBuilder:
+    """Hand-built batches for edge-case tests: add loci made of blocks and pooled reads."""
+
+    def __init__(self):
+        self.loci = []
+
+    def add_locus(self, blocks, reads, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01)):
+        """blocks: list of (period, [option sequences]); reads: list of (bases, quals, seed)."""
+        self.loci.append((blocks, reads, stutter))
+        return self
+
+    def build(self, realign_pool=None, realign_hap=None):
+        lbo, lpo, lho, loo = [0], [0], [0], [0]
+        period, boo, stut, oso, pso, seeds = [], [0], [], [0], [0], []
+        oseq, pb, pq = bytearray(), bytearray(), bytearray()
+        for blocks, reads, stutter in self.loci:
+            H = 1
+            for per, opts in blocks:
+                period.append(per)
+                stut.extend(stutter)
+                for o in opts:
+                    oseq.extend(o.encode())
+                    oso.append(len(oseq))
+                boo.append(len(oso) - 1)
+                H *= len(opts)
+            lbo.append(len(period))
+            for bases, quals, seed in reads:
+                assert len(bases) == len(quals)
+                pb.extend(bases.encode())
+                pq.extend(quals.encode() if isinstance(quals, str) else quals)
+                pso.append(len(pb))
+                seeds.append(seed)
+            lpo.append(len(seeds))
+            lho.append(lho[-1] + H)
+            loo.append(loo[-1] + H * len(reads))
+        keep = dict(
+            lbo=np.array(lbo, np.int32), lpo=np.array(lpo, np.int32), lho=np.array(lho, np.int64),
+            loo=np.array(loo, np.int64), period=np.array(period, np.int32), boo=np.array(boo, np.int32),
+            stut=np.array(stut, np.float64), oso=np.array(oso, np.int32), pso=np.array(pso, np.int32),
+            seeds=np.array(seeds, np.int32), oseq=bytes(oseq) + b"\0", pb=bytes(pb) + b"\0", pq=bytes(pq) + b"\0",
+            rp=None if realign_pool is None else np.ascontiguousarray(realign_pool, np.uint8),
+            rh=None if realign_hap is None else np.ascontiguousarray(realign_hap, np.uint8))
+        b = AlignBatch()
+        b.n_loci, b.n_blocks, b.n_options, b.n_pools, b.n_haps = len(self.loci), len(period), len(oso) - 1, len(seeds), lho[-1]
+        b.locus_block_off, b.locus_pool_off = ptr(keep["lbo"], c_i32p), ptr(keep["lpo"], c_i32p)
+        b.locus_hap_off, b.locus_out_off = ptr(keep["lho"], c_i64p), ptr(keep["loo"], c_i64p)
+        b.block_period, b.block_opt_off = ptr(keep["period"], c_i32p), ptr(keep["boo"], c_i32p)
+        b.block_stutter = ptr(keep["stut"], c_f64p)
+        b.opt_seq_off, b.opt_seq = ptr(keep["oso"], c_i32p), keep["oseq"]
+        b.pool_seq_off, b.pool_bases, b.pool_quals = ptr(keep["pso"], c_i32p), keep["pb"], keep["pq"]
+        b.pool_seed = ptr(keep["seeds"], c_i32p)
+        b.realign_pool, b.realign_hap = ptr(keep["rp"], c_u8p), ptr(keep["rh"], c_u8p)
+        b._keep = keep
+        b.n_out = int(loo[-1])
+        return b
+
+
+class Context:
+    """hipstr_ctx_t on one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        st = self.lib.hipstr_create(device, C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "hipstr_create(device=%d)" % device)
+        self.h = h
+
+    def _check(self, st, what):
+        if st != 0:
+            raise HipstrError(st, "%s: %s" % (what, (self.lib.hipstr_last_error(self.h) or b"").decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hipstr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.hipstr_set_stream(self.h, C.c_void_p(cuda_stream)), "set_stream")
+
+    def align_host(self, batch, n_out, ll=None, want_pos=False):
+        """hipstr_align_batch_host: host buffers in, host LLs out."""
+        if ll is None:
+            ll = np.zeros(n_out, np.float64)
+        pos = np.full(n_out, -1, np.int32) if want_pos else None
+        self._check(self.lib.hipstr_align_batch_host(self.h, C.byref(batch), ptr(ll, c_f64p), ptr(pos, c_i32p)),
+                    "align_batch_host")
+        return (ll, pos) if want_pos else ll
+
+    def upload(self, batch):
+        h = C.c_void_p()
+        self._check(self.lib.hipstr_upload_batch(self.h, C.byref(batch), C.byref(h)), "upload_batch")
+        return h
+
+    def align_dev(self, handle, ll_dev_ptr, pos_dev_ptr=None):
+        self._check(self.lib.hipstr_align_batch_dev(self.h, handle, C.c_void_p(ll_dev_ptr),
+                                                    C.c_void_p(pos_dev_ptr) if pos_dev_ptr else None),
+                    "align_batch_dev")
+
+    def free_batch(self, handle):
+        self.lib.hipstr_free_batch(self.h, handle)
+
+    def scatter_host(self, n_haps, pool_ll, pool_seed, pool_index, second_mate, read_ll, read_seed=None,
+                     copy_read=None, realign_hap=None):
+        n_reads = len(pool_index)
+        self._check(self.lib.hipstr_scatter_pool_lls_host(
+            self.h, n_reads, n_haps, ptr(pool_ll, c_f64p), ptr(pool_seed, c_i32p), ptr(pool_index, c_i32p),
+            ptr(second_mate, c_u8p), ptr(copy_read, c_u8p), ptr(realign_hap, c_u8p), ptr(read_ll, c_f64p),
+            ptr(read_seed, c_i32p)), "scatter_pool_lls_host")
+        return read_ll
+
+    def posteriors_host(self, locus_read_off, locus_sample_off, n_haps, haploid, read_ll, log_p1, log_p2,
+                        sample_label, read_weight):
+        n_loci = len(n_haps)
+        S = int(locus_sample_off[-1])
+        post_size = int(sum(int(locus_sample_off[l + 1] - locus_sample_off[l]) * int(n_haps[l]) ** 2
+                            for l in range(n_loci)))
+        post = np.zeros(post_size, np.float64)
+        sample_ll = np.zeros(S, np.float64)
+        best = np.zeros(2 * S, np.int32)
+        total = np.zeros(n_loci, np.float64)
+        self._check(self.lib.hipstr_posteriors_host(
+            self.h, n_loci, ptr(locus_read_off, c_i32p), ptr(locus_sample_off, c_i32p), ptr(n_haps, c_i32p),
+            ptr(haploid, c_u8p), ptr(read_ll, c_f64p), ptr(log_p1, c_f64p), ptr(log_p2, c_f64p),
+            ptr(sample_label, c_i32p), ptr(read_weight, c_i32p), ptr(post, c_f64p), ptr(sample_ll, c_f64p),
+            ptr(best, c_i32p), ptr(total, c_f64p)), "posteriors_host")
+        return post, sample_ll, best.reshape(-1, 2), total

@@ -1,0 +1,126 @@
+/*
+ * host_ops.cpp -- the integer / byte host logic of the hot path that stays on
+ * the CPU: seed selection (a5) and read pooling (a2).  Pure C++, no CUDA.
+ * Reference behaviour: SeqAlignment/HapAligner.cpp:238-318, read_pooler.cpp:3-20,
+ * base_quality.cpp:11-28.
+ */
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hipstr_b200.h"
+
+namespace {
+
+const int kMinSeedDist = 5;  // HapAligner.cpp:17
+
+// Best seed inside [lo, hi] (genomic, inclusive): the centre of the widest
+// stretch not covered by a repeat block; the later stretch wins ties and
+// within a stretch of even length the left of the two central bases is used
+// (calc_best_seed_position, HapAligner.cpp:238-264).
+inline void widest_free_stretch(int32_t lo, int32_t hi, int32_t n_rep, const int32_t* rs, const int32_t* re,
+                                int32_t& dist, int32_t& pos) {
+  dist = pos = -1;
+  int32_t cursor = lo;
+  auto offer = [&](int32_t a, int32_t b) {  // free stretch [a, b]
+    int32_t d = 1 + (b - a) / 2;
+    if (d >= dist) { dist = d; pos = a + d - 1; }
+  };
+  for (int32_t i = 0; i < n_rep && cursor <= hi; i++) {
+    if (cursor < rs[i]) {
+      offer(cursor, std::min(hi, rs[i] - 1));
+      cursor = re[i];
+    } else if (cursor < re[i])
+      cursor = re[i];
+  }
+  if (cursor <= hi) offer(cursor, hi);
+}
+
+}  // namespace
+
+extern "C" hipstr_status_t hipstr_calc_seeds(int32_t n_reads, const int32_t* read_start, const int32_t* read_len,
+                                             const int32_t* cigar_off, const char* cigar_type,
+                                             const int32_t* cigar_len, int32_t first_block_start,
+                                             int32_t last_block_end, int32_t n_repeats,
+                                             const int32_t* repeat_start, const int32_t* repeat_end,
+                                             int32_t* out_seed) {
+  if (n_reads < 0 || (n_reads > 0 && (!read_start || !read_len || !cigar_off || !out_seed))) return HIPSTR_ERR_BAD_ARG;
+  for (int32_t r = 0; r < n_reads; r++) {
+    int32_t gpos = read_start[r];  // genomic coordinate of the next reference-consuming base
+    int32_t rpos = 0;              // index of the next read base
+    int32_t seed = -1, bar = kMinSeedDist;
+    for (int32_t c = cigar_off[r]; c < cigar_off[r + 1]; c++) {
+      const int32_t n = cigar_len[c];
+      const char t = cigar_type[c];
+      if (t == '=') {
+        int32_t lo = std::max(gpos, first_block_start);
+        int32_t hi = std::min(gpos + n - 1, last_block_end - 1);
+        if (lo <= hi) {
+          int32_t d, p;
+          widest_free_stretch(lo, hi, n_repeats, repeat_start, repeat_end, d, p);
+          if (d >= bar) { bar = d; seed = rpos + (p - gpos); }
+        }
+        gpos += n; rpos += n;
+      } else if (t == 'X') {
+        gpos += n; rpos += n;
+      } else if (t == 'I') {
+        rpos += n;
+      } else if (t == 'D') {
+        gpos += n;
+      } else
+        return HIPSTR_ERR_BAD_CIGAR;
+    }
+    if (seed < -1 || seed == 0 || seed >= read_len[r] - 1) return HIPSTR_ERR_INVALID_SEED;
+    out_seed[r] = seed;
+  }
+  return HIPSTR_OK;
+}
+
+extern "C" hipstr_status_t hipstr_pool_reads(int32_t n_reads, const int32_t* seq_off, const char* bases,
+                                             const char* quals, int32_t* pool_index, int32_t* n_pools,
+                                             int32_t* pool_first_read, int32_t* pool_seq_off, char* pool_bases,
+                                             char* pool_quals) {
+  if (n_reads < 0 || !n_pools) return HIPSTR_ERR_BAD_ARG;
+  if (n_reads > 0 && (!seq_off || !bases || !quals || !pool_index || !pool_first_read || !pool_seq_off ||
+                      !pool_bases || !pool_quals))
+    return HIPSTR_ERR_BAD_ARG;
+  std::unordered_map<std::string, int32_t> by_seq;
+  by_seq.reserve((size_t)n_reads * 2);
+  std::vector<std::vector<int32_t> > members;
+  for (int32_t r = 0; r < n_reads; r++) {
+    std::string key(bases + seq_off[r], bases + seq_off[r + 1]);
+    auto it = by_seq.find(key);
+    if (it == by_seq.end()) {
+      it = by_seq.emplace(std::move(key), (int32_t)members.size()).first;
+      pool_first_read[members.size()] = r;
+      members.emplace_back();
+    }
+    pool_index[r] = it->second;
+    members[it->second].push_back(r);
+  }
+  int32_t at = 0;
+  std::vector<char> column;
+  for (size_t p = 0; p < members.size(); p++) {
+    const int32_t first = members[p][0];
+    const int32_t len = seq_off[first + 1] - seq_off[first];
+    pool_seq_off[p] = at;
+    std::memcpy(pool_bases + at, bases + seq_off[first], len);
+    const size_t m = members[p].size();
+    if (m == 1)
+      std::memcpy(pool_quals + at, quals + seq_off[first], len);
+    else {
+      column.resize(m);
+      for (int32_t i = 0; i < len; i++) {
+        for (size_t k = 0; k < m; k++) column[k] = quals[seq_off[members[p][k]] + i];
+        std::nth_element(column.begin(), column.begin() + m / 2, column.end());  // signed char order, as std::sort
+        pool_quals[at + i] = column[m / 2];
+      }
+    }
+    at += len;
+  }
+  pool_seq_off[members.size()] = at;
+  *n_pools = (int32_t)members.size();
+  return HIPSTR_OK;
+}

@@ -1,0 +1,102 @@
+/*
+ * layout.h -- device-resident layout of a flattened batch of loci.
+ *
+ * The reference keeps a locus as a graph of C++ objects (Haplotype -> HapBlock /
+ * RepeatBlock -> StutterAlignerClass, std::vector<Alignment>); here the host
+ * flattens a whole batch of loci ONCE into a handful of packed arrays that are
+ * uploaded with one cudaMemcpyAsync each and stay resident in HBM:
+ *
+ *   pools      one record per pooled read: 16B-aligned offset of its bases/quals
+ *              (so a pool is fetched into shared memory with one bulk copy), length,
+ *              seed, owning locus, output row
+ *   hapsides   one record per (locus, haplotype, orientation): oriented sequence,
+ *              per-row homopolymer class, block list.  Orientation 0 = forward
+ *              haplotype (left of the seed), 1 = reversed haplotype (right of the
+ *              seed), as in HapAligner.cpp:606-627.
+ *   reps       one record per (repeat-block allele, orientation): what the
+ *              reference's StutterAlignerClass constructor precomputes
+ *              (StutterAlignerClass.h:49-80) + the 13 PCR-artifact log-priors
+ *              (RepeatStutterInfo.h:53-61), computed on the host with glibc.
+ *   jobs       (pool, haplotype range) work items, bucketed by columns-per-lane.
+ */
+#ifndef HIPSTR_B200_LAYOUT_H_
+#define HIPSTR_B200_LAYOUT_H_
+
+#include <stdint.h>
+
+#define HIPSTR_WARPS_PER_CTA 4
+#define HIPSTR_MAX_BLOCKS 8          /* haplotype blocks per locus handled by the kernel */
+#define HIPSTR_ROW_REPEAT 0x80       /* rowinfo flag: row belongs to a repeat block      */
+#define HIPSTR_ROW_AFTER_REPEAT 0x40 /* rowinfo flag: first row after a repeat block     */
+
+struct DevPool {          /* 32 B */
+  int32_t seq_off;        /* byte offset into bases/quals, multiple of 16 */
+  int32_t len;            /* read length */
+  int32_t seed;           /* seed base index (>= 1, <= len-2); never -1 here */
+  int32_t locus;
+  int64_t out_off;        /* ll_out index of haplotype 0 of this pool */
+  int32_t hap_rec0;       /* first hapside record of the locus = 2 * (global hap index of hap 0) */
+  int32_t n_haps;
+};
+
+struct DevHapSide {       /* 32 B */
+  int32_t seq_off;        /* into hapbytes: oriented sequence, len bytes */
+  int32_t row_off;        /* into hapbytes: rowinfo, len bytes: low 4 bits = homopolymer class
+                             (min(15, max(hp(i), hp(i-1)))), flags above */
+  int32_t len;            /* haplotype length L_h */
+  int32_t blk_off;        /* into blocks */
+  int32_t n_blocks;
+  int32_t n_seed_pos;     /* total length of flank blocks (compute_aln_logprob num_seeds) */
+  int32_t seg1_class;     /* haplotypes of a locus with equal class share every row before the
+                             first repeat block in this orientation (sequence AND homopolymer
+                             classes): the kernel may reuse those rows */
+  int32_t pad;
+};
+
+struct DevBlock {         /* 16 B */
+  int32_t row_start;      /* first haplotype row of the block in this orientation */
+  int32_t len;
+  int32_t rep;            /* index into reps, or -1 for a flank block */
+  int32_t pad;
+};
+
+struct DevRep {           /* 128 B */
+  int32_t seq_off;        /* into hapbytes: oriented allele sequence */
+  int32_t len;            /* B */
+  int32_t period;
+  int32_t n_del;          /* StutterAlignerClass num_deletions_ */
+  int32_t runs_off;       /* into runs: max(n_del,1) tables of B uint16 (upstream_match_lengths_) */
+  int32_t left_align;     /* !reversed (RepeatBlock.h:28,41); only the traceback uses it */
+  int32_t pad[2];
+  double  art[13];        /* log_prob_pcr_artifact for D = -6p .. +6p */
+};
+
+struct DevJob {           /* 16 B */
+  int32_t pool;
+  int32_t h0, h1;         /* haplotype range [h0, h1) of the pool's locus */
+  int32_t pad;
+};
+
+struct AlignParams {
+  const DevJob* jobs;
+  int32_t n_jobs;
+  int32_t n_max;          /* shared-memory stride: max read length of the launch (multiple of 16) */
+  int32_t l_max;          /* max haplotype length of the launch (multiple of 2) */
+  const DevPool* pools;
+  const char* bases;
+  const char* quals;
+  const DevHapSide* hapsides;
+  const uint8_t* hapbytes;
+  const DevBlock* blocks;
+  const DevRep* reps;
+  const uint16_t* runs;
+  const uint8_t* hap_mask;   /* per global hap index; NULL = all */
+  const double* qual_lut;    /* [256][2]: log_correct, log_error by quality byte */
+  const double* trans;       /* [3][16]: LOG_MATCH_TO_MATCH / _INS / _DEL by homopolymer class */
+  const double* int_logs;    /* [10000] */
+  double* ll_out;
+  int32_t* pos_out;          /* may be NULL */
+  double* debug_out;         /* may be NULL: [2][l_max] last-column M values of job 0's last haplotype */
+};
+
+#endif

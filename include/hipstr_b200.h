@@ -1,0 +1,221 @@
+/*
+ * hipstr_b200.h -- C-ABI of the B200-native HipSTR hot path.
+ *
+ * Every entry point replaces one seam of the reference (tfwillems/HipSTR); the
+ * reference interface it stands in for is cited next to each declaration as
+ * path:line relative to the reference checkout.  The reference has no FFI of
+ * its own (it is one C++ program), so the "binding" a maintainer adds is a
+ * direct C++ call from the class that owns the seam -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no C++/torch types; all functions return a
+ *     hipstr_status_t (0 = OK) instead of exit()/assert() like the reference;
+ *   - "host" entry points take HOST buffers and do the H2D/D2H copies
+ *     themselves (end-to-end path); "_dev" entry points take DEVICE buffers
+ *     (inputs resident in HBM) and only enqueue kernels on the given stream;
+ *   - a context owns one GPU's streams, workspaces and the constant tables
+ *     (quality LUT, transition tables, INT_LOGS) which are computed ON THE HOST
+ *     with glibc and uploaded -- never recomputed with CUDA libm;
+ *   - no CPU fallback: if no CUDA device is usable hipstr_create() fails with
+ *     HIPSTR_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef HIPSTR_B200_H_
+#define HIPSTR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  HIPSTR_OK               = 0,
+  HIPSTR_ERR_NO_DEVICE    = 1,  /* no usable CUDA device / driver            */
+  HIPSTR_ERR_CUDA         = 2,  /* a CUDA runtime call failed (see last_error) */
+  HIPSTR_ERR_BAD_ARG      = 3,  /* malformed batch (offsets, sizes, NULLs)   */
+  HIPSTR_ERR_UNSUPPORTED  = 4,  /* shape outside the kernel's static limits  */
+  HIPSTR_ERR_INVALID_SEED = 5,  /* reference: printErrorAndDie("Invalid alignment seed") */
+  HIPSTR_ERR_BAD_CIGAR    = 6   /* reference: "Unrecognized CIGAR char in calc_seed_base()" */
+} hipstr_status_t;
+
+/* Number of PCR-stutter artifact sizes evaluated per repeat block:
+ * -6..+6 repeat units (RepeatStutterInfo.h:10-11). */
+#define HIPSTR_NUM_ARTIFACTS 13
+#define HIPSTR_MAX_ARTIFACT_UNITS 6
+
+/* ------------------------------------------------------------------------- *
+ *  Flat description of a batch of loci for the alignment HMM.
+ *
+ *  One locus = the candidate-haplotype structure the reference keeps in
+ *  Haplotype/HapBlock/RepeatBlock objects (SeqAlignment/Haplotype.h:12-50,
+ *  HapBlock.h:18-148, RepeatBlock.h:15-70) plus its pooled reads
+ *  (read_pooler.h:14-53).  Everything is CSR-style: an offsets array of
+ *  length count+1 indexes into a packed payload array.
+ *
+ *  Haplotype h of a locus selects one option per block by the reference's
+ *  reflected mixed-radix Gray code with block 0 varying fastest
+ *  (Haplotype.cpp:123-196); option 0 of a block is its reference sequence.
+ * ------------------------------------------------------------------------- */
+typedef struct hipstr_align_batch {
+  int32_t n_loci;
+  int32_t n_blocks;      /* total over loci */
+  int32_t n_options;     /* total over blocks */
+  int32_t n_pools;       /* total pooled reads over loci */
+  int64_t n_haps;        /* total haplotypes over loci = sum prod(options per block) */
+
+  /* per locus, length n_loci+1 */
+  const int32_t* locus_block_off;   /* blocks  [off[l], off[l+1]) belong to locus l   */
+  const int32_t* locus_pool_off;    /* pools   [off[l], off[l+1]) belong to locus l   */
+  const int64_t* locus_hap_off;     /* haplotype-mask entries of locus l              */
+  const int64_t* locus_out_off;     /* LL outputs of locus l: [P_l][H_l] row-major,
+                                       pool-major / haplotype-minor like
+                                       HapAligner.cpp:324 (aln_probs + i*num_combs)   */
+
+  /* per block, length n_blocks (+1 for the offsets) */
+  const int32_t* block_period;      /* 0 = flank block (HapBlock); >0 = repeat block
+                                       (RepeatBlock) with this motif period          */
+  const int32_t* block_opt_off;     /* options [off[b], off[b+1]) belong to block b   */
+  const double*  block_stutter;     /* [n_blocks][6]: inframe_geom, inframe_up,
+                                       inframe_down, outframe_geom, outframe_up,
+                                       outframe_down (stutter_model.h:36-37); ignored
+                                       for flank blocks                              */
+
+  /* per option, length n_options+1 */
+  const int32_t* opt_seq_off;       /* chars [off[o], off[o+1]) of opt_seq            */
+  const char*    opt_seq;           /* allele sequences, forward strand orientation   */
+
+  /* per pooled read, length n_pools (+1) */
+  const int32_t* pool_seq_off;      /* chars [off[p], off[p+1]) of pool_bases/quals   */
+  const char*    pool_bases;        /* read sequence (ASCII)                          */
+  const char*    pool_quals;        /* Phred+33 base qualities (ASCII)                */
+  const int32_t* pool_seed;         /* seed base index, or -1 = no seed: the read gets
+                                       LL 0.0 for every haplotype (HapAligner.cpp:333) */
+
+  /* optional masks (NULL = everything) */
+  const uint8_t* realign_pool;      /* [n_pools]: 0 = leave this pool's outputs untouched
+                                       (HapAligner.cpp:326-329)                       */
+  const uint8_t* realign_hap;       /* [n_haps]: 0 = leave this column untouched and
+                                       break DP-row reuse (HapAligner.cpp:615-619)    */
+} hipstr_align_batch_t;
+
+typedef struct hipstr_ctx hipstr_ctx_t;
+
+/* --- context ------------------------------------------------------------- */
+
+/* Create a context on CUDA device `device`.  Uploads the constant tables the
+ * reference builds in precompute_integer_logs() (mathops.cpp:15-19),
+ * init_alignment_model() (SeqAlignment/AlignmentModel.cpp:20-32) and
+ * BaseQuality() (base_quality.h:29-38). */
+hipstr_status_t hipstr_create(int device, hipstr_ctx_t** out_ctx);
+void            hipstr_destroy(hipstr_ctx_t* ctx);
+const char*     hipstr_last_error(const hipstr_ctx_t* ctx);
+const char*     hipstr_version(void);
+
+/* Use an externally owned CUDA stream (cudaStream_t passed as void*) for all
+ * subsequent work of this context; NULL restores the context's own stream. */
+hipstr_status_t hipstr_set_stream(hipstr_ctx_t* ctx, void* cuda_stream);
+
+/* --- a5: seed selection (host integer logic) -----------------------------
+ * Replaces HapAligner::calc_seed_base (SeqAlignment/HapAligner.cpp:270-318)
+ * + calc_best_seed_position (:238-264) for n_reads alignments of ONE locus.
+ * CIGAR ops of read r are cigar_type/cigar_len[cigar_off[r]..cigar_off[r+1]),
+ * types are the reference's '=', 'X', 'I', 'D' (AlignmentData.h:12-27).
+ * first_block_start / last_block_end and the repeat block [start,end) lists
+ * are the genomic coordinates HapBlock::start()/end() return. */
+hipstr_status_t hipstr_calc_seeds(int32_t n_reads, const int32_t* read_start,
+                                  const int32_t* read_len,
+                                  const int32_t* cigar_off, const char* cigar_type,
+                                  const int32_t* cigar_len,
+                                  int32_t first_block_start, int32_t last_block_end,
+                                  int32_t n_repeats, const int32_t* repeat_start,
+                                  const int32_t* repeat_end, int32_t* out_seed);
+
+/* --- a2: read pooling (host byte logic) ------------------------------------
+ * Replaces ReadPooler::add_alignment (read_pooler.cpp:3-20) + ReadPooler::pool
+ * (read_pooler.h:42-48) + BaseQuality::median_base_qualities
+ * (base_quality.cpp:11-28) for the n_reads reads of ONE locus.  Reads with an
+ * identical base sequence share a pool; pools are numbered in order of first
+ * appearance; a pool inherits the coordinates / CIGAR of its first member
+ * (pool_first_read) and, per position, the UPPER median (sorted[n/2]) of its
+ * members' quality bytes.
+ *   seq_off [n_reads+1] offsets into bases/quals
+ *   pool_index [n_reads] out; *n_pools out; pool_first_read [n_reads] capacity
+ *   pool_seq_off [n_reads+1] capacity; pool_bases/pool_quals: capacity
+ *   seq_off[n_reads] bytes each. */
+hipstr_status_t hipstr_pool_reads(int32_t n_reads, const int32_t* seq_off, const char* bases,
+                                  const char* quals, int32_t* pool_index, int32_t* n_pools,
+                                  int32_t* pool_first_read, int32_t* pool_seq_off,
+                                  char* pool_bases, char* pool_quals);
+
+/* --- a4,a6-a10: read x haplotype HMM alignment (kernel K1) ----------------
+ * Replaces HapAligner::process_reads (SeqAlignment/HapAligner.h:86-87, impl
+ * HapAligner.cpp:320-343 -> process_read :573-709 -> align_seq_to_hap :26-161,
+ * compute_aln_logprob :163-231, StutterAlignerClass.cpp:12-162) for every
+ * pooled read of every locus of the batch in one call.
+ *   ll_out       [locus_out_off[n_loci]] doubles; entry (l,p,h) at
+ *                locus_out_off[l] + p*H_l + h.  Entries masked out by
+ *                realign_pool / realign_hap are left untouched (so the caller's
+ *                buffer content survives, as in the reference).
+ *   seed_hap_pos optional (may be NULL), same indexing, int32: haplotype
+ *                position the seed base aligns to in the best placement
+ *                (max_index of compute_aln_logprob, HapAligner.cpp:184-222).
+ * Host buffers in, host buffers out; copies are part of the call. */
+hipstr_status_t hipstr_align_batch_host(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch,
+                                        double* ll_out, int32_t* seed_hap_pos);
+
+/* Stage a batch in device memory (host -> HBM) and return a handle; then run
+ * the kernels any number of times on the resident copy.  ll_dev is a DEVICE
+ * pointer of locus_out_off[n_loci] doubles (seed_hap_pos_dev may be NULL). */
+typedef struct hipstr_dev_batch hipstr_dev_batch_t;
+hipstr_status_t hipstr_upload_batch(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch,
+                                    hipstr_dev_batch_t** out_handle);
+hipstr_status_t hipstr_align_batch_dev(hipstr_ctx_t* ctx, const hipstr_dev_batch_t* handle,
+                                       double* ll_dev, int32_t* seed_hap_pos_dev);
+void            hipstr_free_batch(hipstr_ctx_t* ctx, hipstr_dev_batch_t* handle);
+/* Number of (pooled read, haplotype) alignments the batch performs (mask aware,
+ * seedless reads excluded): the count of `*prob_ptr = LL` executions at
+ * HapAligner.cpp:632. */
+int64_t         hipstr_batch_num_alignments(const hipstr_align_batch_t* batch);
+/* Kernel launches issued by the last align call of this context, and the device
+ * time in ms of the last align_batch_dev call when timing is enabled
+ * (CUDA events on the context's stream). */
+int32_t         hipstr_last_launch_count(const hipstr_ctx_t* ctx);
+hipstr_status_t hipstr_enable_timing(hipstr_ctx_t* ctx, int enable);
+float           hipstr_last_kernel_ms(const hipstr_ctx_t* ctx);
+
+/* --- a3 tail: pool -> read scatter and mate merge (kernel K2) -------------
+ * Replaces the tail of SeqStutterGenotyper::calc_hap_aln_probs
+ * (seq_stutter_genotyper.cpp:530-564) for one locus: copies pool LLs to member
+ * reads for realigned haplotypes (copy_read / realign_hap may be NULL = all),
+ * then replaces both mates' entries by their sum where second_mate[r] != 0.
+ * read_ll is [n_reads][n_haps] row-major and is updated IN PLACE. */
+hipstr_status_t hipstr_scatter_pool_lls_host(hipstr_ctx_t* ctx, int32_t n_reads, int32_t n_haps,
+                                             const double* pool_ll, const int32_t* pool_seed,
+                                             const int32_t* pool_index, const uint8_t* second_mate,
+                                             const uint8_t* copy_read, const uint8_t* realign_hap,
+                                             double* read_ll, int32_t* read_seed);
+
+/* --- a13,a14: genotype posteriors (kernel K3) ------------------------------
+ * Replaces Genotyper::calc_log_sample_posteriors (genotyper.h:72, impl
+ * genotyper.cpp:44-80, priors :20-42) and get_optimal_haplotypes (:82-97) for a
+ * batch of loci.  Reads are sample-major within a locus (genotyper.h:104-112).
+ *   locus_read_off [n_loci+1], locus_sample_off [n_loci+1], n_haps [n_loci],
+ *   haploid [n_loci] (0/1)
+ *   read_ll    packed per locus [R_l][H_l]; log_p1/log_p2/sample_label/weight [R]
+ *   post_out   packed per locus [S_l][H_l][H_l] normalised log posteriors
+ *   sample_ll_out [S_total] per-sample total LL (sample_total_LLs_)
+ *   best_out   [S_total][2] argmax diplotype (first maximum wins, strict >)
+ *   returns per-locus total LL in total_ll_out [n_loci] (may be NULL). */
+hipstr_status_t hipstr_posteriors_host(hipstr_ctx_t* ctx, int32_t n_loci,
+                                       const int32_t* locus_read_off, const int32_t* locus_sample_off,
+                                       const int32_t* n_haps, const uint8_t* haploid,
+                                       const double* read_ll, const double* log_p1, const double* log_p2,
+                                       const int32_t* sample_label, const int32_t* read_weight,
+                                       double* post_out, double* sample_ll_out, int32_t* best_out,
+                                       double* total_ll_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPSTR_B200_H_ */

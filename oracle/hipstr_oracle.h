@@ -1,0 +1,60 @@
+/*
+ * hipstr_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain serial C++) of the reference algorithm for the hot
+ * path, taking the same flat inputs as the C-ABI in include/hipstr_b200.h.
+ * It exists to check the CUDA path; nothing under hipstr_b200/ may call it.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs load liboracle.so.
+ *
+ * Parity pinning: the reference ships no golden vectors for this path
+ * (SURVEY.md 4, 8c).  The restatement is pinned against the UNMODIFIED
+ * reference sources compiled into oracle/_ref/libhipstr_ref.so (see
+ * oracle/Makefile, oracle/ref_harness.cpp) by tests/test_oracle_vs_ref.py in
+ * the build container, and against fixtures generated from that library and
+ * committed under tests/golden/ (tests/golden/make_golden.py).
+ */
+#ifndef HIPSTR_ORACLE_H_
+#define HIPSTR_ORACLE_H_
+
+#include "../include/hipstr_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* The reference's two approximate log-sum-exp forms (mathops.cpp:86-106). */
+double oracle_fast_lse2(double a, double b);
+double oracle_fast_lse_vec(const double* v, int32_t n);
+
+/* Per-block option index of haplotype `hap` (Haplotype.cpp:157-196). */
+void oracle_hap_options(int32_t n_blocks, const int32_t* n_opts, int64_t hap, int32_t* out_opts);
+
+int32_t oracle_calc_seeds(int32_t n_reads, const int32_t* read_start, const int32_t* read_len,
+                          const int32_t* cigar_off, const char* cigar_type, const int32_t* cigar_len,
+                          int32_t first_block_start, int32_t last_block_end,
+                          int32_t n_repeats, const int32_t* repeat_start, const int32_t* repeat_end,
+                          int32_t* out_seed);
+
+int32_t oracle_align_batch(const hipstr_align_batch_t* batch, double* ll_out, int32_t* seed_hap_pos);
+
+/* Same, restricted to loci [locus_begin, locus_end) -- lets bench.py fan the
+ * CPU baseline out over host cores by forking over locus shards. */
+int32_t oracle_align_loci(const hipstr_align_batch_t* batch, int32_t locus_begin, int32_t locus_end,
+                          double* ll_out, int32_t* seed_hap_pos);
+
+int32_t oracle_scatter_pool_lls(int32_t n_reads, int32_t n_haps, const double* pool_ll,
+                                const int32_t* pool_seed, const int32_t* pool_index,
+                                const uint8_t* second_mate, const uint8_t* copy_read,
+                                const uint8_t* realign_hap, double* read_ll, int32_t* read_seed);
+
+int32_t oracle_posteriors(int32_t n_loci, const int32_t* locus_read_off, const int32_t* locus_sample_off,
+                          const int32_t* n_haps, const uint8_t* haploid, const double* read_ll,
+                          const double* log_p1, const double* log_p2, const int32_t* sample_label,
+                          const int32_t* read_weight, double* post_out, double* sample_ll_out,
+                          int32_t* best_out, double* total_ll_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

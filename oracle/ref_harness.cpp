@@ -1,0 +1,231 @@
+/*
+ * ref_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Thin extern "C" adapter that drives the UNMODIFIED reference classes
+ * (compiled from /root/reference/src by oracle/Makefile, objects and the
+ * resulting libhipstr_ref.so live only under oracle/_ref/) with the same flat
+ * inputs as include/hipstr_b200.h.  No reference source is copied: this file
+ * only #includes the reference headers from where they lie and calls the
+ * public entry points the survey lists as seams B2-B4:
+ *   HapAligner::process_read / calc_seed_base   (SeqAlignment/HapAligner.h:81-93)
+ *   Genotyper::calc_log_sample_posteriors        (genotyper.h:72, via a test subclass)
+ *   EMStutterGenotyper::train                    (em_stutter_genotyper.h:110)
+ */
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "SeqAlignment/AlignmentData.h"
+#include "SeqAlignment/AlignmentModel.h"
+#include "SeqAlignment/AlignmentTraceback.h"
+#include "SeqAlignment/HapAligner.h"
+#include "SeqAlignment/HapBlock.h"
+#include "SeqAlignment/Haplotype.h"
+#include "SeqAlignment/RepeatBlock.h"
+#include "base_quality.h"
+#include "em_stutter_genotyper.h"
+#include "genotyper.h"
+#include "mathops.h"
+#include "stutter_model.h"
+
+#include "../include/hipstr_b200.h"
+
+// genotyper.cpp (get_vcf_header) pulls in FastaReader, whose only external symbols are
+// htslib's faidx entry points; the hot path never reaches them, so instead of building
+// htslib they are stubbed here (calling one aborts).
+extern "C" {
+void fai_destroy(void*) {}
+void* fai_load(const char*) { abort(); }
+int faidx_nseq(const void*) { abort(); }
+const char* faidx_iseq(const void*, int) { abort(); }
+int faidx_seq_len(const void*, const char*) { abort(); }
+char* fai_fetch(const void*, const char*, int*) { abort(); }
+char* faidx_fetch_seq(const void*, const char*, int, int, int*) { abort(); }
+}
+
+namespace {
+
+struct Init {
+  Init() { precompute_integer_logs(); init_alignment_model(); }
+};
+void ensure_init() { static Init once; }
+
+struct RefLocus {
+  std::vector<HapBlock*> blocks;
+  std::vector<StutterModel*> models;
+  Haplotype* hap = NULL;
+  RefLocus(const hipstr_align_batch_t* bt, int l, const int32_t* starts, const int32_t* ends) {
+    int b0 = bt->locus_block_off[l], b1 = bt->locus_block_off[l + 1];
+    int32_t pos = 0;
+    for (int b = b0; b < b1; b++) {
+      int o0 = bt->block_opt_off[b], o1 = bt->block_opt_off[b + 1];
+      std::string ref(bt->opt_seq + bt->opt_seq_off[o0], bt->opt_seq + bt->opt_seq_off[o0 + 1]);
+      int32_t st = starts ? starts[b - b0] : pos, en = ends ? ends[b - b0] : pos + (int32_t)ref.size();
+      HapBlock* blk;
+      if (bt->block_period[b] > 0) {
+        const double* p = bt->block_stutter + 6 * (size_t)b;
+        StutterModel* m = new StutterModel(p[0], p[1], p[2], p[3], p[4], p[5], bt->block_period[b]);
+        models.push_back(m);
+        blk = new RepeatBlock(st, en, ref, bt->block_period[b], m);
+      } else
+        blk = new HapBlock(st, en, ref);
+      for (int o = o0 + 1; o < o1; o++)
+        blk->add_alternate(std::string(bt->opt_seq + bt->opt_seq_off[o], bt->opt_seq + bt->opt_seq_off[o + 1]));
+      blocks.push_back(blk);
+      pos = en;
+    }
+    hap = new Haplotype(blocks);
+  }
+  ~RefLocus() {
+    delete hap;
+    for (auto b : blocks) delete b;
+    for (auto m : models) delete m;
+  }
+};
+
+class ExposedGenotyper : public Genotyper {
+ public:
+  ExposedGenotyper(bool haploid, const std::vector<std::string>& names, const std::vector<std::vector<double> >& p1,
+                   const std::vector<std::vector<double> >& p2, int num_alleles)
+      : Genotyper(haploid, names, p1, p2) {
+    num_alleles_ = num_alleles;
+    log_sample_posteriors_ = new double[num_samples_ * num_alleles_ * num_alleles_];
+    log_aln_probs_ = new double[num_reads_ * num_alleles_];
+  }
+  double run(const double* ll, const int32_t* weights, double* post, double* sample_ll, int32_t* best) {
+    std::memcpy(log_aln_probs_, ll, sizeof(double) * num_reads_ * num_alleles_);
+    std::vector<int> w(weights, weights + num_reads_);
+    double total = calc_log_sample_posteriors(w);
+    std::memcpy(post, log_sample_posteriors_, sizeof(double) * num_samples_ * num_alleles_ * num_alleles_);
+    std::memcpy(sample_ll, sample_total_LLs_, sizeof(double) * num_samples_);
+    if (best) {
+      std::vector<std::pair<int, int> > gts;
+      get_optimal_haplotypes(gts);
+      for (int s = 0; s < num_samples_; s++) { best[2 * s] = gts[s].first; best[2 * s + 1] = gts[s].second; }
+    }
+    return total;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+double ref_fast_lse2(double a, double b) { return fast_log_sum_exp(a, b); }
+double ref_fast_lse_vec(const double* v, int32_t n) {
+  std::vector<double> x(v, v + n);
+  return fast_log_sum_exp(x);
+}
+
+// Enumerate haplotypes with the reference iterator; out_opts is [n_haps][n_blocks].
+int32_t ref_enumerate_haplotypes(const hipstr_align_batch_t* bt, int32_t locus, int32_t* out_opts) {
+  ensure_init();
+  RefLocus rl(bt, locus, NULL, NULL);
+  int nb = rl.hap->num_blocks();
+  int64_t h = 0;
+  do {
+    for (int b = 0; b < nb; b++) out_opts[h * nb + b] = rl.hap->cur_index(b);
+    h++;
+  } while (rl.hap->next());
+  rl.hap->reset();
+  return (int32_t)h;
+}
+
+int32_t ref_calc_seeds(int32_t n_reads, const int32_t* read_start, const int32_t* read_len, const int32_t* cigar_off,
+                       const char* cigar_type, const int32_t* cigar_len, int32_t first_block_start,
+                       int32_t last_block_end, int32_t n_repeats, const int32_t* repeat_start,
+                       const int32_t* repeat_end, int32_t* out_seed) {
+  ensure_init();
+  // Dummy haplotype with the requested block coordinates: flank, (repeat, flank)*.
+  std::vector<HapBlock*> blocks;
+  StutterModel model(0.9, 0.01, 0.01, 0.9, 0.01, 0.01, 2);
+  if (n_repeats != 1) return HIPSTR_ERR_UNSUPPORTED;  // Haplotype::adjust_indels asserts exactly 3 blocks
+  blocks.push_back(new HapBlock(first_block_start, repeat_start[0], "ACGTAC"));
+  blocks.push_back(new RepeatBlock(repeat_start[0], repeat_end[0], "ATATATAT", 2, &model));
+  blocks.push_back(new HapBlock(repeat_end[0], last_block_end, "GATTAC"));
+  Haplotype hap(blocks);
+  std::vector<bool> mask(hap.num_combs(), true);
+  {
+    HapAligner aligner(&hap, mask);
+    for (int r = 0; r < n_reads; r++) {
+      std::string seq(read_len[r], 'A'), qual(read_len[r], 'I');
+      int32_t ref_span = 0;
+      Alignment aln(read_start[r], 0, false, "r", qual, seq, "");
+      for (int c = cigar_off[r]; c < cigar_off[r + 1]; c++) {
+        aln.add_cigar_element(CigarElement(cigar_type[c], cigar_len[c]));
+        if (cigar_type[c] != 'I') ref_span += cigar_len[c];
+      }
+      aln.set_stop(read_start[r] + ref_span - 1);
+      out_seed[r] = aligner.calc_seed_base(aln);
+    }
+  }
+  for (auto b : blocks) delete b;
+  return HIPSTR_OK;
+}
+
+int32_t ref_align_loci(const hipstr_align_batch_t* bt, int32_t l0, int32_t l1, double* ll_out, int32_t* seed_hap_pos) {
+  ensure_init();
+  (void)seed_hap_pos;
+  BaseQuality base_quality;
+  for (int l = l0; l < l1; l++) {
+    RefLocus rl(bt, l, NULL, NULL);
+    const int64_t H = rl.hap->num_combs();
+    std::vector<bool> mask(H, true);
+    if (bt->realign_hap)
+      for (int64_t h = 0; h < H; h++) mask[h] = bt->realign_hap[bt->locus_hap_off[l] + h] != 0;
+    HapAligner aligner(rl.hap, mask);
+    AlignmentTrace trace(rl.hap->num_blocks());
+    int p0 = bt->locus_pool_off[l], p1 = bt->locus_pool_off[l + 1];
+    for (int p = p0; p < p1; p++) {
+      if (bt->realign_pool && !bt->realign_pool[p]) continue;
+      double* row = ll_out + bt->locus_out_off[l] + (int64_t)(p - p0) * H;
+      int seed = bt->pool_seed[p];
+      if (seed < 0) {
+        for (int64_t h = 0; h < H; h++) row[h] = 0;
+        continue;
+      }
+      int s0 = bt->pool_seq_off[p], s1 = bt->pool_seq_off[p + 1];
+      Alignment aln(0, 0, false, "READPOOL", std::string(bt->pool_quals + s0, bt->pool_quals + s1),
+                    std::string(bt->pool_bases + s0, bt->pool_bases + s1), "");
+      aligner.process_read(aln, seed, &base_quality, false, row, trace);
+    }
+  }
+  return HIPSTR_OK;
+}
+
+int32_t ref_align_batch(const hipstr_align_batch_t* bt, double* ll_out, int32_t* seed_hap_pos) {
+  return ref_align_loci(bt, 0, bt->n_loci, ll_out, seed_hap_pos);
+}
+
+int32_t ref_posteriors(int32_t n_loci, const int32_t* locus_read_off, const int32_t* locus_sample_off,
+                       const int32_t* n_haps, const uint8_t* haploid, const double* read_ll, const double* log_p1,
+                       const double* log_p2, const int32_t* sample_label, const int32_t* read_weight,
+                       double* post_out, double* sample_ll_out, int32_t* best_out, double* total_ll_out) {
+  ensure_init();
+  size_t ll_off = 0, post_off = 0;
+  for (int l = 0; l < n_loci; l++) {
+    const int H = n_haps[l], r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
+    const int s0 = locus_sample_off[l], S = locus_sample_off[l + 1] - s0;
+    std::vector<std::string> names;
+    std::vector<std::vector<double> > p1(S), p2(S);
+    for (int s = 0; s < S; s++) { std::stringstream ss; ss << "S" << s; names.push_back(ss.str()); }
+    int prev = 0;
+    for (int r = r0; r < r1; r++) {
+      if (sample_label[r] < prev) return HIPSTR_ERR_BAD_ARG;  // reads must be sample-major
+      prev = sample_label[r];
+      p1[sample_label[r]].push_back(log_p1[r]);
+      p2[sample_label[r]].push_back(log_p2[r]);
+    }
+    ExposedGenotyper g(haploid[l] != 0, names, p1, p2, H);
+    double total = g.run(read_ll + ll_off, read_weight + r0, post_out + post_off, sample_ll_out + s0,
+                         best_out ? best_out + 2 * s0 : NULL);
+    if (total_ll_out) total_ll_out[l] = total;
+    ll_off += (size_t)(r1 - r0) * H;
+    post_off += (size_t)S * H * H;
+  }
+  return HIPSTR_OK;
+}
+
+}  // extern "C"
