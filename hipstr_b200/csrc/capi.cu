@@ -1,0 +1,387 @@
+/*
+ * capi.cu -- the C-ABI of include/hipstr_b200.h: context, host<->device staging, launches.
+ * No CPU fallback: every compute entry point needs a context, and a context needs a GPU.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hipstr_b200.h"
+#include "flatten.h"
+#include "kernels.h"
+#include "layout.h"
+
+using namespace hipstr;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct hipstr_dev_batch {
+  DevBuf pools, bases, quals, hapsides, hapbytes, blocks, reps, runs, mask, jobs[kNumColVariants];
+  int32_t n_jobs[kNumColVariants];
+  int32_t n_max[kNumColVariants], l_max[kNumColVariants];
+  int64_t n_out = 0, n_alignments = 0;
+  void release() {
+    pools.release(); bases.release(); quals.release(); hapsides.release(); hapbytes.release();
+    blocks.release(); reps.release(); runs.release(); mask.release();
+    for (auto& j : jobs) j.release();
+  }
+};
+
+struct hipstr_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  double *d_qual_lut = nullptr, *d_trans = nullptr, *d_int_logs = nullptr;
+  std::string last_error;
+  int32_t last_launches = 0;
+  bool timing = false;
+  float last_ms = 0.f;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  hipstr_dev_batch scratch;      // reused by the *_host entry points
+  DevBuf d_ll, d_pos, d_misc[12];
+  double* d_debug = nullptr;     // test hook, see hipstr_debug_lastcols
+};
+
+namespace {
+
+hipstr_status_t fail(hipstr_ctx* c, hipstr_status_t st, const std::string& msg) {
+  if (c) c->last_error = msg;
+  return st;
+}
+#define CU(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(ctx, HIPSTR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));  \
+  } while (0)
+
+template <class T>
+cudaError_t put(DevBuf& d, const std::vector<T>& v, cudaStream_t s) {
+  cudaError_t e = d.reserve(std::max<size_t>(v.size() * sizeof(T), 16));
+  if (e != cudaSuccess || v.empty()) return e;
+  return cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+template <class T>
+cudaError_t put(DevBuf& d, const T* v, size_t n, cudaStream_t s) {
+  cudaError_t e = d.reserve(std::max<size_t>(n * sizeof(T), 16));
+  if (e != cudaSuccess || n == 0) return e;
+  return cudaMemcpyAsync(d.p, v, n * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+hipstr_status_t stage(hipstr_ctx* ctx, const hipstr_align_batch_t* batch, hipstr_dev_batch& d) {
+  FlatBatch f;
+  std::string err;
+  hipstr_status_t st = flatten_batch(batch, f, err);
+  if (st != HIPSTR_OK) return fail(ctx, st, err);
+  cudaStream_t s = ctx->stream;
+  CU(put(d.pools, f.pools, s));
+  CU(put(d.bases, f.bases, s));
+  CU(put(d.quals, f.quals, s));
+  CU(put(d.hapsides, f.hapsides, s));
+  CU(put(d.hapbytes, f.hapbytes, s));
+  CU(put(d.blocks, f.blocks, s));
+  CU(put(d.reps, f.reps, s));
+  CU(put(d.runs, f.runs, s));
+  CU(put(d.mask, f.hap_mask, s));
+  for (int v = 0; v < kNumColVariants; v++) {
+    CU(put(d.jobs[v], f.jobs[v], s));
+    d.n_jobs[v] = (int32_t)f.jobs[v].size();
+    d.n_max[v] = f.n_max[v];
+    d.l_max[v] = f.l_max[v];
+  }
+  d.n_out = f.n_out;
+  d.n_alignments = f.n_alignments;
+  if (f.hap_mask.empty()) d.mask.release();
+  // the staging vectors die at return: the copies above must have left pageable memory
+  CU(cudaStreamSynchronize(s));
+  return HIPSTR_OK;
+}
+
+hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll_dev, int32_t* pos_dev) {
+  AlignParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.pools = (const DevPool*)d.pools.p;
+  p.bases = (const char*)d.bases.p;
+  p.quals = (const char*)d.quals.p;
+  p.hapsides = (const DevHapSide*)d.hapsides.p;
+  p.hapbytes = (const uint8_t*)d.hapbytes.p;
+  p.blocks = (const DevBlock*)d.blocks.p;
+  p.reps = (const DevRep*)d.reps.p;
+  p.runs = (const uint16_t*)d.runs.p;
+  p.hap_mask = (const uint8_t*)d.mask.p;
+  p.qual_lut = ctx->d_qual_lut;
+  p.trans = ctx->d_trans;
+  p.int_logs = ctx->d_int_logs;
+  p.ll_out = ll_dev;
+  p.pos_out = pos_dev;
+  ctx->last_launches = 0;
+  if (ctx->timing) CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int v = kNumColVariants - 1; v >= 0; v--) {   // longest reads first
+    if (d.n_jobs[v] == 0) continue;
+    p.jobs = (const DevJob*)d.jobs[v].p;
+    p.n_jobs = d.n_jobs[v];
+    p.n_max = d.n_max[v];
+    p.l_max = d.l_max[v];
+    p.debug_out = ctx->d_debug;
+    CU(launch_align(v, p, ctx->stream));
+    ctx->last_launches++;
+  }
+  if (ctx->timing) {
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  }
+  return HIPSTR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hipstr_version(void) { return "hipstr_b200 0.1.0 (sm_100a)"; }
+
+hipstr_status_t hipstr_create(int device, hipstr_ctx_t** out_ctx) {
+  if (!out_ctx) return HIPSTR_ERR_BAD_ARG;
+  *out_ctx = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return HIPSTR_ERR_NO_DEVICE;
+  }
+  hipstr_ctx* ctx = new hipstr_ctx();
+  ctx->device = device;
+  auto bail = [&](const char* what, cudaError_t e) {
+    std::fprintf(stderr, "hipstr_create: %s: %s\n", what, cudaGetErrorString(e));
+    hipstr_destroy(ctx);
+    return HIPSTR_ERR_CUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  ctx->stream = ctx->own_stream;
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("event", e);
+  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("event", e);
+  const HostTables& T = host_tables();
+  if ((e = cudaMalloc(&ctx->d_qual_lut, sizeof(T.qual_lut))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->d_trans, sizeof(T.trans))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->d_int_logs, sizeof(T.int_logs))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemcpy(ctx->d_qual_lut, T.qual_lut, sizeof(T.qual_lut), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", e);
+  if ((e = cudaMemcpy(ctx->d_trans, T.trans, sizeof(T.trans), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", e);
+  if ((e = cudaMemcpy(ctx->d_int_logs, T.int_logs, sizeof(T.int_logs), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", e);
+  *out_ctx = ctx;
+  return HIPSTR_OK;
+}
+
+void hipstr_destroy(hipstr_ctx_t* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  ctx->scratch.release();
+  ctx->d_ll.release();
+  ctx->d_pos.release();
+  for (auto& b : ctx->d_misc) b.release();
+  if (ctx->d_debug) cudaFree(ctx->d_debug);
+  if (ctx->d_qual_lut) cudaFree(ctx->d_qual_lut);
+  if (ctx->d_trans) cudaFree(ctx->d_trans);
+  if (ctx->d_int_logs) cudaFree(ctx->d_int_logs);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* hipstr_last_error(const hipstr_ctx_t* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
+
+hipstr_status_t hipstr_set_stream(hipstr_ctx_t* ctx, void* cuda_stream) {
+  if (!ctx) return HIPSTR_ERR_BAD_ARG;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return HIPSTR_OK;
+}
+
+int64_t hipstr_batch_num_alignments(const hipstr_align_batch_t* batch) { return batch ? count_alignments(batch) : 0; }
+int32_t hipstr_last_launch_count(const hipstr_ctx_t* ctx) { return ctx ? ctx->last_launches : 0; }
+hipstr_status_t hipstr_enable_timing(hipstr_ctx_t* ctx, int enable) {
+  if (!ctx) return HIPSTR_ERR_BAD_ARG;
+  ctx->timing = enable != 0;
+  return HIPSTR_OK;
+}
+float hipstr_last_kernel_ms(const hipstr_ctx_t* ctx) { return ctx ? ctx->last_ms : 0.f; }
+
+hipstr_status_t hipstr_upload_batch(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch, hipstr_dev_batch_t** out) {
+  if (!ctx || !batch || !out) return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  hipstr_dev_batch* d = new hipstr_dev_batch();
+  hipstr_status_t st = stage(ctx, batch, *d);
+  if (st != HIPSTR_OK) { d->release(); delete d; return st; }
+  *out = d;
+  return HIPSTR_OK;
+}
+
+void hipstr_free_batch(hipstr_ctx_t* ctx, hipstr_dev_batch_t* h) {
+  if (!h) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  h->release();
+  delete h;
+}
+
+hipstr_status_t hipstr_align_batch_dev(hipstr_ctx_t* ctx, const hipstr_dev_batch_t* h, double* ll_dev, int32_t* pos_dev) {
+  if (!ctx || !h || !ll_dev) return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  return run_align(ctx, *h, ll_dev, pos_dev);
+}
+
+hipstr_status_t hipstr_align_batch_host(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch, double* ll_out, int32_t* seed_hap_pos) {
+  if (!ctx || !batch || !ll_out) return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  hipstr_status_t st = stage(ctx, batch, ctx->scratch);
+  if (st != HIPSTR_OK) return st;
+  const size_t n = (size_t)ctx->scratch.n_out;
+  if (n == 0) return HIPSTR_OK;
+  CU(ctx->d_ll.reserve(n * sizeof(double)));
+  if (seed_hap_pos) CU(ctx->d_pos.reserve(n * sizeof(int32_t)));
+  const bool masked = batch->realign_pool || batch->realign_hap;
+  if (masked) {   // entries the masks exclude must come back untouched (HapAligner.cpp:326-329,615-619)
+    CU(cudaMemcpyAsync(ctx->d_ll.p, ll_out, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (seed_hap_pos) CU(cudaMemcpyAsync(ctx->d_pos.p, seed_hap_pos, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  st = run_align(ctx, ctx->scratch, (double*)ctx->d_ll.p, seed_hap_pos ? (int32_t*)ctx->d_pos.p : nullptr);
+  if (st != HIPSTR_OK) return st;
+  CU(cudaMemcpyAsync(ll_out, ctx->d_ll.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (seed_hap_pos) CU(cudaMemcpyAsync(seed_hap_pos, ctx->d_pos.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HIPSTR_OK;
+}
+
+/* Test hook (not part of the public header): after the next align call, returns the last-column
+ * match values [2][l_max] of job 0's last haplotype, to localise a parity failure. */
+hipstr_status_t hipstr_debug_lastcols(hipstr_ctx_t* ctx, int enable, double* out, int32_t n) {
+  if (!ctx) return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (enable && !ctx->d_debug) { CU(cudaMalloc(&ctx->d_debug, 8192 * sizeof(double))); CU(cudaMemset(ctx->d_debug, 0, 8192 * sizeof(double))); }
+  if (out && ctx->d_debug) CU(cudaMemcpy(out, ctx->d_debug, (size_t)std::min(n, 8192) * sizeof(double), cudaMemcpyDeviceToHost));
+  if (!enable && ctx->d_debug) { cudaFree(ctx->d_debug); ctx->d_debug = nullptr; }
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_scatter_pool_lls_host(hipstr_ctx_t* ctx, int32_t n_reads, int32_t n_haps, const double* pool_ll,
+                                             const int32_t* pool_seed, const int32_t* pool_index,
+                                             const uint8_t* second_mate, const uint8_t* copy_read,
+                                             const uint8_t* realign_hap, double* read_ll, int32_t* read_seed) {
+  if (!ctx || n_reads < 0 || n_haps <= 0) return HIPSTR_ERR_BAD_ARG;
+  if (n_reads == 0) return HIPSTR_OK;
+  if (!pool_ll || !pool_index || !second_mate || !read_ll || (read_seed && !pool_seed)) return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int32_t n_pools = 0;
+  for (int r = 0; r < n_reads; r++) {
+    if (pool_index[r] < 0) return fail(ctx, HIPSTR_ERR_BAD_ARG, "negative pool index");
+    n_pools = std::max(n_pools, pool_index[r] + 1);
+  }
+  cudaStream_t s = ctx->stream;
+  DevBuf* m = ctx->d_misc;
+  CU(put(m[0], pool_ll, (size_t)n_pools * n_haps, s));
+  CU(put(m[1], pool_index, (size_t)n_reads, s));
+  CU(put(m[2], second_mate, (size_t)n_reads, s));
+  CU(put(m[3], read_ll, (size_t)n_reads * n_haps, s));
+  if (copy_read) CU(put(m[4], copy_read, (size_t)n_reads, s));
+  if (realign_hap) CU(put(m[5], realign_hap, (size_t)n_haps, s));
+  if (read_seed) { CU(put(m[6], pool_seed, (size_t)n_pools, s)); CU(put(m[7], read_seed, (size_t)n_reads, s)); }
+  ScatterParams p;
+  p.n_reads = n_reads; p.n_haps = n_haps;
+  p.pool_ll = (const double*)m[0].p; p.pool_index = (const int32_t*)m[1].p; p.second_mate = (const uint8_t*)m[2].p;
+  p.read_ll = (double*)m[3].p;
+  p.copy_read = copy_read ? (const uint8_t*)m[4].p : nullptr;
+  p.realign_hap = realign_hap ? (const uint8_t*)m[5].p : nullptr;
+  p.pool_seed = read_seed ? (const int32_t*)m[6].p : nullptr;
+  p.read_seed = read_seed ? (int32_t*)m[7].p : nullptr;
+  CU(launch_scatter(p, s));
+  ctx->last_launches = 1;
+  CU(cudaMemcpyAsync(read_ll, m[3].p, (size_t)n_reads * n_haps * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (read_seed) CU(cudaMemcpyAsync(read_seed, m[7].p, (size_t)n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_posteriors_host(hipstr_ctx_t* ctx, int32_t n_loci, const int32_t* locus_read_off,
+                                       const int32_t* locus_sample_off, const int32_t* n_haps, const uint8_t* haploid,
+                                       const double* read_ll, const double* log_p1, const double* log_p2,
+                                       const int32_t* sample_label, const int32_t* read_weight, double* post_out,
+                                       double* sample_ll_out, int32_t* best_out, double* total_ll_out) {
+  if (!ctx || n_loci < 0) return HIPSTR_ERR_BAD_ARG;
+  if (n_loci == 0) return HIPSTR_OK;
+  if (!locus_read_off || !locus_sample_off || !n_haps || !haploid || !read_ll || !log_p1 || !log_p2 || !sample_label ||
+      !read_weight || !post_out || !sample_ll_out)
+    return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  const int32_t R = locus_read_off[n_loci], S = locus_sample_off[n_loci];
+  std::vector<PostSample> samples((size_t)S);
+  int64_t ll_off = 0, post_off = 0;
+  for (int l = 0; l < n_loci; l++) {
+    const int H = n_haps[l];
+    if (H <= 0 || H + 1 >= 10000) return fail(ctx, HIPSTR_ERR_BAD_ARG, "bad haplotype count");
+    const int s0 = locus_sample_off[l], s1 = locus_sample_off[l + 1];
+    int r = locus_read_off[l];
+    const int r_end = locus_read_off[l + 1];
+    for (int s = s0; s < s1; s++) {
+      PostSample& ps = samples[s];
+      ps.read0 = r;
+      while (r < r_end && sample_label[r] == s - s0) r++;   // reads are sample-major (genotyper.h:104-112)
+      ps.read1 = r;
+      ps.n_haps = H;
+      ps.haploid = haploid[l];
+      ps.ll_off = ll_off;
+      ps.locus_read0 = locus_read_off[l];
+      ps.locus = l;
+      ps.post_off = post_off + (int64_t)(s - s0) * H * H;
+    }
+    if (r != r_end) return fail(ctx, HIPSTR_ERR_BAD_ARG, "reads are not sample-major or a label is out of range");
+    ll_off += (int64_t)(r_end - locus_read_off[l]) * H;
+    post_off += (int64_t)(s1 - s0) * H * H;
+  }
+  cudaStream_t s = ctx->stream;
+  DevBuf* m = ctx->d_misc;
+  CU(put(m[0], samples, s));
+  CU(put(m[1], locus_sample_off, (size_t)n_loci + 1, s));
+  CU(put(m[2], read_ll, (size_t)ll_off, s));
+  CU(put(m[3], log_p1, (size_t)R, s));
+  CU(put(m[4], log_p2, (size_t)R, s));
+  CU(put(m[5], read_weight, (size_t)R, s));
+  CU(m[6].reserve(std::max<size_t>((size_t)post_off * sizeof(double), 16)));
+  CU(m[7].reserve(std::max<size_t>((size_t)S * sizeof(double), 16)));
+  CU(m[8].reserve(std::max<size_t>((size_t)S * 2 * sizeof(int32_t), 16)));
+  CU(m[9].reserve(std::max<size_t>((size_t)n_loci * sizeof(double), 16)));
+  PostParams p;
+  p.n_samples = S; p.n_loci = n_loci;
+  p.samples = (const PostSample*)m[0].p; p.locus_sample_off = (const int32_t*)m[1].p;
+  p.read_ll = (const double*)m[2].p; p.log_p1 = (const double*)m[3].p; p.log_p2 = (const double*)m[4].p;
+  p.read_weight = (const int32_t*)m[5].p;
+  p.int_logs = ctx->d_int_logs; p.log_one_half = host_tables().log_one_half;
+  p.post_out = (double*)m[6].p; p.sample_ll_out = (double*)m[7].p;
+  p.best_out = best_out ? (int32_t*)m[8].p : nullptr;
+  p.total_ll_out = total_ll_out ? (double*)m[9].p : nullptr;
+  CU(launch_posteriors(p, s));
+  ctx->last_launches = total_ll_out ? 2 : 1;
+  CU(cudaMemcpyAsync(post_out, m[6].p, (size_t)post_off * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(sample_ll_out, m[7].p, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (best_out) CU(cudaMemcpyAsync(best_out, m[8].p, (size_t)S * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (total_ll_out) CU(cudaMemcpyAsync(total_ll_out, m[9].p, (size_t)n_loci * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return HIPSTR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+/*
+ * flatten.h -- host side of the kernel boundary: validates a hipstr_align_batch_t and
+ * lowers it to the packed device layout of layout.h.
+ */
+#ifndef HIPSTR_B200_FLATTEN_H_
+#define HIPSTR_B200_FLATTEN_H_
+
+#include <string>
+#include <vector>
+
+#include "../../include/hipstr_b200.h"
+#include "layout.h"
+
+namespace hipstr {
+
+/* Constant tables, computed once with glibc exactly the way the reference builds them
+ * (mathops.cpp:13-21, base_quality.h:29-38, SeqAlignment/AlignmentModel.cpp:9-32) and uploaded;
+ * CUDA's libm is not bit-identical to glibc's. */
+struct HostTables {
+  double int_logs[10000];
+  double qual_lut[256][2];   /* [quality byte] -> {log P(correct), log P(error)/3} */
+  double trans[3][16];       /* match->match, match->ins, match->del by homopolymer class */
+  double log_one_half;
+  HostTables();
+};
+const HostTables& host_tables();
+
+/* Columns-per-lane variants the alignment kernel is instantiated for. */
+static const int kNumColVariants = 8;
+static const int kColVariants[kNumColVariants] = {2, 3, 4, 5, 6, 8, 12, 16};
+
+struct FlatBatch {
+  std::vector<DevPool> pools;
+  std::vector<char> bases, quals;            /* every read padded to a multiple of 16 bytes */
+  std::vector<DevHapSide> hapsides;          /* [global hap][2] */
+  std::vector<uint8_t> hapbytes;
+  std::vector<DevBlock> blocks;
+  std::vector<DevRep> reps;
+  std::vector<uint16_t> runs;
+  std::vector<uint8_t> hap_mask;             /* empty = all haplotypes */
+  std::vector<DevJob> jobs[kNumColVariants];
+  int32_t n_max[kNumColVariants];            /* per variant: max read length (padded) */
+  int32_t l_max[kNumColVariants];            /* per variant: max haplotype length (padded) */
+  int64_t n_out = 0;
+  int64_t n_alignments = 0;
+};
+
+/* Returns HIPSTR_OK or an error with a message. */
+hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std::string& err);
+int64_t count_alignments(const hipstr_align_batch_t* b);
+
+/* Per-block option index of haplotype `hap`: closed form of the reflected mixed-radix Gray
+ * code walked by Haplotype::next() (SeqAlignment/Haplotype.cpp:157-196), block 0 fastest. */
+void haplotype_options(int n_blocks, const int32_t* n_opts, int64_t hap, int32_t* out);
+
+}  // namespace hipstr
+#endif

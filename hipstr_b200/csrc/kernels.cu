@@ -1,0 +1,636 @@
+/*
+ * kernels.cu -- hand-written sm_100a kernels of the HipSTR hot path.
+ *
+ * K1  k_align<C>      one warp per (pooled read, run of haplotypes): the seeded two-sided
+ *                     read-vs-haplotype HMM of HapAligner::process_read
+ *                     (SeqAlignment/HapAligner.cpp:573-709 -> align_seq_to_hap :26-161,
+ *                     compute_aln_logprob :163-231, StutterAlignerClass.cpp:12-162).
+ * K2  k_scatter       pool -> read scatter + mate merge (seq_stutter_genotyper.cpp:530-564).
+ * K3  k_posteriors    genotype posteriors (genotyper.cpp:20-97).
+ *
+ * K1 in one paragraph.  The read is split at its seed base into a left part aligned to the
+ * forward haplotype and a right part aligned (reversed) to the reversed haplotype.  Both DPs run
+ * AT THE SAME TIME in one warp: the lanes are partitioned between the two sides in proportion to
+ * their column counts, every lane owns C adjacent read columns of its side and keeps the previous
+ * DP row of those columns (match + deletion state; the insertion state only flows along a row) in
+ * registers.  Flank rows advance as an anti-diagonal wavefront: at step t lane k computes
+ * haplotype row t-k for its columns and hands the right-most cell to lane k+1 with three warp
+ * shuffles.  A repeat ("stutter") block is a single super-row: the row above it is parked in
+ * shared memory, every lane evaluates the 13 PCR-artifact sizes for one read column at a time
+ * (the per-artifact sums over artifact positions of StutterAlignerClass), and the row is pulled
+ * back into registers.  Only the last column of every row is kept (shared memory); the final
+ * log-likelihood combines them over all seed placements.  All state is FP64 and every operation
+ * is done in the reference's order, so flank cells are bit-identical to the CPU; the approximate
+ * log-sum-exp uses the float replicas in fastapprox.cuh.  The double sums inside a log-sum-exp
+ * add float values spanning < 2^11 in magnitude, which is exact in binary64 in any order, so
+ * warp-parallel reductions of those sums do not change a bit either.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hipstr_b200.h"
+#include "fastapprox.cuh"
+#include "kernels.h"
+#include "layout.h"
+
+namespace hipstr {
+
+#define FULL 0xffffffffu
+#define IMPOSSIBLE (-1000000000.0)            /* HapAligner.cpp:20 */
+#define LOG_INS_TO_INS (-1.0)                 /* AlignmentModel.h:7 */
+#define LOG_INS_TO_MATCH (-0.4586751453870818910216436) /* AlignmentModel.h:8 */
+#define LOG_DEL_TO_DEL (-1.0)                 /* AlignmentModel.h:9 */
+#define LOG_DEL_TO_MATCH (-0.4586751453870818910216436) /* AlignmentModel.h:10 */
+
+__device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(FULL, v, 1); }
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------------------------------
+// Repeat-block evaluator: one (read side, repeat allele).  Everything is anchored at the right
+// ends like the reference: column q of the side pairs with allele base B-1 when it is the last
+// base of the block.
+// ------------------------------------------------------------------------------------------
+struct RepCtx {
+  const uint8_t* s;        // oriented allele sequence (global, read-only)
+  const uint16_t* runs;    // upstream_match_lengths_ tables, [max(n_del,1)][B]
+  const double* int_logs;  // global
+  const double2* lcw;      // shared: {log_correct, log_error} by READ index
+  const uint8_t* rbase;    // shared: read bases by READ index
+  const double* match;     // shared: match_probs_ by side column
+  int B, p, n_del;
+  int n_side;              // columns of this side
+  int rev, n_read;         // read index of side column q = rev ? n_read-1-q : q
+
+  __device__ __forceinline__ double emit(int q, int b) const {
+    const int r = rev ? n_read - 1 - q : q;
+    const double2 v = lcw[r];
+    return rbase[r] == __ldg(s + b) ? v.x : v.y;
+  }
+  __device__ __forceinline__ double lc(int q) const { return lcw[rev ? n_read - 1 - q : q].x; }
+};
+
+// match_probs_[q] of StutterAlignerClass::load_read (StutterAlignerClass.cpp:12-53).
+__device__ double rep_match_prob(const RepCtx& c, int q) {
+  const int terms = min(q + 1, c.B);
+  double acc = 0.0;
+  for (int t = 0; t < terms; t++) acc += c.emit(q - t, c.B - 1 - t);
+  return acc;
+}
+
+// Terms of align_pcr_insertion_reverse (StutterAlignerClass.cpp:59-104) after the first one.
+// pass 0 returns the maximum term, pass 1 the sum of coarse_exp(term - mx).
+__device__ __noinline__ double rep_insertion(const RepCtx& c, int base_len, int j, int D, double lp0) {
+  const uint16_t* runs = c.runs;   // lag = period
+  const int B = c.B, p = c.p;
+  const int stop = -min(max(0, base_len - D), B);
+  double mx = lp0, total = 0.0;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    double lp = lp0;
+    if (pass) total = lse_term(lp, mx);
+    int i = 0;
+    for (; i > stop; i--) {
+      const int b = B - 1 + i;
+      double term = lp;
+      if (-i + p < B) {
+        const int run = __ldg(runs + b);
+        if (run == 0) {
+          for (int idx = i - p; idx >= i - D; idx -= p) {
+            lp -= c.emit(j + idx, b);
+            lp += c.emit(j + idx, b - p);
+          }
+          term = lp;
+        } else {
+          term = __ldg(c.int_logs + run) + lp;
+          i -= run - 1;
+        }
+      }
+      if (pass) total += lse_term(term, mx); else mx = dmax(mx, term);
+    }
+    if (i > -B) {
+      const double term = __ldg(c.int_logs + (B + i)) + lp;
+      if (pass) total += lse_term(term, mx); else mx = dmax(mx, term);
+    }
+  }
+  return lse_finish(mx, total);
+}
+
+// align_pcr_deletion_reverse (StutterAlignerClass.cpp:106-150), D < 0, k = -D/period.
+__device__ __noinline__ double rep_deletion(const RepCtx& c, int base_len, int j, int D, int k) {
+  const int B = c.B;
+  const uint16_t* runs = c.runs + (size_t)(k - 1) * B;
+  double lp0 = -__ldg(c.int_logs + (B + D + 1));
+  const int q = j - D;   // read column |D| bases to the right of j
+  if (q <= c.n_side - 1) {
+    // match_probs_[q] - del_probs_[q][k-1]; the deletion prefix table entry is the first
+    // k*period terms of the same right-anchored sum, recomputed here instead of stored
+    double pre = 0.0;
+    const int terms = -D;
+    for (int t = 0; t < terms; t++) pre += c.emit(q - t, B - 1 - t);
+    lp0 += c.match[q] - pre;
+  } else {
+    for (int t = 0; t < base_len; t++) lp0 += c.emit(j - t, B - 1 - t + D);
+  }
+  double mx = lp0, total = 0.0;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    double lp = lp0;
+    if (pass) total = lse_term(lp, mx);
+    int i = 0;
+    for (; i > -base_len; i--) {
+      const int b = B - 1 + i;
+      const int run = __ldg(runs + b);
+      double term;
+      if (run == 0) {
+        lp -= c.emit(j + i, b + D);
+        lp += c.emit(j + i, b);
+        term = lp;
+      } else {
+        term = __ldg(c.int_logs + run) + lp;
+        i -= run - 1;
+      }
+      if (pass) total += lse_term(term, mx); else mx = dmax(mx, term);
+    }
+    if (-i < B + D) {
+      const double term = __ldg(c.int_logs + (B + D + i)) + lp;
+      if (pass) total += lse_term(term, mx); else mx = dmax(mx, term);
+    }
+  }
+  return lse_finish(mx, total);
+}
+
+// One column of the repeat block's last row: HapAligner.cpp:76-100.
+__device__ double rep_column(const RepCtx& c, const DevRep* rep, const double* prev_row, int j) {
+  const int B = c.B, p = c.p;
+  double probs[HIPSTR_NUM_ARTIFACTS];
+  double ins_acc = 0.0;    // ins_probs_ running sum (StutterAlignerClass.cpp:38-51)
+  int ins_t = 0;
+#pragma unroll
+  for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) {
+    const int units = a - HIPSTR_MAX_ARTIFACT_UNITS;
+    const int D = units * p;
+    const int base_len = min(B + D, j + 1);
+    if (base_len < 0) { probs[a] = IMPOSSIBLE; continue; }
+    double pr;
+    if (units == 0)
+      pr = c.match[j];
+    else if (units < 0)
+      pr = rep_deletion(c, base_len, j, D, -units);
+    else {
+      // extend the periodic-copy sum to `units` copies (at most j+1 read bases exist)
+      const int upto = min(D, j + 1);
+      for (; ins_t < upto; ins_t++) {
+        const int m = ins_t % p;
+        ins_acc += (m < B) ? c.emit(j - ins_t, B - 1 - m) : c.lc(j - ins_t);
+      }
+      double lp0 = -__ldg(c.int_logs + (B + 1)) + ins_acc;
+      lp0 += (base_len > D) ? c.match[j - D] : 0.0;
+      pr = rep_insertion(c, base_len, j, D, lp0);
+    }
+    const double pre = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
+    probs[a] = __ldg(rep->art + a) + pr + pre;
+  }
+  double mx = probs[0];
+#pragma unroll
+  for (int a = 1; a < HIPSTR_NUM_ARTIFACTS; a++) mx = dmax(mx, probs[a]);
+  double total = 0.0;
+#pragma unroll
+  for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) total += lse_term(probs[a], mx);
+  return lse_finish(mx, total);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t align_smem_doubles(int n_max, int l_max) {
+  // lcw[2N] run[N] rowbuf[N] rowout[N] match[N] last[2L] bases[N/8]
+  return (size_t)6 * n_max + 2 * (size_t)l_max + n_max / 8;
+}
+size_t align_smem_bytes(int n_max, int l_max) { return align_smem_doubles(n_max, l_max) * 8 * HIPSTR_WARPS_PER_CTA; }
+
+template <int C>
+__global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA) k_align(const AlignParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int job_id = blockIdx.x * HIPSTR_WARPS_PER_CTA + wib;
+  if (job_id >= P.n_jobs) return;   // whole warp exits together; no block-level barriers below
+  const DevJob job = P.jobs[job_id];
+  const DevPool pool = P.pools[job.pool];
+  double* out = P.ll_out + pool.out_off;
+
+  if (pool.seed < 0) {   // HapAligner.cpp:333-337
+    for (int h = lane; h < pool.n_haps; h += 32) {
+      out[h] = 0.0;
+      if (P.pos_out) P.pos_out[pool.out_off + h] = -1;
+    }
+    return;
+  }
+
+  const int N = P.n_max, L = P.l_max;
+  double* wbase = reinterpret_cast<double*>(smem_raw) + (size_t)wib * align_smem_doubles(N, L);
+  double2* s_lcw = reinterpret_cast<double2*>(wbase);
+  double* s_run = wbase + 2 * N;
+  double* s_rowbuf = s_run + N;
+  double* s_rowout = s_rowbuf + N;
+  double* s_match = s_rowout + N;
+  double* s_last = s_match + N;
+  uint8_t* s_base = reinterpret_cast<uint8_t*>(s_last + 2 * L);
+
+  const int n = pool.len, seed = pool.seed;
+  const int nL = seed, nR = n - seed - 1;
+  // stage the read: bases + per-base log-likelihoods (HapAligner.cpp:579-585)
+  for (int i = lane; i < n; i += 32) {
+    const uint8_t q = (uint8_t)P.quals[pool.seq_off + i];
+    s_base[i] = (uint8_t)P.bases[pool.seq_off + i];
+    s_lcw[i] = make_double2(__ldg(P.qual_lut + 2 * q), __ldg(P.qual_lut + 2 * q + 1));
+  }
+  __syncwarp();
+  // running sums of log_correct from each read end towards the seed (row 0 of either matrix,
+  // HapAligner.cpp:33-42); strictly sequential adds, one lane per side
+  double edge = 0.0;
+  if (lane < 2) {
+    const int cnt = lane ? nR : nL;
+    double* dst = s_run + (lane ? nL : 0);
+    double acc = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < cnt; j++) {
+      dst[j] = acc;
+      acc += s_lcw[lane ? n - 1 - j : j].x;
+    }
+    edge = acc;
+  }
+  const double edgeL = __shfl_sync(FULL, edge, 0), edgeR = __shfl_sync(FULL, edge, 1);
+  __syncwarp();
+
+  // lane -> (side, first column)
+  const int nlL = (nL + C - 1) / C, nlR = (nR + C - 1) / C;
+  const int side = lane < nlL ? 0 : 1;
+  const int k = side ? lane - nlL : lane;
+  const bool lane_on = side == 0 || k < nlR;
+  const int ncol = side ? nR : nL;
+  const int gbase = side ? nL : 0;
+  const int j0 = k * C;
+
+  double lc[C], lw[C], Mp[C], Dp[C];
+  uint8_t bs[C];
+#pragma unroll
+  for (int cc = 0; cc < C; cc++) {
+    const int j = j0 + cc;
+    const bool ok = lane_on && j < ncol;
+    const int r = ok ? (side ? n - 1 - j : j) : 0;
+    const double2 v = s_lcw[r];
+    lc[cc] = v.x; lw[cc] = v.y; bs[cc] = s_base[r];
+  }
+  const int last_cc = (lane_on && ncol - 1 >= j0 && ncol - 1 < j0 + C) ? ncol - 1 - j0 : -1;
+  const uint8_t seed_base = s_base[seed];
+  const double2 seed_lcw = s_lcw[seed];
+
+  for (int h = job.h0; h < job.h1; h++) {
+    const int hap_index = (pool.hap_rec0 >> 1) + h;
+    if (P.hap_mask && !P.hap_mask[hap_index]) continue;
+    const DevHapSide hsF = P.hapsides[pool.hap_rec0 + 2 * h];
+    const DevHapSide hsR = P.hapsides[pool.hap_rec0 + 2 * h + 1];
+    const DevHapSide& hs = side ? hsR : hsF;
+    const uint8_t* seq = P.hapbytes + hs.seq_off;
+    const uint8_t* rows = P.hapbytes + hs.row_off;
+    const int nb = hsF.n_blocks;
+    const int hlen = hsF.len;
+
+    // row 0 (HapAligner.cpp:33-42)
+    {
+      const uint8_t fc = __ldg(seq);
+#pragma unroll
+      for (int cc = 0; cc < C; cc++) {
+        const int j = j0 + cc;
+        const double run = (lane_on && j < ncol) ? s_run[gbase + j] : 0.0;
+        Mp[cc] = (bs[cc] == fc ? lc[cc] : lw[cc]) + run;
+        Dp[cc] = IMPOSSIBLE;
+        if (cc == last_cc) s_last[side * L] = Mp[cc];
+      }
+    }
+
+    for (int b = 0; b < nb; b++) {
+      const DevBlock blkF = P.blocks[hsF.blk_off + b];
+      const DevBlock blkR = P.blocks[hsR.blk_off + b];
+      const DevBlock& blk = side ? blkR : blkF;
+
+      // ---------------- flank block: anti-diagonal wavefront (HapAligner.cpp:110-157) ----------
+      {
+        const int r0 = blk.row_start + (b == 0 ? 1 : 0);
+        const int nrows = blk.row_start + blk.len - r0;
+        const bool flank_on = lane_on && blk.rep < 0 && nrows > 0;
+        const int steps = __reduce_max_sync(FULL, flank_on ? nrows + k : 0);
+        if (steps > 0) {
+          double Mlp = shfl_up_d(Mp[C - 1]), Dlp = shfl_up_d(Dp[C - 1]);
+          double pubM = 0.0, pubI = 0.0, pubD = 0.0;
+          for (int t = 0; t < steps; t++) {
+            const double rI = shfl_up_d(pubI), rM = shfl_up_d(pubM), rD = shfl_up_d(pubD);
+            const int r = t - k;
+            if (flank_on && r >= 0 && r < nrows) {
+              const int row = r0 + r;
+              const uint8_t hc = __ldg(seq + row);
+              const uint8_t info = __ldg(rows + row);
+              const int hp = info & 15;
+              const bool after = (info & HIPSTR_ROW_AFTER_REPEAT) != 0;
+              const double m2m = __ldg(P.trans + hp), m2i = __ldg(P.trans + 16 + hp), m2d = __ldg(P.trans + 32 + hp);
+              double Ileft = rI, Mdiag = Mlp, Ddiag = Dlp;
+#pragma unroll
+              for (int cc = 0; cc < C; cc++) {
+                const double e = bs[cc] == hc ? lc[cc] : lw[cc];
+                const double Mup = Mp[cc], Dup = Dp[cc];
+                const bool col0 = (cc == 0) && (k == 0);
+                double Mn = e + dmax(Ileft + m2i, dmax(Mdiag + m2m, Ddiag + m2d));
+                double In = lc[cc] + dmax(Mdiag + LOG_INS_TO_MATCH, Ileft + LOG_INS_TO_INS);
+                double Dn = dmax(Mup + LOG_DEL_TO_MATCH, Dup + LOG_DEL_TO_DEL);
+                if (col0) { Mn = e; In = lc[cc]; }
+                if (after) {   // first row after a repeat block (HapAligner.cpp:129-139)
+                  Mn = col0 ? e : e + Mdiag;
+                  In = IMPOSSIBLE;
+                  Dn = IMPOSSIBLE;
+                }
+                Mdiag = Mup; Ddiag = Dup; Ileft = In;
+                Mp[cc] = Mn; Dp[cc] = Dn;
+                if (cc == last_cc) s_last[side * L + row] = Mn;
+              }
+              Mlp = rM; Dlp = rD;
+              pubM = Mp[C - 1]; pubI = Ileft; pubD = Dp[C - 1];
+            }
+          }
+        }
+      }
+
+      // ---------------- repeat block: one super-row (HapAligner.cpp:62-109) --------------------
+      if (blkF.rep >= 0 || blkR.rep >= 0) {
+        if (lane_on && blk.rep >= 0) {
+#pragma unroll
+          for (int cc = 0; cc < C; cc++)
+            if (j0 + cc < ncol) s_rowbuf[gbase + j0 + cc] = Mp[cc];
+        }
+        __syncwarp();
+        // pass 1: match_probs_ of every column of the sides that are in a repeat block
+        for (int g = lane; g < n - 1; g += 32) {
+          const int gs = g >= nL;
+          const DevBlock& gb = gs ? blkR : blkF;
+          if (gb.rep < 0) continue;
+          const DevRep* rep = P.reps + gb.rep;
+          RepCtx c;
+          c.s = P.hapbytes + rep->seq_off; c.runs = P.runs + rep->runs_off; c.int_logs = P.int_logs;
+          c.lcw = s_lcw; c.rbase = s_base; c.match = s_match + (gs ? nL : 0);
+          c.B = rep->len; c.p = rep->period; c.n_del = rep->n_del;
+          c.n_side = gs ? nR : nL; c.rev = gs; c.n_read = n;
+          s_match[g] = rep_match_prob(c, g - (gs ? nL : 0));
+        }
+        __syncwarp();
+        // pass 2: the 13 artifact sizes of every column
+        for (int g = lane; g < n - 1; g += 32) {
+          const int gs = g >= nL;
+          const DevBlock& gb = gs ? blkR : blkF;
+          if (gb.rep < 0) continue;
+          const DevRep* rep = P.reps + gb.rep;
+          RepCtx c;
+          c.s = P.hapbytes + rep->seq_off; c.runs = P.runs + rep->runs_off; c.int_logs = P.int_logs;
+          c.lcw = s_lcw; c.rbase = s_base; c.match = s_match + (gs ? nL : 0);
+          c.B = rep->len; c.p = rep->period; c.n_del = rep->n_del;
+          c.n_side = gs ? nR : nL; c.rev = gs; c.n_read = n;
+          s_rowout[g] = rep_column(c, rep, s_rowbuf + (gs ? nL : 0), g - (gs ? nL : 0));
+        }
+        __syncwarp();
+        if (lane_on && blk.rep >= 0) {
+#pragma unroll
+          for (int cc = 0; cc < C; cc++) {
+            if (j0 + cc < ncol) Mp[cc] = s_rowout[gbase + j0 + cc];
+            Dp[cc] = IMPOSSIBLE;
+            if (cc == last_cc) s_last[side * L + blk.row_start + blk.len - 1] = Mp[cc];
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+
+    // ---------------- combine over seed placements (HapAligner.cpp:163-231) -------------------
+    {
+      const uint8_t* fseq = P.hapbytes + hsF.seq_off;
+      const uint8_t* frow = P.hapbytes + hsF.row_off;
+      const double prior = -__ldg(P.int_logs + hsF.n_seed_pos);
+      const double* lastL = s_last;
+      const double* lastR = s_last + L;
+      double vmax = -1.0e300;
+      int vrank = 0x7fffffff;
+      // rank 0: seed on haplotype base 0; rank 1: seed on the last base; rank i+1: interior base i
+      for (int it = lane; it < hlen; it += 32) {
+        double v;
+        int rank;
+        if (it == 0) {
+          v = prior + (seed_base == __ldg(fseq) ? seed_lcw.x : seed_lcw.y) + edgeL + lastR[hlen - 2];
+          rank = 0;
+        } else if (it == hlen - 1) {
+          v = prior + (seed_base == __ldg(fseq + hlen - 1) ? seed_lcw.x : seed_lcw.y) + edgeR + lastL[hlen - 2];
+          rank = 1;
+        } else {
+          if (__ldg(frow + it) & HIPSTR_ROW_REPEAT) continue;
+          v = prior + (seed_base == __ldg(fseq + it) ? seed_lcw.x : seed_lcw.y) + lastL[it - 1] + lastR[hlen - it - 2];
+          rank = it + 1;
+        }
+        if (v > vmax || (v == vmax && rank < vrank)) { vmax = v; vrank = rank; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(FULL, vmax, o);
+        const int orank = __shfl_xor_sync(FULL, vrank, o);
+        if (ov > vmax || (ov == vmax && orank < vrank)) { vmax = ov; vrank = orank; }
+      }
+      double total = 0.0;
+      for (int it = lane; it < hlen; it += 32) {
+        double v;
+        if (it == 0)
+          v = prior + (seed_base == __ldg(fseq) ? seed_lcw.x : seed_lcw.y) + edgeL + lastR[hlen - 2];
+        else if (it == hlen - 1)
+          v = prior + (seed_base == __ldg(fseq + hlen - 1) ? seed_lcw.x : seed_lcw.y) + edgeR + lastL[hlen - 2];
+        else {
+          if (__ldg(frow + it) & HIPSTR_ROW_REPEAT) continue;
+          v = prior + (seed_base == __ldg(fseq + it) ? seed_lcw.x : seed_lcw.y) + lastL[it - 1] + lastR[hlen - it - 2];
+        }
+        total += lse_term(v, vmax);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+      if (lane == 0) {
+        out[h] = lse_finish(vmax, total);
+        if (P.pos_out) P.pos_out[pool.out_off + h] = vrank == 0 ? 0 : (vrank == 1 ? hlen - 1 : vrank - 1);
+      }
+      if (P.debug_out && job_id == 0 && h == job.h1 - 1)
+        for (int i = lane; i < 2 * L; i += 32) P.debug_out[i] = (i % L) < hlen ? s_last[i] : 0.0;
+    }
+    __syncwarp();
+  }
+}
+
+template <int C>
+static cudaError_t launch_align_c(const AlignParams& p, cudaStream_t stream) {
+  const size_t smem = align_smem_bytes(p.n_max, p.l_max);
+  cudaError_t e = cudaFuncSetAttribute(k_align<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = (p.n_jobs + HIPSTR_WARPS_PER_CTA - 1) / HIPSTR_WARPS_PER_CTA;
+  k_align<C><<<grid, 32 * HIPSTR_WARPS_PER_CTA, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_align(int variant, const AlignParams& p, cudaStream_t stream) {
+  if (p.n_jobs <= 0) return cudaSuccess;
+  switch (variant) {
+    case 0: return launch_align_c<2>(p, stream);
+    case 1: return launch_align_c<3>(p, stream);
+    case 2: return launch_align_c<4>(p, stream);
+    case 3: return launch_align_c<5>(p, stream);
+    case 4: return launch_align_c<6>(p, stream);
+    case 5: return launch_align_c<8>(p, stream);
+    case 6: return launch_align_c<12>(p, stream);
+    case 7: return launch_align_c<16>(p, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: pool -> read scatter + mate merge.  One thread per (chain head read, haplotype): a chain is
+// a read followed by its second mates, processed in order exactly like the reference's two loops.
+// ------------------------------------------------------------------------------------------
+__global__ void k_scatter(const ScatterParams P) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)P.n_reads * P.n_haps) return;
+  const int r = (int)(idx / P.n_haps), h = (int)(idx % P.n_haps);
+  if (P.second_mate[r] && r > 0) return;   // handled by its chain head
+  const bool hap_on = !P.realign_hap || P.realign_hap[h];
+  for (int m = r; m < P.n_reads && (m == r || P.second_mate[m]); m++) {
+    const bool copy = !P.copy_read || P.copy_read[m];
+    if (!copy) continue;
+    const int pi = P.pool_index[m];
+    if (h == 0 && P.read_seed) P.read_seed[m] = P.pool_seed[pi];
+    if (!hap_on) continue;
+    double v = P.pool_ll[(size_t)pi * P.n_haps + h];
+    if (m > r) {
+      v += P.read_ll[(size_t)(m - 1) * P.n_haps + h];
+      P.read_ll[(size_t)(m - 1) * P.n_haps + h] = v;
+    }
+    P.read_ll[(size_t)m * P.n_haps + h] = v;
+  }
+}
+
+cudaError_t launch_scatter(const ScatterParams& p, cudaStream_t stream) {
+  const int64_t total = (int64_t)p.n_reads * p.n_haps;
+  if (total <= 0) return cudaSuccess;
+  k_scatter<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: genotype posteriors.  One CTA per (locus, sample); thread t owns diplotypes t, t+T, ...
+// and folds the sample's reads into them in read order (genotyper.cpp:59-64), then the CTA
+// normalises with an exact log-sum-exp (genotyper.cpp:66-71) and picks the first maximum
+// (genotyper.cpp:82-97).
+// ------------------------------------------------------------------------------------------
+#define POST_THREADS 128
+
+__device__ __forceinline__ double block_reduce_max(double v, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = dmax(v, __shfl_xor_sync(FULL, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = scratch[0];
+  for (int w = 1; w < POST_THREADS / 32; w++) r = dmax(r, scratch[w]);
+  return r;
+}
+__device__ __forceinline__ double block_reduce_sum(double v, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = scratch[0];
+  for (int w = 1; w < POST_THREADS / 32; w++) r += scratch[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(POST_THREADS) k_posteriors(const PostParams P) {
+  __shared__ double scratch[POST_THREADS / 32];
+  __shared__ int best_idx_s[POST_THREADS / 32];
+  const PostSample S = P.samples[blockIdx.x];
+  const int H = S.n_haps;
+  const int64_t HH = (int64_t)H * H;
+  double* post = P.post_out + S.post_off;
+  double homoz, hetz;
+  if (S.haploid) { homoz = -P.int_logs[H]; hetz = -1.7976931348623157e308 / 2; }
+  else { homoz = P.int_logs[2] - P.int_logs[H] - P.int_logs[H + 1]; hetz = -P.int_logs[H] - P.int_logs[H + 1]; }
+  const double* ll0 = P.read_ll + S.ll_off;
+  double mx = -1.7976931348623157e308;
+  for (int64_t d = threadIdx.x; d < HH; d += POST_THREADS) {
+    const int a = (int)(d / H), b = (int)(d % H);
+    double acc = a == b ? homoz : hetz;
+    for (int r = S.read0; r < S.read1; r++) {
+      const double* row = ll0 + (size_t)(r - S.locus_read0) * H;
+      const double x = P.log_one_half + P.log_p1[r] + row[a];
+      const double y = P.log_one_half + P.log_p2[r] + row[b];
+      acc += P.read_weight[r] * lse2(x, y);
+    }
+    post[d] = acc;
+    mx = dmax(mx, acc);
+  }
+  mx = block_reduce_max(mx, scratch);
+  double sum = 0.0;
+  for (int64_t d = threadIdx.x; d < HH; d += POST_THREADS) sum += exp(post[d] - mx);
+  sum = block_reduce_sum(sum, scratch);
+  const double sll = mx + log(sum);
+  double best = -1.7976931348623157e308;
+  int64_t best_d = HH;
+  for (int64_t d = threadIdx.x; d < HH; d += POST_THREADS) {
+    const double v = post[d] - sll;
+    post[d] = v;
+    if (v > best) { best = v; best_d = d; }   // ascending d per thread: first maximum kept
+  }
+  if (threadIdx.x == 0) P.sample_ll_out[blockIdx.x] = sll;
+  if (P.best_out) {
+    // first maximum over the CTA: larger value wins, ties go to the smaller index
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(FULL, best, o);
+      const long long od = __shfl_xor_sync(FULL, (long long)best_d, o);
+      if (ov > best || (ov == best && od < best_d)) { best = ov; best_d = od; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { scratch[threadIdx.x >> 5] = best; best_idx_s[threadIdx.x >> 5] = (int)best_d; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double bv = scratch[0];
+      int bd = best_idx_s[0];
+      for (int w = 1; w < POST_THREADS / 32; w++)
+        if (scratch[w] > bv || (scratch[w] == bv && best_idx_s[w] < bd)) { bv = scratch[w]; bd = best_idx_s[w]; }
+      P.best_out[2 * blockIdx.x] = bd / H;
+      P.best_out[2 * blockIdx.x + 1] = bd % H;
+    }
+  }
+}
+
+// per-locus total LL = sum of the sample normalisers in sample order (genotyper.cpp:72-78)
+__global__ void k_total_ll(const PostParams P) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= P.n_loci) return;
+  double t = 0.0;
+  for (int s = P.locus_sample_off[l]; s < P.locus_sample_off[l + 1]; s++) t += P.sample_ll_out[s];
+  P.total_ll_out[l] = t;
+}
+
+cudaError_t launch_posteriors(const PostParams& p, cudaStream_t stream) {
+  if (p.n_samples <= 0) return cudaSuccess;
+  k_posteriors<<<p.n_samples, POST_THREADS, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (p.total_ll_out) {
+    k_total_ll<<<(p.n_loci + 127) / 128, 128, 0, stream>>>(p);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace hipstr

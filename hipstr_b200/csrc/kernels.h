@@ -1,0 +1,57 @@
+/* kernels.h -- launchers of the sm_100a kernels (kernels.cu). */
+#ifndef HIPSTR_B200_KERNELS_H_
+#define HIPSTR_B200_KERNELS_H_
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "layout.h"
+
+namespace hipstr {
+
+/* K1: read x haplotype HMM alignment.  `variant` indexes kColVariants (columns per lane). */
+cudaError_t launch_align(int variant, const AlignParams& p, cudaStream_t stream);
+size_t align_smem_bytes(int n_max, int l_max);
+
+/* K2: pool -> read scatter + mate merge (seq_stutter_genotyper.cpp:530-564). */
+struct ScatterParams {
+  int32_t n_reads, n_haps;
+  const double* pool_ll;
+  const int32_t* pool_seed;
+  const int32_t* pool_index;
+  const uint8_t* second_mate;
+  const uint8_t* copy_read;     /* may be NULL */
+  const uint8_t* realign_hap;   /* may be NULL */
+  double* read_ll;
+  int32_t* read_seed;           /* may be NULL */
+};
+cudaError_t launch_scatter(const ScatterParams& p, cudaStream_t stream);
+
+/* K3: genotype posteriors (genotyper.cpp:20-97). */
+struct PostSample {       /* one per (locus, sample) */
+  int32_t read0, read1;   /* global read range of the sample */
+  int32_t n_haps;
+  int32_t haploid;
+  int64_t ll_off;         /* read_ll offset of the locus's first read (row = read - locus_read0) */
+  int32_t locus_read0;
+  int32_t locus;
+  int64_t post_off;       /* post_out offset of this sample's H*H block */
+};
+struct PostParams {
+  int32_t n_samples;      /* total over loci */
+  int32_t n_loci;
+  const PostSample* samples;
+  const int32_t* locus_sample_off;
+  const double* read_ll;
+  const double* log_p1;
+  const double* log_p2;
+  const int32_t* read_weight;
+  const double* int_logs;
+  double log_one_half;
+  double* post_out;
+  double* sample_ll_out;
+  int32_t* best_out;      /* may be NULL */
+  double* total_ll_out;   /* may be NULL */
+};
+cudaError_t launch_posteriors(const PostParams& p, cudaStream_t stream);
+
+}  // namespace hipstr
+#endif

@@ -24,7 +24,7 @@
 
 #include <stdint.h>
 
-#define HIPSTR_WARPS_PER_CTA 4
+#define HIPSTR_WARPS_PER_CTA 1
 #define HIPSTR_MAX_BLOCKS 8          /* haplotype blocks per locus handled by the kernel */
 #define HIPSTR_ROW_REPEAT 0x80       /* rowinfo flag: row belongs to a repeat block      */
 #define HIPSTR_ROW_AFTER_REPEAT 0x40 /* rowinfo flag: first row after a repeat block     */
