@@ -52,6 +52,21 @@ class SynthView(C.Structure):
     ]
 
 
+class ReadsBatch(C.Structure):
+    """hipstr_reads_batch_t"""
+    _fields_ = [
+        ("locus_read_off", c_i32p), ("locus_sample_off", c_i32p), ("pool_index", c_i32p), ("sample_label", c_i32p),
+        ("second_mate", c_u8p), ("read_weight", c_i32p), ("log_p1", c_f64p), ("log_p2", c_f64p), ("haploid", c_u8p),
+        ("copy_read", c_u8p),
+    ]
+
+
+class GenotypeOut(C.Structure):
+    """hipstr_genotype_out_t (host or device pointers)"""
+    _fields_ = [("read_ll", C.c_void_p), ("read_seed", C.c_void_p), ("post", C.c_void_p), ("sample_ll", C.c_void_p),
+                ("best", C.c_void_p), ("total_ll", C.c_void_p)]
+
+
 STATUS = {0: "OK", 1: "NO_DEVICE", 2: "CUDA", 3: "BAD_ARG", 4: "UNSUPPORTED", 5: "INVALID_SEED", 6: "BAD_CIGAR"}
 
 
@@ -135,6 +150,19 @@ def load():
     lib.hipstr_posteriors_host.restype = C.c_int32
     lib.hipstr_posteriors_host.argtypes = [vp, C.c_int32, c_i32p, c_i32p, c_i32p, c_u8p, c_f64p, c_f64p, c_f64p,
                                            c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_f64p]
+    RB, GO = C.POINTER(ReadsBatch), C.POINTER(GenotypeOut)
+    lib.hipstr_genotype_batch_host.restype = C.c_int32
+    lib.hipstr_genotype_batch_host.argtypes = [vp, B, RB, GO]
+    lib.hipstr_upload_genotype_batch.restype = C.c_int32
+    lib.hipstr_upload_genotype_batch.argtypes = [vp, B, RB, C.POINTER(vp)]
+    lib.hipstr_genotype_batch_dev.restype = C.c_int32
+    lib.hipstr_genotype_batch_dev.argtypes = [vp, vp, GO]
+    lib.hipstr_free_genotype_batch.restype = None
+    lib.hipstr_free_genotype_batch.argtypes = [vp, vp]
+    lib.hipstr_last_traffic.restype = None
+    lib.hipstr_last_traffic.argtypes = [vp, c_i64p, c_i64p, c_i32p]
+    lib.hipstr_collect_timing.restype = C.c_int32
+    lib.hipstr_collect_timing.argtypes = [vp, c_f64p, c_f64p, c_i32p]
     _lib = lib
     return lib
 
@@ -196,6 +224,14 @@ class Synth:
         self.n_out = int(self.locus_out_off[-1])
         self.read_ll_size = v.read_ll_size
         self.post_size = v.post_size
+
+    def reads_batch(self, copy_read=None):
+        """hipstr_reads_batch_t view of the read-level arrays."""
+        v = self.view
+        rb = ReadsBatch(v.locus_read_off, v.locus_sample_off, v.pool_index, v.sample_label, v.second_mate,
+                        v.read_weight, v.log_p1, v.log_p2, v.haploid, ptr(copy_read, c_u8p))
+        rb._keep = copy_read
+        return rb
 
     def close(self):
         if self._h:
@@ -316,6 +352,47 @@ class Context:
 
     def free_batch(self, handle):
         self.lib.hipstr_free_batch(self.h, handle)
+
+    def genotype_host(self, batch, reads, n_elems, n_reads, post_size, n_samples, n_loci, read_ll=None,
+                      read_seed=None):
+        """hipstr_genotype_batch_host: K1 + K2 + K3 with host buffers in and out."""
+        out = dict(read_ll=np.zeros(n_elems, np.float64) if read_ll is None else read_ll,
+                   read_seed=np.full(n_reads, -2, np.int32) if read_seed is None else read_seed,
+                   post=np.zeros(post_size, np.float64), sample_ll=np.zeros(n_samples, np.float64),
+                   best=np.zeros(2 * n_samples, np.int32), total_ll=np.zeros(n_loci, np.float64))
+        go = GenotypeOut(*[out[k].ctypes.data for k in ("read_ll", "read_seed", "post", "sample_ll", "best", "total_ll")])
+        self._check(self.lib.hipstr_genotype_batch_host(self.h, C.byref(batch), C.byref(reads), C.byref(go)),
+                    "genotype_batch_host")
+        out["best"] = out["best"].reshape(-1, 2)
+        return out
+
+    def upload_genotype(self, batch, reads):
+        h = C.c_void_p()
+        self._check(self.lib.hipstr_upload_genotype_batch(self.h, C.byref(batch), C.byref(reads), C.byref(h)),
+                    "upload_genotype_batch")
+        return h
+
+    def genotype_dev(self, handle, read_ll, read_seed, post, sample_ll, best, total_ll):
+        """Device pointers (ints); read_seed / best / total_ll may be 0."""
+        go = GenotypeOut(read_ll, read_seed or None, post, sample_ll, best or None, total_ll or None)
+        self._check(self.lib.hipstr_genotype_batch_dev(self.h, handle, C.byref(go)), "genotype_batch_dev")
+
+    def free_genotype(self, handle):
+        self.lib.hipstr_free_genotype_batch(self.h, handle)
+
+    def traffic(self):
+        a, b, n = C.c_int64(), C.c_int64(), C.c_int32()
+        self.lib.hipstr_last_traffic(self.h, C.byref(a), C.byref(b), C.byref(n))
+        return a.value, b.value, n.value
+
+    def enable_timing(self, on=True):
+        self._check(self.lib.hipstr_enable_timing(self.h, 1 if on else 0), "enable_timing")
+
+    def collect_timing(self):
+        """(K1 ms, scatter+posterior ms, calls) summed since the last collect; synchronises the stream."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int32()
+        self._check(self.lib.hipstr_collect_timing(self.h, C.byref(a), C.byref(b), C.byref(n)), "collect_timing")
+        return a.value, b.value, n.value
 
     def scatter_host(self, n_haps, pool_ll, pool_seed, pool_index, second_mate, read_ll, read_seed=None,
                      copy_read=None, realign_hap=None):

@@ -37,6 +37,7 @@ struct hipstr_dev_batch {
   int32_t n_jobs[kNumColVariants];
   int32_t n_max[kNumColVariants], l_max[kNumColVariants];
   int64_t n_out = 0, n_alignments = 0;
+  bool has_mask = false;
   void release() {
     pools.release(); bases.release(); quals.release(); hapsides.release(); hapbytes.release();
     blocks.release(); reps.release(); runs.release(); mask.release();
@@ -44,18 +45,38 @@ struct hipstr_dev_batch {
   }
 };
 
+struct hipstr_dev_genotype {
+  hipstr_dev_batch align;
+  DevBuf loci, samples, locus_sample_off, pool_seed, pool_index, second_mate, copy_read, read_weight, log_p1, log_p2;
+  DevBuf pool_ll;                      // K1 output, [n_out]
+  int32_t n_loci = 0, n_samples = 0, n_reads = 0;
+  int64_t n_elems = 0, post_size = 0;
+  bool has_copy_read = false, masked = false;
+  void release() {
+    align.release();
+    loci.release(); samples.release(); locus_sample_off.release(); pool_seed.release(); pool_index.release();
+    second_mate.release(); copy_read.release(); read_weight.release(); log_p1.release(); log_p2.release();
+    pool_ll.release();
+  }
+};
+
+struct StageEvents { cudaEvent_t e[3]; };
+
 struct hipstr_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   double *d_qual_lut = nullptr, *d_trans = nullptr, *d_int_logs = nullptr;
   std::string last_error;
   int32_t last_launches = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;
   bool timing = false;
   float last_ms = 0.f;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  hipstr_dev_batch scratch;      // reused by the *_host entry points
-  DevBuf d_ll, d_pos, d_misc[12];
-  double* d_debug = nullptr;     // test hook, see hipstr_debug_lastcols
+  std::vector<StageEvents> pending;      // recorded, not yet read
+  std::vector<StageEvents> free_events;
+  hipstr_dev_batch scratch;              // reused by hipstr_align_batch_host
+  hipstr_dev_genotype gscratch;          // reused by hipstr_genotype_batch_host
+  DevBuf d_ll, d_pos, d_misc[12], d_out[6];
+  double* d_debug = nullptr;             // test hook, see hipstr_debug_lastcols
 };
 
 namespace {
@@ -71,17 +92,23 @@ hipstr_status_t fail(hipstr_ctx* c, hipstr_status_t st, const std::string& msg) 
       return fail(ctx, HIPSTR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));  \
   } while (0)
 
-template <class T>
-cudaError_t put(DevBuf& d, const std::vector<T>& v, cudaStream_t s) {
-  cudaError_t e = d.reserve(std::max<size_t>(v.size() * sizeof(T), 16));
-  if (e != cudaSuccess || v.empty()) return e;
-  return cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-}
+thread_local int64_t g_h2d = 0;   // bytes queued host->device by put() since begin_call()
 template <class T>
 cudaError_t put(DevBuf& d, const T* v, size_t n, cudaStream_t s) {
   cudaError_t e = d.reserve(std::max<size_t>(n * sizeof(T), 16));
   if (e != cudaSuccess || n == 0) return e;
+  g_h2d += (int64_t)(n * sizeof(T));
   return cudaMemcpyAsync(d.p, v, n * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+template <class T>
+cudaError_t put(DevBuf& d, const std::vector<T>& v, cudaStream_t s) { return put(d, v.data(), v.size(), s); }
+void begin_call(hipstr_ctx* c) { g_h2d = 0; c->h2d_bytes = c->d2h_bytes = 0; c->last_launches = 0; }
+void end_call(hipstr_ctx* c) { c->h2d_bytes = g_h2d; }
+template <class T>
+cudaError_t get(hipstr_ctx* c, T* dst, const void* src, size_t n) {
+  if (n == 0) return cudaSuccess;
+  c->d2h_bytes += (int64_t)(n * sizeof(T));
+  return cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream);
 }
 
 hipstr_status_t stage(hipstr_ctx* ctx, const hipstr_align_batch_t* batch, hipstr_dev_batch& d) {
@@ -107,7 +134,7 @@ hipstr_status_t stage(hipstr_ctx* ctx, const hipstr_align_batch_t* batch, hipstr
   }
   d.n_out = f.n_out;
   d.n_alignments = f.n_alignments;
-  if (f.hap_mask.empty()) d.mask.release();
+  d.has_mask = !f.hap_mask.empty();
   // the staging vectors die at return: the copies above must have left pageable memory
   CU(cudaStreamSynchronize(s));
   return HIPSTR_OK;
@@ -124,14 +151,12 @@ hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll
   p.blocks = (const DevBlock*)d.blocks.p;
   p.reps = (const DevRep*)d.reps.p;
   p.runs = (const uint16_t*)d.runs.p;
-  p.hap_mask = (const uint8_t*)d.mask.p;
+  p.hap_mask = d.has_mask ? (const uint8_t*)d.mask.p : nullptr;
   p.qual_lut = ctx->d_qual_lut;
   p.trans = ctx->d_trans;
   p.int_logs = ctx->d_int_logs;
   p.ll_out = ll_dev;
   p.pos_out = pos_dev;
-  ctx->last_launches = 0;
-  if (ctx->timing) CU(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int v = kNumColVariants - 1; v >= 0; v--) {   // longest reads first
     if (d.n_jobs[v] == 0) continue;
     p.jobs = (const DevJob*)d.jobs[v].p;
@@ -142,12 +167,121 @@ hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll
     CU(launch_align(v, p, ctx->stream));
     ctx->last_launches++;
   }
-  if (ctx->timing) {
-    CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    CU(cudaEventSynchronize(ctx->ev1));
-    CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
-  }
   return HIPSTR_OK;
+}
+
+// stage timing: events are recorded on the stream and read later (hipstr_collect_timing), so
+// enabling it does not serialise the steps
+hipstr_status_t mark(hipstr_ctx* ctx, StageEvents& ev, int which) {
+  if (!ctx->timing) return HIPSTR_OK;
+  if (which == 0) {
+    if (ctx->free_events.empty()) {
+      for (auto& e : ev.e) CU(cudaEventCreate(&e));
+    } else {
+      ev = ctx->free_events.back();
+      ctx->free_events.pop_back();
+    }
+  }
+  CU(cudaEventRecord(ev.e[which], ctx->stream));
+  if (which == 2) ctx->pending.push_back(ev);
+  return HIPSTR_OK;
+}
+
+hipstr_status_t stage_reads(hipstr_ctx* ctx, const hipstr_align_batch_t* b, const hipstr_reads_batch_t* r,
+                            hipstr_dev_genotype& g) {
+  const int n_loci = b->n_loci;
+  if (n_loci > 0 && (!r->locus_read_off || !r->locus_sample_off || !r->pool_index || !r->sample_label ||
+                     !r->second_mate || !r->read_weight || !r->log_p1 || !r->log_p2 || !r->haploid))
+    return fail(ctx, HIPSTR_ERR_BAD_ARG, "null array in reads batch");
+  const int32_t R = n_loci ? r->locus_read_off[n_loci] : 0, S = n_loci ? r->locus_sample_off[n_loci] : 0;
+  std::vector<ScatterLocus> loci((size_t)n_loci);
+  std::vector<PostSample> samples((size_t)S);
+  int64_t elem = 0, post = 0, hap0 = 0;
+  for (int l = 0; l < n_loci; l++) {
+    const int64_t H64 = b->locus_hap_off[l + 1] - b->locus_hap_off[l];
+    if (H64 <= 0 || H64 + 1 >= 10000) return fail(ctx, HIPSTR_ERR_UNSUPPORTED, "haplotype count outside 1..9998");
+    const int H = (int)H64;
+    const int r0 = r->locus_read_off[l], r1 = r->locus_read_off[l + 1];
+    const int P = b->locus_pool_off[l + 1] - b->locus_pool_off[l];
+    ScatterLocus& L = loci[l];
+    L.elem_off = elem;
+    L.pool_ll_off = b->locus_out_off[l];
+    L.read0 = r0;
+    L.n_reads = r1 - r0;
+    L.n_haps = H;
+    L.pool0 = b->locus_pool_off[l];
+    L.hap0 = hap0;
+    for (int i = r0; i < r1; i++)
+      if (r->pool_index[i] < 0 || r->pool_index[i] >= P) return fail(ctx, HIPSTR_ERR_BAD_ARG, "pool_index out of range");
+    const int s0 = r->locus_sample_off[l], s1 = r->locus_sample_off[l + 1];
+    int i = r0;
+    for (int s = s0; s < s1; s++) {
+      PostSample& ps = samples[s];
+      ps.read0 = i;
+      while (i < r1 && r->sample_label[i] == s - s0) i++;   // reads are sample-major (genotyper.h:104-112)
+      ps.read1 = i;
+      ps.n_haps = H;
+      ps.haploid = r->haploid[l];
+      ps.ll_off = elem;
+      ps.locus_read0 = r0;
+      ps.locus = l;
+      ps.post_off = post + (int64_t)(s - s0) * H * H;
+    }
+    if (i != r1) return fail(ctx, HIPSTR_ERR_BAD_ARG, "reads are not sample-major or a sample label is out of range");
+    elem += (int64_t)(r1 - r0) * H;
+    post += (int64_t)(s1 - s0) * H * H;
+    hap0 += H;
+  }
+  cudaStream_t s = ctx->stream;
+  CU(put(g.loci, loci, s));
+  CU(put(g.samples, samples, s));
+  CU(put(g.locus_sample_off, r->locus_sample_off, (size_t)n_loci + 1, s));
+  CU(put(g.pool_seed, b->pool_seed, (size_t)b->n_pools, s));
+  CU(put(g.pool_index, r->pool_index, (size_t)R, s));
+  CU(put(g.second_mate, r->second_mate, (size_t)R, s));
+  if (r->copy_read) CU(put(g.copy_read, r->copy_read, (size_t)R, s));
+  CU(put(g.read_weight, r->read_weight, (size_t)R, s));
+  CU(put(g.log_p1, r->log_p1, (size_t)R, s));
+  CU(put(g.log_p2, r->log_p2, (size_t)R, s));
+  CU(cudaStreamSynchronize(s));   // `loci` / `samples` are locals
+  g.n_loci = n_loci; g.n_samples = S; g.n_reads = R; g.n_elems = elem; g.post_size = post;
+  g.has_copy_read = r->copy_read != nullptr;
+  g.masked = r->copy_read || b->realign_pool || b->realign_hap;
+  return HIPSTR_OK;
+}
+
+hipstr_status_t run_genotype(hipstr_ctx* ctx, hipstr_dev_genotype& g, const hipstr_genotype_out_t& o) {
+  StageEvents ev;
+  hipstr_status_t st;
+  CU(g.pool_ll.reserve(std::max<size_t>((size_t)g.align.n_out * sizeof(double), 16)));
+  if ((st = mark(ctx, ev, 0)) != HIPSTR_OK) return st;
+  if ((st = run_align(ctx, g.align, (double*)g.pool_ll.p, nullptr)) != HIPSTR_OK) return st;
+  if ((st = mark(ctx, ev, 1)) != HIPSTR_OK) return st;
+  ScatterBatchParams sp;
+  sp.n_loci = g.n_loci; sp.n_elems = g.n_elems;
+  sp.loci = (const ScatterLocus*)g.loci.p;
+  sp.pool_ll = (const double*)g.pool_ll.p;
+  sp.pool_seed = (const int32_t*)g.pool_seed.p;
+  sp.pool_index = (const int32_t*)g.pool_index.p;
+  sp.second_mate = (const uint8_t*)g.second_mate.p;
+  sp.copy_read = g.has_copy_read ? (const uint8_t*)g.copy_read.p : nullptr;
+  sp.hap_mask = g.align.has_mask ? (const uint8_t*)g.align.mask.p : nullptr;
+  sp.read_ll = o.read_ll;
+  sp.read_seed = o.read_seed;
+  CU(launch_scatter_batch(sp, ctx->stream));
+  if (g.n_elems > 0) ctx->last_launches++;
+  PostParams pp;
+  pp.n_samples = g.n_samples; pp.n_loci = g.n_loci;
+  pp.samples = (const PostSample*)g.samples.p;
+  pp.locus_sample_off = (const int32_t*)g.locus_sample_off.p;
+  pp.read_ll = o.read_ll;
+  pp.log_p1 = (const double*)g.log_p1.p; pp.log_p2 = (const double*)g.log_p2.p;
+  pp.read_weight = (const int32_t*)g.read_weight.p;
+  pp.int_logs = ctx->d_int_logs; pp.log_one_half = host_tables().log_one_half;
+  pp.post_out = o.post; pp.sample_ll_out = o.sample_ll; pp.best_out = o.best; pp.total_ll_out = o.total_ll;
+  CU(launch_posteriors(pp, ctx->stream));
+  if (g.n_samples > 0) ctx->last_launches += o.total_ll ? 2 : 1;
+  return mark(ctx, ev, 2);
 }
 
 }  // namespace
@@ -175,8 +309,6 @@ hipstr_status_t hipstr_create(int device, hipstr_ctx_t** out_ctx) {
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   ctx->stream = ctx->own_stream;
-  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("event", e);
-  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("event", e);
   const HostTables& T = host_tables();
   if ((e = cudaMalloc(&ctx->d_qual_lut, sizeof(T.qual_lut))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->d_trans, sizeof(T.trans))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -193,15 +325,17 @@ void hipstr_destroy(hipstr_ctx_t* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   ctx->scratch.release();
+  ctx->gscratch.release();
   ctx->d_ll.release();
   ctx->d_pos.release();
   for (auto& b : ctx->d_misc) b.release();
+  for (auto& b : ctx->d_out) b.release();
+  for (auto& ev : ctx->pending) for (auto& e : ev.e) cudaEventDestroy(e);
+  for (auto& ev : ctx->free_events) for (auto& e : ev.e) cudaEventDestroy(e);
   if (ctx->d_debug) cudaFree(ctx->d_debug);
   if (ctx->d_qual_lut) cudaFree(ctx->d_qual_lut);
   if (ctx->d_trans) cudaFree(ctx->d_trans);
   if (ctx->d_int_logs) cudaFree(ctx->d_int_logs);
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -216,6 +350,11 @@ hipstr_status_t hipstr_set_stream(hipstr_ctx_t* ctx, void* cuda_stream) {
 
 int64_t hipstr_batch_num_alignments(const hipstr_align_batch_t* batch) { return batch ? count_alignments(batch) : 0; }
 int32_t hipstr_last_launch_count(const hipstr_ctx_t* ctx) { return ctx ? ctx->last_launches : 0; }
+void hipstr_last_traffic(const hipstr_ctx_t* ctx, int64_t* h2d, int64_t* d2h, int32_t* launches) {
+  if (h2d) *h2d = ctx ? ctx->h2d_bytes : 0;
+  if (d2h) *d2h = ctx ? ctx->d2h_bytes : 0;
+  if (launches) *launches = ctx ? ctx->last_launches : 0;
+}
 hipstr_status_t hipstr_enable_timing(hipstr_ctx_t* ctx, int enable) {
   if (!ctx) return HIPSTR_ERR_BAD_ARG;
   ctx->timing = enable != 0;
@@ -223,11 +362,35 @@ hipstr_status_t hipstr_enable_timing(hipstr_ctx_t* ctx, int enable) {
 }
 float hipstr_last_kernel_ms(const hipstr_ctx_t* ctx) { return ctx ? ctx->last_ms : 0.f; }
 
+/* Test/bench hook (not in the public header): waits for the stream, then sums the stage times of
+ * every call since the last collect: k1_ms = alignment kernels, rest_ms = scatter + posteriors. */
+hipstr_status_t hipstr_collect_timing(hipstr_ctx_t* ctx, double* k1_ms, double* rest_ms, int32_t* n_calls) {
+  if (!ctx) return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  double a = 0, b = 0;
+  for (auto& ev : ctx->pending) {
+    float t0 = 0, t1 = 0;
+    CU(cudaEventElapsedTime(&t0, ev.e[0], ev.e[1]));
+    CU(cudaEventElapsedTime(&t1, ev.e[1], ev.e[2]));
+    a += t0; b += t1;
+    ctx->free_events.push_back(ev);
+  }
+  if (k1_ms) *k1_ms = a;
+  if (rest_ms) *rest_ms = b;
+  if (n_calls) *n_calls = (int32_t)ctx->pending.size();
+  if (!ctx->pending.empty()) ctx->last_ms = (float)(a / ctx->pending.size());
+  ctx->pending.clear();
+  return HIPSTR_OK;
+}
+
 hipstr_status_t hipstr_upload_batch(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch, hipstr_dev_batch_t** out) {
   if (!ctx || !batch || !out) return HIPSTR_ERR_BAD_ARG;
   CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
   hipstr_dev_batch* d = new hipstr_dev_batch();
   hipstr_status_t st = stage(ctx, batch, *d);
+  end_call(ctx);
   if (st != HIPSTR_OK) { d->release(); delete d; return st; }
   *out = d;
   return HIPSTR_OK;
@@ -243,12 +406,19 @@ void hipstr_free_batch(hipstr_ctx_t* ctx, hipstr_dev_batch_t* h) {
 hipstr_status_t hipstr_align_batch_dev(hipstr_ctx_t* ctx, const hipstr_dev_batch_t* h, double* ll_dev, int32_t* pos_dev) {
   if (!ctx || !h || !ll_dev) return HIPSTR_ERR_BAD_ARG;
   CU(cudaSetDevice(ctx->device));
-  return run_align(ctx, *h, ll_dev, pos_dev);
+  begin_call(ctx);
+  StageEvents ev;
+  hipstr_status_t st;
+  if ((st = mark(ctx, ev, 0)) != HIPSTR_OK) return st;
+  if ((st = run_align(ctx, *h, ll_dev, pos_dev)) != HIPSTR_OK) return st;
+  if ((st = mark(ctx, ev, 1)) != HIPSTR_OK) return st;
+  return mark(ctx, ev, 2);
 }
 
 hipstr_status_t hipstr_align_batch_host(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch, double* ll_out, int32_t* seed_hap_pos) {
   if (!ctx || !batch || !ll_out) return HIPSTR_ERR_BAD_ARG;
   CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
   hipstr_status_t st = stage(ctx, batch, ctx->scratch);
   if (st != HIPSTR_OK) return st;
   const size_t n = (size_t)ctx->scratch.n_out;
@@ -257,14 +427,15 @@ hipstr_status_t hipstr_align_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   if (seed_hap_pos) CU(ctx->d_pos.reserve(n * sizeof(int32_t)));
   const bool masked = batch->realign_pool || batch->realign_hap;
   if (masked) {   // entries the masks exclude must come back untouched (HapAligner.cpp:326-329,615-619)
-    CU(cudaMemcpyAsync(ctx->d_ll.p, ll_out, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (seed_hap_pos) CU(cudaMemcpyAsync(ctx->d_pos.p, seed_hap_pos, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(put(ctx->d_ll, ll_out, n, ctx->stream));
+    if (seed_hap_pos) CU(put(ctx->d_pos, seed_hap_pos, n, ctx->stream));
   }
   st = run_align(ctx, ctx->scratch, (double*)ctx->d_ll.p, seed_hap_pos ? (int32_t*)ctx->d_pos.p : nullptr);
   if (st != HIPSTR_OK) return st;
-  CU(cudaMemcpyAsync(ll_out, ctx->d_ll.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (seed_hap_pos) CU(cudaMemcpyAsync(seed_hap_pos, ctx->d_pos.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(get(ctx, ll_out, ctx->d_ll.p, n));
+  if (seed_hap_pos) CU(get(ctx, seed_hap_pos, ctx->d_pos.p, n));
   CU(cudaStreamSynchronize(ctx->stream));
+  end_call(ctx);
   return HIPSTR_OK;
 }
 
@@ -279,6 +450,75 @@ hipstr_status_t hipstr_debug_lastcols(hipstr_ctx_t* ctx, int enable, double* out
   return HIPSTR_OK;
 }
 
+hipstr_status_t hipstr_upload_genotype_batch(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch,
+                                             const hipstr_reads_batch_t* reads, hipstr_dev_genotype_t** out) {
+  if (!ctx || !batch || !reads || !out) return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
+  hipstr_dev_genotype* g = new hipstr_dev_genotype();
+  hipstr_status_t st = stage(ctx, batch, g->align);
+  if (st == HIPSTR_OK) st = stage_reads(ctx, batch, reads, *g);
+  end_call(ctx);
+  if (st != HIPSTR_OK) { g->release(); delete g; return st; }
+  *out = g;
+  return HIPSTR_OK;
+}
+
+void hipstr_free_genotype_batch(hipstr_ctx_t* ctx, hipstr_dev_genotype_t* h) {
+  if (!h) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  h->release();
+  delete h;
+}
+
+hipstr_status_t hipstr_genotype_batch_dev(hipstr_ctx_t* ctx, const hipstr_dev_genotype_t* h, const hipstr_genotype_out_t* o) {
+  if (!ctx || !h || !o || !o->read_ll || !o->post || !o->sample_ll) return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
+  return run_genotype(ctx, *const_cast<hipstr_dev_genotype*>(h), *o);
+}
+
+hipstr_status_t hipstr_genotype_batch_host(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch,
+                                           const hipstr_reads_batch_t* reads, const hipstr_genotype_out_t* o) {
+  if (!ctx || !batch || !reads || !o || !o->read_ll || !o->post || !o->sample_ll) return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
+  hipstr_dev_genotype& g = ctx->gscratch;
+  hipstr_status_t st = stage(ctx, batch, g.align);
+  if (st == HIPSTR_OK) st = stage_reads(ctx, batch, reads, g);
+  if (st != HIPSTR_OK) return st;
+  DevBuf* d = ctx->d_out;
+  CU(d[0].reserve(std::max<size_t>((size_t)g.n_elems * sizeof(double), 16)));
+  CU(d[1].reserve(std::max<size_t>((size_t)g.n_reads * sizeof(int32_t), 16)));
+  CU(d[2].reserve(std::max<size_t>((size_t)g.post_size * sizeof(double), 16)));
+  CU(d[3].reserve(std::max<size_t>((size_t)g.n_samples * sizeof(double), 16)));
+  CU(d[4].reserve(std::max<size_t>((size_t)g.n_samples * 2 * sizeof(int32_t), 16)));
+  CU(d[5].reserve(std::max<size_t>((size_t)g.n_loci * sizeof(double), 16)));
+  if (g.masked) {   // in-place semantics of log_aln_probs_ / seed_positions_ under the masks
+    CU(put(d[0], o->read_ll, (size_t)g.n_elems, ctx->stream));
+    if (o->read_seed) CU(put(d[1], o->read_seed, (size_t)g.n_reads, ctx->stream));
+    // K1 writes only the realigned entries of the pool buffer; K2 reads only those
+  }
+  hipstr_genotype_out_t dev;
+  dev.read_ll = (double*)d[0].p;
+  dev.read_seed = o->read_seed ? (int32_t*)d[1].p : nullptr;
+  dev.post = (double*)d[2].p;
+  dev.sample_ll = (double*)d[3].p;
+  dev.best = o->best ? (int32_t*)d[4].p : nullptr;
+  dev.total_ll = o->total_ll ? (double*)d[5].p : nullptr;
+  st = run_genotype(ctx, g, dev);
+  if (st != HIPSTR_OK) return st;
+  CU(get(ctx, o->read_ll, d[0].p, (size_t)g.n_elems));
+  if (o->read_seed) CU(get(ctx, o->read_seed, d[1].p, (size_t)g.n_reads));
+  CU(get(ctx, o->post, d[2].p, (size_t)g.post_size));
+  CU(get(ctx, o->sample_ll, d[3].p, (size_t)g.n_samples));
+  if (o->best) CU(get(ctx, o->best, d[4].p, (size_t)g.n_samples * 2));
+  if (o->total_ll) CU(get(ctx, o->total_ll, d[5].p, (size_t)g.n_loci));
+  CU(cudaStreamSynchronize(ctx->stream));
+  end_call(ctx);
+  return HIPSTR_OK;
+}
+
 hipstr_status_t hipstr_scatter_pool_lls_host(hipstr_ctx_t* ctx, int32_t n_reads, int32_t n_haps, const double* pool_ll,
                                              const int32_t* pool_seed, const int32_t* pool_index,
                                              const uint8_t* second_mate, const uint8_t* copy_read,
@@ -287,6 +527,7 @@ hipstr_status_t hipstr_scatter_pool_lls_host(hipstr_ctx_t* ctx, int32_t n_reads,
   if (n_reads == 0) return HIPSTR_OK;
   if (!pool_ll || !pool_index || !second_mate || !read_ll || (read_seed && !pool_seed)) return HIPSTR_ERR_BAD_ARG;
   CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
   int32_t n_pools = 0;
   for (int r = 0; r < n_reads; r++) {
     if (pool_index[r] < 0) return fail(ctx, HIPSTR_ERR_BAD_ARG, "negative pool index");
@@ -311,9 +552,10 @@ hipstr_status_t hipstr_scatter_pool_lls_host(hipstr_ctx_t* ctx, int32_t n_reads,
   p.read_seed = read_seed ? (int32_t*)m[7].p : nullptr;
   CU(launch_scatter(p, s));
   ctx->last_launches = 1;
-  CU(cudaMemcpyAsync(read_ll, m[3].p, (size_t)n_reads * n_haps * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (read_seed) CU(cudaMemcpyAsync(read_seed, m[7].p, (size_t)n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CU(get(ctx, read_ll, m[3].p, (size_t)n_reads * n_haps));
+  if (read_seed) CU(get(ctx, read_seed, m[7].p, (size_t)n_reads));
   CU(cudaStreamSynchronize(s));
+  end_call(ctx);
   return HIPSTR_OK;
 }
 
@@ -328,6 +570,7 @@ hipstr_status_t hipstr_posteriors_host(hipstr_ctx_t* ctx, int32_t n_loci, const 
       !read_weight || !post_out || !sample_ll_out)
     return HIPSTR_ERR_BAD_ARG;
   CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
   const int32_t R = locus_read_off[n_loci], S = locus_sample_off[n_loci];
   std::vector<PostSample> samples((size_t)S);
   int64_t ll_off = 0, post_off = 0;
@@ -376,11 +619,12 @@ hipstr_status_t hipstr_posteriors_host(hipstr_ctx_t* ctx, int32_t n_loci, const 
   p.total_ll_out = total_ll_out ? (double*)m[9].p : nullptr;
   CU(launch_posteriors(p, s));
   ctx->last_launches = total_ll_out ? 2 : 1;
-  CU(cudaMemcpyAsync(post_out, m[6].p, (size_t)post_off * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CU(cudaMemcpyAsync(sample_ll_out, m[7].p, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (best_out) CU(cudaMemcpyAsync(best_out, m[8].p, (size_t)S * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (total_ll_out) CU(cudaMemcpyAsync(total_ll_out, m[9].p, (size_t)n_loci * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(get(ctx, post_out, m[6].p, (size_t)post_off));
+  CU(get(ctx, sample_ll_out, m[7].p, (size_t)S));
+  if (best_out) CU(get(ctx, best_out, m[8].p, (size_t)S * 2));
+  if (total_ll_out) CU(get(ctx, total_ll_out, m[9].p, (size_t)n_loci));
   CU(cudaStreamSynchronize(s));
+  end_call(ctx);
   return HIPSTR_OK;
 }
 

@@ -524,6 +524,44 @@ cudaError_t launch_scatter(const ScatterParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+__global__ void k_scatter_batch(const ScatterBatchParams P) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P.n_elems) return;
+  int lo = 0, hi = P.n_loci - 1;   // last locus with elem_off <= idx
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (P.loci[mid].elem_off <= idx) lo = mid; else hi = mid - 1;
+  }
+  const ScatterLocus L = P.loci[lo];
+  const int64_t e = idx - L.elem_off;
+  const int r = (int)(e / L.n_haps), h = (int)(e % L.n_haps);
+  const uint8_t* second = P.second_mate + L.read0;
+  if (second[r] && r > 0) return;
+  const bool hap_on = !P.hap_mask || P.hap_mask[L.hap0 + h];
+  const int32_t* pidx = P.pool_index + L.read0;
+  double* ll = P.read_ll + L.elem_off;
+  const double* pll = P.pool_ll + L.pool_ll_off;
+  for (int m = r; m < L.n_reads && (m == r || second[m]); m++) {
+    const int pi = pidx[m];
+    bool copy = !P.copy_read || P.copy_read[L.read0 + m];
+    if (!copy) continue;
+    if (h == 0 && P.read_seed) P.read_seed[L.read0 + m] = P.pool_seed[L.pool0 + pi];
+    if (!hap_on) continue;
+    double v = pll[(size_t)pi * L.n_haps + h];
+    if (m > r) {
+      v += ll[(size_t)(m - 1) * L.n_haps + h];
+      ll[(size_t)(m - 1) * L.n_haps + h] = v;
+    }
+    ll[(size_t)m * L.n_haps + h] = v;
+  }
+}
+
+cudaError_t launch_scatter_batch(const ScatterBatchParams& p, cudaStream_t stream) {
+  if (p.n_elems <= 0) return cudaSuccess;
+  k_scatter_batch<<<(unsigned)((p.n_elems + 255) / 256), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // K3: genotype posteriors.  One CTA per (locus, sample); thread t owns diplotypes t, t+T, ...
 // and folds the sample's reads into them in read order (genotyper.cpp:59-64), then the CTA

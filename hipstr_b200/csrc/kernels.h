@@ -25,6 +25,31 @@ struct ScatterParams {
 };
 cudaError_t launch_scatter(const ScatterParams& p, cudaStream_t stream);
 
+/* K2, batched over loci: same semantics, one launch for every locus of a batch. */
+struct ScatterLocus {      /* one per locus */
+  int64_t elem_off;        /* first (read, hap) element of the locus = read_ll offset */
+  int64_t pool_ll_off;     /* locus_out_off: pool LL row 0 */
+  int32_t read0;           /* global index of the locus's first read */
+  int32_t n_reads;
+  int32_t n_haps;
+  int32_t pool0;           /* global index of the locus's first pool */
+  int64_t hap0;            /* dense global index of haplotype 0 (mask lookup) */
+};
+struct ScatterBatchParams {
+  int32_t n_loci;
+  int64_t n_elems;
+  const ScatterLocus* loci;
+  const double* pool_ll;
+  const int32_t* pool_seed;     /* global per pool */
+  const int32_t* pool_index;    /* per read, local to locus */
+  const uint8_t* second_mate;
+  const uint8_t* copy_read;     /* may be NULL */
+  const uint8_t* hap_mask;      /* may be NULL */
+  double* read_ll;
+  int32_t* read_seed;           /* may be NULL */
+};
+cudaError_t launch_scatter_batch(const ScatterBatchParams& p, cudaStream_t stream);
+
 /* K3: genotype posteriors (genotyper.cpp:20-97). */
 struct PostSample {       /* one per (locus, sample) */
   int32_t read0, read1;   /* global read range of the sample */

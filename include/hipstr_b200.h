@@ -215,6 +215,55 @@ hipstr_status_t hipstr_posteriors_host(hipstr_ctx_t* ctx, int32_t n_loci,
                                        double* post_out, double* sample_ll_out, int32_t* best_out,
                                        double* total_ll_out);
 
+/* --- a1 first pass: align + scatter + posteriors for a batch of loci --------
+ * One call = what SeqStutterGenotyper::genotype does at
+ * seq_stutter_genotyper.cpp:638-639 (calc_hap_aln_probs(all haplotypes) ->
+ * calc_log_sample_posteriors()) for MANY loci at once: K1 over every pooled
+ * read x haplotype, K2 pool->read scatter + mate merge, K3 posteriors.
+ *
+ * hipstr_reads_batch_t is the read-level view of the same loci: the Genotyper /
+ * SeqStutterGenotyper member arrays (genotyper.h:21-46,
+ * seq_stutter_genotyper.h:34-68), packed over loci. */
+typedef struct hipstr_reads_batch {
+  const int32_t* locus_read_off;    /* [n_loci+1] reads of locus l: [off[l], off[l+1])        */
+  const int32_t* locus_sample_off;  /* [n_loci+1]                                             */
+  const int32_t* pool_index;        /* [R] pool_index_: pool of the read, local to its locus  */
+  const int32_t* sample_label;      /* [R] sample_label_, local to its locus, non-decreasing  */
+  const uint8_t* second_mate;       /* [R] second_mate_ (the read before it is its mate)      */
+  const int32_t* read_weight;       /* [R] read_weights_ (0 for second mates)                 */
+  const double*  log_p1;            /* [R] SNP-phasing log-likelihoods                        */
+  const double*  log_p2;            /* [R]                                                    */
+  const uint8_t* haploid;           /* [n_loci]                                               */
+  const uint8_t* copy_read;         /* [R] or NULL = every read (calc_hap_aln_probs copy_read) */
+} hipstr_reads_batch_t;
+
+typedef struct hipstr_genotype_out {
+  double*  read_ll;    /* [sum R_l*H_l] log_aln_probs_; entries the masks exclude keep their content */
+  int32_t* read_seed;  /* [R] seed_positions_, may be NULL                                   */
+  double*  post;       /* [sum S_l*H_l^2] log_sample_posteriors_                             */
+  double*  sample_ll;  /* [S] sample_total_LLs_                                              */
+  int32_t* best;       /* [S][2] get_optimal_haplotypes, may be NULL                         */
+  double*  total_ll;   /* [n_loci] return value of calc_log_sample_posteriors, may be NULL   */
+} hipstr_genotype_out_t;
+
+/* HOST buffers in and out (end-to-end path: flatten, H2D, K1-K3, D2H). */
+hipstr_status_t hipstr_genotype_batch_host(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch,
+                                           const hipstr_reads_batch_t* reads,
+                                           const hipstr_genotype_out_t* out);
+/* Resident variant: inputs staged once in HBM, `out` holds DEVICE pointers. */
+typedef struct hipstr_dev_genotype hipstr_dev_genotype_t;
+hipstr_status_t hipstr_upload_genotype_batch(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch,
+                                             const hipstr_reads_batch_t* reads,
+                                             hipstr_dev_genotype_t** out_handle);
+hipstr_status_t hipstr_genotype_batch_dev(hipstr_ctx_t* ctx, const hipstr_dev_genotype_t* handle,
+                                          const hipstr_genotype_out_t* dev_out);
+void            hipstr_free_genotype_batch(hipstr_ctx_t* ctx, hipstr_dev_genotype_t* handle);
+
+/* Accounting of the last public call on this context: bytes copied host->device and
+ * device->host, and kernels launched. */
+void hipstr_last_traffic(const hipstr_ctx_t* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes,
+                         int32_t* kernel_launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -184,3 +184,85 @@ def test_posteriors(ctx, name):
         assert np.abs(gp[finite] - wp[finite]).max() <= 1e-9      # exp/log of CUDA vs glibc differ in ulps
         assert np.abs(gs - ws).max() <= 1e-9 and np.abs(gt - wt).max() <= 1e-8
         assert np.array_equal(gb, wb)
+
+
+def _oracle_genotype(s, copy_read=None, read_ll0=None):
+    """align -> scatter -> posteriors with the CPU oracle, locus by locus."""
+    from hipstr_b200.capi import c_f64p, c_i32p, c_u8p, ptr
+    o = checkers.oracle()
+    fill = 0.0
+    pool_ll = checkers.align(o, "oracle_", s.batch, s.n_out, fill=fill)
+    read_ll = np.zeros(int(s.read_ll_size)) if read_ll0 is None else read_ll0.copy()
+    read_seed = np.full(s.n_reads, -2, np.int32)
+    off = 0
+    hap_mask_all = s.batch.realign_hap
+    for l in range(s.n_loci):
+        H = int(s.n_haps[l])
+        r0, r1 = int(s.locus_read_off[l]), int(s.locus_read_off[l + 1])
+        p0, p1 = int(s.locus_pool_off[l]), int(s.locus_pool_off[l + 1])
+        pl = np.ascontiguousarray(pool_ll[s.locus_out_off[l]:s.locus_out_off[l + 1]])
+        seeds = np.ascontiguousarray(s.pool_seed[p0:p1])
+        rl = np.ascontiguousarray(read_ll[off:off + (r1 - r0) * H])
+        rs = np.ascontiguousarray(read_seed[r0:r1])
+        cr = None if copy_read is None else np.ascontiguousarray(copy_read[r0:r1])
+        hm = None
+        if hap_mask_all:
+            hm = np.ascontiguousarray(np.ctypeslib.as_array(hap_mask_all, shape=(int(s.locus_hap_off[-1]),))[s.locus_hap_off[l]:s.locus_hap_off[l + 1]])
+        o.oracle_scatter_pool_lls(r1 - r0, H, ptr(pl, c_f64p), ptr(seeds, c_i32p),
+                                  ptr(np.ascontiguousarray(s.pool_index[r0:r1]), c_i32p),
+                                  ptr(np.ascontiguousarray(s.second_mate[r0:r1]), c_u8p), ptr(cr, c_u8p), ptr(hm, c_u8p),
+                                  ptr(rl, c_f64p), ptr(rs, c_i32p))
+        read_ll[off:off + (r1 - r0) * H] = rl
+        read_seed[r0:r1] = rs
+        off += (r1 - r0) * H
+    post, sll, best, tot = checkers.posteriors(o, "oracle_", s.locus_read_off, s.locus_sample_off, s.n_haps, s.haploid,
+                                               read_ll, s.log_p1, s.log_p2, s.sample_label, s.read_weight)
+    return dict(read_ll=read_ll, read_seed=read_seed, post=post, sample_ll=sll, best=best, total_ll=tot)
+
+
+@pytest.mark.parametrize("name", ["cfg1_plumbing", "cfg2_shape", "mates", "period3_noisy"])
+def test_genotype_batch_host(ctx, name):
+    s = cases.synth(name)
+    want = _oracle_genotype(s)
+    got = ctx.genotype_host(s.batch, s.reads_batch(), int(s.read_ll_size), int(s.n_reads), int(s.post_size),
+                            int(s.locus_sample_off[-1]), s.n_loci)
+    assert np.array_equal(got["read_ll"], want["read_ll"])
+    assert np.array_equal(got["read_seed"], want["read_seed"])
+    assert np.abs(got["post"] - want["post"]).max() <= 1e-9
+    assert np.abs(got["sample_ll"] - want["sample_ll"]).max() <= 1e-9
+    assert np.abs(got["total_ll"] - want["total_ll"]).max() <= 1e-8
+    assert np.array_equal(got["best"], want["best"])
+    h2d, d2h, launches = ctx.traffic()
+    assert h2d > 0 and d2h >= got["read_ll"].nbytes and launches >= 3
+
+
+def test_genotype_batch_resident_and_copy_read_mask(ctx):
+    import torch
+    s = cases.synth("mates")
+    rng = np.random.default_rng(1)
+    # resident path == host path
+    want = ctx.genotype_host(s.batch, s.reads_batch(), int(s.read_ll_size), int(s.n_reads), int(s.post_size),
+                             int(s.locus_sample_off[-1]), s.n_loci)
+    h = ctx.upload_genotype(s.batch, s.reads_batch())
+    S = int(s.locus_sample_off[-1])
+    t = dict(read_ll=torch.zeros(int(s.read_ll_size), dtype=torch.float64, device="cuda:0"),
+             read_seed=torch.zeros(int(s.n_reads), dtype=torch.int32, device="cuda:0"),
+             post=torch.zeros(int(s.post_size), dtype=torch.float64, device="cuda:0"),
+             sample_ll=torch.zeros(S, dtype=torch.float64, device="cuda:0"),
+             best=torch.zeros(2 * S, dtype=torch.int32, device="cuda:0"),
+             total_ll=torch.zeros(s.n_loci, dtype=torch.float64, device="cuda:0"))
+    ctx.genotype_dev(h, *[t[k].data_ptr() for k in ("read_ll", "read_seed", "post", "sample_ll", "best", "total_ll")])
+    torch.cuda.synchronize()
+    ctx.free_genotype(h)
+    for k in ("read_ll", "read_seed", "post", "sample_ll", "total_ll"):
+        assert np.array_equal(t[k].cpu().numpy(), want[k]), k
+    assert np.array_equal(t["best"].cpu().numpy().reshape(-1, 2), want["best"])
+    # copy_read mask: excluded reads keep the caller's read_ll / read_seed content
+    copy_read = (rng.random(s.n_reads) < 0.7).astype(np.uint8)
+    base = -rng.uniform(1, 50, int(s.read_ll_size))
+    ref = _oracle_genotype(s, copy_read=copy_read, read_ll0=base)
+    got = ctx.genotype_host(s.batch, s.reads_batch(copy_read), int(s.read_ll_size), int(s.n_reads), int(s.post_size),
+                            S, s.n_loci, read_ll=base.copy(), read_seed=np.full(s.n_reads, -2, np.int32))
+    assert np.array_equal(got["read_ll"], ref["read_ll"])
+    assert np.array_equal(got["read_seed"], ref["read_seed"])
+    assert np.array_equal(got["best"], ref["best"])
