@@ -134,6 +134,29 @@ int pick_variant(int n_left, int n_right) {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Bases travel to the device as codes 0..4 = A,C,G,T,N.  The reference compares raw characters
+// (HapAligner.cpp:115,149); restricted to this alphabet that is the same relation.
+inline int base_code(char c) {
+  switch (c) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': return 3;
+    case 'N': return 4;
+    default: return -1;
+  }
+}
+// appends the codes of [b, e) to dst; false if a character is outside ACGTN
+template <class It, class V>
+bool append_codes(V& dst, It b, It e) {
+  for (; b != e; ++b) {
+    const int x = base_code(*b);
+    if (x < 0) return false;
+    dst.push_back((typename V::value_type)x);
+  }
+  return true;
+}
+
 }  // namespace
 
 int64_t count_alignments(const hipstr_align_batch_t* b) {
@@ -206,7 +229,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
             DevRep r;
             std::memset(&r, 0, sizeof(r));
             r.seq_off = (int32_t)out.hapbytes.size();
-            out.hapbytes.insert(out.hapbytes.end(), op.seq[s].begin(), op.seq[s].end());
+            if (!append_codes(out.hapbytes, op.seq[s].begin(), op.seq[s].end())) { err = "haplotype bases must be A,C,G,T or N"; return HIPSTR_ERR_UNSUPPORTED; }
             r.len = B;
             r.period = p;
             r.n_del = n_del;
@@ -269,7 +292,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
         hs.seq_off = (int32_t)out.hapbytes.size();
         int len = 0;
         for (int k = 0; k < nb; k++) {
-          out.hapbytes.insert(out.hapbytes.end(), opt[k]->seq[side].begin(), opt[k]->seq[side].end());
+          if (!append_codes(out.hapbytes, opt[k]->seq[side].begin(), opt[k]->seq[side].end())) { err = "haplotype bases must be A,C,G,T or N"; return HIPSTR_ERR_UNSUPPORTED; }
           len += (int)opt[k]->seq[side].size();
         }
         hs.len = len;
@@ -333,8 +356,8 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
       dp.hap_rec0 = hap_rec0;
       dp.n_haps = (int32_t)H;
       const int padded = round_up(std::max(n, 1), 16);
-      out.bases.insert(out.bases.end(), b->pool_bases + s0, b->pool_bases + s0 + n);
-      out.bases.resize(out.bases.size() + (padded - n), 'N');
+      if (!append_codes(out.bases, b->pool_bases + s0, b->pool_bases + s0 + n)) { err = "read bases must be A,C,G,T or N"; return HIPSTR_ERR_UNSUPPORTED; }
+      out.bases.resize(out.bases.size() + (padded - n), 4);
       out.quals.insert(out.quals.end(), b->pool_quals + s0, b->pool_quals + s0 + n);
       out.quals.resize(out.quals.size() + (padded - n), '!');
       const int pool_id = (int)out.pools.size();

@@ -48,75 +48,138 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 // ------------------------------------------------------------------------------------------
 // Repeat-block evaluator: one (read side, repeat allele).  Everything is anchored at the right
 // ends like the reference: column q of the side pairs with allele base B-1 when it is the last
-// base of the block.
+// base of the block.  Bases are 0..4 codes (A,C,G,T,N); val[q*5 + x] is the emission
+// log-likelihood of read column q against haplotype base x (log_correct if equal, else
+// log_error), so an emission is ONE shared-memory load.
 // ------------------------------------------------------------------------------------------
 struct RepCtx {
-  const uint8_t* s;        // oriented allele sequence (global, read-only)
+  const uint8_t* s;        // oriented allele base codes (global, read-only)
   const uint16_t* runs;    // upstream_match_lengths_ tables, [max(n_del,1)][B]
   const double* int_logs;  // global
-  const double2* lcw;      // shared: {log_correct, log_error} by READ index
-  const uint8_t* rbase;    // shared: read bases by READ index
+  const double* val;       // shared: emission table of this side, [n_side][5]
+  const uint8_t* code;     // shared: read base codes of this side
   const double* match;     // shared: match_probs_ by side column
-  int B, p, n_del;
-  int n_side;              // columns of this side
-  int rev, n_read;         // read index of side column q = rev ? n_read-1-q : q
+  int B, p, n_side;
 
-  __device__ __forceinline__ double emit(int q, int b) const {
-    const int r = rev ? n_read - 1 - q : q;
-    const double2 v = lcw[r];
-    return rbase[r] == __ldg(s + b) ? v.x : v.y;
-  }
-  __device__ __forceinline__ double lc(int q) const { return lcw[rev ? n_read - 1 - q : q].x; }
+  __device__ __forceinline__ double emit(int q, int b) const { return val[q * 5 + __ldg(s + b)]; }
+  __device__ __forceinline__ double emit_code(int q, int x) const { return val[q * 5 + x]; }
+  __device__ __forceinline__ double lc(int q) const { return val[q * 5 + code[q]]; }
 };
 
 // match_probs_[q] of StutterAlignerClass::load_read (StutterAlignerClass.cpp:12-53).
-__device__ double rep_match_prob(const RepCtx& c, int q) {
+__device__ __forceinline__ double rep_match_prob(const RepCtx& c, int q) {
   const int terms = min(q + 1, c.B);
   double acc = 0.0;
   for (int t = 0; t < terms; t++) acc += c.emit(q - t, c.B - 1 - t);
   return acc;
 }
 
-// Terms of align_pcr_insertion_reverse (StutterAlignerClass.cpp:59-104) after the first one.
-// pass 0 returns the maximum term, pass 1 the sum of coarse_exp(term - mx).
-__device__ __noinline__ double rep_insertion(const RepCtx& c, int base_len, int j, int D, double lp0) {
+// Sinks for the terms of one fast_log_sum_exp(vector) call (mathops.cpp:97-106).
+// CandSink does it in ONE pass: a term can only contribute if it is within LOG_THRESH of the
+// final maximum, hence of the running maximum at the time it is produced (the subtraction is
+// monotone in the maximum, also after rounding), so only those few are kept, in registers.
+// If more than 4 are alive at once the caller falls back to a second (sum) pass.
+struct CandSink {
+  // four most recent candidates, newest first; an evicted candidate that could still matter
+  // (within the threshold of the current maximum) sets `lost` and the caller falls back
+  double mx, c0, c1, c2, c3;
+  bool lost;
+  __device__ __forceinline__ void first(double t) { mx = t; c0 = t; c1 = c2 = c3 = -1.0e300; lost = false; }
+  __device__ __forceinline__ void push(double t) {
+    mx = dmax(mx, t);
+    if (t - mx > HIPSTR_LOG_THRESH) {
+      if (c3 - mx > HIPSTR_LOG_THRESH) lost = true;
+      c3 = c2; c2 = c1; c1 = c0; c0 = t;
+    }
+  }
+  __device__ __forceinline__ bool overflow() const { return lost; }
+  __device__ __forceinline__ double finish() const {
+    double total = lse_term(c0, mx);
+    if (c1 - mx > HIPSTR_LOG_THRESH) total += lse_term(c1, mx);
+    if (c2 - mx > HIPSTR_LOG_THRESH) total += lse_term(c2, mx);
+    if (c3 - mx > HIPSTR_LOG_THRESH) total += lse_term(c3, mx);
+    return lse_finish(mx, total);
+  }
+};
+struct MaxSink {
+  double mx;
+  __device__ __forceinline__ void first(double t) { mx = t; }
+  __device__ __forceinline__ void push(double t) { mx = dmax(mx, t); }
+};
+struct SumSink {
+  double mx, total;
+  __device__ __forceinline__ void first(double t) { total = lse_term(t, mx); }
+  __device__ __forceinline__ void push(double t) { total += lse_term(t, mx); }
+};
+
+// Terms of align_pcr_insertion_reverse (StutterAlignerClass.cpp:59-104): insertion of D = k*period
+// bases that copy the period bases upstream, summed over insertion positions; runs of positions
+// with identical likelihood are collapsed with int_log(run length).
+template <class Sink>
+__device__ __forceinline__ void insertion_terms(const RepCtx& c, int base_len, int j, int D, double lp, Sink& sink) {
   const uint16_t* runs = c.runs;   // lag = period
   const int B = c.B, p = c.p;
   const int stop = -min(max(0, base_len - D), B);
-  double mx = lp0, total = 0.0;
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    double lp = lp0;
-    if (pass) total = lse_term(lp, mx);
-    int i = 0;
-    for (; i > stop; i--) {
-      const int b = B - 1 + i;
-      double term = lp;
-      if (-i + p < B) {
-        const int run = __ldg(runs + b);
-        if (run == 0) {
-          for (int idx = i - p; idx >= i - D; idx -= p) {
-            lp -= c.emit(j + idx, b);
-            lp += c.emit(j + idx, b - p);
-          }
-          term = lp;
-        } else {
-          term = __ldg(c.int_logs + run) + lp;
-          i -= run - 1;
+  sink.first(lp);
+  int i = 0;
+  for (; i > stop; i--) {
+    const int b = B - 1 + i;
+    double term = lp;
+    if (-i + p < B) {
+      const int run = __ldg(runs + b);
+      if (run == 0) {
+        const int x_old = __ldg(c.s + b), x_new = __ldg(c.s + b - p);
+        const double* col = c.val + (j + i - p) * 5;
+        for (int idx = i - p; idx >= i - D; idx -= p, col -= p * 5) {
+          lp -= col[x_old];
+          lp += col[x_new];
         }
+        term = lp;
+      } else {
+        term = __ldg(c.int_logs + run) + lp;
+        i -= run - 1;
       }
-      if (pass) total += lse_term(term, mx); else mx = dmax(mx, term);
     }
-    if (i > -B) {
-      const double term = __ldg(c.int_logs + (B + i)) + lp;
-      if (pass) total += lse_term(term, mx); else mx = dmax(mx, term);
-    }
+    sink.push(term);
   }
-  return lse_finish(mx, total);
+  if (i > -B) sink.push(__ldg(c.int_logs + (B + i)) + lp);
 }
 
-// align_pcr_deletion_reverse (StutterAlignerClass.cpp:106-150), D < 0, k = -D/period.
-__device__ __noinline__ double rep_deletion(const RepCtx& c, int base_len, int j, int D, int k) {
+// align_pcr_deletion_reverse (StutterAlignerClass.cpp:106-150), D < 0.
+template <class Sink>
+__device__ __forceinline__ void deletion_terms(const RepCtx& c, const uint16_t* runs, int base_len, int j, int D, double lp, Sink& sink) {
+  const int B = c.B;
+  sink.first(lp);
+  int i = 0;
+  for (; i > -base_len; i--) {
+    const int b = B - 1 + i;
+    const int run = __ldg(runs + b);
+    double term;
+    if (run == 0) {
+      const double* col = c.val + (j + i) * 5;
+      lp -= col[__ldg(c.s + b + D)];
+      lp += col[__ldg(c.s + b)];
+      term = lp;
+    } else {
+      term = __ldg(c.int_logs + run) + lp;
+      i -= run - 1;
+    }
+    sink.push(term);
+  }
+  if (-i < B + D) sink.push(__ldg(c.int_logs + (B + D + i)) + lp);
+}
+
+__device__ __forceinline__ double rep_insertion(const RepCtx& c, int base_len, int j, int D, double lp0) {
+  CandSink cs;
+  insertion_terms(c, base_len, j, D, lp0, cs);
+  if (!cs.overflow()) return cs.finish();
+  SumSink ss;
+  ss.mx = cs.mx;
+  insertion_terms(c, base_len, j, D, lp0, ss);
+  return lse_finish(ss.mx, ss.total);
+}
+
+__device__ __forceinline__ double rep_deletion(const RepCtx& c, int base_len, int j, int D, int k) {
   const int B = c.B;
   const uint16_t* runs = c.runs + (size_t)(k - 1) * B;
   double lp0 = -__ldg(c.int_logs + (B + D + 1));
@@ -126,75 +189,69 @@ __device__ __noinline__ double rep_deletion(const RepCtx& c, int base_len, int j
     // k*period terms of the same right-anchored sum, recomputed here instead of stored
     double pre = 0.0;
     const int terms = -D;
-    for (int t = 0; t < terms; t++) pre += c.emit(q - t, B - 1 - t);
+    const double* col = c.val + q * 5;
+    const uint8_t* sb = c.s + B - 1;
+    for (int t = 0; t < terms; t++, col -= 5, sb--) pre += col[__ldg(sb)];
     lp0 += c.match[q] - pre;
   } else {
     for (int t = 0; t < base_len; t++) lp0 += c.emit(j - t, B - 1 - t + D);
   }
-  double mx = lp0, total = 0.0;
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    double lp = lp0;
-    if (pass) total = lse_term(lp, mx);
-    int i = 0;
-    for (; i > -base_len; i--) {
-      const int b = B - 1 + i;
-      const int run = __ldg(runs + b);
-      double term;
-      if (run == 0) {
-        lp -= c.emit(j + i, b + D);
-        lp += c.emit(j + i, b);
-        term = lp;
-      } else {
-        term = __ldg(c.int_logs + run) + lp;
-        i -= run - 1;
-      }
-      if (pass) total += lse_term(term, mx); else mx = dmax(mx, term);
-    }
-    if (-i < B + D) {
-      const double term = __ldg(c.int_logs + (B + D + i)) + lp;
-      if (pass) total += lse_term(term, mx); else mx = dmax(mx, term);
-    }
-  }
-  return lse_finish(mx, total);
+  CandSink cs;
+  deletion_terms(c, runs, base_len, j, D, lp0, cs);
+  if (!cs.overflow()) return cs.finish();
+  SumSink ss;
+  ss.mx = cs.mx;
+  deletion_terms(c, runs, base_len, j, D, lp0, ss);
+  return lse_finish(ss.mx, ss.total);
 }
 
-// One column of the repeat block's last row: HapAligner.cpp:76-100.
-__device__ double rep_column(const RepCtx& c, const DevRep* rep, const double* prev_row, int j) {
+// One column of the repeat block's last row: HapAligner.cpp:76-100.  The 13 artifact sizes are
+// evaluated by two rolled loops (deletions, insertions) so the evaluator code exists once; their
+// results wait in a small per-thread array for the final log-sum-exp.
+__device__ __forceinline__ double rep_column(const RepCtx& c, const DevRep* rep, const double* prev_row, int j) {
   const int B = c.B, p = c.p;
   double probs[HIPSTR_NUM_ARTIFACTS];
+#pragma unroll 1
+  for (int k = HIPSTR_MAX_ARTIFACT_UNITS; k >= 1; k--) {   // deletions of k units
+    const int D = -k * p;
+    const int base_len = min(B + D, j + 1);
+    double v = IMPOSSIBLE;
+    if (base_len >= 0) {
+      const double pr = rep_deletion(c, base_len, j, D, k);
+      const double pre = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
+      v = __ldg(rep->art + (HIPSTR_MAX_ARTIFACT_UNITS - k)) + pr + pre;
+    }
+    probs[HIPSTR_MAX_ARTIFACT_UNITS - k] = v;
+  }
+  {
+    const int base_len = min(B, j + 1);
+    const double pre = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
+    probs[HIPSTR_MAX_ARTIFACT_UNITS] = __ldg(rep->art + HIPSTR_MAX_ARTIFACT_UNITS) + c.match[j] + pre;
+  }
   double ins_acc = 0.0;    // ins_probs_ running sum (StutterAlignerClass.cpp:38-51)
   int ins_t = 0;
-#pragma unroll
-  for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) {
-    const int units = a - HIPSTR_MAX_ARTIFACT_UNITS;
-    const int D = units * p;
+  const double ins_prior = -__ldg(c.int_logs + (B + 1));
+#pragma unroll 1
+  for (int k = 1; k <= HIPSTR_MAX_ARTIFACT_UNITS; k++) {    // insertions of k units
+    const int D = k * p;
     const int base_len = min(B + D, j + 1);
-    if (base_len < 0) { probs[a] = IMPOSSIBLE; continue; }
-    double pr;
-    if (units == 0)
-      pr = c.match[j];
-    else if (units < 0)
-      pr = rep_deletion(c, base_len, j, D, -units);
-    else {
-      // extend the periodic-copy sum to `units` copies (at most j+1 read bases exist)
-      const int upto = min(D, j + 1);
-      for (; ins_t < upto; ins_t++) {
-        const int m = ins_t % p;
-        ins_acc += (m < B) ? c.emit(j - ins_t, B - 1 - m) : c.lc(j - ins_t);
-      }
-      double lp0 = -__ldg(c.int_logs + (B + 1)) + ins_acc;
-      lp0 += (base_len > D) ? c.match[j - D] : 0.0;
-      pr = rep_insertion(c, base_len, j, D, lp0);
+    // extend the periodic-copy sum to k copies (at most j+1 read bases exist)
+    const int upto = min(D, j + 1);
+    for (; ins_t < upto; ins_t++) {
+      const int m = ins_t % p;
+      ins_acc += (m < B) ? c.emit(j - ins_t, B - 1 - m) : c.lc(j - ins_t);
     }
+    double lp0 = ins_prior + ins_acc;
+    lp0 += (base_len > D) ? c.match[j - D] : 0.0;
+    const double pr = rep_insertion(c, base_len, j, D, lp0);
     const double pre = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
-    probs[a] = __ldg(rep->art + a) + pr + pre;
+    probs[HIPSTR_MAX_ARTIFACT_UNITS + k] = __ldg(rep->art + HIPSTR_MAX_ARTIFACT_UNITS + k) + pr + pre;
   }
   double mx = probs[0];
-#pragma unroll
+#pragma unroll 1
   for (int a = 1; a < HIPSTR_NUM_ARTIFACTS; a++) mx = dmax(mx, probs[a]);
   double total = 0.0;
-#pragma unroll
+#pragma unroll 1
   for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) total += lse_term(probs[a], mx);
   return lse_finish(mx, total);
 }
@@ -203,13 +260,13 @@ __device__ double rep_column(const RepCtx& c, const DevRep* rep, const double* p
 // K1
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t align_smem_doubles(int n_max, int l_max) {
-  // lcw[2N] run[N] rowbuf[N] rowout[N] match[N] last[2L] bases[N/8]
-  return (size_t)6 * n_max + 2 * (size_t)l_max + n_max / 8;
+  // val[5N] run[N] rowbuf[N] rowout[N] match[N] last[2L] code[N bytes]
+  return (size_t)9 * n_max + 2 * (size_t)l_max + n_max / 8;
 }
 size_t align_smem_bytes(int n_max, int l_max) { return align_smem_doubles(n_max, l_max) * 8 * HIPSTR_WARPS_PER_CTA; }
 
 template <int C>
-__global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA) k_align(const AlignParams P) {
+__global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <= 8 ? 12 : 8)) / HIPSTR_WARPS_PER_CTA) k_align(const AlignParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -229,34 +286,44 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA) k_align(const Align
 
   const int N = P.n_max, L = P.l_max;
   double* wbase = reinterpret_cast<double*>(smem_raw) + (size_t)wib * align_smem_doubles(N, L);
-  double2* s_lcw = reinterpret_cast<double2*>(wbase);
-  double* s_run = wbase + 2 * N;
+  double* s_val = wbase;               // [column g][5]: emission of column g against base code x
+  double* s_run = s_val + 5 * N;
   double* s_rowbuf = s_run + N;
   double* s_rowout = s_rowbuf + N;
   double* s_match = s_rowout + N;
   double* s_last = s_match + N;
-  uint8_t* s_base = reinterpret_cast<uint8_t*>(s_last + 2 * L);
+  uint8_t* s_code = reinterpret_cast<uint8_t*>(s_last + 2 * L);
 
   const int n = pool.len, seed = pool.seed;
   const int nL = seed, nR = n - seed - 1;
-  // stage the read: bases + per-base log-likelihoods (HapAligner.cpp:579-585)
+  // Stage the read in SIDE order: columns 0..nL-1 are read bases 0..seed-1 (left of the seed, aligned
+  // to the forward haplotype), columns nL..n-2 are read bases n-1..seed+1 (right of the seed,
+  // reversed, aligned to the reversed haplotype), HapAligner.cpp:579-585,606-609.
   for (int i = lane; i < n; i += 32) {
+    if (i == seed) continue;
+    const int g = i < seed ? i : nL + (n - 1 - i);
     const uint8_t q = (uint8_t)P.quals[pool.seq_off + i];
-    s_base[i] = (uint8_t)P.bases[pool.seq_off + i];
-    s_lcw[i] = make_double2(__ldg(P.qual_lut + 2 * q), __ldg(P.qual_lut + 2 * q + 1));
+    const uint8_t x = (uint8_t)P.bases[pool.seq_off + i];
+    const double ok = __ldg(P.qual_lut + 2 * q), bad = __ldg(P.qual_lut + 2 * q + 1);
+    s_code[g] = x;
+#pragma unroll
+    for (int y = 0; y < 5; y++) s_val[g * 5 + y] = (y == x) ? ok : bad;
   }
+  const uint8_t seed_code = (uint8_t)P.bases[pool.seq_off + seed];
+  const uint8_t seed_q = (uint8_t)P.quals[pool.seq_off + seed];
+  const double seed_ok = __ldg(P.qual_lut + 2 * seed_q), seed_bad = __ldg(P.qual_lut + 2 * seed_q + 1);
   __syncwarp();
   // running sums of log_correct from each read end towards the seed (row 0 of either matrix,
   // HapAligner.cpp:33-42); strictly sequential adds, one lane per side
   double edge = 0.0;
   if (lane < 2) {
     const int cnt = lane ? nR : nL;
-    double* dst = s_run + (lane ? nL : 0);
+    const int g0 = lane ? nL : 0;
     double acc = 0.0;
 #pragma unroll 4
     for (int j = 0; j < cnt; j++) {
-      dst[j] = acc;
-      acc += s_lcw[lane ? n - 1 - j : j].x;
+      s_run[g0 + j] = acc;
+      acc += s_val[(g0 + j) * 5 + s_code[g0 + j]];
     }
     edge = acc;
   }
@@ -278,13 +345,13 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA) k_align(const Align
   for (int cc = 0; cc < C; cc++) {
     const int j = j0 + cc;
     const bool ok = lane_on && j < ncol;
-    const int r = ok ? (side ? n - 1 - j : j) : 0;
-    const double2 v = s_lcw[r];
-    lc[cc] = v.x; lw[cc] = v.y; bs[cc] = s_base[r];
+    const int g = ok ? gbase + j : 0;
+    const uint8_t x = s_code[g];
+    bs[cc] = x;
+    lc[cc] = s_val[g * 5 + x];
+    lw[cc] = s_val[g * 5 + (x == 0 ? 1 : 0)];
   }
   const int last_cc = (lane_on && ncol - 1 >= j0 && ncol - 1 < j0 + C) ? ncol - 1 - j0 : -1;
-  const uint8_t seed_base = s_base[seed];
-  const double2 seed_lcw = s_lcw[seed];
 
   for (int h = job.h0; h < job.h1; h++) {
     const int hap_index = (pool.hap_rec0 >> 1) + h;
@@ -362,10 +429,13 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA) k_align(const Align
 
       // ---------------- repeat block: one super-row (HapAligner.cpp:62-109) --------------------
       if (blkF.rep >= 0 || blkR.rep >= 0) {
-        if (lane_on && blk.rep >= 0) {
+        if (lane_on) {   // park the row above the block (a side that is in a flank block parks M and D)
 #pragma unroll
           for (int cc = 0; cc < C; cc++)
-            if (j0 + cc < ncol) s_rowbuf[gbase + j0 + cc] = Mp[cc];
+            if (j0 + cc < ncol) {
+              s_rowbuf[gbase + j0 + cc] = Mp[cc];
+              if (blk.rep < 0) s_rowout[gbase + j0 + cc] = Dp[cc];
+            }
         }
         __syncwarp();
         // pass 1: match_probs_ of every column of the sides that are in a repeat block
@@ -376,9 +446,8 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA) k_align(const Align
           const DevRep* rep = P.reps + gb.rep;
           RepCtx c;
           c.s = P.hapbytes + rep->seq_off; c.runs = P.runs + rep->runs_off; c.int_logs = P.int_logs;
-          c.lcw = s_lcw; c.rbase = s_base; c.match = s_match + (gs ? nL : 0);
-          c.B = rep->len; c.p = rep->period; c.n_del = rep->n_del;
-          c.n_side = gs ? nR : nL; c.rev = gs; c.n_read = n;
+          c.val = s_val + (gs ? nL : 0) * 5; c.code = s_code + (gs ? nL : 0); c.match = s_match + (gs ? nL : 0);
+          c.B = rep->len; c.p = rep->period; c.n_side = gs ? nR : nL;
           s_match[g] = rep_match_prob(c, g - (gs ? nL : 0));
         }
         __syncwarp();
@@ -390,18 +459,29 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA) k_align(const Align
           const DevRep* rep = P.reps + gb.rep;
           RepCtx c;
           c.s = P.hapbytes + rep->seq_off; c.runs = P.runs + rep->runs_off; c.int_logs = P.int_logs;
-          c.lcw = s_lcw; c.rbase = s_base; c.match = s_match + (gs ? nL : 0);
-          c.B = rep->len; c.p = rep->period; c.n_del = rep->n_del;
-          c.n_side = gs ? nR : nL; c.rev = gs; c.n_read = n;
+          c.val = s_val + (gs ? nL : 0) * 5; c.code = s_code + (gs ? nL : 0); c.match = s_match + (gs ? nL : 0);
+          c.B = rep->len; c.p = rep->period; c.n_side = gs ? nR : nL;
           s_rowout[g] = rep_column(c, rep, s_rowbuf + (gs ? nL : 0), g - (gs ? nL : 0));
         }
         __syncwarp();
-        if (lane_on && blk.rep >= 0) {
+        // every lane re-reads its column constants: nothing of the flank state has to stay in
+        // registers across the evaluator above
 #pragma unroll
-          for (int cc = 0; cc < C; cc++) {
-            if (j0 + cc < ncol) Mp[cc] = s_rowout[gbase + j0 + cc];
+        for (int cc = 0; cc < C; cc++) {
+          const int j = j0 + cc;
+          const bool ok = lane_on && j < ncol;
+          const int g = ok ? gbase + j : 0;
+          const uint8_t x = s_code[g];
+          bs[cc] = x;
+          lc[cc] = s_val[g * 5 + x];
+          lw[cc] = s_val[g * 5 + (x == 0 ? 1 : 0)];
+          if (blk.rep >= 0) {
+            Mp[cc] = ok ? s_rowout[g] : 0.0;
             Dp[cc] = IMPOSSIBLE;
             if (cc == last_cc) s_last[side * L + blk.row_start + blk.len - 1] = Mp[cc];
+          } else {   // this side is not in a repeat block at this block index: state was parked
+            Mp[cc] = ok ? s_rowbuf[g] : 0.0;
+            Dp[cc] = ok ? s_rowout[g] : 0.0;
           }
         }
         __syncwarp();
@@ -423,14 +503,14 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA) k_align(const Align
         double v;
         int rank;
         if (it == 0) {
-          v = prior + (seed_base == __ldg(fseq) ? seed_lcw.x : seed_lcw.y) + edgeL + lastR[hlen - 2];
+          v = prior + (seed_code == __ldg(fseq) ? seed_ok : seed_bad) + edgeL + lastR[hlen - 2];
           rank = 0;
         } else if (it == hlen - 1) {
-          v = prior + (seed_base == __ldg(fseq + hlen - 1) ? seed_lcw.x : seed_lcw.y) + edgeR + lastL[hlen - 2];
+          v = prior + (seed_code == __ldg(fseq + hlen - 1) ? seed_ok : seed_bad) + edgeR + lastL[hlen - 2];
           rank = 1;
         } else {
           if (__ldg(frow + it) & HIPSTR_ROW_REPEAT) continue;
-          v = prior + (seed_base == __ldg(fseq + it) ? seed_lcw.x : seed_lcw.y) + lastL[it - 1] + lastR[hlen - it - 2];
+          v = prior + (seed_code == __ldg(fseq + it) ? seed_ok : seed_bad) + lastL[it - 1] + lastR[hlen - it - 2];
           rank = it + 1;
         }
         if (v > vmax || (v == vmax && rank < vrank)) { vmax = v; vrank = rank; }
@@ -445,12 +525,12 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA) k_align(const Align
       for (int it = lane; it < hlen; it += 32) {
         double v;
         if (it == 0)
-          v = prior + (seed_base == __ldg(fseq) ? seed_lcw.x : seed_lcw.y) + edgeL + lastR[hlen - 2];
+          v = prior + (seed_code == __ldg(fseq) ? seed_ok : seed_bad) + edgeL + lastR[hlen - 2];
         else if (it == hlen - 1)
-          v = prior + (seed_base == __ldg(fseq + hlen - 1) ? seed_lcw.x : seed_lcw.y) + edgeR + lastL[hlen - 2];
+          v = prior + (seed_code == __ldg(fseq + hlen - 1) ? seed_ok : seed_bad) + edgeR + lastL[hlen - 2];
         else {
           if (__ldg(frow + it) & HIPSTR_ROW_REPEAT) continue;
-          v = prior + (seed_base == __ldg(fseq + it) ? seed_lcw.x : seed_lcw.y) + lastL[it - 1] + lastR[hlen - it - 2];
+          v = prior + (seed_code == __ldg(fseq + it) ? seed_ok : seed_bad) + lastL[it - 1] + lastR[hlen - it - 2];
         }
         total += lse_term(v, vmax);
       }

@@ -12,10 +12,11 @@ print("synth %.1fs pools=%d out=%d" % (time.time() - t, s.n_pools, s.n_out))
 ctx = hb.Context(0)
 t = time.time(); h = ctx.upload(s.batch); print("upload %.2fs" % (time.time() - t))
 out = torch.zeros(s.n_out, dtype=torch.float64, device="cuda:0")
-ctx.lib.hipstr_enable_timing(ctx.h, 1)
-for i in range(4):
+ctx.enable_timing(True)
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+for i in range(reps):
     ctx.align_dev(h, out.data_ptr())
-    ms = ctx.lib.hipstr_last_kernel_ms(ctx.h)
+    ms = ctx.collect_timing()[0]
     print("run %d: %.2f ms  %.3f M aln/s  launches=%d" % (i, ms, s.n_out / ms / 1e3, ctx.lib.hipstr_last_launch_count(ctx.h)))
 t = time.time(); ll = ctx.align_host(s.batch, s.n_out); print("host path %.3fs" % (time.time() - t))
 print("checksum", float(out.sum()), float(ll.sum()))
