@@ -324,12 +324,16 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
           }
           row += n;
         }
-        if (first_repeat_row < 0) first_repeat_row = len;
-        std::string key((const char*)out.hapbytes.data() + hs.seq_off, first_repeat_row);
-        key.append((const char*)rows, first_repeat_row);
-        auto it = seg1_ids[side].find(key);
-        if (it == seg1_ids[side].end()) it = seg1_ids[side].emplace(key, (int)seg1_ids[side].size()).first;
-        hs.seg1_class = it->second;
+        hs.first_rep = nb;
+        for (int k = nb - 1; k >= 0; k--) if (period[k] > 0) hs.first_rep = k;
+        hs.seg1_class = -1;
+        if (nb == 3 && period[0] == 0 && period[1] > 0 && period[2] == 0) {   // the canonical HipSTR haplotype
+          std::string key((const char*)out.hapbytes.data() + hs.seq_off, first_repeat_row);
+          key.append((const char*)rows, first_repeat_row);
+          auto it = seg1_ids[side].find(key);
+          if (it == seg1_ids[side].end()) it = seg1_ids[side].emplace(key, (int)seg1_ids[side].size()).first;
+          hs.seg1_class = it->second;
+        }
         max_len = std::max(max_len, len);
         out.hapsides.push_back(hs);
       }

@@ -86,8 +86,10 @@ struct CandSink {
   bool lost;
   __device__ __forceinline__ void first(double t) { mx = t; c0 = t; c1 = c2 = c3 = -1.0e300; lost = false; }
   __device__ __forceinline__ void push(double t) {
-    mx = dmax(mx, t);
+    // one subtract + compare for the common case (a term far below the running maximum);
+    // t > mx implies t - mx > 0 > LOG_THRESH, so the maximum update lives on the rare path too
     if (t - mx > HIPSTR_LOG_THRESH) {
+      mx = dmax(mx, t);
       if (c3 - mx > HIPSTR_LOG_THRESH) lost = true;
       c3 = c2; c2 = c1; c1 = c0; c0 = t;
     }
@@ -117,30 +119,35 @@ struct SumSink {
 // with identical likelihood are collapsed with int_log(run length).
 template <class Sink>
 __device__ __forceinline__ void insertion_terms(const RepCtx& c, int base_len, int j, int D, double lp, Sink& sink) {
-  const uint16_t* runs = c.runs;   // lag = period
   const int B = c.B, p = c.p;
   const int stop = -min(max(0, base_len - D), B);
+  const int stride = 5 * p;
+  const uint16_t* rp = c.runs + (B - 1);      // lag = period table, walked right to left
+  const uint8_t* sp = c.s + (B - 1);
+  const double* col = c.val + (j - p) * 5;     // column j + i - p at i = 0
+  const int no_left = p - B;                   // positions i <= no_left have no base `period` upstream
   sink.first(lp);
   int i = 0;
-  for (; i > stop; i--) {
-    const int b = B - 1 + i;
+  while (i > stop) {
     double term = lp;
-    if (-i + p < B) {
-      const int run = __ldg(runs + b);
+    int step = 1;
+    if (i > no_left) {
+      const int run = __ldg(rp);
       if (run == 0) {
-        const int x_old = __ldg(c.s + b), x_new = __ldg(c.s + b - p);
-        const double* col = c.val + (j + i - p) * 5;
-        for (int idx = i - p; idx >= i - D; idx -= p, col -= p * 5) {
-          lp -= col[x_old];
-          lp += col[x_new];
+        const double* ca = col + __ldg(sp);
+        const double* cb = col + __ldg(sp - p);
+        for (int m = 0; m < D; m += p, ca -= stride, cb -= stride) {
+          lp -= *ca;
+          lp += *cb;
         }
         term = lp;
       } else {
         term = __ldg(c.int_logs + run) + lp;
-        i -= run - 1;
+        step = run;
       }
     }
     sink.push(term);
+    i -= step; rp -= step; sp -= step; col -= 5 * step;
   }
   if (i > -B) sink.push(__ldg(c.int_logs + (B + i)) + lp);
 }
@@ -149,22 +156,25 @@ __device__ __forceinline__ void insertion_terms(const RepCtx& c, int base_len, i
 template <class Sink>
 __device__ __forceinline__ void deletion_terms(const RepCtx& c, const uint16_t* runs, int base_len, int j, int D, double lp, Sink& sink) {
   const int B = c.B;
+  const uint16_t* rp = runs + (B - 1);
+  const uint8_t* sp = c.s + (B - 1);
+  const double* col = c.val + j * 5;
   sink.first(lp);
   int i = 0;
-  for (; i > -base_len; i--) {
-    const int b = B - 1 + i;
-    const int run = __ldg(runs + b);
+  while (i > -base_len) {
+    const int run = __ldg(rp);
     double term;
+    int step = 1;
     if (run == 0) {
-      const double* col = c.val + (j + i) * 5;
-      lp -= col[__ldg(c.s + b + D)];
-      lp += col[__ldg(c.s + b)];
+      lp -= col[__ldg(sp + D)];
+      lp += col[__ldg(sp)];
       term = lp;
     } else {
       term = __ldg(c.int_logs + run) + lp;
-      i -= run - 1;
+      step = run;
     }
     sink.push(term);
+    i -= step; rp -= step; sp -= step; col -= 5 * step;
   }
   if (-i < B + D) sink.push(__ldg(c.int_logs + (B + D + i)) + lp);
 }
@@ -353,6 +363,8 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
   }
   const int last_cc = (lane_on && ncol - 1 >= j0 && ncol - 1 < j0 + C) ? ncol - 1 - j0 : -1;
 
+  int cached_class = -1;   // seg1_class of the rows before the first repeat block that this lane's
+                           // side currently holds in s_rowbuf / s_last (from an earlier haplotype)
   for (int h = job.h0; h < job.h1; h++) {
     const int hap_index = (pool.hap_rec0 >> 1) + h;
     if (P.hap_mask && !P.hap_mask[hap_index]) continue;
@@ -364,8 +376,15 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
     const int nb = hsF.n_blocks;
     const int hlen = hsF.len;
 
+    // Rows before the first repeat block depend only on the read and on seg1_class: when the
+    // previous haplotype of this job had the same class they are still in shared memory (the row
+    // above the repeat block in s_rowbuf, the last-column values in s_last) -- the same reuse the
+    // reference gets from walking haplotypes in Gray-code order (HapAligner.cpp:54-60).
+    const bool reuse = hs.seg1_class >= 0 && hs.seg1_class == cached_class;
+    const int first_rep = hs.first_rep;
+    cached_class = hs.seg1_class;
     // row 0 (HapAligner.cpp:33-42)
-    {
+    if (!reuse) {
       const uint8_t fc = __ldg(seq);
 #pragma unroll
       for (int cc = 0; cc < C; cc++) {
@@ -386,7 +405,7 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
       {
         const int r0 = blk.row_start + (b == 0 ? 1 : 0);
         const int nrows = blk.row_start + blk.len - r0;
-        const bool flank_on = lane_on && blk.rep < 0 && nrows > 0;
+        const bool flank_on = lane_on && blk.rep < 0 && nrows > 0 && !(reuse && b < first_rep);
         const int steps = __reduce_max_sync(FULL, flank_on ? nrows + k : 0);
         if (steps > 0) {
           double Mlp = shfl_up_d(Mp[C - 1]), Dlp = shfl_up_d(Dp[C - 1]);
@@ -429,7 +448,8 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
 
       // ---------------- repeat block: one super-row (HapAligner.cpp:62-109) --------------------
       if (blkF.rep >= 0 || blkR.rep >= 0) {
-        if (lane_on) {   // park the row above the block (a side that is in a flank block parks M and D)
+        if (lane_on && !(reuse && b == first_rep)) {   // park the row above the block (a side that is in a
+                                                        // flank block parks M and D); a reused row is already there
 #pragma unroll
           for (int cc = 0; cc < C; cc++)
             if (j0 + cc < ncol) {

@@ -47,10 +47,11 @@ struct DevHapSide {       /* 32 B */
   int32_t blk_off;        /* into blocks */
   int32_t n_blocks;
   int32_t n_seed_pos;     /* total length of flank blocks (compute_aln_logprob num_seeds) */
-  int32_t seg1_class;     /* haplotypes of a locus with equal class share every row before the
+  int32_t seg1_class;     /* >= 0: haplotypes of a locus with equal class share every row before the
                              first repeat block in this orientation (sequence AND homopolymer
-                             classes): the kernel may reuse those rows */
-  int32_t pad;
+                             classes), so the kernel reuses those rows from the previous haplotype
+                             of the job; -1: never reuse (non flank/repeat/flank structures) */
+  int32_t first_rep;      /* index of the first repeat block in this orientation (n_blocks if none) */
 };
 
 struct DevBlock {         /* 16 B */
