@@ -317,8 +317,10 @@ def main():
     # ---- end-to-end path: host buffers through the C-ABI ------------------------------------------
     e2e = None
     if not a.no_e2e:
-        read_ll = np.zeros(int(s.read_ll_size), np.float64)
-        read_seed = np.zeros(R_tot, np.int32)
+        # page-locked host buffers for the results (the inputs are staged through the library's own
+        # page-locked arena)
+        read_ll = torch.zeros(int(s.read_ll_size), dtype=torch.float64).pin_memory().numpy()
+        read_seed = torch.zeros(R_tot, dtype=torch.int32).pin_memory().numpy()
 
         def host_step():
             return ctx.genotype_host(s.batch, reads, int(s.read_ll_size), R_tot, int(s.post_size), S_tot, s.n_loci,

@@ -73,6 +73,7 @@ struct hipstr_ctx {
   float last_ms = 0.f;
   std::vector<StageEvents> pending;      // recorded, not yet read
   std::vector<StageEvents> free_events;
+  FlatBatch flat;                        // host staging (page-locked), reused by every call
   hipstr_dev_batch scratch;              // reused by hipstr_align_batch_host
   hipstr_dev_genotype gscratch;          // reused by hipstr_genotype_batch_host
   DevBuf d_ll, d_pos, d_misc[12], d_out[6];
@@ -102,6 +103,16 @@ cudaError_t put(DevBuf& d, const T* v, size_t n, cudaStream_t s) {
 }
 template <class T>
 cudaError_t put(DevBuf& d, const std::vector<T>& v, cudaStream_t s) { return put(d, v.data(), v.size(), s); }
+template <class T>
+cudaError_t put(DevBuf& d, const HostBuf<T>& v, cudaStream_t s) { return put(d, v.data(), v.size(), s); }
+
+// page-locked staging for flatten.cpp's big arrays
+void* pinned_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void pinned_free(void* p) { cudaFreeHost(p); }
 void begin_call(hipstr_ctx* c) { g_h2d = 0; c->h2d_bytes = c->d2h_bytes = 0; c->last_launches = 0; }
 void end_call(hipstr_ctx* c) { c->h2d_bytes = g_h2d; }
 template <class T>
@@ -112,9 +123,14 @@ cudaError_t get(hipstr_ctx* c, T* dst, const void* src, size_t n) {
 }
 
 hipstr_status_t stage(hipstr_ctx* ctx, const hipstr_align_batch_t* batch, hipstr_dev_batch& d) {
-  FlatBatch f;
+  FlatBatch& f = ctx->flat;
   std::string err;
-  hipstr_status_t st = flatten_batch(batch, f, err);
+  hipstr_status_t st;
+  try {
+    st = flatten_batch(batch, f, err);
+  } catch (const std::bad_alloc&) {
+    return fail(ctx, HIPSTR_ERR_CUDA, "out of (page-locked) host memory while staging the batch");
+  }
   if (st != HIPSTR_OK) return fail(ctx, st, err);
   cudaStream_t s = ctx->stream;
   CU(put(d.pools, f.pools, s));
@@ -135,7 +151,7 @@ hipstr_status_t stage(hipstr_ctx* ctx, const hipstr_align_batch_t* batch, hipstr
   d.n_out = f.n_out;
   d.n_alignments = f.n_alignments;
   d.has_mask = !f.hap_mask.empty();
-  // the staging vectors die at return: the copies above must have left pageable memory
+  // the staging buffers are reused by the next call: the copies above must have completed
   CU(cudaStreamSynchronize(s));
   return HIPSTR_OK;
 }
@@ -298,6 +314,7 @@ hipstr_status_t hipstr_create(int device, hipstr_ctx_t** out_ctx) {
     cudaGetLastError();
     return HIPSTR_ERR_NO_DEVICE;
   }
+  set_host_allocator(pinned_alloc, pinned_free);
   hipstr_ctx* ctx = new hipstr_ctx();
   ctx->device = device;
   auto bail = [&](const char* what, cudaError_t e) {

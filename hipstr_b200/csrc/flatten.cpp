@@ -17,10 +17,36 @@
 
 #include <algorithm>
 #include <cmath>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <new>
+#include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace hipstr {
+
+namespace {
+host_alloc_fn g_alloc = nullptr;
+host_free_fn g_free = nullptr;
+}
+void set_host_allocator(host_alloc_fn alloc, host_free_fn release) { g_alloc = alloc; g_free = release; }
+void* host_alloc(size_t bytes) {
+  void* p = g_alloc ? g_alloc(bytes) : std::malloc(bytes);
+  if (!p) throw std::bad_alloc();
+  return p;
+}
+void host_free(void* p) { if (g_free) g_free(p); else std::free(p); }
+
+void FlatBatch::clear() {
+  pools.clear(); bases.clear(); quals.clear();
+  hapsides.clear(); hapbytes.clear(); blocks.clear(); reps.clear(); runs.clear(); hap_mask.clear();
+  for (auto& j : jobs) j.clear();
+  n_out = n_alignments = 0;
+}
 
 HostTables::HostTables() {
   int_logs[0] = -1000;
@@ -86,6 +112,9 @@ struct Option {
   std::string seq[2];   // forward, reversed
   Runs runs[2];
   int rep[2] = {-1, -1};
+  std::vector<uint8_t> codes[2];   // base codes of seq[]
+  std::vector<uint8_t> cls0[2];    // homopolymer class of every row ignoring the neighbour blocks
+  std::vector<int> sens[2];        // rows whose class can change with the neighbour blocks
 };
 
 struct BlockInfo {
@@ -134,14 +163,16 @@ int pick_variant(int n_left, int n_right) {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// Bases travel to the device as codes 0..4 = A,C,G,T,N.  The reference compares raw characters
-// (HapAligner.cpp:115,149); restricted to this alphabet that is the same relation.
+struct LocusInfo { int32_t hap_rec0, H, max_len; int64_t live_haps; };
+// Bases travel to the device as codes 0..4.  The reference compares raw characters
+// (HapAligner.cpp:115,149); restricted to the alphabet ACGTN that is the same relation.
+// (A,C,T,G) = (c >> 1) & 3, which the bulk converter below computes without a table; N = 4.
 inline int base_code(char c) {
   switch (c) {
     case 'A': return 0;
     case 'C': return 1;
-    case 'G': return 2;
-    case 'T': return 3;
+    case 'T': return 2;
+    case 'G': return 3;
     case 'N': return 4;
     default: return -1;
   }
@@ -155,6 +186,35 @@ bool append_codes(V& dst, It b, It e) {
     dst.push_back((typename V::value_type)x);
   }
   return true;
+}
+
+// Bulk conversion of read bases to codes, 16 bytes per step (SSE2 is part of x86-64); returns
+// non-zero if a byte is outside ACGTN.
+inline unsigned convert_bases(const unsigned char* __restrict src, char* __restrict dst, int n) {
+  unsigned bad = 0;
+  int i = 0;
+#if defined(__SSE2__)
+  const __m128i cA = _mm_set1_epi8('A'), cC = _mm_set1_epi8('C'), cG = _mm_set1_epi8('G'), cT = _mm_set1_epi8('T');
+  const __m128i cN = _mm_set1_epi8('N'), three = _mm_set1_epi8(3), four = _mm_set1_epi8(4);
+  __m128i all_ok = _mm_set1_epi8((char)0xff);
+  for (; i + 16 <= n; i += 16) {
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+    const __m128i is_n = _mm_cmpeq_epi8(c, cN);
+    const __m128i ok = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(c, cA), _mm_cmpeq_epi8(c, cC)),
+                                    _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(c, cG), _mm_cmpeq_epi8(c, cT)), is_n));
+    all_ok = _mm_and_si128(all_ok, ok);
+    const __m128i acgt = _mm_and_si128(_mm_srli_epi16(c, 1), three);
+    const __m128i code = _mm_or_si128(_mm_and_si128(is_n, four), _mm_andnot_si128(is_n, acgt));
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), code);
+  }
+  bad |= (_mm_movemask_epi8(all_ok) != 0xffff);
+#endif
+  for (; i < n; i++) {
+    const int x = base_code((char)src[i]);
+    bad |= (x < 0);
+    dst[i] = (char)x;
+  }
+  return bad;
 }
 
 }  // namespace
@@ -184,11 +244,14 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     err = "null array in batch";
     return HIPSTR_ERR_BAD_ARG;
   }
+  out.clear();
   for (int v = 0; v < kNumColVariants; v++) { out.n_max[v] = 16; out.l_max[v] = 2; }
   out.n_out = b->n_loci ? b->locus_out_off[b->n_loci] : 0;
 
   int64_t total_pairs = count_alignments(b);
   out.n_alignments = total_pairs;
+  std::vector<LocusInfo> loci;
+  loci.reserve((size_t)b->n_loci);
 
   for (int l = 0; l < b->n_loci; l++) {
     const int b0 = b->locus_block_off[l], nb = b->locus_block_off[l + 1] - b0;
@@ -215,7 +278,28 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
         if (op.seq[0].empty()) { err = "empty block option"; return HIPSTR_ERR_UNSUPPORTED; }
         if (op.seq[0].size() > 60000) { err = "block option too long"; return HIPSTR_ERR_UNSUPPORTED; }
         op.seq[1].assign(op.seq[0].rbegin(), op.seq[0].rend());
-        for (int s = 0; s < 2; s++) op.runs[s].build(op.seq[s]);
+        for (int s = 0; s < 2; s++) {
+          op.runs[s].build(op.seq[s]);
+          if (!append_codes(op.codes[s], op.seq[s].begin(), op.seq[s].end())) { err = "haplotype bases must be A,C,G,T or N"; return HIPSTR_ERR_UNSUPPORTED; }
+          if (blk[k].period == 0) {
+            // class of a row = min(15, max(h(c), h(c-1))) with h the homopolymer length around the
+            // base (HapAligner.cpp:119-120).  Away from the block ends h only depends on the block.
+            const int n = (int)op.seq[s].size();
+            const Runs& r = op.runs[s];
+            std::vector<int> h0(n);
+            std::vector<char> edge(n);
+            for (int c = 0; c < n; c++) {
+              h0[c] = r.left[c] + r.right[c] + 1;
+              edge[c] = (c - r.left[c] == 0) || (c + r.right[c] == n - 1);
+            }
+            op.cls0[s].resize(n);
+            for (int c = 0; c < n; c++) {
+              const int cm = std::max(0, c - 1);
+              op.cls0[s][c] = (uint8_t)std::min(15, std::max(h0[c], h0[cm]));
+              if (edge[c] || edge[cm]) op.sens[s].push_back(c);
+            }
+          }
+        }
         if (blk[k].period > 0) {
           // StutterAlignerClass constructor (StutterAlignerClass.h:49-80) for both orientations
           const int p = blk[k].period, B = (int)op.seq[0].size();
@@ -229,7 +313,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
             DevRep r;
             std::memset(&r, 0, sizeof(r));
             r.seq_off = (int32_t)out.hapbytes.size();
-            if (!append_codes(out.hapbytes, op.seq[s].begin(), op.seq[s].end())) { err = "haplotype bases must be A,C,G,T or N"; return HIPSTR_ERR_UNSUPPORTED; }
+            out.hapbytes.insert(out.hapbytes.end(), op.codes[s].begin(), op.codes[s].end());
             r.len = B;
             r.period = p;
             r.n_del = n_del;
@@ -268,7 +352,9 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     std::vector<int32_t> cur(nb), prev(nb);
     std::vector<std::vector<uint8_t> > cached[2];   // [side][oriented block] -> classes of its rows
     cached[0].resize(nb); cached[1].resize(nb);
-    std::map<std::string, int> seg1_ids[2];
+    std::vector<int> seg1_reps[2];                  // hapside indices, one per distinct seg-1 class
+    std::vector<const Option*> opt(nb);
+    std::vector<int> period(nb);
     bool reuse = false;
     int max_len = 0;
     for (int64_t h = 0; h < H; h++) {
@@ -281,8 +367,6 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
         DevHapSide hs;
         std::memset(&hs, 0, sizeof(hs));
         if (!live) { out.hapsides.push_back(hs); continue; }   // placeholder keeps indexing dense
-        std::vector<const Option*> opt(nb);
-        std::vector<int> period(nb);
         for (int k = 0; k < nb; k++) {
           const int src = side == 0 ? k : nb - 1 - k;
           opt[k] = &blk[src].opts[cur[src]];
@@ -292,47 +376,53 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
         hs.seq_off = (int32_t)out.hapbytes.size();
         int len = 0;
         for (int k = 0; k < nb; k++) {
-          if (!append_codes(out.hapbytes, opt[k]->seq[side].begin(), opt[k]->seq[side].end())) { err = "haplotype bases must be A,C,G,T or N"; return HIPSTR_ERR_UNSUPPORTED; }
-          len += (int)opt[k]->seq[side].size();
+          out.hapbytes.insert(out.hapbytes.end(), opt[k]->codes[side].begin(), opt[k]->codes[side].end());
+          len += (int)opt[k]->codes[side].size();
         }
         hs.len = len;
         hs.row_off = (int32_t)out.hapbytes.size();
-        out.hapbytes.resize(out.hapbytes.size() + len, 0);
+        out.hapbytes.resize(out.hapbytes.size() + len, HIPSTR_ROW_REPEAT);
         uint8_t* rows = out.hapbytes.data() + hs.row_off;
         hs.blk_off = (int32_t)out.blocks.size();
         hs.n_blocks = nb;
+        hs.first_rep = nb;
         int row = 0, first_repeat_row = -1;
         for (int k = 0; k < nb; k++) {
           const int n = (int)opt[k]->seq[side].size();
           DevBlock db = {row, n, period[k] > 0 ? opt[k]->rep[side] : -1, 0};
           out.blocks.push_back(db);
           if (period[k] > 0) {
-            if (first_repeat_row < 0) first_repeat_row = row;
-            for (int c = 0; c < n; c++) rows[row + c] = HIPSTR_ROW_REPEAT;
+            if (first_repeat_row < 0) { first_repeat_row = row; hs.first_rep = k; }
           } else {
             hs.n_seed_pos += n;
             std::vector<uint8_t>& keep = cached[side][k];
             if (!(reuse && k < changed)) {   // HapAligner.cpp:54-60: these rows are recomputed now
-              keep.resize(n);
-              for (int c = 0; c < n; c++) {
+              keep = opt[k]->cls0[side];
+              for (int c : opt[k]->sens[side]) {   // rows whose run reaches a block end see the neighbours
                 const int hp = std::max(homopolymer(opt, side, k, c), homopolymer(opt, side, k, std::max(0, c - 1)));
                 keep[c] = (uint8_t)std::min(15, hp);
               }
             }
-            for (int c = 0; c < n; c++) rows[row + c] = keep[c];
+            std::memcpy(rows + row, keep.data(), (size_t)n);
             if (k > 0 && period[k - 1] > 0) rows[row] |= HIPSTR_ROW_AFTER_REPEAT;
           }
           row += n;
         }
-        hs.first_rep = nb;
-        for (int k = nb - 1; k >= 0; k--) if (period[k] > 0) hs.first_rep = k;
+        if (first_repeat_row < 0) first_repeat_row = len;
         hs.seg1_class = -1;
         if (nb == 3 && period[0] == 0 && period[1] > 0 && period[2] == 0) {   // the canonical HipSTR haplotype
-          std::string key((const char*)out.hapbytes.data() + hs.seq_off, first_repeat_row);
-          key.append((const char*)rows, first_repeat_row);
-          auto it = seg1_ids[side].find(key);
-          if (it == seg1_ids[side].end()) it = seg1_ids[side].emplace(key, (int)seg1_ids[side].size()).first;
-          hs.seg1_class = it->second;
+          const uint8_t* seq = out.hapbytes.data() + hs.seq_off;
+          for (size_t c = 0; c < seg1_reps[side].size() && hs.seg1_class < 0; c++) {
+            const DevHapSide& o = out.hapsides[seg1_reps[side][c]];
+            const int o_first = out.blocks[o.blk_off + 1].row_start;
+            if (o_first == first_repeat_row && !std::memcmp(out.hapbytes.data() + o.seq_off, seq, first_repeat_row) &&
+                !std::memcmp(out.hapbytes.data() + o.row_off, rows, first_repeat_row))
+              hs.seg1_class = (int32_t)c;
+          }
+          if (hs.seg1_class < 0) {
+            hs.seg1_class = (int32_t)seg1_reps[side].size();
+            seg1_reps[side].push_back((int)out.hapsides.size());
+          }
         }
         max_len = std::max(max_len, len);
         out.hapsides.push_back(hs);
@@ -342,45 +432,126 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     // DevHapSide offsets into hapbytes were taken while the vector was still growing: they are
     // indices, not pointers, so they stay valid.
 
-    // ---- pooled reads and jobs ----
-    int64_t live_haps = H;
-    if (mask) { live_haps = 0; for (int64_t h = 0; h < H; h++) live_haps += mask[h] != 0; }
-    // Split a pool's haplotypes over several warps only when the batch is too small to fill the GPU.
-    int chunk = (int)H;
-    if (total_pairs > 0 && total_pairs / H < 16384) chunk = (int)std::max<int64_t>(1, std::min<int64_t>(H, total_pairs / 16384));
-    for (int p = b->locus_pool_off[l]; p < b->locus_pool_off[l + 1]; p++) {
-      const int s0 = b->pool_seq_off[p], n = b->pool_seq_off[p + 1] - s0;
+    // ---- per-locus facts the pool pass needs ----
+    LocusInfo li;
+    li.hap_rec0 = hap_rec0;
+    li.H = (int32_t)H;
+    li.max_len = max_len;
+    li.live_haps = H;
+    if (mask) { li.live_haps = 0; for (int64_t h = 0; h < H; h++) li.live_haps += mask[h] != 0; }
+    loci.push_back(li);
+  }
+
+  // ---- pooled reads: offsets (serial prefix), then a threaded fill of the big byte arrays ----
+  const int n_pools = b->n_pools;
+  std::vector<int32_t> pool_off((size_t)n_pools + 1);
+  {
+    int64_t at = 0;
+    for (int p = 0; p < n_pools; p++) {
+      const int n = b->pool_seq_off[p + 1] - b->pool_seq_off[p];
       if (n < 0) { err = "pool_seq_off not monotone"; return HIPSTR_ERR_BAD_ARG; }
-      DevPool dp;
-      dp.seq_off = (int32_t)out.bases.size();
-      dp.len = n;
-      dp.seed = b->pool_seed[p];
-      dp.locus = l;
-      dp.out_off = b->locus_out_off[l] + (int64_t)(p - b->locus_pool_off[l]) * H;
-      dp.hap_rec0 = hap_rec0;
-      dp.n_haps = (int32_t)H;
-      const int padded = round_up(std::max(n, 1), 16);
-      if (!append_codes(out.bases, b->pool_bases + s0, b->pool_bases + s0 + n)) { err = "read bases must be A,C,G,T or N"; return HIPSTR_ERR_UNSUPPORTED; }
-      out.bases.resize(out.bases.size() + (padded - n), 4);
-      out.quals.insert(out.quals.end(), b->pool_quals + s0, b->pool_quals + s0 + n);
-      out.quals.resize(out.quals.size() + (padded - n), '!');
-      const int pool_id = (int)out.pools.size();
-      out.pools.push_back(dp);
-      if (b->realign_pool && !b->realign_pool[p]) continue;
-      if (dp.seed < 0) {   // HapAligner.cpp:333-337: LL 0 for every haplotype, mask ignored
-        DevJob j = {pool_id, 0, (int32_t)H, 0};
-        out.jobs[0].push_back(j);
+      pool_off[p] = (int32_t)at;
+      at += round_up(std::max(n, 1), 16);
+      if (at > 0x7fffffff) { err = "more than 2 GiB of read bases in one batch"; return HIPSTR_ERR_UNSUPPORTED; }
+    }
+    pool_off[n_pools] = (int32_t)at;
+    out.bases.resize((size_t)at);
+    out.quals.resize((size_t)at);
+    out.pools.resize((size_t)n_pools);
+  }
+  std::vector<uint8_t> pool_variant((size_t)n_pools, 255);   // 255 = no job, 254 = seedless
+  std::atomic<int> status(HIPSTR_OK);
+  auto fill = [&](int l0, int l1) {
+    for (int l = l0; l < l1 && status.load(std::memory_order_relaxed) == HIPSTR_OK; l++) {
+      const LocusInfo& li = loci[l];
+      for (int p = b->locus_pool_off[l]; p < b->locus_pool_off[l + 1]; p++) {
+        const int s0 = b->pool_seq_off[p], n = b->pool_seq_off[p + 1] - s0;
+        const int padded = pool_off[p + 1] - pool_off[p];
+        DevPool dp;
+        dp.seq_off = pool_off[p];
+        dp.len = n;
+        dp.seed = b->pool_seed[p];
+        dp.locus = l;
+        dp.out_off = b->locus_out_off[l] + (int64_t)(p - b->locus_pool_off[l]) * li.H;
+        dp.hap_rec0 = li.hap_rec0;
+        dp.n_haps = li.H;
+        out.pools[p] = dp;
+        char* bd = out.bases.data() + pool_off[p];
+        char* qd = out.quals.data() + pool_off[p];
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(b->pool_bases + s0);
+        const unsigned bad = convert_bases(src, bd, n);
+        std::memcpy(qd, b->pool_quals + s0, (size_t)n);
+        for (int i = n; i < padded; i++) { bd[i] = 4; qd[i] = '!'; }
+        if (bad) { status.store(HIPSTR_ERR_UNSUPPORTED); return; }   // a base outside ACGTN
+        if (b->realign_pool && !b->realign_pool[p]) continue;
+        if (dp.seed < 0) { pool_variant[p] = 254; continue; }
+        if (dp.seed == 0 || dp.seed >= n - 1) { status.store(HIPSTR_ERR_INVALID_SEED); return; }
+        if (li.live_haps == 0) continue;
+        const int v = pick_variant(dp.seed, n - dp.seed - 1);
+        if (v < 0) { status.store(HIPSTR_ERR_BAD_ARG + 100); return; }
+        pool_variant[p] = (uint8_t)v;
+      }
+    }
+  };
+  int n_threads = (int)std::thread::hardware_concurrency();
+  if (const char* e = std::getenv("HIPSTR_HOST_THREADS")) n_threads = std::atoi(e);
+  n_threads = std::max(1, std::min(n_threads, 32));
+  if (n_pools < 20000) n_threads = 1;
+  if (n_threads == 1) fill(0, b->n_loci);
+  else {
+    std::vector<std::thread> workers;
+    int l0 = 0;
+    for (int t = 0; t < n_threads; t++) {   // split by pool count, not locus count
+      const int64_t target = (int64_t)n_pools * (t + 1) / n_threads;
+      int l1 = l0;
+      while (l1 < b->n_loci && b->locus_pool_off[l1 + 1] <= target) l1++;
+      if (t == n_threads - 1) l1 = b->n_loci;
+      if (l1 > l0) workers.emplace_back(fill, l0, l1);
+      l0 = l1;
+    }
+    for (auto& w : workers) w.join();
+  }
+  switch (status.load()) {
+    case HIPSTR_OK: break;
+    case HIPSTR_ERR_UNSUPPORTED: err = "read bases must be A,C,G,T or N"; return HIPSTR_ERR_UNSUPPORTED;
+    case HIPSTR_ERR_INVALID_SEED: err = "invalid alignment seed"; return HIPSTR_ERR_INVALID_SEED;
+    default: err = "read longer than the kernel's limit"; return HIPSTR_ERR_UNSUPPORTED;
+  }
+
+  // ---- jobs ----
+  // Split a pool's haplotypes over several warps only when the batch is too small to fill the GPU.
+  size_t count[kNumColVariants] = {0};
+  for (int l = 0; l < b->n_loci; l++) {
+    const LocusInfo& li = loci[l];
+    int chunk = li.H;
+    if (total_pairs > 0 && total_pairs / li.H < 16384) chunk = (int)std::max<int64_t>(1, std::min<int64_t>(li.H, total_pairs / 16384));
+    const int per_pool = (li.H + chunk - 1) / chunk;
+    for (int p = b->locus_pool_off[l]; p < b->locus_pool_off[l + 1]; p++) {
+      const uint8_t v = pool_variant[p];
+      if (v == 255) continue;
+      if (v == 254) { count[0]++; continue; }
+      count[v] += per_pool;
+      out.n_max[v] = std::max(out.n_max[v], pool_off[p + 1] - pool_off[p]);
+      out.l_max[v] = std::max(out.l_max[v], round_up(li.max_len, 2));
+    }
+  }
+  size_t at[kNumColVariants];
+  for (int v = 0; v < kNumColVariants; v++) { out.jobs[v].resize(count[v]); at[v] = 0; }
+  for (int l = 0; l < b->n_loci; l++) {
+    const LocusInfo& li = loci[l];
+    int chunk = li.H;
+    if (total_pairs > 0 && total_pairs / li.H < 16384) chunk = (int)std::max<int64_t>(1, std::min<int64_t>(li.H, total_pairs / 16384));
+    for (int p = b->locus_pool_off[l]; p < b->locus_pool_off[l + 1]; p++) {
+      const uint8_t v = pool_variant[p];
+      if (v == 255) continue;
+      if (v == 254) {   // HapAligner.cpp:333-337: LL 0 for every haplotype, mask ignored
+        DevJob j = {p, 0, li.H, 0};
+        out.jobs[0][at[0]++] = j;
         continue;
       }
-      if (dp.seed == 0 || dp.seed >= n - 1) { err = "invalid alignment seed"; return HIPSTR_ERR_INVALID_SEED; }
-      if (live_haps == 0) continue;
-      const int v = pick_variant(dp.seed, n - dp.seed - 1);
-      if (v < 0) { err = "read longer than the kernel's limit"; return HIPSTR_ERR_UNSUPPORTED; }
-      out.n_max[v] = std::max(out.n_max[v], padded);
-      out.l_max[v] = std::max(out.l_max[v], round_up(max_len, 2));
-      for (int h0 = 0; h0 < H; h0 += chunk) {
-        DevJob j = {pool_id, h0, (int32_t)std::min<int64_t>(H, h0 + chunk), 0};
-        out.jobs[v].push_back(j);
+      for (int h0 = 0; h0 < li.H; h0 += chunk) {
+        DevJob j = {p, h0, std::min(li.H, h0 + chunk), 0};
+        out.jobs[v][at[v]++] = j;
       }
     }
   }

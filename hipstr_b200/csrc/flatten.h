@@ -5,6 +5,7 @@
 #ifndef HIPSTR_B200_FLATTEN_H_
 #define HIPSTR_B200_FLATTEN_H_
 
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -29,20 +30,59 @@ const HostTables& host_tables();
 static const int kNumColVariants = 8;
 static const int kColVariants[kNumColVariants] = {2, 3, 4, 5, 6, 8, 12, 16};
 
+/* Growable host buffer for the large staging arrays.  The allocator is pluggable so that the
+ * C-ABI layer can hand out page-locked memory (cudaHostAlloc) -- H2D copies then run at full PCIe
+ * speed and truly asynchronously -- while this file stays free of CUDA.  Contents are NOT
+ * initialised on growth (a 130 MB zero-fill per call would cost more than the flattening). */
+typedef void* (*host_alloc_fn)(size_t bytes);
+typedef void (*host_free_fn)(void* p);
+void set_host_allocator(host_alloc_fn alloc, host_free_fn release);
+void* host_alloc(size_t bytes);
+void host_free(void* p);
+
+template <class T>
+struct HostBuf {
+  T* p = nullptr;
+  size_t n = 0, cap = 0;
+  HostBuf() {}
+  HostBuf(const HostBuf&) = delete;
+  HostBuf& operator=(const HostBuf&) = delete;
+  ~HostBuf() { if (p) host_free(p); }
+  void resize(size_t count) {   // keeps the first min(n, count) elements
+    if (count > cap) {
+      size_t want = count + count / 4 + 64;
+      T* q = static_cast<T*>(host_alloc(want * sizeof(T)));
+      if (p) { if (n) std::memcpy(q, p, n * sizeof(T)); host_free(p); }
+      p = q;
+      cap = want;
+    }
+    n = count;
+  }
+  void clear() { n = 0; }
+  void push_back(const T& v) { if (n == cap) { size_t old = n; resize(n + 1); n = old; } p[n++] = v; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct FlatBatch {
-  std::vector<DevPool> pools;
-  std::vector<char> bases, quals;            /* every read padded to a multiple of 16 bytes */
+  HostBuf<DevPool> pools;
+  HostBuf<char> bases, quals;                /* every read padded to a multiple of 16 bytes */
   std::vector<DevHapSide> hapsides;          /* [global hap][2] */
   std::vector<uint8_t> hapbytes;
   std::vector<DevBlock> blocks;
   std::vector<DevRep> reps;
   std::vector<uint16_t> runs;
   std::vector<uint8_t> hap_mask;             /* empty = all haplotypes */
-  std::vector<DevJob> jobs[kNumColVariants];
+  HostBuf<DevJob> jobs[kNumColVariants];
   int32_t n_max[kNumColVariants];            /* per variant: max read length (padded) */
   int32_t l_max[kNumColVariants];            /* per variant: max haplotype length (padded) */
   int64_t n_out = 0;
   int64_t n_alignments = 0;
+  void clear();
 };
 
 /* Returns HIPSTR_OK or an error with a message. */
