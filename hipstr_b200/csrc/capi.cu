@@ -33,14 +33,14 @@ struct DevBuf {
 };
 
 struct hipstr_dev_batch {
-  DevBuf pools, bases, quals, hapsides, hapbytes, blocks, reps, runs, mask, jobs[kNumColVariants];
+  DevBuf pools, bases, quals, hapsides, hapbytes, blocks, reps, progs, mask, jobs[kNumColVariants];
   int32_t n_jobs[kNumColVariants];
   int32_t n_max[kNumColVariants], l_max[kNumColVariants];
   int64_t n_out = 0, n_alignments = 0;
   bool has_mask = false;
   void release() {
     pools.release(); bases.release(); quals.release(); hapsides.release(); hapbytes.release();
-    blocks.release(); reps.release(); runs.release(); mask.release();
+    blocks.release(); reps.release(); progs.release(); mask.release();
     for (auto& j : jobs) j.release();
   }
 };
@@ -140,7 +140,7 @@ hipstr_status_t stage(hipstr_ctx* ctx, const hipstr_align_batch_t* batch, hipstr
   CU(put(d.hapbytes, f.hapbytes, s));
   CU(put(d.blocks, f.blocks, s));
   CU(put(d.reps, f.reps, s));
-  CU(put(d.runs, f.runs, s));
+  CU(put(d.progs, f.progs, s));
   CU(put(d.mask, f.hap_mask, s));
   for (int v = 0; v < kNumColVariants; v++) {
     CU(put(d.jobs[v], f.jobs[v], s));
@@ -166,7 +166,7 @@ hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll
   p.hapbytes = (const uint8_t*)d.hapbytes.p;
   p.blocks = (const DevBlock*)d.blocks.p;
   p.reps = (const DevRep*)d.reps.p;
-  p.runs = (const uint16_t*)d.runs.p;
+  p.progs = (const DevProgEntry*)d.progs.p;
   p.hap_mask = d.has_mask ? (const uint8_t*)d.mask.p : nullptr;
   p.qual_lut = ctx->d_qual_lut;
   p.trans = ctx->d_trans;

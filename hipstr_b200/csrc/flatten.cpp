@@ -43,7 +43,7 @@ void host_free(void* p) { if (g_free) g_free(p); else std::free(p); }
 
 void FlatBatch::clear() {
   pools.clear(); bases.clear(); quals.clear();
-  hapsides.clear(); hapbytes.clear(); blocks.clear(); reps.clear(); runs.clear(); hap_mask.clear();
+  hapsides.clear(); hapbytes.clear(); blocks.clear(); reps.clear(); progs.clear(); hap_mask.clear();
   for (auto& j : jobs) j.clear();
   n_out = n_alignments = 0;
 }
@@ -276,7 +276,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
         Option& op = blk[k].opts[o - o0];
         op.seq[0].assign(b->opt_seq + b->opt_seq_off[o], b->opt_seq + b->opt_seq_off[o + 1]);
         if (op.seq[0].empty()) { err = "empty block option"; return HIPSTR_ERR_UNSUPPORTED; }
-        if (op.seq[0].size() > 60000) { err = "block option too long"; return HIPSTR_ERR_UNSUPPORTED; }
+        if (op.seq[0].size() > 9000) { err = "block option too long"; return HIPSTR_ERR_UNSUPPORTED; }
         op.seq[1].assign(op.seq[0].rbegin(), op.seq[0].rend());
         for (int s = 0; s < 2; s++) {
           op.runs[s].build(op.seq[s]);
@@ -318,14 +318,52 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
             r.period = p;
             r.n_del = n_del;
             r.left_align = (s == 0);
-            r.runs_off = (int32_t)out.runs.size();
+            // upstream_match_lengths_ (StutterAlignerClass.h:35-42,70-75): for lag = k*period,
+            // m[i] = 0 if seq[i-lag] != seq[i] else 1 + m[i-1]
+            const std::string& sq = op.seq[s];
+            const std::vector<uint8_t>& cd = op.codes[s];
             const int n_lag = std::max(n_del, 1);
-            for (int k2 = 1; k2 <= n_lag; k2++) {
-              const int lag = k2 * p;
-              size_t base = out.runs.size();
-              out.runs.resize(base + B, 0);
-              for (int i = lag; i < B; i++)
-                out.runs[base + i] = op.seq[s][i - lag] != op.seq[s][i] ? 0 : (uint16_t)(1 + out.runs[base + i - 1]);
+            std::vector<std::vector<int> > runs(n_lag, std::vector<int>(B, 0));
+            for (int k2 = 1; k2 <= n_lag; k2++)
+              for (int i = k2 * p; i < B; i++) runs[k2 - 1][i] = sq[i - k2 * p] != sq[i] ? 0 : 1 + runs[k2 - 1][i - 1];
+            auto emit_entry = [&](int pos, int kind, int xa, int xb, double logrun) {
+              DevProgEntry e;
+              e.pos = pos; e.kind = (uint8_t)kind; e.xa = (uint8_t)xa; e.xb = (uint8_t)xb; e.pad = 0; e.logrun = logrun;
+              out.progs.push_back(e);
+            };
+            const HostTables& T = host_tables();
+            // insertion walk (StutterAlignerClass.cpp:75-97), full extent i > -B
+            r.prog_off[0] = (int32_t)out.progs.size();
+            {
+              int i = 0;
+              while (i > -B) {
+                const int bpos = B - 1 + i;
+                int step = 1;
+                if (-i + p < B) {
+                  const int run = runs[0][bpos];
+                  if (run == 0) emit_entry(i, HIPSTR_PROG_UPDATE, cd[bpos], cd[bpos - p], 0.0);
+                  else { emit_entry(i, HIPSTR_PROG_COLLAPSED, 0, 0, T.int_logs[run]); step = run; }
+                } else
+                  emit_entry(i, HIPSTR_PROG_PLAIN, 0, 0, 0.0);
+                i -= step;
+              }
+              emit_entry(i, HIPSTR_PROG_END, 0, 0, 0.0);
+            }
+            // deletion walks (StutterAlignerClass.cpp:127-142), full extent i > -(B + D)
+            for (int k2 = 1; k2 <= HIPSTR_MAX_ARTIFACT_UNITS; k2++) {
+              r.prog_off[k2] = (int32_t)out.progs.size();
+              if (k2 > n_del) continue;
+              const int D = -k2 * p;
+              int i = 0;
+              while (i > -(B + D)) {
+                const int bpos = B - 1 + i;
+                int step = 1;
+                const int run = runs[k2 - 1][bpos];
+                if (run == 0) emit_entry(i, HIPSTR_PROG_UPDATE, cd[bpos + D], cd[bpos], 0.0);
+                else { emit_entry(i, HIPSTR_PROG_COLLAPSED, 0, 0, T.int_logs[run]); step = run; }
+                i -= step;
+              }
+              emit_entry(i, HIPSTR_PROG_END, 0, 0, 0.0);
             }
             for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) {
               const int units = a - HIPSTR_MAX_ARTIFACT_UNITS;

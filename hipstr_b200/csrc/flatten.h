@@ -75,7 +75,7 @@ struct FlatBatch {
   std::vector<uint8_t> hapbytes;
   std::vector<DevBlock> blocks;
   std::vector<DevRep> reps;
-  std::vector<uint16_t> runs;
+  std::vector<DevProgEntry> progs;
   std::vector<uint8_t> hap_mask;             /* empty = all haplotypes */
   HostBuf<DevJob> jobs[kNumColVariants];
   int32_t n_max[kNumColVariants];            /* per variant: max read length (padded) */

@@ -54,172 +54,129 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 // ------------------------------------------------------------------------------------------
 struct RepCtx {
   const uint8_t* s;        // oriented allele base codes (global, read-only)
-  const uint16_t* runs;    // upstream_match_lengths_ tables, [max(n_del,1)][B]
+  const DevProgEntry* progs;
+  const DevRep* rep;
   const double* int_logs;  // global
   const double* val;       // shared: emission table of this side, [n_side][5]
   const uint8_t* code;     // shared: read base codes of this side
   const double* match;     // shared: match_probs_ by side column
+  double* terms;           // shared: this lane's term cache, slot s at terms[32 * s]
   int B, p, n_side;
 
   __device__ __forceinline__ double emit(int q, int b) const { return val[q * 5 + __ldg(s + b)]; }
-  __device__ __forceinline__ double emit_code(int q, int x) const { return val[q * 5 + x]; }
   __device__ __forceinline__ double lc(int q) const { return val[q * 5 + code[q]]; }
 };
+
+#define HIPSTR_TERM_SLOTS 16   /* terms of one fast_log_sum_exp call kept in shared memory per lane */
 
 // match_probs_[q] of StutterAlignerClass::load_read (StutterAlignerClass.cpp:12-53).
 __device__ __forceinline__ double rep_match_prob(const RepCtx& c, int q) {
   const int terms = min(q + 1, c.B);
   double acc = 0.0;
-  for (int t = 0; t < terms; t++) acc += c.emit(q - t, c.B - 1 - t);
+  const double* col = c.val + q * 5;
+  const uint8_t* sb = c.s + c.B - 1;
+  for (int t = 0; t < terms; t++, col -= 5, sb--) acc += col[__ldg(sb)];
   return acc;
 }
 
-// Sinks for the terms of one fast_log_sum_exp(vector) call (mathops.cpp:97-106).
-// CandSink does it in ONE pass: a term can only contribute if it is within LOG_THRESH of the
-// final maximum, hence of the running maximum at the time it is produced (the subtraction is
-// monotone in the maximum, also after rounding), so only those few are kept, in registers.
-// If more than 4 are alive at once the caller falls back to a second (sum) pass.
-struct CandSink {
-  // four most recent candidates, newest first; an evicted candidate that could still matter
-  // (within the threshold of the current maximum) sets `lost` and the caller falls back
-  double mx, c0, c1, c2, c3;
-  bool lost;
-  __device__ __forceinline__ void first(double t) { mx = t; c0 = t; c1 = c2 = c3 = -1.0e300; lost = false; }
-  __device__ __forceinline__ void push(double t) {
-    // one subtract + compare for the common case (a term far below the running maximum);
-    // t > mx implies t - mx > 0 > LOG_THRESH, so the maximum update lives on the rare path too
-    if (t - mx > HIPSTR_LOG_THRESH) {
-      mx = dmax(mx, t);
-      if (c3 - mx > HIPSTR_LOG_THRESH) lost = true;
-      c3 = c2; c2 = c1; c1 = c0; c0 = t;
-    }
-  }
-  __device__ __forceinline__ bool overflow() const { return lost; }
-  __device__ __forceinline__ double finish() const {
-    double total = lse_term(c0, mx);
-    if (c1 - mx > HIPSTR_LOG_THRESH) total += lse_term(c1, mx);
-    if (c2 - mx > HIPSTR_LOG_THRESH) total += lse_term(c2, mx);
-    if (c3 - mx > HIPSTR_LOG_THRESH) total += lse_term(c3, mx);
-    return lse_finish(mx, total);
-  }
-};
-struct MaxSink {
-  double mx;
-  __device__ __forceinline__ void first(double t) { mx = t; }
-  __device__ __forceinline__ void push(double t) { mx = dmax(mx, t); }
-};
-struct SumSink {
-  double mx, total;
-  __device__ __forceinline__ void first(double t) { total = lse_term(t, mx); }
-  __device__ __forceinline__ void push(double t) { total += lse_term(t, mx); }
-};
+struct ProgStep { int pos; unsigned bits; double logrun; };
+__device__ __forceinline__ ProgStep load_step(const DevProgEntry* e) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(e));
+  ProgStep s;
+  s.pos = v.x;
+  s.bits = (unsigned)v.y;
+  s.logrun = __hiloint2double(v.w, v.z);
+  return s;
+}
 
-// Terms of align_pcr_insertion_reverse (StutterAlignerClass.cpp:59-104): insertion of D = k*period
-// bases that copy the period bases upstream, summed over insertion positions; runs of positions
-// with identical likelihood are collapsed with int_log(run length).
-template <class Sink>
-__device__ __forceinline__ void insertion_terms(const RepCtx& c, int base_len, int j, int D, double lp, Sink& sink) {
-  const int B = c.B, p = c.p;
-  const int stop = -min(max(0, base_len - D), B);
-  const int stride = 5 * p;
-  const uint16_t* rp = c.runs + (B - 1);      // lag = period table, walked right to left
-  const uint8_t* sp = c.s + (B - 1);
-  const double* col = c.val + (j - p) * 5;     // column j + i - p at i = 0
-  const int no_left = p - B;                   // positions i <= no_left have no base `period` upstream
-  sink.first(lp);
-  int i = 0;
-  while (i > stop) {
+// Replays one position walk for read column j (see DevProgEntry) and returns
+// fast_log_sum_exp(vector) of its terms (mathops.cpp:97-106).
+//   INS: align_pcr_insertion_reverse (StutterAlignerClass.cpp:59-104), units = D / period copies
+//        inserted, an UPDATE touches the `units` read bases upstream of the position;
+//   else align_pcr_deletion_reverse (:106-150), an UPDATE touches one read base.
+// Terms are parked in shared memory (they are few: the walk collapses runs of equivalent
+// positions) so maximum and sum need ONE pass; a longer walk falls back to a second pass.
+template <bool INS>
+__device__ __forceinline__ double rep_walk(const RepCtx& c, const DevProgEntry* prog, int stop, int j, int units,
+                                           double lp0, int tail_base) {
+  const int stride = 5 * c.p;
+  const double* colbase = c.val + (INS ? (j - c.p) : j) * 5;
+  double* cache = c.terms;
+  double lp = lp0, mx = lp0;
+  int n = 1;
+  cache[0] = lp0;
+  ProgStep cur = load_step(prog);
+  while (cur.pos > stop) {
+    const ProgStep nxt = load_step(++prog);   // independent of the work below: prefetched
+    const unsigned kind = cur.bits & 0xffu;
     double term = lp;
-    int step = 1;
-    if (i > no_left) {
-      const int run = __ldg(rp);
-      if (run == 0) {
-        const double* ca = col + __ldg(sp);
-        const double* cb = col + __ldg(sp - p);
-        for (int m = 0; m < D; m += p, ca -= stride, cb -= stride) {
+    if (kind == HIPSTR_PROG_UPDATE) {
+      const double* ca = colbase + cur.pos * 5 + ((cur.bits >> 8) & 0xffu);
+      const double* cb = colbase + cur.pos * 5 + ((cur.bits >> 16) & 0xffu);
+      if (INS) {
+        for (int m = 0; m < units; m++, ca -= stride, cb -= stride) {
           lp -= *ca;
           lp += *cb;
         }
-        term = lp;
       } else {
-        term = __ldg(c.int_logs + run) + lp;
-        step = run;
+        lp -= *ca;
+        lp += *cb;
       }
-    }
-    sink.push(term);
-    i -= step; rp -= step; sp -= step; col -= 5 * step;
-  }
-  if (i > -B) sink.push(__ldg(c.int_logs + (B + i)) + lp);
-}
-
-// align_pcr_deletion_reverse (StutterAlignerClass.cpp:106-150), D < 0.
-template <class Sink>
-__device__ __forceinline__ void deletion_terms(const RepCtx& c, const uint16_t* runs, int base_len, int j, int D, double lp, Sink& sink) {
-  const int B = c.B;
-  const uint16_t* rp = runs + (B - 1);
-  const uint8_t* sp = c.s + (B - 1);
-  const double* col = c.val + j * 5;
-  sink.first(lp);
-  int i = 0;
-  while (i > -base_len) {
-    const int run = __ldg(rp);
-    double term;
-    int step = 1;
-    if (run == 0) {
-      lp -= col[__ldg(sp + D)];
-      lp += col[__ldg(sp)];
       term = lp;
-    } else {
-      term = __ldg(c.int_logs + run) + lp;
-      step = run;
-    }
-    sink.push(term);
-    i -= step; rp -= step; sp -= step; col -= 5 * step;
+    } else if (kind == HIPSTR_PROG_COLLAPSED)
+      term = cur.logrun + lp;
+    if (n < HIPSTR_TERM_SLOTS) cache[32 * n] = term;
+    n++;
+    mx = dmax(mx, term);
+    cur = nxt;
   }
-  if (-i < B + D) sink.push(__ldg(c.int_logs + (B + D + i)) + lp);
-}
-
-__device__ __forceinline__ double rep_insertion(const RepCtx& c, int base_len, int j, int D, double lp0) {
-  CandSink cs;
-  insertion_terms(c, base_len, j, D, lp0, cs);
-  if (!cs.overflow()) return cs.finish();
-  SumSink ss;
-  ss.mx = cs.mx;
-  insertion_terms(c, base_len, j, D, lp0, ss);
-  return lse_finish(ss.mx, ss.total);
-}
-
-__device__ __forceinline__ double rep_deletion(const RepCtx& c, int base_len, int j, int D, int k) {
-  const int B = c.B;
-  const uint16_t* runs = c.runs + (size_t)(k - 1) * B;
-  double lp0 = -__ldg(c.int_logs + (B + D + 1));
-  const int q = j - D;   // read column |D| bases to the right of j
-  if (q <= c.n_side - 1) {
-    // match_probs_[q] - del_probs_[q][k-1]; the deletion prefix table entry is the first
-    // k*period terms of the same right-anchored sum, recomputed here instead of stored
-    double pre = 0.0;
-    const int terms = -D;
-    const double* col = c.val + q * 5;
-    const uint8_t* sb = c.s + B - 1;
-    for (int t = 0; t < terms; t++, col -= 5, sb--) pre += col[__ldg(sb)];
-    lp0 += c.match[q] - pre;
-  } else {
-    for (int t = 0; t < base_len; t++) lp0 += c.emit(j - t, B - 1 - t + D);
+  double tail = 0.0;
+  const bool has_tail = INS ? (cur.pos > -tail_base) : (-cur.pos < tail_base);
+  if (has_tail) {
+    tail = __ldg(c.int_logs + (tail_base + cur.pos)) + lp;
+    mx = dmax(mx, tail);
   }
-  CandSink cs;
-  deletion_terms(c, runs, base_len, j, D, lp0, cs);
-  if (!cs.overflow()) return cs.finish();
-  SumSink ss;
-  ss.mx = cs.mx;
-  deletion_terms(c, runs, base_len, j, D, lp0, ss);
-  return lse_finish(ss.mx, ss.total);
+  double total = has_tail ? lse_term(tail, mx) : 0.0;
+  if (n <= HIPSTR_TERM_SLOTS) {
+    for (int s = 0; s < n; s++) total += lse_term(cache[32 * s], mx);
+    return lse_finish(mx, total);
+  }
+  // rare: more terms than slots -> replay the walk, summing against the known maximum
+  lp = lp0;
+  total += lse_term(lp0, mx);
+  prog -= (n - 1);
+  cur = load_step(prog);
+  while (cur.pos > stop) {
+    const ProgStep nxt = load_step(++prog);
+    const unsigned kind = cur.bits & 0xffu;
+    double term = lp;
+    if (kind == HIPSTR_PROG_UPDATE) {
+      const double* ca = colbase + cur.pos * 5 + ((cur.bits >> 8) & 0xffu);
+      const double* cb = colbase + cur.pos * 5 + ((cur.bits >> 16) & 0xffu);
+      if (INS) {
+        for (int m = 0; m < units; m++, ca -= stride, cb -= stride) {
+          lp -= *ca;
+          lp += *cb;
+        }
+      } else {
+        lp -= *ca;
+        lp += *cb;
+      }
+      term = lp;
+    } else if (kind == HIPSTR_PROG_COLLAPSED)
+      term = cur.logrun + lp;
+    total += lse_term(term, mx);
+    cur = nxt;
+  }
+  return lse_finish(mx, total);
 }
 
 // One column of the repeat block's last row: HapAligner.cpp:76-100.  The 13 artifact sizes are
 // evaluated by two rolled loops (deletions, insertions) so the evaluator code exists once; their
 // results wait in a small per-thread array for the final log-sum-exp.
-__device__ __forceinline__ double rep_column(const RepCtx& c, const DevRep* rep, const double* prev_row, int j) {
+__device__ __forceinline__ double rep_column(const RepCtx& c, const double* prev_row, int j) {
   const int B = c.B, p = c.p;
+  const DevRep* rep = c.rep;
   double probs[HIPSTR_NUM_ARTIFACTS];
 #pragma unroll 1
   for (int k = HIPSTR_MAX_ARTIFACT_UNITS; k >= 1; k--) {   // deletions of k units
@@ -227,20 +184,34 @@ __device__ __forceinline__ double rep_column(const RepCtx& c, const DevRep* rep,
     const int base_len = min(B + D, j + 1);
     double v = IMPOSSIBLE;
     if (base_len >= 0) {
-      const double pr = rep_deletion(c, base_len, j, D, k);
-      const double pre = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
-      v = __ldg(rep->art + (HIPSTR_MAX_ARTIFACT_UNITS - k)) + pr + pre;
+      double lp0 = -__ldg(c.int_logs + (B + D + 1));
+      const int q = j - D;   // read column |D| bases to the right of j
+      if (q <= c.n_side - 1) {
+        // match_probs_[q] - del_probs_[q][k-1]; the deletion prefix table entry is the first
+        // k*period terms of the same right-anchored sum, recomputed here instead of stored
+        double pre = 0.0;
+        const double* col = c.val + q * 5;
+        const uint8_t* sb = c.s + B - 1;
+        for (int t = 0; t < -D; t++, col -= 5, sb--) pre += col[__ldg(sb)];
+        lp0 += c.match[q] - pre;
+      } else {
+        for (int t = 0; t < base_len; t++) lp0 += c.emit(j - t, B - 1 - t + D);
+      }
+      const double pr = rep_walk<false>(c, c.progs + __ldg(rep->prog_off + k), -base_len, j, k, lp0, B + D);
+      const double pre_row = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
+      v = __ldg(rep->art + (HIPSTR_MAX_ARTIFACT_UNITS - k)) + pr + pre_row;
     }
     probs[HIPSTR_MAX_ARTIFACT_UNITS - k] = v;
   }
   {
     const int base_len = min(B, j + 1);
-    const double pre = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
-    probs[HIPSTR_MAX_ARTIFACT_UNITS] = __ldg(rep->art + HIPSTR_MAX_ARTIFACT_UNITS) + c.match[j] + pre;
+    const double pre_row = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
+    probs[HIPSTR_MAX_ARTIFACT_UNITS] = __ldg(rep->art + HIPSTR_MAX_ARTIFACT_UNITS) + c.match[j] + pre_row;
   }
   double ins_acc = 0.0;    // ins_probs_ running sum (StutterAlignerClass.cpp:38-51)
   int ins_t = 0;
   const double ins_prior = -__ldg(c.int_logs + (B + 1));
+  const DevProgEntry* ins_prog = c.progs + __ldg(rep->prog_off);
 #pragma unroll 1
   for (int k = 1; k <= HIPSTR_MAX_ARTIFACT_UNITS; k++) {    // insertions of k units
     const int D = k * p;
@@ -253,9 +224,10 @@ __device__ __forceinline__ double rep_column(const RepCtx& c, const DevRep* rep,
     }
     double lp0 = ins_prior + ins_acc;
     lp0 += (base_len > D) ? c.match[j - D] : 0.0;
-    const double pr = rep_insertion(c, base_len, j, D, lp0);
-    const double pre = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
-    probs[HIPSTR_MAX_ARTIFACT_UNITS + k] = __ldg(rep->art + HIPSTR_MAX_ARTIFACT_UNITS + k) + pr + pre;
+    const int stop = -min(max(0, base_len - D), B);
+    const double pr = rep_walk<true>(c, ins_prog, stop, j, k, lp0, B);
+    const double pre_row = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
+    probs[HIPSTR_MAX_ARTIFACT_UNITS + k] = __ldg(rep->art + HIPSTR_MAX_ARTIFACT_UNITS + k) + pr + pre_row;
   }
   double mx = probs[0];
 #pragma unroll 1
@@ -270,8 +242,8 @@ __device__ __forceinline__ double rep_column(const RepCtx& c, const DevRep* rep,
 // K1
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t align_smem_doubles(int n_max, int l_max) {
-  // val[5N] run[N] rowbuf[N] rowout[N] match[N] last[2L] code[N bytes]
-  return (size_t)9 * n_max + 2 * (size_t)l_max + n_max / 8;
+  // val[5N] run[N] rowbuf[N] rowout[N] match[N] last[2L] terms[32*SLOTS] code[N bytes]
+  return (size_t)9 * n_max + 2 * (size_t)l_max + 32 * HIPSTR_TERM_SLOTS + n_max / 8;
 }
 size_t align_smem_bytes(int n_max, int l_max) { return align_smem_doubles(n_max, l_max) * 8 * HIPSTR_WARPS_PER_CTA; }
 
@@ -302,7 +274,8 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
   double* s_rowout = s_rowbuf + N;
   double* s_match = s_rowout + N;
   double* s_last = s_match + N;
-  uint8_t* s_code = reinterpret_cast<uint8_t*>(s_last + 2 * L);
+  double* s_terms = s_last + 2 * L;
+  uint8_t* s_code = reinterpret_cast<uint8_t*>(s_terms + 32 * HIPSTR_TERM_SLOTS);
 
   const int n = pool.len, seed = pool.seed;
   const int nL = seed, nR = n - seed - 1;
@@ -465,8 +438,9 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
           if (gb.rep < 0) continue;
           const DevRep* rep = P.reps + gb.rep;
           RepCtx c;
-          c.s = P.hapbytes + rep->seq_off; c.runs = P.runs + rep->runs_off; c.int_logs = P.int_logs;
+          c.s = P.hapbytes + rep->seq_off; c.progs = P.progs; c.rep = rep; c.int_logs = P.int_logs;
           c.val = s_val + (gs ? nL : 0) * 5; c.code = s_code + (gs ? nL : 0); c.match = s_match + (gs ? nL : 0);
+          c.terms = s_terms + lane;
           c.B = rep->len; c.p = rep->period; c.n_side = gs ? nR : nL;
           s_match[g] = rep_match_prob(c, g - (gs ? nL : 0));
         }
@@ -478,10 +452,11 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
           if (gb.rep < 0) continue;
           const DevRep* rep = P.reps + gb.rep;
           RepCtx c;
-          c.s = P.hapbytes + rep->seq_off; c.runs = P.runs + rep->runs_off; c.int_logs = P.int_logs;
+          c.s = P.hapbytes + rep->seq_off; c.progs = P.progs; c.rep = rep; c.int_logs = P.int_logs;
           c.val = s_val + (gs ? nL : 0) * 5; c.code = s_code + (gs ? nL : 0); c.match = s_match + (gs ? nL : 0);
+          c.terms = s_terms + lane;
           c.B = rep->len; c.p = rep->period; c.n_side = gs ? nR : nL;
-          s_rowout[g] = rep_column(c, rep, s_rowbuf + (gs ? nL : 0), g - (gs ? nL : 0));
+          s_rowout[g] = rep_column(c, s_rowbuf + (gs ? nL : 0), g - (gs ? nL : 0));
         }
         __syncwarp();
         // every lane re-reads its column constants: nothing of the flank state has to stay in

@@ -13,10 +13,10 @@
  *              per-row homopolymer class, block list.  Orientation 0 = forward
  *              haplotype (left of the seed), 1 = reversed haplotype (right of the
  *              seed), as in HapAligner.cpp:606-627.
- *   reps       one record per (repeat-block allele, orientation): what the
- *              reference's StutterAlignerClass constructor precomputes
- *              (StutterAlignerClass.h:49-80) + the 13 PCR-artifact log-priors
- *              (RepeatStutterInfo.h:53-61), computed on the host with glibc.
+ *   reps       one record per (repeat-block allele, orientation): the position walks the
+ *              reference derives from StutterAlignerClass's upstream_match_lengths_
+ *              (StutterAlignerClass.h:35-80), unrolled into programs, + the 13 PCR-artifact
+ *              log-priors (RepeatStutterInfo.h:53-61), computed on the host with glibc.
  *   jobs       (pool, haplotype range) work items, bucketed by columns-per-lane.
  */
 #ifndef HIPSTR_B200_LAYOUT_H_
@@ -61,13 +61,28 @@ struct DevBlock {         /* 16 B */
   int32_t pad;
 };
 
-struct DevRep {           /* 128 B */
-  int32_t seq_off;        /* into hapbytes: oriented allele sequence */
+/* One step of a repeat-block "program": the position walk of align_pcr_insertion_reverse /
+ * align_pcr_deletion_reverse (StutterAlignerClass.cpp:75-100,127-147) depends only on the allele
+ * (its upstream_match_lengths_ table), not on the read, so the host unrolls it once per allele and
+ * every read column replays it: no data-dependent pointer chasing on the device, and the next
+ * step can be prefetched while the current one is applied. */
+#define HIPSTR_PROG_PLAIN 0      /* term = lp                                   */
+#define HIPSTR_PROG_UPDATE 1     /* lp -= emit(.., xa); lp += emit(.., xb); term = lp */
+#define HIPSTR_PROG_COLLAPSED 2  /* term = logrun + lp (a run of equivalent positions) */
+#define HIPSTR_PROG_END 3        /* terminal entry: `pos` is where the walk stops */
+struct DevProgEntry {     /* 16 B */
+  int32_t pos;            /* artifact position i (<= 0, offset from the right end of the block) */
+  uint8_t kind, xa, xb, pad;
+  double  logrun;         /* int_log(run length) for COLLAPSED */
+};
+
+struct DevRep {           /* 160 B */
+  int32_t seq_off;        /* into hapbytes: oriented allele base codes */
   int32_t len;            /* B */
   int32_t period;
   int32_t n_del;          /* StutterAlignerClass num_deletions_ */
-  int32_t runs_off;       /* into runs: max(n_del,1) tables of B uint16 (upstream_match_lengths_) */
   int32_t left_align;     /* !reversed (RepeatBlock.h:28,41); only the traceback uses it */
+  int32_t prog_off[7];    /* into progs: [0] insertion walk (lag = period), [k] deletion of k units */
   int32_t pad[2];
   double  art[13];        /* log_prob_pcr_artifact for D = -6p .. +6p */
 };
@@ -90,7 +105,7 @@ struct AlignParams {
   const uint8_t* hapbytes;
   const DevBlock* blocks;
   const DevRep* reps;
-  const uint16_t* runs;
+  const DevProgEntry* progs;
   const uint8_t* hap_mask;   /* per global hap index; NULL = all */
   const double* qual_lut;    /* [256][2]: log_correct, log_error by quality byte */
   const double* trans;       /* [3][16]: LOG_MATCH_TO_MATCH / _INS / _DEL by homopolymer class */
