@@ -354,6 +354,13 @@ def main():
             pass
         hbm_peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
         k1_avg_ms = k1_ms / max(n_calls, 1)
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes of K1 from the committed ncu --set full capture, scaled per alignment
+            tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+            traffic = tr["dram_bytes_per_alignment"] * n_aln
+            traffic_src = tr["capture"]
+        except (OSError, ValueError, KeyError):
+            pass
         achieved = alg_bytes / (k1_avg_ms / 1e3) / 1e9 if k1_avg_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -362,7 +369,7 @@ def main():
             "loci_per_s": world * a.loci * a.steps / (ms_total / 1e3),
             "alignments_per_step": int(total_aln), "gpu_launches": int(launches_per_step[0]) * a.steps,
             "roofline": {"bound": "hbm", "kernel": "k_align (K1)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch_set": int(alg_bytes), "bytes_per_alignment": alg_bytes / max(n_aln, 1),
                          "k1_ms_per_step": k1_avg_ms, "k1_share_of_step": k1_ms / max(k1_ms + rest_ms, 1e-9),
                          "note": "K1 keeps the DP on chip: it is FP64-issue / latency bound, not HBM bound (DESIGN.md)"},

@@ -1,0 +1,84 @@
+"""The N>1 path of bench.py on CPU: world size 2 over gloo.  Loci shard across ranks with no data-path
+collective; the single collective is the gather of per-locus genotype records to rank 0.  The per-rank
+"compute" here is the CPU oracle (test infrastructure) -- what is under test is the sharding, the
+gather and the rank-0 merge order, which are device independent."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_loci, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import checkers
+    from hipstr_b200.capi import Synth
+    from hipstr_b200.sharding import shard_bounds, merge_records
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s = Synth(n_loci=n_loci, n_samples=4, reads_per_sample=6, n_alleles=3, read_len=100, seed=77)   # same loci on every rank
+    l0, l1 = shard_bounds(n_loci, rank, world)
+    o = checkers.oracle()
+    ll = np.zeros(s.n_out)
+    import ctypes as C
+    from hipstr_b200.capi import c_f64p, ptr
+    o.oracle_align_loci(C.byref(s.batch), l0, l1, ptr(ll, c_f64p), None)
+    # per-locus record = (global locus index, checksum of its LLs)
+    rec = torch.tensor([[l, ll[s.locus_out_off[l]:s.locus_out_off[l + 1]].sum()] for l in range(l0, l1)], dtype=torch.float64).reshape(-1, 2)
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([rec.shape[0]], dtype=torch.int64))
+    width = int(max(c.item() for c in counts))
+    padded = torch.full((width, 2), -1.0, dtype=torch.float64)
+    padded[:rec.shape[0]] = rec
+    gathered = [torch.zeros_like(padded) for _ in range(world)] if rank == 0 else None
+    dist.gather(padded, gathered, dst=0)
+    if rank == 0:
+        merged = merge_records([g[:int(c.item())].numpy() for g, c in zip(gathered, counts)])
+        np.save(out_path, merged)
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_everything():
+    sys.path.insert(0, ROOT)
+    from hipstr_b200.sharding import shard_bounds
+    for n in (0, 1, 7, 8, 1000):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(x[1] - x[0] for x in b) - min(x[1] - x[0] for x in b) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_gather_matches_single_rank(tmp_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    n_loci = 5
+    out = str(tmp_path / "merged.npy")
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, n_loci, out), nprocs=2, join=True)
+    merged = np.load(out)
+    import checkers
+    from hipstr_b200.capi import Synth
+    s = Synth(n_loci=n_loci, n_samples=4, reads_per_sample=6, n_alleles=3, read_len=100, seed=77)
+    ll = checkers.align(checkers.oracle(), "oracle_", s.batch, s.n_out)
+    want = np.array([[l, ll[s.locus_out_off[l]:s.locus_out_off[l + 1]].sum()] for l in range(n_loci)])
+    assert merged.shape == want.shape
+    assert np.array_equal(merged[:, 0], want[:, 0])          # rank 0 feeds records in locus (position) order
+    assert np.array_equal(merged[:, 1], want[:, 1])
