@@ -259,6 +259,35 @@ hipstr_status_t hipstr_genotype_batch_dev(hipstr_ctx_t* ctx, const hipstr_dev_ge
                                           const hipstr_genotype_out_t* dev_out);
 void            hipstr_free_genotype_batch(hipstr_ctx_t* ctx, hipstr_dev_genotype_t* handle);
 
+/* --- a17 / seam B4: EM stutter-model learner (kernel K4) --------------------
+ * Replaces EMStutterGenotyper(...) + train(...) + get_stutter_model()
+ * (em_stutter_genotyper.h:50-117, em_stutter_genotyper.cpp:10-226) for a batch of
+ * loci, each an independent EM problem over read STR lengths.  Reads are
+ * sample-major per locus like everywhere else.
+ *   num_bps      [R] base-pair size of each read's STR (the ctor's num_bps)
+ *   motif_len    [n_loci], ref_allele [n_loci] (bp size of the reference allele)
+ * Outputs per locus: params [6] = inframe_geom, inframe_up, inframe_down,
+ * outframe_geom, outframe_up, outframe_down (StutterModel ctor order,
+ * stutter_model.h:36-37); converged = train()'s return value; iterations run;
+ * final total log-likelihood. */
+typedef struct hipstr_em_batch {
+  int32_t n_loci;
+  const int32_t* locus_read_off;    /* [n_loci+1] */
+  const int32_t* locus_sample_off;  /* [n_loci+1] */
+  const int32_t* num_bps;           /* [R] */
+  const int32_t* sample_label;      /* [R] local to the locus, non-decreasing */
+  const double*  log_p1;            /* [R] */
+  const double*  log_p2;            /* [R] */
+  const int32_t* motif_len;         /* [n_loci] */
+  const int32_t* ref_allele;        /* [n_loci] */
+  const uint8_t* haploid;           /* [n_loci] */
+} hipstr_em_batch_t;
+
+hipstr_status_t hipstr_em_train_host(hipstr_ctx_t* ctx, const hipstr_em_batch_t* batch, int32_t max_iter,
+                                     double min_LL_abs_change, double min_LL_frac_change,
+                                     double* params_out, uint8_t* converged_out, int32_t* iters_out,
+                                     double* ll_out);
+
 /* Accounting of the last public call on this context: bytes copied host->device and
  * device->host, and kernels launched. */
 void hipstr_last_traffic(const hipstr_ctx_t* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes,

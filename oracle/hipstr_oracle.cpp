@@ -569,6 +569,174 @@ void align_pool(const Locus& loc, const char* bases, const char* quals, int len,
 
 }  // namespace
 
+
+// ---------------------------------------------------------------------------
+// EM stutter learner (em_stutter_genotyper.cpp:10-226, em_stutter_genotyper.h:50-101),
+// one locus.  Same loops, same accumulation orders, same libm.
+// ---------------------------------------------------------------------------
+namespace {
+
+double exact_lse2(double a, double b) {                       // mathops.cpp:51-56
+  return a > b ? a + std::log(1 + std::exp(b - a)) : b + std::log(1 + std::exp(a - b));
+}
+double exact_lse3(double a, double b, double c) {             // mathops.cpp:58-61
+  double mx = std::max(std::max(a, b), c);
+  return mx + std::log(std::exp(a - mx) + std::exp(b - mx) + std::exp(c - mx));
+}
+void stream_lse(double v, double& mx, double& total) {        // mathops.cpp:72-80
+  if (v <= mx) total += std::exp(v - mx);
+  else { total *= std::exp(mx - v); total += 1.0; mx = v; }
+}
+
+struct EmLocus {
+  int R, S, A, period;
+  bool haploid;
+  std::vector<int> bps, allele_of, label, per_sample;
+  const double *p1, *p2;
+  std::vector<double> gt_prior, post, sll;
+  double prm[6];
+
+  double prior(int a, int b) const {                           // em_stutter_genotyper.cpp:129-144 (use_pop_freqs_)
+    if (!haploid) return gt_prior[a] + gt_prior[b];
+    return a == b ? gt_prior[a] : -DBL_MAX / 2;
+  }
+  // E-step: calc_hap_aln_probs + calc_log_sample_posteriors (genotyper.cpp:44-80)
+  double posteriors(const StutterPmf& pmf) {
+    const Tables& t = T();
+    for (int s = 0; s < S; s++)
+      for (int a = 0; a < A; a++)
+        for (int b = 0; b < A; b++) post[((size_t)s * A + a) * A + b] = prior(a, b);
+    std::vector<double> row(A);
+    for (int r = 0; r < R; r++) {
+      for (int a = 0; a < A; a++) row[a] = pmf(bps[a], bps[allele_of[r]]);
+      double* sp = &post[(size_t)label[r] * A * A];
+      for (int a = 0; a < A; a++)
+        for (int b = 0; b < A; b++, sp++) *sp += 1 * lse2(t.log_half + p1[r] + row[a], t.log_half + p2[r] + row[b]);
+    }
+    double total = 0.0;
+    for (int s = 0; s < S; s++) {
+      double* sp = &post[(size_t)s * A * A];
+      sll[s] = exact_lse(sp, sp + (size_t)A * A);
+      for (int i = 0; i < A * A; i++) sp[i] -= sll[s];
+    }
+    for (int s = 0; s < S; s++) total += sll[s];
+    return total;
+  }
+  void recalc_gt_priors() {                                    // :21-56
+    std::vector<double> mx(A, -DBL_MAX / 2), tot(A, 0.0);
+    const double* p = post.data();
+    for (int s = 0; s < S; s++)
+      for (int a = 0; a < A; a++, p += A) stream_lse(exact_lse(p, p + A), mx[a], tot[a]);
+    p = post.data();
+    for (int s = 0; s < S; s++)
+      for (int a = 0; a < A; a++)
+        for (int b = 0; b < A; b++, p++) stream_lse(*p, mx[b], tot[b]);
+    for (int a = 0; a < A; a++) gt_prior[a] = mx[a] + std::log(tot[a]);
+    double lt = exact_lse(gt_prior.data(), gt_prior.data() + A);
+    for (int a = 0; a < A; a++) gt_prior[a] -= lt;
+  }
+  void recalc_model(const StutterPmf& pmf) {                   // :63-127 with :152-168 folded in
+    const Tables& t = T();
+    std::vector<double> in_up(1, 0.0), in_down(1, 0.0), in_eq(1, 0.0), in_diffs, out_up(1, 0.0), out_down(1, 0.0), out_diffs;
+    in_diffs.push_back(0.0); in_diffs.push_back(std::log(1.1));
+    out_diffs.push_back(0.0); out_diffs.push_back(std::log(1.1));
+    for (int r = 0; r < R; r++) {
+      const double* gp = &post[(size_t)label[r] * A * A];
+      const int rb = bps[allele_of[r]];
+      for (int a = 0; a < A; a++)
+        for (int b = 0; b < A; b++, gp++) {
+          double one = t.log_half + p1[r] + pmf(bps[a], rb), two = t.log_half + p2[r] + pmf(bps[b], rb);
+          double both = lse2(one, two);
+          double phase[2] = {one - both, two - both};
+          for (int ph = 0; ph < 2; ph++) {
+            int gt = ph == 0 ? a : b, d = rb - bps[gt];
+            double f = *gp + phase[ph];
+            if (d == 0) in_eq.push_back(f);
+            else if (d % period != 0) {
+              int eff = d - d / period;
+              out_diffs.push_back(f + t.int_logs[std::abs(eff)]);
+              (d > 0 ? out_up : out_down).push_back(f);
+            } else {
+              int eff = d / period;
+              in_diffs.push_back(f + t.int_logs[std::abs(eff)]);
+              (d > 0 ? in_up : in_down).push_back(f);
+            }
+          }
+        }
+    }
+    auto L = [](std::vector<double>& v) { return lse_vec(v.data(), (int)v.size()); };
+    double iu = L(in_up), id = L(in_down), ie = L(in_eq), idf = L(in_diffs), ou = L(out_up), od = L(out_down), odf = L(out_diffs);
+    double ot = lse2(ou, od);
+    prm[0] = std::min(0.999, std::exp(exact_lse2(iu, id) - idf));
+    prm[3] = std::min(0.999, std::exp(ot - odf));
+    double lt = exact_lse2(exact_lse3(iu, id, ie), ot);
+    prm[1] = std::exp(iu - lt); prm[2] = std::exp(id - lt);
+    prm[4] = std::exp(ou - lt); prm[5] = std::exp(od - lt);
+  }
+};
+
+}  // namespace
+
+extern "C" int32_t oracle_em_train(const hipstr_em_batch_t* bt, int32_t max_iter, double min_abs, double min_frac,
+                                   double* params_out, uint8_t* converged_out, int32_t* iters_out, double* ll_out) {
+  for (int l = 0; l < bt->n_loci; l++) {
+    EmLocus e;
+    const int r0 = bt->locus_read_off[l], r1 = bt->locus_read_off[l + 1];
+    e.R = r1 - r0; e.S = bt->locus_sample_off[l + 1] - bt->locus_sample_off[l];
+    e.period = bt->motif_len[l]; e.haploid = bt->haploid[l] != 0;
+    e.p1 = bt->log_p1 + r0; e.p2 = bt->log_p2 + r0;
+    // allele list: reference first, the rest sorted (em_stutter_genotyper.h:59-81)
+    std::vector<int> sizes(bt->num_bps + r0, bt->num_bps + r1);
+    std::sort(sizes.begin(), sizes.end());
+    sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
+    sizes.erase(std::remove(sizes.begin(), sizes.end(), bt->ref_allele[l]), sizes.end());
+    e.bps.push_back(bt->ref_allele[l]);
+    e.bps.insert(e.bps.end(), sizes.begin(), sizes.end());
+    e.A = (int)e.bps.size();
+    e.per_sample.assign(e.S, 0);
+    for (int r = r0; r < r1; r++) {
+      e.label.push_back(bt->sample_label[r]);
+      e.per_sample[bt->sample_label[r]]++;
+      e.allele_of.push_back((int)(std::find(e.bps.begin(), e.bps.end(), bt->num_bps[r]) - e.bps.begin()));
+    }
+    e.post.assign((size_t)e.S * e.A * e.A, 0.0);
+    e.sll.assign(e.S, 0.0);
+    // init_log_gt_priors (:10-19)
+    e.gt_prior.assign(e.A, 1.0);
+    for (int r = 0; r < e.R; r++) e.gt_prior[e.allele_of[r]] += 1.0 / e.per_sample[e.label[r]];
+    double tot = 0.0;
+    for (int a = 0; a < e.A; a++) tot += e.gt_prior[a];
+    const double log_total = std::log(tot);
+    for (int a = 0; a < e.A; a++) e.gt_prior[a] = std::log(e.gt_prior[a]) - log_total;
+    const double init[6] = {0.9, 0.1, 0.1, 0.8, 0.01, 0.01};   // :58-61
+    std::copy(init, init + 6, e.prm);
+    // train (:170-226)
+    int iter = 1;
+    double LL = -DBL_MAX;
+    bool converged = false;
+    while (iter <= max_iter) {
+      StutterPmf pmf(e.prm, e.period);
+      double new_LL = e.posteriors(pmf);
+      if (new_LL < LL + 1e-10) { converged = true; LL = new_LL; break; }
+      e.recalc_gt_priors();
+      double prev[6];
+      std::copy(e.prm, e.prm + 6, prev);
+      e.recalc_model(pmf);
+      const double abs_change = new_LL - LL, frac_change = -(new_LL - LL) / LL;
+      bool close = true;
+      for (int k = 0; k < 6; k++) close = close && std::fabs(prev[k] - e.prm[k]) < 0.0001;
+      LL = new_LL;
+      if ((abs_change < min_abs && frac_change < min_frac) || close) { converged = true; break; }
+      iter++;
+    }
+    std::copy(e.prm, e.prm + 6, params_out + 6 * (size_t)l);
+    converged_out[l] = converged;
+    if (iters_out) iters_out[l] = std::min(iter, max_iter);
+    if (ll_out) ll_out[l] = LL;
+  }
+  return HIPSTR_OK;
+}
+
 extern "C" {
 
 double oracle_fast_lse2(double a, double b) { return lse2(a, b); }

@@ -54,6 +54,11 @@ int32_t oracle_posteriors(int32_t n_loci, const int32_t* locus_read_off, const i
                           const int32_t* read_weight, double* post_out, double* sample_ll_out,
                           int32_t* best_out, double* total_ll_out);
 
+/* EMStutterGenotyper::train for every locus of the batch (em_stutter_genotyper.cpp:170-226). */
+int32_t oracle_em_train(const hipstr_em_batch_t* batch, int32_t max_iter, double min_LL_abs_change,
+                        double min_LL_frac_change, double* params_out, uint8_t* converged_out,
+                        int32_t* iters_out, double* ll_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -228,4 +228,31 @@ int32_t ref_posteriors(int32_t n_loci, const int32_t* locus_read_off, const int3
   return HIPSTR_OK;
 }
 
+// EMStutterGenotyper::train for every locus (seam B4).
+int32_t ref_em_train(const hipstr_em_batch_t* bt, int32_t max_iter, double min_abs, double min_frac, double* params_out,
+                     uint8_t* converged_out, int32_t* iters_out, double* ll_out) {
+  ensure_init();
+  (void)iters_out; (void)ll_out;   // not observable through the reference's public interface
+  std::stringstream sink;
+  for (int l = 0; l < bt->n_loci; l++) {
+    const int r0 = bt->locus_read_off[l], r1 = bt->locus_read_off[l + 1];
+    const int S = bt->locus_sample_off[l + 1] - bt->locus_sample_off[l];
+    std::vector<std::vector<int> > bps(S);
+    std::vector<std::vector<double> > p1(S), p2(S);
+    std::vector<std::string> names;
+    for (int s = 0; s < S; s++) { std::stringstream ss; ss << "S" << s; names.push_back(ss.str()); }
+    for (int r = r0; r < r1; r++) {
+      bps[bt->sample_label[r]].push_back(bt->num_bps[r]);
+      p1[bt->sample_label[r]].push_back(bt->log_p1[r]);
+      p2[bt->sample_label[r]].push_back(bt->log_p2[r]);
+    }
+    EMStutterGenotyper em(bt->haploid[l] != 0, bt->motif_len[l], bps, p1, p2, names, bt->ref_allele[l]);
+    converged_out[l] = em.train(max_iter, min_abs, min_frac, false, sink);
+    StutterModel* m = em.get_stutter_model();
+    const char which[3] = {'P', 'U', 'D'};
+    for (int k = 0; k < 6; k++) params_out[6 * (size_t)l + k] = m->get_parameter(k < 3, which[k % 3]);
+  }
+  return HIPSTR_OK;
+}
+
 }  // extern "C"
