@@ -174,6 +174,16 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons}
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version
+    banner, warnings) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -213,7 +223,7 @@ def main():
             tot_t += wall
         v = tot_aln / tot_t
         sample = "%d loci per step (1 per core) of the same synthetic workload" % n
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / a.steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
@@ -376,7 +386,7 @@ def main():
             "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks.summary() if clocks else None,
             "synth_seconds": t_gen, "checksum_total_ll": checksum,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
