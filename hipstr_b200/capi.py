@@ -67,6 +67,36 @@ class GenotypeOut(C.Structure):
                 ("best", C.c_void_p), ("total_ll", C.c_void_p)]
 
 
+class EmBatch(C.Structure):
+    """hipstr_em_batch_t"""
+    _fields_ = [("n_loci", C.c_int32), ("locus_read_off", c_i32p), ("locus_sample_off", c_i32p), ("num_bps", c_i32p),
+                ("sample_label", c_i32p), ("log_p1", c_f64p), ("log_p2", c_f64p), ("motif_len", c_i32p),
+                ("ref_allele", c_i32p), ("haploid", c_u8p)]
+
+
+def make_em_batch(locus_read_off, locus_sample_off, num_bps, sample_label, log_p1, log_p2, motif_len, ref_allele, haploid):
+    arrs = [np.ascontiguousarray(a, dt) for a, dt in ((locus_read_off, np.int32), (locus_sample_off, np.int32), (num_bps, np.int32),
+            (sample_label, np.int32), (log_p1, np.float64), (log_p2, np.float64), (motif_len, np.int32), (ref_allele, np.int32),
+            (haploid, np.uint8))]
+    b = EmBatch(len(arrs[6]), ptr(arrs[0], c_i32p), ptr(arrs[1], c_i32p), ptr(arrs[2], c_i32p), ptr(arrs[3], c_i32p),
+                ptr(arrs[4], c_f64p), ptr(arrs[5], c_f64p), ptr(arrs[6], c_i32p), ptr(arrs[7], c_i32p), ptr(arrs[8], c_u8p))
+    b._keep = arrs
+    return b
+
+
+def em_train(fn, batch, max_iter=100, min_abs=0.01, min_frac=0.001, ctx_handle=None):
+    """Calls an em_train entry point (product, oracle or reference harness share the signature after the context)."""
+    L = batch.n_loci
+    prm = np.zeros(6 * L)
+    conv = np.zeros(L, np.uint8)
+    it = np.zeros(L, np.int32)
+    ll = np.zeros(L)
+    args = [C.byref(batch), C.c_int32(max_iter), C.c_double(min_abs), C.c_double(min_frac), ptr(prm, c_f64p), ptr(conv, c_u8p),
+            ptr(it, c_i32p), ptr(ll, c_f64p)]
+    st = fn(ctx_handle, *args) if ctx_handle is not None else fn(*args)
+    return st, prm.reshape(L, 6), conv, it, ll
+
+
 STATUS = {0: "OK", 1: "NO_DEVICE", 2: "CUDA", 3: "BAD_ARG", 4: "UNSUPPORTED", 5: "INVALID_SEED", 6: "BAD_CIGAR"}
 
 
@@ -159,6 +189,9 @@ def load():
     lib.hipstr_genotype_batch_dev.argtypes = [vp, vp, GO]
     lib.hipstr_free_genotype_batch.restype = None
     lib.hipstr_free_genotype_batch.argtypes = [vp, vp]
+    lib.hipstr_em_train_host.restype = C.c_int32
+    lib.hipstr_em_train_host.argtypes = [vp, C.POINTER(EmBatch), C.c_int32, C.c_double, C.c_double, c_f64p, c_u8p, c_i32p,
+                                         c_f64p]
     lib.hipstr_last_traffic.restype = None
     lib.hipstr_last_traffic.argtypes = [vp, c_i64p, c_i64p, c_i32p]
     lib.hipstr_collect_timing.restype = C.c_int32
@@ -379,6 +412,12 @@ class Context:
 
     def free_genotype(self, handle):
         self.lib.hipstr_free_genotype_batch(self.h, handle)
+
+    def em_train(self, batch, max_iter=100, min_abs=0.01, min_frac=0.001):
+        """hipstr_em_train_host -> (params [L][6], converged [L], iterations [L], final LL [L])."""
+        st, prm, conv, it, ll = em_train(self.lib.hipstr_em_train_host, batch, max_iter, min_abs, min_frac, self.h)
+        self._check(st, "em_train_host")
+        return prm, conv, it, ll
 
     def traffic(self):
         a, b, n = C.c_int64(), C.c_int64(), C.c_int32()

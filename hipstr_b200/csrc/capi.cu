@@ -4,6 +4,8 @@
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -641,6 +643,104 @@ hipstr_status_t hipstr_posteriors_host(hipstr_ctx_t* ctx, int32_t n_loci, const 
   if (best_out) CU(get(ctx, best_out, m[8].p, (size_t)S * 2));
   if (total_ll_out) CU(get(ctx, total_ll_out, m[9].p, (size_t)n_loci));
   CU(cudaStreamSynchronize(s));
+  end_call(ctx);
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_em_train_host(hipstr_ctx_t* ctx, const hipstr_em_batch_t* b, int32_t max_iter, double min_abs,
+                                     double min_frac, double* params_out, uint8_t* converged_out, int32_t* iters_out,
+                                     double* ll_out) {
+  if (!ctx || !b || b->n_loci < 0 || !params_out || !converged_out) return HIPSTR_ERR_BAD_ARG;
+  if (b->n_loci == 0) return HIPSTR_OK;
+  if (!b->locus_read_off || !b->locus_sample_off || !b->num_bps || !b->sample_label || !b->log_p1 || !b->log_p2 ||
+      !b->motif_len || !b->ref_allele || !b->haploid)
+    return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
+  const int n_loci = b->n_loci;
+  const int32_t R = b->locus_read_off[n_loci], S = b->locus_sample_off[n_loci];
+  std::vector<EmLocus> loci((size_t)n_loci);
+  std::vector<int32_t> allele_of((size_t)R), sample_read_off((size_t)S + 1), bps;
+  std::vector<double> gt_prior, params((size_t)n_loci * 6);
+  int64_t post_off = 0, row_off = 0;
+  int max_alleles = 1;
+  for (int l = 0; l < n_loci; l++) {
+    const int r0 = b->locus_read_off[l], r1 = b->locus_read_off[l + 1];
+    const int s0 = b->locus_sample_off[l], Sl = b->locus_sample_off[l + 1] - s0;
+    if (b->motif_len[l] < 1 || b->motif_len[l] > 9) return fail(ctx, HIPSTR_ERR_BAD_ARG, "motif length must be 1..9");
+    // allele sizes: reference first, the rest ascending (em_stutter_genotyper.h:59-81)
+    std::vector<int32_t> sizes(b->num_bps + r0, b->num_bps + r1);
+    std::sort(sizes.begin(), sizes.end());
+    sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
+    sizes.erase(std::remove(sizes.begin(), sizes.end(), b->ref_allele[l]), sizes.end());
+    sizes.insert(sizes.begin(), b->ref_allele[l]);
+    const int A = (int)sizes.size();
+    if (A > 100) return fail(ctx, HIPSTR_ERR_UNSUPPORTED, "more than 100 distinct STR sizes at one locus");
+    max_alleles = std::max(max_alleles, A);
+    EmLocus& L = loci[l];
+    L.read0 = r0; L.n_reads = r1 - r0; L.sample0 = s0; L.n_samples = Sl;
+    L.n_alleles = A; L.period = b->motif_len[l]; L.haploid = b->haploid[l];
+    L.allele_off = (int32_t)bps.size();
+    L.post_off = post_off; L.row_off = row_off;
+    post_off += (int64_t)Sl * A * A;
+    row_off += (int64_t)Sl * A;
+    // reads: allele index, per-sample ranges; init_log_gt_priors (em_stutter_genotyper.cpp:10-19) with the host libm
+    std::vector<int> per_sample((size_t)Sl, 0);
+    int at = r0;
+    for (int s = 0; s < Sl; s++) {
+      sample_read_off[s0 + s] = at;
+      while (at < r1 && b->sample_label[at] == s) at++;
+      per_sample[s] = at - sample_read_off[s0 + s];
+    }
+    if (at != r1) return fail(ctx, HIPSTR_ERR_BAD_ARG, "reads are not sample-major or a sample label is out of range");
+    std::vector<double> prior((size_t)A, 1.0);
+    for (int r = r0; r < r1; r++) {
+      const int a = (int)(std::lower_bound(sizes.begin() + 1, sizes.end(), b->num_bps[r]) - sizes.begin());
+      allele_of[r] = (b->num_bps[r] == b->ref_allele[l]) ? 0 : a;
+      prior[allele_of[r]] += 1.0 / per_sample[b->sample_label[r]];
+    }
+    double total = 0.0;
+    for (int a = 0; a < A; a++) total += prior[a];
+    const double log_total = std::log(total);
+    for (int a = 0; a < A; a++) gt_prior.push_back(std::log(prior[a]) - log_total);
+    bps.insert(bps.end(), sizes.begin(), sizes.end());
+    const double init[6] = {0.9, 0.1, 0.1, 0.8, 0.01, 0.01};   // init_stutter_model (:58-61)
+    std::copy(init, init + 6, params.begin() + 6 * (size_t)l);
+  }
+  sample_read_off[S] = R;
+  cudaStream_t st = ctx->stream;
+  DevBuf* m = ctx->d_misc;
+  DevBuf* o = ctx->d_out;
+  CU(put(m[0], loci, st));
+  CU(put(m[1], allele_of, st));
+  CU(put(m[2], b->sample_label, (size_t)R, st));
+  CU(put(m[3], sample_read_off, st));
+  CU(put(m[4], b->log_p1, (size_t)R, st));
+  CU(put(m[5], b->log_p2, (size_t)R, st));
+  CU(put(m[6], bps, st));
+  CU(put(m[7], gt_prior, st));
+  CU(put(m[8], params, st));
+  CU(o[0].reserve(std::max<size_t>((size_t)post_off * sizeof(double), 16)));
+  CU(o[1].reserve(std::max<size_t>((size_t)row_off * sizeof(double), 16)));
+  CU(o[2].reserve(std::max<size_t>((size_t)S * sizeof(double), 16)));
+  CU(o[3].reserve((size_t)n_loci));
+  CU(o[4].reserve((size_t)n_loci * sizeof(int32_t)));
+  CU(o[5].reserve((size_t)n_loci * sizeof(double)));
+  EmParams p;
+  p.n_loci = n_loci; p.max_iter = max_iter; p.min_abs = min_abs; p.min_frac = min_frac;
+  p.loci = (const EmLocus*)m[0].p; p.allele_of = (const int32_t*)m[1].p; p.sample_label = (const int32_t*)m[2].p;
+  p.sample_read_off = (const int32_t*)m[3].p; p.log_p1 = (const double*)m[4].p; p.log_p2 = (const double*)m[5].p;
+  p.bps = (const int32_t*)m[6].p; p.gt_prior = (double*)m[7].p; p.params = (double*)m[8].p;
+  p.int_logs = ctx->d_int_logs; p.log_one_half = host_tables().log_one_half;
+  p.post = (double*)o[0].p; p.rowlse = (double*)o[1].p; p.sample_ll = (double*)o[2].p;
+  p.converged = (uint8_t*)o[3].p; p.iters = (int32_t*)o[4].p; p.final_ll = (double*)o[5].p;
+  CU(launch_em(p, max_alleles, st));
+  ctx->last_launches = 1;
+  CU(get(ctx, params_out, m[8].p, (size_t)n_loci * 6));
+  CU(get(ctx, converged_out, o[3].p, (size_t)n_loci));
+  if (iters_out) CU(get(ctx, iters_out, o[4].p, (size_t)n_loci));
+  if (ll_out) CU(get(ctx, ll_out, o[5].p, (size_t)n_loci));
+  CU(cudaStreamSynchronize(st));
   end_call(ctx);
   return HIPSTR_OK;
 }

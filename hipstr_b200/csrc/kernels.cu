@@ -746,4 +746,240 @@ cudaError_t launch_posteriors(const PostParams& p, cudaStream_t stream) {
   return e;
 }
 
+// ------------------------------------------------------------------------------------------
+// K4: EM stutter learner.  One CTA per locus runs EMStutterGenotyper::train
+// (em_stutter_genotyper.cpp:170-226) to convergence: E-step = length-only alignment
+// probabilities (a log_stutter_pmf table) + sample posteriors + read phase posteriors (recomputed
+// on the fly, never materialised: the reference's R*A*A*2 array is the largest object of the
+// learner), M-step = allele frequencies + the 7 approximate log-sum-exp buckets of the stutter
+// parameters.  Exact exp/log come from CUDA's libm (ulp-level differences from glibc); the
+// approximate log-sum-exps are the bit-faithful replicas of fastapprox.cuh.
+// ------------------------------------------------------------------------------------------
+#define EM_THREADS 512
+#define EM_WARPS (EM_THREADS / 32)
+#define EM_NEG_MAX (-1.7976931348623157e308)
+
+struct EmModel {   // StutterModel log parameters (stutter_model.h:43-58)
+  double in_step, in_nostep, in_up, in_down, out_step, out_nostep, out_up, out_down, equal;
+};
+__device__ __forceinline__ double em_pmf(const EmModel& m, int period, int sample_bps, int read_bps) {   // stutter_model.cpp:29-53
+  const int d = read_bps - sample_bps;
+  if (d % period != 0) {
+    const int eff = d - d / period;
+    return eff < 0 ? m.out_down + m.out_nostep + m.out_step * (-eff - 1) : m.out_up + m.out_nostep + m.out_step * (eff - 1);
+  }
+  const int reps = d / period;
+  if (reps == 0) return m.equal;
+  return reps < 0 ? m.in_down + m.in_nostep + m.in_step * (-reps - 1) : m.in_up + m.in_nostep + m.in_step * (reps - 1);
+}
+__device__ __forceinline__ double exact_lse2(double a, double b) {   // mathops.cpp:51-56
+  return a > b ? a + log(1 + exp(b - a)) : b + log(1 + exp(a - b));
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = dmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(EM_THREADS) k_em_train(const EmParams P) {
+  extern __shared__ __align__(16) double em_smem[];
+  const EmLocus L = P.loci[blockIdx.x];
+  const int A = L.n_alleles, S = L.n_samples, R = L.n_reads, AA = A * A;
+  double* s_T = em_smem;                       // [A][A]: log_stutter_pmf(bps[a], bps[c])
+  double* s_prior = s_T + AA;                  // [A]
+  double* s_newprior = s_prior + A;            // [A]
+  double* s_red = s_newprior + A;              // [7][EM_WARPS]
+  double* s_bucket = s_red + 7 * EM_WARPS;     // [7]
+  __shared__ EmModel s_model;
+  __shared__ double s_prm[6];
+  __shared__ double s_LL, s_newLL;
+  __shared__ int s_state;                      // 0 = continue, 1 = converged
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int32_t* bps = P.bps + L.allele_off;
+  double* post = P.post + L.post_off;
+  double* rowlse = P.rowlse + L.row_off;
+  double* sll = P.sample_ll + L.sample0;
+  const int32_t* allele_of = P.allele_of + L.read0;
+  const int32_t* label = P.sample_label + L.read0;
+  const double* p1 = P.log_p1 + L.read0;
+  const double* p2 = P.log_p2 + L.read0;
+  const double LH = P.log_one_half;
+
+  for (int a = tid; a < A; a += EM_THREADS) s_prior[a] = P.gt_prior[L.allele_off + a];
+  if (tid < 6) s_prm[tid] = P.params[6 * (size_t)blockIdx.x + tid];
+  if (tid == 0) { s_LL = EM_NEG_MAX; s_state = 0; }
+  __syncthreads();
+  int iter = 1;
+  bool converged = false;
+  while (iter <= P.max_iter) {
+    if (tid == 0) {
+      EmModel m;
+      m.in_step = log(1 - s_prm[0]); m.in_nostep = log(s_prm[0]); m.in_up = log(s_prm[1]); m.in_down = log(s_prm[2]);
+      m.out_step = log(1 - s_prm[3]); m.out_nostep = log(s_prm[3]); m.out_up = log(s_prm[4]); m.out_down = log(s_prm[5]);
+      m.equal = log(1 - s_prm[1] - s_prm[2] - s_prm[4] - s_prm[5]);
+      s_model = m;
+    }
+    __syncthreads();
+    for (int d = tid; d < AA; d += EM_THREADS) s_T[d] = em_pmf(s_model, L.period, bps[d / A], bps[d % A]);
+    __syncthreads();
+
+    // ---- E-step: sample posteriors (genotyper.cpp:44-80 with the allele-frequency priors of :129-144) ----
+    for (int s = warp; s < S; s += EM_WARPS) {
+      const int r0 = P.sample_read_off[L.sample0 + s] - L.read0, r1 = P.sample_read_off[L.sample0 + s + 1] - L.read0;
+      double* sp = post + (size_t)s * AA;
+      double mx = EM_NEG_MAX;
+      for (int d = lane; d < AA; d += 32) {
+        const int a = d / A, b = d % A;
+        double acc = L.haploid ? (a == b ? s_prior[a] : EM_NEG_MAX / 2) : s_prior[a] + s_prior[b];
+        for (int r = r0; r < r1; r++) {
+          const int c = allele_of[r];
+          acc += lse2(LH + p1[r] + s_T[a * A + c], LH + p2[r] + s_T[b * A + c]);
+        }
+        sp[d] = acc;
+        mx = dmax(mx, acc);
+      }
+      mx = warp_max(mx);
+      double sum = 0.0;
+      for (int d = lane; d < AA; d += 32) sum += exp(sp[d] - mx);
+      sum = warp_sum(sum);
+      const double total = mx + log(sum);
+      for (int d = lane; d < AA; d += 32) sp[d] -= total;
+      if (lane == 0) sll[s] = total;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int s = 0; s < S; s++) t += sll[s];
+      s_newLL = t;
+      if (t < s_LL + 1e-10) { s_state = 1; s_LL = t; }   // em_stutter_genotyper.cpp:195-199
+    }
+    __syncthreads();
+    if (s_state) { converged = true; break; }
+
+    // ---- M-step 1: allele frequencies (recalc_log_gt_priors, :21-56) ----
+    for (int i = tid; i < S * A; i += EM_THREADS) {   // log_sum_exp over the second allele
+      const double* row = post + (size_t)i * A;
+      double mx = row[0];
+      for (int b = 1; b < A; b++) mx = dmax(mx, row[b]);
+      double sum = 0.0;
+      for (int b = 0; b < A; b++) sum += exp(row[b] - mx);
+      rowlse[i] = mx + log(sum);
+    }
+    __syncthreads();
+    for (int b = warp; b < A; b += EM_WARPS) {
+      double mx = EM_NEG_MAX / 2;
+      for (int s = lane; s < S; s += 32) mx = dmax(mx, rowlse[(size_t)s * A + b]);
+      for (int i = lane; i < S * A; i += 32) mx = dmax(mx, post[(size_t)i * A + b]);
+      mx = warp_max(mx);
+      double sum = 0.0;
+      for (int s = lane; s < S; s += 32) sum += exp(rowlse[(size_t)s * A + b] - mx);
+      for (int i = lane; i < S * A; i += 32) sum += exp(post[(size_t)i * A + b] - mx);
+      sum = warp_sum(sum);
+      if (lane == 0) s_newprior[b] = mx + log(sum);
+    }
+    __syncthreads();
+
+    // ---- M-step 2: stutter parameters (recalc_stutter_model, :63-127; phase posteriors :152-168) ----
+    // buckets: 0 in_up 1 in_down 2 in_eq 3 in_diffs 4 out_up 5 out_down 6 out_diffs
+    for (int pass = 0; pass < 2; pass++) {
+      double acc[7];
+      const double log11 = log(1.1);
+      if (pass == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; k++) acc[k] = tid == 0 ? 0.0 : EM_NEG_MAX;       // pseudocount terms (:67-70)
+        if (tid == 0) { acc[3] = dmax(0.0, log11); acc[6] = dmax(0.0, log11); }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 7; k++) acc[k] = tid == 0 ? lse_term(0.0, s_bucket[k]) : 0.0;
+        if (tid == 0) { acc[3] += lse_term(log11, s_bucket[3]); acc[6] += lse_term(log11, s_bucket[6]); }
+      }
+      const long long total_items = (long long)R * AA;
+      for (long long it = tid; it < total_items; it += EM_THREADS) {
+        const int r = (int)(it / AA), d = (int)(it % AA);
+        const int a = d / A, b = d % A;
+        const int c = allele_of[r];
+        const double one = LH + p1[r] + s_T[a * A + c], two = LH + p2[r] + s_T[b * A + c];
+        const double both = lse2(one, two);
+        const double g = post[(size_t)label[r] * AA + d];
+        const int rb = bps[c];
+#pragma unroll
+        for (int ph = 0; ph < 2; ph++) {
+          const double f = g + ((ph == 0 ? one : two) - both);
+          const int diff = rb - bps[ph == 0 ? a : b];
+          int k_main, k_diff = -1, eff = 0;
+          if (diff == 0) k_main = 2;
+          else if (diff % L.period != 0) { eff = diff - diff / L.period; k_main = diff > 0 ? 4 : 5; k_diff = 6; }
+          else { eff = diff / L.period; k_main = diff > 0 ? 0 : 1; k_diff = 3; }
+          const double fd = k_diff >= 0 ? f + P.int_logs[eff < 0 ? -eff : eff] : 0.0;
+#pragma unroll
+          for (int k = 0; k < 7; k++) {
+            if (k == k_main) acc[k] = pass ? acc[k] + lse_term(f, s_bucket[k]) : dmax(acc[k], f);
+            if (k == k_diff) acc[k] = pass ? acc[k] + lse_term(fd, s_bucket[k]) : dmax(acc[k], fd);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 7; k++) {
+        const double v = pass ? warp_sum(acc[k]) : warp_max(acc[k]);
+        if (lane == 0) s_red[k * EM_WARPS + warp] = v;
+      }
+      __syncthreads();
+      if (tid < 7) {
+        double v = s_red[tid * EM_WARPS];
+        for (int w = 1; w < EM_WARPS; w++) v = pass ? v + s_red[tid * EM_WARPS + w] : dmax(v, s_red[tid * EM_WARPS + w]);
+        s_bucket[tid] = pass ? lse_finish(s_bucket[tid], v) : v;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const double iu = s_bucket[0], id = s_bucket[1], ie = s_bucket[2], idf = s_bucket[3];
+      const double ou = s_bucket[4], od = s_bucket[5], odf = s_bucket[6];
+      const double ot = lse2(ou, od);
+      double prm[6];
+      prm[0] = fmin(0.999, exp(exact_lse2(iu, id) - idf));
+      prm[3] = fmin(0.999, exp(ot - odf));
+      const double m3 = dmax(dmax(iu, id), ie);
+      const double in_all = m3 + log(exp(iu - m3) + exp(id - m3) + exp(ie - m3));   // mathops.cpp:58-61
+      const double lt = exact_lse2(in_all, ot);
+      prm[1] = exp(iu - lt); prm[2] = exp(id - lt); prm[4] = exp(ou - lt); prm[5] = exp(od - lt);
+      bool close = true;
+      for (int k = 0; k < 6; k++) { close = close && fabs(s_prm[k] - prm[k]) < 0.0001; s_prm[k] = prm[k]; }
+      const double abs_change = s_newLL - s_LL, frac_change = -(s_newLL - s_LL) / s_LL;
+      s_LL = s_newLL;
+      if ((abs_change < P.min_abs && frac_change < P.min_frac) || close) s_state = 1;
+      // normalise the new allele frequencies (:50-55)
+      double mx = s_newprior[0];
+      for (int a = 1; a < A; a++) mx = dmax(mx, s_newprior[a]);
+      double sum = 0.0;
+      for (int a = 0; a < A; a++) sum += exp(s_newprior[a] - mx);
+      const double total = mx + log(sum);
+      for (int a = 0; a < A; a++) s_prior[a] = s_newprior[a] - total;
+    }
+    __syncthreads();
+    if (s_state) { converged = true; break; }
+    iter++;
+  }
+  if (tid < 6) P.params[6 * (size_t)blockIdx.x + tid] = s_prm[tid];
+  for (int a = tid; a < A; a += EM_THREADS) P.gt_prior[L.allele_off + a] = s_prior[a];
+  if (tid == 0) {
+    P.converged[blockIdx.x] = converged;
+    P.iters[blockIdx.x] = iter < P.max_iter ? iter : P.max_iter;
+    P.final_ll[blockIdx.x] = s_LL;
+  }
+}
+
+cudaError_t launch_em(const EmParams& p, int max_alleles, cudaStream_t stream) {
+  if (p.n_loci <= 0) return cudaSuccess;
+  const size_t smem = ((size_t)max_alleles * max_alleles + 2 * (size_t)max_alleles + 7 * EM_WARPS + 7) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(k_em_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_em_train<<<p.n_loci, EM_THREADS, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace hipstr

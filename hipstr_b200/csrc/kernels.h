@@ -78,5 +78,37 @@ struct PostParams {
 };
 cudaError_t launch_posteriors(const PostParams& p, cudaStream_t stream);
 
+/* K4: EM stutter learner (em_stutter_genotyper.cpp:10-226), one CTA per locus for the whole training loop. */
+struct EmLocus {            /* one per locus */
+  int32_t read0, n_reads;   /* global read range */
+  int32_t sample0, n_samples;
+  int32_t n_alleles, period, haploid;
+  int32_t allele_off;       /* into bps / gt_prior */
+  int64_t post_off;         /* into post scratch: S * A * A doubles */
+  int64_t row_off;          /* into row scratch: S * A doubles */
+};
+struct EmParams {
+  int32_t n_loci, max_iter;
+  double min_abs, min_frac;
+  const EmLocus* loci;
+  const int32_t* allele_of;       /* [R] allele index of each read */
+  const int32_t* sample_label;    /* [R] sample of each read, local to its locus */
+  const int32_t* sample_read_off; /* [S_total + 1] global read range of each sample */
+  const double* log_p1;
+  const double* log_p2;
+  const int32_t* bps;             /* [sum A] bp size per allele (reference allele first) */
+  double* gt_prior;               /* [sum A] in: init_log_gt_priors; updated in place */
+  const double* int_logs;
+  double log_one_half;
+  double* post;                   /* scratch */
+  double* rowlse;                 /* scratch */
+  double* sample_ll;              /* scratch [S_total] */
+  double* params;                 /* [n_loci][6] in: initial model; out: learned model */
+  uint8_t* converged;             /* [n_loci] */
+  int32_t* iters;                 /* [n_loci] */
+  double* final_ll;               /* [n_loci] */
+};
+cudaError_t launch_em(const EmParams& p, int max_alleles, cudaStream_t stream);
+
 }  // namespace hipstr
 #endif

@@ -105,3 +105,34 @@ def n_haps_of(blocks):
     for _, opts in blocks:
         h *= len(opts)
     return h
+
+
+# ---- EM stutter learner inputs (BASELINE.json configs[3] shape, scaled down) --------------------------
+EM_CASES = [
+    ("em_diploid", dict(n_loci=3, n_samples=40, reads_per_sample=8, n_alleles=6, read_len=150, seed=4100, stutter_rate=0.15), 0),
+    ("em_many_alleles", dict(n_loci=2, n_samples=60, reads_per_sample=5, n_alleles=12, read_len=150, seed=4200, stutter_rate=0.3), 0),
+    ("em_haploid_p2", dict(n_loci=2, n_samples=30, reads_per_sample=6, n_alleles=5, read_len=150, seed=4300, stutter_rate=0.2,
+                           period=2, ref_copies=15), 1),
+    ("em_cfg4_shape", dict(n_loci=2, n_samples=120, reads_per_sample=5, n_alleles=32, read_len=150, seed=4400, stutter_rate=0.1), 0),
+]
+
+
+def em_case(name, out_of_frame=0.03):
+    """Returns (Synth, hipstr_em_batch_t).  Read STR sizes come from the simulated reads (what ExtractCigar would
+    report); a few reads get a +/-1 bp out-of-frame artefact so every bucket of the M-step is exercised."""
+    from hipstr_b200.capi import make_em_batch
+    for n, kw, haploid in EM_CASES:
+        if n == name:
+            s = Synth(**kw)
+            period = kw.get("period", 4)
+            ref_bp = period * kw.get("ref_copies", 12)
+            rng = np.random.default_rng(kw["seed"])
+            diff = np.ctypeslib.as_array(s.view.read_bp_diff, shape=(s.n_reads,)).copy()
+            jitter = rng.random(s.n_reads) < out_of_frame
+            diff[jitter] += rng.choice([-1, 1], int(jitter.sum()))
+            p1 = np.log(rng.uniform(0.2, 1.0, s.n_reads))
+            p2 = np.log(rng.uniform(0.2, 1.0, s.n_reads))
+            b = make_em_batch(s.locus_read_off, s.locus_sample_off, diff + ref_bp, s.sample_label, p1, p2,
+                              np.full(s.n_loci, period), np.full(s.n_loci, ref_bp), np.full(s.n_loci, haploid))
+            return s, b
+    raise KeyError(name)

@@ -56,3 +56,13 @@ def main():
 
 if __name__ == "__main__":
     main()
+# tests/golden/em_params.json (EM stutter learner) is produced the same way: ref_em_train of the compiled reference
+# on cases.EM_CASES; see the snippet in the git history of tests/test_em.py / run:
+#   python - <<'PY'
+#   import json, ctypes as C, cases, checkers
+#   from hipstr_b200.capi import EmBatch, c_f64p, c_i32p, c_u8p, em_train
+#   f = checkers.ref().ref_em_train; f.restype = C.c_int32
+#   f.argtypes = [C.POINTER(EmBatch), C.c_int32, C.c_double, C.c_double, c_f64p, c_u8p, c_i32p, c_f64p]
+#   json.dump({n: dict(params=em_train(f, cases.em_case(n)[1])[1].tolist(), converged=em_train(f, cases.em_case(n)[1])[2].tolist())
+#              for n, _, _ in cases.EM_CASES}, open("tests/golden/em_params.json", "w"), indent=1)
+#   PY
