@@ -35,14 +35,14 @@ struct DevBuf {
 };
 
 struct hipstr_dev_batch {
-  DevBuf pools, bases, quals, hapsides, hapbytes, blocks, reps, progs, mask, jobs[kNumColVariants];
+  DevBuf pools, bases, quals, hapsides, hapbytes, blocks, reps, progs, logrun, tabs, mask, jobs[kNumColVariants];
   int32_t n_jobs[kNumColVariants];
   int32_t n_max[kNumColVariants], l_max[kNumColVariants];
   int64_t n_out = 0, n_alignments = 0;
   bool has_mask = false;
   void release() {
     pools.release(); bases.release(); quals.release(); hapsides.release(); hapbytes.release();
-    blocks.release(); reps.release(); progs.release(); mask.release();
+    blocks.release(); reps.release(); progs.release(); logrun.release(); tabs.release(); mask.release();
     for (auto& j : jobs) j.release();
   }
 };
@@ -78,7 +78,7 @@ struct hipstr_ctx {
   FlatBatch flat;                        // host staging (page-locked), reused by every call
   hipstr_dev_batch scratch;              // reused by hipstr_align_batch_host
   hipstr_dev_genotype gscratch;          // reused by hipstr_genotype_batch_host
-  DevBuf d_ll, d_pos, d_misc[12], d_out[6];
+  DevBuf d_ll, d_pos, d_misc[12], d_out[6], d_last, d_counters;
   double* d_debug = nullptr;             // test hook, see hipstr_debug_lastcols
 };
 
@@ -143,6 +143,8 @@ hipstr_status_t stage(hipstr_ctx* ctx, const hipstr_align_batch_t* batch, hipstr
   CU(put(d.blocks, f.blocks, s));
   CU(put(d.reps, f.reps, s));
   CU(put(d.progs, f.progs, s));
+  CU(put(d.logrun, f.prog_logrun, s));
+  CU(put(d.tabs, f.rep_tabs, s));
   CU(put(d.mask, f.hap_mask, s));
   for (int v = 0; v < kNumColVariants; v++) {
     CU(put(d.jobs[v], f.jobs[v], s));
@@ -169,20 +171,29 @@ hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll
   p.blocks = (const DevBlock*)d.blocks.p;
   p.reps = (const DevRep*)d.reps.p;
   p.progs = (const DevProgEntry*)d.progs.p;
+  p.prog_logrun = (const double*)d.logrun.p;
+  p.rep_tabs = (const int32_t*)d.tabs.p;
   p.hap_mask = d.has_mask ? (const uint8_t*)d.mask.p : nullptr;
   p.qual_lut = ctx->d_qual_lut;
   p.trans = ctx->d_trans;
   p.int_logs = ctx->d_int_logs;
   p.ll_out = ll_dev;
   p.pos_out = pos_dev;
+  int l_all = 2;
+  for (int v = 0; v < kNumColVariants; v++) if (d.n_jobs[v]) l_all = std::max(l_all, d.l_max[v]);
+  CU(ctx->d_last.reserve((size_t)HIPSTR_MAX_ALIGN_CTAS * HIPSTR_WARPS_PER_CTA * 2 * l_all * sizeof(double)));
+  CU(ctx->d_counters.reserve(kNumColVariants * sizeof(int32_t)));
+  CU(cudaMemsetAsync(ctx->d_counters.p, 0, kNumColVariants * sizeof(int32_t), ctx->stream));
+  p.last_scratch = (double*)ctx->d_last.p;
   for (int v = kNumColVariants - 1; v >= 0; v--) {   // longest reads first
     if (d.n_jobs[v] == 0) continue;
     p.jobs = (const DevJob*)d.jobs[v].p;
     p.n_jobs = d.n_jobs[v];
     p.n_max = d.n_max[v];
-    p.l_max = d.l_max[v];
+    p.l_max = l_all;
     p.debug_out = ctx->d_debug;
-    CU(launch_align(v, p, ctx->stream));
+    p.job_counter = (int32_t*)ctx->d_counters.p + v;
+    CU(launch_align(v, p, HIPSTR_MAX_ALIGN_CTAS, ctx->stream, nullptr));
     ctx->last_launches++;
   }
   return HIPSTR_OK;
@@ -347,6 +358,8 @@ void hipstr_destroy(hipstr_ctx_t* ctx) {
   ctx->gscratch.release();
   ctx->d_ll.release();
   ctx->d_pos.release();
+  ctx->d_last.release();
+  ctx->d_counters.release();
   for (auto& b : ctx->d_misc) b.release();
   for (auto& b : ctx->d_out) b.release();
   for (auto& ev : ctx->pending) for (auto& e : ev.e) cudaEventDestroy(e);

@@ -43,7 +43,7 @@ void host_free(void* p) { if (g_free) g_free(p); else std::free(p); }
 
 void FlatBatch::clear() {
   pools.clear(); bases.clear(); quals.clear();
-  hapsides.clear(); hapbytes.clear(); blocks.clear(); reps.clear(); progs.clear(); hap_mask.clear();
+  hapsides.clear(); hapbytes.clear(); blocks.clear(); reps.clear(); progs.clear(); prog_logrun.clear(); rep_tabs.clear(); hap_mask.clear();
   for (auto& j : jobs) j.clear();
   n_out = n_alignments = 0;
 }
@@ -326,13 +326,16 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
             std::vector<std::vector<int> > runs(n_lag, std::vector<int>(B, 0));
             for (int k2 = 1; k2 <= n_lag; k2++)
               for (int i = k2 * p; i < B; i++) runs[k2 - 1][i] = sq[i - k2 * p] != sq[i] ? 0 : 1 + runs[k2 - 1][i - 1];
-            auto emit_entry = [&](int pos, int kind, int xa, int xb, double logrun) {
-              DevProgEntry e;
-              e.pos = pos; e.kind = (uint8_t)kind; e.xa = (uint8_t)xa; e.xb = (uint8_t)xb; e.pad = 0; e.logrun = logrun;
+            const int VB = HIPSTR_VAL_STRIDE * 8;   // bytes per read column of the emission table
+            auto emit_entry = [&](int pos, int off_a, int off_b, int moves, double logrun) {
+              DevProgEntry e = {pos, off_a, off_b, moves};
               out.progs.push_back(e);
+              out.prog_logrun.push_back(logrun);
             };
+            const int zero = 0;
             const HostTables& T = host_tables();
-            // insertion walk (StutterAlignerClass.cpp:75-97), full extent i > -B
+            // insertion walk (StutterAlignerClass.cpp:75-97), full extent i > -B; offsets are relative to
+            // column j - period, and every further inserted copy is `period` columns further left
             r.prog_off[0] = (int32_t)out.progs.size();
             {
               int i = 0;
@@ -341,15 +344,15 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
                 int step = 1;
                 if (-i + p < B) {
                   const int run = runs[0][bpos];
-                  if (run == 0) emit_entry(i, HIPSTR_PROG_UPDATE, cd[bpos], cd[bpos - p], 0.0);
-                  else { emit_entry(i, HIPSTR_PROG_COLLAPSED, 0, 0, T.int_logs[run]); step = run; }
+                  if (run == 0) emit_entry(i, i * VB + cd[bpos] * 8, i * VB + cd[bpos - p] * 8, 1, 0.0);
+                  else { emit_entry(i, zero, zero, 0, T.int_logs[run]); step = run; }
                 } else
-                  emit_entry(i, HIPSTR_PROG_PLAIN, 0, 0, 0.0);
+                  emit_entry(i, zero, zero, 0, 0.0);
                 i -= step;
               }
-              emit_entry(i, HIPSTR_PROG_END, 0, 0, 0.0);
+              emit_entry(i, zero, zero, 0, 0.0);
             }
-            // deletion walks (StutterAlignerClass.cpp:127-142), full extent i > -(B + D)
+            // deletion walks (StutterAlignerClass.cpp:127-142), full extent i > -(B + D); relative to column j
             for (int k2 = 1; k2 <= HIPSTR_MAX_ARTIFACT_UNITS; k2++) {
               r.prog_off[k2] = (int32_t)out.progs.size();
               if (k2 > n_del) continue;
@@ -359,12 +362,18 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
                 const int bpos = B - 1 + i;
                 int step = 1;
                 const int run = runs[k2 - 1][bpos];
-                if (run == 0) emit_entry(i, HIPSTR_PROG_UPDATE, cd[bpos + D], cd[bpos], 0.0);
-                else { emit_entry(i, HIPSTR_PROG_COLLAPSED, 0, 0, T.int_logs[run]); step = run; }
+                if (run == 0) emit_entry(i, i * VB + cd[bpos + D] * 8, i * VB + cd[bpos] * 8, 1, 0.0);
+                else { emit_entry(i, zero, zero, 0, T.int_logs[run]); step = run; }
                 i -= step;
               }
-              emit_entry(i, HIPSTR_PROG_END, 0, 0, 0.0);
+              emit_entry(i, zero, zero, 0, 0.0);
             }
+            // offset tables of the prefix sums of StutterAlignerClass::load_read (:12-53)
+            r.diag_off = (int32_t)out.rep_tabs.size();
+            for (int t = 0; t < B; t++) out.rep_tabs.push_back(-t * VB + cd[B - 1 - t] * 8);
+            r.ins_off = (int32_t)out.rep_tabs.size();
+            for (int t = 0; t < HIPSTR_MAX_ARTIFACT_UNITS * p; t++)
+              out.rep_tabs.push_back((t % p) < B ? -t * VB + cd[B - 1 - (t % p)] * 8 : -1);
             for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) {
               const int units = a - HIPSTR_MAX_ARTIFACT_UNITS;
               double v;
@@ -480,6 +489,9 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     loci.push_back(li);
   }
 
+  // the kernel prefetches two program entries ahead: pad the arrays
+  for (int k = 0; k < 2; k++) { DevProgEntry e = {-(1 << 30), 0, 0, 0}; out.progs.push_back(e); out.prog_logrun.push_back(0.0); }
+
   // ---- pooled reads: offsets (serial prefix), then a threaded fill of the big byte arrays ----
   const int n_pools = b->n_pools;
   std::vector<int32_t> pool_off((size_t)n_pools + 1);
@@ -569,7 +581,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
       if (v == 255) continue;
       if (v == 254) { count[0]++; continue; }
       count[v] += per_pool;
-      out.n_max[v] = std::max(out.n_max[v], pool_off[p + 1] - pool_off[p]);
+      out.n_max[v] = std::max(out.n_max[v], round_up(b->pool_seq_off[p + 1] - b->pool_seq_off[p], 4));
       out.l_max[v] = std::max(out.l_max[v], round_up(li.max_len, 2));
     }
   }

@@ -76,6 +76,8 @@ struct FlatBatch {
   std::vector<DevBlock> blocks;
   std::vector<DevRep> reps;
   std::vector<DevProgEntry> progs;
+  std::vector<double> prog_logrun;
+  std::vector<int32_t> rep_tabs;
   std::vector<uint8_t> hap_mask;             /* empty = all haplotypes */
   HostBuf<DevJob> jobs[kNumColVariants];
   int32_t n_max[kNumColVariants];            /* per variant: max read length (padded) */

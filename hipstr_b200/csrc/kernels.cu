@@ -52,121 +52,133 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 // log-likelihood of read column q against haplotype base x (log_correct if equal, else
 // log_error), so an emission is ONE shared-memory load.
 // ------------------------------------------------------------------------------------------
-struct RepCtx {
-  const uint8_t* s;        // oriented allele base codes (global, read-only)
-  const DevProgEntry* progs;
-  const DevRep* rep;
-  const double* int_logs;  // global
-  const double* val;       // shared: emission table of this side, [n_side][5]
-  const uint8_t* code;     // shared: read base codes of this side
-  const double* match;     // shared: match_probs_ by side column
-  double* terms;           // shared: this lane's term cache, slot s at terms[32 * s]
-  int B, p, n_side;
+// Shared-memory accesses of the evaluator use explicit 32-bit shared-window addresses: the compiler
+// otherwise rebuilds the generic->shared base (S2UR/ULEA) inside the hot loop.
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" :: "r"(addr), "d"(v));
+}
 
-  __device__ __forceinline__ double emit(int q, int b) const { return val[q * 5 + __ldg(s + b)]; }
-  __device__ __forceinline__ double lc(int q) const { return val[q * 5 + code[q]]; }
+#define HIPSTR_COL_BYTES (HIPSTR_VAL_STRIDE * 8)
+
+struct RepCtx {
+  const uint8_t* s;          // oriented allele base codes (global, read-only)
+  const DevProgEntry* progs;
+  const double* prog_logrun;
+  const int32_t* diag;       // global: byte offsets of the right-anchored diagonal (see DevRep)
+  const int32_t* ins_tab;    // global: byte offsets of the periodic-copy sum
+  const DevRep* rep;
+  const double* int_logs;    // global
+  unsigned val;              // shared address: emission table of this side, column q at val + q*COL_BYTES
+  const uint8_t* code;       // shared: read base codes of this side
+  const double* match;       // shared: match_probs_ by side column
+  unsigned terms;            // shared address: this lane's term cache, slot s at terms + 256*s
+  int B, p, n_side;
 };
 
-#define HIPSTR_TERM_SLOTS 16   /* terms of one fast_log_sum_exp call kept in shared memory per lane */
+#define HIPSTR_TERM_SLOTS 8    /* terms of one fast_log_sum_exp call kept in shared memory per lane ... */
+#define HIPSTR_TERM_EXTRA 8    /* ... and in a per-thread local array (L1) when a walk has more */
 
 // match_probs_[q] of StutterAlignerClass::load_read (StutterAlignerClass.cpp:12-53).
 __device__ __forceinline__ double rep_match_prob(const RepCtx& c, int q) {
   const int terms = min(q + 1, c.B);
+  const unsigned col = c.val + q * HIPSTR_COL_BYTES;
   double acc = 0.0;
-  const double* col = c.val + q * 5;
-  const uint8_t* sb = c.s + c.B - 1;
-  for (int t = 0; t < terms; t++, col -= 5, sb--) acc += col[__ldg(sb)];
+#pragma unroll 4
+  for (int t = 0; t < terms; t++) acc += lds_f64(col + __ldg(c.diag + t));
   return acc;
-}
-
-struct ProgStep { int pos; unsigned bits; double logrun; };
-__device__ __forceinline__ ProgStep load_step(const DevProgEntry* e) {
-  const int4 v = __ldg(reinterpret_cast<const int4*>(e));
-  ProgStep s;
-  s.pos = v.x;
-  s.bits = (unsigned)v.y;
-  s.logrun = __hiloint2double(v.w, v.z);
-  return s;
 }
 
 // Replays one position walk for read column j (see DevProgEntry) and returns
 // fast_log_sum_exp(vector) of its terms (mathops.cpp:97-106).
-//   INS: align_pcr_insertion_reverse (StutterAlignerClass.cpp:59-104), units = D / period copies
-//        inserted, an UPDATE touches the `units` read bases upstream of the position;
-//   else align_pcr_deletion_reverse (:106-150), an UPDATE touches one read base.
+//   INS: align_pcr_insertion_reverse (StutterAlignerClass.cpp:59-104), `units` copies inserted, a
+//        moving step touches the `units` read bases upstream of the position;
+//   else align_pcr_deletion_reverse (:106-150), a moving step touches one read base.
 // Terms are parked in shared memory (they are few: the walk collapses runs of equivalent
 // positions) so maximum and sum need ONE pass; a longer walk falls back to a second pass.
 template <bool INS>
-__device__ __forceinline__ double rep_walk(const RepCtx& c, const DevProgEntry* prog, int stop, int j, int units,
-                                           double lp0, int tail_base) {
-  const int stride = 5 * c.p;
-  const double* colbase = c.val + (INS ? (j - c.p) : j) * 5;
-  double* cache = c.terms;
+__device__ __forceinline__ double rep_walk(const RepCtx& c, int prog_index, int stop, int j, int units, double lp0,
+                                           int tail_base) {
+  const DevProgEntry* prog = c.progs + prog_index;
+  const double* lr = c.prog_logrun + prog_index;
+  const unsigned col = c.val + (INS ? (j - c.p) : j) * HIPSTR_COL_BYTES;
+  const int stride = c.p * HIPSTR_COL_BYTES;
   double lp = lp0, mx = lp0;
+  double extra[HIPSTR_TERM_EXTRA];
   int n = 1;
-  cache[0] = lp0;
-  ProgStep cur = load_step(prog);
-  while (cur.pos > stop) {
-    const ProgStep nxt = load_step(++prog);   // independent of the work below: prefetched
-    const unsigned kind = cur.bits & 0xffu;
-    double term = lp;
-    if (kind == HIPSTR_PROG_UPDATE) {
-      const double* ca = colbase + cur.pos * 5 + ((cur.bits >> 8) & 0xffu);
-      const double* cb = colbase + cur.pos * 5 + ((cur.bits >> 16) & 0xffu);
+  sts_f64(c.terms, lp0);
+  // two steps are always in flight ahead of the one being applied (every walk ends with a terminal
+  // entry and the program array is padded, so reading two entries past the end of a walk is safe)
+  int4 cur = __ldg(reinterpret_cast<const int4*>(prog));
+  double cur_lr = __ldg(lr);
+  int4 nx1 = __ldg(reinterpret_cast<const int4*>(prog + 1));
+  double nx1_lr = __ldg(lr + 1);
+  prog += 2; lr += 2;
+  while (cur.x > stop) {
+    const int4 nx2 = __ldg(reinterpret_cast<const int4*>(prog++));
+    const double nx2_lr = __ldg(lr++);
+    if (cur.w) {
+      unsigned a = col + cur.y, b = col + cur.z;
       if (INS) {
-        for (int m = 0; m < units; m++, ca -= stride, cb -= stride) {
-          lp -= *ca;
-          lp += *cb;
+        for (int m = 0; m < units; m++, a -= stride, b -= stride) {
+          lp -= lds_f64(a);
+          lp += lds_f64(b);
         }
       } else {
-        lp -= *ca;
-        lp += *cb;
+        lp -= lds_f64(a);
+        lp += lds_f64(b);
       }
-      term = lp;
-    } else if (kind == HIPSTR_PROG_COLLAPSED)
-      term = cur.logrun + lp;
-    if (n < HIPSTR_TERM_SLOTS) cache[32 * n] = term;
+    }
+    const double term = lp + cur_lr;
+    if (n < HIPSTR_TERM_SLOTS) sts_f64(c.terms + 256 * n, term);
+    else if (n < HIPSTR_TERM_SLOTS + HIPSTR_TERM_EXTRA) extra[n - HIPSTR_TERM_SLOTS] = term;
     n++;
     mx = dmax(mx, term);
-    cur = nxt;
+    cur = nx1; cur_lr = nx1_lr;
+    nx1 = nx2; nx1_lr = nx2_lr;
   }
   double tail = 0.0;
-  const bool has_tail = INS ? (cur.pos > -tail_base) : (-cur.pos < tail_base);
+  const bool has_tail = INS ? (cur.x > -tail_base) : (-cur.x < tail_base);
   if (has_tail) {
-    tail = __ldg(c.int_logs + (tail_base + cur.pos)) + lp;
+    tail = __ldg(c.int_logs + (tail_base + cur.x)) + lp;
     mx = dmax(mx, tail);
   }
   double total = has_tail ? lse_term(tail, mx) : 0.0;
-  if (n <= HIPSTR_TERM_SLOTS) {
-    for (int s = 0; s < n; s++) total += lse_term(cache[32 * s], mx);
+  if (n <= HIPSTR_TERM_SLOTS + HIPSTR_TERM_EXTRA) {
+    const int in_smem = min(n, HIPSTR_TERM_SLOTS);
+    for (int s = 0; s < in_smem; s++) total += lse_term(lds_f64(c.terms + 256 * s), mx);
+    for (int s = HIPSTR_TERM_SLOTS; s < n; s++) total += lse_term(extra[s - HIPSTR_TERM_SLOTS], mx);
     return lse_finish(mx, total);
   }
   // rare: more terms than slots -> replay the walk, summing against the known maximum
   lp = lp0;
   total += lse_term(lp0, mx);
-  prog -= (n - 1);
-  cur = load_step(prog);
-  while (cur.pos > stop) {
-    const ProgStep nxt = load_step(++prog);
-    const unsigned kind = cur.bits & 0xffu;
-    double term = lp;
-    if (kind == HIPSTR_PROG_UPDATE) {
-      const double* ca = colbase + cur.pos * 5 + ((cur.bits >> 8) & 0xffu);
-      const double* cb = colbase + cur.pos * 5 + ((cur.bits >> 16) & 0xffu);
+  prog -= (n - 1) + 2;
+  lr -= (n - 1) + 2;
+  cur = __ldg(reinterpret_cast<const int4*>(prog));
+  cur_lr = __ldg(lr);
+  while (cur.x > stop) {
+    const int4 nxt = __ldg(reinterpret_cast<const int4*>(++prog));
+    const double nxt_lr = __ldg(++lr);
+    if (cur.w) {
+      unsigned a = col + cur.y, b = col + cur.z;
       if (INS) {
-        for (int m = 0; m < units; m++, ca -= stride, cb -= stride) {
-          lp -= *ca;
-          lp += *cb;
+        for (int m = 0; m < units; m++, a -= stride, b -= stride) {
+          lp -= lds_f64(a);
+          lp += lds_f64(b);
         }
       } else {
-        lp -= *ca;
-        lp += *cb;
+        lp -= lds_f64(a);
+        lp += lds_f64(b);
       }
-      term = lp;
-    } else if (kind == HIPSTR_PROG_COLLAPSED)
-      term = cur.logrun + lp;
-    total += lse_term(term, mx);
+    }
+    total += lse_term(lp + cur_lr, mx);
     cur = nxt;
+    cur_lr = nxt_lr;
   }
   return lse_finish(mx, total);
 }
@@ -177,6 +189,7 @@ __device__ __forceinline__ double rep_walk(const RepCtx& c, const DevProgEntry* 
 __device__ __forceinline__ double rep_column(const RepCtx& c, const double* prev_row, int j) {
   const int B = c.B, p = c.p;
   const DevRep* rep = c.rep;
+  const unsigned colj = c.val + j * HIPSTR_COL_BYTES;
   double probs[HIPSTR_NUM_ARTIFACTS];
 #pragma unroll 1
   for (int k = HIPSTR_MAX_ARTIFACT_UNITS; k >= 1; k--) {   // deletions of k units
@@ -190,14 +203,17 @@ __device__ __forceinline__ double rep_column(const RepCtx& c, const double* prev
         // match_probs_[q] - del_probs_[q][k-1]; the deletion prefix table entry is the first
         // k*period terms of the same right-anchored sum, recomputed here instead of stored
         double pre = 0.0;
-        const double* col = c.val + q * 5;
-        const uint8_t* sb = c.s + B - 1;
-        for (int t = 0; t < -D; t++, col -= 5, sb--) pre += col[__ldg(sb)];
+        const unsigned colq = c.val + q * HIPSTR_COL_BYTES;
+#pragma unroll 4
+        for (int t = 0; t < -D; t++) pre += lds_f64(colq + __ldg(c.diag + t));
         lp0 += c.match[q] - pre;
       } else {
-        for (int t = 0; t < base_len; t++) lp0 += c.emit(j - t, B - 1 - t + D);
+        // read base j-t against allele base B-1-(t-D): entry t-D of the same diagonal, seen from column j
+        const unsigned cold = colj - D * HIPSTR_COL_BYTES;
+#pragma unroll 4
+        for (int t = 0; t < base_len; t++) lp0 += lds_f64(cold + __ldg(c.diag + (t - D)));
       }
-      const double pr = rep_walk<false>(c, c.progs + __ldg(rep->prog_off + k), -base_len, j, k, lp0, B + D);
+      const double pr = rep_walk<false>(c, __ldg(rep->prog_off + k), -base_len, j, k, lp0, B + D);
       const double pre_row = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
       v = __ldg(rep->art + (HIPSTR_MAX_ARTIFACT_UNITS - k)) + pr + pre_row;
     }
@@ -211,7 +227,7 @@ __device__ __forceinline__ double rep_column(const RepCtx& c, const double* prev
   double ins_acc = 0.0;    // ins_probs_ running sum (StutterAlignerClass.cpp:38-51)
   int ins_t = 0;
   const double ins_prior = -__ldg(c.int_logs + (B + 1));
-  const DevProgEntry* ins_prog = c.progs + __ldg(rep->prog_off);
+  const int ins_prog = __ldg(rep->prog_off);
 #pragma unroll 1
   for (int k = 1; k <= HIPSTR_MAX_ARTIFACT_UNITS; k++) {    // insertions of k units
     const int D = k * p;
@@ -219,8 +235,8 @@ __device__ __forceinline__ double rep_column(const RepCtx& c, const double* prev
     // extend the periodic-copy sum to k copies (at most j+1 read bases exist)
     const int upto = min(D, j + 1);
     for (; ins_t < upto; ins_t++) {
-      const int m = ins_t % p;
-      ins_acc += (m < B) ? c.emit(j - ins_t, B - 1 - m) : c.lc(j - ins_t);
+      const int off = __ldg(c.ins_tab + ins_t);
+      ins_acc += lds_f64(off != -1 ? colj + off : colj - ins_t * HIPSTR_COL_BYTES + 8 * c.code[j - ins_t]);
     }
     double lp0 = ins_prior + ins_acc;
     lp0 += (base_len > D) ? c.match[j - D] : 0.0;
@@ -242,8 +258,9 @@ __device__ __forceinline__ double rep_column(const RepCtx& c, const double* prev
 // K1
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t align_smem_doubles(int n_max, int l_max) {
-  // val[5N] run[N] rowbuf[N] rowout[N] match[N] last[2L] terms[32*SLOTS] code[N bytes]
-  return (size_t)9 * n_max + 2 * (size_t)l_max + 32 * HIPSTR_TERM_SLOTS + n_max / 8;
+  // val[5N] run/rowout[N] rowbuf[N] match[N] terms[32*SLOTS] code[N bytes]
+  (void)l_max;
+  return (size_t)(HIPSTR_VAL_STRIDE + 3) * n_max + 32 * HIPSTR_TERM_SLOTS + (n_max + 7) / 8;
 }
 size_t align_smem_bytes(int n_max, int l_max) { return align_smem_doubles(n_max, l_max) * 8 * HIPSTR_WARPS_PER_CTA; }
 
@@ -252,8 +269,16 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int job_id = blockIdx.x * HIPSTR_WARPS_PER_CTA + wib;
-  if (job_id >= P.n_jobs) return;   // whole warp exits together; no block-level barriers below
+  const int N = P.n_max, L = P.l_max;
+  // last-column values of both sides live in a per-warp slab of global memory (L1/L2 resident):
+  // they are written once per row and read once per haplotype, not worth shared memory
+  double* s_last = P.last_scratch + ((size_t)blockIdx.x * HIPSTR_WARPS_PER_CTA + wib) * 2 * (size_t)L;
+  // Persistent warps: every warp pulls (pooled read, haplotype range) jobs from a global counter.
+  for (;;) {
+  int job_id = 0;
+  if (lane == 0) job_id = atomicAdd(P.job_counter, 1);
+  job_id = __shfl_sync(FULL, job_id, 0);
+  if (job_id >= P.n_jobs) break;
   const DevJob job = P.jobs[job_id];
   const DevPool pool = P.pools[job.pool];
   double* out = P.ll_out + pool.out_off;
@@ -263,18 +288,16 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
       out[h] = 0.0;
       if (P.pos_out) P.pos_out[pool.out_off + h] = -1;
     }
-    return;
+    continue;
   }
 
-  const int N = P.n_max, L = P.l_max;
   double* wbase = reinterpret_cast<double*>(smem_raw) + (size_t)wib * align_smem_doubles(N, L);
   double* s_val = wbase;               // [column g][5]: emission of column g against base code x
-  double* s_run = s_val + 5 * N;
+  double* s_run = s_val + HIPSTR_VAL_STRIDE * N;
   double* s_rowbuf = s_run + N;
-  double* s_rowout = s_rowbuf + N;
-  double* s_match = s_rowout + N;
-  double* s_last = s_match + N;
-  double* s_terms = s_last + 2 * L;
+  double* s_rowout = s_run;            // aliases s_run (dead once the running sums are in registers)
+  double* s_match = s_rowbuf + N;
+  double* s_terms = s_match + N;
   uint8_t* s_code = reinterpret_cast<uint8_t*>(s_terms + 32 * HIPSTR_TERM_SLOTS);
 
   const int n = pool.len, seed = pool.seed;
@@ -290,7 +313,7 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
     const double ok = __ldg(P.qual_lut + 2 * q), bad = __ldg(P.qual_lut + 2 * q + 1);
     s_code[g] = x;
 #pragma unroll
-    for (int y = 0; y < 5; y++) s_val[g * 5 + y] = (y == x) ? ok : bad;
+    for (int y = 0; y < 5; y++) s_val[g * HIPSTR_VAL_STRIDE + y] = (y == x) ? ok : bad;
   }
   const uint8_t seed_code = (uint8_t)P.bases[pool.seq_off + seed];
   const uint8_t seed_q = (uint8_t)P.quals[pool.seq_off + seed];
@@ -306,7 +329,7 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
 #pragma unroll 4
     for (int j = 0; j < cnt; j++) {
       s_run[g0 + j] = acc;
-      acc += s_val[(g0 + j) * 5 + s_code[g0 + j]];
+      acc += s_val[(g0 + j) * HIPSTR_VAL_STRIDE + s_code[g0 + j]];
     }
     edge = acc;
   }
@@ -331,10 +354,18 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
     const int g = ok ? gbase + j : 0;
     const uint8_t x = s_code[g];
     bs[cc] = x;
-    lc[cc] = s_val[g * 5 + x];
-    lw[cc] = s_val[g * 5 + (x == 0 ? 1 : 0)];
+    lc[cc] = s_val[g * HIPSTR_VAL_STRIDE + x];
+    lw[cc] = s_val[g * HIPSTR_VAL_STRIDE + (x == 0 ? 1 : 0)];
   }
   const int last_cc = (lane_on && ncol - 1 >= j0 && ncol - 1 < j0 + C) ? ncol - 1 - j0 : -1;
+  // the running sums of this lane's columns stay in registers for the whole job; their shared-memory
+  // staging area is reused as the repeat block's output row
+  double runv[C];
+#pragma unroll
+  for (int cc = 0; cc < C; cc++) runv[cc] = (lane_on && j0 + cc < ncol) ? s_run[gbase + j0 + cc] : 0.0;
+  __syncwarp();
+  const unsigned val_addr = (unsigned)__cvta_generic_to_shared(s_val);
+  const unsigned terms_addr = (unsigned)__cvta_generic_to_shared(s_terms + lane);
 
   int cached_class = -1;   // seg1_class of the rows before the first repeat block that this lane's
                            // side currently holds in s_rowbuf / s_last (from an earlier haplotype)
@@ -362,8 +393,7 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
 #pragma unroll
       for (int cc = 0; cc < C; cc++) {
         const int j = j0 + cc;
-        const double run = (lane_on && j < ncol) ? s_run[gbase + j] : 0.0;
-        Mp[cc] = (bs[cc] == fc ? lc[cc] : lw[cc]) + run;
+        Mp[cc] = (bs[cc] == fc ? lc[cc] : lw[cc]) + runv[cc];
         Dp[cc] = IMPOSSIBLE;
         if (cc == last_cc) s_last[side * L] = Mp[cc];
       }
@@ -438,9 +468,10 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
           if (gb.rep < 0) continue;
           const DevRep* rep = P.reps + gb.rep;
           RepCtx c;
-          c.s = P.hapbytes + rep->seq_off; c.progs = P.progs; c.rep = rep; c.int_logs = P.int_logs;
-          c.val = s_val + (gs ? nL : 0) * 5; c.code = s_code + (gs ? nL : 0); c.match = s_match + (gs ? nL : 0);
-          c.terms = s_terms + lane;
+          c.s = P.hapbytes + rep->seq_off; c.progs = P.progs; c.prog_logrun = P.prog_logrun; c.rep = rep;
+          c.diag = P.rep_tabs + rep->diag_off; c.ins_tab = P.rep_tabs + rep->ins_off; c.int_logs = P.int_logs;
+          c.val = val_addr + (gs ? nL : 0) * HIPSTR_COL_BYTES; c.code = s_code + (gs ? nL : 0); c.match = s_match + (gs ? nL : 0);
+          c.terms = terms_addr;
           c.B = rep->len; c.p = rep->period; c.n_side = gs ? nR : nL;
           s_match[g] = rep_match_prob(c, g - (gs ? nL : 0));
         }
@@ -452,9 +483,10 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
           if (gb.rep < 0) continue;
           const DevRep* rep = P.reps + gb.rep;
           RepCtx c;
-          c.s = P.hapbytes + rep->seq_off; c.progs = P.progs; c.rep = rep; c.int_logs = P.int_logs;
-          c.val = s_val + (gs ? nL : 0) * 5; c.code = s_code + (gs ? nL : 0); c.match = s_match + (gs ? nL : 0);
-          c.terms = s_terms + lane;
+          c.s = P.hapbytes + rep->seq_off; c.progs = P.progs; c.prog_logrun = P.prog_logrun; c.rep = rep;
+          c.diag = P.rep_tabs + rep->diag_off; c.ins_tab = P.rep_tabs + rep->ins_off; c.int_logs = P.int_logs;
+          c.val = val_addr + (gs ? nL : 0) * HIPSTR_COL_BYTES; c.code = s_code + (gs ? nL : 0); c.match = s_match + (gs ? nL : 0);
+          c.terms = terms_addr;
           c.B = rep->len; c.p = rep->period; c.n_side = gs ? nR : nL;
           s_rowout[g] = rep_column(c, s_rowbuf + (gs ? nL : 0), g - (gs ? nL : 0));
         }
@@ -468,8 +500,8 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
           const int g = ok ? gbase + j : 0;
           const uint8_t x = s_code[g];
           bs[cc] = x;
-          lc[cc] = s_val[g * 5 + x];
-          lw[cc] = s_val[g * 5 + (x == 0 ? 1 : 0)];
+          lc[cc] = s_val[g * HIPSTR_VAL_STRIDE + x];
+          lw[cc] = s_val[g * HIPSTR_VAL_STRIDE + (x == 0 ? 1 : 0)];
           if (blk.rep >= 0) {
             Mp[cc] = ok ? s_rowout[g] : 0.0;
             Dp[cc] = IMPOSSIBLE;
@@ -540,29 +572,45 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
     }
     __syncwarp();
   }
+  __syncwarp();
+  }   // next job
 }
 
 template <int C>
-static cudaError_t launch_align_c(const AlignParams& p, cudaStream_t stream) {
+static cudaError_t launch_align_c(const AlignParams& p, int max_ctas, cudaStream_t stream, int* grid_out) {
   const size_t smem = align_smem_bytes(p.n_max, p.l_max);
   cudaError_t e = cudaFuncSetAttribute(k_align<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int grid = (p.n_jobs + HIPSTR_WARPS_PER_CTA - 1) / HIPSTR_WARPS_PER_CTA;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align<C>, 32 * HIPSTR_WARPS_PER_CTA, smem);
+  if (e != cudaSuccess) return e;
+  // persistent grid: exactly as many CTAs as can be resident (a multiple of the SM count)
+  const int jobs_ctas = (p.n_jobs + HIPSTR_WARPS_PER_CTA - 1) / HIPSTR_WARPS_PER_CTA;
+  int grid = sms * (per_sm > 0 ? per_sm : 1);
+  if (grid > jobs_ctas) grid = jobs_ctas;
+  if (grid > max_ctas) grid = max_ctas;
+  if (grid_out) *grid_out = grid;
   k_align<C><<<grid, 32 * HIPSTR_WARPS_PER_CTA, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_align(int variant, const AlignParams& p, cudaStream_t stream) {
+cudaError_t launch_align(int variant, const AlignParams& p, int max_ctas, cudaStream_t stream, int* grid_out) {
   if (p.n_jobs <= 0) return cudaSuccess;
   switch (variant) {
-    case 0: return launch_align_c<2>(p, stream);
-    case 1: return launch_align_c<3>(p, stream);
-    case 2: return launch_align_c<4>(p, stream);
-    case 3: return launch_align_c<5>(p, stream);
-    case 4: return launch_align_c<6>(p, stream);
-    case 5: return launch_align_c<8>(p, stream);
-    case 6: return launch_align_c<12>(p, stream);
-    case 7: return launch_align_c<16>(p, stream);
+    case 0: return launch_align_c<2>(p, max_ctas, stream, grid_out);
+    case 1: return launch_align_c<3>(p, max_ctas, stream, grid_out);
+    case 2: return launch_align_c<4>(p, max_ctas, stream, grid_out);
+    case 3: return launch_align_c<5>(p, max_ctas, stream, grid_out);
+    case 4: return launch_align_c<6>(p, max_ctas, stream, grid_out);
+    case 5: return launch_align_c<8>(p, max_ctas, stream, grid_out);
+    case 6: return launch_align_c<12>(p, max_ctas, stream, grid_out);
+    case 7: return launch_align_c<16>(p, max_ctas, stream, grid_out);
   }
   return cudaErrorInvalidValue;
 }

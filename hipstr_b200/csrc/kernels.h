@@ -8,7 +8,9 @@
 namespace hipstr {
 
 /* K1: read x haplotype HMM alignment.  `variant` indexes kColVariants (columns per lane). */
-cudaError_t launch_align(int variant, const AlignParams& p, cudaStream_t stream);
+/* Persistent launch: at most max_ctas CTAs (the size of p.last_scratch in CTA slabs). */
+#define HIPSTR_MAX_ALIGN_CTAS 8192
+cudaError_t launch_align(int variant, const AlignParams& p, int max_ctas, cudaStream_t stream, int* grid_out);
 size_t align_smem_bytes(int n_max, int l_max);
 
 /* K2: pool -> read scatter + mate merge (seq_stutter_genotyper.cpp:530-564). */

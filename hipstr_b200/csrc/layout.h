@@ -65,25 +65,33 @@ struct DevBlock {         /* 16 B */
  * align_pcr_deletion_reverse (StutterAlignerClass.cpp:75-100,127-147) depends only on the allele
  * (its upstream_match_lengths_ table), not on the read, so the host unrolls it once per allele and
  * every read column replays it: no data-dependent pointer chasing on the device, and the next
- * step can be prefetched while the current one is applied. */
-#define HIPSTR_PROG_PLAIN 0      /* term = lp                                   */
-#define HIPSTR_PROG_UPDATE 1     /* lp -= emit(.., xa); lp += emit(.., xb); term = lp */
-#define HIPSTR_PROG_COLLAPSED 2  /* term = logrun + lp (a run of equivalent positions) */
-#define HIPSTR_PROG_END 3        /* terminal entry: `pos` is where the walk stops */
+ * step can be prefetched while the current one is applied.
+ *
+ * Every step has the same shape:
+ *     if (moves) lp = (lp - val[col + off_a]) + val[col + off_b];   term = lp + logrun
+ * where val is the per-read emission table with HIPSTR_VAL_STRIDE doubles per read column (base
+ * codes 0..4) and logrun = 0.0 unless the step is a collapsed run (x + 0.0 is exact).  Offsets are
+ * BYTES relative to the table entry of the column the walk started at (insertion walks: relative
+ * to column j - period, the first base an inserted copy overwrites). */
+#define HIPSTR_VAL_STRIDE 5   /* odd stride in 8-byte words: consecutive columns fall in distinct banks */
 struct DevProgEntry {     /* 16 B */
-  int32_t pos;            /* artifact position i (<= 0, offset from the right end of the block) */
-  uint8_t kind, xa, xb, pad;
-  double  logrun;         /* int_log(run length) for COLLAPSED */
+  int32_t pos;            /* artifact position i (<= 0, offset from the right end of the block); the
+                             terminal entry of a walk holds the position where the walk stops */
+  int32_t off_a, off_b;   /* byte offsets into val of the emission to remove / to add */
+  int32_t moves;          /* 1 if the step changes lp (insertions repeat it once per inserted copy) */
 };
 
-struct DevRep {           /* 160 B */
+struct DevRep {           /* 168 B */
   int32_t seq_off;        /* into hapbytes: oriented allele base codes */
   int32_t len;            /* B */
   int32_t period;
   int32_t n_del;          /* StutterAlignerClass num_deletions_ */
   int32_t left_align;     /* !reversed (RepeatBlock.h:28,41); only the traceback uses it */
-  int32_t prog_off[7];    /* into progs: [0] insertion walk (lag = period), [k] deletion of k units */
-  int32_t pad[2];
+  int32_t prog_off[7];    /* into progs / prog_logrun: [0] insertion walk (lag = period), [k] deletion of k units */
+  int32_t diag_off;       /* into rep_tabs: B byte offsets of the right-anchored diagonal,
+                             entry t = emission of column q - t against allele base B-1-t, relative to column q */
+  int32_t ins_off;        /* into rep_tabs: 6*period byte offsets of the periodic-copy sum
+                             (StutterAlignerClass.cpp:38-51); -1 marks "log_correct of the read base" */
   double  art[13];        /* log_prob_pcr_artifact for D = -6p .. +6p */
 };
 
@@ -106,6 +114,8 @@ struct AlignParams {
   const DevBlock* blocks;
   const DevRep* reps;
   const DevProgEntry* progs;
+  const double* prog_logrun;   /* parallel to progs: int_log(run length) of a collapsed step, else 0.0 */
+  const int32_t* rep_tabs;
   const uint8_t* hap_mask;   /* per global hap index; NULL = all */
   const double* qual_lut;    /* [256][2]: log_correct, log_error by quality byte */
   const double* trans;       /* [3][16]: LOG_MATCH_TO_MATCH / _INS / _DEL by homopolymer class */
@@ -113,6 +123,8 @@ struct AlignParams {
   double* ll_out;
   int32_t* pos_out;          /* may be NULL */
   double* debug_out;         /* may be NULL: [2][l_max] last-column M values of job 0's last haplotype */
+  int32_t* job_counter;      /* zeroed before the launch: persistent warps pull jobs from it */
+  double* last_scratch;      /* [resident warps][2][l_max] last-column slabs */
 };
 
 #endif
