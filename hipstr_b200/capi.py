@@ -84,6 +84,31 @@ def make_em_batch(locus_read_off, locus_sample_off, num_bps, sample_label, log_p
     return b
 
 
+EXTRACT_ARGTYPES = [C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_u8p, c_f64p, c_f64p, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p,
+                    c_f64p, c_f64p, c_f64p, c_f64p, c_i32p]
+
+
+def extract_genotypes(fn, locus_sample_off, n_haps, n_variants, hap_to_allele, haploid, post, sample_ll, ctx_handle=None):
+    """Calls an extract_genotypes entry point (product / oracle / reference harness share the signature)."""
+    lso, nh, nv = (np.ascontiguousarray(a, np.int32) for a in (locus_sample_off, n_haps, n_variants))
+    h2a = np.ascontiguousarray(hap_to_allele, np.int32)
+    hp = np.ascontiguousarray(haploid, np.uint8)
+    S, Sl = int(lso[-1]), np.diff(lso)
+    G = np.where(hp != 0, nv, nv * (nv + 1) // 2)
+    PG = np.where(hp != 0, nv, nv * nv)
+    out = dict(best_hap=np.zeros(2 * S, np.int32), best_gt=np.zeros(2 * S, np.int32), log_phased=np.zeros(S),
+               log_unphased=np.zeros(S), hap_log_phased=np.zeros(S), hap_log_unphased=np.zeros(S),
+               gl=np.zeros(int((Sl * G).sum())), phased_gl=np.zeros(int((Sl * PG).sum())), gl_diff=np.zeros(S),
+               pl=np.zeros(int((Sl * G).sum()), np.int32))
+    args = [len(nh), ptr(lso, c_i32p), ptr(nh, c_i32p), ptr(nv, c_i32p), ptr(h2a, c_i32p), ptr(hp, c_u8p),
+            ptr(np.ascontiguousarray(post), c_f64p), ptr(np.ascontiguousarray(sample_ll), c_f64p),
+            ptr(out["best_hap"], c_i32p), ptr(out["best_gt"], c_i32p), ptr(out["log_phased"], c_f64p),
+            ptr(out["log_unphased"], c_f64p), ptr(out["hap_log_phased"], c_f64p), ptr(out["hap_log_unphased"], c_f64p),
+            ptr(out["gl"], c_f64p), ptr(out["phased_gl"], c_f64p), ptr(out["gl_diff"], c_f64p), ptr(out["pl"], c_i32p)]
+    st = fn(ctx_handle, *args) if ctx_handle is not None else fn(*args)
+    return st, out
+
+
 def em_train(fn, batch, max_iter=100, min_abs=0.01, min_frac=0.001, ctx_handle=None):
     """Calls an em_train entry point (product, oracle or reference harness share the signature after the context)."""
     L = batch.n_loci
@@ -189,6 +214,8 @@ def load():
     lib.hipstr_genotype_batch_dev.argtypes = [vp, vp, GO]
     lib.hipstr_free_genotype_batch.restype = None
     lib.hipstr_free_genotype_batch.argtypes = [vp, vp]
+    lib.hipstr_extract_genotypes_host.restype = C.c_int32
+    lib.hipstr_extract_genotypes_host.argtypes = [vp] + EXTRACT_ARGTYPES
     lib.hipstr_em_train_host.restype = C.c_int32
     lib.hipstr_em_train_host.argtypes = [vp, C.POINTER(EmBatch), C.c_int32, C.c_double, C.c_double, c_f64p, c_u8p, c_i32p,
                                          c_f64p]
@@ -412,6 +439,13 @@ class Context:
 
     def free_genotype(self, handle):
         self.lib.hipstr_free_genotype_batch(self.h, handle)
+
+    def extract_genotypes(self, locus_sample_off, n_haps, n_variants, hap_to_allele, haploid, post, sample_ll):
+        """hipstr_extract_genotypes_host -> dict of per-sample genotype outputs."""
+        st, out = extract_genotypes(self.lib.hipstr_extract_genotypes_host, locus_sample_off, n_haps, n_variants,
+                                    hap_to_allele, haploid, post, sample_ll, self.h)
+        self._check(st, "extract_genotypes_host")
+        return out
 
     def em_train(self, batch, max_iter=100, min_abs=0.01, min_frac=0.001):
         """hipstr_em_train_host -> (params [L][6], converged [L], iterations [L], final LL [L])."""

@@ -758,4 +758,74 @@ hipstr_status_t hipstr_em_train_host(hipstr_ctx_t* ctx, const hipstr_em_batch_t*
   return HIPSTR_OK;
 }
 
+hipstr_status_t hipstr_extract_genotypes_host(hipstr_ctx_t* ctx, int32_t n_loci, const int32_t* locus_sample_off,
+                                              const int32_t* n_haps, const int32_t* n_variants,
+                                              const int32_t* hap_to_allele, const uint8_t* haploid, const double* post,
+                                              const double* sample_ll, int32_t* best_hap, int32_t* best_gt,
+                                              double* log_phased, double* log_unphased, double* hap_log_phased,
+                                              double* hap_log_unphased, double* gl, double* phased_gl, double* gl_diff,
+                                              int32_t* pl) {
+  if (!ctx || n_loci < 0) return HIPSTR_ERR_BAD_ARG;
+  if (n_loci == 0) return HIPSTR_OK;
+  if (!locus_sample_off || !n_haps || !n_variants || !hap_to_allele || !haploid || !post || !sample_ll || !best_hap ||
+      !best_gt || !log_phased || !log_unphased || !hap_log_phased || !hap_log_unphased || !gl || !phased_gl || !gl_diff || !pl)
+    return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
+  const int32_t S = locus_sample_off[n_loci];
+  std::vector<ExtractSample> samples((size_t)S);
+  int64_t post_off = 0, gl_off = 0, pgl_off = 0;
+  int32_t h2a_off = 0;
+  for (int l = 0; l < n_loci; l++) {
+    const int H = n_haps[l], V = n_variants[l];
+    if (H <= 0 || V <= 0 || V > H || H + 1 >= 10000) return fail(ctx, HIPSTR_ERR_BAD_ARG, "bad haplotype / allele count");
+    for (int h = 0; h < H; h++)
+      if (hap_to_allele[h2a_off + h] < 0 || hap_to_allele[h2a_off + h] >= V) return fail(ctx, HIPSTR_ERR_BAD_ARG, "hap_to_allele out of range");
+    const int G = haploid[l] ? V : V * (V + 1) / 2, PG = haploid[l] ? V : V * V;
+    for (int s = locus_sample_off[l]; s < locus_sample_off[l + 1]; s++) {
+      ExtractSample& e = samples[s];
+      e.n_haps = H; e.n_variants = V; e.haploid = haploid[l]; e.h2a_off = h2a_off;
+      e.post_off = post_off; e.gl_off = gl_off; e.pgl_off = pgl_off;
+      post_off += (int64_t)H * H; gl_off += G; pgl_off += PG;
+    }
+    h2a_off += H;
+  }
+  cudaStream_t st = ctx->stream;
+  DevBuf* m = ctx->d_misc;
+  DevBuf* o = ctx->d_out;
+  CU(put(m[0], samples, st));
+  CU(put(m[1], hap_to_allele, (size_t)h2a_off, st));
+  CU(put(m[2], post, (size_t)post_off, st));
+  CU(put(m[3], sample_ll, (size_t)S, st));
+  CU(m[4].reserve(std::max<size_t>((size_t)S * 4 * sizeof(int32_t), 16)));
+  CU(m[5].reserve(std::max<size_t>((size_t)S * 5 * sizeof(double), 16)));
+  CU(o[0].reserve(std::max<size_t>((size_t)gl_off * sizeof(double), 16)));
+  CU(o[1].reserve(std::max<size_t>((size_t)pgl_off * sizeof(double), 16)));
+  CU(o[2].reserve(std::max<size_t>((size_t)gl_off * sizeof(int32_t), 16)));
+  ExtractParams p;
+  p.n_samples = S; p.samples = (const ExtractSample*)m[0].p; p.hap_to_allele = (const int32_t*)m[1].p;
+  p.post = (const double*)m[2].p; p.sample_ll = (const double*)m[3].p; p.int_logs = ctx->d_int_logs;
+  int32_t* di = (int32_t*)m[4].p;
+  double* dd = (double*)m[5].p;
+  p.best_hap = di; p.best_gt = di + 2 * (size_t)S;
+  p.log_phased = dd; p.log_unphased = dd + S; p.hap_log_phased = dd + 2 * (size_t)S; p.hap_log_unphased = dd + 3 * (size_t)S;
+  p.gl_diff = dd + 4 * (size_t)S;
+  p.gl = (double*)o[0].p; p.phased_gl = (double*)o[1].p; p.pl = (int32_t*)o[2].p;
+  CU(launch_extract(p, st));
+  ctx->last_launches = 1;
+  CU(get(ctx, best_hap, p.best_hap, (size_t)S * 2));
+  CU(get(ctx, best_gt, p.best_gt, (size_t)S * 2));
+  CU(get(ctx, log_phased, p.log_phased, (size_t)S));
+  CU(get(ctx, log_unphased, p.log_unphased, (size_t)S));
+  CU(get(ctx, hap_log_phased, p.hap_log_phased, (size_t)S));
+  CU(get(ctx, hap_log_unphased, p.hap_log_unphased, (size_t)S));
+  CU(get(ctx, gl_diff, p.gl_diff, (size_t)S));
+  CU(get(ctx, gl, p.gl, (size_t)gl_off));
+  CU(get(ctx, phased_gl, p.phased_gl, (size_t)pgl_off));
+  CU(get(ctx, pl, p.pl, (size_t)gl_off));
+  CU(cudaStreamSynchronize(st));
+  end_call(ctx);
+  return HIPSTR_OK;
+}
+
 }  // extern "C"

@@ -834,6 +834,138 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ------------------------------------------------------------------------------------------
+// K3b: genotypes and likelihoods from the posteriors: Genotyper::extract_genotypes_and_likelihoods
+// (genotyper.cpp:129-251) + calc_PLs (:99-104) + calc_gl_diff (:106-127).  One warp per (locus,
+// sample).  The haplotype -> allele marginalisation is an exact log-sum-exp (the reference streams
+// it; same value up to libm ulps); GL averaging uses the approximate two-argument form like the
+// reference.
+// ------------------------------------------------------------------------------------------
+#define LOG_E_BASE_10 0.4342944819   /* mathops.cpp:11, as written there */
+
+__global__ void __launch_bounds__(128) k_extract(const ExtractParams P) {
+  const int lane = threadIdx.x & 31;
+  const int sidx = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (sidx >= P.n_samples) return;
+  const ExtractSample S = P.samples[sidx];
+  const int H = S.n_haps, V = S.n_variants;
+  const bool hap1 = S.haploid != 0;
+  const int G = hap1 ? V : V * (V + 1) / 2, PG = hap1 ? V : V * V;
+  const double* sp = P.post + S.post_off;
+  const int32_t* h2a = P.hap_to_allele + S.h2a_off;
+  double* gl = P.gl + S.gl_off;
+  double* pgl = P.phased_gl + S.pgl_off;
+  int32_t* pl = P.pl + S.gl_off;
+  const double sll = P.sample_ll[sidx];
+
+  // get_optimal_haplotypes (:82-97): first maximum
+  double best = -1.7976931348623157e308;
+  int best_d = H * H;
+  for (int d = lane; d < H * H; d += 32) {
+    const double v = sp[d];
+    if (v > best) { best = v; best_d = d; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(FULL, best, o);
+    const int od = __shfl_xor_sync(FULL, best_d, o);
+    if (ov > best || (ov == best && od < best_d)) { best = ov; best_d = od; }
+  }
+  const int ba = best_d / H, bb = best_d % H;
+  const int ga = h2a[ba], gb = h2a[bb];
+
+  // marginalise haplotype pairs to allele pairs (:152-171).  totals live in a per-sample scratch:
+  // the tail of the phased-GL slot when diploid (it has exactly V*V entries), else computed twice.
+  // For the haploid case only the diagonal is ever used.
+  auto total_of = [&](int va, int vb) {
+    double mx = -1.7976931348623157e308 / 2;
+    for (int a = 0; a < H; a++) {
+      if (h2a[a] != va) continue;
+      for (int b = 0; b < H; b++) if (h2a[b] == vb) mx = dmax(mx, sp[a * H + b]);
+    }
+    double sum = 0.0;
+    for (int a = 0; a < H; a++) {
+      if (h2a[a] != va) continue;
+      for (int b = 0; b < H; b++) if (h2a[b] == vb) sum += exp(sp[a * H + b] - mx);
+    }
+    return mx + log(sum);
+  };
+  const double hom = hap1 ? -P.int_logs[H] : P.int_logs[2] - P.int_logs[H] - P.int_logs[H + 1];
+  const double het = hap1 ? 0.0 : -P.int_logs[H] - P.int_logs[H + 1];
+  const double gl_nconfig = hap1 ? P.int_logs[2] + P.int_logs[H] - P.int_logs[V] : P.int_logs[2] + 2 * (P.int_logs[H] - P.int_logs[V]);
+  const double pgl_nconfig = hap1 ? P.int_logs[H] - P.int_logs[V] : 2 * (P.int_logs[H] - P.int_logs[V]);
+
+  if (!hap1) {
+    for (int g = lane; g < V * V; g += 32) pgl[g] = total_of(g / V, g % V);   // raw totals first
+    __syncwarp();
+    if (lane == 0) {
+      const double lp = pgl[V * ga + gb];
+      P.log_phased[sidx] = lp;
+      P.log_unphased[sidx] = ga == gb ? lp : exact_lse2(lp, pgl[V * gb + ga]);
+    }
+    for (int i = lane; i < G; i += 32) {   // i -> (i1 >= i2)
+      int i1 = (int)((sqrt(8.0 * i + 1.0) - 1.0) / 2.0);
+      while ((i1 + 1) * (i1 + 2) / 2 <= i) i1++;
+      while (i1 * (i1 + 1) / 2 > i) i1--;
+      const int i2 = i - i1 * (i1 + 1) / 2;
+      const double corr = (i1 == i2 ? hom : het) + gl_nconfig;
+      gl[i] = (sll - corr + lse2(pgl[i1 * V + i2], pgl[i2 * V + i1])) * LOG_E_BASE_10;
+    }
+    __syncwarp();
+    for (int g = lane; g < V * V; g += 32) {
+      const double corr = ((g / V) == (g % V) ? hom : het) + pgl_nconfig;
+      pgl[g] = (sll - corr + pgl[g]) * LOG_E_BASE_10;
+    }
+  } else {
+    for (int v = lane; v < V; v += 32) {
+      const double tot = total_of(v, v);
+      if (v == ga) { P.log_phased[sidx] = tot; P.log_unphased[sidx] = tot; }   // haploid: ga == gb
+      gl[v] = (sll - (hom + gl_nconfig) + lse2(tot, tot)) * LOG_E_BASE_10;
+      pgl[v] = (sll - (hom + pgl_nconfig) + tot) * LOG_E_BASE_10;
+    }
+    if (ga != gb && lane == 0) {   // cannot happen with the haploid priors, kept for arbitrary inputs
+      const double lp = total_of(ga, gb);
+      P.log_phased[sidx] = lp;
+      P.log_unphased[sidx] = exact_lse2(lp, total_of(gb, ga));
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    P.best_hap[2 * sidx] = ba; P.best_hap[2 * sidx + 1] = bb;
+    P.best_gt[2 * sidx] = ga; P.best_gt[2 * sidx + 1] = gb;
+    P.hap_log_phased[sidx] = sp[ba * H + bb];
+    P.hap_log_unphased[sidx] = ba != bb ? lse2(sp[ba * H + bb], sp[bb * H + ba]) : sp[ba * H + bb];
+  }
+  // GLDIFF (:106-127) and PLs (:99-104)
+  double mg = -1.7976931348623157e308;
+  for (int i = lane; i < G; i += 32) mg = dmax(mg, gl[i]);
+  mg = warp_max(mg);
+  double second = -1.7976931348623157e308;
+  for (int i = lane; i < G; i += 32) if (gl[i] < mg) second = dmax(second, gl[i]);
+  second = warp_max(second);
+  if (second == -1.7976931348623157e308) second = mg;
+  for (int i = lane; i < G; i += 32) {
+    const int v = (int)(-10 * (gl[i] - mg));
+    pl[i] = v < 999 ? v : 999;
+  }
+  if (lane == 0) {
+    double d;
+    if (H == 1) d = -1000;
+    else {
+      const int hi = ga > gb ? ga : gb, lo = ga > gb ? gb : ga;
+      const int idx = hap1 ? ga : hi * (hi + 1) / 2 + lo;
+      d = fabs(mg - gl[idx]) < 1e-10 ? mg - second : gl[idx] - mg;
+    }
+    P.gl_diff[sidx] = d;
+  }
+}
+
+cudaError_t launch_extract(const ExtractParams& p, cudaStream_t stream) {
+  if (p.n_samples <= 0) return cudaSuccess;
+  k_extract<<<(p.n_samples + 3) / 4, 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(EM_THREADS) k_em_train(const EmParams P) {
   extern __shared__ __align__(16) double em_smem[];
   const EmLocus L = P.loci[blockIdx.x];

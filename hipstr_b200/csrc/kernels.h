@@ -80,6 +80,27 @@ struct PostParams {
 };
 cudaError_t launch_posteriors(const PostParams& p, cudaStream_t stream);
 
+/* K3b: genotypes and likelihoods from the posteriors (genotyper.cpp:99-251), one warp per (locus, sample). */
+struct ExtractSample {     /* one per (locus, sample) */
+  int32_t n_haps, n_variants, haploid;
+  int32_t h2a_off;         /* into hap_to_allele */
+  int64_t post_off;        /* this sample's H*H block */
+  int64_t gl_off;          /* into gl / pl */
+  int64_t pgl_off;         /* into phased_gl */
+};
+struct ExtractParams {
+  int32_t n_samples;
+  const ExtractSample* samples;
+  const int32_t* hap_to_allele;
+  const double* post;
+  const double* sample_ll;
+  const double* int_logs;
+  int32_t* best_hap; int32_t* best_gt;
+  double* log_phased; double* log_unphased; double* hap_log_phased; double* hap_log_unphased;
+  double* gl; double* phased_gl; double* gl_diff; int32_t* pl;
+};
+cudaError_t launch_extract(const ExtractParams& p, cudaStream_t stream);
+
 /* K4: EM stutter learner (em_stutter_genotyper.cpp:10-226), one CTA per locus for the whole training loop. */
 struct EmLocus {            /* one per locus */
   int32_t read0, n_reads;   /* global read range */

@@ -259,6 +259,30 @@ hipstr_status_t hipstr_genotype_batch_dev(hipstr_ctx_t* ctx, const hipstr_dev_ge
                                           const hipstr_genotype_out_t* dev_out);
 void            hipstr_free_genotype_batch(hipstr_ctx_t* ctx, hipstr_dev_genotype_t* handle);
 
+/* --- a14: genotypes and likelihoods from the posteriors (kernel K3b) ---------
+ * Replaces Genotyper::extract_genotypes_and_likelihoods (genotyper.h:140-147, impl
+ * genotyper.cpp:129-251, with calc_PLs :99-104 and calc_gl_diff :106-127) for a batch
+ * of loci: haplotype posteriors are marginalised to STR-allele genotypes through
+ * hap_to_allele (SeqStutterGenotyper::haps_to_alleles, seq_stutter_genotyper.cpp:219-227).
+ *   n_variants  [n_loci]  number of alleles V_l of the STR block
+ *   hap_to_allele packed per locus, [H_l] values in [0, V_l)
+ *   post / sample_ll  outputs of hipstr_posteriors_host / hipstr_genotype_batch_*
+ * Per sample outputs (all required unless noted):
+ *   best_hap [S][2], best_gt [S][2]
+ *   log_phased [S], log_unphased [S]            genotype posteriors (PQ / Q before exp)
+ *   hap_log_phased [S], hap_log_unphased [S]
+ *   gl   packed per locus [S_l][G_l], G_l = V(V+1)/2 (diploid, order (0,0),(1,0),(1,1),...) or V (haploid)
+ *   phased_gl packed per locus [S_l][V_l*V_l] (diploid) or [S_l][V_l] (haploid)
+ *   gl_diff [S]; pl packed like gl (int32). */
+hipstr_status_t hipstr_extract_genotypes_host(hipstr_ctx_t* ctx, int32_t n_loci, const int32_t* locus_sample_off,
+                                              const int32_t* n_haps, const int32_t* n_variants,
+                                              const int32_t* hap_to_allele, const uint8_t* haploid,
+                                              const double* post, const double* sample_ll,
+                                              int32_t* best_hap, int32_t* best_gt, double* log_phased,
+                                              double* log_unphased, double* hap_log_phased,
+                                              double* hap_log_unphased, double* gl, double* phased_gl,
+                                              double* gl_diff, int32_t* pl);
+
 /* --- a17 / seam B4: EM stutter-model learner (kernel K4) --------------------
  * Replaces EMStutterGenotyper(...) + train(...) + get_stutter_model()
  * (em_stutter_genotyper.h:50-117, em_stutter_genotyper.cpp:10-226) for a batch of

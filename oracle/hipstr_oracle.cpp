@@ -737,6 +737,75 @@ extern "C" int32_t oracle_em_train(const hipstr_em_batch_t* bt, int32_t max_iter
   return HIPSTR_OK;
 }
 
+// genotyper.cpp:129-251 (+ calc_PLs :99-104, calc_gl_diff :106-127), one locus at a time
+extern "C" int32_t oracle_extract_genotypes(int32_t n_loci, const int32_t* locus_sample_off, const int32_t* n_haps,
+                                            const int32_t* n_variants, const int32_t* hap_to_allele, const uint8_t* haploid,
+                                            const double* post, const double* sample_ll, int32_t* best_hap, int32_t* best_gt,
+                                            double* log_phased, double* log_unphased, double* hap_log_phased,
+                                            double* hap_log_unphased, double* gl, double* phased_gl, double* gl_diff,
+                                            int32_t* pl) {
+  const Tables& t = T();
+  const double LOG_E_BASE_10 = 0.4342944819;   // mathops.cpp:11
+  size_t post_off = 0, h2a_off = 0, gl_off = 0, pgl_off = 0;
+  for (int l = 0; l < n_loci; l++) {
+    const int H = n_haps[l], V = n_variants[l], s0 = locus_sample_off[l], S = locus_sample_off[l + 1] - s0;
+    const bool hap1 = haploid[l] != 0;
+    const int32_t* h2a = hap_to_allele + h2a_off;
+    const int G = hap1 ? V : V * (V + 1) / 2, PG = hap1 ? V : V * V;
+    const double hom = hap1 ? -t.int_logs[H] : t.int_logs[2] - t.int_logs[H] - t.int_logs[H + 1];
+    const double het = hap1 ? 0 : -t.int_logs[H] - t.int_logs[H + 1];
+    const double gl_nconfig = hap1 ? t.int_logs[2] + t.int_logs[H] - t.int_logs[V] : t.int_logs[2] + 2 * (t.int_logs[H] - t.int_logs[V]);
+    const double pgl_nconfig = hap1 ? t.int_logs[H] - t.int_logs[V] : 2 * (t.int_logs[H] - t.int_logs[V]);
+    for (int s = 0; s < S; s++) {
+      const double* sp = post + post_off + (size_t)s * H * H;
+      // get_optimal_haplotypes (:82-97)
+      double best = -DBL_MAX; int ba = -1, bb = -1;
+      for (int a = 0; a < H; a++) for (int b = 0; b < H; b++) if (sp[a * H + b] > best) { best = sp[a * H + b]; ba = a; bb = b; }
+      best_hap[2 * (s0 + s)] = ba; best_hap[2 * (s0 + s) + 1] = bb;
+      const int ga = h2a[ba], gb = h2a[bb];
+      best_gt[2 * (s0 + s)] = ga; best_gt[2 * (s0 + s) + 1] = gb;
+      // streaming marginalisation (:152-171)
+      std::vector<double> mx((size_t)V * V, -DBL_MAX / 2), tot((size_t)V * V, 0.0);
+      for (int a = 0; a < H; a++) for (int b = 0; b < H; b++) stream_lse(sp[a * H + b], mx[V * h2a[a] + h2a[b]], tot[V * h2a[a] + h2a[b]]);
+      for (int g = 0; g < V * V; g++) tot[g] = mx[g] + std::log(tot[g]);
+      hap_log_phased[s0 + s] = sp[ba * H + bb];
+      hap_log_unphased[s0 + s] = ba != bb ? lse2(sp[ba * H + bb], sp[bb * H + ba]) : sp[ba * H + bb];
+      const double lp = tot[V * ga + gb];
+      log_phased[s0 + s] = lp;
+      log_unphased[s0 + s] = ga == gb ? lp : exact_lse2(lp, tot[V * gb + ga]);
+      double* g_out = gl + gl_off + (size_t)s * G;
+      double* pg_out = phased_gl + pgl_off + (size_t)s * PG;
+      int gi = 0, pi = 0;
+      for (int i1 = 0; i1 < V; i1++)
+        for (int i2 = 0; i2 < V; i2++) {
+          const int g = i1 * V + i2, ag = i2 * V + i1;
+          const double glc = (i1 == i2 ? hom : het) + gl_nconfig, pglc = (i1 == i2 ? hom : het) + pgl_nconfig;
+          if (i2 <= i1 && (!hap1 || i1 == i2)) g_out[gi++] = (sample_ll[s0 + s] - glc + lse2(tot[g], tot[ag])) * LOG_E_BASE_10;
+          if (!hap1 || i1 == i2) pg_out[pi++] = (sample_ll[s0 + s] - pglc + tot[g]) * LOG_E_BASE_10;
+        }
+      // calc_gl_diff (:106-127)
+      double d;
+      if (H == 1) d = -1000;
+      else {
+        double mg = g_out[0];
+        for (int i = 1; i < G; i++) mg = std::max(mg, g_out[i]);
+        double second = -DBL_MAX;
+        for (int i = 0; i < G; i++) if (g_out[i] < mg) second = std::max(second, g_out[i]);
+        if (second == -DBL_MAX) second = mg;
+        const int idx = hap1 ? ga : std::max(ga, gb) * (std::max(ga, gb) + 1) / 2 + std::min(ga, gb);
+        d = std::fabs(mg - g_out[idx]) < 1e-10 ? mg - second : g_out[idx] - mg;
+      }
+      gl_diff[s0 + s] = d;
+      double mg = g_out[0];
+      for (int i = 1; i < G; i++) mg = std::max(mg, g_out[i]);
+      int32_t* pl_out = pl + gl_off + (size_t)s * G;
+      for (int i = 0; i < G; i++) pl_out[i] = std::min(999, (int)(-10 * (g_out[i] - mg)));
+    }
+    post_off += (size_t)S * H * H; h2a_off += H; gl_off += (size_t)S * G; pgl_off += (size_t)S * PG;
+  }
+  return HIPSTR_OK;
+}
+
 extern "C" {
 
 double oracle_fast_lse2(double a, double b) { return lse2(a, b); }

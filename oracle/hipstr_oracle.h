@@ -54,6 +54,13 @@ int32_t oracle_posteriors(int32_t n_loci, const int32_t* locus_read_off, const i
                           const int32_t* read_weight, double* post_out, double* sample_ll_out,
                           int32_t* best_out, double* total_ll_out);
 
+/* Genotyper::extract_genotypes_and_likelihoods (genotyper.cpp:129-251); same arguments as the product entry. */
+int32_t oracle_extract_genotypes(int32_t n_loci, const int32_t* locus_sample_off, const int32_t* n_haps,
+                                 const int32_t* n_variants, const int32_t* hap_to_allele, const uint8_t* haploid,
+                                 const double* post, const double* sample_ll, int32_t* best_hap, int32_t* best_gt,
+                                 double* log_phased, double* log_unphased, double* hap_log_phased,
+                                 double* hap_log_unphased, double* gl, double* phased_gl, double* gl_diff, int32_t* pl);
+
 /* EMStutterGenotyper::train for every locus of the batch (em_stutter_genotyper.cpp:170-226). */
 int32_t oracle_em_train(const hipstr_em_batch_t* batch, int32_t max_iter, double min_LL_abs_change,
                         double min_LL_frac_change, double* params_out, uint8_t* converged_out,

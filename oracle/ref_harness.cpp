@@ -94,6 +94,10 @@ class ExposedGenotyper : public Genotyper {
     log_sample_posteriors_ = new double[num_samples_ * num_alleles_ * num_alleles_];
     log_aln_probs_ = new double[num_reads_ * num_alleles_];
   }
+  void load_posteriors(const double* post, const double* sample_ll) {
+    std::memcpy(log_sample_posteriors_, post, sizeof(double) * num_samples_ * num_alleles_ * num_alleles_);
+    std::memcpy(sample_total_LLs_, sample_ll, sizeof(double) * num_samples_);
+  }
   double run(const double* ll, const int32_t* weights, double* post, double* sample_ll, int32_t* best) {
     std::memcpy(log_aln_probs_, ll, sizeof(double) * num_reads_ * num_alleles_);
     std::vector<int> w(weights, weights + num_reads_);
@@ -224,6 +228,43 @@ int32_t ref_posteriors(int32_t n_loci, const int32_t* locus_read_off, const int3
     if (total_ll_out) total_ll_out[l] = total;
     ll_off += (size_t)(r1 - r0) * H;
     post_off += (size_t)S * H * H;
+  }
+  return HIPSTR_OK;
+}
+
+// Genotyper::extract_genotypes_and_likelihoods for every locus.
+int32_t ref_extract_genotypes(int32_t n_loci, const int32_t* locus_sample_off, const int32_t* n_haps, const int32_t* n_variants,
+                              const int32_t* hap_to_allele, const uint8_t* haploid, const double* post, const double* sample_ll,
+                              int32_t* best_hap, int32_t* best_gt, double* log_phased, double* log_unphased, double* hap_log_phased,
+                              double* hap_log_unphased, double* gl, double* phased_gl, double* gl_diff, int32_t* pl) {
+  ensure_init();
+  size_t post_off = 0, h2a_off = 0, gl_off = 0, pgl_off = 0;
+  for (int l = 0; l < n_loci; l++) {
+    const int H = n_haps[l], V = n_variants[l], s0 = locus_sample_off[l], S = locus_sample_off[l + 1] - s0;
+    const bool hap1 = haploid[l] != 0;
+    const int G = hap1 ? V : V * (V + 1) / 2, PG = hap1 ? V : V * V;
+    std::vector<std::string> names;
+    std::vector<std::vector<double> > p1(S), p2(S);
+    for (int s = 0; s < S; s++) { std::stringstream ss; ss << "S" << s; names.push_back(ss.str()); }
+    ExposedGenotyper g(hap1, names, p1, p2, H);
+    g.load_posteriors(post + post_off, sample_ll + s0);
+    std::vector<int> h2a(hap_to_allele + h2a_off, hap_to_allele + h2a_off + H);
+    std::vector<std::pair<int, int> > bh, bg;
+    std::vector<double> lp, lu, hlp, hlu, gd;
+    std::vector<std::vector<double> > gls, pgls;
+    std::vector<std::vector<int> > pls;
+    g.extract_genotypes_and_likelihoods(V, h2a, bh, bg, lp, lu, hlp, hlu, true, gls, gd, true, pls, true, pgls);
+    for (int s = 0; s < S; s++) {
+      best_hap[2 * (s0 + s)] = bh[s].first; best_hap[2 * (s0 + s) + 1] = bh[s].second;
+      best_gt[2 * (s0 + s)] = bg[s].first; best_gt[2 * (s0 + s) + 1] = bg[s].second;
+      log_phased[s0 + s] = lp[s]; log_unphased[s0 + s] = lu[s]; hap_log_phased[s0 + s] = hlp[s]; hap_log_unphased[s0 + s] = hlu[s];
+      gl_diff[s0 + s] = gd[s];
+      if ((int)gls[s].size() != G || (int)pgls[s].size() != PG) return HIPSTR_ERR_BAD_ARG;
+      std::copy(gls[s].begin(), gls[s].end(), gl + gl_off + (size_t)s * G);
+      std::copy(pgls[s].begin(), pgls[s].end(), phased_gl + pgl_off + (size_t)s * PG);
+      std::copy(pls[s].begin(), pls[s].end(), pl + gl_off + (size_t)s * G);
+    }
+    post_off += (size_t)S * H * H; h2a_off += H; gl_off += (size_t)S * G; pgl_off += (size_t)S * PG;
   }
   return HIPSTR_OK;
 }
