@@ -65,6 +65,32 @@ __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
 
 #define HIPSTR_COL_BYTES (HIPSTR_VAL_STRIDE * 8)
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a pooled read's packed bases + qualities ------
+// One elected lane arms an mbarrier with the byte count and issues the two bulk copies; the warp
+// then waits on the barrier's phase.  Sources are 16-byte aligned and padded by the host lowering.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
 struct RepCtx {
   const uint8_t* s;          // oriented allele base codes (global, read-only)
   const DevProgEntry* progs;
@@ -258,9 +284,12 @@ __device__ __forceinline__ double rep_column(const RepCtx& c, const double* prev
 // K1
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t align_smem_doubles(int n_max, int l_max) {
-  // val[5N] run/rowout[N] rowbuf[N] match[N] terms[32*SLOTS] code[N bytes]
+  // val[5N] run/rowout[N] rowbuf[N] match[N] terms[32*SLOTS] raw bases/quals, mbarrier, code[N bytes]
   (void)l_max;
-  return (size_t)(HIPSTR_VAL_STRIDE + 3) * n_max + 32 * HIPSTR_TERM_SLOTS + (n_max + 7) / 8;
+  // + 2 x raw[2][round16(N)] bytes (double-buffered bulk-copy landing zones) + two mbarriers
+  const size_t n16 = ((size_t)n_max + 15) / 16 * 16;
+  const size_t d = (size_t)(HIPSTR_VAL_STRIDE + 3) * n_max + 32 * HIPSTR_TERM_SLOTS + 4 * n16 / 8 + 2 + (n_max + 7) / 8;
+  return (d + 1) / 2 * 2;   // keep every warp's slab 16-byte aligned
 }
 size_t align_smem_bytes(int n_max, int l_max) { return align_smem_doubles(n_max, l_max) * 8 * HIPSTR_WARPS_PER_CTA; }
 
@@ -274,12 +303,49 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
   // they are written once per row and read once per haplotype, not worth shared memory
   double* s_last = P.last_scratch + ((size_t)blockIdx.x * HIPSTR_WARPS_PER_CTA + wib) * 2 * (size_t)L;
   // Persistent warps: every warp pulls (pooled read, haplotype range) jobs from a global counter.
+  const int N16 = (N + 15) / 16 * 16;
+  double* wbase0 = reinterpret_cast<double*>(smem_raw) + (size_t)wib * align_smem_doubles(N, L);
+  uint8_t* s_raw0 = reinterpret_cast<uint8_t*>(wbase0 + (HIPSTR_VAL_STRIDE + 3) * (size_t)N + 32 * HIPSTR_TERM_SLOTS);
+  const unsigned raw_addr = (unsigned)__cvta_generic_to_shared(s_raw0);
+  const unsigned bar_addr = raw_addr + 4 * N16;   // two 8-byte mbarriers after the two zones
+  if (lane == 0) { mbar_init(bar_addr, 1); mbar_init(bar_addr + 8, 1); }
+  __syncwarp();
+  unsigned bar_phase[2] = {0, 0};
+  // Double-buffered TMA staging: the bulk copy of the NEXT job's read (packed bases + qualities) is
+  // issued before the current job is processed, so its latency never shows.
+  auto fetch_and_stage = [&](int buf) {
+    int id = 0;
+    if (lane == 0) {
+      id = atomicAdd(P.job_counter, 1);
+      if (id < P.n_jobs) {
+        const DevPool* pp = P.pools + P.jobs[id].pool;
+        const int len = pp->len, off = pp->seq_off;
+        const unsigned bytes = (unsigned)((len + 15) / 16 * 16);
+        const unsigned zone = raw_addr + buf * 2 * N16;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the zone are done
+        mbar_expect_tx(bar_addr + 8 * buf, 2 * bytes);
+        bulk_g2s(zone, P.bases + off, bytes, bar_addr + 8 * buf);
+        bulk_g2s(zone + N16, P.quals + off, bytes, bar_addr + 8 * buf);
+      }
+    }
+    return __shfl_sync(FULL, id, 0);
+  };
+  int cur_buf = 0;
+  int job_id = fetch_and_stage(0);
   for (;;) {
-  int job_id = 0;
-  if (lane == 0) job_id = atomicAdd(P.job_counter, 1);
-  job_id = __shfl_sync(FULL, job_id, 0);
   if (job_id >= P.n_jobs) break;
-  const DevJob job = P.jobs[job_id];
+  __syncwarp();   // every lane is done with the zone the next copy will overwrite
+  const int next_job_id = fetch_and_stage(cur_buf ^ 1);
+  const uint8_t* s_rawb = s_raw0 + cur_buf * 2 * N16;
+  const uint8_t* s_rawq = s_rawb + N16;
+  mbar_wait(bar_addr + 8 * cur_buf, bar_phase[cur_buf]);
+  bar_phase[cur_buf] ^= 1;
+  const int this_buf = cur_buf;
+  (void)this_buf;
+  cur_buf ^= 1;
+  const int my_job = job_id;
+  job_id = next_job_id;
+  const DevJob job = P.jobs[my_job];
   const DevPool pool = P.pools[job.pool];
   double* out = P.ll_out + pool.out_off;
 
@@ -298,25 +364,27 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
   double* s_rowout = s_run;            // aliases s_run (dead once the running sums are in registers)
   double* s_match = s_rowbuf + N;
   double* s_terms = s_match + N;
-  uint8_t* s_code = reinterpret_cast<uint8_t*>(s_terms + 32 * HIPSTR_TERM_SLOTS);
+  uint8_t* s_code = s_raw0 + 4 * N16 + 16;   // after the landing zones and the mbarriers
 
   const int n = pool.len, seed = pool.seed;
   const int nL = seed, nR = n - seed - 1;
   // Stage the read in SIDE order: columns 0..nL-1 are read bases 0..seed-1 (left of the seed, aligned
   // to the forward haplotype), columns nL..n-2 are read bases n-1..seed+1 (right of the seed,
   // reversed, aligned to the reversed haplotype), HapAligner.cpp:579-585,606-609.
+  // The packed bases and qualities arrived by TMA bulk copy in the landing zone (waited for above);
+  // every lane expands its read positions into the emission table.
   for (int i = lane; i < n; i += 32) {
     if (i == seed) continue;
     const int g = i < seed ? i : nL + (n - 1 - i);
-    const uint8_t q = (uint8_t)P.quals[pool.seq_off + i];
-    const uint8_t x = (uint8_t)P.bases[pool.seq_off + i];
+    const uint8_t q = s_rawq[i];
+    const uint8_t x = s_rawb[i];
     const double ok = __ldg(P.qual_lut + 2 * q), bad = __ldg(P.qual_lut + 2 * q + 1);
     s_code[g] = x;
 #pragma unroll
     for (int y = 0; y < 5; y++) s_val[g * HIPSTR_VAL_STRIDE + y] = (y == x) ? ok : bad;
   }
-  const uint8_t seed_code = (uint8_t)P.bases[pool.seq_off + seed];
-  const uint8_t seed_q = (uint8_t)P.quals[pool.seq_off + seed];
+  const uint8_t seed_code = s_rawb[seed];
+  const uint8_t seed_q = s_rawq[seed];
   const double seed_ok = __ldg(P.qual_lut + 2 * seed_q), seed_bad = __ldg(P.qual_lut + 2 * seed_q + 1);
   __syncwarp();
   // running sums of log_correct from each read end towards the seed (row 0 of either matrix,
@@ -567,7 +635,7 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
         out[h] = lse_finish(vmax, total);
         if (P.pos_out) P.pos_out[pool.out_off + h] = vrank == 0 ? 0 : (vrank == 1 ? hlen - 1 : vrank - 1);
       }
-      if (P.debug_out && job_id == 0 && h == job.h1 - 1)
+      if (P.debug_out && my_job == 0 && h == job.h1 - 1)
         for (int i = lane; i < 2 * L; i += 32) P.debug_out[i] = (i % L) < hlen ? s_last[i] : 0.0;
     }
     __syncwarp();
