@@ -322,10 +322,16 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
         const int len = pp->len, off = pp->seq_off;
         const unsigned bytes = (unsigned)((len + 15) / 16 * 16);
         const unsigned zone = raw_addr + buf * 2 * N16;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the zone are done
-        mbar_expect_tx(bar_addr + 8 * buf, 2 * bytes);
-        bulk_g2s(zone, P.bases + off, bytes, bar_addr + 8 * buf);
-        bulk_g2s(zone + N16, P.quals + off, bytes, bar_addr + 8 * buf);
+        if (pp->seed < 0 || (int)bytes > N16) {
+          // a read without a seed is never aligned (and may be longer than this launch's zones):
+          // complete the barrier phase without a copy
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_addr + 8 * buf) : "memory");
+        } else {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the zone are done
+          mbar_expect_tx(bar_addr + 8 * buf, 2 * bytes);
+          bulk_g2s(zone, P.bases + off, bytes, bar_addr + 8 * buf);
+          bulk_g2s(zone + N16, P.quals + off, bytes, bar_addr + 8 * buf);
+        }
       }
     }
     return __shfl_sync(FULL, id, 0);

@@ -266,3 +266,17 @@ def test_genotype_batch_resident_and_copy_read_mask(ctx):
     assert np.array_equal(got["read_ll"], ref["read_ll"])
     assert np.array_equal(got["read_seed"], ref["read_seed"])
     assert np.array_equal(got["best"], ref["best"])
+
+
+def test_seedless_long_read_in_short_read_batch(ctx):
+    """Seedless pools ride in the shortest-read launch; their bases must not be staged into its (smaller) landing
+    zone (regression: out-of-bounds TMA write found by the configs[4] sweep under compute-sanitizer)."""
+    bb = BatchBuilder()
+    blocks, reads = cases.handmade(seed=51, n_reads=6)
+    short = [(r[0][:40], r[1][:40], 20) for r in reads[:3]]
+    long_seedless = [(reads[3][0] * 3, reads[3][1] * 3, -1)]
+    bb.add_locus(blocks, short + long_seedless + [(reads[4][0], reads[4][1], reads[4][2])])
+    b = bb.build()
+    want = checkers.align(checkers.oracle(), "oracle_", b, b.n_out, fill=7.0)
+    got = ctx.align_host(b, b.n_out, ll=np.full(b.n_out, 7.0))
+    assert _report("seedless-long", got, want) <= TIGHT
