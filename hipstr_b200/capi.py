@@ -84,6 +84,41 @@ def make_em_batch(locus_read_off, locus_sample_off, num_bps, sample_label, log_p
     return b
 
 
+class TraceOut(C.Structure):
+    """hipstr_trace_out_t"""
+    _fields_ = [("aln_stride", C.c_int32), ("hap_aln", C.c_void_p), ("seed_hap_pos", c_i32p), ("stutter_size", c_i32p),
+                ("span_start", c_i32p), ("span_len", c_i32p), ("flank_ins", c_i32p), ("flank_del", c_i32p),
+                ("n_indels", c_i32p), ("indels", c_i32p), ("n_snps", c_i32p), ("snps", c_i32p)]
+
+
+MAX_BLOCKS, MAX_TRACE_INDELS, MAX_TRACE_SNPS, NO_STR_DATA = 8, 16, 32, -2147483648
+
+
+def trace_batch(fn, batch, block_start, trace_pool, trace_hap, aln_stride=1024, ctx_handle=None, extra_args=()):
+    """Calls a trace_batch entry point; returns a dict of numpy arrays (hap_aln as a list of str)."""
+    bs = np.ascontiguousarray(block_start, np.int32)
+    tp = np.ascontiguousarray(trace_pool, np.int32)
+    th = np.ascontiguousarray(trace_hap, np.int32)
+    n = len(tp)
+    o = dict(hap_aln=np.zeros(n * aln_stride, np.uint8), seed_hap_pos=np.zeros(n, np.int32),
+             stutter_size=np.zeros(n * MAX_BLOCKS, np.int32), span_start=np.zeros(n * MAX_BLOCKS, np.int32),
+             span_len=np.zeros(n * MAX_BLOCKS, np.int32), flank_ins=np.zeros(n, np.int32), flank_del=np.zeros(n, np.int32),
+             n_indels=np.zeros(n, np.int32), indels=np.zeros(n * MAX_TRACE_INDELS * 2, np.int32),
+             n_snps=np.zeros(n, np.int32), snps=np.zeros(n * MAX_TRACE_SNPS * 2, np.int32))
+    to = TraceOut(aln_stride, o["hap_aln"].ctypes.data, *[ptr(o[k], c_i32p) for k in
+                  ("seed_hap_pos", "stutter_size", "span_start", "span_len", "flank_ins", "flank_del", "n_indels", "indels",
+                   "n_snps", "snps")])
+    args = [C.byref(batch), ptr(bs, c_i32p), C.c_int32(n), ptr(tp, c_i32p), ptr(th, c_i32p), C.byref(to)] + list(extra_args)
+    st = fn(ctx_handle, *args) if ctx_handle is not None else fn(*args)
+    raw = o["hap_aln"].reshape(n, aln_stride)
+    o["hap_aln"] = [bytes(r[:int(np.argmax(r == 0))]).decode() for r in raw]
+    for k in ("stutter_size", "span_start", "span_len"):
+        o[k] = o[k].reshape(n, MAX_BLOCKS)
+    o["indels"] = o["indels"].reshape(n, MAX_TRACE_INDELS, 2)
+    o["snps"] = o["snps"].reshape(n, MAX_TRACE_SNPS, 2)
+    return st, o
+
+
 EXTRACT_ARGTYPES = [C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_u8p, c_f64p, c_f64p, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p,
                     c_f64p, c_f64p, c_f64p, c_f64p, c_i32p]
 

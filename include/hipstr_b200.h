@@ -283,6 +283,44 @@ hipstr_status_t hipstr_extract_genotypes_host(hipstr_ctx_t* ctx, int32_t n_loci,
                                               double* hap_log_unphased, double* gl, double* phased_gl,
                                               double* gl_diff, int32_t* pl);
 
+/* --- a16: alignment traceback (kernel K5) ------------------------------------
+ * Replaces HapAligner::trace_optimal_aln (SeqAlignment/HapAligner.h:93, impl
+ * HapAligner.cpp:711-722 -> process_read(retrace_aln = true) :636-690 -> retrace :363-571)
+ * for a list of (pooled read, haplotype) pairs of a batch: the read is realigned to that ONE
+ * haplotype keeping the full matrices, the best seed placement is found, and the most likely
+ * path is walked back on both sides of the seed (ties within TRACE_LL_TOL = 0.001 resolved as
+ * the reference does, :345-361).  What the reference stores as strings in AlignmentTrace
+ * (SeqAlignment/AlignmentTraceback.h:10-115) comes back as index ranges into the read:
+ *   str_seq(b) / flank_seq(b) == read[span_start[b] .. span_start[b] + span_len[b]).
+ * Re-expressing the trace against the reference genome (stitch_alignment_trace,
+ * AlignmentTraceback.cpp:55-144) needs the haplotype-vs-reference alignments of
+ * Haplotype::aln_haps_to_ref and stays with the caller.
+ *   block_start [n_blocks] genomic start of every haplotype block (HapBlock::start())
+ *   trace_pool / trace_hap [n_traces]: global pool index, haplotype index local to its locus */
+#define HIPSTR_MAX_BLOCKS_PER_LOCUS 8
+#define HIPSTR_MAX_TRACE_INDELS 16
+#define HIPSTR_MAX_TRACE_SNPS 32
+#define HIPSTR_NO_STR_DATA (-2147483647 - 1)
+typedef struct hipstr_trace_out {
+  int32_t  aln_stride;    /* bytes per trace in hap_aln, >= read length + haplotype length + 1      */
+  char*    hap_aln;       /* [n_traces][aln_stride] 'M','I','D','S' ops, NUL-terminated (hap_aln()) */
+  int32_t* seed_hap_pos;  /* [n_traces] haplotype position of the seed base (max_index)            */
+  int32_t* stutter_size;  /* [n_traces][8] per block: stutter_size(b), HIPSTR_NO_STR_DATA if none  */
+  int32_t* span_start;    /* [n_traces][8] per block: first read base of str_seq(b) / flank_seq(b) */
+  int32_t* span_len;      /* [n_traces][8] per block: its length (0 = empty)                       */
+  int32_t* flank_ins;     /* [n_traces] flank_ins_size()                                           */
+  int32_t* flank_del;     /* [n_traces] flank_del_size()                                           */
+  int32_t* n_indels;      /* [n_traces] entries of flank_indel_data(), in the reference's order    */
+  int32_t* indels;        /* [n_traces][16][2] (position, size)                                    */
+  int32_t* n_snps;        /* [n_traces] entries of flank_snp_data()                                */
+  int32_t* snps;          /* [n_traces][32][2] (position, read base character)                     */
+} hipstr_trace_out_t;
+
+hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch,
+                                        const int32_t* block_start, int32_t n_traces,
+                                        const int32_t* trace_pool, const int32_t* trace_hap,
+                                        const hipstr_trace_out_t* out);
+
 /* --- a17 / seam B4: EM stutter-model learner (kernel K4) --------------------
  * Replaces EMStutterGenotyper(...) + train(...) + get_stutter_model()
  * (em_stutter_genotyper.h:50-117, em_stutter_genotyper.cpp:10-226) for a batch of

@@ -806,6 +806,222 @@ extern "C" int32_t oracle_extract_genotypes(int32_t n_loci, const int32_t* locus
   return HIPSTR_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Traceback: HapAligner::process_read with retrace_aln = true for ONE haplotype
+// (HapAligner.cpp:636-690) and HapAligner::retrace (:363-571).
+// ---------------------------------------------------------------------------
+namespace {
+
+const double kTraceTol = 0.001;                    // HapAligner.cpp:345
+const double kMinSnpLogCorrect = -0.0043648054;    // HapAligner.cpp:24
+
+// tie-break helpers (:346-361); `rev` selects the mirrored preference order
+int pick3(bool rev, double v1, double v2, double v3) {
+  if (!rev) {
+    if (v1 > v2 + kTraceTol) return v1 > v3 + kTraceTol ? 0 : 2;
+    return v2 > v3 + kTraceTol ? 1 : 2;
+  }
+  if (v3 > v2 + kTraceTol) return v3 > v1 + kTraceTol ? 2 : 0;
+  return v2 > v1 + kTraceTol ? 1 : 0;
+}
+int pick2(bool rev, double v1, double v2) {
+  if (!rev) return v1 > v2 + kTraceTol ? 0 : 1;
+  return v2 > v1 + kTraceTol ? 1 : 0;
+}
+
+struct TraceAcc {
+  int nb;
+  std::vector<int> stutter, lo, hi;   // per FORWARD block; lo > hi = nothing recorded
+  int ins = 0, del = 0;
+  std::vector<std::pair<int, int> > indels, snps;
+  explicit TraceAcc(int n) : nb(n), stutter(n, HIPSTR_NO_STR_DATA), lo(n, 1 << 30), hi(n, -1) {}
+  void touch(int block, int read_index) { lo[block] = std::min(lo[block], read_index); hi[block] = std::max(hi[block], read_index); }
+};
+
+// One side.  `side_to_read(k)` maps a column of this side to the index of that base in the read.
+std::string walk_back(const std::vector<OrientedBlock>& hb, bool rev, const SideDP& sd, const std::vector<int>& start_of,
+                      int block_index, int base_index, long matrix_index, int read_len, TraceAcc& acc) {
+  const Tables& t = T();
+  const int n = sd.n, nb = (int)hb.size();
+  auto to_read = [&](int k) { return rev ? read_len - 1 - k : k; };
+  int seq_index = n - 1, type = 0;   // 0 MATCH, 1 DEL, 2 INS
+  std::string aln;
+  while (block_index >= 0) {
+    const OrientedBlock& blk = hb[block_index];
+    const int fw_block = rev ? nb - 1 - block_index : block_index;
+    if (blk.period > 0) {
+      const int size = sd.art_size[(size_t)n * block_index + seq_index], pos = sd.art_pos[(size_t)n * block_index + seq_index];
+      const int len = (int)blk.seq.size();
+      int i = 0;
+      for (; i < std::min(seq_index + 1, pos); i++) { aln += 'M'; acc.touch(fw_block, to_read(seq_index - i)); }
+      if (size < 0) aln += std::string(-size, 'D');
+      else for (; i < std::min(seq_index + 1, pos + size); i++) { aln += 'I'; acc.touch(fw_block, to_read(seq_index - i)); }
+      for (; i < std::min(len + size, seq_index + 1); i++) { aln += 'M'; acc.touch(fw_block, to_read(seq_index - i)); }
+      acc.stutter[fw_block] = size;
+      if (len + size >= seq_index + 1) return aln;   // the read ends inside the repeat block
+      matrix_index -= (len + size + (long)n * len);
+      type = 0;
+      seq_index -= (len + size);
+    } else {
+      int prev_type = -1;
+      int pos = start_of[block_index] + (rev ? -base_index : base_index);
+      const int step = rev ? 1 : -1;
+      int indel_seq_index = -1, indel_pos = -1;
+      while (base_index >= 0 && seq_index >= 0) {
+        const int hp = std::min(kMaxHomop, std::max(homopolymer_len(hb, block_index, base_index),
+                                                    homopolymer_len(hb, block_index, std::max(0, base_index - 1))));
+        if (type != prev_type) {
+          if (prev_type == 1) acc.indels.push_back(rev ? std::make_pair(indel_pos, indel_pos - pos) : std::make_pair(pos + 1, pos - indel_pos));
+          else if (prev_type == 2) acc.indels.push_back(std::make_pair(indel_pos + (rev ? 0 : 1), indel_seq_index - seq_index));
+          if (type == 1 || type == 2) { indel_seq_index = seq_index; indel_pos = pos; }
+          prev_type = type;
+        }
+        if (type == 0) {
+          if (blk.seq[base_index] != sd.rd[seq_index] && sd.lc[seq_index] > kMinSnpLogCorrect) acc.snps.push_back(std::make_pair(pos, (int)sd.rd[seq_index]));
+          acc.touch(fw_block, to_read(seq_index));
+          aln += 'M'; seq_index--; base_index--; pos += step;
+        } else if (type == 1) {
+          acc.del++; aln += 'D'; base_index--; pos += step;
+        } else {
+          acc.ins++; acc.touch(fw_block, to_read(seq_index)); aln += 'I'; seq_index--;
+        }
+        if (seq_index == -1 || (base_index == -1 && block_index == 0)) {
+          for (; seq_index != -1; seq_index--) aln += 'S';
+          return aln;
+        }
+        if (type == 0) {
+          const int best = pick3(rev, sd.I[matrix_index - 1] + t.m2i[hp], sd.D[matrix_index - n - 1] + t.m2d[hp], sd.M[matrix_index - n - 1] + t.m2m[hp]);
+          if (best == 0) { type = 2; matrix_index -= 1; }
+          else { type = best == 1 ? 1 : 0; matrix_index -= n + 1; }
+        } else if (type == 1) {
+          type = pick2(rev, sd.D[matrix_index - n] + kDelToDel, sd.M[matrix_index - n] + kDelToMatch) == 0 ? 1 : 0;
+          matrix_index -= n;
+        } else {
+          if (pick2(rev, sd.I[matrix_index - 1] + kInsToIns, sd.M[matrix_index - n - 1] + kInsToMatch) == 0) { type = 2; matrix_index -= 1; }
+          else { type = 0; matrix_index -= n + 1; }
+        }
+      }
+    }
+    --block_index;
+    if (block_index >= 0) base_index = (int)hb[block_index].seq.size() - 1;
+  }
+  return aln;
+}
+
+}  // namespace
+
+extern "C" int32_t oracle_trace_batch(const hipstr_align_batch_t* bt, const int32_t* block_start, int32_t n_traces,
+                                      const int32_t* trace_pool, const int32_t* trace_hap, const hipstr_trace_out_t* out) {
+  const Tables& t = T();
+  for (int tr = 0; tr < n_traces; tr++) {
+    const int p = trace_pool[tr];
+    int l = 0;
+    while (!(p >= bt->locus_pool_off[l] && p < bt->locus_pool_off[l + 1])) l++;
+    Locus loc(bt, l);
+    const int nb = loc.nb;
+    const int s0 = bt->pool_seq_off[p], len = bt->pool_seq_off[p + 1] - s0, seed = bt->pool_seed[p];
+    if (seed <= 0 || seed >= len - 1 || trace_hap[tr] < 0 || trace_hap[tr] >= loc.n_haps) return HIPSTR_ERR_BAD_ARG;
+    const char* bases = bt->pool_bases + s0;
+    const char* quals = bt->pool_quals + s0;
+    std::vector<double> lw(len), lc(len);
+    for (int j = 0; j < len; j++) { unsigned char q = (unsigned char)quals[j]; lw[j] = t.qual_error[q]; lc[j] = t.qual_correct[q]; }
+    SideDP L, R;
+    L.n = seed; L.rd.assign(bases, bases + seed); L.lc.assign(lc.begin(), lc.begin() + seed); L.lw.assign(lw.begin(), lw.begin() + seed);
+    R.n = len - seed - 1; R.rd.assign(bases + seed + 1, bases + len); std::reverse(R.rd.begin(), R.rd.end());
+    R.lc.assign(lc.begin() + seed + 1, lc.end()); R.lw.assign(lw.begin() + seed + 1, lw.end());
+    std::reverse(R.lc.begin(), R.lc.end()); std::reverse(R.lw.begin(), R.lw.end());
+    for (SideDP* sd : {&L, &R}) {
+      size_t cells = (size_t)sd->n * loc.max_rows;
+      sd->M.assign(cells, 0.0); sd->I.assign(cells, 0.0); sd->D.assign(cells, 0.0);
+      sd->art_size.assign((size_t)sd->n * nb, 0); sd->art_pos.assign((size_t)sd->n * nb, 0);
+    }
+    std::vector<int> opts(nb);
+    hap_options(nb, loc.nopt.data(), trace_hap[tr], opts.data());
+    std::vector<OrientedBlock> fw, rv;
+    build_oriented(loc, opts.data(), false, fw);
+    build_oriented(loc, opts.data(), true, rv);
+    fill_side(L, fw, loc, false, -1, false);
+    fill_side(R, rv, loc, false, -1, true);
+    // best seed placement (compute_aln_logprob, :163-231)
+    int hs = 0, num_seeds = 0;
+    for (auto& b : fw) { hs += (int)b.seq.size(); if (b.period == 0) num_seeds += (int)b.seq.size(); }
+    const int lf = L.n, rf = R.n;
+    const double prior = -t.int_logs[num_seeds];
+    const char sc = bases[seed];
+    int max_index = 0;
+    double best = prior + (sc == fw.front().seq[0] ? lc[seed] : lw[seed]) + L.edge + R.M[(size_t)rf * (hs - 1) - 1];
+    {
+      const double v = prior + (sc == fw.back().seq.back() ? lc[seed] : lw[seed]) + R.edge + L.M[(size_t)lf * (hs - 1) - 1];
+      if (v > best) { max_index = hs - 1; best = v; }
+      int hp = 1;
+      for (int b = 0; b < nb; b++) {
+        const std::string& sq = fw[b].seq;
+        if (fw[b].period > 0) { hp += (int)sq.size(); continue; }
+        int c0 = (b == 0 ? 1 : 0), c1 = (b == nb - 1 ? (int)sq.size() - 1 : (int)sq.size());
+        for (int c = c0; c < c1; c++, hp++) {
+          const double w = prior + (sc == sq[c] ? lc[seed] : lw[seed]) + L.M[(size_t)lf * hp - 1] + R.M[(size_t)rf * (hs - hp - 1) - 1];
+          if (w > best) { max_index = hp; best = w; }
+        }
+      }
+    }
+    // genomic start() of the oriented blocks: forward = block start; reversed block = end - 1 of the original
+    std::vector<int> start_fw(nb), start_rv(nb);
+    for (int b = 0; b < nb; b++) {
+      start_fw[b] = block_start[loc.first_block + b];
+      start_rv[nb - 1 - b] = block_start[loc.first_block + b] + loc.option_len(b, 0) - 1;
+    }
+    auto coords = [&](const std::vector<OrientedBlock>& hb, int pos, int& blk, int& off) {
+      for (blk = 0; pos >= (int)hb[blk].seq.size(); blk++) pos -= (int)hb[blk].seq.size();
+      off = pos;
+    };
+    TraceAcc acc(nb);
+    std::string left, right;
+    int fb, fc;
+    coords(fw, max_index, fb, fc);
+    if (max_index == 0) left = std::string(seed, 'S');
+    else {
+      const long mi = (long)seed * max_index - 1;
+      if (fc == 0) left = walk_back(fw, false, L, start_fw, fb - 1, (int)fw[fb - 1].seq.size() - 1, mi, len, acc);
+      else left = walk_back(fw, false, L, start_fw, fb, fc - 1, mi, len, acc);
+    }
+    std::reverse(left.begin(), left.end());
+    if (fw[fb].period == 0) acc.touch(fb, seed);
+    const int rmax = hs - 1 - max_index;
+    int rb, rc;
+    coords(rv, rmax, rb, rc);
+    if (rmax == 0) right = std::string(len - 1 - seed, 'S');
+    else {
+      const long mi = (long)(len - 1 - seed) * rmax - 1;
+      if (rc == 0) right = walk_back(rv, true, R, start_rv, rb - 1, (int)rv[rb - 1].seq.size() - 1, mi, len, acc);
+      else right = walk_back(rv, true, R, start_rv, rb, rc - 1, mi, len, acc);
+    }
+    const std::string aln = left + "M" + right;
+    if ((int)aln.size() + 1 > out->aln_stride) return HIPSTR_ERR_BAD_ARG;
+    std::memcpy(out->hap_aln + (size_t)tr * out->aln_stride, aln.c_str(), aln.size() + 1);
+    out->seed_hap_pos[tr] = max_index;
+    for (int b = 0; b < HIPSTR_MAX_BLOCKS_PER_LOCUS; b++) {
+      const size_t o = (size_t)tr * HIPSTR_MAX_BLOCKS_PER_LOCUS + b;
+      out->stutter_size[o] = b < nb ? acc.stutter[b] : HIPSTR_NO_STR_DATA;
+      const bool any = b < nb && acc.hi[b] >= acc.lo[b];
+      out->span_start[o] = any ? acc.lo[b] : 0;
+      out->span_len[o] = any ? acc.hi[b] - acc.lo[b] + 1 : 0;
+    }
+    out->flank_ins[tr] = acc.ins; out->flank_del[tr] = acc.del;
+    out->n_indels[tr] = (int)acc.indels.size(); out->n_snps[tr] = (int)acc.snps.size();
+    for (int k = 0; k < HIPSTR_MAX_TRACE_INDELS; k++) {
+      const size_t o = ((size_t)tr * HIPSTR_MAX_TRACE_INDELS + k) * 2;
+      out->indels[o] = k < (int)acc.indels.size() ? acc.indels[k].first : 0;
+      out->indels[o + 1] = k < (int)acc.indels.size() ? acc.indels[k].second : 0;
+    }
+    for (int k = 0; k < HIPSTR_MAX_TRACE_SNPS; k++) {
+      const size_t o = ((size_t)tr * HIPSTR_MAX_TRACE_SNPS + k) * 2;
+      out->snps[o] = k < (int)acc.snps.size() ? acc.snps[k].first : 0;
+      out->snps[o + 1] = k < (int)acc.snps.size() ? acc.snps[k].second : 0;
+    }
+  }
+  return HIPSTR_OK;
+}
+
 extern "C" {
 
 double oracle_fast_lse2(double a, double b) { return lse2(a, b); }

@@ -61,6 +61,10 @@ int32_t oracle_extract_genotypes(int32_t n_loci, const int32_t* locus_sample_off
                                  double* log_phased, double* log_unphased, double* hap_log_phased,
                                  double* hap_log_unphased, double* gl, double* phased_gl, double* gl_diff, int32_t* pl);
 
+/* HapAligner::trace_optimal_aln for a list of (pool, haplotype) pairs; same arguments as the product entry. */
+int32_t oracle_trace_batch(const hipstr_align_batch_t* batch, const int32_t* block_start, int32_t n_traces,
+                           const int32_t* trace_pool, const int32_t* trace_hap, const hipstr_trace_out_t* out);
+
 /* EMStutterGenotyper::train for every locus of the batch (em_stutter_genotyper.cpp:170-226). */
 int32_t oracle_em_train(const hipstr_em_batch_t* batch, int32_t max_iter, double min_LL_abs_change,
                         double min_LL_frac_change, double* params_out, uint8_t* converged_out,

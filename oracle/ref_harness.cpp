@@ -19,7 +19,10 @@
 
 #include "SeqAlignment/AlignmentData.h"
 #include "SeqAlignment/AlignmentModel.h"
+// the harness needs to see whether a block got STR data at all; AlignmentTrace has no accessor for that
+#define private public
 #include "SeqAlignment/AlignmentTraceback.h"
+#undef private
 #include "SeqAlignment/HapAligner.h"
 #include "SeqAlignment/HapBlock.h"
 #include "SeqAlignment/Haplotype.h"
@@ -228,6 +231,66 @@ int32_t ref_posteriors(int32_t n_loci, const int32_t* locus_read_off, const int3
     if (total_ll_out) total_ll_out[l] = total;
     ll_off += (size_t)(r1 - r0) * H;
     post_off += (size_t)S * H * H;
+  }
+  return HIPSTR_OK;
+}
+
+// HapAligner::trace_optimal_aln for a list of (pool, haplotype) pairs.  Besides the index-range outputs of
+// hipstr_trace_out_t, the strings the reference keeps are returned verbatim so the tests can check that
+// read[span] reproduces them: str_or_flank_seq is [n_traces][8][seq_stride].
+int32_t ref_trace_batch(const hipstr_align_batch_t* bt, const int32_t* block_start, int32_t n_traces, const int32_t* trace_pool,
+                        const int32_t* trace_hap, const hipstr_trace_out_t* out, char* str_or_flank_seq, int32_t seq_stride) {
+  ensure_init();
+  BaseQuality base_quality;
+  for (int tr = 0; tr < n_traces; tr++) {
+    const int p = trace_pool[tr];
+    int l = 0;
+    while (!(p >= bt->locus_pool_off[l] && p < bt->locus_pool_off[l + 1])) l++;
+    const int b0 = bt->locus_block_off[l], nb = bt->locus_block_off[l + 1] - b0;
+    std::vector<int32_t> starts(nb), ends(nb);
+    for (int b = 0; b < nb; b++) {
+      const int o0 = bt->block_opt_off[b0 + b];
+      starts[b] = block_start[b0 + b];
+      ends[b] = starts[b] + (bt->opt_seq_off[o0 + 1] - bt->opt_seq_off[o0]);
+    }
+    RefLocus rl(bt, l, starts.data(), ends.data());
+    std::vector<bool> mask(rl.hap->num_combs(), true);
+    HapAligner aligner(rl.hap, mask);
+    const int s0 = bt->pool_seq_off[p], s1 = bt->pool_seq_off[p + 1];
+    Alignment aln(0, 0, false, "READPOOL", std::string(bt->pool_quals + s0, bt->pool_quals + s1),
+                  std::string(bt->pool_bases + s0, bt->pool_bases + s1), "");
+    AlignmentTrace* trace = aligner.trace_optimal_aln(aln, bt->pool_seed[p], trace_hap[tr], &base_quality);
+    const std::string& ha = trace->hap_aln();
+    if ((int)ha.size() + 1 > out->aln_stride) { delete trace; return HIPSTR_ERR_BAD_ARG; }
+    std::memcpy(out->hap_aln + (size_t)tr * out->aln_stride, ha.c_str(), ha.size() + 1);
+    out->seed_hap_pos[tr] = -1;   // not observable through the public interface
+    for (int b = 0; b < HIPSTR_MAX_BLOCKS_PER_LOCUS; b++) {
+      const size_t o = (size_t)tr * HIPSTR_MAX_BLOCKS_PER_LOCUS + b;
+      out->stutter_size[o] = HIPSTR_NO_STR_DATA; out->span_start[o] = 0; out->span_len[o] = 0;
+      char* dst = str_or_flank_seq + o * seq_stride;
+      dst[0] = 0;
+      if (b >= nb) continue;
+      std::string sq = trace->flank_seq(b);
+      if (trace->str_data_[b] != NULL) { out->stutter_size[o] = trace->stutter_size(b); sq = trace->str_seq(b); }
+      if ((int)sq.size() + 1 > seq_stride) { delete trace; return HIPSTR_ERR_BAD_ARG; }
+      std::memcpy(dst, sq.c_str(), sq.size() + 1);
+      out->span_len[o] = (int32_t)sq.size();
+    }
+    out->flank_ins[tr] = trace->flank_ins_size(); out->flank_del[tr] = trace->flank_del_size();
+    const auto& ind = trace->flank_indel_data();
+    const auto& snp = trace->flank_snp_data();
+    out->n_indels[tr] = (int)ind.size(); out->n_snps[tr] = (int)snp.size();
+    for (int k = 0; k < HIPSTR_MAX_TRACE_INDELS; k++) {
+      const size_t o = ((size_t)tr * HIPSTR_MAX_TRACE_INDELS + k) * 2;
+      out->indels[o] = k < (int)ind.size() ? ind[k].first : 0;
+      out->indels[o + 1] = k < (int)ind.size() ? ind[k].second : 0;
+    }
+    for (int k = 0; k < HIPSTR_MAX_TRACE_SNPS; k++) {
+      const size_t o = ((size_t)tr * HIPSTR_MAX_TRACE_SNPS + k) * 2;
+      out->snps[o] = k < (int)snp.size() ? snp[k].first : 0;
+      out->snps[o + 1] = k < (int)snp.size() ? (int)snp[k].second : 0;
+    }
+    delete trace;
   }
   return HIPSTR_OK;
 }

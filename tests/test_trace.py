@@ -1,0 +1,113 @@
+"""a16: alignment traceback (HapAligner::trace_optimal_aln / retrace).
+CPU: the oracle restatement reproduces the compiled reference exactly -- alignment-operation strings, stutter
+sizes, flank indel / SNP lists and, through read[span], the STR / flank sequences the reference keeps as strings.
+GPU (K5): every output must be identical to the oracle's (all integers / bytes)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import checkers
+from hipstr_b200.capi import MAX_BLOCKS, AlignBatch, BatchBuilder, TraceOut, c_i32p, trace_batch
+
+KEYS = ("stutter_size", "span_start", "span_len", "flank_ins", "flank_del", "n_indels", "indels", "n_snps", "snps")
+
+
+def _fn(lib, name, extra=False):
+    f = getattr(lib, name)
+    f.restype = C.c_int32
+    f.argtypes = [C.POINTER(AlignBatch), c_i32p, C.c_int32, c_i32p, c_i32p, C.POINTER(TraceOut)] + ([C.c_char_p, C.c_int32] if extra else [])
+    return f
+
+
+def block_starts(batch, first=1000):
+    """Genomic starts: blocks of a locus tile the reference from `first` on (reference allele lengths)."""
+    lbo = np.ctypeslib.as_array(batch.locus_block_off, shape=(batch.n_loci + 1,))
+    boo = np.ctypeslib.as_array(batch.block_opt_off, shape=(batch.n_blocks + 1,))
+    oso = np.ctypeslib.as_array(batch.opt_seq_off, shape=(batch.n_options + 1,))
+    out = []
+    for l in range(batch.n_loci):
+        pos = first
+        for b in range(lbo[l], lbo[l + 1]):
+            out.append(pos)
+            pos += int(oso[boo[b] + 1] - oso[boo[b]])
+    return np.array(out, np.int32)
+
+
+def synth_traces(name, n=120, seed=0):
+    s = cases.synth(name)
+    rng = np.random.default_rng(seed)
+    pools = np.nonzero(s.pool_seed >= 0)[0][:n].astype(np.int32)
+    loc = np.searchsorted(s.locus_pool_off, pools, side="right") - 1
+    haps = np.array([rng.integers(0, s.n_haps[l]) for l in loc], np.int32)
+    addr = C.c_void_p.from_buffer(s.batch, AlignBatch.pool_bases.offset).value
+    pb = C.string_at(addr, int(s.pool_seq_off[-1]))
+    reads = [pb[s.pool_seq_off[p]:s.pool_seq_off[p + 1]].decode() for p in pools]
+    return s, s.batch, pools, haps, reads
+
+
+def hand_traces(kw, seed=0):
+    blocks, reads = cases.handmade(**kw)
+    b = BatchBuilder().add_locus(blocks, reads).build()
+    rng = np.random.default_rng(seed)
+    H = cases.n_haps_of(blocks)
+    pools = np.repeat(np.arange(len(reads)), 2).astype(np.int32)
+    haps = rng.integers(0, H, len(pools)).astype(np.int32)
+    return None, b, pools, haps, [reads[p][0] for p in pools]
+
+
+SYNTH = ["cfg1_plumbing", "cfg2_shape", "period2", "period1_homopolymer", "period3_noisy", "short_reads", "long_untrimmed"]
+HAND = [dict(seed=1), dict(seed=4, flank_opts=(2, 1)), dict(seed=6, homopolymer_edges=True, flank_opts=(2, 2), rep_opts=3, motif="A", copies=9),
+        dict(seed=8, motif="AGAT", copies=3, rep_opts=5), dict(seed=10, qual_lo=-5, qual_hi=60),
+        dict(seed=12, n_reads=40, motif="AAAG", copies=20, rep_opts=3)]
+ALL = [("synth", n) for n in SYNTH] + [("hand", k) for k in HAND]
+
+
+def _load(case):
+    kind, arg = case
+    return synth_traces(arg) if kind == "synth" else hand_traces(arg)
+
+
+@pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libhipstr_ref.so not built")
+@pytest.mark.parametrize("case", ALL, ids=lambda c: str(c[1]))
+def test_oracle_trace_equals_reference(case):
+    keep, batch, pools, haps, reads = _load(case)
+    bs = block_starts(batch)
+    st, o = trace_batch(_fn(checkers.oracle(), "oracle_trace_batch"), batch, bs, pools, haps)
+    assert st == 0
+    stride = 1024
+    buf = C.create_string_buffer(len(pools) * MAX_BLOCKS * stride)
+    st, r = trace_batch(_fn(checkers.ref(), "ref_trace_batch", True), batch, bs, pools, haps, extra_args=(buf, C.c_int32(stride)))
+    assert st == 0
+    assert o["hap_aln"] == r["hap_aln"]
+    for k in ("stutter_size", "flank_ins", "flank_del", "n_indels", "indels", "n_snps", "snps"):
+        assert np.array_equal(o[k], r[k]), k
+    for i in range(len(pools)):       # read[span] reproduces the reference's str_seq / flank_seq strings
+        for b in range(MAX_BLOCKS):
+            want = buf.raw[(i * MAX_BLOCKS + b) * stride:(i * MAX_BLOCKS + b + 1) * stride].split(b"\0")[0].decode()
+            assert reads[i][o["span_start"][i][b]:o["span_start"][i][b] + o["span_len"][i][b]] == want, (i, b)
+    # the operation string consumes exactly the read: M + I + S == read length
+    for a, rd in zip(o["hap_aln"], reads):
+        assert sum(a.count(c) for c in "MIS") == len(rd)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ALL, ids=lambda c: str(c[1]))
+def test_gpu_trace_equals_oracle(case):
+    from hipstr_b200.capi import Context
+    keep, batch, pools, haps, reads = _load(case)
+    bs = block_starts(batch)
+    st, o = trace_batch(_fn(checkers.oracle(), "oracle_trace_batch"), batch, bs, pools, haps)
+    assert st == 0
+    ctx = Context(0)
+    g = ctx.trace(batch, bs, pools, haps)
+    ctx.close()
+    bad = [i for i in range(len(pools)) if g["hap_aln"][i] != o["hap_aln"][i]]
+    if bad:
+        i = bad[0]
+        print("first mismatch trace %d pool %d hap %d\n gpu    %s\n oracle %s" % (i, pools[i], haps[i], g["hap_aln"][i], o["hap_aln"][i]))
+    assert not bad, "%d of %d alignment strings differ" % (len(bad), len(pools))
+    assert np.array_equal(g["seed_hap_pos"], o["seed_hap_pos"])
+    for k in KEYS:
+        assert np.array_equal(g[k], o[k]), k
