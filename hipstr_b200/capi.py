@@ -251,6 +251,8 @@ def load():
     lib.hipstr_free_genotype_batch.argtypes = [vp, vp]
     lib.hipstr_extract_genotypes_host.restype = C.c_int32
     lib.hipstr_extract_genotypes_host.argtypes = [vp] + EXTRACT_ARGTYPES
+    lib.hipstr_trace_batch_host.restype = C.c_int32
+    lib.hipstr_trace_batch_host.argtypes = [vp, B, c_i32p, C.c_int32, c_i32p, c_i32p, C.POINTER(TraceOut)]
     lib.hipstr_em_train_host.restype = C.c_int32
     lib.hipstr_em_train_host.argtypes = [vp, C.POINTER(EmBatch), C.c_int32, C.c_double, C.c_double, c_f64p, c_u8p, c_i32p,
                                          c_f64p]
@@ -480,6 +482,12 @@ class Context:
         st, out = extract_genotypes(self.lib.hipstr_extract_genotypes_host, locus_sample_off, n_haps, n_variants,
                                     hap_to_allele, haploid, post, sample_ll, self.h)
         self._check(st, "extract_genotypes_host")
+        return out
+
+    def trace(self, batch, block_start, trace_pool, trace_hap, aln_stride=1024):
+        """hipstr_trace_batch_host -> dict of traceback outputs (see hipstr_trace_out_t)."""
+        st, out = trace_batch(self.lib.hipstr_trace_batch_host, batch, block_start, trace_pool, trace_hap, aln_stride, self.h)
+        self._check(st, "trace_batch_host")
         return out
 
     def em_train(self, batch, max_iter=100, min_abs=0.01, min_frac=0.001):

@@ -828,4 +828,115 @@ hipstr_status_t hipstr_extract_genotypes_host(hipstr_ctx_t* ctx, int32_t n_loci,
   return HIPSTR_OK;
 }
 
+hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch, const int32_t* block_start,
+                                        int32_t n_traces, const int32_t* trace_pool, const int32_t* trace_hap,
+                                        const hipstr_trace_out_t* out) {
+  if (!ctx || !batch || !block_start || n_traces < 0 || !out) return HIPSTR_ERR_BAD_ARG;
+  if (n_traces == 0) return HIPSTR_OK;
+  if (!trace_pool || !trace_hap || !out->hap_aln || !out->seed_hap_pos || !out->stutter_size || !out->span_start ||
+      !out->span_len || !out->flank_ins || !out->flank_del || !out->n_indels || !out->indels || !out->n_snps || !out->snps)
+    return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
+  // a trace sees its haplotype from scratch: lower with fresh homopolymer classes, no masks
+  hipstr_align_batch_t plain = *batch;
+  plain.realign_pool = nullptr;
+  plain.realign_hap = nullptr;
+  FlatBatch& f = ctx->flat;
+  std::string err;
+  hipstr_status_t st;
+  try {
+    st = flatten_batch(&plain, f, err, /*fresh_rows=*/true);
+  } catch (const std::bad_alloc&) {
+    return fail(ctx, HIPSTR_ERR_CUDA, "out of host memory while staging the batch");
+  }
+  if (st != HIPSTR_OK) return fail(ctx, st, err);
+  int n_max = 1, l_max = 1;
+  std::vector<int32_t> block_ref_end((size_t)batch->n_blocks), locus_block0((size_t)batch->n_loci);
+  for (int l = 0; l < batch->n_loci; l++) {
+    locus_block0[l] = batch->locus_block_off[l];
+    for (int b = batch->locus_block_off[l]; b < batch->locus_block_off[l + 1]; b++) {
+      const int o0 = batch->block_opt_off[b];
+      block_ref_end[b] = block_start[b] + (batch->opt_seq_off[o0 + 1] - batch->opt_seq_off[o0]);
+    }
+  }
+  for (int t = 0; t < n_traces; t++) {
+    const int p = trace_pool[t];
+    if (p < 0 || p >= batch->n_pools) return fail(ctx, HIPSTR_ERR_BAD_ARG, "trace_pool out of range");
+    const DevPool& dp = f.pools[p];
+    if (trace_hap[t] < 0 || trace_hap[t] >= dp.n_haps) return fail(ctx, HIPSTR_ERR_BAD_ARG, "trace_hap out of range");
+    if (dp.seed <= 0 || dp.seed >= dp.len - 1) return fail(ctx, HIPSTR_ERR_INVALID_SEED, "a traced read needs a seed");
+    n_max = std::max(n_max, dp.len);
+    l_max = std::max(l_max, f.hapsides[dp.hap_rec0 + 2 * trace_hap[t]].len);
+  }
+  if (out->aln_stride < n_max + l_max + 2) return fail(ctx, HIPSTR_ERR_BAD_ARG, "aln_stride too small");
+  cudaStream_t s = ctx->stream;
+  hipstr_dev_batch& d = ctx->scratch;
+  CU(put(d.pools, f.pools, s));
+  CU(put(d.bases, f.bases, s));
+  CU(put(d.quals, f.quals, s));
+  CU(put(d.hapsides, f.hapsides, s));
+  CU(put(d.hapbytes, f.hapbytes, s));
+  CU(put(d.blocks, f.blocks, s));
+  CU(put(d.reps, f.reps, s));
+  CU(put(d.progs, f.progs, s));
+  CU(put(d.logrun, f.prog_logrun, s));
+  DevBuf* m = ctx->d_misc;
+  DevBuf* o = ctx->d_out;
+  CU(put(m[0], trace_pool, (size_t)n_traces, s));
+  CU(put(m[1], trace_hap, (size_t)n_traces, s));
+  CU(put(m[2], block_start, (size_t)batch->n_blocks, s));
+  CU(put(m[3], block_ref_end, s));
+  CU(put(m[4], locus_block0, s));
+  const int n_slots = (std::min(n_traces, 8192) + 63) / 64 * 64;
+  TraceParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.slab_doubles = (int64_t)3 * n_max * l_max;
+  p.art_ints = (int64_t)2 * n_max * HIPSTR_MAX_BLOCKS;
+  CU(ctx->d_last.reserve((size_t)n_slots * p.slab_doubles * sizeof(double)));
+  CU(m[5].reserve((size_t)n_slots * p.art_ints * sizeof(int32_t)));
+  const size_t T = (size_t)n_traces;
+  CU(o[0].reserve(T * out->aln_stride));
+  CU(o[1].reserve(T * (1 + 3 * HIPSTR_MAX_BLOCKS_PER_LOCUS + 4 + 2 * HIPSTR_MAX_TRACE_INDELS + 2 * HIPSTR_MAX_TRACE_SNPS) * sizeof(int32_t)));
+  int32_t* di = (int32_t*)o[1].p;
+  p.n_traces = n_traces;
+  p.trace_pool = (const int32_t*)m[0].p; p.trace_hap = (const int32_t*)m[1].p;
+  p.pools = (const DevPool*)d.pools.p; p.bases = (const char*)d.bases.p; p.quals = (const char*)d.quals.p;
+  p.hapsides = (const DevHapSide*)d.hapsides.p; p.hapbytes = (const uint8_t*)d.hapbytes.p;
+  p.blocks = (const DevBlock*)d.blocks.p; p.reps = (const DevRep*)d.reps.p;
+  p.progs = (const DevProgEntry*)d.progs.p; p.prog_logrun = (const double*)d.logrun.p;
+  p.qual_lut = ctx->d_qual_lut; p.trans = ctx->d_trans; p.int_logs = ctx->d_int_logs;
+  p.block_start = (const int32_t*)m[2].p; p.block_ref_end = (const int32_t*)m[3].p; p.locus_block0 = (const int32_t*)m[4].p;
+  p.slab = (double*)ctx->d_last.p; p.art_slab = (int32_t*)m[5].p;
+  p.aln_stride = out->aln_stride;
+  p.out_aln = (char*)o[0].p;
+  p.out_seed_pos = di; di += T;
+  p.out_stutter = di; di += T * HIPSTR_MAX_BLOCKS_PER_LOCUS;
+  p.out_span_start = di; di += T * HIPSTR_MAX_BLOCKS_PER_LOCUS;
+  p.out_span_len = di; di += T * HIPSTR_MAX_BLOCKS_PER_LOCUS;
+  p.out_flank_ins = di; di += T;
+  p.out_flank_del = di; di += T;
+  p.out_n_indels = di; di += T;
+  p.out_n_snps = di; di += T;
+  p.out_indels = di; di += T * 2 * HIPSTR_MAX_TRACE_INDELS;
+  p.out_snps = di;
+  CU(cudaMemsetAsync(o[0].p, 0, T * out->aln_stride, s));
+  CU(launch_trace(p, n_slots, s));
+  ctx->last_launches = 1;
+  CU(get(ctx, out->hap_aln, p.out_aln, T * out->aln_stride));
+  CU(get(ctx, out->seed_hap_pos, p.out_seed_pos, T));
+  CU(get(ctx, out->stutter_size, p.out_stutter, T * HIPSTR_MAX_BLOCKS_PER_LOCUS));
+  CU(get(ctx, out->span_start, p.out_span_start, T * HIPSTR_MAX_BLOCKS_PER_LOCUS));
+  CU(get(ctx, out->span_len, p.out_span_len, T * HIPSTR_MAX_BLOCKS_PER_LOCUS));
+  CU(get(ctx, out->flank_ins, p.out_flank_ins, T));
+  CU(get(ctx, out->flank_del, p.out_flank_del, T));
+  CU(get(ctx, out->n_indels, p.out_n_indels, T));
+  CU(get(ctx, out->n_snps, p.out_n_snps, T));
+  CU(get(ctx, out->indels, p.out_indels, T * 2 * HIPSTR_MAX_TRACE_INDELS));
+  CU(get(ctx, out->snps, p.out_snps, T * 2 * HIPSTR_MAX_TRACE_SNPS));
+  CU(cudaStreamSynchronize(s));
+  end_call(ctx);
+  return HIPSTR_OK;
+}
+
 }  // extern "C"

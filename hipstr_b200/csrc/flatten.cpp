@@ -236,7 +236,7 @@ int64_t count_alignments(const hipstr_align_batch_t* b) {
   return total;
 }
 
-hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std::string& err) {
+hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std::string& err, bool fresh_rows) {
   if (!b || b->n_loci < 0) { err = "null batch"; return HIPSTR_ERR_BAD_ARG; }
   if (b->n_loci > 0 && (!b->locus_block_off || !b->locus_pool_off || !b->locus_hap_off || !b->locus_out_off ||
                         !b->block_period || !b->block_opt_off || !b->block_stutter || !b->opt_seq_off || !b->opt_seq ||
@@ -474,7 +474,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
         max_len = std::max(max_len, len);
         out.hapsides.push_back(hs);
       }
-      reuse = live;   // HapAligner.cpp:615-619,634: a skipped haplotype breaks the reuse chain
+      reuse = live && !fresh_rows;   // HapAligner.cpp:615-619,634: a skipped haplotype breaks the reuse chain
     }
     // DevHapSide offsets into hapbytes were taken while the vector was still growing: they are
     // indices, not pointers, so they stay valid.

@@ -88,7 +88,10 @@ struct FlatBatch {
 };
 
 /* Returns HIPSTR_OK or an error with a message. */
-hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std::string& err);
+/* fresh_rows: give every haplotype the homopolymer classes of a from-scratch alignment (what
+ * trace_optimal_aln sees: the haplotype is fixed, nothing is reused) instead of replaying the
+ * reuse history of a process_reads run. */
+hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std::string& err, bool fresh_rows = false);
 int64_t count_alignments(const hipstr_align_batch_t* b);
 
 /* Per-block option index of haplotype `hap`: closed form of the reflected mixed-radix Gray

@@ -1,0 +1,428 @@
+/*
+ * trace.cu -- K5: alignment traceback (HapAligner::trace_optimal_aln, SeqAlignment/HapAligner.cpp:711-722
+ * -> process_read(retrace_aln = true) :636-690 -> retrace :363-571).
+ *
+ * First version: ONE THREAD per (pooled read, haplotype) trace.  A trace needs the three FULL
+ * matrices of both sides of the seed (the forward kernel K1 keeps only a row in registers), the
+ * best artifact size / position of every repeat-block column, and then a strictly sequential walk
+ * back along the best path -- a different shape of work from K1 (one haplotype per read instead of
+ * all of them, memory-resident state, data-dependent control), so it gets its own kernel: every
+ * thread owns a slab of global memory for its matrices and runs the reference's recurrences in the
+ * reference's order (bit-identical cells, hence identical tie decisions within TRACE_LL_TOL).
+ * The repeat-block evaluator replays the same host-unrolled programs as K1 (layout.h); the position
+ * of the best artifact is read off the program: after a step, the reference's position counter is
+ * one above the next step's position.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hipstr_b200.h"
+#include "fastapprox.cuh"
+#include "kernels.h"
+#include "layout.h"
+
+namespace hipstr {
+
+#define T_IMPOSSIBLE (-1000000000.0)
+#define T_INS_TO_INS (-1.0)
+#define T_INS_TO_MATCH (-0.4586751453870818910216436)
+#define T_DEL_TO_DEL (-1.0)
+#define T_DEL_TO_MATCH (-0.4586751453870818910216436)
+#define T_TRACE_TOL 0.001                    /* HapAligner.cpp:345 */
+#define T_MIN_SNP_LOG_CORRECT (-0.0043648054) /* HapAligner.cpp:24 */
+
+__device__ __forceinline__ double tmax(double a, double b) { return a > b ? a : b; }
+
+// One side of the seed: column k of the side is read base (rev ? n_read-1-k : k).
+struct TSide {
+  const uint8_t* bases;   // codes, read order
+  const uint8_t* quals;
+  const double* lut;      // [256][2]
+  int n, rev, n_read;
+  __device__ __forceinline__ int ridx(int k) const { return rev ? n_read - 1 - k : k; }
+  __device__ __forceinline__ int code(int k) const { return bases[ridx(k)]; }
+  __device__ __forceinline__ double lc(int k) const { return __ldg(lut + 2 * quals[ridx(k)]); }
+  __device__ __forceinline__ double emit(int k, int x) const {
+    const int r = ridx(k);
+    return __ldg(lut + 2 * quals[r] + (bases[r] == x ? 0 : 1));
+  }
+};
+
+struct TRep {
+  const uint8_t* s;          // oriented allele codes
+  const DevProgEntry* progs;
+  const double* logrun;
+  const DevRep* rep;
+  const double* int_logs;
+  int B, p, left_align;
+};
+
+// match_probs_[q] (StutterAlignerClass.cpp:12-53), recomputed on demand
+__device__ double t_match(const TSide& sd, const TRep& r, int q) {
+  const int terms = min(q + 1, r.B);
+  double acc = 0.0;
+  for (int t = 0; t < terms; t++) acc += sd.emit(q - t, r.s[r.B - 1 - t]);
+  return acc;
+}
+
+// Replays a position walk twice (maximum, then sum) and tracks the reference's best position
+// (StutterAlignerClass.cpp:92-95,137-140: the position counter after a step is one above the next
+// step's position, so best_pos = 1 - i == -next.pos).
+template <bool INS>
+__device__ double t_walk(const TSide& sd, const TRep& r, int prog_index, int stop, int j, int units, double lp0,
+                         int tail_base, int& best_pos) {
+  const int CB = HIPSTR_VAL_STRIDE * 8;
+  double mx = lp0, total = 0.0, best = lp0;
+  best_pos = 0;
+  int fin = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const DevProgEntry* e = r.progs + prog_index;
+    const double* lr = r.logrun + prog_index;
+    double lp = lp0;
+    if (pass) total = lse_term(lp0, mx);
+    while (e->pos > stop) {
+      if (e->moves) {
+        // offsets are pos * CB + code * 8 (see DevProgEntry); recover the two base codes
+        const int xa = (e->off_a - e->pos * CB) / 8, xb = (e->off_b - e->pos * CB) / 8;
+        if (INS) {
+          for (int m = 0; m < units; m++) {
+            const int col = j - r.p + e->pos - m * r.p;
+            lp -= sd.emit(col, xa);
+            lp += sd.emit(col, xb);
+          }
+        } else {
+          lp -= sd.emit(j + e->pos, xa);
+          lp += sd.emit(j + e->pos, xb);
+        }
+      }
+      const double term = lp + *lr;
+      if (pass) total += lse_term(term, mx);
+      else {
+        mx = tmax(mx, term);
+        if (lp > best || (r.left_align && lp == best)) { best_pos = -(e + 1)->pos; best = lp; }
+      }
+      e++; lr++;
+    }
+    fin = e->pos;
+    const bool has_tail = INS ? (fin > -tail_base) : (-fin < tail_base);
+    if (has_tail) {
+      const double tail = __ldg(r.int_logs + (tail_base + fin)) + lp;
+      if (pass) total += lse_term(tail, mx); else mx = tmax(mx, tail);
+    }
+  }
+  return lse_finish(mx, total);
+}
+
+// Repeat block of one side: the super-row `out_row` from the row above it (HapAligner.cpp:62-109).
+__device__ void t_repeat_block(const TSide& sd, const TRep& r, const double* M_prev, double* M_out, double* I_out,
+                               double* D_out, int* art_size, int* art_pos) {
+  const int B = r.B, p = r.p, n = sd.n;
+  for (int j = 0; j < n; j++) {
+    double probs[HIPSTR_NUM_ARTIFACTS];
+    double best = T_IMPOSSIBLE;
+    art_size[j] = -10000;
+    art_pos[j] = 0;
+    for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) {
+      const int units = a - HIPSTR_MAX_ARTIFACT_UNITS, D = units * p;
+      const int base_len = min(B + D, j + 1);
+      int pos = -1;
+      double v = T_IMPOSSIBLE;
+      if (base_len >= 0) {
+        double pr;
+        if (units == 0) pr = t_match(sd, r, j);
+        else if (units < 0) {
+          const int k = -units;
+          double lp0 = -__ldg(r.int_logs + (B + D + 1));
+          const int q = j - D;
+          if (q <= n - 1) {
+            double pre = 0.0;
+            for (int t = 0; t < -D; t++) pre += sd.emit(q - t, r.s[B - 1 - t]);
+            lp0 += t_match(sd, r, q) - pre;
+          } else {
+            for (int t = 0; t < base_len; t++) lp0 += sd.emit(j - t, r.s[B - 1 - t + D]);
+          }
+          pr = t_walk<false>(sd, r, __ldg(r.rep->prog_off + k), -base_len, j, k, lp0, B + D, pos);
+        } else {
+          double ins = 0.0;
+          const int upto = min(D, j + 1);
+          for (int t = 0; t < upto; t++) {
+            const int m = t % p;
+            ins += (m < B) ? sd.emit(j - t, r.s[B - 1 - m]) : sd.lc(j - t);
+          }
+          double lp0 = -__ldg(r.int_logs + (B + 1)) + ins;
+          lp0 += (base_len > D) ? t_match(sd, r, j - D) : 0.0;
+          const int stop = -min(max(0, base_len - D), B);
+          pr = t_walk<true>(sd, r, __ldg(r.rep->prog_off), stop, j, units, lp0, B, pos);
+        }
+        const double pre_row = (j - base_len < 0) ? 0.0 : M_prev[j - base_len];
+        v = __ldg(r.rep->art + a) + pr + pre_row;
+      }
+      probs[a] = v;
+      if (v > best) { art_size[j] = D; art_pos[j] = pos; best = v; }
+    }
+    double mx = probs[0];
+    for (int a = 1; a < HIPSTR_NUM_ARTIFACTS; a++) mx = tmax(mx, probs[a]);
+    double total = 0.0;
+    for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) total += lse_term(probs[a], mx);
+    M_out[j] = lse_finish(mx, total);
+    I_out[j] = T_IMPOSSIBLE;
+    D_out[j] = T_IMPOSSIBLE;
+  }
+}
+
+// Full matrices of one side (align_seq_to_hap, HapAligner.cpp:26-161).  Matrices are [row][n].
+__device__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHapSide& hs, double* M, double* I, double* D,
+                              int* art_size, int* art_pos) {
+  const int n = sd.n;
+  const uint8_t* seq = P.hapbytes + hs.seq_off;
+  const uint8_t* rows = P.hapbytes + hs.row_off;
+  double run = 0.0;
+  for (int j = 0; j < n; j++) {
+    M[j] = sd.emit(j, seq[0]) + run;
+    I[j] = sd.lc(j) + run;
+    D[j] = T_IMPOSSIBLE;
+    run += sd.lc(j);
+  }
+  for (int b = 0; b < hs.n_blocks; b++) {
+    const DevBlock blk = P.blocks[hs.blk_off + b];
+    if (blk.rep >= 0) {
+      const DevRep* rep = P.reps + blk.rep;
+      TRep r;
+      r.s = P.hapbytes + rep->seq_off; r.progs = P.progs; r.logrun = P.prog_logrun; r.rep = rep; r.int_logs = P.int_logs;
+      r.B = rep->len; r.p = rep->period; r.left_align = rep->left_align;
+      const size_t out = (size_t)n * (blk.row_start + blk.len - 1);
+      t_repeat_block(sd, r, M + (size_t)n * (blk.row_start - 1), M + out, I + out, D + out, art_size + (size_t)n * b,
+                     art_pos + (size_t)n * b);
+      continue;
+    }
+    for (int row = blk.row_start + (b == 0 ? 1 : 0); row < blk.row_start + blk.len; row++) {
+      const int hc = seq[row];
+      const int info = rows[row], hp = info & 15;
+      const bool after = (info & HIPSTR_ROW_AFTER_REPEAT) != 0;
+      const double m2m = __ldg(P.trans + hp), m2i = __ldg(P.trans + 16 + hp), m2d = __ldg(P.trans + 32 + hp);
+      size_t at = (size_t)n * row;
+      M[at] = sd.emit(0, hc);
+      I[at] = after ? T_IMPOSSIBLE : sd.lc(0);
+      D[at] = after ? T_IMPOSSIBLE : tmax(D[at - n] + T_DEL_TO_DEL, M[at - n] + T_DEL_TO_MATCH);
+      at++;
+      for (int j = 1; j < n; j++, at++) {
+        const double e = sd.emit(j, hc);
+        if (after) {
+          M[at] = e + M[at - n - 1];
+          I[at] = T_IMPOSSIBLE;
+          D[at] = T_IMPOSSIBLE;
+        } else {
+          M[at] = e + tmax(I[at - 1] + m2i, tmax(M[at - n - 1] + m2m, D[at - n - 1] + m2d));
+          I[at] = sd.lc(j) + tmax(M[at - n - 1] + T_INS_TO_MATCH, I[at - 1] + T_INS_TO_INS);
+          D[at] = tmax(M[at - n] + T_DEL_TO_MATCH, D[at - n] + T_DEL_TO_DEL);
+        }
+      }
+    }
+  }
+  return run;
+}
+
+struct TAcc {
+  int32_t* stutter; int32_t* lo; int32_t* hi;   // per forward block
+  int32_t* indels; int32_t* snps;
+  int n_indels, n_snps, ins, del;
+  __device__ void touch(int block, int read_index) {
+    if (read_index < lo[block]) lo[block] = read_index;
+    if (read_index > hi[block]) hi[block] = read_index;
+  }
+  __device__ void indel(int pos, int size) {
+    if (n_indels < HIPSTR_MAX_TRACE_INDELS) { indels[2 * n_indels] = pos; indels[2 * n_indels + 1] = size; }
+    n_indels++;
+  }
+  __device__ void snp(int pos, int base) {
+    if (n_snps < HIPSTR_MAX_TRACE_SNPS) { snps[2 * n_snps] = pos; snps[2 * n_snps + 1] = base; }
+    n_snps++;
+  }
+};
+
+__device__ __forceinline__ int t_pick3(bool rev, double v1, double v2, double v3) {   // HapAligner.cpp:346-358
+  if (!rev) {
+    if (v1 > v2 + T_TRACE_TOL) return v1 > v3 + T_TRACE_TOL ? 0 : 2;
+    return v2 > v3 + T_TRACE_TOL ? 1 : 2;
+  }
+  if (v3 > v2 + T_TRACE_TOL) return v3 > v1 + T_TRACE_TOL ? 2 : 0;
+  return v2 > v1 + T_TRACE_TOL ? 1 : 0;
+}
+__device__ __forceinline__ int t_pick2(bool rev, double v1, double v2) {              // :360-361
+  if (!rev) return v1 > v2 + T_TRACE_TOL ? 0 : 1;
+  return v2 > v1 + T_TRACE_TOL ? 1 : 0;
+}
+
+// Homopolymer class of a flank row: the lowering stored min(15, max(h(i), h(i-1))) per row.
+// retrace (HapAligner.cpp:363-571) for one side; writes ops BACKWARDS-in-walk order into `ops`
+// (the caller reverses the left side); returns the number of ops.
+__device__ int t_walk_back(const TraceParams& P, const TSide& sd, const DevHapSide& hs, const int32_t* start_of,
+                           const double* M, const double* I, const double* D, const int* art_size, const int* art_pos,
+                           int block_index, int base_index, long matrix_index, char* ops, TAcc& acc) {
+  const int n = sd.n, nb = hs.n_blocks;
+  const bool rev = sd.rev != 0;
+  const uint8_t* seq = P.hapbytes + hs.seq_off;
+  const uint8_t* rows = P.hapbytes + hs.row_off;
+  const char* letters = "ACTGN";   // base codes of the host lowering -> characters (flatten.cpp base_code)
+  int seq_index = n - 1, type = 0, n_ops = 0;
+  while (block_index >= 0) {
+    const DevBlock blk = P.blocks[hs.blk_off + block_index];
+    const int fw_block = rev ? nb - 1 - block_index : block_index;
+    if (blk.rep >= 0) {
+      const int size = art_size[(size_t)n * block_index + seq_index], pos = art_pos[(size_t)n * block_index + seq_index];
+      const int len = blk.len;
+      int i = 0;
+      for (; i < min(seq_index + 1, pos); i++) { ops[n_ops++] = 'M'; acc.touch(fw_block, sd.ridx(seq_index - i)); }
+      if (size < 0) for (int d = 0; d < -size; d++) ops[n_ops++] = 'D';
+      else for (; i < min(seq_index + 1, pos + size); i++) { ops[n_ops++] = 'I'; acc.touch(fw_block, sd.ridx(seq_index - i)); }
+      for (; i < min(len + size, seq_index + 1); i++) { ops[n_ops++] = 'M'; acc.touch(fw_block, sd.ridx(seq_index - i)); }
+      acc.stutter[fw_block] = size;
+      if (len + size >= seq_index + 1) return n_ops;
+      matrix_index -= (len + size + (long)n * len);
+      type = 0;
+      seq_index -= (len + size);
+    } else {
+      int prev_type = -1;
+      int pos = start_of[block_index] + (rev ? -base_index : base_index);
+      const int step = rev ? 1 : -1;
+      int indel_seq_index = -1, indel_pos = -1;
+      while (base_index >= 0 && seq_index >= 0) {
+        const int hp = rows[blk.row_start + base_index] & 15;
+        if (type != prev_type) {
+          if (prev_type == 1) { if (rev) acc.indel(indel_pos, indel_pos - pos); else acc.indel(pos + 1, pos - indel_pos); }
+          else if (prev_type == 2) acc.indel(indel_pos + (rev ? 0 : 1), indel_seq_index - seq_index);
+          if (type == 1 || type == 2) { indel_seq_index = seq_index; indel_pos = pos; }
+          prev_type = type;
+        }
+        if (type == 0) {
+          const int x = sd.code(seq_index);
+          if (seq[blk.row_start + base_index] != x && sd.lc(seq_index) > T_MIN_SNP_LOG_CORRECT) acc.snp(pos, letters[x]);
+          acc.touch(fw_block, sd.ridx(seq_index));
+          ops[n_ops++] = 'M'; seq_index--; base_index--; pos += step;
+        } else if (type == 1) {
+          acc.del++; ops[n_ops++] = 'D'; base_index--; pos += step;
+        } else {
+          acc.ins++; acc.touch(fw_block, sd.ridx(seq_index)); ops[n_ops++] = 'I'; seq_index--;
+        }
+        if (seq_index == -1 || (base_index == -1 && block_index == 0)) {
+          for (; seq_index != -1; seq_index--) ops[n_ops++] = 'S';
+          return n_ops;
+        }
+        const double m2m = __ldg(P.trans + hp), m2i = __ldg(P.trans + 16 + hp), m2d = __ldg(P.trans + 32 + hp);
+        if (type == 0) {
+          const int best = t_pick3(rev, I[matrix_index - 1] + m2i, D[matrix_index - n - 1] + m2d, M[matrix_index - n - 1] + m2m);
+          if (best == 0) { type = 2; matrix_index -= 1; }
+          else { type = best == 1 ? 1 : 0; matrix_index -= n + 1; }
+        } else if (type == 1) {
+          type = t_pick2(rev, D[matrix_index - n] + T_DEL_TO_DEL, M[matrix_index - n] + T_DEL_TO_MATCH) == 0 ? 1 : 0;
+          matrix_index -= n;
+        } else {
+          if (t_pick2(rev, I[matrix_index - 1] + T_INS_TO_INS, M[matrix_index - n - 1] + T_INS_TO_MATCH) == 0) { type = 2; matrix_index -= 1; }
+          else { type = 0; matrix_index -= n + 1; }
+        }
+      }
+    }
+    --block_index;
+    if (block_index >= 0) base_index = P.blocks[hs.blk_off + block_index].len - 1;
+  }
+  return n_ops;
+}
+
+__global__ void __launch_bounds__(64) k_trace(const TraceParams P) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_slots = gridDim.x * blockDim.x;
+  for (int tr = slot; tr < P.n_traces; tr += n_slots) {
+    const DevPool pool = P.pools[P.trace_pool[tr]];
+    const int h = P.trace_hap[tr];
+    const DevHapSide hsF = P.hapsides[pool.hap_rec0 + 2 * h];
+    const DevHapSide hsR = P.hapsides[pool.hap_rec0 + 2 * h + 1];
+    const int n = pool.len, seed = pool.seed, nL = seed, nR = n - seed - 1, hs_len = hsF.len, nb = hsF.n_blocks;
+    // per-thread slab: [M I D] x (left, right) + artifact tables
+    double* slab = P.slab + (size_t)slot * P.slab_doubles;
+    double* LM = slab; double* LI = LM + (size_t)nL * hs_len; double* LD = LI + (size_t)nL * hs_len;
+    double* RM = LD + (size_t)nL * hs_len; double* RI = RM + (size_t)nR * hs_len; double* RD = RI + (size_t)nR * hs_len;
+    int* arts = P.art_slab + (size_t)slot * P.art_ints;
+    int* Ls = arts; int* Lp = Ls + nL * nb; int* Rs = Lp + nL * nb; int* Rp = Rs + nR * nb;
+    TSide L, R;
+    L.bases = (const uint8_t*)P.bases + pool.seq_off; L.quals = (const uint8_t*)P.quals + pool.seq_off; L.lut = P.qual_lut;
+    L.n = nL; L.rev = 0; L.n_read = n;
+    R = L; R.n = nR; R.rev = 1;
+    const double edgeL = t_fill_side(P, L, hsF, LM, LI, LD, Ls, Lp);
+    const double edgeR = t_fill_side(P, R, hsR, RM, RI, RD, Rs, Rp);
+    // best seed placement (compute_aln_logprob, HapAligner.cpp:163-231)
+    const uint8_t* fseq = P.hapbytes + hsF.seq_off;
+    const uint8_t* frow = P.hapbytes + hsF.row_off;
+    const double prior = -__ldg(P.int_logs + hsF.n_seed_pos);
+    const int sx = L.bases[seed];
+    const double s_ok = __ldg(P.qual_lut + 2 * L.quals[seed]), s_bad = __ldg(P.qual_lut + 2 * L.quals[seed] + 1);
+    int max_index = 0;
+    double best = prior + (sx == fseq[0] ? s_ok : s_bad) + edgeL + RM[(size_t)nR * (hs_len - 1) - 1];
+    {
+      const double v = prior + (sx == fseq[hs_len - 1] ? s_ok : s_bad) + edgeR + LM[(size_t)nL * (hs_len - 1) - 1];
+      if (v > best) { max_index = hs_len - 1; best = v; }
+      for (int i = 1; i < hs_len - 1; i++) {
+        if (frow[i] & HIPSTR_ROW_REPEAT) continue;
+        const double w = prior + (sx == fseq[i] ? s_ok : s_bad) + LM[(size_t)nL * i - 1] + RM[(size_t)nR * (hs_len - i - 1) - 1];
+        if (w > best) { max_index = i; best = w; }
+      }
+    }
+    // genomic start() of the oriented blocks
+    int32_t start_fw[HIPSTR_MAX_BLOCKS], start_rv[HIPSTR_MAX_BLOCKS];
+    const int32_t* bstart = P.block_start + P.locus_block0[pool.locus];
+    const int32_t* bend = P.block_ref_end + P.locus_block0[pool.locus];
+    for (int b = 0; b < nb; b++) { start_fw[b] = bstart[b]; start_rv[nb - 1 - b] = bend[b] - 1; }
+    TAcc acc;
+    acc.stutter = P.out_stutter + (size_t)tr * HIPSTR_MAX_BLOCKS_PER_LOCUS;
+    acc.lo = P.out_span_start + (size_t)tr * HIPSTR_MAX_BLOCKS_PER_LOCUS;
+    acc.hi = P.out_span_len + (size_t)tr * HIPSTR_MAX_BLOCKS_PER_LOCUS;    // holds `hi` until the end
+    acc.indels = P.out_indels + (size_t)tr * HIPSTR_MAX_TRACE_INDELS * 2;
+    acc.snps = P.out_snps + (size_t)tr * HIPSTR_MAX_TRACE_SNPS * 2;
+    acc.n_indels = acc.n_snps = acc.ins = acc.del = 0;
+    for (int b = 0; b < HIPSTR_MAX_BLOCKS_PER_LOCUS; b++) { acc.stutter[b] = HIPSTR_NO_STR_DATA; acc.lo[b] = 1 << 30; acc.hi[b] = -1; }
+    for (int k = 0; k < HIPSTR_MAX_TRACE_INDELS * 2; k++) acc.indels[k] = 0;
+    for (int k = 0; k < HIPSTR_MAX_TRACE_SNPS * 2; k++) acc.snps[k] = 0;
+    char* aln = P.out_aln + (size_t)tr * P.aln_stride;
+    int n_left = 0;
+    // block / offset of a haplotype position
+    int fb = 0, fc = max_index;
+    while (fc >= P.blocks[hsF.blk_off + fb].len) { fc -= P.blocks[hsF.blk_off + fb].len; fb++; }
+    if (max_index == 0) { for (int i = 0; i < seed; i++) aln[n_left++] = 'S'; }
+    else {
+      const long mi = (long)seed * max_index - 1;
+      if (fc == 0) n_left = t_walk_back(P, L, hsF, start_fw, LM, LI, LD, Ls, Lp, fb - 1, P.blocks[hsF.blk_off + fb - 1].len - 1, mi, aln, acc);
+      else n_left = t_walk_back(P, L, hsF, start_fw, LM, LI, LD, Ls, Lp, fb, fc - 1, mi, aln, acc);
+      for (int a = 0, z = n_left - 1; a < z; a++, z--) { const char c = aln[a]; aln[a] = aln[z]; aln[z] = c; }   // left side is walked backwards
+    }
+    if (P.blocks[hsF.blk_off + fb].rep < 0) acc.touch(fb, seed);
+    aln[n_left] = 'M';
+    const int rmax = hs_len - 1 - max_index;
+    int rb = 0, rc = rmax;
+    while (rc >= P.blocks[hsR.blk_off + rb].len) { rc -= P.blocks[hsR.blk_off + rb].len; rb++; }
+    int n_right = 0;
+    char* right = aln + n_left + 1;
+    if (rmax == 0) { for (int i = 0; i < n - 1 - seed; i++) right[n_right++] = 'S'; }
+    else {
+      const long mi = (long)(n - 1 - seed) * rmax - 1;
+      if (rc == 0) n_right = t_walk_back(P, R, hsR, start_rv, RM, RI, RD, Rs, Rp, rb - 1, P.blocks[hsR.blk_off + rb - 1].len - 1, mi, right, acc);
+      else n_right = t_walk_back(P, R, hsR, start_rv, RM, RI, RD, Rs, Rp, rb, rc - 1, mi, right, acc);
+    }
+    right[n_right] = 0;
+    P.out_seed_pos[tr] = max_index;
+    P.out_flank_ins[tr] = acc.ins; P.out_flank_del[tr] = acc.del;
+    P.out_n_indels[tr] = acc.n_indels; P.out_n_snps[tr] = acc.n_snps;
+    for (int b = 0; b < HIPSTR_MAX_BLOCKS_PER_LOCUS; b++) {
+      const bool any = acc.hi[b] >= acc.lo[b];
+      const int lo = acc.lo[b], hi = acc.hi[b];
+      acc.lo[b] = any ? lo : 0;            // span_start
+      acc.hi[b] = any ? hi - lo + 1 : 0;   // span_len
+    }
+  }
+}
+
+cudaError_t launch_trace(const TraceParams& p, int n_slots, cudaStream_t stream) {
+  if (p.n_traces <= 0) return cudaSuccess;
+  k_trace<<<(n_slots + 63) / 64, 64, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace hipstr
