@@ -888,7 +888,7 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   CU(put(m[2], block_start, (size_t)batch->n_blocks, s));
   CU(put(m[3], block_ref_end, s));
   CU(put(m[4], locus_block0, s));
-  const int n_slots = (std::min(n_traces, 8192) + 63) / 64 * 64;
+  const int n_slots = (std::min(n_traces, 32768) + 63) / 64 * 64;   // threads in flight; each owns a ~0.4 MB slab
   TraceParams p;
   std::memset(&p, 0, sizeof(p));
   p.slab_doubles = (int64_t)3 * n_max * l_max;

@@ -1,0 +1,22 @@
+"""Times K5 (traceback) end to end on a synthetic batch: one trace per pooled read against a random haplotype."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import hipstr_b200 as hb
+from test_trace import block_starts
+n_loci = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+s = hb.Synth(n_loci=n_loci, n_samples=100, reads_per_sample=30, n_alleles=8, read_len=150, seed=2000)
+rng = np.random.default_rng(0)
+pools = np.nonzero(s.pool_seed >= 0)[0].astype(np.int32)
+loc = np.searchsorted(s.locus_pool_off, pools, side="right") - 1
+haps = rng.integers(0, 8, len(pools)).astype(np.int32)
+ctx = hb.Context(0)
+bs = block_starts(s.batch)
+ctx.trace(s.batch, bs, pools[:64], haps[:64])
+for rep in range(2):
+    t = time.perf_counter()
+    out = ctx.trace(s.batch, bs, pools, haps)
+    dt = time.perf_counter() - t
+    print("K5: %d traces in %.1f ms -> %.2f M traces/s (host buffers, end to end); stutter!=0 in %d" %
+          (len(pools), dt * 1e3, len(pools) / dt / 1e6, int(((out["stutter_size"][:, 1] != 0)).sum())))
