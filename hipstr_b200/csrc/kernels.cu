@@ -144,20 +144,24 @@ __device__ __forceinline__ double rep_walk(const RepCtx& c, int prog_index, int 
   int4 nx1 = __ldg(reinterpret_cast<const int4*>(prog + 1));
   double nx1_lr = __ldg(lr + 1);
   prog += 2; lr += 2;
+  // deletion walks: the pair of emissions of the NEXT step is loaded while this step's adds run
+  double pa = 0.0, pb = 0.0;
+  if (!INS && cur.w && cur.x > stop) { pa = lds_f64(col + cur.y); pb = lds_f64(col + cur.z); }
   while (cur.x > stop) {
     const int4 nx2 = __ldg(reinterpret_cast<const int4*>(prog++));
     const double nx2_lr = __ldg(lr++);
-    if (cur.w) {
-      unsigned a = col + cur.y, b = col + cur.z;
-      if (INS) {
+    if (INS) {
+      if (cur.w) {
+        unsigned a = col + cur.y, b = col + cur.z;
         for (int m = 0; m < units; m++, a -= stride, b -= stride) {
           lp -= lds_f64(a);
           lp += lds_f64(b);
         }
-      } else {
-        lp -= lds_f64(a);
-        lp += lds_f64(b);
       }
+    } else {
+      const double va = pa, vb = pb;
+      if (nx1.w && nx1.x > stop) { pa = lds_f64(col + nx1.y); pb = lds_f64(col + nx1.z); }
+      if (cur.w) { lp -= va; lp += vb; }
     }
     const double term = lp + cur_lr;
     if (n < HIPSTR_TERM_SLOTS) sts_f64(c.terms + 256 * n, term);
@@ -175,8 +179,15 @@ __device__ __forceinline__ double rep_walk(const RepCtx& c, int prog_index, int 
   }
   double total = has_tail ? lse_term(tail, mx) : 0.0;
   if (n <= HIPSTR_TERM_SLOTS + HIPSTR_TERM_EXTRA) {
-    const int in_smem = min(n, HIPSTR_TERM_SLOTS);
-    for (int s = 0; s < in_smem; s++) total += lse_term(lds_f64(c.terms + 256 * s), mx);
+    // the cached terms are independent: load them all, then evaluate (the sum of the float results
+    // in a double is exact in any order, see the header of this file)
+    double tv[HIPSTR_TERM_SLOTS];
+#pragma unroll
+    for (int s = 0; s < HIPSTR_TERM_SLOTS; s++) tv[s] = s < n ? lds_f64(c.terms + 256 * s) : -1.0e300;
+    double part[2] = {0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < HIPSTR_TERM_SLOTS; s++) part[s & 1] += lse_term(tv[s], mx);
+    total += part[0] + part[1];
     for (int s = HIPSTR_TERM_SLOTS; s < n; s++) total += lse_term(extra[s - HIPSTR_TERM_SLOTS], mx);
     return lse_finish(mx, total);
   }
