@@ -364,11 +364,13 @@ def main():
             pass
         hbm_peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
         k1_avg_ms = k1_ms / max(n_calls, 1)
-        traffic, traffic_src = None, None
+        traffic, traffic_src, fp64 = None, None, None
         try:   # DRAM bytes of K1 from the committed ncu --set full capture, scaled per alignment
             tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
             traffic = tr["dram_bytes_per_alignment"] * n_aln
             traffic_src = tr["capture"]
+            fp64 = {"dadd_per_alignment": tr["fp64_dadd_thread_ops_per_alignment"],
+                    "peak_dadd_per_s": tr["fp64_dadd_peak_thread_ops_per_cycle"] * 1.965e9}
         except (OSError, ValueError, KeyError):
             pass
         achieved = alg_bytes / (k1_avg_ms / 1e3) / 1e9 if k1_avg_ms > 0 else 0.0
@@ -382,7 +384,12 @@ def main():
                          "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch_set": int(alg_bytes), "bytes_per_alignment": alg_bytes / max(n_aln, 1),
                          "k1_ms_per_step": k1_avg_ms, "k1_share_of_step": k1_ms / max(k1_ms + rest_ms, 1e-9),
-                         "note": "K1 keeps the DP on chip: it is FP64-issue / latency bound, not HBM bound (DESIGN.md)"},
+                         "note": "K1 keeps the DP on chip: it is FP64-issue / latency bound, not HBM bound (DESIGN.md)",
+                         "fp64": None if not fp64 else {
+                             "achieved": fp64["dadd_per_alignment"] * (n_aln / (k1_avg_ms / 1e3)) if k1_avg_ms > 0 else 0.0,
+                             "peak": fp64["peak_dadd_per_s"], "unit": "DADD/s",
+                             "frac": fp64["dadd_per_alignment"] * (n_aln / (k1_avg_ms / 1e3)) / fp64["peak_dadd_per_s"] if k1_avg_ms > 0 else 0.0,
+                             "source": "ncu DADD count per alignment (profiles/k1_traffic.json) x live alignments/s; peak = 64 FP64 lanes x 148 SMs x 1965 MHz"}},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks.summary() if clocks else None,
             "synth_seconds": t_gen, "checksum_total_ll": checksum,
         }
