@@ -144,6 +144,21 @@ def extract_genotypes(fn, locus_sample_off, n_haps, n_variants, hap_to_allele, h
     return st, out
 
 
+def stitch_trace(hap_start, hap_aln_to_ref, read_aln_to_hap, seed_hap_pos, seed_base, read_bases):
+    """hipstr_stitch_trace -> (status, start, stop, cigar string like '3S50M2D10M', gapped alignment)."""
+    lib = load()
+    cap = 4096
+    start, stop, n = C.c_int32(), C.c_int32(), C.c_int32()
+    ctype = C.create_string_buffer(cap)
+    clen = np.zeros(cap, np.int32)
+    aln = C.create_string_buffer(cap)
+    st = lib.hipstr_stitch_trace(hap_start, hap_aln_to_ref.encode(), read_aln_to_hap.encode(), seed_hap_pos, seed_base,
+                                 read_bases.encode(), C.byref(start), C.byref(stop), cap, ctype, ptr(clen, c_i32p), C.byref(n),
+                                 cap, aln)
+    cigar = "".join("%d%s" % (clen[i], ctype.raw[i:i + 1].decode()) for i in range(n.value))
+    return st, start.value, stop.value, cigar, aln.value.decode()
+
+
 def em_train(fn, batch, max_iter=100, min_abs=0.01, min_frac=0.001, ctx_handle=None):
     """Calls an em_train entry point (product, oracle or reference harness share the signature after the context)."""
     L = batch.n_loci
@@ -253,6 +268,9 @@ def load():
     lib.hipstr_extract_genotypes_host.argtypes = [vp] + EXTRACT_ARGTYPES
     lib.hipstr_trace_batch_host.restype = C.c_int32
     lib.hipstr_trace_batch_host.argtypes = [vp, B, c_i32p, C.c_int32, c_i32p, c_i32p, C.POINTER(TraceOut)]
+    lib.hipstr_stitch_trace.restype = C.c_int32
+    lib.hipstr_stitch_trace.argtypes = [C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, c_i32p, c_i32p,
+                                        C.c_int32, C.c_char_p, c_i32p, c_i32p, C.c_int32, C.c_char_p]
     lib.hipstr_em_train_host.restype = C.c_int32
     lib.hipstr_em_train_host.argtypes = [vp, C.POINTER(EmBatch), C.c_int32, C.c_double, C.c_double, c_f64p, c_u8p, c_i32p,
                                          c_f64p]

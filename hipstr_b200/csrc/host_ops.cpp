@@ -124,3 +124,98 @@ extern "C" hipstr_status_t hipstr_pool_reads(int32_t n_reads, const int32_t* seq
   *n_pools = (int32_t)members.size();
   return HIPSTR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Trace -> alignment against the reference (AlignmentTraceback.cpp:5-144).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// Composes the two op strings walking away from the seed column in direction `step`
+// (stitch, AlignmentTraceback.cpp:5-53).  Returns false on an inconsistent pair.
+bool compose(const std::string& hap, const std::string& read, long h, long r, int step, std::string& out) {
+  out.clear();
+  while (r >= 0 && r < (long)read.size()) {
+    const char rc = read[r];
+    if (rc == 'S') { out += 'S'; r += step; continue; }
+    if (h < 0 || h >= (long)hap.size()) return false;
+    const char hc = hap[h];
+    if (hc == 'D') {                      // reference base absent from the haplotype
+      if (rc == 'I') { out += 'M'; r += step; h += step; }   // ... but the read re-inserts a base there
+      else { out += 'D'; h += step; }
+    } else if (rc == 'I') { out += 'I'; r += step; }
+    else if (rc == 'D') {
+      if (hc == 'M') out += 'D';
+      else if (hc != 'I') return false;   // haplotype insertion that the read deletes: nothing to emit
+      r += step; h += step;
+    } else if (rc == 'M') {
+      if (hc != 'M' && hc != 'I') return false;
+      out += hc; r += step; h += step;
+    } else
+      return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" hipstr_status_t hipstr_stitch_trace(int32_t hap_start, const char* hap_aln_to_ref, const char* read_aln_to_hap,
+                                               int32_t seed_hap_pos, int32_t seed_base, const char* read_bases,
+                                               int32_t* start, int32_t* stop, int32_t cigar_cap, char* cigar_type,
+                                               int32_t* cigar_len, int32_t* n_cigar, int32_t aln_cap, char* alignment) {
+  if (!hap_aln_to_ref || !read_aln_to_hap || !read_bases || !start || !stop || !cigar_type || !cigar_len || !n_cigar || !alignment)
+    return HIPSTR_ERR_BAD_ARG;
+  const std::string hap(hap_aln_to_ref), read(read_aln_to_hap);
+  // column of the haplotype-vs-reference alignment that holds haplotype base seed_hap_pos, and its coordinate
+  long hcol = 0, remaining = seed_hap_pos;
+  int32_t seed_pos = hap_start;
+  while (remaining > 0 && hcol < (long)hap.size()) {
+    if (hap[hcol] == 'M' || hap[hcol] == 'I') remaining--;
+    if (hap[hcol] == 'M' || hap[hcol] == 'D') seed_pos++;
+    hcol++;
+  }
+  while (hcol < (long)hap.size() && hap[hcol] == 'D') hcol++;
+  if (hcol == (long)hap.size()) return HIPSTR_ERR_BAD_ARG;
+  // column of the read-vs-haplotype string that holds the seed base
+  long rcol = 0;
+  remaining = seed_base;
+  while (remaining > 0 && rcol < (long)read.size()) {
+    if (read[rcol] == 'M' || read[rcol] == 'I' || read[rcol] == 'S') remaining--;
+    rcol++;
+  }
+  while (rcol < (long)read.size() && read[rcol] == 'D') rcol++;
+  if (rcol == (long)read.size()) return HIPSTR_ERR_BAD_ARG;
+  std::string left, right;
+  if (!compose(hap, read, hcol - 1, rcol - 1, -1, left) || !compose(hap, read, hcol + 1, rcol + 1, 1, right)) return HIPSTR_ERR_BAD_ARG;
+  std::reverse(left.begin(), left.end());
+  std::string full = left + "M" + right;
+  for (size_t i = 0; i < full.size() && full[i] == 'I'; i++) full[i] = 'S';   // leading insertion = soft clip
+  int32_t a = seed_pos, b = seed_pos;
+  for (char c : left) if (c == 'D' || c == 'M') a--;
+  for (char c : right) if (c == 'D' || c == 'M') b++;
+  *start = a;
+  *stop = b;
+  int32_t runs = 0;
+  for (size_t i = 0; i < full.size();) {
+    size_t k = i;
+    while (k < full.size() && full[k] == full[i]) k++;
+    if (runs >= cigar_cap) return HIPSTR_ERR_BAD_ARG;
+    cigar_type[runs] = full[i];
+    cigar_len[runs] = (int32_t)(k - i);
+    runs++;
+    i = k;
+  }
+  *n_cigar = runs;
+  const size_t n_bases = std::strlen(read_bases);
+  size_t ri = 0, out = 0;
+  for (char c : full) {
+    if (c == 'S') { ri++; continue; }
+    if (out + 1 >= (size_t)aln_cap) return HIPSTR_ERR_BAD_ARG;
+    if (c == 'D') alignment[out++] = '-';
+    else {
+      if (ri >= n_bases) return HIPSTR_ERR_BAD_ARG;
+      alignment[out++] = read_bases[ri++];
+    }
+  }
+  alignment[out] = 0;
+  return HIPSTR_OK;
+}

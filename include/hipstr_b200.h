@@ -321,6 +321,22 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
                                         const int32_t* trace_pool, const int32_t* trace_hap,
                                         const hipstr_trace_out_t* out);
 
+/* --- a16 (host part): trace -> alignment against the reference genome ---------
+ * Replaces stitch_alignment_trace + stitch (SeqAlignment/AlignmentTraceback.cpp:5-144), the
+ * last step of process_read(retrace_aln = true) (HapAligner.cpp:686-688): the read-vs-haplotype
+ * operation string of K5 (hap_aln, seed_hap_pos) is composed with the haplotype-vs-reference
+ * alignment string of Haplotype::aln_haps_to_ref ('M','I','D' per column, Haplotype.cpp:58-86) into
+ * the read's alignment against the reference: start/stop coordinates, CIGAR ('M','I','D','S'
+ * runs) and the gapped read string ('-' for deleted reference bases, soft-clipped bases dropped).
+ *   hap_start   genomic start of the haplotype's first block (HapBlock::start())
+ *   cigar_cap   capacity of cigar_type / cigar_len; *n_cigar receives the number of runs
+ *   aln_cap     capacity of alignment (NUL-terminated on return)
+ * Pure host string logic; HIPSTR_ERR_BAD_ARG on inconsistent inputs (the reference dies). */
+hipstr_status_t hipstr_stitch_trace(int32_t hap_start, const char* hap_aln_to_ref, const char* read_aln_to_hap,
+                                    int32_t seed_hap_pos, int32_t seed_base, const char* read_bases,
+                                    int32_t* start, int32_t* stop, int32_t cigar_cap, char* cigar_type,
+                                    int32_t* cigar_len, int32_t* n_cigar, int32_t aln_cap, char* alignment);
+
 /* --- a17 / seam B4: EM stutter-model learner (kernel K4) --------------------
  * Replaces EMStutterGenotyper(...) + train(...) + get_stutter_model()
  * (em_stutter_genotyper.h:50-117, em_stutter_genotyper.cpp:10-226) for a batch of

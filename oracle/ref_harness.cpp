@@ -295,6 +295,49 @@ int32_t ref_trace_batch(const hipstr_align_batch_t* bt, const int32_t* block_sta
   return HIPSTR_OK;
 }
 
+// The reference's own stitched alignment of a trace (AlignmentTrace::traced_aln) together with the two inputs
+// stitch_alignment_trace gets: hap_aln_to_ref = Haplotype::get_aln_info() of the traced haplotype (computed by the
+// reference's Needleman-Wunsch in the Haplotype constructor) and the read-vs-haplotype string.
+int32_t ref_trace_stitched(const hipstr_align_batch_t* bt, const int32_t* block_start, int32_t pool, int32_t hap,
+                           char* hap_aln_to_ref, char* read_aln_to_hap, int32_t cap, int32_t* start, int32_t* stop,
+                           char* cigar, char* alignment) {
+  ensure_init();
+  BaseQuality base_quality;
+  int l = 0;
+  while (!(pool >= bt->locus_pool_off[l] && pool < bt->locus_pool_off[l + 1])) l++;
+  const int b0 = bt->locus_block_off[l], nb = bt->locus_block_off[l + 1] - b0;
+  std::vector<int32_t> starts(nb), ends(nb);
+  for (int b = 0; b < nb; b++) {
+    const int o0 = bt->block_opt_off[b0 + b];
+    starts[b] = block_start[b0 + b];
+    ends[b] = starts[b] + (bt->opt_seq_off[o0 + 1] - bt->opt_seq_off[o0]);
+  }
+  RefLocus rl(bt, l, starts.data(), ends.data());
+  rl.hap->go_to(hap);
+  const std::string info = rl.hap->get_aln_info();
+  rl.hap->reset();
+  std::vector<bool> mask(rl.hap->num_combs(), true);
+  HapAligner aligner(rl.hap, mask);
+  const int s0 = bt->pool_seq_off[pool], s1 = bt->pool_seq_off[pool + 1];
+  Alignment aln(0, 0, false, "READPOOL", std::string(bt->pool_quals + s0, bt->pool_quals + s1),
+                std::string(bt->pool_bases + s0, bt->pool_bases + s1), "");
+  AlignmentTrace* trace = aligner.trace_optimal_aln(aln, bt->pool_seed[pool], hap, &base_quality);
+  Alignment& t = trace->traced_aln();
+  std::stringstream cg;
+  for (auto c = t.get_cigar_list().begin(); c != t.get_cigar_list().end(); c++) cg << c->get_num() << c->get_type();
+  const std::string cgs = cg.str();
+  if ((int)info.size() + 1 > cap || (int)trace->hap_aln().size() + 1 > cap || (int)cgs.size() + 1 > cap ||
+      (int)t.get_alignment().size() + 1 > cap) { delete trace; return HIPSTR_ERR_BAD_ARG; }
+  std::strcpy(hap_aln_to_ref, info.c_str());
+  std::strcpy(read_aln_to_hap, trace->hap_aln().c_str());
+  std::strcpy(cigar, cgs.c_str());
+  std::strcpy(alignment, t.get_alignment().c_str());
+  *start = t.get_start();
+  *stop = t.get_stop();
+  delete trace;
+  return HIPSTR_OK;
+}
+
 // Genotyper::extract_genotypes_and_likelihoods for every locus.
 int32_t ref_extract_genotypes(int32_t n_loci, const int32_t* locus_sample_off, const int32_t* n_haps, const int32_t* n_variants,
                               const int32_t* hap_to_allele, const uint8_t* haploid, const double* post, const double* sample_ll,

@@ -111,3 +111,39 @@ def test_gpu_trace_equals_oracle(case):
     assert np.array_equal(g["seed_hap_pos"], o["seed_hap_pos"])
     for k in KEYS:
         assert np.array_equal(g[k], o[k]), k
+
+
+@pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libhipstr_ref.so not built")
+@pytest.mark.parametrize("case", ALL, ids=lambda c: str(c[1]))
+def test_stitch_trace_matches_reference(case):
+    """hipstr_stitch_trace (host) on the oracle's trace reproduces AlignmentTrace::traced_aln() of the reference:
+    start, stop, CIGAR and gapped alignment, given the reference's own haplotype-vs-reference alignment string."""
+    from hipstr_b200.capi import stitch_trace
+    keep, batch, pools, haps, reads = _load(case)
+    bs = block_starts(batch)
+    st, o = trace_batch(_fn(checkers.oracle(), "oracle_trace_batch"), batch, bs, pools, haps)
+    assert st == 0
+    ref = checkers.ref()
+    f = ref.ref_trace_stitched
+    f.restype = C.c_int32
+    f.argtypes = [C.POINTER(AlignBatch), c_i32p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, c_i32p, c_i32p,
+                  C.c_char_p, C.c_char_p]
+    lbo = np.ctypeslib.as_array(batch.locus_block_off, shape=(batch.n_loci + 1,))
+    lpo = np.ctypeslib.as_array(batch.locus_pool_off, shape=(batch.n_loci + 1,))
+    seeds = np.ctypeslib.as_array(batch.pool_seed, shape=(batch.n_pools,))
+    n_checked = 0
+    for i in range(0, len(pools), 3):
+        cap = 4096
+        b1, b2, b3, b4 = (C.create_string_buffer(cap) for _ in range(4))
+        a, b = C.c_int32(), C.c_int32()
+        st = f(C.byref(batch), bs.ctypes.data_as(c_i32p), int(pools[i]), int(haps[i]), b1, b2, cap, C.byref(a), C.byref(b), b3, b4)
+        assert st == 0
+        assert b2.value.decode() == o["hap_aln"][i]
+        locus = int(np.searchsorted(lpo, pools[i], side="right") - 1)
+        hap_start = int(bs[lbo[locus]])
+        st, start, stop, cigar, aln = stitch_trace(hap_start, b1.value.decode(), o["hap_aln"][i], int(o["seed_hap_pos"][i]),
+                                                   int(seeds[pools[i]]), reads[i])
+        assert st == 0
+        assert (start, stop, cigar, aln) == (a.value, b.value, b3.value.decode(), b4.value.decode()), i
+        n_checked += 1
+    assert n_checked >= 10
