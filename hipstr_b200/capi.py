@@ -268,6 +268,14 @@ def load():
     lib.hipstr_extract_genotypes_host.argtypes = [vp] + EXTRACT_ARGTYPES
     lib.hipstr_trace_batch_host.restype = C.c_int32
     lib.hipstr_trace_batch_host.argtypes = [vp, B, c_i32p, C.c_int32, c_i32p, c_i32p, C.POINTER(TraceOut)]
+    lib.hipstr_vcf_writer_open.restype = vp
+    lib.hipstr_vcf_writer_open.argtypes = [C.c_char_p]
+    lib.hipstr_vcf_writer_header.restype = C.c_int32
+    lib.hipstr_vcf_writer_header.argtypes = [vp, C.c_char_p]
+    lib.hipstr_vcf_writer_add_record.restype = C.c_int32
+    lib.hipstr_vcf_writer_add_record.argtypes = [vp, C.c_char_p, C.c_int32, C.c_char_p]
+    lib.hipstr_vcf_writer_close.restype = None
+    lib.hipstr_vcf_writer_close.argtypes = [vp]
     lib.hipstr_stitch_trace.restype = C.c_int32
     lib.hipstr_stitch_trace.argtypes = [C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, c_i32p, c_i32p,
                                         C.c_int32, C.c_char_p, c_i32p, c_i32p, C.c_int32, C.c_char_p]

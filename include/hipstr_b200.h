@@ -366,6 +366,20 @@ hipstr_status_t hipstr_em_train_host(hipstr_ctx_t* ctx, const hipstr_em_batch_t*
                                      double* params_out, uint8_t* converged_out, int32_t* iters_out,
                                      double* ll_out);
 
+/* --- seam B5: ordered VCF output (host) ---------------------------------------
+ * Replaces VCFWriter::open / write_header / add_vcf_record / close (vcf_writer.h:63-82,
+ * vcf_writer.cpp:7-36): records of a chromosome may arrive up to 50 bp out of order and are
+ * held in a min-heap keyed by POS until no later record can precede them; chromosomes must
+ * arrive grouped.  A path ending in ".gz" is written as BGZF (what the reference's
+ * bgzfostream produces), anything else as plain text.  The C++ class with the reference's
+ * method names is hipstr::VCFWriter (hipstr_b200/host/vcf_writer.h). */
+typedef struct hipstr_vcf_writer hipstr_vcf_writer_t;
+hipstr_vcf_writer_t* hipstr_vcf_writer_open(const char* path);   /* NULL if the file cannot be created */
+hipstr_status_t hipstr_vcf_writer_header(hipstr_vcf_writer_t* w, const char* header_text);
+hipstr_status_t hipstr_vcf_writer_add_record(hipstr_vcf_writer_t* w, const char* chrom, int32_t pos,
+                                             const char* record_text);
+void            hipstr_vcf_writer_close(hipstr_vcf_writer_t* w);   /* flushes, writes the BGZF EOF block, frees */
+
 /* Accounting of the last public call on this context: bytes copied host->device and
  * device->host, and kernels launched. */
 void hipstr_last_traffic(const hipstr_ctx_t* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes,
