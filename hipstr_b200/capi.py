@@ -49,6 +49,10 @@ class SynthView(C.Structure):
         ("second_mate", c_u8p), ("read_weight", c_i32p), ("log_p1", c_f64p), ("log_p2", c_f64p),
         ("n_haps", c_i32p), ("haploid", c_u8p), ("true_gt", c_i32p), ("read_bp_diff", c_i32p),
         ("read_ll_size", C.c_int64), ("post_size", C.c_int64),
+        ("read_seq_off", c_i32p), ("read_bases", C.c_void_p), ("read_quals", C.c_void_p), ("read_start", c_i32p),
+        ("read_cigar_off", c_i32p), ("read_cigar_type", C.c_void_p), ("read_cigar_len", c_i32p),
+        ("read_name_id", c_i32p), ("block_start", c_i32p), ("block_end", c_i32p), ("chrom_len", C.c_int32),
+        ("chrom_seqs", C.c_void_p), ("region_start", C.c_int32), ("region_stop", C.c_int32),
     ]
 
 
@@ -59,6 +63,14 @@ class ReadsBatch(C.Structure):
         ("second_mate", c_u8p), ("read_weight", c_i32p), ("log_p1", c_f64p), ("log_p2", c_f64p), ("haploid", c_u8p),
         ("copy_read", c_u8p),
     ]
+
+
+class LocusReadsStruct(C.Structure):
+    """hipstr_locus_reads_t"""
+    _fields_ = [("locus_read_off", c_i32p), ("locus_sample_off", c_i32p), ("read_seq_off", c_i32p), ("bases", C.c_void_p),
+                ("quals", C.c_void_p), ("read_start", c_i32p), ("cigar_off", c_i32p), ("cigar_type", C.c_void_p),
+                ("cigar_len", c_i32p), ("sample_label", c_i32p), ("name_id", c_i32p), ("log_p1", c_f64p), ("log_p2", c_f64p),
+                ("haploid", c_u8p)]
 
 
 class GenotypeOut(C.Structure):
@@ -284,6 +296,26 @@ def load():
                                          c_f64p]
     lib.hipstr_last_traffic.restype = None
     lib.hipstr_last_traffic.argtypes = [vp, c_i64p, c_i64p, c_i32p]
+    lib.hipstr_hap_aln_to_ref.restype = C.c_int32
+    lib.hipstr_hap_aln_to_ref.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p]
+    lib.hipstr_genotyper_create.restype = C.c_int32
+    lib.hipstr_genotyper_create.argtypes = [vp, B, c_i32p, c_i32p, C.POINTER(LocusReadsStruct), C.POINTER(vp)]
+    lib.hipstr_genotyper_destroy.restype = None
+    lib.hipstr_genotyper_destroy.argtypes = [vp]
+    lib.hipstr_genotyper_last_error.restype = C.c_char_p
+    lib.hipstr_genotyper_last_error.argtypes = [vp]
+    lib.hipstr_genotyper_genotype.restype = C.c_int32
+    lib.hipstr_genotyper_genotype.argtypes = [vp, C.c_int32, c_u8p]
+    lib.hipstr_genotyper_stats.restype = C.c_int32
+    lib.hipstr_genotyper_stats.argtypes = [vp, c_i64p, c_i64p, c_i32p]
+    lib.hipstr_genotyper_locus_info.restype = C.c_int32
+    lib.hipstr_genotyper_locus_info.argtypes = [vp, C.c_int32, c_i32p]
+    lib.hipstr_genotyper_locus_blocks.restype = C.c_int32
+    lib.hipstr_genotyper_locus_blocks.argtypes = [vp, C.c_int32, c_i32p, c_i32p, C.c_void_p]
+    lib.hipstr_genotyper_locus_results.restype = C.c_int32
+    lib.hipstr_genotyper_locus_results.argtypes = [vp, C.c_int32, c_f64p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_u8p]
+    lib.hipstr_genotyper_locus_log.restype = C.c_int32
+    lib.hipstr_genotyper_locus_log.argtypes = [vp, C.c_int32, C.c_void_p, C.c_int32]
     lib.hipstr_collect_timing.restype = C.c_int32
     lib.hipstr_collect_timing.argtypes = [vp, c_f64p, c_f64p, c_i32p]
     _lib = lib
@@ -360,6 +392,142 @@ class Synth:
         if self._h:
             load_synth().hipstr_synth_destroy(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def hap_aln_to_ref(ref_hap, alt_hap, first_block_start, repeat_block_start):
+    """hipstr_hap_aln_to_ref -> 'M'/'I'/'D' string (Haplotype::aln_haps_to_ref for one haplotype)."""
+    lib = load()
+    cap = len(ref_hap) + len(alt_hap) + 8
+    buf = C.create_string_buffer(cap)
+    st = lib.hipstr_hap_aln_to_ref(ref_hap.encode(), alt_hap.encode(), first_block_start, repeat_block_start, cap, buf)
+    if st != 0:
+        raise HipstrError(st, "hap_aln_to_ref")
+    return buf.value.decode()
+
+
+def blocks_batch(loci_blocks, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01)):
+    """hipstr_align_batch_t carrying only haplotype blocks: loci_blocks = [[(start, end, period, [seqs])]] per locus.
+    Returns (AlignBatch, block_start, block_end)."""
+    lbo, period, boo, stut, oso, starts, ends = [0], [], [0], [], [0], [], []
+    oseq = bytearray()
+    n_haps = 0
+    for blocks in loci_blocks:
+        H = 1
+        for st, en, per, seqs in blocks:
+            period.append(per)
+            starts.append(st)
+            ends.append(en)
+            stut.extend(stutter)
+            for q in seqs:
+                oseq.extend(q.encode())
+                oso.append(len(oseq))
+            boo.append(len(oso) - 1)
+            H *= len(seqs)
+        lbo.append(len(period))
+        n_haps += H
+    arrs = dict(lbo=np.array(lbo, np.int32), period=np.array(period, np.int32), boo=np.array(boo, np.int32),
+                stut=np.array(stut, np.float64), oso=np.array(oso, np.int32), oseq=bytes(oseq) + b"\0")
+    b = AlignBatch()
+    b.n_loci, b.n_blocks, b.n_options, b.n_pools, b.n_haps = len(loci_blocks), len(period), len(oso) - 1, 0, n_haps
+    b.locus_block_off = ptr(arrs["lbo"], c_i32p)
+    b.block_period = ptr(arrs["period"], c_i32p)
+    b.block_opt_off = ptr(arrs["boo"], c_i32p)
+    b.block_stutter = ptr(arrs["stut"], c_f64p)
+    b.opt_seq_off = ptr(arrs["oso"], c_i32p)
+    b.opt_seq = arrs["oseq"]
+    b._keep = arrs
+    return b, np.array(starts, np.int32), np.array(ends, np.int32)
+
+
+class Genotyper:
+    """hipstr_genotyper_t: a batch of loci run through the SeqStutterGenotyper::genotype() loop on the GPU."""
+
+    def __init__(self, ctx, blocks, block_start, block_end, reads_struct, n_loci):
+        self.lib, self.ctx, self.n_loci = ctx.lib, ctx, n_loci
+        self._keep = (blocks, block_start, block_end, reads_struct)
+        h = C.c_void_p()
+        st = self.lib.hipstr_genotyper_create(ctx.h, C.byref(blocks), ptr(block_start, c_i32p), ptr(block_end, c_i32p),
+                                              C.byref(reads_struct), C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "genotyper_create")
+        self.h = h
+
+    @classmethod
+    def from_synth(cls, ctx, synth, loci_blocks=None):
+        """All loci of a Synth; loci_blocks overrides the generator's own haplotype blocks."""
+        v = synth.view
+        rs = LocusReadsStruct(v.locus_read_off, v.locus_sample_off, v.read_seq_off, v.read_bases, v.read_quals, v.read_start,
+                              v.read_cigar_off, v.read_cigar_type, v.read_cigar_len, v.sample_label, v.read_name_id,
+                              v.log_p1, v.log_p2, v.haploid)
+        if loci_blocks is None:
+            b = synth.batch
+            bs = _np(v.block_start, b.n_blocks, np.int32)
+            be = _np(v.block_end, b.n_blocks, np.int32)
+        else:
+            b, bs, be = blocks_batch(loci_blocks)
+        g = cls(ctx, b, bs, be, rs, synth.n_loci)
+        g._synth = synth
+        return g
+
+    def genotype(self, max_total_haplotypes=1000):
+        ok = np.zeros(self.n_loci, np.uint8)
+        st = self.lib.hipstr_genotyper_genotype(self.h, max_total_haplotypes, ptr(ok, c_u8p))
+        if st != 0:
+            raise HipstrError(st, "genotyper_genotype: " + (self.lib.hipstr_genotyper_last_error(self.h) or b"").decode())
+        return ok
+
+    def stats(self):
+        a, t, r = C.c_int64(), C.c_int64(), C.c_int32()
+        self.lib.hipstr_genotyper_stats(self.h, C.byref(a), C.byref(t), C.byref(r))
+        return dict(alignments=a.value, traces=t.value, rounds=r.value)
+
+    def info(self, l):
+        info = np.zeros(8, np.int32)
+        self.lib.hipstr_genotyper_locus_info(self.h, l, ptr(info, c_i32p))
+        return dict(zip(("blocks", "haps", "reads", "samples", "pools", "options", "seq_bytes", "rounds"), map(int, info)))
+
+    def blocks(self, l):
+        """[[sequences]] per block of locus l."""
+        i = self.info(l)
+        n = np.zeros(i["blocks"], np.int32)
+        off = np.zeros(i["options"] + 1, np.int32)
+        buf = np.zeros(max(i["seq_bytes"], 1), np.uint8)
+        self.lib.hipstr_genotyper_locus_blocks(self.h, l, ptr(n, c_i32p), ptr(off, c_i32p), buf.ctypes.data)
+        raw, out, o = bytes(buf), [], 0
+        for k in n:
+            out.append([raw[off[o + j]:off[o + j + 1]].decode() for j in range(k)])
+            o += int(k)
+        return out
+
+    def results(self, l):
+        i = self.info(l)
+        R, S, H = i["reads"], i["samples"], i["haps"]
+        o = dict(read_ll=np.zeros(R * H), seeds=np.zeros(R, np.int32), pool_index=np.zeros(R, np.int32),
+                 post=np.zeros(S * H * H), sample_ll=np.zeros(S), best=np.zeros(S * 2, np.int32), call_ok=np.zeros(S, np.uint8))
+        self.lib.hipstr_genotyper_locus_results(self.h, l, ptr(o["read_ll"], c_f64p), ptr(o["seeds"], c_i32p),
+                                                ptr(o["pool_index"], c_i32p), ptr(o["post"], c_f64p),
+                                                ptr(o["sample_ll"], c_f64p), ptr(o["best"], c_i32p), ptr(o["call_ok"], c_u8p))
+        o["n_haps"] = H
+        o["read_ll"] = o["read_ll"].reshape(R, H)
+        o["post"] = o["post"].reshape(S, H, H)
+        o["best"] = o["best"].reshape(S, 2)
+        return o
+
+    def log(self, l):
+        buf = np.zeros(1 << 16, np.uint8)
+        n = self.lib.hipstr_genotyper_locus_log(self.h, l, buf.ctypes.data, len(buf))
+        return bytes(buf[:max(n, 0)]).decode()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hipstr_genotyper_destroy(self.h)
+            self.h = None
 
     def __del__(self):
         try:

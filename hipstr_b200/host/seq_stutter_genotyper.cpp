@@ -1,0 +1,931 @@
+/*
+ * seq_stutter_genotyper.cpp -- see seq_stutter_genotyper.h.  Host control loop of seam B1 above the
+ * C-ABI: every alignment, posterior and traceback is a batched device call; this file only holds the
+ * reference's per-locus decisions, restated so that many loci advance together.
+ */
+#include "seq_stutter_genotyper.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <set>
+#include <sstream>
+
+#include "../csrc/flatten.h"
+
+namespace hipstr {
+
+namespace {
+
+bool order_by_length_and_sequence(const std::string& a, const std::string& b) {   // stringops.cpp:35-39
+  if (a.size() != b.size()) return a.size() < b.size();
+  return a.compare(b) < 0;
+}
+
+/* ---- Needleman-Wunsch of a haplotype against the reference haplotype -------------------------- */
+const float kMatch = 2.0f, kMismatch = -2.0f, kGapOpen = 5.0f, kGapExtend = 0.125f, kLarge = 1000000.0f;
+
+inline int base_code(char c) {   // NeedlemanWunsch.cpp:105-123 (anything else scores like N)
+  switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 4;
+  }
+}
+inline float pair_score(int a, int b) { return (a == 4 || b == 4 || a == b) ? kMatch : kMismatch; }
+
+/* The reference's three-way choice (NeedlemanWunsch.cpp:125-147): ties prefer the LATER matrix
+ * between the second and third, the FIRST matrix against either. */
+inline float pick3(float s1, float s2, float s3, int8_t* which) {
+  if (s2 > s1) {
+    if (s2 > s3) { *which = 1; return s2; }
+    *which = 2;
+    return s3;
+  }
+  if (s3 > s1) { *which = 2; return s3; }
+  *which = 0;
+  return s1;
+}
+
+/* Move indels the aligner left in the upstream flank to the right until they touch the repeat block
+ * (Haplotype::adjust_indels, Haplotype.cpp:8-56). */
+void shift_indels_toward_repeat(std::string& ref_row, std::string& alt_row, int32_t flank_start, int32_t repeat_start) {
+  const size_t n = alt_row.size();
+  int32_t ref_pos = flank_start;
+  size_t col = 0;
+  while (col < n) {
+    if (alt_row[col] == '-' && ref_pos < repeat_start) {          // a deletion run
+      size_t run_end = col;
+      while (run_end < n && alt_row[run_end] == '-') run_end++;
+      const int32_t run_len = (int32_t)(run_end - col);
+      int32_t pos = ref_pos;
+      size_t head = col;
+      while (run_end < n && pos < repeat_start && ref_row[head] == ref_row[run_end]) {
+        alt_row[head++] = alt_row[run_end];
+        alt_row[run_end++] = '-';
+        pos++;
+      }
+      col = run_end;
+      ref_pos = pos + run_len;
+    } else if (ref_row[col] == '-' && ref_pos < repeat_start) {   // an insertion run
+      size_t run_end = col;
+      while (run_end < n && ref_row[run_end] == '-') run_end++;
+      int32_t pos = ref_pos;
+      size_t head = col;
+      while (run_end < n && pos < repeat_start && alt_row[head] == alt_row[run_end]) {
+        ref_row[head++] = ref_row[run_end];
+        ref_row[run_end++] = '-';
+        pos++;
+      }
+      col = run_end;
+      ref_pos = pos;
+    } else {
+      if (ref_row[col] != '-') ref_pos++;
+      col++;
+    }
+  }
+}
+
+/* DebruijnGraph::calc_kmer_length (debruijn_graph.cpp:22-29): smallest k in [min_k, max_k] for which
+ * the k-mer path of the sequence has no cycle.  For a single string the graph is a walk, which is
+ * acyclic exactly when no k-mer occurs twice. */
+bool acyclic_kmer_length(const std::string& seq, int min_k, int max_k, int* k_out) {
+  for (int k = min_k; k <= max_k; k++) {
+    std::set<std::string> seen;
+    bool repeat = false;
+    for (size_t i = 0; i + k <= seq.size() && !repeat; i++) repeat = !seen.insert(seq.substr(i, k)).second;
+    if (!repeat) { *k_out = k; return true; }
+  }
+  return false;
+}
+
+}  // namespace
+
+/* ---- HapBlock ---------------------------------------------------------------------------------- */
+bool HapBlock::contains(const std::string& s) const { return std::find(seqs.begin(), seqs.end(), s) != seqs.end(); }
+
+HapBlock HapBlock::remove_alleles(const std::vector<int>& allele_indices) const {
+  HapBlock out;
+  out.start = start; out.end = end; out.period = period;
+  std::memcpy(out.stutter, stutter, sizeof(stutter));
+  for (size_t i = 0; i < seqs.size(); i++)
+    if (i == 0 || std::find(allele_indices.begin(), allele_indices.end(), (int)i) == allele_indices.end()) out.seqs.push_back(seqs[i]);
+  return out;
+}
+
+bool AlignmentTrace::has_stutter() const {
+  for (int32_t s : stutter_size)
+    if (s != HIPSTR_NO_STR_DATA && s != 0) return true;
+  return false;
+}
+int AlignmentTrace::total_stutter_size() const {
+  int total = 0;
+  for (int32_t s : stutter_size)
+    if (s != HIPSTR_NO_STR_DATA) total += s;
+  return total;
+}
+
+std::string hap_aln_to_ref(const std::string& ref_hap, const std::string& alt_hap, int32_t first_block_start,
+                           int32_t repeat_block_start) {
+  const int L1 = (int)ref_hap.size(), L2 = (int)alt_hap.size(), W = L1 + 1;
+  const size_t cells = (size_t)W * (L2 + 1);
+  // M: bases paired; X: reference base against a gap; Y: alternate base against a gap
+  std::vector<float> M(cells), X(cells), Y(cells);
+  std::vector<int8_t> tM(cells, -1), tX(cells, -1), tY(cells, -1);
+  M[0] = 0.0f; X[0] = -kLarge; Y[0] = -kLarge;
+  for (int j = 1; j <= L1; j++) { X[j] = -kGapOpen - (j - 1) * kGapExtend; tX[j] = 1; Y[j] = -kLarge; M[j] = -kLarge; }
+  for (int i = 1; i <= L2; i++) {
+    const size_t c = (size_t)i * W;
+    Y[c] = -kGapOpen - (i - 1) * kGapExtend; tY[c] = 2; X[c] = -kLarge; M[c] = -kLarge;
+  }
+  std::vector<int> rc(L1), ac(L2);
+  for (int j = 0; j < L1; j++) rc[j] = base_code(ref_hap[j]);
+  for (int i = 0; i < L2; i++) ac[i] = base_code(alt_hap[i]);
+  for (int i = 1; i <= L2; i++)
+    for (int j = 1; j <= L1; j++) {
+      const size_t here = (size_t)i * W + j, diag = here - W - 1, left = here - 1, up = here - W;
+      M[here] = pick3(M[diag], X[diag], Y[diag], &tM[here]) + pair_score(rc[j - 1], ac[i - 1]);
+      X[here] = pick3(M[left] - kGapOpen, X[left] - kGapExtend, Y[left] - kGapOpen, &tX[here]);
+      Y[here] = pick3(M[up] - kGapOpen, X[up] - kGapOpen, Y[up] - kGapExtend, &tY[here]);
+    }
+  // end-to-end alignment: stop in the corner (findOptimalStopEndPenalty)
+  const size_t corner = cells - 1;
+  int kind = 0;
+  float best = M[corner];
+  if (X[corner] > best) { best = X[corner]; kind = 1; }
+  if (Y[corner] > best) { best = Y[corner]; kind = 2; }
+  std::string ref_row, alt_row;   // built back to front
+  int row = L2, col = L1;
+  while (row > 0) {
+    const size_t here = (size_t)row * W + col;
+    if (kind == 0 && col > 0) { ref_row += ref_hap[col - 1]; alt_row += alt_hap[row - 1]; kind = tM[here]; row--; col--; }
+    else if (kind == 1 && col > 0) { ref_row += ref_hap[col - 1]; alt_row += '-'; kind = tX[here]; col--; }
+    else if (kind == 2) { ref_row += '-'; alt_row += alt_hap[row - 1]; kind = tY[here]; row--; }
+    else return std::string();   // the reference dies here ("Invalid matrix type")
+  }
+  for (; col > 0; col--) { ref_row += ref_hap[col - 1]; alt_row += '-'; }
+  std::reverse(ref_row.begin(), ref_row.end());
+  std::reverse(alt_row.begin(), alt_row.end());
+  shift_indels_toward_repeat(ref_row, alt_row, first_block_start, repeat_block_start);
+  std::string info(alt_row.size(), 'M');
+  for (size_t i = 0; i < alt_row.size(); i++)
+    if (ref_row[i] == '-') info[i] = 'I';
+    else if (alt_row[i] == '-') info[i] = 'D';
+  return info;
+}
+
+/* ---- one locus ---------------------------------------------------------------------------------- */
+std::string SeqStutterGenotyper::hap_seq(int hap) const {
+  std::vector<int32_t> n(hap_blocks_.size()), opt(hap_blocks_.size());
+  for (size_t b = 0; b < hap_blocks_.size(); b++) n[b] = hap_blocks_[b].num_options();
+  haplotype_options((int)n.size(), n.data(), hap, opt.data());
+  std::string s;
+  for (size_t b = 0; b < hap_blocks_.size(); b++) s += hap_blocks_[b].seqs[opt[b]];
+  return s;
+}
+
+void SeqStutterGenotyper::haps_to_alleles(int block_index, std::vector<int>& allele_indices) const {
+  std::vector<int32_t> n(hap_blocks_.size()), opt(hap_blocks_.size());
+  for (size_t b = 0; b < hap_blocks_.size(); b++) n[b] = hap_blocks_[b].num_options();
+  allele_indices.resize(num_alleles_);
+  for (int h = 0; h < num_alleles_; h++) {
+    haplotype_options((int)n.size(), n.data(), h, opt.data());
+    allele_indices[h] = opt[block_index];
+  }
+}
+
+void SeqStutterGenotyper::rebuild_hap_aln_info(const std::map<std::string, std::string>* known) {
+  hap_aln_info_.assign(num_alleles_, std::string());
+  const std::string ref = hap_seq(0);
+  // Haplotype::adjust_indels only knows flank / repeat / flank haplotypes (Haplotype.cpp:9 asserts 3 blocks)
+  const int32_t first = hap_blocks_.front().start;
+  const int32_t rep = hap_blocks_.size() > 1 ? hap_blocks_[1].start : hap_blocks_.front().end;
+  for (int h = 0; h < num_alleles_; h++) {
+    const std::string seq = hap_seq(h);
+    if (known) {
+      auto it = known->find(seq);
+      if (it != known->end()) { hap_aln_info_[h] = it->second; continue; }
+    }
+    hap_aln_info_[h] = hap_aln_to_ref(ref, seq, first, rep);
+  }
+}
+
+int SeqStutterGenotyper::best_hap_of_read(int r) const {
+  const double log_one_half = host_tables().log_one_half;
+  const int s = sample_label_[r], hap_a = optimal_haps_[2 * s], hap_b = optimal_haps_[2 * s + 1];
+  const double* ll = &log_aln_probs_[(size_t)r * num_alleles_];
+  return (log_one_half + log_p1_[r] + ll[hap_a] > log_one_half + log_p2_[r] + ll[hap_b]) ? hap_a : hap_b;
+}
+
+bool SeqStutterGenotyper::collect_missing_traces() {
+  missing_traces_.clear();
+  std::set<std::pair<int, int> > wanted;
+  for (int r = 0; r < num_reads_; r++) {
+    if (seed_positions_[r] < 0) continue;
+    std::pair<int, int> key(pool_index_[r], best_hap_of_read(r));
+    if (trace_cache_.count(key) == 0 && wanted.insert(key).second) missing_traces_.push_back(key);
+  }
+  return missing_traces_.empty();
+}
+
+void SeqStutterGenotyper::get_stutter_candidate_alleles(int block_index, std::vector<std::string>& candidate_seqs) {
+  const HapBlock& block = hap_blocks_[block_index];
+  std::vector<int> sample_counts(num_samples_, 0);
+  std::vector<std::map<std::string, int> > sample_stutter_counts(num_samples_);
+  for (int r = 0; r < num_reads_; r++) {
+    if (seed_positions_[r] < 0) continue;
+    const AlignmentTrace& trace = trace_cache_.at(std::make_pair(pool_index_[r], best_hap_of_read(r)));
+    if (trace.start < block.start && trace.stop > block.end) {
+      if (trace.stutter_size[block_index] != 0) sample_stutter_counts[sample_label_[r]][trace.str_seq[block_index]]++;
+      sample_counts[sample_label_[r]]++;
+    }
+  }
+  std::set<std::string> candidate_set;   // artifacts seen at least twice and in >= 15 % of a sample's spanning reads
+  for (int s = 0; s < num_samples_; s++)
+    for (const auto& kv : sample_stutter_counts[s])
+      if (kv.second >= 2 && 1.0 * kv.second / sample_counts[s] >= 0.15 && !block.contains(kv.first)) candidate_set.insert(kv.first);
+  candidate_seqs.assign(candidate_set.begin(), candidate_set.end());
+  if (!candidate_seqs.empty()) {
+    std::ostringstream msg;
+    msg << "Identified " << candidate_seqs.size() << " additional candidate alleles from stutter artifacts\n";
+    for (const auto& s : candidate_seqs) msg << "\t" << s << "\n";
+    log_ += msg.str();
+  }
+}
+
+void SeqStutterGenotyper::get_unused_alleles(bool check_spanned, bool check_called,
+                                             std::vector<std::vector<int> >& allele_indices, int& num_aff_blocks,
+                                             int& num_aff_alleles) {
+  allele_indices.clear();
+  num_aff_blocks = num_aff_alleles = 0;
+  std::vector<bool> aligned_read(num_samples_, false);
+  for (int r = 0; r < num_reads_; r++)
+    if (seed_positions_[r] >= 0) aligned_read[sample_label_[r]] = true;
+  const double tolerance = 1e-10;   // mathops.cpp:10
+  for (int b = 0; b < (int)hap_blocks_.size(); b++) {
+    allele_indices.push_back(std::vector<int>());
+    const HapBlock& block = hap_blocks_[b];
+    if (block.num_options() == 1) continue;
+    std::vector<int> hap_to_allele;
+    haps_to_alleles(b, hap_to_allele);
+    std::vector<bool> spanned(block.num_options(), false), called(block.num_options(), false);
+    if (check_spanned) {   // alleles supported by a spanning read whose best alignment carries no stutter
+      for (int r = 0; r < num_reads_; r++) {
+        if (seed_positions_[r] < 0) continue;
+        const AlignmentTrace& trace = trace_cache_.at(std::make_pair(pool_index_[r], best_hap_of_read(r)));
+        if (!(trace.start < block.start && trace.stop > block.end)) continue;
+        if (trace.stutter_size[b] != 0) continue;
+        const int s = sample_label_[r], hap_a = optimal_haps_[2 * s], hap_b = optimal_haps_[2 * s + 1];
+        int best_hap = hap_a;
+        if (!haploid_ && hap_a != hap_b) {
+          const double* ll = &log_aln_probs_[(size_t)r * num_alleles_];
+          const double v1 = log_p1_[r] + ll[hap_a], v2 = log_p2_[r] + ll[hap_b];
+          if (std::fabs(v1 - v2) > tolerance) best_hap = v1 > v2 ? hap_a : hap_b;
+        }
+        spanned[hap_to_allele[best_hap]] = true;
+      }
+    }
+    if (check_called)
+      for (int s = 0; s < num_samples_; s++)
+        if (aligned_read[s] && call_sample_[s].empty()) {
+          called[hap_to_allele[optimal_haps_[2 * s]]] = true;
+          called[hap_to_allele[optimal_haps_[2 * s + 1]]] = true;
+        }
+    bool affected = false;
+    for (int a = 1; a < block.num_options(); a++)
+      if ((check_spanned && !spanned[a]) || (check_called && !called[a])) {
+        allele_indices.back().push_back(a);
+        affected = true;
+        num_aff_alleles++;
+      }
+    if (affected) num_aff_blocks++;
+  }
+}
+
+bool SeqStutterGenotyper::add_and_remove_alleles(const std::vector<std::vector<int> >& alleles_to_remove,
+                                                 const std::vector<std::vector<std::string> >& alleles_to_add) {
+  const int old_H = num_alleles_;
+  // haplotypes are matched across the change by SEQUENCE; of two old haplotypes with one sequence the later wins
+  std::map<std::string, int> old_index;
+  std::map<std::string, std::string> old_info;
+  for (int h = 0; h < old_H; h++) {
+    const std::string seq = hap_seq(h);
+    old_index[seq] = h;
+    old_info[seq] = hap_aln_info_[h];
+  }
+  bool added_seq = false;
+  for (size_t b = 0; b < hap_blocks_.size(); b++) {
+    hap_blocks_[b] = hap_blocks_[b].remove_alleles(alleles_to_remove[b]);
+    for (const std::string& s : alleles_to_add[b]) { hap_blocks_[b].seqs.push_back(s); added_seq = true; }
+  }
+  int new_H = 1;
+  for (const HapBlock& b : hap_blocks_) new_H *= b.num_options();
+  num_alleles_ = new_H;
+  std::vector<int> allele_mapping(old_H, -1);
+  realign_hap_.assign(new_H, 0);
+  for (int h = 0; h < new_H; h++) {
+    auto match = old_index.find(hap_seq(h));
+    if (match == old_index.end()) realign_hap_[h] = 1;
+    else allele_mapping[match->second] = h;
+  }
+  // surviving columns keep their likelihoods; new columns start at -100000 (seq_stutter_genotyper.cpp:374)
+  std::vector<double> fixed((size_t)num_reads_ * new_H, -100000.0);
+  for (int r = 0; r < num_reads_; r++)
+    for (int j = 0; j < old_H; j++)
+      if (allele_mapping[j] != -1) fixed[(size_t)r * new_H + allele_mapping[j]] = log_aln_probs_[(size_t)r * old_H + j];
+  log_aln_probs_.swap(fixed);
+  std::map<std::pair<int, int>, AlignmentTrace> remapped;
+  for (auto& kv : trace_cache_) {
+    const int h = allele_mapping[kv.first.second];
+    if (h != -1) remapped[std::make_pair(kv.first.first, h)] = std::move(kv.second);
+  }
+  trace_cache_.swap(remapped);
+  log_sample_posteriors_.assign((size_t)num_samples_ * new_H * new_H, 0.0);
+  rebuild_hap_aln_info(&old_info);
+  realign_pool_.clear();
+  copy_read_.clear();
+  return added_seq;
+}
+
+SeqStutterGenotyper::Request SeqStutterGenotyper::advance() {
+  for (;;) {
+    switch (phase_) {
+      case ALIGN_ALL:
+        realign_hap_.assign(num_alleles_, 1);
+        realign_pool_.clear();
+        copy_read_.clear();
+        log_aln_probs_.assign((size_t)num_reads_ * num_alleles_, 0.0);
+        log_sample_posteriors_.assign((size_t)num_samples_ * num_alleles_ * num_alleles_, 0.0);
+        log_ += "Aligning reads to each candidate haplotype\n";
+        phase_ = STUTTER_ALLELES;
+        rounds_++;
+        return NEED_ALIGNMENT;
+      case STUTTER_ALLELES: {   // id_and_align_to_stutter_alleles, seq_stutter_genotyper.cpp:570-601
+        if (!collect_missing_traces()) return NEED_TRACES;
+        std::vector<std::vector<int> > none(hap_blocks_.size());
+        std::vector<std::vector<std::string> > stutter_seqs(hap_blocks_.size());
+        int new_total_haps = num_alleles_;
+        bool added = false;
+        for (size_t b = 0; b < hap_blocks_.size(); b++) {
+          if (hap_blocks_[b].period <= 0) continue;
+          get_stutter_candidate_alleles((int)b, stutter_seqs[b]);
+          added |= !stutter_seqs[b].empty();
+          std::sort(stutter_seqs[b].begin(), stutter_seqs[b].end(), order_by_length_and_sequence);
+          new_total_haps /= hap_blocks_[b].num_options();
+          new_total_haps *= hap_blocks_[b].num_options() + (int)stutter_seqs[b].size();
+        }
+        if (!added) { phase_ = PRUNE_UNCALLED; break; }
+        if (new_total_haps > max_total_haplotypes_) {
+          std::ostringstream msg;
+          msg << "Aborting genotyping of the locus as too many candidate haplotypes were found (# Found = " << new_total_haps
+              << ", MAX = " << max_total_haplotypes_ << ")\n";
+          log_ += msg.str();
+          phase_ = FAILED;
+          return NONE;
+        }
+        add_and_remove_alleles(none, stutter_seqs);
+        rounds_++;
+        return NEED_ALIGNMENT;
+      }
+      case PRUNE_UNCALLED: {    // seq_stutter_genotyper.cpp:646-654
+        std::vector<std::vector<int> > unused;
+        int blocks = 0, alleles = 0;
+        get_unused_alleles(false, true, unused, blocks, alleles);
+        phase_ = PRUNE_UNSPANNED;
+        if (alleles == 0) break;
+        std::ostringstream msg;
+        msg << "Recomputing sample posteriors after removing " << alleles << " uncalled alleles across " << blocks << " blocks\n";
+        log_ += msg.str();
+        add_and_remove_alleles(unused, std::vector<std::vector<std::string> >(hap_blocks_.size()));
+        return NEED_POSTERIORS;
+      }
+      case PRUNE_UNSPANNED: {   // seq_stutter_genotyper.cpp:656-664
+        if (!collect_missing_traces()) return NEED_TRACES;
+        std::vector<std::vector<int> > unused;
+        int blocks = 0, alleles = 0;
+        get_unused_alleles(true, false, unused, blocks, alleles);
+        phase_ = DONE;
+        if (alleles == 0) break;
+        std::ostringstream msg;
+        msg << "Recomputing sample posteriors after removing " << alleles << " alleles with no spanning reads across " << blocks
+            << " blocks\n";
+        log_ += msg.str();
+        add_and_remove_alleles(unused, std::vector<std::vector<std::string> >(hap_blocks_.size()));
+        return NEED_POSTERIORS;
+      }
+      case DONE:
+      case FAILED:
+        return NONE;
+    }
+  }
+}
+
+/* ---- batching ------------------------------------------------------------------------------------ */
+namespace {
+
+/* A hipstr_align_batch_t assembled from a list of loci. */
+struct PackedBatch {
+  std::vector<int32_t> locus_block_off{0}, locus_pool_off{0}, block_period, block_opt_off{0}, opt_seq_off{0}, pool_seq_off{0},
+      pool_seed, block_start;
+  std::vector<int64_t> locus_hap_off{0}, locus_out_off{0};
+  std::vector<double> block_stutter;
+  std::string opt_seq, pool_bases, pool_quals;
+  std::vector<uint8_t> realign_pool, realign_hap;
+  bool pool_masked = false, hap_masked = false;
+
+  void add(const SeqStutterGenotyper& g, const std::vector<uint8_t>* hap_mask, const std::vector<uint8_t>* pool_mask) {
+    for (const HapBlock& b : g.hap_blocks_) {
+      block_period.push_back(b.period);
+      block_start.push_back(b.start);
+      block_stutter.insert(block_stutter.end(), b.stutter, b.stutter + 6);
+      for (const std::string& s : b.seqs) { opt_seq += s; opt_seq_off.push_back((int32_t)opt_seq.size()); }
+      block_opt_off.push_back((int32_t)opt_seq_off.size() - 1);
+    }
+    locus_block_off.push_back((int32_t)block_period.size());
+    const int32_t base = (int32_t)pool_bases.size();
+    pool_bases += g.pool_bases_;
+    pool_quals += g.pool_quals_;
+    for (int p = 0; p < g.num_pools_; p++) {
+      pool_seq_off.push_back(base + g.pool_seq_off_[p + 1]);
+      pool_seed.push_back(g.pool_seed_[p]);
+      const uint8_t m = (pool_mask && !pool_mask->empty()) ? (*pool_mask)[p] : 1;
+      realign_pool.push_back(m);
+      pool_masked |= (m == 0);
+    }
+    locus_pool_off.push_back((int32_t)pool_seed.size());
+    for (int h = 0; h < g.num_alleles_; h++) {
+      const uint8_t m = (hap_mask && !hap_mask->empty()) ? (*hap_mask)[h] : 1;
+      realign_hap.push_back(m);
+      hap_masked |= (m == 0);
+    }
+    locus_hap_off.push_back(locus_hap_off.back() + g.num_alleles_);
+    locus_out_off.push_back(locus_out_off.back() + (int64_t)g.num_pools_ * g.num_alleles_);
+  }
+
+  hipstr_align_batch_t view() const {
+    hipstr_align_batch_t b;
+    std::memset(&b, 0, sizeof(b));
+    b.n_loci = (int32_t)locus_block_off.size() - 1;
+    b.n_blocks = (int32_t)block_period.size();
+    b.n_options = (int32_t)opt_seq_off.size() - 1;
+    b.n_pools = (int32_t)pool_seed.size();
+    b.n_haps = locus_hap_off.back();
+    b.locus_block_off = locus_block_off.data();
+    b.locus_pool_off = locus_pool_off.data();
+    b.locus_hap_off = locus_hap_off.data();
+    b.locus_out_off = locus_out_off.data();
+    b.block_period = block_period.data();
+    b.block_opt_off = block_opt_off.data();
+    b.block_stutter = block_stutter.data();
+    b.opt_seq_off = opt_seq_off.data();
+    b.opt_seq = opt_seq.data();
+    b.pool_seq_off = pool_seq_off.data();
+    b.pool_bases = pool_bases.data();
+    b.pool_quals = pool_quals.data();
+    b.pool_seed = pool_seed.data();
+    b.realign_pool = pool_masked ? realign_pool.data() : nullptr;
+    b.realign_hap = hap_masked ? realign_hap.data() : nullptr;
+    return b;
+  }
+};
+
+/* The read-level arrays (hipstr_reads_batch_t) of a list of loci plus the in/out result buffers. */
+struct PackedReads {
+  std::vector<int32_t> locus_read_off{0}, locus_sample_off{0}, pool_index, sample_label, read_weight, n_haps;
+  std::vector<uint8_t> second_mate, haploid, copy_read;
+  std::vector<double> log_p1, log_p2;
+  bool copy_masked = false;
+  std::vector<double> read_ll, post, sample_ll, total_ll;
+  std::vector<int32_t> read_seed, best;
+
+  void add(const SeqStutterGenotyper& g) {
+    pool_index.insert(pool_index.end(), g.pool_index_.begin(), g.pool_index_.end());
+    sample_label.insert(sample_label.end(), g.sample_label_.begin(), g.sample_label_.end());
+    read_weight.insert(read_weight.end(), g.read_weights_.begin(), g.read_weights_.end());
+    second_mate.insert(second_mate.end(), g.second_mate_.begin(), g.second_mate_.end());
+    log_p1.insert(log_p1.end(), g.log_p1_.begin(), g.log_p1_.end());
+    log_p2.insert(log_p2.end(), g.log_p2_.begin(), g.log_p2_.end());
+    haploid.push_back(g.haploid_ ? 1 : 0);
+    n_haps.push_back(g.num_alleles_);
+    locus_read_off.push_back((int32_t)pool_index.size());
+    locus_sample_off.push_back(locus_sample_off.back() + g.num_samples_);
+    read_ll.insert(read_ll.end(), g.log_aln_probs_.begin(), g.log_aln_probs_.end());
+    read_seed.insert(read_seed.end(), g.seed_positions_.begin(), g.seed_positions_.end());
+  }
+  void size_outputs(const std::vector<SeqStutterGenotyper*>& gs) {
+    size_t post_size = 0;
+    for (auto g : gs) post_size += (size_t)g->num_samples_ * g->num_alleles_ * g->num_alleles_;
+    post.assign(post_size, 0.0);
+    sample_ll.assign(locus_sample_off.back(), 0.0);
+    best.assign((size_t)locus_sample_off.back() * 2, 0);
+    total_ll.assign(gs.size(), 0.0);
+  }
+  void scatter_back(const std::vector<SeqStutterGenotyper*>& gs, bool with_ll) {
+    size_t ll_at = 0, post_at = 0;
+    for (size_t k = 0; k < gs.size(); k++) {
+      SeqStutterGenotyper& g = *gs[k];
+      const size_t nll = (size_t)g.num_reads_ * g.num_alleles_, npost = (size_t)g.num_samples_ * g.num_alleles_ * g.num_alleles_;
+      if (with_ll) {
+        std::copy(read_ll.begin() + ll_at, read_ll.begin() + ll_at + nll, g.log_aln_probs_.begin());
+        std::copy(read_seed.begin() + locus_read_off[k], read_seed.begin() + locus_read_off[k + 1], g.seed_positions_.begin());
+      }
+      g.log_sample_posteriors_.assign(post.begin() + post_at, post.begin() + post_at + npost);
+      g.sample_total_LLs_.assign(sample_ll.begin() + locus_sample_off[k], sample_ll.begin() + locus_sample_off[k + 1]);
+      g.optimal_haps_.assign(best.begin() + 2 * (size_t)locus_sample_off[k], best.begin() + 2 * (size_t)locus_sample_off[k + 1]);
+      ll_at += nll;
+      post_at += npost;
+    }
+  }
+};
+
+}  // namespace
+
+hipstr_status_t GenotyperBatch::add_loci(const hipstr_align_batch_t* bt, const int32_t* block_start, const int32_t* block_end,
+                                         const hipstr_locus_reads_t* rd, std::string& err) {
+  if (!bt || !block_start || !block_end || !rd) { err = "null argument"; return HIPSTR_ERR_BAD_ARG; }
+  for (int l = 0; l < bt->n_loci; l++) {
+    loci.emplace_back();
+    SeqStutterGenotyper& g = loci.back();
+    const int b0 = bt->locus_block_off[l], b1 = bt->locus_block_off[l + 1];
+    if (b1 - b0 < 1 || b1 - b0 > HIPSTR_MAX_BLOCKS_PER_LOCUS) { err = "unsupported number of haplotype blocks"; return HIPSTR_ERR_BAD_ARG; }
+    g.num_alleles_ = 1;
+    for (int b = b0; b < b1; b++) {
+      HapBlock blk;
+      blk.start = block_start[b]; blk.end = block_end[b]; blk.period = bt->block_period[b];
+      std::memcpy(blk.stutter, bt->block_stutter + 6 * (size_t)b, sizeof(blk.stutter));
+      for (int o = bt->block_opt_off[b]; o < bt->block_opt_off[b + 1]; o++)
+        blk.seqs.emplace_back(bt->opt_seq + bt->opt_seq_off[o], bt->opt_seq + bt->opt_seq_off[o + 1]);
+      if (blk.seqs.empty()) { err = "haplotype block without a reference allele"; return HIPSTR_ERR_BAD_ARG; }
+      g.num_alleles_ *= blk.num_options();
+      g.hap_blocks_.push_back(blk);
+    }
+    const int r0 = rd->locus_read_off[l], r1 = rd->locus_read_off[l + 1], R = r1 - r0;
+    g.haploid_ = rd->haploid && rd->haploid[l];
+    g.num_samples_ = rd->locus_sample_off[l + 1] - rd->locus_sample_off[l];
+    g.num_reads_ = R;
+    g.call_sample_.assign(g.num_samples_, std::string());
+    g.sample_label_.assign(rd->sample_label + r0, rd->sample_label + r1);
+    g.log_p1_.assign(rd->log_p1 + r0, rd->log_p1 + r1);
+    g.log_p2_.assign(rd->log_p2 + r0, rd->log_p2 + r1);
+    g.read_start_.assign(rd->read_start + r0, rd->read_start + r1);
+    // init(): a read is a second mate when it carries the name of the read before it (.cpp:495-503)
+    g.second_mate_.resize(R);
+    g.read_weights_.resize(R);
+    for (int r = 0; r < R; r++) {
+      g.second_mate_[r] = (r > 0 && rd->name_id[r0 + r] == rd->name_id[r0 + r - 1]) ? 1 : 0;
+      g.read_weights_[r] = g.second_mate_[r] ? 0 : 1;
+    }
+    g.read_cigar_off_.resize(R + 1);
+    for (int r = 0; r <= R; r++) g.read_cigar_off_[r] = rd->cigar_off[r0 + r] - rd->cigar_off[r0];
+    g.read_cigar_type_.assign(rd->cigar_type + rd->cigar_off[r0], rd->cigar_type + rd->cigar_off[r1]);
+    g.read_cigar_len_.assign(rd->cigar_len + rd->cigar_off[r0], rd->cigar_len + rd->cigar_off[r1]);
+    // ReadPooler: identical sequences share a pool, upper-median qualities
+    std::vector<int32_t> seq_off(R + 1);
+    for (int r = 0; r <= R; r++) seq_off[r] = rd->read_seq_off[r0 + r] - rd->read_seq_off[r0];
+    const char* bases = rd->bases + rd->read_seq_off[r0];
+    const char* quals = rd->quals + rd->read_seq_off[r0];
+    g.pool_index_.resize(R);
+    std::vector<int32_t> first(std::max(R, 1));
+    g.pool_seq_off_.resize(R + 1);
+    g.pool_bases_.resize(seq_off[R]);
+    g.pool_quals_.resize(seq_off[R]);
+    int32_t P = 0;
+    hipstr_status_t st = hipstr_pool_reads(R, seq_off.data(), bases, quals, g.pool_index_.data(), &P, first.data(),
+                                           g.pool_seq_off_.data(), &g.pool_bases_[0], &g.pool_quals_[0]);
+    if (st != HIPSTR_OK) { err = "hipstr_pool_reads failed"; return st; }
+    g.num_pools_ = P;
+    g.pool_seq_off_.resize(P + 1);
+    g.pool_bases_.resize(g.pool_seq_off_[P]);
+    g.pool_quals_.resize(g.pool_seq_off_[P]);
+    // seeds from the pool's first member alignment (HapAligner::calc_seed_base)
+    std::vector<int32_t> starts(P), lens(P), coff(P + 1, 0), clen, rs, re;
+    std::vector<char> ctype;
+    for (int p = 0; p < P; p++) {
+      const int r = first[p];
+      starts[p] = g.read_start_[r];
+      lens[p] = seq_off[r + 1] - seq_off[r];
+      ctype.insert(ctype.end(), g.read_cigar_type_.begin() + g.read_cigar_off_[r], g.read_cigar_type_.begin() + g.read_cigar_off_[r + 1]);
+      clen.insert(clen.end(), g.read_cigar_len_.begin() + g.read_cigar_off_[r], g.read_cigar_len_.begin() + g.read_cigar_off_[r + 1]);
+      coff[p + 1] = (int32_t)ctype.size();
+    }
+    for (const HapBlock& b : g.hap_blocks_)
+      if (b.period > 0) { rs.push_back(b.start); re.push_back(b.end); }
+    g.pool_seed_.assign(P, -1);
+    st = hipstr_calc_seeds(P, starts.data(), lens.data(), coff.data(), ctype.data(), clen.data(), g.hap_blocks_.front().start,
+                           g.hap_blocks_.back().end, (int32_t)rs.size(), rs.data(), re.data(), g.pool_seed_.data());
+    if (st != HIPSTR_OK) { err = "hipstr_calc_seeds failed (the reference dies on a seed at a read end)"; return st; }
+    g.seed_positions_.assign(R, -1);
+    g.sample_total_LLs_.assign(g.num_samples_, 0.0);
+    g.optimal_haps_.assign((size_t)g.num_samples_ * 2, 0);
+    g.rebuild_hap_aln_info(nullptr);
+  }
+  return HIPSTR_OK;
+}
+
+hipstr_status_t GenotyperBatch::run_alignments(const std::vector<int>& which, std::string& err) {
+  if (which.empty()) return HIPSTR_OK;
+  PackedBatch pb;
+  PackedReads pr;
+  std::vector<SeqStutterGenotyper*> gs;
+  for (int l : which) {
+    SeqStutterGenotyper& g = loci[l];
+    pb.add(g, &g.realign_hap_, &g.realign_pool_);
+    pr.add(g);
+    if (!g.copy_read_.empty()) pr.copy_masked = true;
+    gs.push_back(&g);
+  }
+  if (pr.copy_masked)
+    for (auto g : gs) {
+      if (g->copy_read_.empty()) pr.copy_read.insert(pr.copy_read.end(), g->num_reads_, 1);
+      else pr.copy_read.insert(pr.copy_read.end(), g->copy_read_.begin(), g->copy_read_.end());
+    }
+  pr.size_outputs(gs);
+  hipstr_align_batch_t bt = pb.view();
+  hipstr_reads_batch_t rb;
+  rb.locus_read_off = pr.locus_read_off.data();
+  rb.locus_sample_off = pr.locus_sample_off.data();
+  rb.pool_index = pr.pool_index.data();
+  rb.sample_label = pr.sample_label.data();
+  rb.second_mate = pr.second_mate.data();
+  rb.read_weight = pr.read_weight.data();
+  rb.log_p1 = pr.log_p1.data();
+  rb.log_p2 = pr.log_p2.data();
+  rb.haploid = pr.haploid.data();
+  rb.copy_read = pr.copy_masked ? pr.copy_read.data() : nullptr;
+  hipstr_genotype_out_t out;
+  out.read_ll = pr.read_ll.data();
+  out.read_seed = pr.read_seed.data();
+  out.post = pr.post.data();
+  out.sample_ll = pr.sample_ll.data();
+  out.best = pr.best.data();
+  out.total_ll = pr.total_ll.data();
+  hipstr_status_t st = hipstr_genotype_batch_host(ctx_, &bt, &rb, &out);
+  if (st != HIPSTR_OK) { err = std::string("hipstr_genotype_batch_host: ") + hipstr_last_error(ctx_); return st; }
+  n_alignments += hipstr_batch_num_alignments(&bt);
+  pr.scatter_back(gs, true);
+  return HIPSTR_OK;
+}
+
+hipstr_status_t GenotyperBatch::run_posteriors(const std::vector<int>& which, std::string& err) {
+  if (which.empty()) return HIPSTR_OK;
+  PackedReads pr;
+  std::vector<SeqStutterGenotyper*> gs;
+  for (int l : which) { pr.add(loci[l]); gs.push_back(&loci[l]); }
+  pr.size_outputs(gs);
+  hipstr_status_t st = hipstr_posteriors_host(ctx_, (int32_t)gs.size(), pr.locus_read_off.data(), pr.locus_sample_off.data(),
+                                              pr.n_haps.data(), pr.haploid.data(), pr.read_ll.data(), pr.log_p1.data(),
+                                              pr.log_p2.data(), pr.sample_label.data(), pr.read_weight.data(), pr.post.data(),
+                                              pr.sample_ll.data(), pr.best.data(), pr.total_ll.data());
+  if (st != HIPSTR_OK) { err = std::string("hipstr_posteriors_host: ") + hipstr_last_error(ctx_); return st; }
+  pr.scatter_back(gs, false);
+  return HIPSTR_OK;
+}
+
+hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::string& err) {
+  const size_t kChunk = 1 << 17;   // traces per device call (bounds the host result buffers)
+  size_t li = 0, ti = 0;           // next locus of `which`, next missing trace of that locus
+  while (li < which.size()) {
+    PackedBatch pb;
+    std::vector<int32_t> trace_pool, trace_hap;
+    std::vector<std::pair<int, int> > owner;   // (locus, index into missing_traces_)
+    int32_t max_read = 0, max_hap = 0;
+    while (li < which.size() && trace_pool.size() < kChunk) {
+      SeqStutterGenotyper& g = loci[which[li]];
+      if (ti >= g.missing_traces_.size()) { li++; ti = 0; continue; }
+      const int32_t pool_base = (int32_t)pb.pool_seed.size();
+      pb.add(g, nullptr, nullptr);
+      for (int p = 0; p < g.num_pools_; p++) max_read = std::max(max_read, g.pool_seq_off_[p + 1] - g.pool_seq_off_[p]);
+      int32_t longest = 0;
+      for (const HapBlock& b : g.hap_blocks_) {
+        size_t m = 0;
+        for (const auto& s : b.seqs) m = std::max(m, s.size());
+        longest += (int32_t)m;
+      }
+      max_hap = std::max(max_hap, longest);
+      for (; ti < g.missing_traces_.size() && trace_pool.size() < kChunk; ti++) {
+        trace_pool.push_back(pool_base + g.missing_traces_[ti].first);
+        trace_hap.push_back(g.missing_traces_[ti].second);
+        owner.emplace_back(which[li], (int)ti);
+      }
+      if (ti >= g.missing_traces_.size()) { li++; ti = 0; }
+    }
+    const size_t n = trace_pool.size();
+    if (n == 0) break;
+    const int32_t stride = ((max_read + max_hap + 2 + 15) / 16) * 16;
+    std::vector<char> hap_aln(n * (size_t)stride);
+    std::vector<int32_t> seed_hap_pos(n), stutter(n * 8), span_start(n * 8), span_len(n * 8), flank_ins(n), flank_del(n), n_indels(n),
+        indels(n * HIPSTR_MAX_TRACE_INDELS * 2), n_snps(n), snps(n * HIPSTR_MAX_TRACE_SNPS * 2);
+    hipstr_trace_out_t out;
+    out.aln_stride = stride;
+    out.hap_aln = hap_aln.data();
+    out.seed_hap_pos = seed_hap_pos.data();
+    out.stutter_size = stutter.data();
+    out.span_start = span_start.data();
+    out.span_len = span_len.data();
+    out.flank_ins = flank_ins.data();
+    out.flank_del = flank_del.data();
+    out.n_indels = n_indels.data();
+    out.indels = indels.data();
+    out.n_snps = n_snps.data();
+    out.snps = snps.data();
+    hipstr_align_batch_t bt = pb.view();
+    hipstr_status_t st = hipstr_trace_batch_host(ctx_, &bt, pb.block_start.data(), (int32_t)n, trace_pool.data(), trace_hap.data(), &out);
+    if (st != HIPSTR_OK) { err = std::string("hipstr_trace_batch_host: ") + hipstr_last_error(ctx_); return st; }
+    n_traces += (int64_t)n;
+    std::vector<char> ctype(stride + 8), aln(2 * (size_t)stride + 8);
+    std::vector<int32_t> clen(stride + 8);
+    for (size_t i = 0; i < n; i++) {
+      SeqStutterGenotyper& g = loci[owner[i].first];
+      const std::pair<int, int> key = g.missing_traces_[owner[i].second];
+      const int nb = (int)g.hap_blocks_.size();
+      const std::string read = g.pool_read(key.first);
+      AlignmentTrace t;
+      t.hap_aln = std::string(&hap_aln[i * (size_t)stride]);
+      t.flank_ins_size = flank_ins[i];
+      t.flank_del_size = flank_del[i];
+      t.stutter_size.assign(stutter.begin() + i * 8, stutter.begin() + i * 8 + nb);
+      t.str_seq.assign(nb, std::string());
+      t.flank_seq.assign(nb, std::string());
+      for (int b = 0; b < nb; b++) {
+        const std::string span = span_len[i * 8 + b] > 0 ? read.substr(span_start[i * 8 + b], span_len[i * 8 + b]) : std::string();
+        (g.hap_blocks_[b].period > 0 ? t.str_seq : t.flank_seq)[b] = span;
+      }
+      for (int k = 0; k < n_indels[i]; k++)
+        t.flank_indel_data.emplace_back(indels[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2], indels[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2 + 1]);
+      for (int k = 0; k < n_snps[i]; k++)
+        t.flank_snp_data.emplace_back(snps[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2], (char)snps[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2 + 1]);
+      int32_t n_cigar = 0;
+      st = hipstr_stitch_trace(g.hap_blocks_.front().start, g.hap_aln_info_[key.second].c_str(), t.hap_aln.c_str(), seed_hap_pos[i],
+                               g.pool_seed_[key.first], read.c_str(), &t.start, &t.stop, (int32_t)ctype.size(), ctype.data(),
+                               clen.data(), &n_cigar, (int32_t)aln.size(), aln.data());
+      if (st != HIPSTR_OK) { err = "hipstr_stitch_trace failed"; return st; }
+      std::ostringstream cig;
+      for (int k = 0; k < n_cigar; k++) cig << clen[k] << ctype[k];
+      t.cigar = cig.str();
+      t.alignment = std::string(aln.data());
+      g.trace_cache_[key] = std::move(t);
+    }
+  }
+  for (int l : which) loci[l].missing_traces_.clear();
+  return HIPSTR_OK;
+}
+
+hipstr_status_t GenotyperBatch::genotype(int max_total_haplotypes, std::string& err) {
+  const int kMinKmer = 10, kMaxKmer = 15;   // seq_stutter_genotyper.h:153-154
+  for (SeqStutterGenotyper& g : loci) {
+    if (g.phase_ != SeqStutterGenotyper::ALIGN_ALL) continue;
+    g.max_total_haplotypes_ = max_total_haplotypes;
+    if (g.num_alleles_ > max_total_haplotypes) {
+      std::ostringstream msg;
+      msg << "Aborting genotyping of the locus as too many candidate haplotypes were found (# Found = " << g.num_alleles_
+          << ", MAX = " << max_total_haplotypes << ")\n";
+      g.log_ += msg.str();
+      g.phase_ = SeqStutterGenotyper::FAILED;
+      continue;
+    }
+    // flanks too repetitive to assemble -> skip the locus (seq_stutter_genotyper.cpp:616-630)
+    for (int flank = 0; flank < 2 && g.phase_ != SeqStutterGenotyper::FAILED; flank++) {
+      const std::string& ref_seq = (flank == 0 ? g.hap_blocks_.front() : g.hap_blocks_.back()).seqs[0];
+      const int max_k = std::min(kMaxKmer, ref_seq.empty() ? -1 : (int)ref_seq.size() - 1);
+      int k = 0;
+      if (!acyclic_kmer_length(ref_seq, kMinKmer, max_k, &k)) {
+        g.log_ += std::string("Aborting genotyping of the locus as the sequence ") + (flank == 0 ? "upstream" : "downstream") +
+                  " of the repeat is too repetitive for accurate genotyping\n";
+        g.phase_ = SeqStutterGenotyper::FAILED;
+      }
+    }
+  }
+  for (;;) {
+    std::vector<int> need_traces, need_alignment, need_posteriors;
+    for (size_t l = 0; l < loci.size(); l++) {
+      switch (loci[l].advance()) {
+        case SeqStutterGenotyper::NEED_TRACES: need_traces.push_back((int)l); break;
+        case SeqStutterGenotyper::NEED_ALIGNMENT: need_alignment.push_back((int)l); break;
+        case SeqStutterGenotyper::NEED_POSTERIORS: need_posteriors.push_back((int)l); break;
+        case SeqStutterGenotyper::NONE: break;
+      }
+    }
+    if (need_traces.empty() && need_alignment.empty() && need_posteriors.empty()) break;
+    n_rounds++;
+    hipstr_status_t st = run_traces(need_traces, err);
+    if (st == HIPSTR_OK) st = run_alignments(need_alignment, err);
+    if (st == HIPSTR_OK) st = run_posteriors(need_posteriors, err);
+    if (st != HIPSTR_OK) return st;
+  }
+  return HIPSTR_OK;
+}
+
+}  // namespace hipstr
+
+/* ---- C-ABI ------------------------------------------------------------------------------------------ */
+struct hipstr_genotyper {
+  hipstr::GenotyperBatch batch;
+  std::string last_error;
+  explicit hipstr_genotyper(hipstr_ctx_t* ctx) : batch(ctx) {}
+};
+
+extern "C" {
+
+hipstr_status_t hipstr_hap_aln_to_ref(const char* ref_hap, const char* alt_hap, int32_t first_block_start,
+                                      int32_t repeat_block_start, int32_t cap, char* out) {
+  if (!ref_hap || !alt_hap || !out) return HIPSTR_ERR_BAD_ARG;
+  const std::string info = hipstr::hap_aln_to_ref(ref_hap, alt_hap, first_block_start, repeat_block_start);
+  if (info.empty() || (int32_t)info.size() + 1 > cap) return HIPSTR_ERR_BAD_ARG;
+  std::memcpy(out, info.c_str(), info.size() + 1);
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_genotyper_create(hipstr_ctx_t* ctx, const hipstr_align_batch_t* blocks, const int32_t* block_start,
+                                        const int32_t* block_end, const hipstr_locus_reads_t* reads, hipstr_genotyper_t** out) {
+  if (!ctx || !out) return HIPSTR_ERR_BAD_ARG;   // no context = no device = nothing to run on
+  hipstr_genotyper* g = new hipstr_genotyper(ctx);
+  hipstr_status_t st = g->batch.add_loci(blocks, block_start, block_end, reads, g->last_error);
+  if (st != HIPSTR_OK) { delete g; return st; }
+  *out = g;
+  return HIPSTR_OK;
+}
+
+void hipstr_genotyper_destroy(hipstr_genotyper_t* g) { delete g; }
+const char* hipstr_genotyper_last_error(const hipstr_genotyper_t* g) { return g ? g->last_error.c_str() : "null genotyper"; }
+
+hipstr_status_t hipstr_genotyper_genotype(hipstr_genotyper_t* g, int32_t max_total_haplotypes, uint8_t* locus_ok) {
+  if (!g) return HIPSTR_ERR_BAD_ARG;
+  hipstr_status_t st = g->batch.genotype(max_total_haplotypes, g->last_error);
+  if (st != HIPSTR_OK) return st;
+  if (locus_ok)
+    for (size_t l = 0; l < g->batch.loci.size(); l++) locus_ok[l] = g->batch.loci[l].succeeded() ? 1 : 0;
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_genotyper_stats(const hipstr_genotyper_t* g, int64_t* n_alignments, int64_t* n_traces, int32_t* n_rounds) {
+  if (!g) return HIPSTR_ERR_BAD_ARG;
+  if (n_alignments) *n_alignments = g->batch.n_alignments;
+  if (n_traces) *n_traces = g->batch.n_traces;
+  if (n_rounds) *n_rounds = g->batch.n_rounds;
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_genotyper_locus_info(const hipstr_genotyper_t* g, int32_t locus, int32_t* info) {
+  if (!g || !info || locus < 0 || locus >= (int32_t)g->batch.loci.size()) return HIPSTR_ERR_BAD_ARG;
+  const hipstr::SeqStutterGenotyper& s = g->batch.loci[locus];
+  int32_t n_opts = 0, seq_bytes = 0;
+  for (const auto& b : s.hap_blocks_) {
+    n_opts += b.num_options();
+    for (const auto& q : b.seqs) seq_bytes += (int32_t)q.size();
+  }
+  info[0] = (int32_t)s.hap_blocks_.size();
+  info[1] = s.num_alleles_;
+  info[2] = s.num_reads_;
+  info[3] = s.num_samples_;
+  info[4] = s.num_pools_;
+  info[5] = n_opts;
+  info[6] = seq_bytes;
+  info[7] = s.rounds_;
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_genotyper_locus_blocks(const hipstr_genotyper_t* g, int32_t locus, int32_t* block_n_opts,
+                                              int32_t* opt_seq_off, char* opt_seq) {
+  if (!g || !block_n_opts || !opt_seq_off || !opt_seq || locus < 0 || locus >= (int32_t)g->batch.loci.size()) return HIPSTR_ERR_BAD_ARG;
+  const hipstr::SeqStutterGenotyper& s = g->batch.loci[locus];
+  int32_t o = 0, at = 0;
+  opt_seq_off[0] = 0;
+  for (size_t b = 0; b < s.hap_blocks_.size(); b++) {
+    block_n_opts[b] = s.hap_blocks_[b].num_options();
+    for (const auto& q : s.hap_blocks_[b].seqs) {
+      std::memcpy(opt_seq + at, q.data(), q.size());
+      at += (int32_t)q.size();
+      opt_seq_off[++o] = at;
+    }
+  }
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_genotyper_locus_results(const hipstr_genotyper_t* g, int32_t locus, double* read_ll, int32_t* read_seed,
+                                               int32_t* pool_index, double* post, double* sample_ll, int32_t* best,
+                                               uint8_t* call_sample_ok) {
+  if (!g || locus < 0 || locus >= (int32_t)g->batch.loci.size()) return HIPSTR_ERR_BAD_ARG;
+  const hipstr::SeqStutterGenotyper& s = g->batch.loci[locus];
+  if (read_ll) std::copy(s.log_aln_probs_.begin(), s.log_aln_probs_.end(), read_ll);
+  if (read_seed) std::copy(s.seed_positions_.begin(), s.seed_positions_.end(), read_seed);
+  if (pool_index) std::copy(s.pool_index_.begin(), s.pool_index_.end(), pool_index);
+  if (post) std::copy(s.log_sample_posteriors_.begin(), s.log_sample_posteriors_.end(), post);
+  if (sample_ll) std::copy(s.sample_total_LLs_.begin(), s.sample_total_LLs_.end(), sample_ll);
+  if (best) std::copy(s.optimal_haps_.begin(), s.optimal_haps_.end(), best);
+  if (call_sample_ok)
+    for (int i = 0; i < s.num_samples_; i++) call_sample_ok[i] = s.call_sample_[i].empty() ? 1 : 0;
+  return HIPSTR_OK;
+}
+
+int32_t hipstr_genotyper_locus_log(const hipstr_genotyper_t* g, int32_t locus, char* out, int32_t cap) {
+  if (!g || !out || cap <= 0 || locus < 0 || locus >= (int32_t)g->batch.loci.size()) return -1;
+  const std::string& s = g->batch.loci[locus].log_;
+  const size_t n = std::min(s.size(), (size_t)cap - 1);
+  std::memcpy(out, s.data() + (s.size() - n), n);
+  out[n] = 0;
+  return (int32_t)n;
+}
+
+}  // extern "C"

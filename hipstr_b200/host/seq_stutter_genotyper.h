@@ -1,0 +1,145 @@
+/*
+ * seq_stutter_genotyper.h -- host side of seam B1: the per-locus control loop of the
+ * reference's SeqStutterGenotyper (src/seq_stutter_genotyper.h:143-196, .cpp:219-415, 486-671, 805-879),
+ * re-designed for a GPU: instead of one object per locus that aligns, traces and prunes serially,
+ * a GenotyperBatch holds MANY loci and advances all of them in lockstep rounds.  Every round is at
+ * most three batched device calls through the C-ABI --
+ *     hipstr_trace_batch_host     (K5: the traces the loci are waiting for)
+ *     hipstr_genotype_batch_host  (K1+K2+K3: loci that gained haplotypes, masked to the new columns)
+ *     hipstr_posteriors_host      (K3: loci that only lost alleles)
+ * -- and the host work in between is the reference's own decision logic per locus
+ * (stutter-allele discovery, removal of uncalled / unspanned alleles, haplotype remapping by
+ * sequence identity).  There is no CPU alignment path: without a context nothing here can run.
+ *
+ * Names follow the reference (SeqStutterGenotyper, HapBlock, genotype(), add_and_remove_alleles,
+ * get_unused_alleles, get_stutter_candidate_alleles, retrace_alignments, trace_cache_).
+ */
+#ifndef HIPSTR_B200_SEQ_STUTTER_GENOTYPER_H_
+#define HIPSTR_B200_SEQ_STUTTER_GENOTYPER_H_
+
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/hipstr_b200.h"
+
+namespace hipstr {
+
+/* HapBlock / RepeatBlock (SeqAlignment/HapBlock.h:18-148, RepeatBlock.h:15-70) as plain data. */
+struct HapBlock {
+  int32_t start = 0, end = 0;        /* reference coordinates, end exclusive */
+  int32_t period = 0;                /* 0 = flank block, > 0 = repeat block with this motif length */
+  double stutter[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<std::string> seqs;     /* [0] = reference allele, then alternates in insertion order */
+  int num_options() const { return (int)seqs.size(); }
+  bool contains(const std::string& s) const;
+  HapBlock remove_alleles(const std::vector<int>& allele_indices) const;   /* HapBlock.h:138-147 */
+};
+
+/* What the control loop and the VCF writer read off an AlignmentTrace (AlignmentTraceback.h:9-117). */
+struct AlignmentTrace {
+  std::string hap_aln;                              /* hap_aln(): read vs haplotype operations */
+  int32_t start = 0, stop = 0;                      /* traced_aln().get_start() / get_stop() */
+  std::string cigar;                                /* traced_aln().getCigarString() */
+  std::string alignment;                            /* traced_aln().get_alignment() */
+  int32_t flank_ins_size = 0, flank_del_size = 0;
+  std::vector<int32_t> stutter_size;                /* per block; HIPSTR_NO_STR_DATA where no STR data */
+  std::vector<std::string> str_seq, flank_seq;      /* per block */
+  std::vector<std::pair<int32_t, int32_t> > flank_indel_data;
+  std::vector<std::pair<int32_t, char> > flank_snp_data;
+  bool has_stutter() const;
+  int total_stutter_size() const;
+};
+
+/* Haplotype::aln_haps_to_ref for one haplotype (SeqAlignment/Haplotype.cpp:8-86): global affine-gap
+ * alignment of the alternate haplotype against the reference haplotype (NeedlemanWunsch::Align with
+ * the reference end penalty, NeedlemanWunsch.cpp:84-131,193-241,253-337,339-423), indels in the
+ * upstream flank shifted right to the repeat block, encoded as one of 'M','I','D' per column. */
+std::string hap_aln_to_ref(const std::string& ref_hap, const std::string& alt_hap, int32_t first_block_start,
+                           int32_t repeat_block_start);
+
+class GenotyperBatch;
+
+/* One locus.  Member names follow seq_stutter_genotyper.h:28-68 / genotyper.h:20-46. */
+class SeqStutterGenotyper {
+ public:
+  enum Phase { ALIGN_ALL, STUTTER_ALLELES, PRUNE_UNCALLED, PRUNE_UNSPANNED, DONE, FAILED };
+  enum Request { NONE, NEED_TRACES, NEED_ALIGNMENT, NEED_POSTERIORS };
+
+  bool haploid_ = false;
+  int num_samples_ = 0, num_reads_ = 0, num_alleles_ = 0;   /* num_alleles_ = number of haplotypes */
+  std::vector<HapBlock> hap_blocks_;
+  std::vector<std::string> hap_aln_info_;                    /* per haplotype, Haplotype::get_aln_info */
+  /* reads (sample-major) */
+  std::vector<int32_t> sample_label_, pool_index_, read_weights_, seed_positions_;
+  std::vector<uint8_t> second_mate_;
+  std::vector<double> log_p1_, log_p2_;
+  std::vector<int32_t> read_start_, read_cigar_off_, read_cigar_len_;
+  std::vector<char> read_cigar_type_;
+  /* pooled reads (ReadPooler) */
+  int num_pools_ = 0;
+  std::vector<int32_t> pool_seq_off_, pool_seed_;
+  std::string pool_bases_, pool_quals_;
+  /* results */
+  std::vector<double> log_aln_probs_;          /* [R][H] */
+  std::vector<double> log_sample_posteriors_;  /* [S][H][H] */
+  std::vector<double> sample_total_LLs_;       /* [S] */
+  std::vector<int32_t> optimal_haps_;          /* [S][2] get_optimal_haplotypes */
+  std::vector<std::string> call_sample_;       /* non-empty = sample not genotyped, with the reason */
+  std::map<std::pair<int, int>, AlignmentTrace> trace_cache_;   /* (pool, haplotype) -> trace */
+  std::string log_;
+  int rounds_ = 0;                             /* alignment rounds run (1 = no allele discovery) */
+
+  Phase phase() const { return phase_; }
+  bool succeeded() const { return phase_ == DONE; }
+  std::string pool_read(int pool) const { return pool_bases_.substr(pool_seq_off_[pool], pool_seq_off_[pool + 1] - pool_seq_off_[pool]); }
+  void haps_to_alleles(int block_index, std::vector<int>& allele_indices) const;   /* .cpp:219-227 */
+  std::string hap_seq(int hap) const;
+
+ private:
+  friend class GenotyperBatch;
+  Phase phase_ = ALIGN_ALL;
+  int max_total_haplotypes_ = 1000;
+  /* pending device work */
+  std::vector<uint8_t> realign_hap_, realign_pool_, copy_read_;   /* masks of the pending alignment */
+  std::vector<std::pair<int, int> > missing_traces_;
+
+  Request advance();                                   /* runs host logic until device work is needed */
+  int best_hap_of_read(int read) const;                /* retrace_alignments, .cpp:825-827 */
+  bool collect_missing_traces();                       /* true if every needed trace is cached */
+  void get_stutter_candidate_alleles(int block_index, std::vector<std::string>& candidate_seqs);
+  void get_unused_alleles(bool check_spanned, bool check_called, std::vector<std::vector<int> >& allele_indices,
+                          int& num_aff_blocks, int& num_aff_alleles);
+  bool add_and_remove_alleles(const std::vector<std::vector<int> >& alleles_to_remove,
+                              const std::vector<std::vector<std::string> >& alleles_to_add);   /* true if K1 is needed */
+  void rebuild_hap_aln_info(const std::map<std::string, std::string>* known);
+};
+
+/* The batch engine: seam B1 for many loci at once. */
+class GenotyperBatch {
+ public:
+  explicit GenotyperBatch(hipstr_ctx_t* ctx) : ctx_(ctx) {}
+  /* Mirrors the SeqStutterGenotyper constructor + init() (.cpp:486-517) for pre-built haplotype blocks:
+   * pools the reads, marks second mates, computes pool seeds. */
+  hipstr_status_t add_loci(const hipstr_align_batch_t* blocks, const int32_t* block_start, const int32_t* block_end,
+                           const hipstr_locus_reads_t* reads, std::string& err);
+  /* genotype() of every locus (.cpp:603-671), lockstep rounds. */
+  hipstr_status_t genotype(int max_total_haplotypes, std::string& err);
+
+  std::vector<SeqStutterGenotyper> loci;
+  int64_t n_alignments = 0, n_traces = 0;
+  int n_rounds = 0;
+  /* Ensure traces for arbitrary (locus, pool, haplotype) keys (used by write_vcf_record). */
+  hipstr_status_t run_traces(const std::vector<int>& which, std::string& err);
+
+ private:
+  hipstr_ctx_t* ctx_;
+  hipstr_status_t run_alignments(const std::vector<int>& which, std::string& err);
+  hipstr_status_t run_posteriors(const std::vector<int>& which, std::string& err);
+};
+
+}  // namespace hipstr
+#endif

@@ -29,6 +29,8 @@ struct hipstr_synth {
   std::vector<int32_t> locus_read_off, locus_sample_off, pool_index, sample_label, read_weight, n_haps, true_gt, read_bp_diff;
   std::vector<uint8_t> second_mate, haploid;
   std::vector<double> log_p1, log_p2;
+  std::vector<int32_t> read_seq_off, read_start, read_cigar_off, read_cigar_len, read_name_id, block_start, block_end;
+  std::vector<char> read_bases, read_quals, read_cigar_type, chrom_seqs;
 };
 
 namespace {
@@ -63,6 +65,8 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
   S->locus_block_off.push_back(0); S->locus_pool_off.push_back(0); S->locus_hap_off.push_back(0);
   S->locus_out_off.push_back(0); S->block_opt_off.push_back(0); S->opt_seq_off.push_back(0);
   S->pool_seq_off.push_back(0); S->locus_read_off.push_back(0); S->locus_sample_off.push_back(0);
+  S->read_seq_off.push_back(0); S->read_cigar_off.push_back(0);
+  int32_t next_name = 0;
   int64_t read_ll_size = 0, post_size = 0;
 
   for (int l = 0; l < cfg.n_loci; l++) {
@@ -106,7 +110,10 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
       else if (b == 2) add_opt(chrom.substr(blk_end, kFlank));
       else for (int a = 0; a < A; a++) add_opt(rep_seq(copies[a]));
       S->block_opt_off.push_back((int32_t)S->opt_seq_off.size() - 1);
+      S->block_start.push_back(b == 0 ? first_start : b == 1 ? blk_start : blk_end);
+      S->block_end.push_back(b == 0 ? blk_start : b == 1 ? blk_end : last_end);
     }
+    S->chrom_seqs.insert(S->chrom_seqs.end(), chrom.begin(), chrom.end());
     S->locus_block_off.push_back((int32_t)S->block_period.size());
 
     // reads
@@ -209,6 +216,15 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
       S->read_weight.push_back(mates[r] ? 0 : 1);
       S->log_p1.push_back(0.0); S->log_p2.push_back(0.0);
       S->read_bp_diff.push_back(reads[r].bp_diff);
+      S->read_bases.insert(S->read_bases.end(), reads[r].seq.begin(), reads[r].seq.end());
+      S->read_quals.insert(S->read_quals.end(), reads[r].qual.begin(), reads[r].qual.end());
+      S->read_seq_off.push_back((int32_t)S->read_bases.size());
+      S->read_start.push_back(reads[r].start);
+      S->read_cigar_type.insert(S->read_cigar_type.end(), reads[r].ctype.begin(), reads[r].ctype.end());
+      S->read_cigar_len.insert(S->read_cigar_len.end(), reads[r].clen.begin(), reads[r].clen.end());
+      S->read_cigar_off.push_back((int32_t)S->read_cigar_type.size());
+      if (!mates[r]) next_name++;
+      S->read_name_id.push_back(next_name);
     }
     S->locus_read_off.push_back((int32_t)S->pool_index.size());
     S->locus_sample_off.push_back(S->locus_sample_off.back() + cfg.n_samples);
@@ -255,6 +271,20 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
   S->view.read_bp_diff = S->read_bp_diff.data();
   S->view.read_ll_size = read_ll_size;
   S->view.post_size = post_size;
+  S->view.read_seq_off = S->read_seq_off.data();
+  S->view.read_bases = S->read_bases.data();
+  S->view.read_quals = S->read_quals.data();
+  S->view.read_start = S->read_start.data();
+  S->view.read_cigar_off = S->read_cigar_off.data();
+  S->view.read_cigar_type = S->read_cigar_type.data();
+  S->view.read_cigar_len = S->read_cigar_len.data();
+  S->view.read_name_id = S->read_name_id.data();
+  S->view.block_start = S->block_start.data();
+  S->view.block_end = S->block_end.data();
+  S->view.chrom_len = kChromLen;
+  S->view.chrom_seqs = S->chrom_seqs.data();
+  S->view.region_start = kStrStart;
+  S->view.region_stop = str_end;
   return S;
 }
 

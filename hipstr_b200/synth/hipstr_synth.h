@@ -44,6 +44,20 @@ typedef struct {
   const int32_t* read_bp_diff;     /* [n_reads] bp difference of the read's STR vs the reference */
   int64_t read_ll_size;            /* sum over loci R_l * H_l */
   int64_t post_size;               /* sum over loci S_l * H_l^2 */
+  /* the un-pooled reads as seam B1 receives them (std::vector<Alignment>, sample-major) */
+  const int32_t* read_seq_off;     /* [n_reads+1] offsets into read_bases / read_quals */
+  const char*    read_bases;
+  const char*    read_quals;
+  const int32_t* read_start;       /* [n_reads] Alignment::get_start() */
+  const int32_t* read_cigar_off;   /* [n_reads+1] */
+  const char*    read_cigar_type;  /* '=', 'X', 'I', 'D' */
+  const int32_t* read_cigar_len;
+  const int32_t* read_name_id;     /* [n_reads] equal ids on adjacent reads = mates (same read name) */
+  const int32_t* block_start;      /* [n_blocks] HapBlock::start() */
+  const int32_t* block_end;        /* [n_blocks] HapBlock::end() */
+  int32_t chrom_len;               /* every locus has its own chromosome of this length */
+  const char* chrom_seqs;          /* [n_loci][chrom_len] */
+  int32_t region_start, region_stop; /* the STR Region of every locus */
 } hipstr_synth_view_t;
 
 typedef struct hipstr_synth hipstr_synth_t;

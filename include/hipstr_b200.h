@@ -366,6 +366,72 @@ hipstr_status_t hipstr_em_train_host(hipstr_ctx_t* ctx, const hipstr_em_batch_t*
                                      double* params_out, uint8_t* converged_out, int32_t* iters_out,
                                      double* ll_out);
 
+/* --- a1, a15 / seam B1: the per-locus genotyping loop, many loci at once --------
+ * Replaces SeqStutterGenotyper(...) + genotype() (seq_stutter_genotyper.h:143-189; init()
+ * .cpp:486-517, genotype() :603-671, id_and_align_to_stutter_alleles :570-601,
+ * get_stutter_candidate_alleles :843-879, get_unused_alleles :229-315, add_and_remove_alleles
+ * :324-415, retrace_alignments :805-841) for a BATCH of loci.  The reference builds one object
+ * per locus and loops align -> trace -> add / remove alleles serially; here all loci advance
+ * in lockstep rounds and every round is at most three device calls (hipstr_trace_batch_host,
+ * hipstr_genotype_batch_host masked to the new haplotypes, hipstr_posteriors_host), with the
+ * reference's per-locus decisions made on the host in between.  C++ callers use
+ * hipstr::GenotyperBatch / hipstr::SeqStutterGenotyper (hipstr_b200/host/seq_stutter_genotyper.h).
+ *
+ * Inputs are what seam B1 receives after haplotype generation: the haplotype blocks of every
+ * locus (only the locus/block/option fields of hipstr_align_batch_t are read) with their
+ * reference coordinates, and the un-pooled, left-aligned reads, sample-major per locus
+ * (std::vector<Alignment>, genotyper.h:104-112).  Pooling, second-mate detection (adjacent reads
+ * with equal name_id, .cpp:499) and seeding happen inside.  ref_vcf == NULL and
+ * reassemble_flanks == false semantics: flank re-assembly (.cpp:40-217) is not run yet.
+ * A locus the reference would skip (too many haplotypes, repetitive flanks) ends with
+ * locus_ok = 0 and its reason in the locus log; the call itself still returns HIPSTR_OK. */
+typedef struct hipstr_locus_reads {
+  const int32_t* locus_read_off;    /* [n_loci+1]                                              */
+  const int32_t* locus_sample_off;  /* [n_loci+1]                                              */
+  const int32_t* read_seq_off;      /* [R+1] offsets into bases / quals                        */
+  const char*    bases;             /* Alignment::get_sequence()                               */
+  const char*    quals;             /* Alignment::get_base_qualities() (Phred+33)              */
+  const int32_t* read_start;        /* [R] Alignment::get_start()                              */
+  const int32_t* cigar_off;         /* [R+1]                                                   */
+  const char*    cigar_type;        /* '=', 'X', 'I', 'D' (AlignmentData.h:12-27)              */
+  const int32_t* cigar_len;
+  const int32_t* sample_label;      /* [R] local to the locus, non-decreasing                  */
+  const int32_t* name_id;           /* [R] stand-in for the read name: equal ids on adjacent reads = mates */
+  const double*  log_p1;            /* [R]                                                     */
+  const double*  log_p2;            /* [R]                                                     */
+  const uint8_t* haploid;           /* [n_loci]                                                */
+} hipstr_locus_reads_t;
+
+typedef struct hipstr_genotyper hipstr_genotyper_t;
+hipstr_status_t hipstr_genotyper_create(hipstr_ctx_t* ctx, const hipstr_align_batch_t* blocks,
+                                        const int32_t* block_start, const int32_t* block_end,
+                                        const hipstr_locus_reads_t* reads, hipstr_genotyper_t** out);
+void            hipstr_genotyper_destroy(hipstr_genotyper_t* g);
+const char*     hipstr_genotyper_last_error(const hipstr_genotyper_t* g);
+/* genotype(max_total_haplotypes, ...) of every locus; locus_ok [n_loci] = its return value. */
+hipstr_status_t hipstr_genotyper_genotype(hipstr_genotyper_t* g, int32_t max_total_haplotypes, uint8_t* locus_ok);
+/* alignments (pooled read x haplotype) and traces computed so far, lockstep rounds run */
+hipstr_status_t hipstr_genotyper_stats(const hipstr_genotyper_t* g, int64_t* n_alignments, int64_t* n_traces,
+                                       int32_t* n_rounds);
+/* info[8] = {blocks, haplotypes (num_alleles_), reads, samples, pools, total options,
+ *            total allele bytes, alignment rounds of this locus} */
+hipstr_status_t hipstr_genotyper_locus_info(const hipstr_genotyper_t* g, int32_t locus, int32_t* info);
+/* current haplotype blocks: options per block, CSR offsets [total options + 1] and bytes */
+hipstr_status_t hipstr_genotyper_locus_blocks(const hipstr_genotyper_t* g, int32_t locus, int32_t* block_n_opts,
+                                              int32_t* opt_seq_off, char* opt_seq);
+/* member arrays: log_aln_probs_ [R*H], seed_positions_ [R], pool_index_ [R], log_sample_posteriors_
+ * [S*H*H], sample_total_LLs_ [S], get_optimal_haplotypes [S*2], call_sample_[s].empty() [S]; any may be NULL */
+hipstr_status_t hipstr_genotyper_locus_results(const hipstr_genotyper_t* g, int32_t locus, double* read_ll,
+                                               int32_t* read_seed, int32_t* pool_index, double* post,
+                                               double* sample_ll, int32_t* best, uint8_t* call_sample_ok);
+int32_t         hipstr_genotyper_locus_log(const hipstr_genotyper_t* g, int32_t locus, char* out, int32_t cap);
+
+/* Haplotype::aln_haps_to_ref for one haplotype (SeqAlignment/Haplotype.cpp:8-86 on top of
+ * NeedlemanWunsch::Align, NeedlemanWunsch.cpp:84-423): one of 'M','I','D' per alignment column
+ * of alt_hap against ref_hap -- the string hipstr_stitch_trace consumes.  Pure host logic. */
+hipstr_status_t hipstr_hap_aln_to_ref(const char* ref_hap, const char* alt_hap, int32_t first_block_start,
+                                      int32_t repeat_block_start, int32_t cap, char* out);
+
 /* --- seam B5: ordered VCF output (host) ---------------------------------------
  * Replaces VCFWriter::open / write_header / add_vcf_record / close (vcf_writer.h:63-82,
  * vcf_writer.cpp:7-36): records of a chromosome may arrive up to 50 bp out of order and are

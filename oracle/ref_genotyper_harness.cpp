@@ -1,0 +1,192 @@
+/*
+ * ref_genotyper_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * extern "C" adapter around the UNMODIFIED reference SeqStutterGenotyper (seam B1,
+ * src/seq_stutter_genotyper.h:143-196), compiled by oracle/Makefile from the sources where
+ * they lie under /root/reference into oracle/_ref/libhipstr_ref.so.  It lets the tests run
+ * the reference's whole per-locus control loop -- constructor (pooling + HaplotypeGenerator),
+ * genotype() (align-all, posteriors, stutter-allele discovery rounds, allele pruning, flank
+ * assembly) and write_vcf_record() -- on the same flat inputs the product takes, and read the
+ * member arrays the product must reproduce.  `#define private public` is only used to READ
+ * members (hap_blocks_, log_aln_probs_, ...); no reference source is modified or copied.
+ *
+ * htslib is not built: BAM/VCF/tabix entry points that this path never reaches (ref_vcf is
+ * NULL, no BAM is opened) are stubbed to abort(); kt_fisher_exact (htslib kfunc.c) and bdtr
+ * (cephes) ARE reached by write_vcf_record and are compiled from the vendored C files.
+ */
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#define private public
+#define protected public
+#include "vcf_writer.h"
+#include "genotyper.h"
+#include "seq_stutter_genotyper.h"
+#undef private
+#undef protected
+#include "SeqAlignment/HapBlock.h"
+#include "SeqAlignment/Haplotype.h"
+#include "SeqAlignment/RepeatBlock.h"
+#include "mathops.h"
+#include "region.h"
+#include "stutter_model.h"
+
+namespace {
+
+struct Init {
+  Init() { precompute_integer_logs(); }
+};
+void ensure_init() { static Init once; }
+
+struct RefSG {
+  SeqStutterGenotyper* g = NULL;
+  std::vector<StutterModel*> models;
+  std::vector<std::string> names;
+  std::string chrom_seq;
+  std::ostringstream log;
+  int n_reads = 0;
+  ~RefSG() {
+    delete g;
+    for (auto m : models) delete m;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+/* Reads are sample-major; read r of sample s is named "r<name_id[r]>", so that adjacent reads with the
+ * same id are mates (seq_stutter_genotyper.cpp:499).  The gapped alignment string and the stop
+ * coordinate are derived from bases + CIGAR ('=','X','I','D') the way BamProcessor leaves them. */
+void* ref_sg_create(int32_t n_samples, int32_t n_reads, const int32_t* sample_label, const int32_t* name_id,
+                    const int32_t* read_start, const int32_t* seq_off, const char* bases, const char* quals,
+                    const int32_t* cigar_off, const char* cigar_type, const int32_t* cigar_len, const double* log_p1,
+                    const double* log_p2, const char* chrom_seq, int32_t region_start, int32_t region_stop,
+                    int32_t period, const double* stutter, int32_t haploid, int32_t reassemble_flanks) {
+  ensure_init();
+  RefSG* h = new RefSG();
+  h->chrom_seq = chrom_seq;
+  h->n_reads = n_reads;
+  std::vector<Alignment> alns;
+  std::vector<std::vector<double> > p1(n_samples), p2(n_samples);
+  for (int s = 0; s < n_samples; s++) h->names.push_back("S" + std::to_string(s));
+  for (int r = 0; r < n_reads; r++) {
+    std::string seq(bases + seq_off[r], bases + seq_off[r + 1]), q(quals + seq_off[r], quals + seq_off[r + 1]);
+    std::string gapped;
+    int32_t pos = read_start[r];
+    size_t k = 0;
+    std::vector<CigarElement> cig;
+    for (int c = cigar_off[r]; c < cigar_off[r + 1]; c++) {
+      cig.push_back(CigarElement(cigar_type[c], cigar_len[c]));
+      if (cigar_type[c] == 'D') { gapped.append(cigar_len[c], '-'); pos += cigar_len[c]; }
+      else {
+        gapped.append(seq, k, cigar_len[c]);
+        k += cigar_len[c];
+        if (cigar_type[c] != 'I') pos += cigar_len[c];
+      }
+    }
+    Alignment a(read_start[r], pos, false, "r" + std::to_string(name_id[r]), q, seq, gapped);
+    a.set_cigar_list(cig);
+    a.set_hap_gen_info(std::vector<bool>(1, true));
+    alns.push_back(a);
+    p1[sample_label[r]].push_back(log_p1[r]);
+    p2[sample_label[r]].push_back(log_p2[r]);
+  }
+  Region region("chrS", region_start, region_stop, period, "STR");
+  RegionGroup group(region);
+  h->models.push_back(new StutterModel(stutter[0], stutter[1], stutter[2], stutter[3], stutter[4], stutter[5], period));
+  h->g = new SeqStutterGenotyper(group, haploid != 0, reassemble_flanks != 0, alns, p1, p2, h->names, h->chrom_seq,
+                                 h->models, NULL, h->log);
+  return h;
+}
+
+void ref_sg_destroy(void* hv) { delete static_cast<RefSG*>(hv); }
+int32_t ref_sg_initialized(void* hv) { return static_cast<RefSG*>(hv)->g->initialized_ ? 1 : 0; }
+int32_t ref_sg_num_blocks(void* hv) { return (int32_t)static_cast<RefSG*>(hv)->g->hap_blocks_.size(); }
+int32_t ref_sg_num_haps(void* hv) { return static_cast<RefSG*>(hv)->g->num_alleles_; }
+int32_t ref_sg_num_pools(void* hv) { return static_cast<RefSG*>(hv)->g->pooler_.num_pools(); }
+
+/* info = {start, end, period (0 = flank block), n_options, total sequence bytes} */
+void ref_sg_block_info(void* hv, int32_t b, int32_t* info) {
+  HapBlock* blk = static_cast<RefSG*>(hv)->g->hap_blocks_[b];
+  info[0] = blk->start();
+  info[1] = blk->end();
+  info[2] = blk->get_repeat_info() != NULL ? blk->get_repeat_info()->get_period() : 0;
+  info[3] = blk->num_options();
+  int32_t total = 0;
+  for (int o = 0; o < blk->num_options(); o++) total += (int32_t)blk->get_seq(o).size();
+  info[4] = total;
+}
+void ref_sg_block_seqs(void* hv, int32_t b, int32_t* off, char* seqs) {
+  HapBlock* blk = static_cast<RefSG*>(hv)->g->hap_blocks_[b];
+  off[0] = 0;
+  for (int o = 0; o < blk->num_options(); o++) {
+    const std::string& s = blk->get_seq(o);
+    std::memcpy(seqs + off[o], s.data(), s.size());
+    off[o + 1] = off[o] + (int32_t)s.size();
+  }
+}
+
+int32_t ref_sg_genotype(void* hv, int32_t max_total_haps, int32_t max_flank_haps, double min_flank_freq) {
+  RefSG* h = static_cast<RefSG*>(hv);
+  return h->g->genotype(max_total_haps, max_flank_haps, min_flank_freq, h->log) ? 1 : 0;
+}
+
+/* Member arrays after genotype(): log_aln_probs_ [R*H], seed_positions_ [R], pool_index_ [R],
+ * log_sample_posteriors_ [S*H*H], sample_total_LLs_ [S], optimal haplotypes [S*2], call_sample_ flags [S]. */
+void ref_sg_results(void* hv, double* read_ll, int32_t* seeds, int32_t* pool_index, double* post, double* sample_ll,
+                    int32_t* best, uint8_t* call_sample_ok) {
+  SeqStutterGenotyper* g = static_cast<RefSG*>(hv)->g;
+  const int R = g->num_reads_, H = g->num_alleles_, S = g->num_samples_;
+  if (read_ll) std::memcpy(read_ll, g->log_aln_probs_, sizeof(double) * R * H);
+  for (int r = 0; r < R; r++) {
+    if (seeds) seeds[r] = g->seed_positions_[r];
+    if (pool_index) pool_index[r] = g->pool_index_[r];
+  }
+  if (post) std::memcpy(post, g->log_sample_posteriors_, sizeof(double) * S * H * H);
+  if (sample_ll) std::memcpy(sample_ll, g->sample_total_LLs_, sizeof(double) * S);
+  if (best) {
+    std::vector<std::pair<int, int> > gts;
+    g->get_optimal_haplotypes(gts);
+    for (int s = 0; s < S; s++) { best[2 * s] = gts[s].first; best[2 * s + 1] = gts[s].second; }
+  }
+  if (call_sample_ok)
+    for (int s = 0; s < S; s++) call_sample_ok[s] = g->call_sample_[s].empty() ? 1 : 0;
+}
+
+/* write_vcf_record into a string: the record(s) are taken from the writer's reorder heap, so no
+ * BGZF stream is ever opened.  Returns the number of bytes (excluding NUL), or -needed if cap is short. */
+int32_t ref_sg_write_vcf(void* hv, char* out, int32_t cap) {
+  RefSG* h = static_cast<RefSG*>(hv);
+  VCFWriter w;
+  w.open_ = true;
+  std::ostringstream html;
+  h->g->write_vcf_record(h->names, h->chrom_seq, false, false, html, &w, h->log);
+  std::string text;
+  // records leave the heap in position order
+  while (!w.record_heap_.empty()) {
+    std::pop_heap(w.record_heap_.begin(), w.record_heap_.end(), tuple_comparator);
+    RecordTuple* best = w.record_heap_.back();
+    w.record_heap_.pop_back();
+    text += best->text();
+    text += "\n";
+    delete best;
+  }
+  w.open_ = false;
+  if ((int32_t)text.size() + 1 > cap) return -(int32_t)text.size() - 1;
+  std::memcpy(out, text.c_str(), text.size() + 1);
+  return (int32_t)text.size();
+}
+
+/* The log the reference wrote for this locus (diagnostics in test failures). */
+int32_t ref_sg_log(void* hv, char* out, int32_t cap) {
+  std::string s = static_cast<RefSG*>(hv)->log.str();
+  if ((int32_t)s.size() + 1 > cap) s = s.substr(s.size() + 1 - cap);
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return (int32_t)s.size();
+}
+
+}  // extern "C"

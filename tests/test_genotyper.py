@@ -1,0 +1,135 @@
+"""a1 / a15 (seam B1): the SeqStutterGenotyper::genotype() control loop.
+
+CPU: hipstr_hap_aln_to_ref (Haplotype::aln_haps_to_ref) against the compiled reference for every haplotype of the
+trace-test cases.
+GPU: hipstr_genotyper_* runs the whole loop (align-all, posteriors, stutter-allele discovery rounds, removal of uncalled
+and unspanned alleles) for a batch of loci; the UNMODIFIED reference SeqStutterGenotyper runs locus by locus on the same
+reads (oracle/ref_genotyper_harness.cpp) starting from the same haplotype blocks.  Final allele sets, haplotype order,
+seeds and optimal haplotypes must be identical; log-likelihoods within 1e-4 (north-star tolerance), posteriors 1e-6."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import checkers
+from hipstr_b200.capi import AlignBatch, BatchBuilder, Synth, c_i32p, hap_aln_to_ref
+from test_trace import ALL as TRACE_CASES, _load, block_starts
+
+needs_ref = pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libhipstr_ref.so not built")
+
+
+def _hap_seqs(batch, locus=0):
+    """Sequences of every haplotype of a locus, in the reference's haplotype order."""
+    lbo = np.ctypeslib.as_array(batch.locus_block_off, shape=(batch.n_loci + 1,))
+    boo = np.ctypeslib.as_array(batch.block_opt_off, shape=(batch.n_blocks + 1,))
+    oso = np.ctypeslib.as_array(batch.opt_seq_off, shape=(batch.n_options + 1,))
+    addr = C.c_void_p.from_buffer(batch, AlignBatch.opt_seq.offset).value
+    raw = C.string_at(addr, int(oso[-1]))
+    blocks = []
+    for b in range(lbo[locus], lbo[locus + 1]):
+        blocks.append([raw[oso[o]:oso[o + 1]].decode() for o in range(boo[b], boo[b + 1])])
+    n = np.array([len(b) for b in blocks], np.int32)
+    H = int(np.prod(n))
+    orc = checkers.oracle()
+    out = []
+    opt = np.zeros(len(blocks), np.int32)
+    for h in range(H):
+        orc.oracle_hap_options(len(blocks), n.ctypes.data_as(c_i32p), h, opt.ctypes.data_as(c_i32p))
+        out.append("".join(blocks[b][opt[b]] for b in range(len(blocks))))
+    return out, [len(b[0]) for b in blocks]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", TRACE_CASES, ids=lambda c: str(c[1]))
+def test_hap_aln_to_ref_matches_reference(case):
+    keep, batch, pools, haps, reads = _load(case)
+    lbo = np.ctypeslib.as_array(batch.locus_block_off, shape=(batch.n_loci + 1,))
+    if lbo[1] - lbo[0] != 3:
+        pytest.skip("Haplotype::adjust_indels asserts three blocks")
+    bs = block_starts(batch)
+    seqs, ref_lens = _hap_seqs(batch, 0)
+    ref = checkers.ref()
+    f = ref.ref_trace_stitched
+    f.restype = C.c_int32
+    f.argtypes = [C.POINTER(AlignBatch), c_i32p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, c_i32p, c_i32p,
+                  C.c_char_p, C.c_char_p]
+    lpo = np.ctypeslib.as_array(batch.locus_pool_off, shape=(batch.n_loci + 1,))
+    pool = int(next(p for p in pools if p < lpo[1]))
+    cap = 4096
+    for h, seq in enumerate(seqs):
+        b1, b2, b3, b4 = (C.create_string_buffer(cap) for _ in range(4))
+        a, b = C.c_int32(), C.c_int32()
+        assert f(C.byref(batch), bs.ctypes.data_as(c_i32p), pool, h, b1, b2, cap, C.byref(a), C.byref(b), b3, b4) == 0
+        got = hap_aln_to_ref(seqs[0], seq, int(bs[0]), int(bs[1]))
+        assert got == b1.value.decode(), h
+
+
+def test_hap_aln_to_ref_shifts_flank_indels():
+    """A deletion / insertion the aligner leaves in the upstream flank moves right until it touches the repeat."""
+    left, rep, right = "ACGTTGCAAT", "AGAGAGAGAGAG", "CCGTTAACGG"
+    # the repeat's first unit also ends the flank ("...ATAG|AGAG"): NW may place the indel inside the flank copy
+    ref = left + "AG" + rep + right
+    for alt_rep in ("AGAGAGAGAG", "AGAGAGAGAGAGAG"):
+        info = hap_aln_to_ref(ref, left + "AG" + alt_rep + right, 100, 100 + len(left) + 2)
+        kind = "D" if len(alt_rep) < len(rep) else "I"
+        assert info.count(kind) == 2 and info.count("M") == len(info) - 2
+        assert info.index(kind) >= len(left) + 2
+
+
+# ---- the full loop on the GPU ---------------------------------------------------------------------------
+LOOP_CASES = [
+    ("plain", dict(n_loci=3, n_samples=10, reads_per_sample=20, n_alleles=6, read_len=100, seed=5)),
+    ("discover_stutter_alleles", dict(n_loci=6, n_samples=4, reads_per_sample=25, n_alleles=3, read_len=100, seed=11, stutter_rate=0.35)),
+    ("prune_uncalled", dict(n_loci=5, n_samples=3, reads_per_sample=12, n_alleles=8, read_len=120, seed=21, stutter_rate=0.2)),
+    ("low_coverage", dict(n_loci=6, n_samples=25, reads_per_sample=3, n_alleles=10, read_len=150, seed=31, stutter_rate=0.1)),
+    ("period2_noisy", dict(n_loci=4, n_samples=6, reads_per_sample=15, n_alleles=5, read_len=110, seed=41, period=2, ref_copies=15,
+                           stutter_rate=0.3, sub_rate=0.02)),
+    ("mates", dict(n_loci=3, n_samples=6, reads_per_sample=8, n_alleles=4, read_len=110, seed=51, mate_rate=0.5, stutter_rate=0.25)),
+    ("homopolymer", dict(n_loci=3, n_samples=5, reads_per_sample=15, n_alleles=5, read_len=120, seed=61, period=1, ref_copies=14,
+                         stutter_rate=0.3)),
+]
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw", LOOP_CASES, ids=[c[0] for c in LOOP_CASES])
+def test_genotype_loop_matches_reference(name, kw):
+    from hipstr_b200.capi import Context, Genotyper
+    from ref_genotyper import LocusReads, RefGenotyper
+    s = Synth(**kw)
+    refs, blocks0 = [], []
+    for l in range(s.n_loci):
+        r = RefGenotyper(LocusReads(s, l))
+        assert r.initialized
+        refs.append(r)
+        blocks0.append(r.blocks())     # the reference's own HaplotypeGenerator output is the common starting point
+    ctx = Context(0)
+    g = Genotyper.from_synth(ctx, s, blocks0)
+    ok = g.genotype(1000)
+    stats = g.stats()
+    changed = rounds = 0
+    for l in range(s.n_loci):
+        want_ok = refs[l].genotype()
+        assert bool(ok[l]) == want_ok, (l, g.log(l), refs[l].log())
+        if not want_ok:
+            continue
+        want_blocks = [b[3] for b in refs[l].blocks()]
+        got_blocks = g.blocks(l)
+        assert got_blocks == want_blocks, (l, g.log(l), refs[l].log())
+        changed += want_blocks != [b[3] for b in blocks0[l]]
+        rounds += g.info(l)["rounds"] > 1
+        w, o = refs[l].results(), g.results(l)
+        assert o["n_haps"] == w["n_haps"]
+        assert np.array_equal(o["seeds"], w["seeds"]) and np.array_equal(o["pool_index"], w["pool_index"])
+        assert np.array_equal(o["best"], w["best"]), l
+        assert np.array_equal(o["call_ok"], w["call_ok"])
+        assert np.abs(o["read_ll"] - w["read_ll"]).max() <= 1e-4        # north-star tolerance
+        assert np.abs(o["read_ll"] - w["read_ll"]).max() <= 1e-9        # what the kernels actually reach
+        assert np.abs(o["post"] - w["post"]).max() <= 1e-6
+        assert np.abs(o["sample_ll"] - w["sample_ll"]).max() <= 1e-6
+    print("%s: %d loci, %d with a changed allele set, %d with extra alignment rounds, %s" % (name, s.n_loci, changed, rounds, stats))
+    if name in ("discover_stutter_alleles", "prune_uncalled"):
+        assert changed > 0, "case no longer exercises allele-set changes"
+    g.close()
+    ctx.close()
