@@ -39,6 +39,7 @@ class SynthCfg(C.Structure):
         ("n_loci", C.c_int32), ("n_samples", C.c_int32), ("reads_per_sample", C.c_int32), ("n_alleles", C.c_int32),
         ("read_len", C.c_int32), ("trim", C.c_int32), ("period", C.c_int32), ("ref_copies", C.c_int32),
         ("seed", C.c_uint64), ("stutter_rate", C.c_double), ("sub_rate", C.c_double), ("mate_rate", C.c_double),
+        ("flank_snp_freq", C.c_double),
     ]
 
 
@@ -305,7 +306,7 @@ def load():
     lib.hipstr_genotyper_last_error.restype = C.c_char_p
     lib.hipstr_genotyper_last_error.argtypes = [vp]
     lib.hipstr_genotyper_genotype.restype = C.c_int32
-    lib.hipstr_genotyper_genotype.argtypes = [vp, C.c_int32, c_u8p]
+    lib.hipstr_genotyper_genotype.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, c_u8p]
     lib.hipstr_genotyper_stats.restype = C.c_int32
     lib.hipstr_genotyper_stats.argtypes = [vp, c_i64p, c_i64p, c_i32p]
     lib.hipstr_genotyper_locus_info.restype = C.c_int32
@@ -349,10 +350,10 @@ class Synth:
     """A batch of synthetic loci owned by libhipstr_synth.so."""
 
     def __init__(self, n_loci, n_samples, reads_per_sample, n_alleles, read_len, seed=1, trim=1, period=4,
-                 ref_copies=12, stutter_rate=0.05, sub_rate=1.0 / 200, mate_rate=0.0):
+                 ref_copies=12, stutter_rate=0.05, sub_rate=1.0 / 200, mate_rate=0.0, flank_snp_freq=0.0):
         lib = load_synth()
         self.cfg = SynthCfg(n_loci, n_samples, reads_per_sample, n_alleles, read_len, trim, period, ref_copies, seed,
-                            stutter_rate, sub_rate, mate_rate)
+                            stutter_rate, sub_rate, mate_rate, flank_snp_freq)
         self._h = lib.hipstr_synth_create(C.byref(self.cfg))
         self.view = lib.hipstr_synth_view(self._h).contents
         v, b = self.view, self.view.batch
@@ -475,9 +476,10 @@ class Genotyper:
         g._synth = synth
         return g
 
-    def genotype(self, max_total_haplotypes=1000):
+    def genotype(self, max_total_haplotypes=1000, max_flank_haplotypes=4, min_flank_freq=0.01, reassemble_flanks=False):
         ok = np.zeros(self.n_loci, np.uint8)
-        st = self.lib.hipstr_genotyper_genotype(self.h, max_total_haplotypes, ptr(ok, c_u8p))
+        st = self.lib.hipstr_genotyper_genotype(self.h, max_total_haplotypes, max_flank_haplotypes, min_flank_freq,
+                                                int(reassemble_flanks), ptr(ok, c_u8p))
         if st != 0:
             raise HipstrError(st, "genotyper_genotype: " + (self.lib.hipstr_genotyper_last_error(self.h) or b"").decode())
         return ok

@@ -1,0 +1,182 @@
+/* flank_assembler.cpp -- see flank_assembler.h. */
+#include "flank_assembler.h"
+
+#include <algorithm>
+#include <cmath>
+#include <set>
+
+namespace hipstr {
+
+FlankAssembler::FlankAssembler(int k, const std::string& ref_seq) : k_(k), num_strings_(0) {
+  source_kmer_ = ref_seq.substr(0, k);
+  sink_kmer_ = ref_seq.substr(ref_seq.size() - k, k);
+  add_string(ref_seq, 2);
+  for (Edge& e : edges_) e.from_ref = true;
+}
+
+int FlankAssembler::node(const std::string& kmer) {
+  auto it = node_of_.find(kmer);
+  if (it != node_of_.end()) return it->second;
+  const int id = (int)labels_.size();
+  labels_.push_back(kmer);
+  node_of_[kmer] = id;
+  arriving_.emplace_back();
+  departing_.emplace_back();
+  return id;
+}
+
+void FlankAssembler::increment_edge(const std::string& from, const std::string& to, int delta) {
+  const int s = node(from), d = node(to);
+  for (int e : arriving_[d])
+    if (edges_[e].source == s) { edges_[e].weight += delta; return; }
+  const int id = (int)edges_.size();
+  edges_.push_back(Edge{s, d, delta, false});
+  departing_[s].push_back(id);
+  arriving_[d].push_back(id);
+}
+
+void FlankAssembler::add_string(const std::string& seq, int weight) {
+  if ((int)seq.size() <= k_) return;
+  num_strings_++;
+  for (size_t i = 1; i + k_ <= seq.size(); i++) increment_edge(seq.substr(i - 1, k_), seq.substr(i, k_), weight);
+}
+
+void FlankAssembler::prune_edges(double min_edge_freq, int min_weight) {
+  min_weight = std::max(min_weight, (int)std::ceil(min_edge_freq * num_strings_));
+  const int n_nodes = (int)labels_.size(), n_edges = (int)edges_.size();
+  std::vector<int> new_edge_id(n_edges, -1);
+  std::vector<bool> keep_node(n_nodes, false);
+  keep_node[node(source_kmer_)] = true;
+  keep_node[node(sink_kmer_)] = true;
+  std::vector<Edge> kept;
+  for (int e = 0; e < n_edges; e++) {
+    if (!edges_[e].from_ref && edges_[e].weight < min_weight) continue;
+    new_edge_id[e] = (int)kept.size();
+    kept.push_back(edges_[e]);
+    keep_node[edges_[e].source] = true;
+    keep_node[edges_[e].destination] = true;
+  }
+  // nodes that still touch an edge (plus source and sink) are renumbered in their old order
+  std::vector<int> new_node_id(n_nodes, -1);
+  std::vector<std::string> labels;
+  std::vector<std::vector<int> > arriving, departing;
+  node_of_.clear();
+  for (int v = 0; v < n_nodes; v++) {
+    if (!keep_node[v]) continue;
+    new_node_id[v] = (int)labels.size();
+    node_of_[labels_[v]] = new_node_id[v];
+    labels.push_back(labels_[v]);
+    std::vector<int> in, out;
+    for (int e : arriving_[v]) if (new_edge_id[e] >= 0) in.push_back(new_edge_id[e]);
+    for (int e : departing_[v]) if (new_edge_id[e] >= 0) out.push_back(new_edge_id[e]);
+    arriving.push_back(in);
+    departing.push_back(out);
+  }
+  for (Edge& e : kept) { e.source = new_node_id[e.source]; e.destination = new_node_id[e.destination]; }
+  edges_.swap(kept);
+  labels_.swap(labels);
+  arriving_.swap(arriving);
+  departing_.swap(departing);
+}
+
+bool FlankAssembler::has_cycles() const {   // Kahn's algorithm: a cycle leaves nodes unprocessed
+  const int n = (int)labels_.size();
+  std::vector<int> pending(n);
+  std::vector<int> ready;
+  int left = 0;
+  for (int v = 0; v < n; v++) {
+    pending[v] = (int)arriving_[v].size();
+    if (pending[v] == 0) ready.push_back(v);
+    else left++;
+  }
+  while (!ready.empty()) {
+    const int v = ready.back();
+    ready.pop_back();
+    for (int e : departing_[v]) {
+      const int c = edges_[e].destination;
+      if (--pending[c] == 0) { ready.push_back(c); left--; }
+    }
+  }
+  return left != 0;
+}
+
+bool FlankAssembler::is_source_ok() {
+  const int s = node(source_kmer_);
+  return !departing_[s].empty() && arriving_[s].empty();
+}
+bool FlankAssembler::is_sink_ok() {
+  const int s = node(sink_kmer_);
+  return !arriving_[s].empty() && departing_[s].empty();
+}
+
+/* k-mers one substitution away from `kmer` that are present and are themselves sources / sinks */
+void FlankAssembler::alt_kmer_nodes(std::string kmer, bool source, bool sink, std::vector<int>& nodes) {
+  const char bases[4] = {'A', 'C', 'G', 'T'};
+  for (size_t i = 0; i < kmer.size(); i++) {
+    const char orig = kmer[i];
+    for (char b : bases) {
+      if (b == orig) continue;
+      kmer[i] = b;
+      auto it = node_of_.find(kmer);
+      if (it == node_of_.end()) continue;
+      if (source && !arriving_[it->second].empty()) continue;
+      if (sink && !departing_[it->second].empty()) continue;
+      nodes.push_back(it->second);
+    }
+    kmer[i] = orig;
+  }
+}
+
+void FlankAssembler::enumerate_paths(int min_weight, int max_paths, std::vector<std::pair<std::string, int> >& paths) {
+  struct Path { int parent, node, min_weight; };
+  std::vector<Path> all;
+  std::vector<int> heap;   // indices into `all`; the path with the largest bottleneck weight is popped first
+  auto lighter = [&all](int a, int b) { return all[a].min_weight < all[b].min_weight; };
+  const int source = node(source_kmer_), sink = node(sink_kmer_);
+  all.push_back(Path{-1, source, 1000000});
+  heap.push_back(0);
+  std::make_heap(heap.begin(), heap.end(), lighter);
+  std::vector<int> alt;
+  alt_kmer_nodes(source_kmer_, true, false, alt);
+  for (int v : alt) {
+    all.push_back(Path{-1, v, 1000000});
+    heap.push_back((int)all.size() - 1);
+    std::push_heap(heap.begin(), heap.end(), lighter);
+  }
+  std::set<int> sinks;
+  sinks.insert(sink);
+  alt.clear();
+  alt_kmer_nodes(sink_kmer_, false, true, alt);
+  sinks.insert(alt.begin(), alt.end());
+  while (!heap.empty()) {
+    if ((int)paths.size() == max_paths) break;
+    std::pop_heap(heap.begin(), heap.end(), lighter);
+    const int best = heap.back();
+    heap.pop_back();
+    if (sinks.count(all[best].node)) {
+      std::string seq;   // first base of every k-mer on the path, then the rest of the last k-mer
+      std::vector<int> chain;
+      for (int p = best; p != -1; p = all[p].parent) chain.push_back(p);
+      for (size_t i = chain.size(); i-- > 1;) seq += labels_[all[chain[i]].node][0];
+      seq += labels_[all[best].node];
+      paths.emplace_back(seq, all[best].min_weight);
+    }
+    const std::vector<int> out = departing_[all[best].node];
+    for (int e : out) {
+      if (edges_[e].weight < min_weight) continue;
+      all.push_back(Path{best, edges_[e].destination, std::min(all[best].min_weight, edges_[e].weight)});
+      heap.push_back((int)all.size() - 1);
+      std::push_heap(heap.begin(), heap.end(), lighter);
+    }
+  }
+}
+
+bool FlankAssembler::calc_kmer_length(const std::string& ref_seq, int min_kmer, int max_kmer, int& kmer) {
+  for (kmer = min_kmer; kmer <= max_kmer; kmer++) {
+    FlankAssembler graph(kmer, ref_seq);
+    if (!graph.has_cycles()) return true;
+  }
+  return false;
+}
+
+}  // namespace hipstr

@@ -12,6 +12,7 @@
 #include <sstream>
 
 #include "../csrc/flatten.h"
+#include "flank_assembler.h"
 
 namespace hipstr {
 
@@ -86,19 +87,6 @@ void shift_indels_toward_repeat(std::string& ref_row, std::string& alt_row, int3
       col++;
     }
   }
-}
-
-/* DebruijnGraph::calc_kmer_length (debruijn_graph.cpp:22-29): smallest k in [min_k, max_k] for which
- * the k-mer path of the sequence has no cycle.  For a single string the graph is a walk, which is
- * acyclic exactly when no k-mer occurs twice. */
-bool acyclic_kmer_length(const std::string& seq, int min_k, int max_k, int* k_out) {
-  for (int k = min_k; k <= max_k; k++) {
-    std::set<std::string> seen;
-    bool repeat = false;
-    for (size_t i = 0; i + k <= seq.size() && !repeat; i++) repeat = !seen.insert(seq.substr(i, k)).second;
-    if (!repeat) { *k_out = k; return true; }
-  }
-  return false;
 }
 
 }  // namespace
@@ -305,7 +293,8 @@ void SeqStutterGenotyper::get_unused_alleles(bool check_spanned, bool check_call
 }
 
 bool SeqStutterGenotyper::add_and_remove_alleles(const std::vector<std::vector<int> >& alleles_to_remove,
-                                                 const std::vector<std::vector<std::string> >& alleles_to_add) {
+                                                 const std::vector<std::vector<std::string> >& alleles_to_add,
+                                                 const std::vector<uint8_t>* realign_pool, const std::vector<uint8_t>* copy_read) {
   const int old_H = num_alleles_;
   // haplotypes are matched across the change by SEQUENCE; of two old haplotypes with one sequence the later wins
   std::map<std::string, int> old_index;
@@ -344,8 +333,8 @@ bool SeqStutterGenotyper::add_and_remove_alleles(const std::vector<std::vector<i
   trace_cache_.swap(remapped);
   log_sample_posteriors_.assign((size_t)num_samples_ * new_H * new_H, 0.0);
   rebuild_hap_aln_info(&old_info);
-  realign_pool_.clear();
-  copy_read_.clear();
+  if (realign_pool) realign_pool_ = *realign_pool; else realign_pool_.clear();
+  if (copy_read) copy_read_ = *copy_read; else copy_read_.clear();
   return added_seq;
 }
 
@@ -406,11 +395,32 @@ SeqStutterGenotyper::Request SeqStutterGenotyper::advance() {
         std::vector<std::vector<int> > unused;
         int blocks = 0, alleles = 0;
         get_unused_alleles(true, false, unused, blocks, alleles);
-        phase_ = DONE;
+        phase_ = reassemble_flanks_ ? ASSEMBLE_FLANKS : DONE;
         if (alleles == 0) break;
         std::ostringstream msg;
         msg << "Recomputing sample posteriors after removing " << alleles << " alleles with no spanning reads across " << blocks
             << " blocks\n";
+        log_ += msg.str();
+        add_and_remove_alleles(unused, std::vector<std::vector<std::string> >(hap_blocks_.size()));
+        return NEED_POSTERIORS;
+      }
+      case ASSEMBLE_FLANKS: {   // assemble_flanks, seq_stutter_genotyper.cpp:40-217
+        if (!collect_missing_traces()) return NEED_TRACES;
+        const int outcome = assemble_flanks();
+        if (outcome < 0) { phase_ = FAILED; return NONE; }
+        if (outcome == 0) { phase_ = DONE; break; }
+        phase_ = ASSEMBLE_PRUNE;
+        rounds_++;
+        return NEED_ALIGNMENT;
+      }
+      case ASSEMBLE_PRUNE: {    // seq_stutter_genotyper.cpp:203-213
+        std::vector<std::vector<int> > unused;
+        int blocks = 0, alleles = 0;
+        get_unused_alleles(false, true, unused, blocks, alleles);
+        phase_ = DONE;
+        if (alleles == 0) break;
+        std::ostringstream msg;
+        msg << "Recomputing sample posteriors after removing " << alleles << " uncalled alleles across " << blocks << " blocks\n";
         log_ += msg.str();
         add_and_remove_alleles(unused, std::vector<std::vector<std::string> >(hap_blocks_.size()));
         return NEED_POSTERIORS;
@@ -420,6 +430,114 @@ SeqStutterGenotyper::Request SeqStutterGenotyper::advance() {
         return NONE;
     }
   }
+}
+
+int SeqStutterGenotyper::assemble_flanks() {
+  const int kMinPathWeight = 2, kMinKmer = 10, kMaxKmer = 15;   // seq_stutter_genotyper.h:152-154
+  log_ += "Reassembling flanking sequences\n";
+  std::vector<std::vector<std::string> > alleles_to_add(hap_blocks_.size());
+  std::vector<bool> realign_sample(num_samples_, false);
+  int new_total_haps = num_alleles_;
+  // reads are sample-major: [first_read[s], first_read[s+1]) belong to sample s
+  std::vector<int> first_read(num_samples_ + 1, num_reads_);
+  for (int r = num_reads_ - 1; r >= 0; r--) first_read[sample_label_[r]] = r;
+  for (int s = num_samples_ - 1; s >= 0; s--) first_read[s] = std::min(first_read[s], first_read[s + 1]);
+
+  for (int flank = 0; flank < 2; flank++) {
+    const int block_index = flank == 0 ? 0 : (int)hap_blocks_.size() - 1;
+    const std::string& ref_seq = hap_blocks_[block_index].seqs[0];
+    const int max_k = std::min(kMaxKmer, ref_seq.empty() ? -1 : (int)ref_seq.size() - 1);
+    new_total_haps /= hap_blocks_[block_index].num_options();
+    int kmer_length;
+    if (!FlankAssembler::calc_kmer_length(ref_seq, kMinKmer, max_k, kmer_length)) return -1;
+
+    std::map<std::string, int> haplotype_indexes;           // alternate flank -> index
+    std::vector<std::vector<int> > haplotype_to_sample;     // samples supporting each alternate flank
+    std::vector<std::pair<std::string, int> > assembly_data;
+    for (int s = 0; s < num_samples_; s++) {
+      if (!call_sample_[s].empty()) continue;
+      assembly_data.clear();
+      bool acyclic = false;
+      for (int k = kmer_length; k <= max_k; k++) {
+        FlankAssembler assembler(k, ref_seq);
+        for (int r = first_read[s]; r < first_read[s + 1]; r++) {
+          if (seed_positions_[r] < 0) continue;
+          const std::string& seq = trace_cache_.at(std::make_pair(pool_index_[r], best_hap_of_read(r))).flank_seq[block_index];
+          if (!seq.empty()) assembler.add_string(seq);
+        }
+        assembler.prune_edges(0.02, 2);
+        if (!assembler.has_cycles() && assembler.is_source_ok() && assembler.is_sink_ok()) {
+          acyclic = true;
+          assembler.enumerate_paths(kMinPathWeight, 10, assembly_data);
+          break;
+        }
+      }
+      if (!acyclic) { call_sample_[s] = "FLANK_ASSEMBLY_CYCLIC"; continue; }
+      if (assembly_data.size() <= 1) continue;
+      int total_depth = 0;
+      for (const auto& path : assembly_data) total_depth += path.second;
+      for (const auto& path : assembly_data) {
+        if (path.first == ref_seq || !(path.second * 1.0 / total_depth > 0.25)) continue;
+        if (ref_seq.size() != path.first.size()) {
+          // a flank with an indel would clobber indels in the repeat: the sample is not genotyped
+          call_sample_[s] = "FLANK_ASSEMBLY_INDEL";
+          realign_sample[s] = false;
+        } else {
+          if (haplotype_indexes.find(path.first) == haplotype_indexes.end()) {
+            const int index = (int)haplotype_indexes.size();
+            haplotype_indexes[path.first] = index;
+            haplotype_to_sample.push_back(std::vector<int>());
+          }
+          realign_sample[s] = true;
+          haplotype_to_sample[haplotype_indexes[path.first]].push_back(s);
+        }
+      }
+    }
+    // flanks seen in too few samples are dropped and their samples are not genotyped
+    for (auto it = haplotype_indexes.begin(); it != haplotype_indexes.end();) {
+      const std::vector<int>& hap_samples = haplotype_to_sample[it->second];
+      if (hap_samples.size() < min_flank_freq_ * num_samples_) {
+        for (int s : hap_samples)
+          if (call_sample_[s].empty()) { call_sample_[s] = "LOW_FREQUENCY_ALT_FLANK"; realign_sample[s] = false; }
+        log_ += std::string("\tPruning low frequency ") + (flank == 0 ? "left" : "right") + " flank\t" + it->first + "\n";
+        haplotype_indexes.erase(it++);
+      } else
+        ++it;
+    }
+    if (!haplotype_indexes.empty()) {
+      if ((int)haplotype_indexes.size() > max_flank_haplotypes_) {
+        log_ += std::string("Skipping locus with too many ") + (flank == 0 ? "left" : "right") + " alternate flanking sequences\n";
+        return -1;
+      }
+      std::ostringstream msg;
+      msg << "Identified " << haplotype_indexes.size() << " new " << (flank == 0 ? "left" : "right") << " flank haplotype(s)\n";
+      for (const auto& kv : haplotype_indexes) {
+        msg << "\t" << kv.first << "\t" << haplotype_to_sample[kv.second].size() << "\n";
+        alleles_to_add[block_index].push_back(kv.first);
+      }
+      log_ += msg.str();
+      new_total_haps *= 1 + (int)haplotype_indexes.size();
+    }
+  }
+  if (new_total_haps > max_total_haplotypes_) {
+    log_ += "Aborting genotyping of the locus as too many candidate haplotypes were found\n";
+    return -1;
+  }
+  // realign a pool when any of its reads belongs to a sample with a new flank; update a read's
+  // likelihoods only when its whole sample is realigned
+  std::vector<uint8_t> realign_pools(num_pools_, 0), copy_reads(num_reads_, 0);
+  for (int r = 0; r < num_reads_; r++) {
+    const bool flag = realign_sample[sample_label_[r]];
+    if (flag) realign_pools[pool_index_[r]] = 1;
+    copy_reads[r] = flag ? 1 : 0;
+  }
+  const int realign_count = (int)std::count(realign_pools.begin(), realign_pools.end(), 1);
+  if (realign_count == 0) return 0;
+  std::ostringstream msg;
+  msg << "Realigning " << realign_count << " out of " << num_pools_ << " read pools to polish flanking sequences\n";
+  log_ += msg.str();
+  add_and_remove_alleles(std::vector<std::vector<int> >(hap_blocks_.size()), alleles_to_add, &realign_pools, &copy_reads);
+  return 1;
 }
 
 /* ---- batching ------------------------------------------------------------------------------------ */
@@ -772,11 +890,15 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
   return HIPSTR_OK;
 }
 
-hipstr_status_t GenotyperBatch::genotype(int max_total_haplotypes, std::string& err) {
+hipstr_status_t GenotyperBatch::genotype(int max_total_haplotypes, int max_flank_haplotypes, double min_flank_freq,
+                                         bool reassemble_flanks, std::string& err) {
   const int kMinKmer = 10, kMaxKmer = 15;   // seq_stutter_genotyper.h:153-154
   for (SeqStutterGenotyper& g : loci) {
     if (g.phase_ != SeqStutterGenotyper::ALIGN_ALL) continue;
     g.max_total_haplotypes_ = max_total_haplotypes;
+    g.max_flank_haplotypes_ = max_flank_haplotypes;
+    g.min_flank_freq_ = min_flank_freq;
+    g.reassemble_flanks_ = reassemble_flanks;
     if (g.num_alleles_ > max_total_haplotypes) {
       std::ostringstream msg;
       msg << "Aborting genotyping of the locus as too many candidate haplotypes were found (# Found = " << g.num_alleles_
@@ -790,7 +912,7 @@ hipstr_status_t GenotyperBatch::genotype(int max_total_haplotypes, std::string& 
       const std::string& ref_seq = (flank == 0 ? g.hap_blocks_.front() : g.hap_blocks_.back()).seqs[0];
       const int max_k = std::min(kMaxKmer, ref_seq.empty() ? -1 : (int)ref_seq.size() - 1);
       int k = 0;
-      if (!acyclic_kmer_length(ref_seq, kMinKmer, max_k, &k)) {
+      if (!FlankAssembler::calc_kmer_length(ref_seq, kMinKmer, max_k, k)) {
         g.log_ += std::string("Aborting genotyping of the locus as the sequence ") + (flank == 0 ? "upstream" : "downstream") +
                   " of the repeat is too repetitive for accurate genotyping\n";
         g.phase_ = SeqStutterGenotyper::FAILED;
@@ -850,9 +972,11 @@ hipstr_status_t hipstr_genotyper_create(hipstr_ctx_t* ctx, const hipstr_align_ba
 void hipstr_genotyper_destroy(hipstr_genotyper_t* g) { delete g; }
 const char* hipstr_genotyper_last_error(const hipstr_genotyper_t* g) { return g ? g->last_error.c_str() : "null genotyper"; }
 
-hipstr_status_t hipstr_genotyper_genotype(hipstr_genotyper_t* g, int32_t max_total_haplotypes, uint8_t* locus_ok) {
+hipstr_status_t hipstr_genotyper_genotype(hipstr_genotyper_t* g, int32_t max_total_haplotypes, int32_t max_flank_haplotypes,
+                                          double min_flank_freq, int32_t reassemble_flanks, uint8_t* locus_ok) {
   if (!g) return HIPSTR_ERR_BAD_ARG;
-  hipstr_status_t st = g->batch.genotype(max_total_haplotypes, g->last_error);
+  hipstr_status_t st = g->batch.genotype(max_total_haplotypes, max_flank_haplotypes, min_flank_freq, reassemble_flanks != 0,
+                                         g->last_error);
   if (st != HIPSTR_OK) return st;
   if (locus_ok)
     for (size_t l = 0; l < g->batch.loci.size(); l++) locus_ok[l] = g->batch.loci[l].succeeded() ? 1 : 0;

@@ -66,7 +66,7 @@ class GenotyperBatch;
 /* One locus.  Member names follow seq_stutter_genotyper.h:28-68 / genotyper.h:20-46. */
 class SeqStutterGenotyper {
  public:
-  enum Phase { ALIGN_ALL, STUTTER_ALLELES, PRUNE_UNCALLED, PRUNE_UNSPANNED, DONE, FAILED };
+  enum Phase { ALIGN_ALL, STUTTER_ALLELES, PRUNE_UNCALLED, PRUNE_UNSPANNED, ASSEMBLE_FLANKS, ASSEMBLE_PRUNE, DONE, FAILED };
   enum Request { NONE, NEED_TRACES, NEED_ALIGNMENT, NEED_POSTERIORS };
 
   bool haploid_ = false;
@@ -102,7 +102,9 @@ class SeqStutterGenotyper {
  private:
   friend class GenotyperBatch;
   Phase phase_ = ALIGN_ALL;
-  int max_total_haplotypes_ = 1000;
+  int max_total_haplotypes_ = 1000, max_flank_haplotypes_ = 4;
+  double min_flank_freq_ = 0.01;
+  bool reassemble_flanks_ = false;
   /* pending device work */
   std::vector<uint8_t> realign_hap_, realign_pool_, copy_read_;   /* masks of the pending alignment */
   std::vector<std::pair<int, int> > missing_traces_;
@@ -114,7 +116,12 @@ class SeqStutterGenotyper {
   void get_unused_alleles(bool check_spanned, bool check_called, std::vector<std::vector<int> >& allele_indices,
                           int& num_aff_blocks, int& num_aff_alleles);
   bool add_and_remove_alleles(const std::vector<std::vector<int> >& alleles_to_remove,
-                              const std::vector<std::vector<std::string> >& alleles_to_add);   /* true if K1 is needed */
+                              const std::vector<std::vector<std::string> >& alleles_to_add,
+                              const std::vector<uint8_t>* realign_pool = nullptr,
+                              const std::vector<uint8_t>* copy_read = nullptr);   /* true if K1 is needed */
+  /* assemble_flanks (.cpp:40-217) up to the realignment request: 0 = nothing to realign, 1 = alignment
+   * requested, -1 = the reference returns false (locus skipped) */
+  int assemble_flanks();
   void rebuild_hap_aln_info(const std::map<std::string, std::string>* known);
 };
 
@@ -127,7 +134,8 @@ class GenotyperBatch {
   hipstr_status_t add_loci(const hipstr_align_batch_t* blocks, const int32_t* block_start, const int32_t* block_end,
                            const hipstr_locus_reads_t* reads, std::string& err);
   /* genotype() of every locus (.cpp:603-671), lockstep rounds. */
-  hipstr_status_t genotype(int max_total_haplotypes, std::string& err);
+  hipstr_status_t genotype(int max_total_haplotypes, int max_flank_haplotypes, double min_flank_freq, bool reassemble_flanks,
+                           std::string& err);
 
   std::vector<SeqStutterGenotyper> loci;
   int64_t n_alignments = 0, n_traces = 0;

@@ -120,11 +120,22 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
     std::vector<SimRead> reads;
     std::vector<int32_t> labels;
     std::vector<uint8_t> mates;
+    const int snp_left = kStrStart - 15, snp_right = str_end + 12;   // reference coordinates of the planted SNPs
+    char alt_left = chrom[snp_left], alt_right = chrom[snp_right];
+    if (cfg.flank_snp_freq > 0) {
+      while (alt_left == chrom[snp_left]) alt_left = ACGT[rng() & 3];
+      while (alt_right == chrom[snp_right]) alt_right = ACGT[rng() & 3];
+    }
     for (int s = 0; s < cfg.n_samples; s++) {
       int gt[2] = {uni(0, A - 1), uni(0, A - 1)};
       S->true_gt.push_back(gt[0]); S->true_gt.push_back(gt[1]);
+      bool carries[2][2] = {{false, false}, {false, false}};   // [chromosome copy][left / right SNP]
+      if (cfg.flank_snp_freq > 0)
+        for (int c = 0; c < 2; c++)
+          for (int side = 0; side < 2; side++) carries[c][side] = unif() < cfg.flank_snp_freq;
       for (int r = 0; r < cfg.reads_per_sample; r++) {
-        int k = copies[gt[rng() & 1]];
+        const int copy = rng() & 1;
+        int k = copies[gt[copy]];
         if (unif() < cfg.stutter_rate) k += (rng() & 1) ? 1 : -1;
         if (k < 1) k = 1;
         const int delta = (k - cfg.ref_copies) * p;           // bp difference vs reference
@@ -132,6 +143,8 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
         std::string hap = chrom.substr(0, kStrStart);
         for (int i = 0; i < k * p; i++) hap += motif[i % p];
         hap += chrom.substr(str_end);
+        if (carries[copy][0]) hap[snp_left] = alt_left;
+        if (carries[copy][1]) hap[snp_right + delta] = alt_right;
         const bool mate = unif() < cfg.mate_rate;
         for (int m = 0; m < (mate ? 2 : 1); m++) {
           SimRead rd;
@@ -147,7 +160,7 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
           // CIGAR vs the reference with the indel at the STR start; substitutions only in flanks
           int i = 0;
           const int n = (int)rd.seq.size();
-          auto flank_run = [&](int count) {
+          auto flank_run = [&](int count, int ref_shift) {
             for (int e = i + count; i < e; i++) {
               if (unif() < cfg.sub_rate) {
                 char c;
@@ -155,16 +168,16 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
                 rd.seq[i] = c; rd.qual[i] = '+';
                 push_cigar(rd, 'X', 1);
               } else
-                push_cigar(rd, '=', 1);
+                push_cigar(rd, rd.seq[i] == chrom[start + i - ref_shift] ? '=' : 'X', 1);   // planted SNPs read as mismatches
             }
           };
-          flank_run(std::min(n, kStrStart - start));
+          flank_run(std::min(n, kStrStart - start), 0);
           if (i < n) {
             if (delta > 0) { int ins = std::min(delta, n - i); push_cigar(rd, 'I', ins); i += ins; }
             else if (delta < 0) push_cigar(rd, 'D', -delta);
             int in_str = std::min(n - i, std::max(0, hap_str_end - (start + i)));
             push_cigar(rd, '=', in_str); i += in_str;
-            flank_run(n - i);
+            flank_run(n - i, delta);
           }
           reads.push_back(rd);
           labels.push_back(s);

@@ -25,6 +25,8 @@ typedef struct {
   double stutter_rate;      /* P(read carries +/- 1 copy), default 0.05 */
   double sub_rate;          /* flank substitution rate, default 1/200 */
   double mate_rate;         /* P(read is followed by an adjacent second mate), default 0 */
+  double flank_snp_freq;    /* population frequency of a planted SNP 15 bp upstream and one 12 bp downstream of
+                               the STR (each sample chromosome draws them independently), default 0 */
 } hipstr_synth_cfg_t;
 
 typedef struct {

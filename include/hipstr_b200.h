@@ -381,8 +381,9 @@ hipstr_status_t hipstr_em_train_host(hipstr_ctx_t* ctx, const hipstr_em_batch_t*
  * locus (only the locus/block/option fields of hipstr_align_batch_t are read) with their
  * reference coordinates, and the un-pooled, left-aligned reads, sample-major per locus
  * (std::vector<Alignment>, genotyper.h:104-112).  Pooling, second-mate detection (adjacent reads
- * with equal name_id, .cpp:499) and seeding happen inside.  ref_vcf == NULL and
- * reassemble_flanks == false semantics: flank re-assembly (.cpp:40-217) is not run yet.
+ * with equal name_id, .cpp:499) and seeding happen inside.  ref_vcf == NULL semantics (no
+ * reference panel); flank re-assembly (assemble_flanks .cpp:40-217 over DebruijnGraph,
+ * debruijn_graph.cpp, directed_graph.cpp) runs on the host between rounds when requested.
  * A locus the reference would skip (too many haplotypes, repetitive flanks) ends with
  * locus_ok = 0 and its reason in the locus log; the call itself still returns HIPSTR_OK. */
 typedef struct hipstr_locus_reads {
@@ -408,8 +409,13 @@ hipstr_status_t hipstr_genotyper_create(hipstr_ctx_t* ctx, const hipstr_align_ba
                                         const hipstr_locus_reads_t* reads, hipstr_genotyper_t** out);
 void            hipstr_genotyper_destroy(hipstr_genotyper_t* g);
 const char*     hipstr_genotyper_last_error(const hipstr_genotyper_t* g);
-/* genotype(max_total_haplotypes, ...) of every locus; locus_ok [n_loci] = its return value. */
-hipstr_status_t hipstr_genotyper_genotype(hipstr_genotyper_t* g, int32_t max_total_haplotypes, uint8_t* locus_ok);
+/* genotype(max_total_haplotypes, max_flank_haplotypes, min_flank_freq) of every locus
+ * (seq_stutter_genotyper.h:189; defaults 1000 / 4 / 0.01, genotyper_bam_processor.h:110-112);
+ * reassemble_flanks is the constructor's flag (the reference always passes true,
+ * genotyper_bam_processor.cpp:229).  locus_ok [n_loci] = genotype()'s return value. */
+hipstr_status_t hipstr_genotyper_genotype(hipstr_genotyper_t* g, int32_t max_total_haplotypes,
+                                          int32_t max_flank_haplotypes, double min_flank_freq,
+                                          int32_t reassemble_flanks, uint8_t* locus_ok);
 /* alignments (pooled read x haplotype) and traces computed so far, lockstep rounds run */
 hipstr_status_t hipstr_genotyper_stats(const hipstr_genotyper_t* g, int64_t* n_alignments, int64_t* n_traces,
                                        int32_t* n_rounds);

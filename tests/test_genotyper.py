@@ -88,6 +88,17 @@ LOOP_CASES = [
     ("mates", dict(n_loci=3, n_samples=6, reads_per_sample=8, n_alleles=4, read_len=110, seed=51, mate_rate=0.5, stutter_rate=0.25)),
     ("homopolymer", dict(n_loci=3, n_samples=5, reads_per_sample=15, n_alleles=5, read_len=120, seed=61, period=1, ref_copies=14,
                          stutter_rate=0.3)),
+    # flank re-assembly on (the reference's production setting): planted flank SNPs become flank alleles, subsets of
+    # pools are realigned; with a high min_flank_freq rare flanks are dropped and their samples masked
+    ("assembly_no_variants", dict(n_loci=2, n_samples=8, reads_per_sample=20, n_alleles=4, read_len=120, seed=91, assemble=True)),
+    ("assembly_flank_snps", dict(n_loci=4, n_samples=8, reads_per_sample=20, n_alleles=4, read_len=120, seed=71, flank_snp_freq=0.3,
+                                 assemble=True)),
+    ("assembly_rare_flank_snps", dict(n_loci=4, n_samples=30, reads_per_sample=10, n_alleles=4, read_len=120, seed=81,
+                                      flank_snp_freq=0.03, assemble=True)),
+    ("assembly_low_frequency_pruned", dict(n_loci=4, n_samples=30, reads_per_sample=10, n_alleles=4, read_len=120, seed=81,
+                                           flank_snp_freq=0.03, assemble=True, min_flank_freq=0.1)),
+    ("assembly_stutter_and_flanks", dict(n_loci=4, n_samples=6, reads_per_sample=25, n_alleles=3, read_len=110, seed=101,
+                                         stutter_rate=0.3, flank_snp_freq=0.25, assemble=True)),
 ]
 
 
@@ -97,20 +108,22 @@ LOOP_CASES = [
 def test_genotype_loop_matches_reference(name, kw):
     from hipstr_b200.capi import Context, Genotyper
     from ref_genotyper import LocusReads, RefGenotyper
+    kw = dict(kw)
+    assemble, min_flank_freq = kw.pop("assemble", False), kw.pop("min_flank_freq", 0.01)
     s = Synth(**kw)
     refs, blocks0 = [], []
     for l in range(s.n_loci):
-        r = RefGenotyper(LocusReads(s, l))
+        r = RefGenotyper(LocusReads(s, l), reassemble_flanks=assemble)
         assert r.initialized
         refs.append(r)
         blocks0.append(r.blocks())     # the reference's own HaplotypeGenerator output is the common starting point
     ctx = Context(0)
     g = Genotyper.from_synth(ctx, s, blocks0)
-    ok = g.genotype(1000)
+    ok = g.genotype(1000, 4, min_flank_freq, assemble)
     stats = g.stats()
     changed = rounds = 0
     for l in range(s.n_loci):
-        want_ok = refs[l].genotype()
+        want_ok = refs[l].genotype(1000, 4, min_flank_freq)
         assert bool(ok[l]) == want_ok, (l, g.log(l), refs[l].log())
         if not want_ok:
             continue
@@ -129,7 +142,7 @@ def test_genotype_loop_matches_reference(name, kw):
         assert np.abs(o["post"] - w["post"]).max() <= 1e-6
         assert np.abs(o["sample_ll"] - w["sample_ll"]).max() <= 1e-6
     print("%s: %d loci, %d with a changed allele set, %d with extra alignment rounds, %s" % (name, s.n_loci, changed, rounds, stats))
-    if name in ("discover_stutter_alleles", "prune_uncalled"):
+    if name in ("discover_stutter_alleles", "prune_uncalled", "assembly_flank_snps", "assembly_stutter_and_flanks"):
         assert changed > 0, "case no longer exercises allele-set changes"
     g.close()
     ctx.close()
