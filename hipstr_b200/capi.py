@@ -53,7 +53,7 @@ class SynthView(C.Structure):
         ("read_seq_off", c_i32p), ("read_bases", C.c_void_p), ("read_quals", C.c_void_p), ("read_start", c_i32p),
         ("read_cigar_off", c_i32p), ("read_cigar_type", C.c_void_p), ("read_cigar_len", c_i32p),
         ("read_name_id", c_i32p), ("block_start", c_i32p), ("block_end", c_i32p), ("chrom_len", C.c_int32),
-        ("chrom_seqs", C.c_void_p), ("region_start", C.c_int32), ("region_stop", C.c_int32),
+        ("chrom_seqs", C.c_void_p), ("region_start", C.c_int32), ("region_stop", C.c_int32), ("read_rev_strand", c_u8p),
     ]
 
 
@@ -71,7 +71,22 @@ class LocusReadsStruct(C.Structure):
     _fields_ = [("locus_read_off", c_i32p), ("locus_sample_off", c_i32p), ("read_seq_off", c_i32p), ("bases", C.c_void_p),
                 ("quals", C.c_void_p), ("read_start", c_i32p), ("cigar_off", c_i32p), ("cigar_type", C.c_void_p),
                 ("cigar_len", c_i32p), ("sample_label", c_i32p), ("name_id", c_i32p), ("log_p1", c_f64p), ("log_p2", c_f64p),
-                ("haploid", c_u8p)]
+                ("haploid", c_u8p), ("rev_strand", c_u8p)]
+
+
+class VcfLoci(C.Structure):
+    """hipstr_vcf_loci_t"""
+    _fields_ = [("chrom", C.POINTER(C.c_char_p)), ("name", C.POINTER(C.c_char_p)), ("region_start", c_i32p),
+                ("region_stop", c_i32p), ("period", c_i32p), ("chrom_seq", C.POINTER(C.c_char_p)),
+                ("locus_sample_names", C.POINTER(C.c_char_p)), ("n_out_samples", C.c_int32),
+                ("out_sample_names", C.POINTER(C.c_char_p))]
+
+
+class VcfOptions(C.Structure):
+    """hipstr_vcf_options_t"""
+    _fields_ = [("output_gls", C.c_int32), ("output_pls", C.c_int32), ("output_phased_gls", C.c_int32),
+                ("output_allreads", C.c_int32), ("output_mallreads", C.c_int32), ("output_filters", C.c_int32),
+                ("output_haplotype_data", C.c_int32), ("max_flank_indel_frac", C.c_double)]
 
 
 class GenotypeOut(C.Structure):
@@ -315,6 +330,14 @@ def load():
     lib.hipstr_genotyper_locus_blocks.argtypes = [vp, C.c_int32, c_i32p, c_i32p, C.c_void_p]
     lib.hipstr_genotyper_locus_results.restype = C.c_int32
     lib.hipstr_genotyper_locus_results.argtypes = [vp, C.c_int32, c_f64p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_u8p]
+    lib.hipstr_vcf_default_options.restype = None
+    lib.hipstr_vcf_default_options.argtypes = [C.POINTER(VcfOptions)]
+    lib.hipstr_genotyper_write_vcf.restype = C.c_int32
+    lib.hipstr_genotyper_write_vcf.argtypes = [vp, C.POINTER(VcfLoci), C.POINTER(VcfOptions)]
+    lib.hipstr_genotyper_locus_record.restype = C.c_int32
+    lib.hipstr_genotyper_locus_record.argtypes = [vp, C.c_int32, c_i32p, C.c_void_p, C.c_int32]
+    lib.hipstr_genotyper_emit_records.restype = C.c_int32
+    lib.hipstr_genotyper_emit_records.argtypes = [vp, C.POINTER(VcfLoci), vp]
     lib.hipstr_genotyper_locus_log.restype = C.c_int32
     lib.hipstr_genotyper_locus_log.argtypes = [vp, C.c_int32, C.c_void_p, C.c_int32]
     lib.hipstr_collect_timing.restype = C.c_int32
@@ -465,7 +488,7 @@ class Genotyper:
         v = synth.view
         rs = LocusReadsStruct(v.locus_read_off, v.locus_sample_off, v.read_seq_off, v.read_bases, v.read_quals, v.read_start,
                               v.read_cigar_off, v.read_cigar_type, v.read_cigar_len, v.sample_label, v.read_name_id,
-                              v.log_p1, v.log_p2, v.haploid)
+                              v.log_p1, v.log_p2, v.haploid, v.read_rev_strand)
         if loci_blocks is None:
             b = synth.batch
             bs = _np(v.block_start, b.n_blocks, np.int32)
@@ -520,6 +543,39 @@ class Genotyper:
         o["post"] = o["post"].reshape(S, H, H)
         o["best"] = o["best"].reshape(S, 2)
         return o
+
+    def vcf_loci(self, chroms, names, region_start, region_stop, period, chrom_seqs, locus_sample_names, out_sample_names):
+        """Build a hipstr_vcf_loci_t (lists of str / bytes per locus; sample names flattened over loci)."""
+        def arr(xs):
+            xs = [x if isinstance(x, bytes) else x.encode() for x in xs]
+            a = (C.c_char_p * len(xs))(*xs)
+            a._keep = xs
+            return a
+        keep = [arr(chroms), arr(names), np.ascontiguousarray(region_start, np.int32), np.ascontiguousarray(region_stop, np.int32),
+                np.ascontiguousarray(period, np.int32), arr(chrom_seqs), arr(locus_sample_names), arr(out_sample_names)]
+        v = VcfLoci(keep[0], keep[1], ptr(keep[2], c_i32p), ptr(keep[3], c_i32p), ptr(keep[4], c_i32p), keep[5], keep[6],
+                    len(out_sample_names), keep[7])
+        v._keep = keep
+        return v
+
+    def write_vcf(self, loci, **options):
+        """hipstr_genotyper_write_vcf; options override hipstr_vcf_default_options. Returns [(pos, text) or None] per locus."""
+        opt = VcfOptions()
+        self.lib.hipstr_vcf_default_options(C.byref(opt))
+        for k, val in options.items():
+            setattr(opt, k, val)
+        st = self.lib.hipstr_genotyper_write_vcf(self.h, C.byref(loci), C.byref(opt))
+        if st != 0:
+            raise HipstrError(st, "genotyper_write_vcf: " + (self.lib.hipstr_genotyper_last_error(self.h) or b"").decode())
+        out = []
+        buf = np.zeros(1 << 22, np.uint8)
+        for l in range(self.n_loci):
+            pos = C.c_int32()
+            n = self.lib.hipstr_genotyper_locus_record(self.h, l, C.byref(pos), buf.ctypes.data, len(buf))
+            if n < 0:
+                raise HipstrError(3, "record of locus %d needs %d bytes" % (l, -n))
+            out.append((pos.value, bytes(buf[:n]).decode()) if n > 0 else None)
+        return out
 
     def log(self, l):
         buf = np.zeros(1 << 16, np.uint8)

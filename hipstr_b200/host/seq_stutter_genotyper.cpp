@@ -209,6 +209,7 @@ int SeqStutterGenotyper::best_hap_of_read(int r) const {
 
 bool SeqStutterGenotyper::collect_missing_traces() {
   missing_traces_.clear();
+  missing_trace_read_.clear();
   std::set<std::pair<int, int> > wanted;
   for (int r = 0; r < num_reads_; r++) {
     if (seed_positions_[r] < 0) continue;
@@ -553,7 +554,9 @@ struct PackedBatch {
   std::vector<uint8_t> realign_pool, realign_hap;
   bool pool_masked = false, hap_masked = false;
 
-  void add(const SeqStutterGenotyper& g, const std::vector<uint8_t>* hap_mask, const std::vector<uint8_t>* pool_mask) {
+  /* own_quality_reads: reads appended as extra pools that carry their own qualities (and their pool's seed) */
+  void add(const SeqStutterGenotyper& g, const std::vector<uint8_t>* hap_mask, const std::vector<uint8_t>* pool_mask,
+           const std::vector<int>* own_quality_reads = nullptr) {
     for (const HapBlock& b : g.hap_blocks_) {
       block_period.push_back(b.period);
       block_start.push_back(b.start);
@@ -572,6 +575,17 @@ struct PackedBatch {
       realign_pool.push_back(m);
       pool_masked |= (m == 0);
     }
+    int extra = 0;
+    if (own_quality_reads)
+      for (int r : *own_quality_reads) {
+        const int p = g.pool_index_[r];
+        pool_bases.append(g.pool_bases_, g.pool_seq_off_[p], g.pool_seq_off_[p + 1] - g.pool_seq_off_[p]);
+        pool_quals.append(g.read_quals_, g.read_seq_off_[r], g.read_seq_off_[r + 1] - g.read_seq_off_[r]);
+        pool_seq_off.push_back((int32_t)pool_bases.size());
+        pool_seed.push_back(g.pool_seed_[p]);
+        realign_pool.push_back(1);
+        extra++;
+      }
     locus_pool_off.push_back((int32_t)pool_seed.size());
     for (int h = 0; h < g.num_alleles_; h++) {
       const uint8_t m = (hap_mask && !hap_mask->empty()) ? (*hap_mask)[h] : 1;
@@ -579,7 +593,7 @@ struct PackedBatch {
       hap_masked |= (m == 0);
     }
     locus_hap_off.push_back(locus_hap_off.back() + g.num_alleles_);
-    locus_out_off.push_back(locus_out_off.back() + (int64_t)g.num_pools_ * g.num_alleles_);
+    locus_out_off.push_back(locus_out_off.back() + (int64_t)(g.num_pools_ + extra) * g.num_alleles_);
   }
 
   hipstr_align_batch_t view() const {
@@ -688,6 +702,8 @@ hipstr_status_t GenotyperBatch::add_loci(const hipstr_align_batch_t* bt, const i
     g.log_p1_.assign(rd->log_p1 + r0, rd->log_p1 + r1);
     g.log_p2_.assign(rd->log_p2 + r0, rd->log_p2 + r1);
     g.read_start_.assign(rd->read_start + r0, rd->read_start + r1);
+    if (rd->rev_strand) g.rev_strand_.assign(rd->rev_strand + r0, rd->rev_strand + r1);
+    else g.rev_strand_.assign(R, 0);
     // init(): a read is a second mate when it carries the name of the read before it (.cpp:495-503)
     g.second_mate_.resize(R);
     g.read_weights_.resize(R);
@@ -704,6 +720,8 @@ hipstr_status_t GenotyperBatch::add_loci(const hipstr_align_batch_t* bt, const i
     for (int r = 0; r <= R; r++) seq_off[r] = rd->read_seq_off[r0 + r] - rd->read_seq_off[r0];
     const char* bases = rd->bases + rd->read_seq_off[r0];
     const char* quals = rd->quals + rd->read_seq_off[r0];
+    g.read_seq_off_ = seq_off;
+    g.read_quals_.assign(quals, quals + seq_off[R]);
     g.pool_index_.resize(R);
     std::vector<int32_t> first(std::max(R, 1));
     g.pool_seq_off_.resize(R + 1);
@@ -813,7 +831,10 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
       SeqStutterGenotyper& g = loci[which[li]];
       if (ti >= g.missing_traces_.size()) { li++; ti = 0; continue; }
       const int32_t pool_base = (int32_t)pb.pool_seed.size();
-      pb.add(g, nullptr, nullptr);
+      std::vector<int> own;   // reads traced with their own qualities become extra pools of this locus
+      if (!g.missing_trace_read_.empty())
+        for (size_t t = ti; t < g.missing_traces_.size() && trace_pool.size() + (t - ti) < kChunk; t++) own.push_back(g.missing_trace_read_[t]);
+      pb.add(g, nullptr, nullptr, &own);
       for (int p = 0; p < g.num_pools_; p++) max_read = std::max(max_read, g.pool_seq_off_[p + 1] - g.pool_seq_off_[p]);
       int32_t longest = 0;
       for (const HapBlock& b : g.hap_blocks_) {
@@ -822,8 +843,8 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
         longest += (int32_t)m;
       }
       max_hap = std::max(max_hap, longest);
-      for (; ti < g.missing_traces_.size() && trace_pool.size() < kChunk; ti++) {
-        trace_pool.push_back(pool_base + g.missing_traces_[ti].first);
+      for (size_t first = ti; ti < g.missing_traces_.size() && trace_pool.size() < kChunk; ti++) {
+        trace_pool.push_back(pool_base + (own.empty() ? g.missing_traces_[ti].first : g.num_pools_ + (int)(ti - first)));
         trace_hap.push_back(g.missing_traces_[ti].second);
         owner.emplace_back(which[li], (int)ti);
       }
@@ -886,7 +907,7 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
       g.trace_cache_[key] = std::move(t);
     }
   }
-  for (int l : which) loci[l].missing_traces_.clear();
+  for (int l : which) { loci[l].missing_traces_.clear(); loci[l].missing_trace_read_.clear(); }
   return HIPSTR_OK;
 }
 
@@ -942,12 +963,6 @@ hipstr_status_t GenotyperBatch::genotype(int max_total_haplotypes, int max_flank
 }  // namespace hipstr
 
 /* ---- C-ABI ------------------------------------------------------------------------------------------ */
-struct hipstr_genotyper {
-  hipstr::GenotyperBatch batch;
-  std::string last_error;
-  explicit hipstr_genotyper(hipstr_ctx_t* ctx) : batch(ctx) {}
-};
-
 extern "C" {
 
 hipstr_status_t hipstr_hap_aln_to_ref(const char* ref_hap, const char* alt_hap, int32_t first_block_start,

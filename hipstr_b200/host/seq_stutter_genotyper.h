@@ -79,6 +79,9 @@ class SeqStutterGenotyper {
   std::vector<double> log_p1_, log_p2_;
   std::vector<int32_t> read_start_, read_cigar_off_, read_cigar_len_;
   std::vector<char> read_cigar_type_;
+  std::vector<uint8_t> rev_strand_;            /* Alignment::is_from_reverse_strand() */
+  std::vector<int32_t> read_seq_off_;          /* [R+1] into read_quals_ */
+  std::string read_quals_;                     /* the reads' own base qualities (pools carry the medians) */
   /* pooled reads (ReadPooler) */
   int num_pools_ = 0;
   std::vector<int32_t> pool_seq_off_, pool_seed_;
@@ -91,7 +94,15 @@ class SeqStutterGenotyper {
   std::vector<std::string> call_sample_;       /* non-empty = sample not genotyped, with the reason */
   std::map<std::pair<int, int>, AlignmentTrace> trace_cache_;   /* (pool, haplotype) -> trace */
   std::string log_;
+  std::string vcf_record_;                     /* text of the last write_vcf_record */
+  int32_t vcf_pos_ = 0;                        /* its POS */
   int rounds_ = 0;                             /* alignment rounds run (1 = no allele discovery) */
+
+  /* write_vcf_record (.cpp:995-1510) in two steps around one batched trace call */
+  struct ReadCall { int best_hap; int read_strand; double log_phase_one; bool unique; };
+  std::vector<ReadCall> vcf_calls_;
+  void vcf_prepare(const int32_t* best_hap);   /* per-read strand / haplotype assignment, lists missing traces */
+  bool reassemble_flanks() const { return reassemble_flanks_; }
 
   Phase phase() const { return phase_; }
   bool succeeded() const { return phase_ == DONE; }
@@ -108,6 +119,10 @@ class SeqStutterGenotyper {
   /* pending device work */
   std::vector<uint8_t> realign_hap_, realign_pool_, copy_read_;   /* masks of the pending alignment */
   std::vector<std::pair<int, int> > missing_traces_;
+  /* write_vcf_record traces a read with ITS OWN qualities when its (pool, haplotype) trace is not cached
+   * (.cpp:1118 passes alns_[read_index], retrace_alignments :831 the pooled read): the read whose qualities
+   * to use per missing trace, empty = pooled qualities */
+  std::vector<int> missing_trace_read_;
 
   Request advance();                                   /* runs host logic until device work is needed */
   int best_hap_of_read(int read) const;                /* retrace_alignments, .cpp:825-827 */
@@ -140,8 +155,12 @@ class GenotyperBatch {
   std::vector<SeqStutterGenotyper> loci;
   int64_t n_alignments = 0, n_traces = 0;
   int n_rounds = 0;
-  /* Ensure traces for arbitrary (locus, pool, haplotype) keys (used by write_vcf_record). */
   hipstr_status_t run_traces(const std::vector<int>& which, std::string& err);
+  /* write_vcf_record of every successfully genotyped locus (seq_stutter_genotyper.h:179-181, impl .cpp:984-1510,
+   * get_alleles :691-769, reorder_alleles :673-689, compute_allele_bias :965-982): K3b marginalises the posteriors of
+   * all loci in one call, K5 traces the reads whose strand-assigned haplotype is not cached yet, then each record is
+   * formatted on the host.  Records are kept in vcf_record_ / vcf_pos_ of each locus. */
+  hipstr_status_t write_vcf_records(const hipstr_vcf_loci_t* regions, const hipstr_vcf_options_t* options, std::string& err);
 
  private:
   hipstr_ctx_t* ctx_;
@@ -150,4 +169,11 @@ class GenotyperBatch {
 };
 
 }  // namespace hipstr
+
+/* the opaque handle of the C-ABI */
+struct hipstr_genotyper {
+  hipstr::GenotyperBatch batch;
+  std::string last_error;
+  explicit hipstr_genotyper(hipstr_ctx_t* ctx) : batch(ctx) {}
+};
 #endif

@@ -27,7 +27,7 @@ struct hipstr_synth {
   std::vector<double> block_stutter;
   std::vector<char> opt_seq, pool_bases, pool_quals;
   std::vector<int32_t> locus_read_off, locus_sample_off, pool_index, sample_label, read_weight, n_haps, true_gt, read_bp_diff;
-  std::vector<uint8_t> second_mate, haploid;
+  std::vector<uint8_t> second_mate, haploid, read_rev_strand;
   std::vector<double> log_p1, log_p2;
   std::vector<int32_t> read_seq_off, read_start, read_cigar_off, read_cigar_len, read_name_id, block_start, block_end;
   std::vector<char> read_bases, read_quals, read_cigar_type, chrom_seqs;
@@ -238,6 +238,7 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
       S->read_cigar_off.push_back((int32_t)S->read_cigar_type.size());
       if (!mates[r]) next_name++;
       S->read_name_id.push_back(next_name);
+      S->read_rev_strand.push_back((uint8_t)((((uint32_t)S->read_name_id.size() * 2654435761u) >> 13) & 1));
     }
     S->locus_read_off.push_back((int32_t)S->pool_index.size());
     S->locus_sample_off.push_back(S->locus_sample_off.back() + cfg.n_samples);
@@ -298,6 +299,7 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
   S->view.chrom_seqs = S->chrom_seqs.data();
   S->view.region_start = kStrStart;
   S->view.region_stop = str_end;
+  S->view.read_rev_strand = S->read_rev_strand.data();
   return S;
 }
 

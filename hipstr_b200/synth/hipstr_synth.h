@@ -60,6 +60,7 @@ typedef struct {
   int32_t chrom_len;               /* every locus has its own chromosome of this length */
   const char* chrom_seqs;          /* [n_loci][chrom_len] */
   int32_t region_start, region_stop; /* the STR Region of every locus */
+  const uint8_t* read_rev_strand;  /* [n_reads] Alignment::is_from_reverse_strand(): a hash of the read index */
 } hipstr_synth_view_t;
 
 typedef struct hipstr_synth hipstr_synth_t;

@@ -401,6 +401,7 @@ typedef struct hipstr_locus_reads {
   const double*  log_p1;            /* [R]                                                     */
   const double*  log_p2;            /* [R]                                                     */
   const uint8_t* haploid;           /* [n_loci]                                                */
+  const uint8_t* rev_strand;        /* [R] Alignment::is_from_reverse_strand(), NULL = all forward */
 } hipstr_locus_reads_t;
 
 typedef struct hipstr_genotyper hipstr_genotyper_t;
@@ -432,6 +433,49 @@ hipstr_status_t hipstr_genotyper_locus_results(const hipstr_genotyper_t* g, int3
                                                double* sample_ll, int32_t* best, uint8_t* call_sample_ok);
 int32_t         hipstr_genotyper_locus_log(const hipstr_genotyper_t* g, int32_t locus, char* out, int32_t cap);
 
+/* --- a18: write_vcf_record for every genotyped locus -----------------------------
+ * Replaces SeqStutterGenotyper::write_vcf_record (seq_stutter_genotyper.h:179-181, impl
+ * seq_stutter_genotyper.cpp:984-1510) with get_alleles (:691-769), reorder_alleles (:673-689),
+ * compute_allele_bias (:965-982), ExtractCigar (extract_indels.cpp:18-90) and
+ * Genotyper::condense_read_counts (genotyper.h:51-64).  One K3b call marginalises the
+ * posteriors of all loci, one K5 call traces the reads whose strand-assigned haplotype has no
+ * cached trace, then the text is formatted on the host exactly as the reference prints it
+ * (fixed, 2 decimals).  Loci whose genotype() failed produce no record (the reference skips
+ * write_vcf_record for them, genotyper_bam_processor.cpp:232-246).  One STR region per locus.
+ * The OUTPUT_* switches are the reference's static Genotyper flags (genotyper.cpp:336-343);
+ * hipstr_vcf_default_options() returns their defaults.  HTML visualisation is not produced. */
+typedef struct hipstr_vcf_loci {
+  const char* const* chrom;          /* [n_loci] Region::chrom()                                */
+  const char* const* name;           /* [n_loci] Region::name(), "" or NULL -> "."              */
+  const int32_t* region_start;       /* [n_loci] Region::start()                                */
+  const int32_t* region_stop;        /* [n_loci] Region::stop()                                 */
+  const int32_t* period;             /* [n_loci] Region::period()                               */
+  const char* const* chrom_seq;      /* [n_loci] chromosome sequence the coordinates index into */
+  const char* const* locus_sample_names; /* [total samples] the genotyper's sample_names_, per locus */
+  int32_t n_out_samples;             /* samples_to_genotype: the VCF's sample columns           */
+  const char* const* out_sample_names;
+} hipstr_vcf_loci_t;
+typedef struct hipstr_vcf_options {
+  int32_t output_gls, output_pls, output_phased_gls, output_allreads, output_mallreads, output_filters,
+          output_haplotype_data;
+  double max_flank_indel_frac;
+} hipstr_vcf_options_t;
+void hipstr_vcf_default_options(hipstr_vcf_options_t* o);
+hipstr_status_t hipstr_genotyper_write_vcf(hipstr_genotyper_t* g, const hipstr_vcf_loci_t* loci,
+                                           const hipstr_vcf_options_t* options);
+/* the record of one locus (empty when the locus produced none); returns its length or -needed */
+int32_t         hipstr_genotyper_locus_record(const hipstr_genotyper_t* g, int32_t locus, int32_t* pos, char* out, int32_t cap);
+
+/* Pure host arithmetic of write_vcf_record, exported so that it can be checked on its own:
+ *   hipstr_allele_bias       compute_allele_bias (seq_stutter_genotyper.cpp:965-982): log10 of the two-sided
+ *                            binomial p-value of the read split (the reference uses cephes bdtr, lib/cephes/bdtr.c)
+ *   hipstr_fisher_two_sided  the `two` output of kt_fisher_exact (htslib 1.9 kfunc.c:196-279)
+ *   hipstr_extract_cigar     ExtractCigar (extract_indels.cpp:18-90): 1 and *bp_diff if the read spans the window */
+double  hipstr_allele_bias(int32_t hap_a_reads, int32_t hap_b_reads);
+double  hipstr_fisher_two_sided(int32_t n11, int32_t n12, int32_t n21, int32_t n22);
+int32_t hipstr_extract_cigar(const char* cigar_type, const int32_t* cigar_len, int32_t n, int32_t cigar_start,
+                             int32_t region_start, int32_t region_end, int32_t* bp_diff);
+
 /* Haplotype::aln_haps_to_ref for one haplotype (SeqAlignment/Haplotype.cpp:8-86 on top of
  * NeedlemanWunsch::Align, NeedlemanWunsch.cpp:84-423): one of 'M','I','D' per alignment column
  * of alt_hap against ref_hap -- the string hipstr_stitch_trace consumes.  Pure host logic. */
@@ -446,6 +490,9 @@ hipstr_status_t hipstr_hap_aln_to_ref(const char* ref_hap, const char* alt_hap, 
  * bgzfostream produces), anything else as plain text.  The C++ class with the reference's
  * method names is hipstr::VCFWriter (hipstr_b200/host/vcf_writer.h). */
 typedef struct hipstr_vcf_writer hipstr_vcf_writer_t;
+/* feed the records of hipstr_genotyper_write_vcf to a writer, in locus order (VCFWriter::add_vcf_record) */
+hipstr_status_t hipstr_genotyper_emit_records(const hipstr_genotyper_t* g, const hipstr_vcf_loci_t* loci,
+                                              hipstr_vcf_writer_t* w);
 hipstr_vcf_writer_t* hipstr_vcf_writer_open(const char* path);   /* NULL if the file cannot be created */
 hipstr_status_t hipstr_vcf_writer_header(hipstr_vcf_writer_t* w, const char* header_text);
 hipstr_status_t hipstr_vcf_writer_add_record(hipstr_vcf_writer_t* w, const char* chrom, int32_t pos,

@@ -33,6 +33,11 @@
 #include "mathops.h"
 #include "region.h"
 #include "stutter_model.h"
+#include "extract_indels.h"
+#include "cephes/cephes.h"
+#include "htslib/htslib/kfunc.h"
+#include <cmath>
+#include <algorithm>
 
 namespace {
 
@@ -65,7 +70,8 @@ void* ref_sg_create(int32_t n_samples, int32_t n_reads, const int32_t* sample_la
                     const int32_t* read_start, const int32_t* seq_off, const char* bases, const char* quals,
                     const int32_t* cigar_off, const char* cigar_type, const int32_t* cigar_len, const double* log_p1,
                     const double* log_p2, const char* chrom_seq, int32_t region_start, int32_t region_stop,
-                    int32_t period, const double* stutter, int32_t haploid, int32_t reassemble_flanks) {
+                    int32_t period, const double* stutter, int32_t haploid, int32_t reassemble_flanks,
+                    const uint8_t* rev_strand) {
   ensure_init();
   RefSG* h = new RefSG();
   h->chrom_seq = chrom_seq;
@@ -88,7 +94,7 @@ void* ref_sg_create(int32_t n_samples, int32_t n_reads, const int32_t* sample_la
         if (cigar_type[c] != 'I') pos += cigar_len[c];
       }
     }
-    Alignment a(read_start[r], pos, false, "r" + std::to_string(name_id[r]), q, seq, gapped);
+    Alignment a(read_start[r], pos, rev_strand != NULL && rev_strand[r] != 0, "r" + std::to_string(name_id[r]), q, seq, gapped);
     a.set_cigar_list(cig);
     a.set_hap_gen_info(std::vector<bool>(1, true));
     alns.push_back(a);
@@ -159,6 +165,14 @@ void ref_sg_results(void* hv, double* read_ll, int32_t* seeds, int32_t* pool_ind
 
 /* write_vcf_record into a string: the record(s) are taken from the writer's reorder heap, so no
  * BGZF stream is ever opened.  Returns the number of bytes (excluding NUL), or -needed if cap is short. */
+/* flags = the static Genotyper::OUTPUT_* switches: {GLS, PLS, PHASED_GLS, ALLREADS, MALLREADS, FILTERS, HAPLOTYPE_DATA} */
+void ref_sg_set_output_flags(const int32_t* flags, double max_flank_indel_frac) {
+  Genotyper::OUTPUT_GLS = flags[0]; Genotyper::OUTPUT_PLS = flags[1]; Genotyper::OUTPUT_PHASED_GLS = flags[2];
+  Genotyper::OUTPUT_ALLREADS = flags[3]; Genotyper::OUTPUT_MALLREADS = flags[4]; Genotyper::OUTPUT_FILTERS = flags[5];
+  Genotyper::OUTPUT_HAPLOTYPE_DATA = flags[6];
+  Genotyper::MAX_FLANK_INDEL_FRAC = (float)max_flank_indel_frac;
+}
+
 int32_t ref_sg_write_vcf(void* hv, char* out, int32_t cap) {
   RefSG* h = static_cast<RefSG*>(hv);
   VCFWriter w;
@@ -179,6 +193,28 @@ int32_t ref_sg_write_vcf(void* hv, char* out, int32_t cap) {
   if ((int32_t)text.size() + 1 > cap) return -(int32_t)text.size() - 1;
   std::memcpy(out, text.c_str(), text.size() + 1);
   return (int32_t)text.size();
+}
+
+/* the third-party arithmetic behind AB / FS and the CIGAR window of ALLREADS, called directly */
+double ref_allele_bias(int32_t a, int32_t b) {
+  const int total = a + b;
+  if (total == 0) return 1;
+  if (a == b) return 0.0;
+  return log10(std::min(1.0, 2 * bdtr(std::min(a, b), total, 0.5)));   // compute_allele_bias is private: same three lines
+}
+double ref_fisher_two_sided(int32_t n11, int32_t n12, int32_t n21, int32_t n22) {
+  double left, right, two;
+  kt_fisher_exact(n11, n12, n21, n22, &left, &right, &two);
+  return two;
+}
+int32_t ref_extract_cigar(const char* type, const int32_t* len, int32_t n, int32_t cigar_start, int32_t region_start,
+                          int32_t region_end, int32_t* bp_diff) {
+  std::vector<CigarElement> cig;
+  for (int i = 0; i < n; i++) cig.push_back(CigarElement(type[i], len[i]));
+  int d = 0;
+  const bool ok = ExtractCigar(cig, cigar_start, region_start, region_end, d);
+  *bp_diff = d;
+  return ok ? 1 : 0;
 }
 
 /* The log the reference wrote for this locus (diagnostics in test failures). */

@@ -16,7 +16,9 @@ def bind(lib):
     lib.ref_sg_create.restype = C.c_void_p
     lib.ref_sg_create.argtypes = [C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_void_p, c_i32p,
                                   C.c_void_p, c_i32p, c_f64p, c_f64p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32,
-                                  c_f64p, C.c_int32, C.c_int32]
+                                  c_f64p, C.c_int32, C.c_int32, c_u8p]
+    lib.ref_sg_set_output_flags.restype = None
+    lib.ref_sg_set_output_flags.argtypes = [c_i32p, C.c_double]
     for name in ("destroy",):
         getattr(lib, "ref_sg_" + name).restype = None
         getattr(lib, "ref_sg_" + name).argtypes = [C.c_void_p]
@@ -68,6 +70,7 @@ class LocusReads:
         self.log_p1 = synth.log_p1[r0:r1].copy()
         self.log_p2 = synth.log_p2[r0:r1].copy()
         self.second_mate = synth.second_mate[r0:r1].copy()
+        self.rev_strand = _np(v.read_rev_strand, R, np.uint8)[r0:r1].copy()
         cl = int(v.chrom_len)
         chrom = np.ctypeslib.as_array(C.cast(v.chrom_seqs, C.POINTER(C.c_uint8)), shape=(synth.n_loci * cl,))
         self.chrom_seq = bytes(chrom[l * cl:(l + 1) * cl])
@@ -88,7 +91,7 @@ class RefGenotyper:
             ptr(reads.start, c_i32p), ptr(reads.seq_off, c_i32p), reads.bases.ctypes.data, reads.quals.ctypes.data,
             ptr(reads.cigar_off, c_i32p), reads.cigar_type.ctypes.data, ptr(reads.cigar_len, c_i32p),
             ptr(reads.log_p1, c_f64p), ptr(reads.log_p2, c_f64p), reads.chrom_seq, reads.region[0], reads.region[1],
-            reads.period, ptr(st, c_f64p), reads.haploid, int(reassemble_flanks))
+            reads.period, ptr(st, c_f64p), reads.haploid, int(reassemble_flanks), ptr(reads.rev_strand, c_u8p))
         self.initialized = bool(self.lib.ref_sg_initialized(self.h))
 
     def blocks(self):
@@ -121,7 +124,11 @@ class RefGenotyper:
         o["best"] = o["best"].reshape(S, 2)
         return o
 
-    def vcf(self):
+    def vcf(self, output_gls=0, output_pls=0, output_phased_gls=0, output_allreads=1, output_mallreads=1, output_filters=0,
+            output_haplotype_data=0, max_flank_indel_frac=0.15):
+        flags = np.array([output_gls, output_pls, output_phased_gls, output_allreads, output_mallreads, output_filters,
+                          output_haplotype_data], np.int32)
+        self.lib.ref_sg_set_output_flags(ptr(flags, c_i32p), max_flank_indel_frac)
         buf = np.zeros(1 << 22, np.uint8)
         n = self.lib.ref_sg_write_vcf(self.h, buf.ctypes.data, len(buf))
         assert n >= 0

@@ -1,0 +1,115 @@
+"""a18: write_vcf_record.  CPU: the host arithmetic behind AB / FS / ALLREADS against the reference's third-party
+functions (cephes bdtr, htslib kt_fisher_exact) and ExtractCigar.  GPU: the full VCF record text of every locus --
+after the same genotype() loop -- must equal the text the UNMODIFIED reference writes, character for character."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import checkers
+from hipstr_b200.capi import Synth, c_i32p, load, ptr
+
+needs_ref = pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libhipstr_ref.so not built")
+
+
+def _bind(lib, prefix):
+    f = getattr(lib, prefix + "allele_bias"); f.restype = C.c_double; f.argtypes = [C.c_int32, C.c_int32]
+    f = getattr(lib, prefix + "fisher_two_sided"); f.restype = C.c_double; f.argtypes = [C.c_int32] * 4
+    f = getattr(lib, prefix + "extract_cigar"); f.restype = C.c_int32
+    f.argtypes = [C.c_char_p, c_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32p]
+    return lib
+
+
+@needs_ref
+def test_allele_and_strand_bias_match_third_party_functions():
+    got, want = _bind(load(), "hipstr_"), _bind(checkers.ref(), "ref_")
+    rng = np.random.default_rng(3)
+    for a, b in [(0, 0), (5, 5), (0, 7), (1, 30), (12, 20), (100, 160), (3, 2)] + [tuple(rng.integers(0, 80, 2)) for _ in range(300)]:
+        x, y = got.hipstr_allele_bias(int(a), int(b)), want.ref_allele_bias(int(a), int(b))
+        assert abs(x - y) <= 1e-9 * max(1.0, abs(y)), (a, b, x, y)
+    for t in [(0, 0, 0, 0), (3, 0, 0, 3), (10, 10, 10, 10), (1, 9, 8, 2), (0, 5, 5, 0)] + [tuple(rng.integers(0, 40, 4)) for _ in range(300)]:
+        t = tuple(int(v) for v in t)
+        x, y = got.hipstr_fisher_two_sided(*t), want.ref_fisher_two_sided(*t)
+        assert abs(x - y) <= 1e-9, (t, x, y)
+
+
+@needs_ref
+def test_extract_cigar_matches_reference():
+    got, want = _bind(load(), "hipstr_"), _bind(checkers.ref(), "ref_")
+    rng = np.random.default_rng(5)
+    n_true = 0
+    for _ in range(2000):
+        n = int(rng.integers(1, 7))
+        types = bytes(rng.choice(list(b"=XID="), n))
+        lens = rng.integers(1, 60, n).astype(np.int32)
+        start = int(rng.integers(900, 1000))
+        rs = start + int(rng.integers(-5, 90))
+        re = rs + int(rng.integers(0, 40))
+        a, b = C.c_int32(), C.c_int32()
+        x = got.hipstr_extract_cigar(types, ptr(lens, c_i32p), n, start, rs, re, C.byref(a))
+        y = want.ref_extract_cigar(types, ptr(lens, c_i32p), n, start, rs, re, C.byref(b))
+        assert x == y and (not x or a.value == b.value), (types, lens, start, rs, re)
+        n_true += x
+    assert n_true > 100
+
+
+VCF_CASES = [
+    ("plain", dict(n_loci=3, n_samples=10, reads_per_sample=20, n_alleles=6, read_len=100, seed=5), {}),
+    ("all_fields", dict(n_loci=3, n_samples=6, reads_per_sample=15, n_alleles=4, read_len=110, seed=7, stutter_rate=0.2),
+     dict(output_gls=1, output_pls=1, output_phased_gls=1, output_filters=1)),
+    ("assembly_flank_snps_haplotype_data", dict(n_loci=3, n_samples=8, reads_per_sample=20, n_alleles=4, read_len=120, seed=71,
+                                                flank_snp_freq=0.3, assemble=True), dict(output_haplotype_data=1, output_gls=1)),
+    ("assembly_masked_samples", dict(n_loci=4, n_samples=30, reads_per_sample=10, n_alleles=4, read_len=120, seed=81, flank_snp_freq=0.03,
+                                     assemble=True, min_flank_freq=0.1), dict(output_filters=1)),
+    ("mates_and_stutter", dict(n_loci=3, n_samples=6, reads_per_sample=8, n_alleles=4, read_len=110, seed=51, mate_rate=0.5,
+                               stutter_rate=0.25, assemble=True), {}),
+    ("low_coverage_some_empty_samples", dict(n_loci=4, n_samples=25, reads_per_sample=2, n_alleles=6, read_len=150, seed=33, assemble=True),
+     dict(output_filters=1, output_pls=1)),
+    ("period2", dict(n_loci=3, n_samples=6, reads_per_sample=15, n_alleles=5, read_len=110, seed=41, period=2, ref_copies=15,
+                     stutter_rate=0.3, sub_rate=0.02, assemble=True), {}),
+]
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw,opts", VCF_CASES, ids=[c[0] for c in VCF_CASES])
+def test_vcf_record_text_matches_reference(name, kw, opts):
+    from hipstr_b200.capi import Context, Genotyper
+    from ref_genotyper import LocusReads, RefGenotyper
+    kw = dict(kw)
+    assemble, min_flank_freq = kw.pop("assemble", False), kw.pop("min_flank_freq", 0.01)
+    s = Synth(**kw)
+    refs, blocks0, reads = [], [], []
+    for l in range(s.n_loci):
+        rd = LocusReads(s, l)
+        r = RefGenotyper(rd, reassemble_flanks=assemble)
+        assert r.initialized
+        refs.append(r)
+        reads.append(rd)
+        blocks0.append(r.blocks())
+    ctx = Context(0)
+    g = Genotyper.from_synth(ctx, s, blocks0)
+    ok = g.genotype(1000, 4, min_flank_freq, assemble)
+    S = reads[0].n_samples
+    names = ["S%d" % i for i in range(S)]
+    loci = g.vcf_loci(["chrS"] * s.n_loci, ["STR"] * s.n_loci, [rd.region[0] for rd in reads], [rd.region[1] for rd in reads],
+                      [rd.period for rd in reads], [rd.chrom_seq for rd in reads], names * s.n_loci, names)
+    records = g.write_vcf(loci, **opts)
+    n_checked = 0
+    for l in range(s.n_loci):
+        assert bool(ok[l]) == refs[l].genotype(1000, 4, min_flank_freq)
+        if not ok[l]:
+            assert records[l] is None
+            continue
+        want = refs[l].vcf(**opts).rstrip("\n")
+        pos, got = records[l]
+        if got != want:
+            gf, wf = got.split("\t"), want.split("\t")
+            diff = [(i, a, b) for i, (a, b) in enumerate(zip(gf, wf)) if a != b]
+            print("locus %d: %d differing columns, first: %s" % (l, len(diff), diff[:3]))
+        assert got == want, l
+        assert pos == int(want.split("\t")[1])
+        n_checked += 1
+    assert n_checked > 0
+    g.close()
+    ctx.close()
