@@ -53,6 +53,13 @@ def test_extract_cigar_matches_reference():
     assert n_true > 100
 
 
+def _canon(text):
+    """The reference prints AB = log10(min(1, 2 * bdtr(k, n, 0.5))); where the p-value is mathematically 1 cephes'
+    incomplete-beta series lands a few ulp either side of it, so the reference itself prints "0.00" or "-0.00" depending
+    on rounding noise of a third-party routine.  The two are the same number: compare them as equal."""
+    return text.replace(":-0.00:", ":0.00:")
+
+
 VCF_CASES = [
     ("plain", dict(n_loci=3, n_samples=10, reads_per_sample=20, n_alleles=6, read_len=100, seed=5), {}),
     ("all_fields", dict(n_loci=3, n_samples=6, reads_per_sample=15, n_alleles=4, read_len=110, seed=7, stutter_rate=0.2),
@@ -101,12 +108,13 @@ def test_vcf_record_text_matches_reference(name, kw, opts):
         if not ok[l]:
             assert records[l] is None
             continue
-        want = refs[l].vcf(**opts).rstrip("\n")
+        want = _canon(refs[l].vcf(**opts).rstrip("\n"))
         pos, got = records[l]
+        got = _canon(got)
         if got != want:
             gf, wf = got.split("\t"), want.split("\t")
             diff = [(i, a, b) for i, (a, b) in enumerate(zip(gf, wf)) if a != b]
-            print("locus %d: %d differing columns, first: %s" % (l, len(diff), diff[:3]))
+            print("DIFF %s locus %d: %d differing columns (got, want): %s" % (name, l, len(diff), diff[:3]))
         assert got == want, l
         assert pos == int(want.split("\t")[1])
         n_checked += 1
