@@ -316,6 +316,9 @@ def load():
     lib.hipstr_hap_aln_to_ref.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p]
     lib.hipstr_genotyper_create.restype = C.c_int32
     lib.hipstr_genotyper_create.argtypes = [vp, B, c_i32p, c_i32p, C.POINTER(LocusReadsStruct), C.POINTER(vp)]
+    lib.hipstr_genotyper_create_from_reads.restype = C.c_int32
+    lib.hipstr_genotyper_create_from_reads.argtypes = [vp, C.c_int32, c_i32p, c_i32p, c_i32p, C.POINTER(C.c_char_p), c_f64p,
+                                                       C.POINTER(LocusReadsStruct), C.POINTER(vp)]
     lib.hipstr_genotyper_destroy.restype = None
     lib.hipstr_genotyper_destroy.argtypes = [vp]
     lib.hipstr_genotyper_last_error.restype = C.c_char_p
@@ -473,22 +476,53 @@ class Genotyper:
     """hipstr_genotyper_t: a batch of loci run through the SeqStutterGenotyper::genotype() loop on the GPU."""
 
     def __init__(self, ctx, blocks, block_start, block_end, reads_struct, n_loci):
-        self.lib, self.ctx, self.n_loci = ctx.lib, ctx, n_loci
+        """ctx = a Context, or None for host-only construction (genotype() then raises NO_DEVICE)."""
+        self.lib, self.ctx, self.n_loci = load(), ctx, n_loci
         self._keep = (blocks, block_start, block_end, reads_struct)
         h = C.c_void_p()
-        st = self.lib.hipstr_genotyper_create(ctx.h, C.byref(blocks), ptr(block_start, c_i32p), ptr(block_end, c_i32p),
-                                              C.byref(reads_struct), C.byref(h))
+        st = self.lib.hipstr_genotyper_create(ctx.h if ctx else None, C.byref(blocks), ptr(block_start, c_i32p),
+                                              ptr(block_end, c_i32p), C.byref(reads_struct), C.byref(h))
         if st != 0:
             raise HipstrError(st, "genotyper_create")
         self.h = h
+
+    @staticmethod
+    def _reads_struct(synth):
+        v = synth.view
+        return LocusReadsStruct(v.locus_read_off, v.locus_sample_off, v.read_seq_off, v.read_bases, v.read_quals, v.read_start,
+                                v.read_cigar_off, v.read_cigar_type, v.read_cigar_len, v.sample_label, v.read_name_id,
+                                v.log_p1, v.log_p2, v.haploid, v.read_rev_strand)
+
+    @classmethod
+    def from_synth_reads(cls, ctx, synth, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01)):
+        """The full seam-B1 constructor: haplotype blocks are generated from the reads (hipstr_genotyper_create_from_reads)."""
+        v, L = synth.view, synth.n_loci
+        rs = cls._reads_struct(synth)
+        cl = int(v.chrom_len)
+        raw = C.string_at(v.chrom_seqs, L * cl)
+        chroms = [raw[l * cl:(l + 1) * cl] for l in range(L)]
+        carr = (C.c_char_p * L)(*chroms)
+        start = np.full(L, int(v.region_start), np.int32)
+        stop = np.full(L, int(v.region_stop), np.int32)
+        period = np.full(L, int(synth.cfg.period) or 4, np.int32)
+        st6 = np.tile(np.asarray(stutter, np.float64), L)
+        g = cls.__new__(cls)
+        g.lib, g.ctx, g.n_loci = load(), ctx, L
+        g._keep = (rs, chroms, carr, start, stop, period, st6)
+        g._synth = synth
+        h = C.c_void_p()
+        st = g.lib.hipstr_genotyper_create_from_reads(ctx.h if ctx else None, L, ptr(start, c_i32p), ptr(stop, c_i32p),
+                                                      ptr(period, c_i32p), carr, ptr(st6, c_f64p), C.byref(rs), C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "genotyper_create_from_reads")
+        g.h = h
+        return g
 
     @classmethod
     def from_synth(cls, ctx, synth, loci_blocks=None):
         """All loci of a Synth; loci_blocks overrides the generator's own haplotype blocks."""
         v = synth.view
-        rs = LocusReadsStruct(v.locus_read_off, v.locus_sample_off, v.read_seq_off, v.read_bases, v.read_quals, v.read_start,
-                              v.read_cigar_off, v.read_cigar_type, v.read_cigar_len, v.sample_label, v.read_name_id,
-                              v.log_p1, v.log_p2, v.haploid, v.read_rev_strand)
+        rs = cls._reads_struct(synth)
         if loci_blocks is None:
             b = synth.batch
             bs = _np(v.block_start, b.n_blocks, np.int32)

@@ -13,6 +13,7 @@
 
 #include "../csrc/flatten.h"
 #include "flank_assembler.h"
+#include "haplotype_generator.h"
 
 namespace hipstr {
 
@@ -674,25 +675,8 @@ struct PackedReads {
 
 }  // namespace
 
-hipstr_status_t GenotyperBatch::add_loci(const hipstr_align_batch_t* bt, const int32_t* block_start, const int32_t* block_end,
-                                         const hipstr_locus_reads_t* rd, std::string& err) {
-  if (!bt || !block_start || !block_end || !rd) { err = "null argument"; return HIPSTR_ERR_BAD_ARG; }
-  for (int l = 0; l < bt->n_loci; l++) {
-    loci.emplace_back();
-    SeqStutterGenotyper& g = loci.back();
-    const int b0 = bt->locus_block_off[l], b1 = bt->locus_block_off[l + 1];
-    if (b1 - b0 < 1 || b1 - b0 > HIPSTR_MAX_BLOCKS_PER_LOCUS) { err = "unsupported number of haplotype blocks"; return HIPSTR_ERR_BAD_ARG; }
-    g.num_alleles_ = 1;
-    for (int b = b0; b < b1; b++) {
-      HapBlock blk;
-      blk.start = block_start[b]; blk.end = block_end[b]; blk.period = bt->block_period[b];
-      std::memcpy(blk.stutter, bt->block_stutter + 6 * (size_t)b, sizeof(blk.stutter));
-      for (int o = bt->block_opt_off[b]; o < bt->block_opt_off[b + 1]; o++)
-        blk.seqs.emplace_back(bt->opt_seq + bt->opt_seq_off[o], bt->opt_seq + bt->opt_seq_off[o + 1]);
-      if (blk.seqs.empty()) { err = "haplotype block without a reference allele"; return HIPSTR_ERR_BAD_ARG; }
-      g.num_alleles_ *= blk.num_options();
-      g.hap_blocks_.push_back(blk);
-    }
+hipstr_status_t GenotyperBatch::init_reads(SeqStutterGenotyper& g, const hipstr_locus_reads_t* rd, int l, std::string& err) {
+  {
     const int r0 = rd->locus_read_off[l], r1 = rd->locus_read_off[l + 1], R = r1 - r0;
     g.haploid_ = rd->haploid && rd->haploid[l];
     g.num_samples_ = rd->locus_sample_off[l + 1] - rd->locus_sample_off[l];
@@ -749,13 +733,83 @@ hipstr_status_t GenotyperBatch::add_loci(const hipstr_align_batch_t* bt, const i
     for (const HapBlock& b : g.hap_blocks_)
       if (b.period > 0) { rs.push_back(b.start); re.push_back(b.end); }
     g.pool_seed_.assign(P, -1);
-    st = hipstr_calc_seeds(P, starts.data(), lens.data(), coff.data(), ctype.data(), clen.data(), g.hap_blocks_.front().start,
-                           g.hap_blocks_.back().end, (int32_t)rs.size(), rs.data(), re.data(), g.pool_seed_.data());
+    if (!g.hap_blocks_.empty())
+      st = hipstr_calc_seeds(P, starts.data(), lens.data(), coff.data(), ctype.data(), clen.data(), g.hap_blocks_.front().start,
+                             g.hap_blocks_.back().end, (int32_t)rs.size(), rs.data(), re.data(), g.pool_seed_.data());
     if (st != HIPSTR_OK) { err = "hipstr_calc_seeds failed (the reference dies on a seed at a read end)"; return st; }
     g.seed_positions_.assign(R, -1);
     g.sample_total_LLs_.assign(g.num_samples_, 0.0);
     g.optimal_haps_.assign((size_t)g.num_samples_ * 2, 0);
-    g.rebuild_hap_aln_info(nullptr);
+    if (!g.hap_blocks_.empty()) g.rebuild_hap_aln_info(nullptr);
+  }
+  return HIPSTR_OK;
+}
+
+hipstr_status_t GenotyperBatch::add_loci(const hipstr_align_batch_t* bt, const int32_t* block_start, const int32_t* block_end,
+                                         const hipstr_locus_reads_t* rd, std::string& err) {
+  if (!bt || !block_start || !block_end || !rd) { err = "null argument"; return HIPSTR_ERR_BAD_ARG; }
+  for (int l = 0; l < bt->n_loci; l++) {
+    loci.emplace_back();
+    SeqStutterGenotyper& g = loci.back();
+    const int b0 = bt->locus_block_off[l], b1 = bt->locus_block_off[l + 1];
+    if (b1 - b0 < 1 || b1 - b0 > HIPSTR_MAX_BLOCKS_PER_LOCUS) { err = "unsupported number of haplotype blocks"; return HIPSTR_ERR_BAD_ARG; }
+    g.num_alleles_ = 1;
+    for (int b = b0; b < b1; b++) {
+      HapBlock blk;
+      blk.start = block_start[b]; blk.end = block_end[b]; blk.period = bt->block_period[b];
+      std::memcpy(blk.stutter, bt->block_stutter + 6 * (size_t)b, sizeof(blk.stutter));
+      for (int o = bt->block_opt_off[b]; o < bt->block_opt_off[b + 1]; o++)
+        blk.seqs.emplace_back(bt->opt_seq + bt->opt_seq_off[o], bt->opt_seq + bt->opt_seq_off[o + 1]);
+      if (blk.seqs.empty()) { err = "haplotype block without a reference allele"; return HIPSTR_ERR_BAD_ARG; }
+      g.num_alleles_ *= blk.num_options();
+      g.hap_blocks_.push_back(blk);
+    }
+    hipstr_status_t st = init_reads(g, rd, l, err);
+    if (st != HIPSTR_OK) return st;
+  }
+  return HIPSTR_OK;
+}
+
+hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_t* region_start, const int32_t* region_stop,
+                                                    const int32_t* period, const char* const* chrom_seq, const double* stutter,
+                                                    const hipstr_locus_reads_t* rd, std::string& err) {
+  if (!region_start || !region_stop || !period || !chrom_seq || !stutter || !rd) { err = "null argument"; return HIPSTR_ERR_BAD_ARG; }
+  for (int l = 0; l < n_loci; l++) {
+    loci.emplace_back();
+    SeqStutterGenotyper& g = loci.back();
+    // build_haplotype (seq_stutter_genotyper.cpp:422-484): blocks from the reads that span the padded region
+    const int r0 = rd->locus_read_off[l], r1 = rd->locus_read_off[l + 1];
+    const int S = rd->locus_sample_off[l + 1] - rd->locus_sample_off[l];
+    std::vector<std::vector<ReadView> > by_sample(S);
+    int32_t min_start = INT32_MAX, max_stop = INT32_MIN;
+    for (int r = r0; r < r1; r++) {
+      ReadView v;
+      v.start = rd->read_start[r];
+      v.bases = rd->bases + rd->read_seq_off[r];
+      v.n_cigar = rd->cigar_off[r + 1] - rd->cigar_off[r];
+      v.cigar_type = rd->cigar_type + rd->cigar_off[r];
+      v.cigar_len = rd->cigar_len + rd->cigar_off[r];
+      v.stop = v.start;
+      for (int c = 0; c < v.n_cigar; c++)
+        if (v.cigar_type[c] != 'I') v.stop += v.cigar_len[c];
+      min_start = std::min(min_start, v.start);
+      max_stop = std::max(max_stop, v.stop);
+      by_sample[rd->sample_label[r]].push_back(v);
+    }
+    g.log_ += "Generating candidate haplotypes\n";
+    const std::string chrom(chrom_seq[l]);
+    HaplotypeGenerator generator(min_start, max_stop);
+    if (generator.add_haplotype_block(region_start[l], region_stop[l], period[l], chrom, by_sample, stutter + 6 * (size_t)l) &&
+        generator.fuse_haplotype_blocks(chrom)) {
+      g.hap_blocks_ = generator.get_haplotype_blocks();
+      g.num_alleles_ = 1;
+      for (const HapBlock& b : g.hap_blocks_) g.num_alleles_ *= b.num_options();
+    } else {
+      g.log_ += "Haplotype construction failed: " + generator.failure_msg() + "\n";
+      g.phase_ = SeqStutterGenotyper::FAILED;   // initialized_ = false: genotype() returns false
+    }
+    hipstr_status_t st = init_reads(g, rd, l, err);
+    if (st != HIPSTR_OK) return st;
   }
   return HIPSTR_OK;
 }
@@ -913,6 +967,7 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
 
 hipstr_status_t GenotyperBatch::genotype(int max_total_haplotypes, int max_flank_haplotypes, double min_flank_freq,
                                          bool reassemble_flanks, std::string& err) {
+  if (!ctx_) { err = "no device context: the genotyping loop only runs on the GPU"; return HIPSTR_ERR_NO_DEVICE; }
   const int kMinKmer = 10, kMaxKmer = 15;   // seq_stutter_genotyper.h:153-154
   for (SeqStutterGenotyper& g : loci) {
     if (g.phase_ != SeqStutterGenotyper::ALIGN_ALL) continue;
@@ -976,9 +1031,20 @@ hipstr_status_t hipstr_hap_aln_to_ref(const char* ref_hap, const char* alt_hap, 
 
 hipstr_status_t hipstr_genotyper_create(hipstr_ctx_t* ctx, const hipstr_align_batch_t* blocks, const int32_t* block_start,
                                         const int32_t* block_end, const hipstr_locus_reads_t* reads, hipstr_genotyper_t** out) {
-  if (!ctx || !out) return HIPSTR_ERR_BAD_ARG;   // no context = no device = nothing to run on
+  if (!out) return HIPSTR_ERR_BAD_ARG;   // ctx may be NULL: construction is host work, genotype() then needs a device
   hipstr_genotyper* g = new hipstr_genotyper(ctx);
   hipstr_status_t st = g->batch.add_loci(blocks, block_start, block_end, reads, g->last_error);
+  if (st != HIPSTR_OK) { delete g; return st; }
+  *out = g;
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_genotyper_create_from_reads(hipstr_ctx_t* ctx, int32_t n_loci, const int32_t* region_start,
+                                                   const int32_t* region_stop, const int32_t* period, const char* const* chrom_seq,
+                                                   const double* stutter, const hipstr_locus_reads_t* reads, hipstr_genotyper_t** out) {
+  if (!out || n_loci < 0) return HIPSTR_ERR_BAD_ARG;
+  hipstr_genotyper* g = new hipstr_genotyper(ctx);
+  hipstr_status_t st = g->batch.add_loci_from_reads(n_loci, region_start, region_stop, period, chrom_seq, stutter, reads, g->last_error);
   if (st != HIPSTR_OK) { delete g; return st; }
   *out = g;
   return HIPSTR_OK;

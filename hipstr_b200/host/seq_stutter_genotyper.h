@@ -148,6 +148,11 @@ class GenotyperBatch {
    * pools the reads, marks second mates, computes pool seeds. */
   hipstr_status_t add_loci(const hipstr_align_batch_t* blocks, const int32_t* block_start, const int32_t* block_end,
                            const hipstr_locus_reads_t* reads, std::string& err);
+  /* The whole constructor: build_haplotype (.cpp:422-484, HaplotypeGenerator) from the reads of one STR region per
+   * locus, then init().  A locus whose haplotype construction fails stays uninitialised (genotype() = false). */
+  hipstr_status_t add_loci_from_reads(int32_t n_loci, const int32_t* region_start, const int32_t* region_stop,
+                                      const int32_t* period, const char* const* chrom_seq, const double* stutter,
+                                      const hipstr_locus_reads_t* reads, std::string& err);
   /* genotype() of every locus (.cpp:603-671), lockstep rounds. */
   hipstr_status_t genotype(int max_total_haplotypes, int max_flank_haplotypes, double min_flank_freq, bool reassemble_flanks,
                            std::string& err);
@@ -164,6 +169,7 @@ class GenotyperBatch {
 
  private:
   hipstr_ctx_t* ctx_;
+  hipstr_status_t init_reads(SeqStutterGenotyper& g, const hipstr_locus_reads_t* reads, int locus, std::string& err);
   hipstr_status_t run_alignments(const std::vector<int>& which, std::string& err);
   hipstr_status_t run_posteriors(const std::vector<int>& which, std::string& err);
 };

@@ -467,6 +467,7 @@ void format_record(SeqStutterGenotyper& g, const LocusGenotypes& k3b, const std:
 hipstr_status_t GenotyperBatch::write_vcf_records(const hipstr_vcf_loci_t* regions, const hipstr_vcf_options_t* options,
                                                   std::string& err) {
   if (!regions || !options) { err = "null argument"; return HIPSTR_ERR_BAD_ARG; }
+  if (!ctx_) { err = "no device context"; return HIPSTR_ERR_NO_DEVICE; }
   // K3b over every genotyped locus
   std::vector<int> which;
   std::vector<int32_t> locus_sample_off{0}, n_haps, n_variants, hap_to_allele;

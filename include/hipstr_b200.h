@@ -405,9 +405,23 @@ typedef struct hipstr_locus_reads {
 } hipstr_locus_reads_t;
 
 typedef struct hipstr_genotyper hipstr_genotyper_t;
+/* ctx may be NULL for the two constructors (pooling, seeding and haplotype generation are host
+ * work and can be inspected without a GPU); genotype() / write_vcf then return
+ * HIPSTR_ERR_NO_DEVICE -- there is no CPU alignment path. */
 hipstr_status_t hipstr_genotyper_create(hipstr_ctx_t* ctx, const hipstr_align_batch_t* blocks,
                                         const int32_t* block_start, const int32_t* block_end,
                                         const hipstr_locus_reads_t* reads, hipstr_genotyper_t** out);
+/* The full constructor of seam B1: the haplotype blocks are generated from the reads themselves
+ * (SeqStutterGenotyper::build_haplotype .cpp:422-484 over HaplotypeGenerator::add_haplotype_block /
+ * fuse_haplotype_blocks, SeqAlignment/HaplotypeGenerator.cpp:12-366), one STR region per locus:
+ *   region_start / region_stop / period [n_loci]  the Region;  chrom_seq [n_loci] its chromosome
+ *   stutter [n_loci][6]  the locus' StutterModel parameters (block_stutter order)
+ * A locus whose haplotype construction fails ("No spanning alignments", too near the chromosome
+ * end) is kept uninitialised: genotype() reports locus_ok = 0 for it, like the reference. */
+hipstr_status_t hipstr_genotyper_create_from_reads(hipstr_ctx_t* ctx, int32_t n_loci, const int32_t* region_start,
+                                                   const int32_t* region_stop, const int32_t* period,
+                                                   const char* const* chrom_seq, const double* stutter,
+                                                   const hipstr_locus_reads_t* reads, hipstr_genotyper_t** out);
 void            hipstr_genotyper_destroy(hipstr_genotyper_t* g);
 const char*     hipstr_genotyper_last_error(const hipstr_genotyper_t* g);
 /* genotype(max_total_haplotypes, max_flank_haplotypes, min_flank_freq) of every locus

@@ -77,6 +77,48 @@ def test_hap_aln_to_ref_shifts_flank_indels():
         assert info.index(kind) >= len(left) + 2
 
 
+HAPGEN_CASES = [
+    dict(n_loci=4, n_samples=10, reads_per_sample=20, n_alleles=6, read_len=100, seed=5),
+    dict(n_loci=6, n_samples=4, reads_per_sample=25, n_alleles=3, read_len=100, seed=11, stutter_rate=0.35),
+    dict(n_loci=6, n_samples=25, reads_per_sample=3, n_alleles=10, read_len=150, seed=31, stutter_rate=0.1),
+    dict(n_loci=4, n_samples=6, reads_per_sample=15, n_alleles=5, read_len=110, seed=41, period=2, ref_copies=15, stutter_rate=0.3, sub_rate=0.02),
+    dict(n_loci=3, n_samples=5, reads_per_sample=15, n_alleles=5, read_len=120, seed=61, period=1, ref_copies=14, stutter_rate=0.3),
+    dict(n_loci=3, n_samples=6, reads_per_sample=8, n_alleles=4, read_len=110, seed=51, mate_rate=0.5, stutter_rate=0.25),
+    dict(n_loci=3, n_samples=8, reads_per_sample=20, n_alleles=4, read_len=120, seed=71, flank_snp_freq=0.3),
+    dict(n_loci=3, n_samples=5, reads_per_sample=6, n_alleles=4, read_len=40, seed=77),      # reads too short to span: construction fails
+    dict(n_loci=2, n_samples=5, reads_per_sample=8, n_alleles=6, read_len=250, seed=5100, trim=0),
+    dict(n_loci=2, n_samples=5, reads_per_sample=8, n_alleles=5, read_len=200, seed=5400, period=6, ref_copies=6, trim=0),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("kw", HAPGEN_CASES, ids=lambda k: "seed%d" % k["seed"])
+def test_constructor_matches_reference(kw):
+    """hipstr_genotyper_create_from_reads (host work, no GPU needed): haplotype blocks (HaplotypeGenerator), read pools and
+    success / failure of the construction equal the reference constructor's."""
+    from hipstr_b200.capi import Genotyper
+    from ref_genotyper import LocusReads, RefGenotyper
+    s = Synth(**kw)
+    g = Genotyper.from_synth_reads(None, s)
+    n_ok = 0
+    for l in range(s.n_loci):
+        r = RefGenotyper(LocusReads(s, l))
+        info = g.info(l)
+        if not r.initialized:
+            assert info["blocks"] == 0, l
+            continue
+        n_ok += 1
+        want = r.blocks()
+        assert g.blocks(l) == [b[3] for b in want], l
+        assert info["pools"] == r.lib.ref_sg_num_pools(r.h)
+        assert np.array_equal(g.results(l)["pool_index"], r.results()["pool_index"])
+    if kw["read_len"] > 60:
+        assert n_ok == s.n_loci
+    with pytest.raises(Exception):
+        g.genotype()          # no context -> HIPSTR_ERR_NO_DEVICE, never a CPU path
+    g.close()
+
+
 # ---- the full loop on the GPU ---------------------------------------------------------------------------
 LOOP_CASES = [
     ("plain", dict(n_loci=3, n_samples=10, reads_per_sample=20, n_alleles=6, read_len=100, seed=5)),
@@ -118,7 +160,8 @@ def test_genotype_loop_matches_reference(name, kw):
         refs.append(r)
         blocks0.append(r.blocks())     # the reference's own HaplotypeGenerator output is the common starting point
     ctx = Context(0)
-    g = Genotyper.from_synth(ctx, s, blocks0)
+    # odd cases start from the reference's blocks, even ones run the product's own haplotype generation too
+    g = Genotyper.from_synth(ctx, s, blocks0) if len(name) % 2 else Genotyper.from_synth_reads(ctx, s)
     ok = g.genotype(1000, 4, min_flank_freq, assemble)
     stats = g.stats()
     changed = rounds = 0
