@@ -327,6 +327,10 @@ def load():
     lib.hipstr_genotyper_genotype.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, c_u8p]
     lib.hipstr_genotyper_stats.restype = C.c_int32
     lib.hipstr_genotyper_stats.argtypes = [vp, c_i64p, c_i64p, c_i32p]
+    lib.hipstr_genotyper_timing.restype = C.c_int32
+    lib.hipstr_genotyper_timing.argtypes = [vp, c_f64p]
+    lib.hipstr_genotyper_phase_timing.restype = C.c_int32
+    lib.hipstr_genotyper_phase_timing.argtypes = [vp, c_f64p]
     lib.hipstr_genotyper_locus_info.restype = C.c_int32
     lib.hipstr_genotyper_locus_info.argtypes = [vp, C.c_int32, c_i32p]
     lib.hipstr_genotyper_locus_blocks.restype = C.c_int32
@@ -545,6 +549,17 @@ class Genotyper:
         a, t, r = C.c_int64(), C.c_int64(), C.c_int32()
         self.lib.hipstr_genotyper_stats(self.h, C.byref(a), C.byref(t), C.byref(r))
         return dict(alignments=a.value, traces=t.value, rounds=r.value)
+
+    def timing(self):
+        t = np.zeros(7)
+        self.lib.hipstr_genotyper_timing(self.h, ptr(t, c_f64p))
+        return dict(zip(("construct", "decide", "trace_device", "trace_host", "align", "posteriors", "vcf"), map(float, t)))
+
+    def phase_timing(self):
+        t = np.zeros(8)
+        self.lib.hipstr_genotyper_phase_timing(self.h, ptr(t, c_f64p))
+        return dict(zip(("align_all", "stutter", "prune_uncalled", "prune_unspanned", "assemble", "assemble_prune", "done", "failed"),
+                        map(float, t)))
 
     def info(self, l):
         info = np.zeros(8, np.int32)

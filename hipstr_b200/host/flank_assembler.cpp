@@ -14,18 +14,18 @@ FlankAssembler::FlankAssembler(int k, const std::string& ref_seq) : k_(k), num_s
   for (Edge& e : edges_) e.from_ref = true;
 }
 
-int FlankAssembler::node(const std::string& kmer) {
+int FlankAssembler::node(std::string_view kmer) {
   auto it = node_of_.find(kmer);
   if (it != node_of_.end()) return it->second;
   const int id = (int)labels_.size();
-  labels_.push_back(kmer);
-  node_of_[kmer] = id;
+  labels_.emplace_back(kmer);
+  node_of_.emplace(std::string_view(labels_.back()), id);
   arriving_.emplace_back();
   departing_.emplace_back();
   return id;
 }
 
-void FlankAssembler::increment_edge(const std::string& from, const std::string& to, int delta) {
+void FlankAssembler::increment_edge(std::string_view from, std::string_view to, int delta) {
   const int s = node(from), d = node(to);
   for (int e : arriving_[d])
     if (edges_[e].source == s) { edges_[e].weight += delta; return; }
@@ -35,10 +35,11 @@ void FlankAssembler::increment_edge(const std::string& from, const std::string& 
   arriving_[d].push_back(id);
 }
 
-void FlankAssembler::add_string(const std::string& seq, int weight) {
+void FlankAssembler::add_string(const std::string& seq, int weight, int copies) {
   if ((int)seq.size() <= k_) return;
-  num_strings_++;
-  for (size_t i = 1; i + k_ <= seq.size(); i++) increment_edge(seq.substr(i - 1, k_), seq.substr(i, k_), weight);
+  num_strings_ += copies;
+  const std::string_view s(seq);
+  for (size_t i = 1; i + k_ <= seq.size(); i++) increment_edge(s.substr(i - 1, k_), s.substr(i, k_), weight * copies);
 }
 
 void FlankAssembler::prune_edges(double min_edge_freq, int min_weight) {
@@ -58,13 +59,12 @@ void FlankAssembler::prune_edges(double min_edge_freq, int min_weight) {
   }
   // nodes that still touch an edge (plus source and sink) are renumbered in their old order
   std::vector<int> new_node_id(n_nodes, -1);
-  std::vector<std::string> labels;
+  std::deque<std::string> labels;
   std::vector<std::vector<int> > arriving, departing;
   node_of_.clear();
   for (int v = 0; v < n_nodes; v++) {
     if (!keep_node[v]) continue;
     new_node_id[v] = (int)labels.size();
-    node_of_[labels_[v]] = new_node_id[v];
     labels.push_back(labels_[v]);
     std::vector<int> in, out;
     for (int e : arriving_[v]) if (new_edge_id[e] >= 0) in.push_back(new_edge_id[e]);
@@ -75,6 +75,7 @@ void FlankAssembler::prune_edges(double min_edge_freq, int min_weight) {
   for (Edge& e : kept) { e.source = new_node_id[e.source]; e.destination = new_node_id[e.destination]; }
   edges_.swap(kept);
   labels_.swap(labels);
+  for (size_t v = 0; v < labels_.size(); v++) node_of_.emplace(std::string_view(labels_[v]), (int)v);
   arriving_.swap(arriving);
   departing_.swap(departing);
 }

@@ -12,8 +12,10 @@
 #ifndef HIPSTR_B200_FLANK_ASSEMBLER_H_
 #define HIPSTR_B200_FLANK_ASSEMBLER_H_
 
-#include <map>
+#include <deque>
 #include <string>
+#include <string_view>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -23,7 +25,8 @@ class FlankAssembler {
  public:
   /* DebruijnGraph(k, ref_seq): the reference path enters with weight 2 and its edges are never pruned. */
   FlankAssembler(int k, const std::string& ref_seq);
-  void add_string(const std::string& seq, int weight = 1);       /* debruijn_graph.cpp:31-45 */
+  /* debruijn_graph.cpp:31-45; `copies` identical strings at once (same graph as adding them one by one) */
+  void add_string(const std::string& seq, int weight = 1, int copies = 1);
   void prune_edges(double min_edge_freq, int min_weight);         /* :47-60, 62-121 */
   bool has_cycles() const;                                        /* directed_graph.cpp:29-64 */
   bool is_source_ok();                                            /* debruijn_graph.cpp:12-15 */
@@ -38,13 +41,13 @@ class FlankAssembler {
   int k_;
   std::string source_kmer_, sink_kmer_;
   int num_strings_;
-  std::vector<std::string> labels_;               /* node id -> k-mer */
-  std::map<std::string, int> node_of_;
+  std::deque<std::string> labels_;                /* node id -> k-mer (stable storage: node_of_ keys view into it) */
+  std::unordered_map<std::string_view, int> node_of_;
   std::vector<Edge> edges_;
   std::vector<std::vector<int> > arriving_, departing_;   /* node id -> edge ids, insertion order */
 
-  int node(const std::string& kmer);              /* get_node: creates the node when absent */
-  void increment_edge(const std::string& from, const std::string& to, int delta);
+  int node(std::string_view kmer);                /* get_node: creates the node when absent */
+  void increment_edge(std::string_view from, std::string_view to, int delta);
   void alt_kmer_nodes(std::string kmer, bool source, bool sink, std::vector<int>& nodes);
 };
 

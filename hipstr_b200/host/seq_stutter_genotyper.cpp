@@ -6,10 +6,14 @@
 #include "seq_stutter_genotyper.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <set>
+#include <atomic>
+#include <cstdlib>
 #include <sstream>
+#include <thread>
 
 #include "../csrc/flatten.h"
 #include "flank_assembler.h"
@@ -17,6 +21,28 @@
 
 namespace hipstr {
 
+namespace {
+
+}  // namespace
+int host_threads() {
+  static const int n = [] {
+    const char* env = std::getenv("HIPSTR_HOST_THREADS");
+    int t = env ? std::atoi(env) : (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(t, 32));
+  }();
+  return n;
+}
+void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
+  const size_t workers = std::min<size_t>((size_t)host_threads(), n);
+  if (workers <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+  std::atomic<size_t> next(0);
+  auto body = [&] { for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); };
+  std::vector<std::thread> pool;
+  for (size_t w = 1; w < workers; w++) pool.emplace_back(body);
+  body();
+  for (std::thread& t : pool) t.join();
+}
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 namespace {
 
 bool order_by_length_and_sequence(const std::string& a, const std::string& b) {   // stringops.cpp:35-39
@@ -341,7 +367,13 @@ bool SeqStutterGenotyper::add_and_remove_alleles(const std::vector<std::vector<i
 }
 
 SeqStutterGenotyper::Request SeqStutterGenotyper::advance() {
+  struct PhaseTimer {   // charges the time until the next phase change / return to the phase that was running
+    SeqStutterGenotyper* g; Phase p; double t0;
+    explicit PhaseTimer(SeqStutterGenotyper* g_) : g(g_), p(g_->phase_), t0(now_s()) {}
+    ~PhaseTimer() { g->phase_seconds_[p] += now_s() - t0; }
+  };
   for (;;) {
+    PhaseTimer timer(this);
     switch (phase_) {
       case ALIGN_ALL:
         realign_hap_.assign(num_alleles_, 1);
@@ -460,13 +492,20 @@ int SeqStutterGenotyper::assemble_flanks() {
       if (!call_sample_[s].empty()) continue;
       assembly_data.clear();
       bool acyclic = false;
+      // the sample's flank sequences in read order, identical ones counted once (same graph, fewer k-mer walks)
+      std::vector<std::pair<const std::string*, int> > flank_seqs;
+      for (int r = first_read[s]; r < first_read[s + 1]; r++) {
+        if (seed_positions_[r] < 0) continue;
+        const std::string& seq = trace_cache_.at(std::make_pair(pool_index_[r], best_hap_of_read(r))).flank_seq[block_index];
+        if (seq.empty()) continue;
+        bool seen = false;
+        for (auto& f : flank_seqs)
+          if (*f.first == seq) { f.second++; seen = true; break; }
+        if (!seen) flank_seqs.emplace_back(&seq, 1);
+      }
       for (int k = kmer_length; k <= max_k; k++) {
         FlankAssembler assembler(k, ref_seq);
-        for (int r = first_read[s]; r < first_read[s + 1]; r++) {
-          if (seed_positions_[r] < 0) continue;
-          const std::string& seq = trace_cache_.at(std::make_pair(pool_index_[r], best_hap_of_read(r))).flank_seq[block_index];
-          if (!seq.empty()) assembler.add_string(seq);
-        }
+        for (const auto& f : flank_seqs) assembler.add_string(*f.first, 1, f.second);
         assembler.prune_edges(0.02, 2);
         if (!assembler.has_cycles() && assembler.is_source_ok() && assembler.is_sink_ok()) {
           acyclic = true;
@@ -774,9 +813,14 @@ hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_
                                                     const int32_t* period, const char* const* chrom_seq, const double* stutter,
                                                     const hipstr_locus_reads_t* rd, std::string& err) {
   if (!region_start || !region_stop || !period || !chrom_seq || !stutter || !rd) { err = "null argument"; return HIPSTR_ERR_BAD_ARG; }
-  for (int l = 0; l < n_loci; l++) {
-    loci.emplace_back();
-    SeqStutterGenotyper& g = loci.back();
+  const size_t base = loci.size();
+  loci.resize(base + n_loci);
+  std::vector<hipstr_status_t> status(n_loci, HIPSTR_OK);
+  std::vector<std::string> errors(n_loci);
+  host_tables();
+  parallel_for(n_loci, [&](size_t li) {
+    const int l = (int)li;
+    SeqStutterGenotyper& g = loci[base + li];
     // build_haplotype (seq_stutter_genotyper.cpp:422-484): blocks from the reads that span the padded region
     const int r0 = rd->locus_read_off[l], r1 = rd->locus_read_off[l + 1];
     const int S = rd->locus_sample_off[l + 1] - rd->locus_sample_off[l];
@@ -808,9 +852,10 @@ hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_
       g.log_ += "Haplotype construction failed: " + generator.failure_msg() + "\n";
       g.phase_ = SeqStutterGenotyper::FAILED;   // initialized_ = false: genotype() returns false
     }
-    hipstr_status_t st = init_reads(g, rd, l, err);
-    if (st != HIPSTR_OK) return st;
-  }
+    status[li] = init_reads(g, rd, l, errors[li]);
+  });
+  for (int l = 0; l < n_loci; l++)
+    if (status[l] != HIPSTR_OK) { err = errors[l]; return status[l]; }
   return HIPSTR_OK;
 }
 
@@ -924,12 +969,21 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
     out.n_snps = n_snps.data();
     out.snps = snps.data();
     hipstr_align_batch_t bt = pb.view();
+    const double t_dev = now_s();
     hipstr_status_t st = hipstr_trace_batch_host(ctx_, &bt, pb.block_start.data(), (int32_t)n, trace_pool.data(), trace_hap.data(), &out);
+    seconds[T_TRACE_DEVICE] += now_s() - t_dev;
     if (st != HIPSTR_OK) { err = std::string("hipstr_trace_batch_host: ") + hipstr_last_error(ctx_); return st; }
     n_traces += (int64_t)n;
-    std::vector<char> ctype(stride + 8), aln(2 * (size_t)stride + 8);
-    std::vector<int32_t> clen(stride + 8);
-    for (size_t i = 0; i < n; i++) {
+    // stitch every trace against the reference and file it in its locus' cache; traces of one locus are contiguous
+    std::vector<size_t> group_start;
+    for (size_t i = 0; i < n; i++)
+      if (i == 0 || owner[i].first != owner[i - 1].first) group_start.push_back(i);
+    group_start.push_back(n);
+    std::atomic<int> failed(0);
+    parallel_for(group_start.size() - 1, [&](size_t grp) {
+      std::vector<char> ctype(stride + 8), aln(2 * (size_t)stride + 8);
+      std::vector<int32_t> clen(stride + 8);
+      for (size_t i = group_start[grp]; i < group_start[grp + 1]; i++) {
       SeqStutterGenotyper& g = loci[owner[i].first];
       const std::pair<int, int> key = g.missing_traces_[owner[i].second];
       const int nb = (int)g.hap_blocks_.size();
@@ -950,16 +1004,18 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
       for (int k = 0; k < n_snps[i]; k++)
         t.flank_snp_data.emplace_back(snps[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2], (char)snps[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2 + 1]);
       int32_t n_cigar = 0;
-      st = hipstr_stitch_trace(g.hap_blocks_.front().start, g.hap_aln_info_[key.second].c_str(), t.hap_aln.c_str(), seed_hap_pos[i],
+      const hipstr_status_t st2 = hipstr_stitch_trace(g.hap_blocks_.front().start, g.hap_aln_info_[key.second].c_str(), t.hap_aln.c_str(), seed_hap_pos[i],
                                g.pool_seed_[key.first], read.c_str(), &t.start, &t.stop, (int32_t)ctype.size(), ctype.data(),
                                clen.data(), &n_cigar, (int32_t)aln.size(), aln.data());
-      if (st != HIPSTR_OK) { err = "hipstr_stitch_trace failed"; return st; }
+      if (st2 != HIPSTR_OK) { failed = 1; return; }
       std::ostringstream cig;
       for (int k = 0; k < n_cigar; k++) cig << clen[k] << ctype[k];
       t.cigar = cig.str();
       t.alignment = std::string(aln.data());
       g.trace_cache_[key] = std::move(t);
-    }
+      }
+    });
+    if (failed) { err = "hipstr_stitch_trace failed"; return HIPSTR_ERR_BAD_ARG; }
   }
   for (int l : which) { loci[l].missing_traces_.clear(); loci[l].missing_trace_read_.clear(); }
   return HIPSTR_OK;
@@ -997,19 +1053,31 @@ hipstr_status_t GenotyperBatch::genotype(int max_total_haplotypes, int max_flank
   }
   for (;;) {
     std::vector<int> need_traces, need_alignment, need_posteriors;
+    const double t_decide = now_s();
+    std::vector<SeqStutterGenotyper::Request> requests(loci.size());
+    host_tables();   // build the constant tables before the workers read them
+    parallel_for(loci.size(), [&](size_t l) { requests[l] = loci[l].advance(); });
     for (size_t l = 0; l < loci.size(); l++) {
-      switch (loci[l].advance()) {
+      switch (requests[l]) {
         case SeqStutterGenotyper::NEED_TRACES: need_traces.push_back((int)l); break;
         case SeqStutterGenotyper::NEED_ALIGNMENT: need_alignment.push_back((int)l); break;
         case SeqStutterGenotyper::NEED_POSTERIORS: need_posteriors.push_back((int)l); break;
         case SeqStutterGenotyper::NONE: break;
       }
     }
+    seconds[T_DECIDE] += now_s() - t_decide;
     if (need_traces.empty() && need_alignment.empty() && need_posteriors.empty()) break;
     n_rounds++;
+    double t0 = now_s();
+    const double dev0 = seconds[T_TRACE_DEVICE];
     hipstr_status_t st = run_traces(need_traces, err);
+    double t1 = now_s();
+    seconds[T_TRACE_HOST] += (t1 - t0) - (seconds[T_TRACE_DEVICE] - dev0);
     if (st == HIPSTR_OK) st = run_alignments(need_alignment, err);
+    t0 = now_s();
+    seconds[T_ALIGN] += t0 - t1;
     if (st == HIPSTR_OK) st = run_posteriors(need_posteriors, err);
+    seconds[T_POSTERIORS] += now_s() - t0;
     if (st != HIPSTR_OK) return st;
   }
   return HIPSTR_OK;
@@ -1033,7 +1101,9 @@ hipstr_status_t hipstr_genotyper_create(hipstr_ctx_t* ctx, const hipstr_align_ba
                                         const int32_t* block_end, const hipstr_locus_reads_t* reads, hipstr_genotyper_t** out) {
   if (!out) return HIPSTR_ERR_BAD_ARG;   // ctx may be NULL: construction is host work, genotype() then needs a device
   hipstr_genotyper* g = new hipstr_genotyper(ctx);
+  const double t0 = hipstr::now_s();
   hipstr_status_t st = g->batch.add_loci(blocks, block_start, block_end, reads, g->last_error);
+  g->batch.seconds[hipstr::GenotyperBatch::T_CONSTRUCT] += hipstr::now_s() - t0;
   if (st != HIPSTR_OK) { delete g; return st; }
   *out = g;
   return HIPSTR_OK;
@@ -1044,7 +1114,9 @@ hipstr_status_t hipstr_genotyper_create_from_reads(hipstr_ctx_t* ctx, int32_t n_
                                                    const double* stutter, const hipstr_locus_reads_t* reads, hipstr_genotyper_t** out) {
   if (!out || n_loci < 0) return HIPSTR_ERR_BAD_ARG;
   hipstr_genotyper* g = new hipstr_genotyper(ctx);
+  const double t0 = hipstr::now_s();
   hipstr_status_t st = g->batch.add_loci_from_reads(n_loci, region_start, region_stop, period, chrom_seq, stutter, reads, g->last_error);
+  g->batch.seconds[hipstr::GenotyperBatch::T_CONSTRUCT] += hipstr::now_s() - t0;
   if (st != HIPSTR_OK) { delete g; return st; }
   *out = g;
   return HIPSTR_OK;
@@ -1061,6 +1133,21 @@ hipstr_status_t hipstr_genotyper_genotype(hipstr_genotyper_t* g, int32_t max_tot
   if (st != HIPSTR_OK) return st;
   if (locus_ok)
     for (size_t l = 0; l < g->batch.loci.size(); l++) locus_ok[l] = g->batch.loci[l].succeeded() ? 1 : 0;
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_genotyper_timing(const hipstr_genotyper_t* g, double* seconds7) {
+  if (!g || !seconds7) return HIPSTR_ERR_BAD_ARG;
+  for (int i = 0; i < hipstr::GenotyperBatch::T_COUNT; i++) seconds7[i] = g->batch.seconds[i];
+  return HIPSTR_OK;
+}
+/* host seconds of the per-locus decisions summed over loci, by phase: {align-all set-up, stutter-allele discovery,
+ * uncalled pruning, unspanned pruning, flank assembly, post-assembly pruning, done, failed} */
+hipstr_status_t hipstr_genotyper_phase_timing(const hipstr_genotyper_t* g, double* seconds8) {
+  if (!g || !seconds8) return HIPSTR_ERR_BAD_ARG;
+  for (int i = 0; i < 8; i++) seconds8[i] = 0;
+  for (const auto& l : g->batch.loci)
+    for (int i = 0; i < 8; i++) seconds8[i] += l.phase_seconds_[i];
   return HIPSTR_OK;
 }
 

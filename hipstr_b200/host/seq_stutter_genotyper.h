@@ -19,6 +19,7 @@
 
 #include <stdint.h>
 
+#include <functional>
 #include <map>
 #include <string>
 #include <utility>
@@ -62,6 +63,11 @@ std::string hap_aln_to_ref(const std::string& ref_hap, const std::string& alt_ha
                            int32_t repeat_block_start);
 
 class GenotyperBatch;
+double now_s();   /* steady clock, seconds */
+/* Runs fn(i) for i in [0, n) on the host cores (std::thread, dynamic scheduling).  The per-locus host logic of the
+ * loop is independent across loci; thread count = HIPSTR_HOST_THREADS or the hardware concurrency (at most 32). */
+int host_threads();
+void parallel_for(size_t n, const std::function<void(size_t)>& fn);
 
 /* One locus.  Member names follow seq_stutter_genotyper.h:28-68 / genotyper.h:20-46. */
 class SeqStutterGenotyper {
@@ -96,6 +102,7 @@ class SeqStutterGenotyper {
   std::string log_;
   std::string vcf_record_;                     /* text of the last write_vcf_record */
   int32_t vcf_pos_ = 0;                        /* its POS */
+  double phase_seconds_[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* host seconds spent deciding, by Phase */
   int rounds_ = 0;                             /* alignment rounds run (1 = no allele discovery) */
 
   /* write_vcf_record (.cpp:995-1510) in two steps around one batched trace call */
@@ -160,6 +167,10 @@ class GenotyperBatch {
   std::vector<SeqStutterGenotyper> loci;
   int64_t n_alignments = 0, n_traces = 0;
   int n_rounds = 0;
+  /* wall-clock seconds by stage: construction, per-locus host decisions, trace device calls, trace stitching +
+   * bookkeeping, alignment calls (packing + K1/K2/K3 + unpacking), posterior calls, VCF formatting */
+  enum { T_CONSTRUCT, T_DECIDE, T_TRACE_DEVICE, T_TRACE_HOST, T_ALIGN, T_POSTERIORS, T_VCF, T_COUNT };
+  double seconds[T_COUNT] = {0, 0, 0, 0, 0, 0, 0};
   hipstr_status_t run_traces(const std::vector<int>& which, std::string& err);
   /* write_vcf_record of every successfully genotyped locus (seq_stutter_genotyper.h:179-181, impl .cpp:984-1510,
    * get_alleles :691-769, reorder_alleles :673-689, compute_allele_bias :965-982): K3b marginalises the posteriors of

@@ -468,6 +468,8 @@ hipstr_status_t GenotyperBatch::write_vcf_records(const hipstr_vcf_loci_t* regio
                                                   std::string& err) {
   if (!regions || !options) { err = "null argument"; return HIPSTR_ERR_BAD_ARG; }
   if (!ctx_) { err = "no device context"; return HIPSTR_ERR_NO_DEVICE; }
+  const double t_begin = now_s();
+  const double other0 = seconds[T_TRACE_DEVICE];
   // K3b over every genotyped locus
   std::vector<int> which;
   std::vector<int32_t> locus_sample_off{0}, n_haps, n_variants, hap_to_allele;
@@ -512,10 +514,10 @@ hipstr_status_t GenotyperBatch::write_vcf_records(const hipstr_vcf_loci_t* regio
                                                      hap_log_unphased.data(), gl.data(), phased_gl.data(), gl_diff.data(), pl.data());
   if (st != HIPSTR_OK) { err = std::string("hipstr_extract_genotypes_host: ") + hipstr_last_error(ctx_); return st; }
   // traces of the reads against the haplotype their strand assignment picks
-  for (size_t k = 0; k < which.size(); k++) loci[which[k]].vcf_prepare(&best_hap[2 * (size_t)locus_sample_off[k]]);
+  parallel_for(which.size(), [&](size_t k) { loci[which[k]].vcf_prepare(&best_hap[2 * (size_t)locus_sample_off[k]]); });
   st = run_traces(which, err);
   if (st != HIPSTR_OK) return st;
-  for (size_t k = 0; k < which.size(); k++) {
+  parallel_for(which.size(), [&](size_t k) {
     const int l = which[k];
     SeqStutterGenotyper& g = loci[l];
     const size_t s0 = locus_sample_off[k];
@@ -532,7 +534,8 @@ hipstr_status_t GenotyperBatch::write_vcf_records(const hipstr_vcf_loci_t* regio
     for (int s = 0; s < regions->n_out_samples; s++) out_names.push_back(regions->out_sample_names[s]);
     format_record(g, v, regions->chrom[l], regions->name && regions->name[l] ? regions->name[l] : "", regions->region_start[l],
                   regions->region_stop[l], regions->period[l], regions->chrom_seq[l], locus_names, out_names, *options);
-  }
+  });
+  seconds[T_VCF] += (now_s() - t_begin) - (seconds[T_TRACE_DEVICE] - other0);
   return HIPSTR_OK;
 }
 

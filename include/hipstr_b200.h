@@ -434,6 +434,12 @@ hipstr_status_t hipstr_genotyper_genotype(hipstr_genotyper_t* g, int32_t max_tot
 /* alignments (pooled read x haplotype) and traces computed so far, lockstep rounds run */
 hipstr_status_t hipstr_genotyper_stats(const hipstr_genotyper_t* g, int64_t* n_alignments, int64_t* n_traces,
                                        int32_t* n_rounds);
+/* wall-clock seconds by stage, seconds7 = {construction, per-locus host decisions, trace device calls,
+ * trace stitching, alignment calls (K1+K2+K3 with packing), posterior calls, VCF formatting} */
+hipstr_status_t hipstr_genotyper_timing(const hipstr_genotyper_t* g, double* seconds7);
+/* the host-decision seconds split by phase (summed over loci): {align-all set-up, stutter-allele discovery, uncalled
+ * pruning, unspanned pruning, flank assembly, post-assembly pruning, done, failed} */
+hipstr_status_t hipstr_genotyper_phase_timing(const hipstr_genotyper_t* g, double* seconds8);
 /* info[8] = {blocks, haplotypes (num_alleles_), reads, samples, pools, total options,
  *            total allele bytes, alignment rounds of this locus} */
 hipstr_status_t hipstr_genotyper_locus_info(const hipstr_genotyper_t* g, int32_t locus, int32_t* info);
