@@ -12,6 +12,9 @@ rank 0 over NCCL at the end of every step.
   e2e     the same through the host-buffer C-ABI call (hipstr_genotype_batch_host): host flattening,
           H2D of the inputs, K1-K3, D2H of read LLs / posteriors / genotypes inside the timed region
   roofline, cpu_baseline, clocks: see DESIGN.md "Measurement"
+  full_loop  (N=1) loci/s through the whole seam-B1 path on the same loci -- constructor from reads, genotype() with
+          allele discovery / pruning / flank assembly rounds, write_vcf_record -- next to cpu_baseline.full_loop, the
+          unmodified reference SeqStutterGenotyper on one locus per host core
 
 --impl reference times the reference's own CPU code (oracle/_ref/libhipstr_ref.so compiled from the
 unmodified sources; the C++ restatement in oracle/ if that library is absent) on the host cores.
@@ -84,6 +87,64 @@ def _cpu_worker(rng):
         ptr(best, c_i32p), ptr(tot, c_f64p))
     assert st == 0 and S >= 0
     return time.perf_counter() - t0
+
+
+def _cpu_loop_worker(l):
+    """The reference's whole per-locus path (constructor with haplotype generation, genotype() with flank assembly,
+    write_vcf_record) for locus l of the inherited synthetic batch; returns (seconds, genotype() succeeded)."""
+    from ref_genotyper import LocusReads, RefGenotyper
+    rd = LocusReads(_CPU["synth"], l)
+    t0 = time.perf_counter()
+    g = RefGenotyper(rd, reassemble_flanks=True)
+    ok = g.initialized and g.genotype(1000, 4, 0.01)
+    if ok:
+        g.vcf()
+    dt = time.perf_counter() - t0
+    g.close()
+    return dt, bool(ok)
+
+
+def cpu_full_loop(synth, cores):
+    """One locus per core through the unmodified reference SeqStutterGenotyper (bounded sample)."""
+    import checkers
+    if checkers.ref() is None:
+        return None
+    _CPU.update(synth=synth)
+    n = min(synth.n_loci, cores)
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(n) as pool:
+        res = pool.map(_cpu_loop_worker, range(n))
+    wall = time.perf_counter() - t0
+    return {"loci_per_s": n / wall, "cores": n, "seconds_per_locus_per_core": float(np.mean([r[0] for r in res])),
+            "sample": "first %d loci, one per core: constructor + genotype(flank assembly on) + write_vcf_record, %.1f s wall" % (n, wall)}
+
+
+def gpu_full_loop(ctx, synth, n_loci_cap=1000):
+    """Seam B1 end to end on the GPU: hipstr_genotyper_create_from_reads -> genotype (flank assembly on) -> write_vcf."""
+    from hipstr_b200.capi import Genotyper
+    L = synth.n_loci
+    names = ["S%d" % i for i in range(int(synth.locus_sample_off[1]))]
+    raw = C.string_at(synth.view.chrom_seqs, L * synth.view.chrom_len)
+    cl = synth.view.chrom_len
+    best = None
+    for rep in range(2):   # first pass warms the allocations
+        t0 = time.perf_counter()
+        g = Genotyper.from_synth_reads(ctx, synth)
+        ok = g.genotype(1000, 4, 0.01, True)
+        loci = g.vcf_loci(["chr1"] * L, ["STR%d" % l for l in range(L)], [synth.view.region_start] * L, [synth.view.region_stop] * L,
+                          [int(synth.cfg.period) or 4] * L, [raw[l * cl:(l + 1) * cl] for l in range(L)], names * L, names)
+        rec = g.write_vcf(loci)
+        dt = time.perf_counter() - t0
+        st = g.stats()
+        out = {"loci_per_s": L / dt, "seconds": dt, "loci": L, "loci_genotyped": int(ok.sum()), "records": sum(r is not None for r in rec),
+               "alignments": st["alignments"], "traces": st["traces"], "rounds": st["rounds"],
+               "alignments_per_s": st["alignments"] / dt, "stage_seconds": {k: round(v, 4) for k, v in g.timing().items()},
+               "host_threads": host_cores(),
+               "what": "hipstr_genotyper_create_from_reads + genotype(1000, 4, 0.01, reassemble_flanks) + write_vcf, host buffers in, VCF text out"}
+        g.close()
+        if best is None or out["loci_per_s"] > best["loci_per_s"]:
+            best = out
+    return best
 
 
 def host_cores():
@@ -197,6 +258,7 @@ def main():
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-loop", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3 if a.impl == "ours" else 1)
     rank = int(os.environ.get("RANK", "0"))
@@ -247,6 +309,8 @@ def main():
                         "sample": "first %d loci of the workload, align + posteriors, %d forked workers, %.1f s wall / %.1f s CPU"
                                   % (n, used, wall, cpu_s),
                         "per_core_value": aln / cpu_s}
+        if not a.no_full_loop:
+            cpu_baseline["full_loop"] = cpu_full_loop(s, cores)
 
     import torch
     import torch.distributed as dist
@@ -354,6 +418,9 @@ def main():
                "ms_per_step": 1e3 * t_e2e / a.steps, "checksum_matches_resident": bool(abs(float(out["total_ll"].sum()) - checksum) < 1e-6 * abs(checksum))}
     if clocks:
         clocks.stop()
+    full_loop = None
+    if rank == 0 and world == 1 and not a.no_full_loop:
+        full_loop = gpu_full_loop(ctx, s)
 
     if rank == 0:
         peaks, peak_src = None, "fallback"
@@ -391,7 +458,7 @@ def main():
                              "frac": fp64["dadd_per_alignment"] * (n_aln / (k1_avg_ms / 1e3)) / fp64["peak_dadd_per_s"] if k1_avg_ms > 0 else 0.0,
                              "source": "ncu DADD count per alignment (profiles/k1_traffic.json) x live alignments/s; peak = 64 FP64 lanes x 148 SMs x 1965 MHz"}},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks.summary() if clocks else None,
-            "synth_seconds": t_gen, "checksum_total_ll": checksum,
+            "synth_seconds": t_gen, "checksum_total_ll": checksum, "full_loop": full_loop,
         }
         emit(line)
     if world > 1:
