@@ -119,31 +119,53 @@ def cpu_full_loop(synth, cores):
             "sample": "first %d loci, one per core: constructor + genotype(flank assembly on) + write_vcf_record, %.1f s wall" % (n, wall)}
 
 
-def gpu_full_loop(ctx, synth, n_loci_cap=1000):
-    """Seam B1 end to end on the GPU: hipstr_genotyper_create_from_reads -> genotype (flank assembly on) -> write_vcf."""
-    from hipstr_b200.capi import Genotyper
+def gpu_full_loop(device, synth, pipelines):
+    """Seam B1 end to end on the GPU: hipstr_genotyper_create_from_reads -> genotype (flank assembly on) -> write_vcf.
+    The loci are split into `pipelines` windows, each driven by its own host thread and context, so that the host stages
+    of one window (per-locus decisions, trace stitching, VCF text) overlap the device stages of another."""
+    from hipstr_b200.capi import Context, Genotyper
     L = synth.n_loci
     names = ["S%d" % i for i in range(int(synth.locus_sample_off[1]))]
-    raw = C.string_at(synth.view.chrom_seqs, L * synth.view.chrom_len)
     cl = synth.view.chrom_len
-    best = None
-    for rep in range(2):   # first pass warms the allocations
-        t0 = time.perf_counter()
-        g = Genotyper.from_synth_reads(ctx, synth)
+    raw = C.string_at(synth.view.chrom_seqs, L * cl)
+    period = int(synth.cfg.period) or 4
+    ctxs = [Context(device) for _ in range(pipelines)]
+
+    def window(k, out):
+        l0, l1 = k * L // pipelines, (k + 1) * L // pipelines
+        n = l1 - l0
+        g = Genotyper.from_synth_reads(ctxs[k], synth, loci_range=(l0, l1))
         ok = g.genotype(1000, 4, 0.01, True)
-        loci = g.vcf_loci(["chr1"] * L, ["STR%d" % l for l in range(L)], [synth.view.region_start] * L, [synth.view.region_stop] * L,
-                          [int(synth.cfg.period) or 4] * L, [raw[l * cl:(l + 1) * cl] for l in range(L)], names * L, names)
+        loci = g.vcf_loci(["chr1"] * n, ["STR%d" % l for l in range(l0, l1)], [synth.view.region_start] * n, [synth.view.region_stop] * n,
+                          [period] * n, [raw[l * cl:(l + 1) * cl] for l in range(l0, l1)], names * n, names)
         rec = g.write_vcf(loci)
-        dt = time.perf_counter() - t0
-        st = g.stats()
-        out = {"loci_per_s": L / dt, "seconds": dt, "loci": L, "loci_genotyped": int(ok.sum()), "records": sum(r is not None for r in rec),
-               "alignments": st["alignments"], "traces": st["traces"], "rounds": st["rounds"],
-               "alignments_per_s": st["alignments"] / dt, "stage_seconds": {k: round(v, 4) for k, v in g.timing().items()},
-               "host_threads": host_cores(),
-               "what": "hipstr_genotyper_create_from_reads + genotype(1000, 4, 0.01, reassemble_flanks) + write_vcf, host buffers in, VCF text out"}
+        out[k] = (int(ok.sum()), sum(r is not None for r in rec), g.stats(), g.timing())
         g.close()
-        if best is None or out["loci_per_s"] > best["loci_per_s"]:
-            best = out
+
+    best = None
+    for rep in range(3):   # the first pass warms the allocations
+        out = [None] * pipelines
+        t0 = time.perf_counter()
+        threads = [threading.Thread(target=window, args=(k, out)) for k in range(pipelines)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        dt = time.perf_counter() - t0
+        stages = {}
+        for o in out:
+            for k, v in o[3].items():
+                stages[k] = round(stages.get(k, 0.0) + v, 4)
+        aln = sum(o[2]["alignments"] for o in out)
+        res = {"loci_per_s": L / dt, "seconds": dt, "loci": L, "pipelines": pipelines, "loci_genotyped": sum(o[0] for o in out),
+               "records": sum(o[1] for o in out), "alignments": aln, "traces": sum(o[2]["traces"] for o in out),
+               "rounds": max(o[2]["rounds"] for o in out), "alignments_per_s": aln / dt,
+               "stage_seconds_summed_over_windows": stages, "host_threads": host_cores(),
+               "what": "hipstr_genotyper_create_from_reads + genotype(1000, 4, 0.01, reassemble_flanks) + write_vcf, host buffers in, VCF text out"}
+        if best is None or res["loci_per_s"] > best["loci_per_s"]:
+            best = res
+    for c in ctxs:
+        c.close()
     return best
 
 
@@ -420,7 +442,8 @@ def main():
         clocks.stop()
     full_loop = None
     if rank == 0 and world == 1 and not a.no_full_loop:
-        full_loop = gpu_full_loop(ctx, s)
+        full_loop = gpu_full_loop(local, s, 1)
+        full_loop["pipelined"] = gpu_full_loop(local, s, 4)
 
     if rank == 0:
         peaks, peak_src = None, "fallback"

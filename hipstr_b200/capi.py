@@ -498,12 +498,20 @@ class Genotyper:
                                 v.log_p1, v.log_p2, v.haploid, v.read_rev_strand)
 
     @classmethod
-    def from_synth_reads(cls, ctx, synth, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01)):
-        """The full seam-B1 constructor: haplotype blocks are generated from the reads (hipstr_genotyper_create_from_reads)."""
-        v, L = synth.view, synth.n_loci
+    def from_synth_reads(cls, ctx, synth, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01), loci_range=None):
+        """The full seam-B1 constructor: haplotype blocks are generated from the reads (hipstr_genotyper_create_from_reads).
+        loci_range = (first, end) restricts the batch to a window of the Synth's loci."""
+        v = synth.view
+        l0, l1 = loci_range if loci_range else (0, synth.n_loci)
+        L = l1 - l0
         rs = cls._reads_struct(synth)
+        if l0:   # the per-locus arrays start at the window; read-level arrays stay absolute
+            step = C.sizeof(C.c_int32) * l0
+            rs.locus_read_off = C.cast(C.cast(v.locus_read_off, C.c_void_p).value + step, c_i32p)
+            rs.locus_sample_off = C.cast(C.cast(v.locus_sample_off, C.c_void_p).value + step, c_i32p)
+            rs.haploid = C.cast(C.cast(v.haploid, C.c_void_p).value + l0, c_u8p)
         cl = int(v.chrom_len)
-        raw = C.string_at(v.chrom_seqs, L * cl)
+        raw = C.string_at(C.cast(v.chrom_seqs, C.c_void_p).value + l0 * cl, L * cl)
         chroms = [raw[l * cl:(l + 1) * cl] for l in range(L)]
         carr = (C.c_char_p * L)(*chroms)
         start = np.full(L, int(v.region_start), np.int32)

@@ -888,11 +888,34 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   CU(put(m[2], block_start, (size_t)batch->n_blocks, s));
   CU(put(m[3], block_ref_end, s));
   CU(put(m[4], locus_block0, s));
-  const int n_slots = (std::min(n_traces, 32768) + 63) / 64 * 64;   // threads in flight; each owns a ~0.4 MB slab
+  // Lanes of a warp run in step when they trace against the same haplotype with the seed at a similar place (same
+  // blocks, same repeat programs, same column counts): process the traces sorted by (locus, haplotype, seed).
+  std::vector<int32_t> order(n_traces);
+  for (int t = 0; t < n_traces; t++) order[t] = t;
+  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+    const DevPool &pa = f.pools[trace_pool[a]], &pb = f.pools[trace_pool[b]];
+    if (pa.locus != pb.locus) return pa.locus < pb.locus;
+    if (trace_hap[a] != trace_hap[b]) return trace_hap[a] < trace_hap[b];
+    if (pa.seed != pb.seed) return pa.seed < pb.seed;
+    return a < b;
+  });
+  // a warp pads every lane's rows to its longest left and its longest right side: the slab holds the widest warp
+  int slab_cols = 2;
+  for (int t0 = 0; t0 < n_traces; t0 += 32) {
+    int left = 0, right = 0;
+    for (int t = t0; t < std::min(n_traces, t0 + 32); t++) {
+      const DevPool& dp = f.pools[trace_pool[order[t]]];
+      left = std::max(left, dp.seed);
+      right = std::max(right, dp.len - dp.seed - 1);
+    }
+    slab_cols = std::max(slab_cols, left + right);
+  }
+  CU(put(m[6], order, s));
+  const int n_slots = (std::min(n_traces, 65536) + 63) / 64 * 64;   // threads in flight; each owns a ~0.4 MB slab
   TraceParams p;
   std::memset(&p, 0, sizeof(p));
-  p.slab_doubles = (int64_t)3 * n_max * l_max;
-  p.art_ints = (int64_t)2 * n_max * HIPSTR_MAX_BLOCKS;
+  p.slab_doubles = (int64_t)3 * slab_cols * l_max;
+  p.art_ints = (int64_t)2 * slab_cols * HIPSTR_MAX_BLOCKS;
   CU(ctx->d_last.reserve((size_t)n_slots * p.slab_doubles * sizeof(double)));
   CU(m[5].reserve((size_t)n_slots * p.art_ints * sizeof(int32_t)));
   const size_t T = (size_t)n_traces;
@@ -900,7 +923,7 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   CU(o[1].reserve(T * (1 + 3 * HIPSTR_MAX_BLOCKS_PER_LOCUS + 4 + 2 * HIPSTR_MAX_TRACE_INDELS + 2 * HIPSTR_MAX_TRACE_SNPS) * sizeof(int32_t)));
   int32_t* di = (int32_t*)o[1].p;
   p.n_traces = n_traces;
-  p.trace_pool = (const int32_t*)m[0].p; p.trace_hap = (const int32_t*)m[1].p;
+  p.trace_pool = (const int32_t*)m[0].p; p.trace_hap = (const int32_t*)m[1].p; p.trace_order = (const int32_t*)m[6].p;
   p.pools = (const DevPool*)d.pools.p; p.bases = (const char*)d.bases.p; p.quals = (const char*)d.quals.p;
   p.hapsides = (const DevHapSide*)d.hapsides.p; p.hapbytes = (const uint8_t*)d.hapbytes.p;
   p.blocks = (const DevBlock*)d.blocks.p; p.reps = (const DevRep*)d.reps.p;

@@ -138,6 +138,7 @@ struct TraceParams {
   int32_t n_traces;
   const int32_t* trace_pool;     /* global pool index */
   const int32_t* trace_hap;      /* haplotype index local to the pool's locus */
+  const int32_t* trace_order;    /* [n_traces] processing order: lane i of the k-th group of 32 handles trace_order[32 k + i] */
   const DevPool* pools;
   const char* bases;
   const char* quals;

@@ -33,12 +33,25 @@ namespace hipstr {
 
 __device__ __forceinline__ double tmax(double a, double b) { return a > b ? a : b; }
 
+/* A per-thread array whose element i lives at p[i * 32]: the 32 lanes of a warp interleave their slabs, and because
+ * all lanes index their matrices with the SAME row pitch (the warp's longest read side), lanes that run the DP in
+ * lockstep touch one 256-byte line per access instead of 32 sectors 0.4 MB apart. */
+template <class T>
+struct Lane {
+  T* p;
+  __device__ __forceinline__ T& operator[](long i) const { return p[i * 32]; }
+  __device__ __forceinline__ Lane operator+(long off) const { return Lane{p + off * 32}; }
+};
+typedef Lane<double> Mat;
+typedef Lane<int> IMat;
+
 // One side of the seed: column k of the side is read base (rev ? n_read-1-k : k).
 struct TSide {
   const uint8_t* bases;   // codes, read order
   const uint8_t* quals;
   const double* lut;      // [256][2]
   int n, rev, n_read;
+  int pitch;              // row pitch of this side's matrices (>= n, uniform across the warp)
   __device__ __forceinline__ int ridx(int k) const { return rev ? n_read - 1 - k : k; }
   __device__ __forceinline__ int code(int k) const { return bases[ridx(k)]; }
   __device__ __forceinline__ double lc(int k) const { return __ldg(lut + 2 * quals[ridx(k)]); }
@@ -114,8 +127,8 @@ __device__ double t_walk(const TSide& sd, const TRep& r, int prog_index, int sto
 }
 
 // Repeat block of one side: the super-row `out_row` from the row above it (HapAligner.cpp:62-109).
-__device__ void t_repeat_block(const TSide& sd, const TRep& r, const double* M_prev, double* M_out, double* I_out,
-                               double* D_out, int* art_size, int* art_pos) {
+__device__ void t_repeat_block(const TSide& sd, const TRep& r, const Mat M_prev, const Mat M_out, const Mat I_out,
+                               const Mat D_out, const IMat art_size, const IMat art_pos) {
   const int B = r.B, p = r.p, n = sd.n;
   for (int j = 0; j < n; j++) {
     double probs[HIPSTR_NUM_ARTIFACTS];
@@ -171,9 +184,10 @@ __device__ void t_repeat_block(const TSide& sd, const TRep& r, const double* M_p
 }
 
 // Full matrices of one side (align_seq_to_hap, HapAligner.cpp:26-161).  Matrices are [row][n].
-__device__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHapSide& hs, double* M, double* I, double* D,
-                              int* art_size, int* art_pos) {
+__device__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHapSide& hs, const Mat M, const Mat I, const Mat D,
+                              const IMat art_size, const IMat art_pos) {
   const int n = sd.n;
+  const long pitch = sd.pitch;
   const uint8_t* seq = P.hapbytes + hs.seq_off;
   const uint8_t* rows = P.hapbytes + hs.row_off;
   double run = 0.0;
@@ -190,9 +204,8 @@ __device__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHa
       TRep r;
       r.s = P.hapbytes + rep->seq_off; r.progs = P.progs; r.logrun = P.prog_logrun; r.rep = rep; r.int_logs = P.int_logs;
       r.B = rep->len; r.p = rep->period; r.left_align = rep->left_align;
-      const size_t out = (size_t)n * (blk.row_start + blk.len - 1);
-      t_repeat_block(sd, r, M + (size_t)n * (blk.row_start - 1), M + out, I + out, D + out, art_size + (size_t)n * b,
-                     art_pos + (size_t)n * b);
+      const long out = pitch * (blk.row_start + blk.len - 1);
+      t_repeat_block(sd, r, M + pitch * (blk.row_start - 1), M + out, I + out, D + out, art_size + pitch * b, art_pos + pitch * b);
       continue;
     }
     for (int row = blk.row_start + (b == 0 ? 1 : 0); row < blk.row_start + blk.len; row++) {
@@ -200,21 +213,21 @@ __device__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHa
       const int info = rows[row], hp = info & 15;
       const bool after = (info & HIPSTR_ROW_AFTER_REPEAT) != 0;
       const double m2m = __ldg(P.trans + hp), m2i = __ldg(P.trans + 16 + hp), m2d = __ldg(P.trans + 32 + hp);
-      size_t at = (size_t)n * row;
+      long at = pitch * row;
       M[at] = sd.emit(0, hc);
       I[at] = after ? T_IMPOSSIBLE : sd.lc(0);
-      D[at] = after ? T_IMPOSSIBLE : tmax(D[at - n] + T_DEL_TO_DEL, M[at - n] + T_DEL_TO_MATCH);
+      D[at] = after ? T_IMPOSSIBLE : tmax(D[at - pitch] + T_DEL_TO_DEL, M[at - pitch] + T_DEL_TO_MATCH);
       at++;
       for (int j = 1; j < n; j++, at++) {
         const double e = sd.emit(j, hc);
         if (after) {
-          M[at] = e + M[at - n - 1];
+          M[at] = e + M[at - pitch - 1];
           I[at] = T_IMPOSSIBLE;
           D[at] = T_IMPOSSIBLE;
         } else {
-          M[at] = e + tmax(I[at - 1] + m2i, tmax(M[at - n - 1] + m2m, D[at - n - 1] + m2d));
-          I[at] = sd.lc(j) + tmax(M[at - n - 1] + T_INS_TO_MATCH, I[at - 1] + T_INS_TO_INS);
-          D[at] = tmax(M[at - n] + T_DEL_TO_MATCH, D[at - n] + T_DEL_TO_DEL);
+          M[at] = e + tmax(I[at - 1] + m2i, tmax(M[at - pitch - 1] + m2m, D[at - pitch - 1] + m2d));
+          I[at] = sd.lc(j) + tmax(M[at - pitch - 1] + T_INS_TO_MATCH, I[at - 1] + T_INS_TO_INS);
+          D[at] = tmax(M[at - pitch] + T_DEL_TO_MATCH, D[at - pitch] + T_DEL_TO_DEL);
         }
       }
     }
@@ -257,9 +270,10 @@ __device__ __forceinline__ int t_pick2(bool rev, double v1, double v2) {        
 // retrace (HapAligner.cpp:363-571) for one side; writes ops BACKWARDS-in-walk order into `ops`
 // (the caller reverses the left side); returns the number of ops.
 __device__ int t_walk_back(const TraceParams& P, const TSide& sd, const DevHapSide& hs, const int32_t* start_of,
-                           const double* M, const double* I, const double* D, const int* art_size, const int* art_pos,
+                           const Mat M, const Mat I, const Mat D, const IMat art_size, const IMat art_pos,
                            int block_index, int base_index, long matrix_index, char* ops, TAcc& acc) {
   const int n = sd.n, nb = hs.n_blocks;
+  const long pitch = sd.pitch;
   const bool rev = sd.rev != 0;
   const uint8_t* seq = P.hapbytes + hs.seq_off;
   const uint8_t* rows = P.hapbytes + hs.row_off;
@@ -269,7 +283,7 @@ __device__ int t_walk_back(const TraceParams& P, const TSide& sd, const DevHapSi
     const DevBlock blk = P.blocks[hs.blk_off + block_index];
     const int fw_block = rev ? nb - 1 - block_index : block_index;
     if (blk.rep >= 0) {
-      const int size = art_size[(size_t)n * block_index + seq_index], pos = art_pos[(size_t)n * block_index + seq_index];
+      const int size = art_size[pitch * block_index + seq_index], pos = art_pos[pitch * block_index + seq_index];
       const int len = blk.len;
       int i = 0;
       for (; i < min(seq_index + 1, pos); i++) { ops[n_ops++] = 'M'; acc.touch(fw_block, sd.ridx(seq_index - i)); }
@@ -278,7 +292,7 @@ __device__ int t_walk_back(const TraceParams& P, const TSide& sd, const DevHapSi
       for (; i < min(len + size, seq_index + 1); i++) { ops[n_ops++] = 'M'; acc.touch(fw_block, sd.ridx(seq_index - i)); }
       acc.stutter[fw_block] = size;
       if (len + size >= seq_index + 1) return n_ops;
-      matrix_index -= (len + size + (long)n * len);
+      matrix_index -= (len + size + pitch * len);
       type = 0;
       seq_index -= (len + size);
     } else {
@@ -310,15 +324,15 @@ __device__ int t_walk_back(const TraceParams& P, const TSide& sd, const DevHapSi
         }
         const double m2m = __ldg(P.trans + hp), m2i = __ldg(P.trans + 16 + hp), m2d = __ldg(P.trans + 32 + hp);
         if (type == 0) {
-          const int best = t_pick3(rev, I[matrix_index - 1] + m2i, D[matrix_index - n - 1] + m2d, M[matrix_index - n - 1] + m2m);
+          const int best = t_pick3(rev, I[matrix_index - 1] + m2i, D[matrix_index - pitch - 1] + m2d, M[matrix_index - pitch - 1] + m2m);
           if (best == 0) { type = 2; matrix_index -= 1; }
-          else { type = best == 1 ? 1 : 0; matrix_index -= n + 1; }
+          else { type = best == 1 ? 1 : 0; matrix_index -= pitch + 1; }
         } else if (type == 1) {
-          type = t_pick2(rev, D[matrix_index - n] + T_DEL_TO_DEL, M[matrix_index - n] + T_DEL_TO_MATCH) == 0 ? 1 : 0;
-          matrix_index -= n;
+          type = t_pick2(rev, D[matrix_index - pitch] + T_DEL_TO_DEL, M[matrix_index - pitch] + T_DEL_TO_MATCH) == 0 ? 1 : 0;
+          matrix_index -= pitch;
         } else {
-          if (t_pick2(rev, I[matrix_index - 1] + T_INS_TO_INS, M[matrix_index - n - 1] + T_INS_TO_MATCH) == 0) { type = 2; matrix_index -= 1; }
-          else { type = 0; matrix_index -= n + 1; }
+          if (t_pick2(rev, I[matrix_index - 1] + T_INS_TO_INS, M[matrix_index - pitch - 1] + T_INS_TO_MATCH) == 0) { type = 2; matrix_index -= 1; }
+          else { type = 0; matrix_index -= pitch + 1; }
         }
       }
     }
@@ -331,22 +345,34 @@ __device__ int t_walk_back(const TraceParams& P, const TSide& sd, const DevHapSi
 __global__ void __launch_bounds__(64) k_trace(const TraceParams P) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_slots = gridDim.x * blockDim.x;
-  for (int tr = slot; tr < P.n_traces; tr += n_slots) {
+  const int lane = threadIdx.x & 31;
+  // whole warps iterate together (idle lanes of the last round still take part in the pitch reduction)
+  for (int tr0 = slot - lane; tr0 < P.n_traces; tr0 += n_slots) {
+    const bool live = tr0 + lane < P.n_traces;
+    const int tr = live ? P.trace_order[tr0 + lane] : 0;   // traces sorted by (locus, haplotype, seed): lanes run in step
+    int my_left = 0, my_right = 0;
+    if (live) {
+      const DevPool pl = P.pools[P.trace_pool[tr]];
+      my_left = pl.seed;
+      my_right = pl.len - pl.seed - 1;
+    }
+    const int pitchL = __reduce_max_sync(0xffffffffu, my_left), pitchR = __reduce_max_sync(0xffffffffu, my_right);
+    if (!live) continue;
     const DevPool pool = P.pools[P.trace_pool[tr]];
     const int h = P.trace_hap[tr];
     const DevHapSide hsF = P.hapsides[pool.hap_rec0 + 2 * h];
     const DevHapSide hsR = P.hapsides[pool.hap_rec0 + 2 * h + 1];
     const int n = pool.len, seed = pool.seed, nL = seed, nR = n - seed - 1, hs_len = hsF.len, nb = hsF.n_blocks;
-    // per-thread slab: [M I D] x (left, right) + artifact tables
-    double* slab = P.slab + (size_t)slot * P.slab_doubles;
-    double* LM = slab; double* LI = LM + (size_t)nL * hs_len; double* LD = LI + (size_t)nL * hs_len;
-    double* RM = LD + (size_t)nL * hs_len; double* RI = RM + (size_t)nR * hs_len; double* RD = RI + (size_t)nR * hs_len;
-    int* arts = P.art_slab + (size_t)slot * P.art_ints;
-    int* Ls = arts; int* Lp = Ls + nL * nb; int* Rs = Lp + nL * nb; int* Rp = Rs + nR * nb;
+    // per-warp slab, lanes interleaved: [M I D] x (left, right) + artifact tables, rows pitchL / pitchR apart
+    const Mat slab{P.slab + (size_t)(slot - lane) * P.slab_doubles + lane};
+    const Mat LM = slab, LI = LM + (long)pitchL * hs_len, LD = LI + (long)pitchL * hs_len;
+    const Mat RM = LD + (long)pitchL * hs_len, RI = RM + (long)pitchR * hs_len, RD = RI + (long)pitchR * hs_len;
+    const IMat arts{P.art_slab + (size_t)(slot - lane) * P.art_ints + lane};
+    const IMat Ls = arts, Lp = Ls + (long)pitchL * nb, Rs = Lp + (long)pitchL * nb, Rp = Rs + (long)pitchR * nb;
     TSide L, R;
     L.bases = (const uint8_t*)P.bases + pool.seq_off; L.quals = (const uint8_t*)P.quals + pool.seq_off; L.lut = P.qual_lut;
-    L.n = nL; L.rev = 0; L.n_read = n;
-    R = L; R.n = nR; R.rev = 1;
+    L.n = nL; L.rev = 0; L.n_read = n; L.pitch = pitchL;
+    R = L; R.n = nR; R.rev = 1; R.pitch = pitchR;
     const double edgeL = t_fill_side(P, L, hsF, LM, LI, LD, Ls, Lp);
     const double edgeR = t_fill_side(P, R, hsR, RM, RI, RD, Rs, Rp);
     // best seed placement (compute_aln_logprob, HapAligner.cpp:163-231)
@@ -356,13 +382,13 @@ __global__ void __launch_bounds__(64) k_trace(const TraceParams P) {
     const int sx = L.bases[seed];
     const double s_ok = __ldg(P.qual_lut + 2 * L.quals[seed]), s_bad = __ldg(P.qual_lut + 2 * L.quals[seed] + 1);
     int max_index = 0;
-    double best = prior + (sx == fseq[0] ? s_ok : s_bad) + edgeL + RM[(size_t)nR * (hs_len - 1) - 1];
+    double best = prior + (sx == fseq[0] ? s_ok : s_bad) + edgeL + RM[(long)pitchR * (hs_len - 2) + nR - 1];
     {
-      const double v = prior + (sx == fseq[hs_len - 1] ? s_ok : s_bad) + edgeR + LM[(size_t)nL * (hs_len - 1) - 1];
+      const double v = prior + (sx == fseq[hs_len - 1] ? s_ok : s_bad) + edgeR + LM[(long)pitchL * (hs_len - 2) + nL - 1];
       if (v > best) { max_index = hs_len - 1; best = v; }
       for (int i = 1; i < hs_len - 1; i++) {
         if (frow[i] & HIPSTR_ROW_REPEAT) continue;
-        const double w = prior + (sx == fseq[i] ? s_ok : s_bad) + LM[(size_t)nL * i - 1] + RM[(size_t)nR * (hs_len - i - 1) - 1];
+        const double w = prior + (sx == fseq[i] ? s_ok : s_bad) + LM[(long)pitchL * (i - 1) + nL - 1] + RM[(long)pitchR * (hs_len - i - 2) + nR - 1];
         if (w > best) { max_index = i; best = w; }
       }
     }
@@ -388,7 +414,7 @@ __global__ void __launch_bounds__(64) k_trace(const TraceParams P) {
     while (fc >= P.blocks[hsF.blk_off + fb].len) { fc -= P.blocks[hsF.blk_off + fb].len; fb++; }
     if (max_index == 0) { for (int i = 0; i < seed; i++) aln[n_left++] = 'S'; }
     else {
-      const long mi = (long)seed * max_index - 1;
+      const long mi = (long)pitchL * (max_index - 1) + seed - 1;
       if (fc == 0) n_left = t_walk_back(P, L, hsF, start_fw, LM, LI, LD, Ls, Lp, fb - 1, P.blocks[hsF.blk_off + fb - 1].len - 1, mi, aln, acc);
       else n_left = t_walk_back(P, L, hsF, start_fw, LM, LI, LD, Ls, Lp, fb, fc - 1, mi, aln, acc);
       for (int a = 0, z = n_left - 1; a < z; a++, z--) { const char c = aln[a]; aln[a] = aln[z]; aln[z] = c; }   // left side is walked backwards
@@ -402,7 +428,7 @@ __global__ void __launch_bounds__(64) k_trace(const TraceParams P) {
     char* right = aln + n_left + 1;
     if (rmax == 0) { for (int i = 0; i < n - 1 - seed; i++) right[n_right++] = 'S'; }
     else {
-      const long mi = (long)(n - 1 - seed) * rmax - 1;
+      const long mi = (long)pitchR * (rmax - 1) + (n - 1 - seed) - 1;
       if (rc == 0) n_right = t_walk_back(P, R, hsR, start_rv, RM, RI, RD, Rs, Rp, rb - 1, P.blocks[hsR.blk_off + rb - 1].len - 1, mi, right, acc);
       else n_right = t_walk_back(P, R, hsR, start_rv, RM, RI, RD, Rs, Rp, rb, rc - 1, mi, right, acc);
     }
