@@ -325,6 +325,9 @@ def load():
     lib.hipstr_genotyper_last_error.argtypes = [vp]
     lib.hipstr_genotyper_genotype.restype = C.c_int32
     lib.hipstr_genotyper_genotype.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, c_u8p]
+    lib.hipstr_genotyper_recompute_stutter_models.restype = C.c_int32
+    lib.hipstr_genotyper_recompute_stutter_models.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_double,
+                                                              C.c_double, c_u8p]
     lib.hipstr_genotyper_stats.restype = C.c_int32
     lib.hipstr_genotyper_stats.argtypes = [vp, c_i64p, c_i64p, c_i32p]
     lib.hipstr_genotyper_timing.restype = C.c_int32
@@ -551,6 +554,15 @@ class Genotyper:
                                                 int(reassemble_flanks), ptr(ok, c_u8p))
         if st != 0:
             raise HipstrError(st, "genotyper_genotype: " + (self.lib.hipstr_genotyper_last_error(self.h) or b"").decode())
+        return ok
+
+    def recompute_stutter_models(self, max_total_haplotypes=1000, max_flank_haplotypes=4, min_flank_freq=0.01, max_em_iter=100,
+                                 abs_ll_converge=0.01, frac_ll_converge=0.001):
+        ok = np.zeros(self.n_loci, np.uint8)
+        st = self.lib.hipstr_genotyper_recompute_stutter_models(self.h, max_total_haplotypes, max_flank_haplotypes, min_flank_freq,
+                                                                max_em_iter, abs_ll_converge, frac_ll_converge, ptr(ok, c_u8p))
+        if st != 0:
+            raise HipstrError(st, "recompute_stutter_models: " + (self.lib.hipstr_genotyper_last_error(self.h) or b"").decode())
         return ok
 
     def stats(self):

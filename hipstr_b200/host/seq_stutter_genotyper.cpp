@@ -1083,6 +1083,85 @@ hipstr_status_t GenotyperBatch::genotype(int max_total_haplotypes, int max_flank
   return HIPSTR_OK;
 }
 
+hipstr_status_t GenotyperBatch::recompute_stutter_models(int max_total_haplotypes, int max_flank_haplotypes, double min_flank_freq,
+                                                         int max_em_iter, double abs_ll_converge, double frac_ll_converge,
+                                                         std::string& err) {
+  if (!ctx_) { err = "no device context"; return HIPSTR_ERR_NO_DEVICE; }
+  std::vector<int> which;
+  for (size_t l = 0; l < loci.size(); l++)
+    if (loci[l].succeeded()) which.push_back((int)l);
+  if (which.empty()) return HIPSTR_OK;
+  // retrace_alignments for the final genotypes
+  std::vector<int> need;
+  for (int l : which) {
+    loci[l].log_ += "Retraining EM stutter genotyper using maximum likelihood alignments\n";
+    if (!loci[l].collect_missing_traces()) need.push_back(l);
+  }
+  hipstr_status_t st = run_traces(need, err);
+  if (st != HIPSTR_OK) return st;
+  // one EM problem per (locus, repeat block)
+  std::vector<int32_t> read_off{0}, sample_off{0}, num_bps, labels, motif, ref_allele;
+  std::vector<double> p1, p2;
+  std::vector<uint8_t> haploid;
+  std::vector<std::pair<int, int> > problem;   // (locus, block)
+  for (int l : which) {
+    SeqStutterGenotyper& g = loci[l];
+    for (int b = 0; b < (int)g.hap_blocks_.size(); b++) {
+      const HapBlock& block = g.hap_blocks_[b];
+      if (block.period <= 0) continue;
+      for (int r = 0; r < g.num_reads_; r++) {
+        if (g.seed_positions_[r] < 0) continue;
+        const AlignmentTrace& t = g.trace_cache_.at(std::make_pair(g.pool_index_[r], g.best_hap_of_read(r)));
+        if (!(t.start < block.start && t.stop > block.end)) continue;
+        num_bps.push_back((int32_t)t.str_seq[b].size() + t.stutter_size[b]);
+        labels.push_back(g.sample_label_[r]);
+        p1.push_back(g.log_p1_[r]);
+        p2.push_back(g.log_p2_[r]);
+      }
+      read_off.push_back((int32_t)num_bps.size());
+      sample_off.push_back(sample_off.back() + g.num_samples_);
+      motif.push_back(block.period);
+      ref_allele.push_back(0);   // the reference passes 0 as the reference allele size (.cpp:1570)
+      haploid.push_back(g.haploid_ ? 1 : 0);
+      problem.emplace_back(l, b);
+    }
+  }
+  hipstr_em_batch_t em;
+  em.n_loci = (int32_t)problem.size();
+  em.locus_read_off = read_off.data();
+  em.locus_sample_off = sample_off.data();
+  em.num_bps = num_bps.data();
+  em.sample_label = labels.data();
+  em.log_p1 = p1.data();
+  em.log_p2 = p2.data();
+  em.motif_len = motif.data();
+  em.ref_allele = ref_allele.data();
+  em.haploid = haploid.data();
+  std::vector<double> params(6 * problem.size()), ll(problem.size());
+  std::vector<uint8_t> converged(problem.size());
+  std::vector<int32_t> iters(problem.size());
+  st = hipstr_em_train_host(ctx_, &em, max_em_iter, abs_ll_converge, frac_ll_converge, params.data(), converged.data(), iters.data(),
+                            ll.data());
+  if (st != HIPSTR_OK) { err = std::string("hipstr_em_train_host: ") + hipstr_last_error(ctx_); return st; }
+  for (size_t k = 0; k < problem.size(); k++) {
+    SeqStutterGenotyper& g = loci[problem[k].first];
+    if (g.phase_ == SeqStutterGenotyper::FAILED) continue;
+    if (!converged[k]) {
+      g.log_ += "Retraining stutter model training failed\n";
+      g.phase_ = SeqStutterGenotyper::FAILED;
+      continue;
+    }
+    std::memcpy(g.hap_blocks_[problem[k].second].stutter, &params[6 * k], 6 * sizeof(double));
+  }
+  for (int l : which) {
+    SeqStutterGenotyper& g = loci[l];
+    if (g.phase_ == SeqStutterGenotyper::FAILED) continue;
+    g.trace_cache_.clear();
+    g.phase_ = SeqStutterGenotyper::ALIGN_ALL;   // genotype() again, from the current allele set
+  }
+  return genotype(max_total_haplotypes, max_flank_haplotypes, min_flank_freq, loci[which[0]].reassemble_flanks_, err);
+}
+
 }  // namespace hipstr
 
 /* ---- C-ABI ------------------------------------------------------------------------------------------ */
@@ -1130,6 +1209,18 @@ hipstr_status_t hipstr_genotyper_genotype(hipstr_genotyper_t* g, int32_t max_tot
   if (!g) return HIPSTR_ERR_BAD_ARG;
   hipstr_status_t st = g->batch.genotype(max_total_haplotypes, max_flank_haplotypes, min_flank_freq, reassemble_flanks != 0,
                                          g->last_error);
+  if (st != HIPSTR_OK) return st;
+  if (locus_ok)
+    for (size_t l = 0; l < g->batch.loci.size(); l++) locus_ok[l] = g->batch.loci[l].succeeded() ? 1 : 0;
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_genotyper_recompute_stutter_models(hipstr_genotyper_t* g, int32_t max_total_haplotypes,
+                                                          int32_t max_flank_haplotypes, double min_flank_freq, int32_t max_em_iter,
+                                                          double abs_ll_converge, double frac_ll_converge, uint8_t* locus_ok) {
+  if (!g) return HIPSTR_ERR_BAD_ARG;
+  hipstr_status_t st = g->batch.recompute_stutter_models(max_total_haplotypes, max_flank_haplotypes, min_flank_freq, max_em_iter,
+                                                         abs_ll_converge, frac_ll_converge, g->last_error);
   if (st != HIPSTR_OK) return st;
   if (locus_ok)
     for (size_t l = 0; l < g->batch.loci.size(); l++) locus_ok[l] = g->batch.loci[l].succeeded() ? 1 : 0;

@@ -164,6 +164,13 @@ class GenotyperBatch {
   hipstr_status_t genotype(int max_total_haplotypes, int max_flank_haplotypes, double min_flank_freq, bool reassemble_flanks,
                            std::string& err);
 
+  /* recompute_stutter_models (.h:195-196, .cpp:1541-1583) of every genotyped locus: the STR sizes observed in the
+   * maximum-likelihood alignments (len(str_seq) + stutter size of every spanning read) train a new stutter model per
+   * repeat block -- one batched K4 call for all loci -- then genotype() runs again with it.  A locus whose training does
+   * not converge fails, like the reference's `return false`. */
+  hipstr_status_t recompute_stutter_models(int max_total_haplotypes, int max_flank_haplotypes, double min_flank_freq, int max_em_iter,
+                                           double abs_ll_converge, double frac_ll_converge, std::string& err);
+
   std::vector<SeqStutterGenotyper> loci;
   int64_t n_alignments = 0, n_traces = 0;
   int n_rounds = 0;

@@ -431,6 +431,15 @@ const char*     hipstr_genotyper_last_error(const hipstr_genotyper_t* g);
 hipstr_status_t hipstr_genotyper_genotype(hipstr_genotyper_t* g, int32_t max_total_haplotypes,
                                           int32_t max_flank_haplotypes, double min_flank_freq,
                                           int32_t reassemble_flanks, uint8_t* locus_ok);
+/* recompute_stutter_models(logger, max_total_haplotypes, max_flank_haplotypes, min_flank_freq, max_em_iter,
+ * abs_ll_converge, frac_ll_converge) (seq_stutter_genotyper.h:195-196, impl .cpp:1541-1583; defaults 100 / 0.01 /
+ * 0.001, genotyper_bam_processor.h:106-108) for every locus whose genotype() succeeded: the STR sizes of the
+ * maximum-likelihood alignments train a new stutter model per repeat block (ONE hipstr_em_train_host call for all
+ * loci), then genotype() runs again.  locus_ok = the method's return value per locus. */
+hipstr_status_t hipstr_genotyper_recompute_stutter_models(hipstr_genotyper_t* g, int32_t max_total_haplotypes,
+                                                          int32_t max_flank_haplotypes, double min_flank_freq,
+                                                          int32_t max_em_iter, double abs_ll_converge,
+                                                          double frac_ll_converge, uint8_t* locus_ok);
 /* alignments (pooled read x haplotype) and traces computed so far, lockstep rounds run */
 hipstr_status_t hipstr_genotyper_stats(const hipstr_genotyper_t* g, int64_t* n_alignments, int64_t* n_traces,
                                        int32_t* n_rounds);

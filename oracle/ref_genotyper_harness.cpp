@@ -141,6 +141,23 @@ int32_t ref_sg_genotype(void* hv, int32_t max_total_haps, int32_t max_flank_haps
   return h->g->genotype(max_total_haps, max_flank_haps, min_flank_freq, h->log) ? 1 : 0;
 }
 
+int32_t ref_sg_recompute_stutter_models(void* hv, int32_t max_total_haps, int32_t max_flank_haps, double min_flank_freq,
+                                        int32_t max_em_iter, double abs_ll, double frac_ll) {
+  RefSG* h = static_cast<RefSG*>(hv);
+  return h->g->recompute_stutter_models(h->log, max_total_haps, max_flank_haps, min_flank_freq, max_em_iter, abs_ll, frac_ll) ? 1 : 0;
+}
+/* the six parameters of the (first) repeat block's current stutter model */
+void ref_sg_stutter_params(void* hv, double* out) {
+  SeqStutterGenotyper* g = static_cast<RefSG*>(hv)->g;
+  for (size_t b = 0; b < g->hap_blocks_.size(); b++)
+    if (g->hap_blocks_[b]->get_repeat_info() != NULL) {
+      StutterModel* m = g->hap_blocks_[b]->get_repeat_info()->get_stutter_model();
+      out[0] = m->get_parameter(true, 'P'); out[1] = m->get_parameter(true, 'U'); out[2] = m->get_parameter(true, 'D');
+      out[3] = m->get_parameter(false, 'P'); out[4] = m->get_parameter(false, 'U'); out[5] = m->get_parameter(false, 'D');
+      return;
+    }
+}
+
 /* Member arrays after genotype(): log_aln_probs_ [R*H], seed_positions_ [R], pool_index_ [R],
  * log_sample_posteriors_ [S*H*H], sample_total_LLs_ [S], optimal haplotypes [S*2], call_sample_ flags [S]. */
 void ref_sg_results(void* hv, double* read_ll, int32_t* seeds, int32_t* pool_index, double* post, double* sample_ll,

@@ -31,6 +31,10 @@ def bind(lib):
     lib.ref_sg_block_seqs.argtypes = [C.c_void_p, C.c_int32, c_i32p, C.c_void_p]
     lib.ref_sg_genotype.restype = C.c_int32
     lib.ref_sg_genotype.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double]
+    lib.ref_sg_recompute_stutter_models.restype = C.c_int32
+    lib.ref_sg_recompute_stutter_models.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double]
+    lib.ref_sg_stutter_params.restype = None
+    lib.ref_sg_stutter_params.argtypes = [C.c_void_p, c_f64p]
     lib.ref_sg_results.restype = None
     lib.ref_sg_results.argtypes = [C.c_void_p, c_f64p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_u8p]
     lib.ref_sg_write_vcf.restype = C.c_int32
@@ -109,6 +113,16 @@ class RefGenotyper:
 
     def genotype(self, max_total_haps=1000, max_flank_haps=4, min_flank_freq=0.01):
         return bool(self.lib.ref_sg_genotype(self.h, max_total_haps, max_flank_haps, min_flank_freq))
+
+    def recompute_stutter_models(self, max_total_haps=1000, max_flank_haps=4, min_flank_freq=0.01, max_em_iter=100, abs_ll=0.01,
+                                 frac_ll=0.001):
+        return bool(self.lib.ref_sg_recompute_stutter_models(self.h, max_total_haps, max_flank_haps, min_flank_freq, max_em_iter,
+                                                             abs_ll, frac_ll))
+
+    def stutter_params(self):
+        out = np.zeros(6)
+        self.lib.ref_sg_stutter_params(self.h, ptr(out, c_f64p))
+        return out
 
     def results(self):
         R, S, H = self.reads.n_reads, self.reads.n_samples, self.lib.ref_sg_num_haps(self.h)

@@ -189,3 +189,54 @@ def test_genotype_loop_matches_reference(name, kw):
         assert changed > 0, "case no longer exercises allele-set changes"
     g.close()
     ctx.close()
+
+
+RECOMPUTE_CASES = [
+    ("stutter_heavy", dict(n_loci=4, n_samples=12, reads_per_sample=20, n_alleles=5, read_len=110, seed=111, stutter_rate=0.25), False),
+    ("with_assembly", dict(n_loci=3, n_samples=8, reads_per_sample=20, n_alleles=4, read_len=120, seed=71, flank_snp_freq=0.3,
+                           stutter_rate=0.15), True),
+    ("period2", dict(n_loci=3, n_samples=8, reads_per_sample=15, n_alleles=5, read_len=110, seed=41, period=2, ref_copies=15,
+                     stutter_rate=0.3), True),
+]
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw,assemble", RECOMPUTE_CASES, ids=[c[0] for c in RECOMPUTE_CASES])
+def test_recompute_stutter_models_matches_reference(name, kw, assemble):
+    """genotype() -> recompute_stutter_models() (K5 traces -> one batched K4 EM call -> genotype() again) against the
+    reference's method: same success flags, allele sets and genotypes; the learned stutter parameters show in the VCF INFO
+    fields and, to full precision, in the log-likelihoods computed under them."""
+    from hipstr_b200.capi import Context, Genotyper
+    from ref_genotyper import LocusReads, RefGenotyper
+    s = Synth(**kw)
+    ctx = Context(0)
+    g = Genotyper.from_synth_reads(ctx, s)
+    ok1 = g.genotype(1000, 4, 0.01, assemble)
+    ok2 = g.recompute_stutter_models()
+    names = ["S%d" % i for i in range(kw["n_samples"])]
+    reads = [LocusReads(s, l) for l in range(s.n_loci)]
+    loci = g.vcf_loci(["chrS"] * s.n_loci, ["STR"] * s.n_loci, [rd.region[0] for rd in reads], [rd.region[1] for rd in reads],
+                      [rd.period for rd in reads], [rd.chrom_seq for rd in reads], names * s.n_loci, names)
+    records = g.write_vcf(loci)
+    n_changed = 0
+    for l in range(s.n_loci):
+        r = RefGenotyper(reads[l], reassemble_flanks=assemble)
+        assert r.genotype() == bool(ok1[l])
+        if not ok1[l]:
+            continue
+        want_ok = r.recompute_stutter_models()
+        assert want_ok == bool(ok2[l]), (l, g.log(l)[-600:], r.log()[-600:])
+        if not want_ok:
+            continue
+        n_changed += not np.allclose(r.stutter_params(), (0.95, 0.05, 0.05, 0.95, 0.01, 0.01))
+        assert g.blocks(l) == [b[3] for b in r.blocks()], l
+        w, o = r.results(), g.results(l)
+        assert np.array_equal(o["best"], w["best"]) and np.array_equal(o["call_ok"], w["call_ok"])
+        assert np.abs(o["read_ll"] - w["read_ll"]).max() <= 1e-4
+        assert np.abs(o["read_ll"] - w["read_ll"]).max() <= 1e-8, np.abs(o["read_ll"] - w["read_ll"]).max()
+        assert np.abs(o["post"] - w["post"]).max() <= 1e-6
+        assert records[l][1].replace(":-0.00:", ":0.00:") == r.vcf().rstrip("\n").replace(":-0.00:", ":0.00:")
+    assert n_changed > 0
+    g.close()
+    ctx.close()
