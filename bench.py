@@ -119,7 +119,7 @@ def cpu_full_loop(synth, cores):
             "sample": "first %d loci, one per core: constructor + genotype(flank assembly on) + write_vcf_record, %.1f s wall" % (n, wall)}
 
 
-def gpu_full_loop(device, synth, pipelines):
+def gpu_full_loop(device, synth, pipelines, gather=None, locus_base=0):
     """Seam B1 end to end on the GPU: hipstr_genotyper_create_from_reads -> genotype (flank assembly on) -> write_vcf.
     The loci are split into `pipelines` windows, each driven by its own host thread and context, so that the host stages
     of one window (per-locus decisions, trace stitching, VCF text) overlap the device stages of another."""
@@ -139,7 +139,8 @@ def gpu_full_loop(device, synth, pipelines):
         loci = g.vcf_loci(["chr1"] * n, ["STR%d" % l for l in range(l0, l1)], [synth.view.region_start] * n, [synth.view.region_stop] * n,
                           [period] * n, [raw[l * cl:(l + 1) * cl] for l in range(l0, l1)], names * n, names)
         rec = g.write_vcf(loci)
-        out[k] = (int(ok.sum()), sum(r is not None for r in rec), g.stats(), g.timing())
+        out[k] = (int(ok.sum()), sum(r is not None for r in rec), g.stats(), g.timing(),
+                  [(locus_base + l0 + i, "chr1", r[0], r[1]) for i, r in enumerate(rec) if r is not None])
         g.close()
 
     best = None
@@ -151,7 +152,10 @@ def gpu_full_loop(device, synth, pipelines):
             th.start()
         for th in threads:
             th.join()
-        dt = time.perf_counter() - t0
+        if gather is not None:   # N > 1: the one collective, finished records to rank 0 (inside the timed region)
+            dt = gather([r for o in out for r in o[4]], t0)
+        else:
+            dt = time.perf_counter() - t0
         stages = {}
         for o in out:
             for k, v in o[3].items():
@@ -441,9 +445,26 @@ def main():
     if clocks:
         clocks.stop()
     full_loop = None
-    if rank == 0 and world == 1 and not a.no_full_loop:
-        full_loop = gpu_full_loop(local, s, 1)
-        full_loop["pipelined"] = gpu_full_loop(local, s, 4)
+    if not a.no_full_loop:
+        if world == 1:
+            full_loop = gpu_full_loop(local, s, 1)
+            full_loop["pipelined"] = gpu_full_loop(local, s, 4)
+        else:
+            from hipstr_b200.sharding import gather_vcf_records
+            n_merged = [0]
+
+            def gather(records, t0):
+                merged = gather_vcf_records(records, device=dev)
+                barrier()
+                if merged is not None:
+                    n_merged[0] = len(merged)
+                return max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            full_loop = gpu_full_loop(local, s, 4, gather=gather, locus_base=rank * a.loci)
+            full_loop["loci"] = world * a.loci
+            full_loop["loci_per_s"] = world * a.loci / full_loop["seconds"]
+            full_loop["records_on_rank0"] = n_merged[0]
+            full_loop["note"] = "every rank genotypes its own loci; VCF records gathered to rank 0 over NCCL inside the timed region; per-rank counters are rank 0's"
 
     if rank == 0:
         peaks, peak_src = None, "fallback"

@@ -82,3 +82,51 @@ def test_two_rank_gloo_gather_matches_single_rank(tmp_path):
     assert merged.shape == want.shape
     assert np.array_equal(merged[:, 0], want[:, 0])          # rank 0 feeds records in locus (position) order
     assert np.array_equal(merged[:, 1], want[:, 1])
+
+
+def _records_of(l0, l1):
+    """Fake per-locus VCF records with out-of-order positions inside the writer's 50-bp tolerance."""
+    return [(l, "chr1" if l < 4 else "chr2", 1000 + 100 * l - (30 if l % 3 == 1 else 0), "chrX\t%d\tSTR%d\tpayload-%s" % (l, l, "x" * (l % 5)))
+            for l in range(l0, l1)]
+
+
+def _record_worker(rank, world, port, n_loci, out_path):
+    sys.path.insert(0, ROOT)
+    from hipstr_b200.capi import load
+    from hipstr_b200.sharding import gather_vcf_records, shard_bounds, write_records
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    l0, l1 = shard_bounds(n_loci, rank, world)
+    merged = gather_vcf_records(_records_of(l0, l1))
+    if rank == 0:
+        lib = load()
+        w = lib.hipstr_vcf_writer_open(out_path.encode())
+        lib.hipstr_vcf_writer_header(w, b"##header\n")
+        write_records(merged, w, lib)
+        lib.hipstr_vcf_writer_close(w)
+    else:
+        assert merged is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_vcf_records_gathered_to_rank0_in_locus_order(tmp_path, world):
+    """Sharded loci -> gather_vcf_records -> hipstr::VCFWriter on rank 0 writes the same file a single rank would."""
+    sys.path.insert(0, ROOT)
+    from hipstr_b200.capi import load
+    from hipstr_b200.sharding import pack_records, unpack_records, write_records
+    n_loci = 8
+    recs = _records_of(0, n_loci)
+    assert unpack_records(pack_records(recs)) == recs
+    single = str(tmp_path / "single.vcf")
+    lib = load()
+    w = lib.hipstr_vcf_writer_open(single.encode())
+    lib.hipstr_vcf_writer_header(w, b"##header\n")
+    write_records(recs, w, lib)
+    lib.hipstr_vcf_writer_close(w)
+    sharded = str(tmp_path / "sharded.vcf")
+    mp.spawn(_record_worker, args=(world, _free_port(), n_loci, sharded), nprocs=world, join=True)
+    assert open(sharded).read() == open(single).read()
+    assert open(single).read().count("\n") == n_loci + 1
