@@ -448,7 +448,7 @@ def main():
     if not a.no_full_loop:
         if world == 1:
             full_loop = gpu_full_loop(local, s, 1)
-            full_loop["pipelined"] = gpu_full_loop(local, s, 4)
+            full_loop["pipelined"] = gpu_full_loop(local, s, 3)
         else:
             from hipstr_b200.sharding import gather_vcf_records
             n_merged = [0]
@@ -460,7 +460,7 @@ def main():
                     n_merged[0] = len(merged)
                 return max_over_ranks(time.perf_counter() - t0)
             barrier()
-            full_loop = gpu_full_loop(local, s, 4, gather=gather, locus_base=rank * a.loci)
+            full_loop = gpu_full_loop(local, s, 3, gather=gather, locus_base=rank * a.loci)
             full_loop["loci"] = world * a.loci
             full_loop["loci_per_s"] = world * a.loci / full_loop["seconds"]
             full_loop["records_on_rank0"] = n_merged[0]

@@ -889,12 +889,17 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   CU(put(m[3], block_ref_end, s));
   CU(put(m[4], locus_block0, s));
   // Lanes of a warp run in step when they trace against the same haplotype with the seed at a similar place (same
-  // blocks, same repeat programs, same column counts): process the traces sorted by (locus, haplotype, seed).
+  // blocks, same repeat programs, same column counts): process the traces sorted by (locus, seed in the left / right
+  // half of the read, haplotype, seed).  The half comes before the haplotype so that a warp that straddles two
+  // haplotypes still has all its seeds on one side -- its padded rows (longest left + longest right side) stay near
+  // one read length instead of two.
   std::vector<int32_t> order(n_traces);
   for (int t = 0; t < n_traces; t++) order[t] = t;
   std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
     const DevPool &pa = f.pools[trace_pool[a]], &pb = f.pools[trace_pool[b]];
     if (pa.locus != pb.locus) return pa.locus < pb.locus;
+    const bool ha = 2 * pa.seed >= pa.len, hb = 2 * pb.seed >= pb.len;
+    if (ha != hb) return hb;
     if (trace_hap[a] != trace_hap[b]) return trace_hap[a] < trace_hap[b];
     if (pa.seed != pb.seed) return pa.seed < pb.seed;
     return a < b;
@@ -911,11 +916,14 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
     slab_cols = std::max(slab_cols, left + right);
   }
   CU(put(m[6], order, s));
-  const int n_slots = (std::min(n_traces, 65536) + 63) / 64 * 64;   // threads in flight; each owns a ~0.4 MB slab
   TraceParams p;
   std::memset(&p, 0, sizeof(p));
   p.slab_doubles = (int64_t)3 * slab_cols * l_max;
   p.art_ints = (int64_t)2 * slab_cols * HIPSTR_MAX_BLOCKS;
+  // threads in flight: each owns a ~0.4 MB slab; at most 65536 of them and at most 24 GB of slabs per context
+  const int64_t slab_budget = (int64_t)24 << 30;
+  const int by_budget = (int)std::max<int64_t>(64, slab_budget / (p.slab_doubles * (int64_t)sizeof(double)) / 64 * 64);
+  const int n_slots = std::min((std::min(n_traces, 65536) + 63) / 64 * 64, by_budget);
   CU(ctx->d_last.reserve((size_t)n_slots * p.slab_doubles * sizeof(double)));
   CU(m[5].reserve((size_t)n_slots * p.art_ints * sizeof(int32_t)));
   const size_t T = (size_t)n_traces;
