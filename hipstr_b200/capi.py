@@ -39,7 +39,7 @@ class SynthCfg(C.Structure):
         ("n_loci", C.c_int32), ("n_samples", C.c_int32), ("reads_per_sample", C.c_int32), ("n_alleles", C.c_int32),
         ("read_len", C.c_int32), ("trim", C.c_int32), ("period", C.c_int32), ("ref_copies", C.c_int32),
         ("seed", C.c_uint64), ("stutter_rate", C.c_double), ("sub_rate", C.c_double), ("mate_rate", C.c_double),
-        ("flank_snp_freq", C.c_double),
+        ("flank_snp_freq", C.c_double), ("haploid", C.c_int32),
     ]
 
 
@@ -383,10 +383,10 @@ class Synth:
     """A batch of synthetic loci owned by libhipstr_synth.so."""
 
     def __init__(self, n_loci, n_samples, reads_per_sample, n_alleles, read_len, seed=1, trim=1, period=4,
-                 ref_copies=12, stutter_rate=0.05, sub_rate=1.0 / 200, mate_rate=0.0, flank_snp_freq=0.0):
+                 ref_copies=12, stutter_rate=0.05, sub_rate=1.0 / 200, mate_rate=0.0, flank_snp_freq=0.0, haploid=0):
         lib = load_synth()
         self.cfg = SynthCfg(n_loci, n_samples, reads_per_sample, n_alleles, read_len, trim, period, ref_copies, seed,
-                            stutter_rate, sub_rate, mate_rate, flank_snp_freq)
+                            stutter_rate, sub_rate, mate_rate, flank_snp_freq, haploid)
         self._h = lib.hipstr_synth_create(C.byref(self.cfg))
         self.view = lib.hipstr_synth_view(self._h).contents
         v, b = self.view, self.view.batch

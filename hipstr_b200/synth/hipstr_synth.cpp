@@ -128,11 +128,12 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
     }
     for (int s = 0; s < cfg.n_samples; s++) {
       int gt[2] = {uni(0, A - 1), uni(0, A - 1)};
+      if (cfg.haploid) gt[1] = gt[0];
       S->true_gt.push_back(gt[0]); S->true_gt.push_back(gt[1]);
       bool carries[2][2] = {{false, false}, {false, false}};   // [chromosome copy][left / right SNP]
       if (cfg.flank_snp_freq > 0)
         for (int c = 0; c < 2; c++)
-          for (int side = 0; side < 2; side++) carries[c][side] = unif() < cfg.flank_snp_freq;
+          for (int side = 0; side < 2; side++) carries[c][side] = (cfg.haploid && c == 1) ? carries[0][side] : unif() < cfg.flank_snp_freq;
       for (int r = 0; r < cfg.reads_per_sample; r++) {
         const int copy = rng() & 1;
         int k = copies[gt[copy]];
@@ -243,7 +244,7 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
     S->locus_read_off.push_back((int32_t)S->pool_index.size());
     S->locus_sample_off.push_back(S->locus_sample_off.back() + cfg.n_samples);
     S->n_haps.push_back(A);
-    S->haploid.push_back(0);
+    S->haploid.push_back(cfg.haploid ? 1 : 0);
     read_ll_size += (int64_t)R * A;
     post_size += (int64_t)cfg.n_samples * A * A;
   }

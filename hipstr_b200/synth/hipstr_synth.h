@@ -27,6 +27,7 @@ typedef struct {
   double mate_rate;         /* P(read is followed by an adjacent second mate), default 0 */
   double flank_snp_freq;    /* population frequency of a planted SNP 15 bp upstream and one 12 bp downstream of
                                the STR (each sample chromosome draws them independently), default 0 */
+  int32_t haploid;          /* 1 = haploid loci (one chromosome copy per sample, Genotyper's haploid_ flag), default 0 */
 } hipstr_synth_cfg_t;
 
 typedef struct {

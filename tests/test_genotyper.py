@@ -139,6 +139,9 @@ LOOP_CASES = [
                                       flank_snp_freq=0.03, assemble=True)),
     ("assembly_low_frequency_pruned", dict(n_loci=4, n_samples=30, reads_per_sample=10, n_alleles=4, read_len=120, seed=81,
                                            flank_snp_freq=0.03, assemble=True, min_flank_freq=0.1)),
+    ("haploid", dict(n_loci=4, n_samples=8, reads_per_sample=15, n_alleles=5, read_len=110, seed=121, stutter_rate=0.2, haploid=1)),
+    ("haploid_assembly", dict(n_loci=3, n_samples=8, reads_per_sample=15, n_alleles=4, read_len=120, seed=131, flank_snp_freq=0.3, haploid=1,
+                              assemble=True)),
     ("assembly_stutter_and_flanks", dict(n_loci=4, n_samples=6, reads_per_sample=25, n_alleles=3, read_len=110, seed=101,
                                          stutter_rate=0.3, flank_snp_freq=0.25, assemble=True)),
 ]

@@ -72,6 +72,10 @@ VCF_CASES = [
                                stutter_rate=0.25, assemble=True), {}),
     ("low_coverage_some_empty_samples", dict(n_loci=4, n_samples=25, reads_per_sample=2, n_alleles=6, read_len=150, seed=33, assemble=True),
      dict(output_filters=1, output_pls=1)),
+    ("haploid", dict(n_loci=3, n_samples=8, reads_per_sample=15, n_alleles=5, read_len=110, seed=121, stutter_rate=0.2, haploid=1, assemble=True),
+     dict(output_gls=1, output_pls=1, output_filters=1)),
+    ("haploid_flanks_haplotype_data", dict(n_loci=3, n_samples=8, reads_per_sample=15, n_alleles=4, read_len=120, seed=131, flank_snp_freq=0.3,
+                                           haploid=1, assemble=True), dict(output_haplotype_data=1, output_phased_gls=1)),
     ("period2", dict(n_loci=3, n_samples=6, reads_per_sample=15, n_alleles=5, read_len=110, seed=41, period=2, ref_copies=15,
                      stutter_rate=0.3, sub_rate=0.02, assemble=True), {}),
 ]
