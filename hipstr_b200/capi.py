@@ -53,7 +53,7 @@ class SynthView(C.Structure):
         ("read_seq_off", c_i32p), ("read_bases", C.c_void_p), ("read_quals", C.c_void_p), ("read_start", c_i32p),
         ("read_cigar_off", c_i32p), ("read_cigar_type", C.c_void_p), ("read_cigar_len", c_i32p),
         ("read_name_id", c_i32p), ("block_start", c_i32p), ("block_end", c_i32p), ("chrom_len", C.c_int32),
-        ("chrom_seqs", C.c_void_p), ("region_start", C.c_int32), ("region_stop", C.c_int32), ("read_rev_strand", c_u8p),
+        ("chrom_seqs", C.c_void_p), ("region_start", C.c_int32), ("region_stop", C.c_int32), ("read_stop", c_i32p), ("read_rev_strand", c_u8p),
     ]
 
 
@@ -71,7 +71,7 @@ class LocusReadsStruct(C.Structure):
     _fields_ = [("locus_read_off", c_i32p), ("locus_sample_off", c_i32p), ("read_seq_off", c_i32p), ("bases", C.c_void_p),
                 ("quals", C.c_void_p), ("read_start", c_i32p), ("cigar_off", c_i32p), ("cigar_type", C.c_void_p),
                 ("cigar_len", c_i32p), ("sample_label", c_i32p), ("name_id", c_i32p), ("log_p1", c_f64p), ("log_p2", c_f64p),
-                ("haploid", c_u8p), ("rev_strand", c_u8p)]
+                ("haploid", c_u8p), ("rev_strand", c_u8p), ("read_stop", c_i32p)]
 
 
 class VcfLoci(C.Structure):
@@ -312,6 +312,24 @@ def load():
                                          c_f64p]
     lib.hipstr_last_traffic.restype = None
     lib.hipstr_last_traffic.argtypes = [vp, c_i64p, c_i64p, c_i32p]
+    lib.hipstr_nw_align_batch_host.restype = C.c_int32
+    lib.hipstr_nw_align_batch_host.argtypes = [vp, C.c_int32, c_i32p, C.c_char_p, c_i32p, C.c_char_p, C.c_int32, C.c_int32,
+                                               C.c_void_p, c_i32p, C.POINTER(C.c_float)]
+    lib.hipstr_left_align_reads_host.restype = C.c_int32
+    lib.hipstr_left_align_reads_host.argtypes = [vp, C.c_int32, C.POINTER(LocusReadsStruct), C.POINTER(C.c_char_p), c_i32p, c_i32p,
+                                                 C.POINTER(vp)]
+    lib.hipstr_left_aligned_reads.restype = C.POINTER(LocusReadsStruct)
+    lib.hipstr_left_aligned_reads.argtypes = [vp]
+    lib.hipstr_left_aligned_source.restype = c_i32p
+    lib.hipstr_left_aligned_source.argtypes = [vp, c_i64p]
+    lib.hipstr_left_aligned_counts.restype = None
+    lib.hipstr_left_aligned_counts.argtypes = [vp, c_i64p, c_i64p]
+    lib.hipstr_left_aligned_free.restype = None
+    lib.hipstr_left_aligned_free.argtypes = [vp]
+    lib.hipstr_left_align_one.restype = C.c_int32
+    lib.hipstr_left_align_one.argtypes = [C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, c_i32p, C.c_char_p,
+                                          C.c_int32, C.c_int32, C.c_int32, C.c_char_p, c_i32p, c_i32p, C.c_char_p, C.c_char_p,
+                                          c_i32p, C.c_char_p, c_i32p]
     lib.hipstr_hap_aln_to_ref.restype = C.c_int32
     lib.hipstr_hap_aln_to_ref.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p]
     lib.hipstr_genotyper_create.restype = C.c_int32
@@ -479,6 +497,95 @@ def blocks_batch(loci_blocks, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01)):
     return b, np.array(starts, np.int32), np.array(ends, np.int32)
 
 
+def make_locus_reads(locus_read_off, locus_sample_off, reads, sample_label, name_id, log_p1, log_p2, haploid, rev_strand=None):
+    """hipstr_locus_reads_t from Python lists: reads = [(start, stop, bases, quals, [(op, len)])] over all loci."""
+    so, co = [0], [0]
+    bases, quals, ctype, clen = bytearray(), bytearray(), bytearray(), []
+    for start, stop, b, q, cig in reads:
+        bases += b.encode()
+        quals += q.encode()
+        so.append(len(bases))
+        for t, n in cig:
+            ctype += t.encode()
+            clen.append(n)
+        co.append(len(clen))
+    keep = dict(lro=np.ascontiguousarray(locus_read_off, np.int32), lso=np.ascontiguousarray(locus_sample_off, np.int32),
+                so=np.array(so, np.int32), bases=np.frombuffer(bytes(bases) + b"\0", np.uint8).copy(),
+                quals=np.frombuffer(bytes(quals) + b"\0", np.uint8).copy(), start=np.array([r[0] for r in reads], np.int32),
+                stop=np.array([r[1] for r in reads], np.int32), co=np.array(co, np.int32),
+                ctype=np.frombuffer(bytes(ctype) + b"\0", np.uint8).copy(), clen=np.array(clen + [0], np.int32),
+                label=np.ascontiguousarray(sample_label, np.int32), name=np.ascontiguousarray(name_id, np.int32),
+                p1=np.ascontiguousarray(log_p1, np.float64), p2=np.ascontiguousarray(log_p2, np.float64),
+                hap=np.ascontiguousarray(haploid, np.uint8),
+                rev=np.ascontiguousarray(rev_strand if rev_strand is not None else np.zeros(len(reads)), np.uint8))
+    rs = LocusReadsStruct(ptr(keep["lro"], c_i32p), ptr(keep["lso"], c_i32p), ptr(keep["so"], c_i32p), keep["bases"].ctypes.data,
+                          keep["quals"].ctypes.data, ptr(keep["start"], c_i32p), ptr(keep["co"], c_i32p), keep["ctype"].ctypes.data,
+                          ptr(keep["clen"], c_i32p), ptr(keep["label"], c_i32p), ptr(keep["name"], c_i32p), ptr(keep["p1"], c_f64p),
+                          ptr(keep["p2"], c_f64p), ptr(keep["hap"], c_u8p), ptr(keep["rev"], c_u8p), ptr(keep["stop"], c_i32p))
+    rs._keep = keep
+    return rs
+
+
+def read_locus_reads(rs, n_loci):
+    """The reads of a hipstr_locus_reads_t back as Python tuples [(start, stop, bases, quals, [(op, len)])] + locus_read_off."""
+    lro = np.ctypeslib.as_array(rs.locus_read_off, shape=(n_loci + 1,)).copy()
+    R = int(lro[-1])
+    if R == 0:
+        return [], lro
+    so = np.ctypeslib.as_array(rs.read_seq_off, shape=(R + 1,))
+    co = np.ctypeslib.as_array(rs.cigar_off, shape=(R + 1,))
+    bases = C.string_at(rs.bases, int(so[-1]))
+    quals = C.string_at(rs.quals, int(so[-1]))
+    ctype = C.string_at(rs.cigar_type, int(co[-1]))
+    clen = np.ctypeslib.as_array(rs.cigar_len, shape=(max(int(co[-1]), 1),))
+    start = np.ctypeslib.as_array(rs.read_start, shape=(R,))
+    stop = np.ctypeslib.as_array(rs.read_stop, shape=(R,))
+    out = []
+    for r in range(R):
+        out.append((int(start[r]), int(stop[r]), bases[so[r]:so[r + 1]].decode(), quals[so[r]:so[r + 1]].decode(),
+                    [(ctype[c:c + 1].decode(), int(clen[c])) for c in range(co[r], co[r + 1])]))
+    return out, lro
+
+
+class LeftAligned:
+    """hipstr_left_aligned_t: the result of hipstr_left_align_reads_host (owns a hipstr_locus_reads_t)."""
+
+    def __init__(self, ctx, n_loci, raw, chrom_seqs, trim_start=None, trim_stop=None):
+        self.lib, self.n_loci = load(), n_loci
+        chroms = [c if isinstance(c, bytes) else c.encode() for c in chrom_seqs]
+        carr = (C.c_char_p * n_loci)(*chroms)
+        ts = None if trim_start is None else np.ascontiguousarray(trim_start, np.int32)
+        te = None if trim_stop is None else np.ascontiguousarray(trim_stop, np.int32)
+        self._keep = (raw, chroms, carr, ts, te)
+        h = C.c_void_p()
+        st = self.lib.hipstr_left_align_reads_host(ctx.h if ctx else None, n_loci, C.byref(raw), carr, ptr(ts, c_i32p), ptr(te, c_i32p),
+                                                   C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "left_align_reads_host")
+        self.h = h
+        self.view = self.lib.hipstr_left_aligned_reads(h).contents
+        n = C.c_int64()
+        src = self.lib.hipstr_left_aligned_source(h, C.byref(n))
+        self.source = np.ctypeslib.as_array(src, shape=(n.value,)).copy() if n.value else np.zeros(0, np.int32)
+        a, b = C.c_int64(), C.c_int64()
+        self.lib.hipstr_left_aligned_counts(h, C.byref(a), C.byref(b))
+        self.failed, self.nw_alignments = a.value, b.value
+
+    def reads(self):
+        return read_locus_reads(self.view, self.n_loci)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hipstr_left_aligned_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Genotyper:
     """hipstr_genotyper_t: a batch of loci run through the SeqStutterGenotyper::genotype() loop on the GPU."""
 
@@ -498,7 +605,7 @@ class Genotyper:
         v = synth.view
         return LocusReadsStruct(v.locus_read_off, v.locus_sample_off, v.read_seq_off, v.read_bases, v.read_quals, v.read_start,
                                 v.read_cigar_off, v.read_cigar_type, v.read_cigar_len, v.sample_label, v.read_name_id,
-                                v.log_p1, v.log_p2, v.haploid, v.read_rev_strand)
+                                v.log_p1, v.log_p2, v.haploid, v.read_rev_strand, v.read_stop)
 
     @classmethod
     def from_synth_reads(cls, ctx, synth, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01), loci_range=None):
@@ -810,6 +917,24 @@ class Context:
         st, out = trace_batch(self.lib.hipstr_trace_batch_host, batch, block_start, trace_pool, trace_hap, aln_stride, self.h)
         self._check(st, "trace_batch_host")
         return out
+
+    def nw_align(self, refs, reads, use_ref_end_penalty=False):
+        """hipstr_nw_align_batch_host on lists of str -> ([ops], scores float32)."""
+        n = len(refs)
+        ro = np.zeros(n + 1, np.int32)
+        qo = np.zeros(n + 1, np.int32)
+        ro[1:] = np.cumsum([len(r) for r in refs])
+        qo[1:] = np.cumsum([len(r) for r in reads])
+        stride = max(len(a) for a in refs) + max(len(b) for b in reads) + 2
+        ops = np.zeros(n * stride, np.uint8)
+        lens = np.zeros(n, np.int32)
+        score = np.zeros(n, np.float32)
+        self._check(self.lib.hipstr_nw_align_batch_host(self.h, n, ptr(ro, c_i32p), "".join(refs).encode(), ptr(qo, c_i32p),
+                                                        "".join(reads).encode(), int(use_ref_end_penalty), stride, ops.ctypes.data,
+                                                        ptr(lens, c_i32p), score.ctypes.data_as(C.POINTER(C.c_float))),
+                    "nw_align_batch_host")
+        raw = ops.reshape(n, stride)
+        return [bytes(raw[i, :max(int(lens[i]), 0)]).decode() if lens[i] >= 0 else None for i in range(n)], score
 
     def em_train(self, batch, max_iter=100, min_abs=0.01, min_frac=0.001):
         """hipstr_em_train_host -> (params [L][6], converged [L], iterations [L], final LL [L])."""

@@ -828,6 +828,56 @@ hipstr_status_t hipstr_extract_genotypes_host(hipstr_ctx_t* ctx, int32_t n_loci,
   return HIPSTR_OK;
 }
 
+hipstr_status_t hipstr_nw_align_batch_host(hipstr_ctx_t* ctx, int32_t n_pairs, const int32_t* ref_off, const char* ref_seqs,
+                                           const int32_t* read_off, const char* read_seqs, int32_t use_ref_end_penalty,
+                                           int32_t ops_stride, char* ops, int32_t* ops_len, float* score) {
+  if (!ctx || n_pairs < 0) return HIPSTR_ERR_BAD_ARG;
+  if (n_pairs == 0) return HIPSTR_OK;
+  if (!ref_off || !ref_seqs || !read_off || !read_seqs || !ops || !ops_len || !score) return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
+  int max_ref = 1, max_read = 1;
+  for (int i = 0; i < n_pairs; i++) {
+    const int l1 = ref_off[i + 1] - ref_off[i], l2 = read_off[i + 1] - read_off[i];
+    if (l1 < 1 || l2 < 1) return fail(ctx, HIPSTR_ERR_BAD_ARG, "empty sequence in an alignment pair");
+    max_ref = std::max(max_ref, l1);
+    max_read = std::max(max_read, l2);
+  }
+  if (ops_stride < max_ref + max_read + 1) return fail(ctx, HIPSTR_ERR_BAD_ARG, "ops_stride too small");
+  if (nw_shared_bytes(max_ref, max_read) > (size_t)227 * 1024)
+    return fail(ctx, HIPSTR_ERR_UNSUPPORTED, "window x read exceeds the shared-memory trace (227 KB)");
+  cudaStream_t s = ctx->stream;
+  DevBuf* m = ctx->d_misc;
+  DevBuf* o = ctx->d_out;
+  CU(put(m[0], ref_off, (size_t)n_pairs + 1, s));
+  CU(put(m[1], ref_seqs, (size_t)ref_off[n_pairs], s));
+  CU(put(m[2], read_off, (size_t)n_pairs + 1, s));
+  CU(put(m[3], read_seqs, (size_t)read_off[n_pairs], s));
+  const size_t T = (size_t)n_pairs;
+  CU(o[0].reserve(T * ops_stride));
+  CU(o[1].reserve(T * sizeof(int32_t)));
+  CU(o[2].reserve(T * sizeof(float)));
+  NwParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n_pairs = n_pairs;
+  p.ref_off = (const int32_t*)m[0].p; p.ref_seqs = (const char*)m[1].p;
+  p.read_off = (const int32_t*)m[2].p; p.read_seqs = (const char*)m[3].p;
+  p.use_ref_end_penalty = use_ref_end_penalty ? 1 : 0;
+  p.max_ref = max_ref; p.max_read = max_read; p.ops_stride = ops_stride;
+  p.out_ops = (char*)o[0].p; p.out_len = (int32_t*)o[1].p; p.out_score = (float*)o[2].p;
+  // one warp per CTA; a few waves of CTAs per SM keep the tail short
+  int n_sm = 148;
+  CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+  CU(launch_nw(p, n_sm * 8, s));
+  ctx->last_launches = 1;
+  CU(get(ctx, ops, p.out_ops, T * ops_stride));
+  CU(get(ctx, ops_len, p.out_len, T));
+  CU(get(ctx, score, p.out_score, T));
+  CU(cudaStreamSynchronize(s));
+  end_call(ctx);
+  return HIPSTR_OK;
+}
+
 hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch, const int32_t* block_start,
                                         int32_t n_traces, const int32_t* trace_pool, const int32_t* trace_hap,
                                         const hipstr_trace_out_t* out) {

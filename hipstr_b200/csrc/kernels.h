@@ -166,5 +166,22 @@ struct TraceParams {
 };
 cudaError_t launch_trace(const TraceParams& p, int n_slots, cudaStream_t stream);
 
+/* ---- K6: batched Needleman-Wunsch (nw.cu) -------------------------------------------------- */
+struct NwParams {
+  int32_t n_pairs;
+  const int32_t* ref_off;    /* [n_pairs+1] into ref_seqs */
+  const char* ref_seqs;
+  const int32_t* read_off;   /* [n_pairs+1] into read_seqs */
+  const char* read_seqs;
+  int32_t use_ref_end_penalty;
+  int32_t max_ref, max_read; /* longest window / read of the batch (sizes the shared memory) */
+  int32_t ops_stride;
+  char* out_ops;             /* [n_pairs][ops_stride] 'M' / 'D' (reference base vs gap) / 'I' (read base vs gap), NUL-terminated */
+  int32_t* out_len;          /* [n_pairs] number of operations, -1 if the walk back hit an impossible cell */
+  float* out_score;          /* [n_pairs] */
+};
+cudaError_t launch_nw(const NwParams& p, int max_ctas, cudaStream_t stream);
+size_t nw_shared_bytes(int max_ref, int max_read);
+
 }  // namespace hipstr
 #endif

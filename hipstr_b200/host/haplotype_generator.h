@@ -20,7 +20,7 @@ namespace hipstr {
 
 /* A left-aligned read as the generator sees it (Alignment, SeqAlignment/AlignmentData.h:29-137). */
 struct ReadView {
-  int32_t start, stop;            /* reference span, stop exclusive */
+  int32_t start, stop;            /* Alignment::get_start() / get_stop() (HipSTR: stop = last aligned reference position) */
   const char* bases;              /* ungapped read sequence */
   int32_t n_cigar;
   const char* cigar_type;         /* '=', 'X', 'I', 'D' */

@@ -833,9 +833,12 @@ hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_
       v.n_cigar = rd->cigar_off[r + 1] - rd->cigar_off[r];
       v.cigar_type = rd->cigar_type + rd->cigar_off[r];
       v.cigar_len = rd->cigar_len + rd->cigar_off[r];
-      v.stop = v.start;
-      for (int c = 0; c < v.n_cigar; c++)
-        if (v.cigar_type[c] != 'I') v.stop += v.cigar_len[c];
+      if (rd->read_stop) v.stop = rd->read_stop[r];
+      else {   // HipSTR's convention: the last aligned reference position
+        v.stop = v.start - 1;
+        for (int c = 0; c < v.n_cigar; c++)
+          if (v.cigar_type[c] != 'I') v.stop += v.cigar_len[c];
+      }
       min_start = std::min(min_start, v.start);
       max_stop = std::max(max_stop, v.stop);
       by_sample[rd->sample_label[r]].push_back(v);

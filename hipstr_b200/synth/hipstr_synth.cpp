@@ -29,6 +29,7 @@ struct hipstr_synth {
   std::vector<int32_t> locus_read_off, locus_sample_off, pool_index, sample_label, read_weight, n_haps, true_gt, read_bp_diff;
   std::vector<uint8_t> second_mate, haploid, read_rev_strand;
   std::vector<double> log_p1, log_p2;
+  std::vector<int32_t> read_stop;
   std::vector<int32_t> read_seq_off, read_start, read_cigar_off, read_cigar_len, read_name_id, block_start, block_end;
   std::vector<char> read_bases, read_quals, read_cigar_type, chrom_seqs;
 };
@@ -234,6 +235,12 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
       S->read_quals.insert(S->read_quals.end(), reads[r].qual.begin(), reads[r].qual.end());
       S->read_seq_off.push_back((int32_t)S->read_bases.size());
       S->read_start.push_back(reads[r].start);
+      {
+        int32_t stop = reads[r].start - 1;
+        for (size_t c = 0; c < reads[r].ctype.size(); c++)
+          if (reads[r].ctype[c] != 'I') stop += reads[r].clen[c];
+        S->read_stop.push_back(stop);
+      }
       S->read_cigar_type.insert(S->read_cigar_type.end(), reads[r].ctype.begin(), reads[r].ctype.end());
       S->read_cigar_len.insert(S->read_cigar_len.end(), reads[r].clen.begin(), reads[r].clen.end());
       S->read_cigar_off.push_back((int32_t)S->read_cigar_type.size());
@@ -300,6 +307,7 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
   S->view.chrom_seqs = S->chrom_seqs.data();
   S->view.region_start = kStrStart;
   S->view.region_stop = str_end;
+  S->view.read_stop = S->read_stop.data();
   S->view.read_rev_strand = S->read_rev_strand.data();
   return S;
 }

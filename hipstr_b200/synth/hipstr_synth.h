@@ -61,6 +61,7 @@ typedef struct {
   int32_t chrom_len;               /* every locus has its own chromosome of this length */
   const char* chrom_seqs;          /* [n_loci][chrom_len] */
   int32_t region_start, region_stop; /* the STR Region of every locus */
+  const int32_t* read_stop;        /* [n_reads] Alignment::get_stop(): last aligned reference position (inclusive) */
   const uint8_t* read_rev_strand;  /* [n_reads] Alignment::is_from_reverse_strand(): a hash of the read index */
 } hipstr_synth_view_t;
 

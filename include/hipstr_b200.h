@@ -402,6 +402,9 @@ typedef struct hipstr_locus_reads {
   const double*  log_p2;            /* [R]                                                     */
   const uint8_t* haploid;           /* [n_loci]                                                */
   const uint8_t* rev_strand;        /* [R] Alignment::is_from_reverse_strand(), NULL = all forward */
+  const int32_t* read_stop;         /* [R] Alignment::get_stop(): HipSTR keeps the LAST aligned reference position
+                                       (inclusive; AlignmentOps.cpp:56-57,106).  NULL = derived from the CIGAR as
+                                       read_start + reference bases consumed - 1                              */
 } hipstr_locus_reads_t;
 
 typedef struct hipstr_genotyper hipstr_genotyper_t;
@@ -510,6 +513,55 @@ int32_t hipstr_extract_cigar(const char* cigar_type, const int32_t* cigar_len, i
  * of alt_hap against ref_hap -- the string hipstr_stitch_trace consumes.  Pure host logic. */
 hipstr_status_t hipstr_hap_aln_to_ref(const char* ref_hap, const char* alt_hap, int32_t first_block_start,
                                       int32_t repeat_block_start, int32_t cap, char* out);
+
+/* --- the arithmetic of read left-alignment (kernel K6) ------
+ * Replaces NeedlemanWunsch::Align (SeqAlignment/NeedlemanWunsch.h:16-18, impl NeedlemanWunsch.cpp:384-423:
+ * initMatrices :339-381, nw_helper :193-241, findOptimalStop / findOptimalStopEndPenalty :149-191,
+ * traceAlignment :243-337) for a BATCH of (reference window, read) pairs -- what realign()
+ * (SeqAlignment/AlignmentOps.cpp:14-100) runs once per distinct read sequence inside left_align_reads
+ * (genotyper_bam_processor.cpp:38-102), and Haplotype::aln_haps_to_ref once per haplotype.
+ *   ref_off / read_off [n_pairs+1] offsets into ref_seqs / read_seqs (A, C, G, T, anything else scores like N)
+ *   use_ref_end_penalty  0 = the read may start and end anywhere in the window (realign), 1 = end-to-end
+ *   ops  [n_pairs][ops_stride], ops_stride > longest window + longest read: one character per alignment column,
+ *        'M' base against base, 'D' reference base against a gap (also the unaligned window ends),
+ *        'I' read base against a gap; NUL-terminated.  ref_al / read_al / the CIGAR of the reference follow
+ *        by walking the two sequences along it (hipstr_realign_read).
+ *   ops_len [n_pairs] number of columns; score [n_pairs] the alignment score (float, like the reference)
+ * Tie decisions are the reference's (bestIndex :125-147), so the strings are identical, not merely optimal. */
+hipstr_status_t hipstr_nw_align_batch_host(hipstr_ctx_t* ctx, int32_t n_pairs, const int32_t* ref_off,
+                                           const char* ref_seqs, const int32_t* read_off, const char* read_seqs,
+                                           int32_t use_ref_end_penalty, int32_t ops_stride, char* ops,
+                                           int32_t* ops_len, float* score);
+
+/* GenotyperBamProcessor::left_align_reads (genotyper_bam_processor.cpp:38-102) for a batch of loci: every read is
+ * trimmed to [trim_start, trim_stop] of its locus (BamAlignment::TrimAlignment, bam_io.cpp:384-477; the reference
+ * passes region_group.start() - 40 (or 1) and region_group.stop() + 40; NULL = no trimming), reads whose CIGAR holds
+ * only M / = are re-expressed with = / X (convertAlignment, AlignmentOps.cpp:102-167), the others are re-aligned
+ * against chromosome[Position - 76, EndPosition + 74] once per distinct sequence of the locus (realign, :14-100) --
+ * ALL Needleman-Wunsch alignments of the call in one K6 launch (a second one only for sequences whose first
+ * alignment came back clipped) -- and later reads with a known sequence reuse that alignment (:62-79).
+ *   raw  BAM-level alignments, sample-major per locus, in hipstr_locus_reads_t: read_start = Position(),
+ *        read_stop = GetEndPosition() (BAM's exclusive end, REQUIRED), CIGAR operations M = X I D S H.
+ * The result owns a hipstr_locus_reads_t of the left-aligned reads (HipSTR's conventions: = / X / I / D CIGARs,
+ * inclusive stop), ready for hipstr_genotyper_create_from_reads; reads that are empty after trimming or fail to
+ * realign are dropped (hipstr_left_aligned_source maps every kept read to its input index).  Region filters
+ * (set_hap_gen_info, :90-92) stay with the caller. */
+typedef struct hipstr_left_aligned hipstr_left_aligned_t;
+hipstr_status_t hipstr_left_align_reads_host(hipstr_ctx_t* ctx, int32_t n_loci, const hipstr_locus_reads_t* raw,
+                                             const char* const* chrom_seq, const int32_t* trim_start,
+                                             const int32_t* trim_stop, hipstr_left_aligned_t** out);
+const hipstr_locus_reads_t* hipstr_left_aligned_reads(const hipstr_left_aligned_t* h);
+const int32_t* hipstr_left_aligned_source(const hipstr_left_aligned_t* h, int64_t* n_reads);
+void hipstr_left_aligned_counts(const hipstr_left_aligned_t* h, int64_t* failed, int64_t* nw_alignments);
+void hipstr_left_aligned_free(hipstr_left_aligned_t* h);
+/* The host steps for ONE read, exported so that they can be checked without a GPU: returns -1 nothing left after
+ * trimming, 1 converted, 3 "needs a Needleman-Wunsch alignment" (window = {start, length} of the chromosome window,
+ * out_seq = the trimmed read; call again with nw_ops = the operation string of that alignment), 2 realigned, 0 failed. */
+int32_t hipstr_left_align_one(int32_t pos, int32_t end_pos, const char* bases, const char* quals, int32_t n_cigar,
+                              const char* cigar_type, const int32_t* cigar_len, const char* chrom_seq, int32_t do_trim,
+                              int32_t trim_start, int32_t trim_stop, const char* nw_ops, int32_t* window,
+                              int32_t* out_pos, char* out_seq, char* out_qual, int32_t* n_out_cigar, char* out_ctype,
+                              int32_t* out_clen);
 
 /* --- seam B5: ordered VCF output (host) ---------------------------------------
  * Replaces VCFWriter::open / write_header / add_vcf_record / close (vcf_writer.h:63-82,

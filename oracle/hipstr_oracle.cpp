@@ -1175,4 +1175,66 @@ int32_t oracle_posteriors(int32_t n_loci, const int32_t* locus_read_off, const i
   return HIPSTR_OK;
 }
 
+/* NeedlemanWunsch::Align (SeqAlignment/NeedlemanWunsch.cpp:384-423) for one (reference window, read) pair, serial,
+ * with the three full matrices: the checker of kernel K6.  ops: 'M' base vs base, 'D' reference base vs gap,
+ * 'I' read base vs gap.  Returns the number of columns or -1. */
+int32_t oracle_nw_align(const char* ref, int32_t L1, const char* read, int32_t L2, int32_t use_ref_end_penalty, char* ops,
+                        float* score) {
+  const float kOpen = 5.0f, kExt = 0.125f, kLarge = 1000000.0f;
+  auto code = [](char c) {
+    switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2;
+                 case 'T': case 't': return 3; default: return 4; }
+  };
+  auto pick = [](float s1, float s2, float s3, int8_t* w) {   // bestIndex :125-147
+    if (s2 > s1) { if (s2 > s3) { *w = 1; return s2; } *w = 2; return s3; }
+    if (s3 > s1) { *w = 2; return s3; }
+    *w = 0; return s1;
+  };
+  const int W = L1 + 1;
+  const size_t cells = (size_t)W * (L2 + 1);
+  std::vector<float> M(cells), X(cells), Y(cells);
+  std::vector<int8_t> tM(cells, -1), tX(cells, -1), tY(cells, -1);
+  M[0] = 0.0f; X[0] = -kLarge; Y[0] = -kLarge;
+  for (int j = 1; j <= L1; j++) { X[j] = use_ref_end_penalty ? -kOpen - (j - 1) * kExt : 0.0f; tX[j] = 1; Y[j] = -kLarge; M[j] = -kLarge; }
+  for (int i = 1; i <= L2; i++) { const size_t c = (size_t)i * W; Y[c] = -kOpen - (i - 1) * kExt; tY[c] = 2; X[c] = -kLarge; M[c] = -kLarge; }
+  for (int i = 1; i <= L2; i++)
+    for (int j = 1; j <= L1; j++) {
+      const size_t h = (size_t)i * W + j, d = h - W - 1, l = h - 1, u = h - W;
+      const int a = code(ref[j - 1]), b = code(read[i - 1]);
+      M[h] = pick(M[d], X[d], Y[d], &tM[h]) + ((a == 4 || b == 4 || a == b) ? 2.0f : -2.0f);
+      X[h] = pick(M[l] - kOpen, X[l] - kExt, Y[l] - kOpen, &tX[h]);
+      Y[h] = pick(M[u] - kOpen, X[u] - kOpen, Y[u] - kExt, &tY[h]);
+    }
+  int col = L1, kind = 0;
+  float best;
+  const size_t last = (size_t)L2 * W;
+  if (use_ref_end_penalty) {
+    best = M[last + L1];
+    if (X[last + L1] > best) { best = X[last + L1]; kind = 1; }
+    if (Y[last + L1] > best) { best = Y[last + L1]; kind = 2; }
+  } else {
+    best = -kLarge; col = -1; kind = -1;
+    for (int j = 0; j <= L1; j++) {
+      if (M[last + j] >= best) { best = M[last + j]; col = j; kind = 0; }
+      if (X[last + j] > best) { best = X[last + j]; col = j; kind = 1; }
+      if (Y[last + j] > best) { best = Y[last + j]; col = j; kind = 2; }
+    }
+  }
+  *score = best;
+  std::string out;
+  for (int j = L1; j > col; j--) out += 'D';
+  int row = L2;
+  while (row > 0) {
+    const size_t h = (size_t)row * W + col;
+    if (kind == 0 && col > 0) { out += 'M'; kind = tM[h]; row--; col--; }
+    else if (kind == 1 && col > 0) { out += 'D'; kind = tX[h]; col--; }
+    else if (kind == 2) { out += 'I'; kind = tY[h]; row--; }
+    else return -1;
+  }
+  for (; col > 0; col--) out += 'D';
+  std::reverse(out.begin(), out.end());
+  std::memcpy(ops, out.c_str(), out.size() + 1);
+  return (int32_t)out.size();
+}
+
 }  // extern "C"

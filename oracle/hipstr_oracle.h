@@ -66,6 +66,9 @@ int32_t oracle_trace_batch(const hipstr_align_batch_t* batch, const int32_t* blo
                            const int32_t* trace_pool, const int32_t* trace_hap, const hipstr_trace_out_t* out);
 
 /* EMStutterGenotyper::train for every locus of the batch (em_stutter_genotyper.cpp:170-226). */
+/* NeedlemanWunsch::Align for one pair (checker of K6); ops capacity >= L1 + L2 + 1 */
+int32_t oracle_nw_align(const char* ref, int32_t L1, const char* read, int32_t L2, int32_t use_ref_end_penalty, char* ops,
+                        float* score);
 int32_t oracle_em_train(const hipstr_em_batch_t* batch, int32_t max_iter, double min_LL_abs_change,
                         double min_LL_frac_change, double* params_out, uint8_t* converged_out,
                         int32_t* iters_out, double* ll_out);

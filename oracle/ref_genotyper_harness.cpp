@@ -34,6 +34,8 @@
 #include "region.h"
 #include "stutter_model.h"
 #include "extract_indels.h"
+#include "SeqAlignment/NeedlemanWunsch.h"
+#include "SeqAlignment/AlignmentOps.h"
 #include "cephes/cephes.h"
 #include "htslib/htslib/kfunc.h"
 #include <cmath>
@@ -64,10 +66,10 @@ struct RefSG {
 extern "C" {
 
 /* Reads are sample-major; read r of sample s is named "r<name_id[r]>", so that adjacent reads with the
- * same id are mates (seq_stutter_genotyper.cpp:499).  The gapped alignment string and the stop
- * coordinate are derived from bases + CIGAR ('=','X','I','D') the way BamProcessor leaves them. */
+ * same id are mates (seq_stutter_genotyper.cpp:499).  The gapped alignment string is derived from bases +
+ * CIGAR ('=','X','I','D'); read_stop is Alignment::get_stop() (HipSTR: last aligned reference position). */
 void* ref_sg_create(int32_t n_samples, int32_t n_reads, const int32_t* sample_label, const int32_t* name_id,
-                    const int32_t* read_start, const int32_t* seq_off, const char* bases, const char* quals,
+                    const int32_t* read_start, const int32_t* read_stop, const int32_t* seq_off, const char* bases, const char* quals,
                     const int32_t* cigar_off, const char* cigar_type, const int32_t* cigar_len, const double* log_p1,
                     const double* log_p2, const char* chrom_seq, int32_t region_start, int32_t region_stop,
                     int32_t period, const double* stutter, int32_t haploid, int32_t reassemble_flanks,
@@ -94,7 +96,7 @@ void* ref_sg_create(int32_t n_samples, int32_t n_reads, const int32_t* sample_la
         if (cigar_type[c] != 'I') pos += cigar_len[c];
       }
     }
-    Alignment a(read_start[r], pos, rev_strand != NULL && rev_strand[r] != 0, "r" + std::to_string(name_id[r]), q, seq, gapped);
+    Alignment a(read_start[r], read_stop ? read_stop[r] : pos - 1, rev_strand != NULL && rev_strand[r] != 0, "r" + std::to_string(name_id[r]), q, seq, gapped);
     a.set_cigar_list(cig);
     a.set_hap_gen_info(std::vector<bool>(1, true));
     alns.push_back(a);
@@ -232,6 +234,57 @@ int32_t ref_extract_cigar(const char* type, const int32_t* len, int32_t n, int32
   const bool ok = ExtractCigar(cig, cigar_start, region_start, region_end, d);
   *bp_diff = d;
   return ok ? 1 : 0;
+}
+
+/* NeedlemanWunsch::Align itself on one pair: the alignment rows folded into one operation per column
+ * ('I' where the reference row has a gap, 'D' where the read row has one, 'M' otherwise). */
+int32_t ref_nw_align(const char* ref, int32_t L1, const char* read, int32_t L2, int32_t use_ref_end_penalty, char* ops, float* score) {
+  std::string ref_al, read_al;
+  std::vector<CigarOp> cigar;
+  NeedlemanWunsch::Align(std::string(ref, ref + L1), std::string(read, read + L2), ref_al, read_al, score, cigar,
+                         use_ref_end_penalty != 0);
+  for (size_t i = 0; i < ref_al.size(); i++) ops[i] = ref_al[i] == '-' ? 'I' : (read_al[i] == '-' ? 'D' : 'M');
+  ops[ref_al.size()] = 0;
+  return (int32_t)ref_al.size();
+}
+
+/* One BAM-level alignment through the reference's left-alignment steps (genotyper_bam_processor.cpp:53-67):
+ * TrimAlignment (bam_io.cpp:384-477) when do_trim, then convertAlignment for reads whose CIGAR is all M / = , else
+ * realign (SeqAlignment/AlignmentOps.cpp:14-167).  The BamAlignment is assembled in memory (bam_min.c).
+ * Returns -1 if nothing is left after trimming, 0 if realign() failed, 1 = converted, 2 = realigned.
+ * out_pos = {start, stop}; strings NUL-terminated; CIGAR in out_ctype / out_clen (*n_out_cigar runs). */
+int32_t ref_left_align_one(int32_t pos, int32_t end_pos, const char* bases, const char* quals, int32_t n_cigar,
+                           const char* cigar_type, const int32_t* cigar_len, const char* chrom_seq, int32_t do_trim,
+                           int32_t trim_start, int32_t trim_stop, int32_t* out_pos, char* out_seq, char* out_qual,
+                           char* out_aln, int32_t* n_out_cigar, char* out_ctype, int32_t* out_clen) {
+  BamAlignment b;
+  b.bases_ = bases;
+  b.qualities_ = quals;
+  for (int i = 0; i < n_cigar; i++) b.cigar_ops_.push_back(CigarOp(cigar_type[i], cigar_len[i]));
+  b.built_ = true;
+  b.length_ = (int32_t)b.bases_.size();
+  b.pos_ = pos;
+  b.end_pos_ = end_pos;
+  const char* qname = "read";
+  b.b_->data = (uint8_t*)malloc(8);
+  memcpy(b.b_->data, qname, 5);
+  b.b_->l_data = 5; b.b_->m_data = 8;
+  b.b_->core.l_qname = 5;
+  if (do_trim) b.TrimAlignment(trim_start, trim_stop);
+  if (b.Length() == 0) return -1;
+  Alignment out("read");
+  int32_t how;
+  const std::string chrom(chrom_seq);
+  if (b.MatchesReference()) { convertAlignment(b, chrom, out); how = 1; }
+  else how = realign(b, chrom, out) ? 2 : 0;
+  out_pos[0] = out.get_start();
+  out_pos[1] = out.get_stop();
+  strcpy(out_seq, out.get_sequence().c_str());
+  strcpy(out_qual, out.get_base_qualities().c_str());
+  strcpy(out_aln, out.get_alignment().c_str());
+  *n_out_cigar = (int32_t)out.get_cigar_list().size();
+  for (int i = 0; i < *n_out_cigar; i++) { out_ctype[i] = out.get_cigar_list()[i].get_type(); out_clen[i] = out.get_cigar_list()[i].get_num(); }
+  return how;
 }
 
 /* The log the reference wrote for this locus (diagnostics in test failures). */

@@ -14,7 +14,7 @@ def bind(lib):
     if getattr(lib, "_sg_bound", False):
         return lib
     lib.ref_sg_create.restype = C.c_void_p
-    lib.ref_sg_create.argtypes = [C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_void_p, c_i32p,
+    lib.ref_sg_create.argtypes = [C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_void_p, c_i32p,
                                   C.c_void_p, c_i32p, c_f64p, c_f64p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32,
                                   c_f64p, C.c_int32, C.c_int32, c_u8p]
     lib.ref_sg_set_output_flags.restype = None
@@ -69,6 +69,7 @@ class LocusReads:
         self.cigar_type = ctype[co[r0]:co[r1]].copy()
         self.cigar_len = clen[co[r0]:co[r1]].copy()
         self.start = _np(v.read_start, R, np.int32)[r0:r1].copy()
+        self.stop = _np(v.read_stop, R, np.int32)[r0:r1].copy()
         self.name_id = _np(v.read_name_id, R, np.int32)[r0:r1].copy()
         self.sample_label = synth.sample_label[r0:r1].copy()
         self.log_p1 = synth.log_p1[r0:r1].copy()
@@ -92,7 +93,7 @@ class RefGenotyper:
         st = np.asarray(stutter, np.float64)
         self.h = self.lib.ref_sg_create(
             reads.n_samples, reads.n_reads, ptr(reads.sample_label, c_i32p), ptr(reads.name_id, c_i32p),
-            ptr(reads.start, c_i32p), ptr(reads.seq_off, c_i32p), reads.bases.ctypes.data, reads.quals.ctypes.data,
+            ptr(reads.start, c_i32p), ptr(reads.stop, c_i32p), ptr(reads.seq_off, c_i32p), reads.bases.ctypes.data, reads.quals.ctypes.data,
             ptr(reads.cigar_off, c_i32p), reads.cigar_type.ctypes.data, ptr(reads.cigar_len, c_i32p),
             ptr(reads.log_p1, c_f64p), ptr(reads.log_p2, c_f64p), reads.chrom_seq, reads.region[0], reads.region[1],
             reads.period, ptr(st, c_f64p), reads.haploid, int(reassemble_flanks), ptr(reads.rev_strand, c_u8p))
