@@ -641,6 +641,25 @@ class Genotyper:
         return g
 
     @classmethod
+    def from_reads(cls, ctx, reads_struct, n_loci, region_start, region_stop, period, chrom_seqs,
+                   stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01)):
+        """hipstr_genotyper_create_from_reads on any hipstr_locus_reads_t (e.g. the output of LeftAligned)."""
+        chroms = [c if isinstance(c, bytes) else c.encode() for c in chrom_seqs]
+        carr = (C.c_char_p * n_loci)(*chroms)
+        start, stop, per = (np.ascontiguousarray(a, np.int32) for a in (region_start, region_stop, period))
+        st6 = np.tile(np.asarray(stutter, np.float64), n_loci)
+        g = cls.__new__(cls)
+        g.lib, g.ctx, g.n_loci = load(), ctx, n_loci
+        g._keep = (reads_struct, chroms, carr, start, stop, per, st6)
+        h = C.c_void_p()
+        st = g.lib.hipstr_genotyper_create_from_reads(ctx.h if ctx else None, n_loci, ptr(start, c_i32p), ptr(stop, c_i32p),
+                                                      ptr(per, c_i32p), carr, ptr(st6, c_f64p), C.byref(reads_struct), C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "genotyper_create_from_reads")
+        g.h = h
+        return g
+
+    @classmethod
     def from_synth(cls, ctx, synth, loci_blocks=None):
         """All loci of a Synth; loci_blocks overrides the generator's own haplotype blocks."""
         v = synth.view

@@ -84,6 +84,34 @@ class LocusReads:
         self.haploid = int(synth.haploid[l])
 
 
+class ReadsOfLocus:
+    """LocusReads built from Python tuples [(start, stop, bases, quals, [(op, len)])] (e.g. left-aligned reads)."""
+
+    def __init__(self, reads, n_samples, sample_label, name_id, log_p1, log_p2, chrom_seq, region, period, haploid=0, rev_strand=None):
+        self.n_reads, self.n_samples = len(reads), n_samples
+        so, co, bases, quals, ctype, clen = [0], [0], bytearray(), bytearray(), bytearray(), []
+        for start, stop, b, q, cig in reads:
+            bases += b.encode()
+            quals += q.encode()
+            so.append(len(bases))
+            for t, n in cig:
+                ctype += t.encode()
+                clen.append(n)
+            co.append(len(clen))
+        self.seq_off, self.cigar_off = np.array(so, np.int32), np.array(co, np.int32)
+        self.bases = np.frombuffer(bytes(bases) + b"\0", np.uint8).copy()
+        self.quals = np.frombuffer(bytes(quals) + b"\0", np.uint8).copy()
+        self.cigar_type = np.frombuffer(bytes(ctype) + b"\0", np.uint8).copy()
+        self.cigar_len = np.array(clen + [0], np.int32)
+        self.start = np.array([r[0] for r in reads], np.int32)
+        self.stop = np.array([r[1] for r in reads], np.int32)
+        self.sample_label = np.ascontiguousarray(sample_label, np.int32)
+        self.name_id = np.ascontiguousarray(name_id, np.int32)
+        self.log_p1, self.log_p2 = np.ascontiguousarray(log_p1, np.float64), np.ascontiguousarray(log_p2, np.float64)
+        self.rev_strand = np.ascontiguousarray(rev_strand if rev_strand is not None else np.zeros(len(reads)), np.uint8)
+        self.chrom_seq, self.region, self.period, self.haploid = chrom_seq, region, period, haploid
+
+
 class RefGenotyper:
     """One reference SeqStutterGenotyper object."""
 

@@ -204,6 +204,42 @@ def test_batched_left_alignment_matches_reference_loop(kw):
     ctx.close()
 
 
+@needs_ref
+@pytest.mark.gpu
+def test_raw_reads_to_vcf_through_left_alignment():
+    """The chain a caller runs: raw BAM-level reads -> hipstr_left_align_reads_host (K6) -> hipstr_genotyper_create_from_reads ->
+    genotype() -> write_vcf; the reference SeqStutterGenotyper gets the same left-aligned reads."""
+    from hipstr_b200.capi import Context, Genotyper, LeftAligned
+    from ref_genotyper import ReadsOfLocus, RefGenotyper
+    kw = dict(n_loci=3, n_samples=8, reads_per_sample=15, n_alleles=5, read_len=120, seed=305, stutter_rate=0.2)
+    s = Synth(**kw)
+    reads, chroms, lro, t0, t1 = raw_reads(s, seed=3)
+    R = len(reads)
+    raw = make_locus_reads(lro, s.locus_sample_off, reads, s.sample_label, np.arange(R), s.log_p1, s.log_p2, s.haploid)
+    ctx = Context(0)
+    la = LeftAligned(ctx, s.n_loci, raw, chroms, [t0] * s.n_loci, [t1] * s.n_loci)
+    aligned, alro = la.reads()
+    L = s.n_loci
+    start, stop, period = int(s.view.region_start), int(s.view.region_stop), int(s.cfg.period) or 4
+    g = Genotyper.from_reads(ctx, la.view, L, [start] * L, [stop] * L, [period] * L, chroms)
+    ok = g.genotype(1000, 4, 0.01, True)
+    names = ["S%d" % i for i in range(kw["n_samples"])]
+    loci = g.vcf_loci(["chrS"] * L, ["STR"] * L, [start] * L, [stop] * L, [period] * L, chroms, names * L, names)
+    records = g.write_vcf(loci)
+    for l in range(L):
+        src = la.source[alro[l]:alro[l + 1]]
+        rd = ReadsOfLocus(aligned[alro[l]:alro[l + 1]], kw["n_samples"], s.sample_label[src], src, s.log_p1[src], s.log_p2[src], chroms[l],
+                          (start, stop), period)
+        r = RefGenotyper(rd, reassemble_flanks=True)
+        assert r.initialized and r.genotype() == bool(ok[l])
+        assert g.blocks(l) == [b[3] for b in r.blocks()]
+        assert np.array_equal(g.results(l)["best"], r.results()["best"])
+        assert records[l][1].replace(":-0.00:", ":0.00:") == r.vcf().rstrip("\n").replace(":-0.00:", ":0.00:")
+    g.close()
+    la.close()
+    ctx.close()
+
+
 def trim_like_reference(read, t0, t1):
     """Bases / qualities left after BamAlignment::TrimAlignment (quality bound '~' never stops the trimming)."""
     pos, end_pos, b, q, ops = read
