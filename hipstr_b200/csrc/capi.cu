@@ -968,14 +968,17 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   CU(put(m[6], order, s));
   TraceParams p;
   std::memset(&p, 0, sizeof(p));
-  p.slab_doubles = (int64_t)3 * slab_cols * l_max;
+  // two rolling rows of M / I / D, last columns of both sides, the emission table of the read
+  p.slab_doubles = (int64_t)7 * slab_cols + 2 * l_max + 6 * (int64_t)n_max;   // (+ one row of match_probs_)
+  p.dec_bytes = (int64_t)slab_cols * l_max;                // one predecessor-choice byte per cell of both sides
   p.art_ints = (int64_t)2 * slab_cols * HIPSTR_MAX_BLOCKS;
-  // threads in flight: each owns a ~0.4 MB slab; at most 65536 of them and at most 24 GB of slabs per context
-  const int64_t slab_budget = (int64_t)24 << 30;
-  const int by_budget = (int)std::max<int64_t>(64, slab_budget / (p.slab_doubles * (int64_t)sizeof(double)) / 64 * 64);
-  const int n_slots = std::min((std::min(n_traces, 65536) + 63) / 64 * 64, by_budget);
+  // threads in flight: each owns ~25 KB; at most 131072 of them and at most 8 GB per context
+  const int64_t per_thread = p.slab_doubles * (int64_t)sizeof(double) + p.dec_bytes + p.art_ints * (int64_t)sizeof(int32_t);
+  const int by_budget = (int)std::max<int64_t>(64, ((int64_t)8 << 30) / per_thread / 64 * 64);
+  const int n_slots = std::min((std::min(n_traces, 131072) + 63) / 64 * 64, by_budget);
   CU(ctx->d_last.reserve((size_t)n_slots * p.slab_doubles * sizeof(double)));
   CU(m[5].reserve((size_t)n_slots * p.art_ints * sizeof(int32_t)));
+  CU(m[7].reserve((size_t)n_slots * p.dec_bytes));
   const size_t T = (size_t)n_traces;
   CU(o[0].reserve(T * out->aln_stride));
   CU(o[1].reserve(T * (1 + 3 * HIPSTR_MAX_BLOCKS_PER_LOCUS + 4 + 2 * HIPSTR_MAX_TRACE_INDELS + 2 * HIPSTR_MAX_TRACE_SNPS) * sizeof(int32_t)));
@@ -988,7 +991,7 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   p.progs = (const DevProgEntry*)d.progs.p; p.prog_logrun = (const double*)d.logrun.p;
   p.qual_lut = ctx->d_qual_lut; p.trans = ctx->d_trans; p.int_logs = ctx->d_int_logs;
   p.block_start = (const int32_t*)m[2].p; p.block_ref_end = (const int32_t*)m[3].p; p.locus_block0 = (const int32_t*)m[4].p;
-  p.slab = (double*)ctx->d_last.p; p.art_slab = (int32_t*)m[5].p;
+  p.slab = (double*)ctx->d_last.p; p.art_slab = (int32_t*)m[5].p; p.dec_slab = (unsigned char*)m[7].p;
   p.aln_stride = out->aln_stride;
   p.out_aln = (char*)o[0].p;
   p.out_seed_pos = di; di += T;

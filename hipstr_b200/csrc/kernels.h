@@ -154,8 +154,10 @@ struct TraceParams {
   const int32_t* block_start;    /* [n_blocks] genomic start of every block */
   const int32_t* block_ref_end;  /* [n_blocks] start + length of the reference allele */
   const int32_t* locus_block0;   /* [n_loci] first block of the locus */
-  double* slab;                  /* [n_slots][slab_doubles] matrices */
+  double* slab;                  /* [n_slots][slab_doubles] rolling rows + last columns */
   int64_t slab_doubles;
+  unsigned char* dec_slab;       /* [n_slots][dec_bytes] predecessor choices, one byte per cell */
+  int64_t dec_bytes;
   int32_t* art_slab;             /* [n_slots][art_ints] best artifact size / position tables */
   int64_t art_ints;
   int32_t aln_stride;

@@ -2,19 +2,23 @@
  * trace.cu -- K5: alignment traceback (HapAligner::trace_optimal_aln, SeqAlignment/HapAligner.cpp:711-722
  * -> process_read(retrace_aln = true) :636-690 -> retrace :363-571).
  *
- * First version: ONE THREAD per (pooled read, haplotype) trace.  A trace needs the three FULL
- * matrices of both sides of the seed (the forward kernel K1 keeps only a row in registers), the
- * best artifact size / position of every repeat-block column, and then a strictly sequential walk
- * back along the best path -- a different shape of work from K1 (one haplotype per read instead of
- * all of them, memory-resident state, data-dependent control), so it gets its own kernel: every
- * thread owns a slab of global memory for its matrices and runs the reference's recurrences in the
- * reference's order (bit-identical cells, hence identical tie decisions within TRACE_LL_TOL).
+ * ONE THREAD per (pooled read, haplotype) trace.  The reference keeps the three FULL matrices of both
+ * sides of the seed and, walking back, re-derives at every visited cell which predecessor was best
+ * (within TRACE_LL_TOL, preferring different states on the two sides).  Those choices depend only on
+ * values that are all at hand when the cell is computed in the forward pass, so here they are TAKEN
+ * in the forward pass and stored as one byte per cell (2 bits for the match state, 1 each for the
+ * insertion and deletion states); the matrices themselves shrink to two rolling rows, the last
+ * column of every row (for the seed placement) and the best artifact size / position of every
+ * repeat-block column.  A trace needs ~25 KB instead of ~400 KB, all of it L1/L2-resident, and the
+ * strictly sequential walk back reads bytes.  Recurrences run in the reference's order (bit-identical
+ * cells, hence identical tie decisions).
  * The repeat-block evaluator replays the same host-unrolled programs as K1 (layout.h); the position
  * of the best artifact is read off the program: after a step, the reference's position counter is
  * one above the next step's position.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/hipstr_b200.h"
 #include "fastapprox.cuh"
@@ -33,6 +37,7 @@ namespace hipstr {
 
 __device__ __forceinline__ double tmax(double a, double b) { return a > b ? a : b; }
 
+
 /* A per-thread array whose element i lives at p[i * 32]: the 32 lanes of a warp interleave their slabs, and because
  * all lanes index their matrices with the SAME row pitch (the warp's longest read side), lanes that run the DP in
  * lockstep touch one 256-byte line per access instead of 32 sectors 0.4 MB apart. */
@@ -44,21 +49,25 @@ struct Lane {
 };
 typedef Lane<double> Mat;
 typedef Lane<int> IMat;
+typedef Lane<unsigned char> BMat;
+
+/* Two rolling rows of the three matrices. */
+struct Rows {
+  Mat M[2], I[2], D[2];
+};
 
 // One side of the seed: column k of the side is read base (rev ? n_read-1-k : k).
 struct TSide {
   const uint8_t* bases;   // codes, read order
-  const uint8_t* quals;
-  const double* lut;      // [256][2]
+  Lane<double> E;         // per-thread emission table [read position][6]: log P(read base | haplotype code 0..4), then
+                          // log P(base correct); built once per trace so that an emission is ONE load instead of the
+                          // dependent chain quality byte -> base byte -> quality table
   int n, rev, n_read;
   int pitch;              // row pitch of this side's matrices (>= n, uniform across the warp)
   __device__ __forceinline__ int ridx(int k) const { return rev ? n_read - 1 - k : k; }
   __device__ __forceinline__ int code(int k) const { return bases[ridx(k)]; }
-  __device__ __forceinline__ double lc(int k) const { return __ldg(lut + 2 * quals[ridx(k)]); }
-  __device__ __forceinline__ double emit(int k, int x) const {
-    const int r = ridx(k);
-    return __ldg(lut + 2 * quals[r] + (bases[r] == x ? 0 : 1));
-  }
+  __device__ __forceinline__ double lc(int k) const { return E[ridx(k) * 6 + 5]; }
+  __device__ __forceinline__ double emit(int k, int x) const { return E[ridx(k) * 6 + x]; }
 };
 
 struct TRep {
@@ -126,10 +135,26 @@ __device__ double t_walk(const TSide& sd, const TRep& r, int prog_index, int sto
   return lse_finish(mx, total);
 }
 
+__device__ __forceinline__ int t_pick3(bool rev, double v1, double v2, double v3) {   // HapAligner.cpp:346-358
+  if (!rev) {
+    if (v1 > v2 + T_TRACE_TOL) return v1 > v3 + T_TRACE_TOL ? 0 : 2;
+    return v2 > v3 + T_TRACE_TOL ? 1 : 2;
+  }
+  if (v3 > v2 + T_TRACE_TOL) return v3 > v1 + T_TRACE_TOL ? 2 : 0;
+  return v2 > v1 + T_TRACE_TOL ? 1 : 0;
+}
+__device__ __forceinline__ int t_pick2(bool rev, double v1, double v2) {              // :360-361
+  if (!rev) return v1 > v2 + T_TRACE_TOL ? 0 : 1;
+  return v2 > v1 + T_TRACE_TOL ? 1 : 0;
+}
+
+
 // Repeat block of one side: the super-row `out_row` from the row above it (HapAligner.cpp:62-109).
 __device__ void t_repeat_block(const TSide& sd, const TRep& r, const Mat M_prev, const Mat M_out, const Mat I_out,
-                               const Mat D_out, const IMat art_size, const IMat art_pos) {
+                               const Mat D_out, const Mat match, const IMat art_size, const IMat art_pos) {
   const int B = r.B, p = r.p, n = sd.n;
+  // match_probs_ of load_read, once per (side, allele) like the reference's table instead of once per use
+  for (int q = 0; q < n; q++) match[q] = t_match(sd, r, q);
   for (int j = 0; j < n; j++) {
     double probs[HIPSTR_NUM_ARTIFACTS];
     double best = T_IMPOSSIBLE;
@@ -142,7 +167,7 @@ __device__ void t_repeat_block(const TSide& sd, const TRep& r, const Mat M_prev,
       double v = T_IMPOSSIBLE;
       if (base_len >= 0) {
         double pr;
-        if (units == 0) pr = t_match(sd, r, j);
+        if (units == 0) pr = match[j];
         else if (units < 0) {
           const int k = -units;
           double lp0 = -__ldg(r.int_logs + (B + D + 1));
@@ -150,7 +175,7 @@ __device__ void t_repeat_block(const TSide& sd, const TRep& r, const Mat M_prev,
           if (q <= n - 1) {
             double pre = 0.0;
             for (int t = 0; t < -D; t++) pre += sd.emit(q - t, r.s[B - 1 - t]);
-            lp0 += t_match(sd, r, q) - pre;
+            lp0 += match[q] - pre;
           } else {
             for (int t = 0; t < base_len; t++) lp0 += sd.emit(j - t, r.s[B - 1 - t + D]);
           }
@@ -163,7 +188,7 @@ __device__ void t_repeat_block(const TSide& sd, const TRep& r, const Mat M_prev,
             ins += (m < B) ? sd.emit(j - t, r.s[B - 1 - m]) : sd.lc(j - t);
           }
           double lp0 = -__ldg(r.int_logs + (B + 1)) + ins;
-          lp0 += (base_len > D) ? t_match(sd, r, j - D) : 0.0;
+          lp0 += (base_len > D) ? match[j - D] : 0.0;
           const int stop = -min(max(0, base_len - D), B);
           pr = t_walk<true>(sd, r, __ldg(r.rep->prog_off), stop, j, units, lp0, B, pos);
         }
@@ -183,20 +208,26 @@ __device__ void t_repeat_block(const TSide& sd, const TRep& r, const Mat M_prev,
   }
 }
 
-// Full matrices of one side (align_seq_to_hap, HapAligner.cpp:26-161).  Matrices are [row][n].
-__device__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHapSide& hs, const Mat M, const Mat I, const Mat D,
-                              const IMat art_size, const IMat art_pos) {
+// One side of align_seq_to_hap (HapAligner.cpp:26-161) with two rolling rows.  For every cell the predecessor choices
+// of retrace (:363-571) are taken here and stored in `dec` ([row][pitch]): bits 0-1 = best of (insertion to the
+// left, deletion on the diagonal, match on the diagonal) for the match state, bit 2 = deletion state came from a
+// match, bit 3 = insertion state came from a match.  lastcol[row] = M[row][n-1] (compute_aln_logprob reads those).
+__device__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHapSide& hs, const Rows& rw, const BMat dec,
+                              const Mat lastcol, const Mat match, const IMat art_size, const IMat art_pos) {
   const int n = sd.n;
   const long pitch = sd.pitch;
+  const bool rev = sd.rev != 0;
   const uint8_t* seq = P.hapbytes + hs.seq_off;
   const uint8_t* rows = P.hapbytes + hs.row_off;
+  int cur = 0;   // rw.*[cur] holds the row computed last
   double run = 0.0;
   for (int j = 0; j < n; j++) {
-    M[j] = sd.emit(j, seq[0]) + run;
-    I[j] = sd.lc(j) + run;
-    D[j] = T_IMPOSSIBLE;
+    rw.M[0][j] = sd.emit(j, seq[0]) + run;
+    rw.I[0][j] = sd.lc(j) + run;
+    rw.D[0][j] = T_IMPOSSIBLE;
     run += sd.lc(j);
   }
+  if (n > 0) lastcol[0] = rw.M[0][n - 1];
   for (int b = 0; b < hs.n_blocks; b++) {
     const DevBlock blk = P.blocks[hs.blk_off + b];
     if (blk.rep >= 0) {
@@ -204,8 +235,10 @@ __device__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHa
       TRep r;
       r.s = P.hapbytes + rep->seq_off; r.progs = P.progs; r.logrun = P.prog_logrun; r.rep = rep; r.int_logs = P.int_logs;
       r.B = rep->len; r.p = rep->period; r.left_align = rep->left_align;
-      const long out = pitch * (blk.row_start + blk.len - 1);
-      t_repeat_block(sd, r, M + pitch * (blk.row_start - 1), M + out, I + out, D + out, art_size + pitch * b, art_pos + pitch * b);
+      const int nxt = cur ^ 1;
+      t_repeat_block(sd, r, rw.M[cur], rw.M[nxt], rw.I[nxt], rw.D[nxt], match, art_size + pitch * b, art_pos + pitch * b);
+      cur = nxt;
+      if (n > 0) lastcol[blk.row_start + blk.len - 1] = rw.M[cur][n - 1];
       continue;
     }
     for (int row = blk.row_start + (b == 0 ? 1 : 0); row < blk.row_start + blk.len; row++) {
@@ -213,23 +246,40 @@ __device__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHa
       const int info = rows[row], hp = info & 15;
       const bool after = (info & HIPSTR_ROW_AFTER_REPEAT) != 0;
       const double m2m = __ldg(P.trans + hp), m2i = __ldg(P.trans + 16 + hp), m2d = __ldg(P.trans + 32 + hp);
-      long at = pitch * row;
-      M[at] = sd.emit(0, hc);
-      I[at] = after ? T_IMPOSSIBLE : sd.lc(0);
-      D[at] = after ? T_IMPOSSIBLE : tmax(D[at - pitch] + T_DEL_TO_DEL, M[at - pitch] + T_DEL_TO_MATCH);
-      at++;
-      for (int j = 1; j < n; j++, at++) {
-        const double e = sd.emit(j, hc);
-        if (after) {
-          M[at] = e + M[at - pitch - 1];
-          I[at] = T_IMPOSSIBLE;
-          D[at] = T_IMPOSSIBLE;
-        } else {
-          M[at] = e + tmax(I[at - 1] + m2i, tmax(M[at - pitch - 1] + m2m, D[at - pitch - 1] + m2d));
-          I[at] = sd.lc(j) + tmax(M[at - pitch - 1] + T_INS_TO_MATCH, I[at - 1] + T_INS_TO_INS);
-          D[at] = tmax(M[at - pitch] + T_DEL_TO_MATCH, D[at - pitch] + T_DEL_TO_DEL);
-        }
+      const Mat pM = rw.M[cur], pD = rw.D[cur];
+      const int nxt = cur ^ 1;
+      const Mat cM = rw.M[nxt], cI = rw.I[nxt], cD = rw.D[nxt];
+      const BMat drow = dec + pitch * row;
+      if (n > 0) {
+        const double upM = pM[0], upD = pD[0];
+        cM[0] = sd.emit(0, hc);
+        cI[0] = after ? T_IMPOSSIBLE : sd.lc(0);
+        cD[0] = after ? T_IMPOSSIBLE : tmax(upD + T_DEL_TO_DEL, upM + T_DEL_TO_MATCH);
+        drow[0] = (unsigned char)(t_pick2(rev, upD + T_DEL_TO_DEL, upM + T_DEL_TO_MATCH) << 2);
       }
+      double diagM = n > 0 ? pM[0] : 0.0, diagD = n > 0 ? pD[0] : 0.0, leftI = n > 0 ? cI[0] : 0.0;
+      for (int j = 1; j < n; j++) {
+        const double e = sd.emit(j, hc);
+        const double upM = pM[j], upD = pD[j];
+        double m, i, d;
+        if (after) {
+          m = e + diagM;
+          i = T_IMPOSSIBLE;
+          d = T_IMPOSSIBLE;
+        } else {
+          m = e + tmax(leftI + m2i, tmax(diagM + m2m, diagD + m2d));
+          i = sd.lc(j) + tmax(diagM + T_INS_TO_MATCH, leftI + T_INS_TO_INS);
+          d = tmax(upM + T_DEL_TO_MATCH, upD + T_DEL_TO_DEL);
+        }
+        // the choices retrace would make standing on this cell, from the very values it would read
+        drow[j] = (unsigned char)(t_pick3(rev, leftI + m2i, diagD + m2d, diagM + m2m) |
+                                  (t_pick2(rev, upD + T_DEL_TO_DEL, upM + T_DEL_TO_MATCH) << 2) |
+                                  (t_pick2(rev, leftI + T_INS_TO_INS, diagM + T_INS_TO_MATCH) << 3));
+        cM[j] = m; cI[j] = i; cD[j] = d;
+        diagM = upM; diagD = upD; leftI = i;
+      }
+      cur = nxt;
+      if (n > 0) lastcol[row] = rw.M[cur][n - 1];
     }
   }
   return run;
@@ -253,24 +303,11 @@ struct TAcc {
   }
 };
 
-__device__ __forceinline__ int t_pick3(bool rev, double v1, double v2, double v3) {   // HapAligner.cpp:346-358
-  if (!rev) {
-    if (v1 > v2 + T_TRACE_TOL) return v1 > v3 + T_TRACE_TOL ? 0 : 2;
-    return v2 > v3 + T_TRACE_TOL ? 1 : 2;
-  }
-  if (v3 > v2 + T_TRACE_TOL) return v3 > v1 + T_TRACE_TOL ? 2 : 0;
-  return v2 > v1 + T_TRACE_TOL ? 1 : 0;
-}
-__device__ __forceinline__ int t_pick2(bool rev, double v1, double v2) {              // :360-361
-  if (!rev) return v1 > v2 + T_TRACE_TOL ? 0 : 1;
-  return v2 > v1 + T_TRACE_TOL ? 1 : 0;
-}
-
 // Homopolymer class of a flank row: the lowering stored min(15, max(h(i), h(i-1))) per row.
 // retrace (HapAligner.cpp:363-571) for one side; writes ops BACKWARDS-in-walk order into `ops`
 // (the caller reverses the left side); returns the number of ops.
 __device__ int t_walk_back(const TraceParams& P, const TSide& sd, const DevHapSide& hs, const int32_t* start_of,
-                           const Mat M, const Mat I, const Mat D, const IMat art_size, const IMat art_pos,
+                           const BMat dec, const IMat art_size, const IMat art_pos,
                            int block_index, int base_index, long matrix_index, char* ops, TAcc& acc) {
   const int n = sd.n, nb = hs.n_blocks;
   const long pitch = sd.pitch;
@@ -301,7 +338,6 @@ __device__ int t_walk_back(const TraceParams& P, const TSide& sd, const DevHapSi
       const int step = rev ? 1 : -1;
       int indel_seq_index = -1, indel_pos = -1;
       while (base_index >= 0 && seq_index >= 0) {
-        const int hp = rows[blk.row_start + base_index] & 15;
         if (type != prev_type) {
           if (prev_type == 1) { if (rev) acc.indel(indel_pos, indel_pos - pos); else acc.indel(pos + 1, pos - indel_pos); }
           else if (prev_type == 2) acc.indel(indel_pos + (rev ? 0 : 1), indel_seq_index - seq_index);
@@ -322,16 +358,16 @@ __device__ int t_walk_back(const TraceParams& P, const TSide& sd, const DevHapSi
           for (; seq_index != -1; seq_index--) ops[n_ops++] = 'S';
           return n_ops;
         }
-        const double m2m = __ldg(P.trans + hp), m2i = __ldg(P.trans + 16 + hp), m2d = __ldg(P.trans + 32 + hp);
+        const int choice = dec[matrix_index];   // taken in the forward pass on this very cell
         if (type == 0) {
-          const int best = t_pick3(rev, I[matrix_index - 1] + m2i, D[matrix_index - pitch - 1] + m2d, M[matrix_index - pitch - 1] + m2m);
+          const int best = choice & 3;
           if (best == 0) { type = 2; matrix_index -= 1; }
           else { type = best == 1 ? 1 : 0; matrix_index -= pitch + 1; }
         } else if (type == 1) {
-          type = t_pick2(rev, D[matrix_index - pitch] + T_DEL_TO_DEL, M[matrix_index - pitch] + T_DEL_TO_MATCH) == 0 ? 1 : 0;
+          type = ((choice >> 2) & 1) == 0 ? 1 : 0;
           matrix_index -= pitch;
         } else {
-          if (t_pick2(rev, I[matrix_index - 1] + T_INS_TO_INS, M[matrix_index - pitch - 1] + T_INS_TO_MATCH) == 0) { type = 2; matrix_index -= 1; }
+          if (((choice >> 3) & 1) == 0) { type = 2; matrix_index -= 1; }
           else { type = 0; matrix_index -= pitch + 1; }
         }
       }
@@ -342,7 +378,8 @@ __device__ int t_walk_back(const TraceParams& P, const TSide& sd, const DevHapSi
   return n_ops;
 }
 
-__global__ void __launch_bounds__(64) k_trace(const TraceParams P) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(64, MIN_BLOCKS) k_trace(const TraceParams P) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_slots = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
@@ -363,32 +400,50 @@ __global__ void __launch_bounds__(64) k_trace(const TraceParams P) {
     const DevHapSide hsF = P.hapsides[pool.hap_rec0 + 2 * h];
     const DevHapSide hsR = P.hapsides[pool.hap_rec0 + 2 * h + 1];
     const int n = pool.len, seed = pool.seed, nL = seed, nR = n - seed - 1, hs_len = hsF.len, nb = hsF.n_blocks;
-    // per-warp slab, lanes interleaved: [M I D] x (left, right) + artifact tables, rows pitchL / pitchR apart
+    // per-warp slab, lanes interleaved: two rolling rows of [M I D] (shared by the two sides, which run one after the
+    // other), the last column of every row of both sides, the decision bytes of both sides, the artifact tables
     const Mat slab{P.slab + (size_t)(slot - lane) * P.slab_doubles + lane};
-    const Mat LM = slab, LI = LM + (long)pitchL * hs_len, LD = LI + (long)pitchL * hs_len;
-    const Mat RM = LD + (long)pitchL * hs_len, RI = RM + (long)pitchR * hs_len, RD = RI + (long)pitchR * hs_len;
+    const long pitch = max(pitchL, pitchR);
+    Rows rw;
+    rw.M[0] = slab; rw.M[1] = slab + pitch; rw.I[0] = slab + 2 * pitch; rw.I[1] = slab + 3 * pitch;
+    rw.D[0] = slab + 4 * pitch; rw.D[1] = slab + 5 * pitch;
+    const Mat lastL = slab + 6 * pitch, lastR = lastL + hs_len;
+    const Mat matchq = lastR + hs_len;   // [pitch] match_probs_ of the repeat block being evaluated
+    const Mat emis = matchq + pitch;     // [n][6]
+    const BMat decL{P.dec_slab + (size_t)(slot - lane) * P.dec_bytes + lane};
+    const BMat decR = decL + (long)pitchL * hs_len;
     const IMat arts{P.art_slab + (size_t)(slot - lane) * P.art_ints + lane};
     const IMat Ls = arts, Lp = Ls + (long)pitchL * nb, Rs = Lp + (long)pitchL * nb, Rp = Rs + (long)pitchR * nb;
     TSide L, R;
-    L.bases = (const uint8_t*)P.bases + pool.seq_off; L.quals = (const uint8_t*)P.quals + pool.seq_off; L.lut = P.qual_lut;
+    L.bases = (const uint8_t*)P.bases + pool.seq_off;
+    L.E = emis;
+    {
+      const uint8_t* quals = (const uint8_t*)P.quals + pool.seq_off;
+      for (int r = 0; r < n; r++) {
+        const double ok = __ldg(P.qual_lut + 2 * quals[r]), bad = __ldg(P.qual_lut + 2 * quals[r] + 1);
+        const int b = L.bases[r];
+        for (int x = 0; x < 5; x++) emis[r * 6 + x] = b == x ? ok : bad;
+        emis[r * 6 + 5] = ok;
+      }
+    }
     L.n = nL; L.rev = 0; L.n_read = n; L.pitch = pitchL;
     R = L; R.n = nR; R.rev = 1; R.pitch = pitchR;
-    const double edgeL = t_fill_side(P, L, hsF, LM, LI, LD, Ls, Lp);
-    const double edgeR = t_fill_side(P, R, hsR, RM, RI, RD, Rs, Rp);
+    const double edgeL = t_fill_side(P, L, hsF, rw, decL, lastL, matchq, Ls, Lp);
+    const double edgeR = t_fill_side(P, R, hsR, rw, decR, lastR, matchq, Rs, Rp);
     // best seed placement (compute_aln_logprob, HapAligner.cpp:163-231)
     const uint8_t* fseq = P.hapbytes + hsF.seq_off;
     const uint8_t* frow = P.hapbytes + hsF.row_off;
     const double prior = -__ldg(P.int_logs + hsF.n_seed_pos);
     const int sx = L.bases[seed];
-    const double s_ok = __ldg(P.qual_lut + 2 * L.quals[seed]), s_bad = __ldg(P.qual_lut + 2 * L.quals[seed] + 1);
+    const double s_ok = emis[seed * 6 + 5], s_bad = emis[seed * 6 + (sx == 0 ? 1 : 0)];
     int max_index = 0;
-    double best = prior + (sx == fseq[0] ? s_ok : s_bad) + edgeL + RM[(long)pitchR * (hs_len - 2) + nR - 1];
+    double best = prior + (sx == fseq[0] ? s_ok : s_bad) + edgeL + lastR[hs_len - 2];
     {
-      const double v = prior + (sx == fseq[hs_len - 1] ? s_ok : s_bad) + edgeR + LM[(long)pitchL * (hs_len - 2) + nL - 1];
+      const double v = prior + (sx == fseq[hs_len - 1] ? s_ok : s_bad) + edgeR + lastL[hs_len - 2];
       if (v > best) { max_index = hs_len - 1; best = v; }
       for (int i = 1; i < hs_len - 1; i++) {
         if (frow[i] & HIPSTR_ROW_REPEAT) continue;
-        const double w = prior + (sx == fseq[i] ? s_ok : s_bad) + LM[(long)pitchL * (i - 1) + nL - 1] + RM[(long)pitchR * (hs_len - i - 2) + nR - 1];
+        const double w = prior + (sx == fseq[i] ? s_ok : s_bad) + lastL[i - 1] + lastR[hs_len - i - 2];
         if (w > best) { max_index = i; best = w; }
       }
     }
@@ -415,8 +470,8 @@ __global__ void __launch_bounds__(64) k_trace(const TraceParams P) {
     if (max_index == 0) { for (int i = 0; i < seed; i++) aln[n_left++] = 'S'; }
     else {
       const long mi = (long)pitchL * (max_index - 1) + seed - 1;
-      if (fc == 0) n_left = t_walk_back(P, L, hsF, start_fw, LM, LI, LD, Ls, Lp, fb - 1, P.blocks[hsF.blk_off + fb - 1].len - 1, mi, aln, acc);
-      else n_left = t_walk_back(P, L, hsF, start_fw, LM, LI, LD, Ls, Lp, fb, fc - 1, mi, aln, acc);
+      if (fc == 0) n_left = t_walk_back(P, L, hsF, start_fw, decL, Ls, Lp, fb - 1, P.blocks[hsF.blk_off + fb - 1].len - 1, mi, aln, acc);
+      else n_left = t_walk_back(P, L, hsF, start_fw, decL, Ls, Lp, fb, fc - 1, mi, aln, acc);
       for (int a = 0, z = n_left - 1; a < z; a++, z--) { const char c = aln[a]; aln[a] = aln[z]; aln[z] = c; }   // left side is walked backwards
     }
     if (P.blocks[hsF.blk_off + fb].rep < 0) acc.touch(fb, seed);
@@ -429,8 +484,8 @@ __global__ void __launch_bounds__(64) k_trace(const TraceParams P) {
     if (rmax == 0) { for (int i = 0; i < n - 1 - seed; i++) right[n_right++] = 'S'; }
     else {
       const long mi = (long)pitchR * (rmax - 1) + (n - 1 - seed) - 1;
-      if (rc == 0) n_right = t_walk_back(P, R, hsR, start_rv, RM, RI, RD, Rs, Rp, rb - 1, P.blocks[hsR.blk_off + rb - 1].len - 1, mi, right, acc);
-      else n_right = t_walk_back(P, R, hsR, start_rv, RM, RI, RD, Rs, Rp, rb, rc - 1, mi, right, acc);
+      if (rc == 0) n_right = t_walk_back(P, R, hsR, start_rv, decR, Rs, Rp, rb - 1, P.blocks[hsR.blk_off + rb - 1].len - 1, mi, right, acc);
+      else n_right = t_walk_back(P, R, hsR, start_rv, decR, Rs, Rp, rb, rc - 1, mi, right, acc);
     }
     right[n_right] = 0;
     P.out_seed_pos[tr] = max_index;
@@ -447,7 +502,11 @@ __global__ void __launch_bounds__(64) k_trace(const TraceParams P) {
 
 cudaError_t launch_trace(const TraceParams& p, int n_slots, cudaStream_t stream) {
   if (p.n_traces <= 0) return cudaSuccess;
-  k_trace<<<(n_slots + 63) / 64, 64, 0, stream>>>(p);
+  // residency experiment hook: HIPSTR_K5_BLOCKS = 8 (128 registers), 12 (80) or 16 (64) resident CTAs per SM
+  static const int blocks = [] { const char* e = getenv("HIPSTR_K5_BLOCKS"); return e ? atoi(e) : 8; }();
+  if (blocks >= 16) k_trace<16><<<(n_slots + 63) / 64, 64, 0, stream>>>(p);
+  else if (blocks >= 12) k_trace<12><<<(n_slots + 63) / 64, 64, 0, stream>>>(p);
+  else k_trace<8><<<(n_slots + 63) / 64, 64, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
