@@ -162,8 +162,8 @@ extern "C" hipstr_status_t hipstr_stitch_trace(int32_t hap_start, const char* ha
                                                int32_t seed_hap_pos, int32_t seed_base, const char* read_bases,
                                                int32_t* start, int32_t* stop, int32_t cigar_cap, char* cigar_type,
                                                int32_t* cigar_len, int32_t* n_cigar, int32_t aln_cap, char* alignment) {
-  if (!hap_aln_to_ref || !read_aln_to_hap || !read_bases || !start || !stop || !cigar_type || !cigar_len || !n_cigar || !alignment)
-    return HIPSTR_ERR_BAD_ARG;
+  if (!hap_aln_to_ref || !read_aln_to_hap || !read_bases || !start || !stop || !n_cigar) return HIPSTR_ERR_BAD_ARG;
+  const bool want_strings = cigar_type && cigar_len && alignment;   // NULL = only the span is wanted
   const std::string hap(hap_aln_to_ref), read(read_aln_to_hap);
   // column of the haplotype-vs-reference alignment that holds haplotype base seed_hap_pos, and its coordinate
   long hcol = 0, remaining = seed_hap_pos;
@@ -194,6 +194,8 @@ extern "C" hipstr_status_t hipstr_stitch_trace(int32_t hap_start, const char* ha
   for (char c : right) if (c == 'D' || c == 'M') b++;
   *start = a;
   *stop = b;
+  *n_cigar = 0;
+  if (!want_strings) return HIPSTR_OK;
   int32_t runs = 0;
   for (size_t i = 0; i < full.size();) {
     size_t k = i;

@@ -503,6 +503,13 @@ int SeqStutterGenotyper::assemble_flanks() {
           if (*f.first == seq) { f.second++; seen = true; break; }
         if (!seen) flank_seqs.emplace_back(&seq, 1);
       }
+      // Reads that only repeat (part of) the reference flank add weight to reference edges and nothing else: the graph
+      // is the reference path, acyclic at kmer_length by construction, with exactly one source-to-sink path -- the
+      // outcome "no alternate flank" is known without building it.
+      bool only_reference = true;
+      for (const auto& f : flank_seqs)
+        if (ref_seq.find(*f.first) == std::string::npos) { only_reference = false; break; }
+      if (only_reference) continue;
       for (int k = kmer_length; k <= max_k; k++) {
         FlankAssembler assembler(k, ref_seq);
         for (const auto& f : flank_seqs) assembler.add_string(*f.first, 1, f.second);
@@ -1006,15 +1013,20 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
         t.flank_indel_data.emplace_back(indels[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2], indels[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2 + 1]);
       for (int k = 0; k < n_snps[i]; k++)
         t.flank_snp_data.emplace_back(snps[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2], (char)snps[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2 + 1]);
+      // only the span against the reference is needed by the loop and the VCF record; the CIGAR / gapped string of the
+      // traced alignment (used by the reference's HTML visualisation) are built on request (keep_traced_alignments)
       int32_t n_cigar = 0;
+      const bool full = keep_traced_alignments;
       const hipstr_status_t st2 = hipstr_stitch_trace(g.hap_blocks_.front().start, g.hap_aln_info_[key.second].c_str(), t.hap_aln.c_str(), seed_hap_pos[i],
-                               g.pool_seed_[key.first], read.c_str(), &t.start, &t.stop, (int32_t)ctype.size(), ctype.data(),
-                               clen.data(), &n_cigar, (int32_t)aln.size(), aln.data());
+                               g.pool_seed_[key.first], read.c_str(), &t.start, &t.stop, (int32_t)ctype.size(), full ? ctype.data() : nullptr,
+                               full ? clen.data() : nullptr, &n_cigar, (int32_t)aln.size(), full ? aln.data() : nullptr);
       if (st2 != HIPSTR_OK) { failed = 1; return; }
-      std::ostringstream cig;
-      for (int k = 0; k < n_cigar; k++) cig << clen[k] << ctype[k];
-      t.cigar = cig.str();
-      t.alignment = std::string(aln.data());
+      if (full) {
+        std::ostringstream cig;
+        for (int k = 0; k < n_cigar; k++) cig << clen[k] << ctype[k];
+        t.cigar = cig.str();
+        t.alignment = std::string(aln.data());
+      }
       g.trace_cache_[key] = std::move(t);
       }
     });

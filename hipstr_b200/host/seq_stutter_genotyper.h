@@ -44,8 +44,8 @@ struct HapBlock {
 struct AlignmentTrace {
   std::string hap_aln;                              /* hap_aln(): read vs haplotype operations */
   int32_t start = 0, stop = 0;                      /* traced_aln().get_start() / get_stop() */
-  std::string cigar;                                /* traced_aln().getCigarString() */
-  std::string alignment;                            /* traced_aln().get_alignment() */
+  std::string cigar;                                /* traced_aln().getCigarString()   (filled when keep_traced_alignments) */
+  std::string alignment;                            /* traced_aln().get_alignment()    (filled when keep_traced_alignments) */
   int32_t flank_ins_size = 0, flank_del_size = 0;
   std::vector<int32_t> stutter_size;                /* per block; HIPSTR_NO_STR_DATA where no STR data */
   std::vector<std::string> str_seq, flank_seq;      /* per block */
@@ -172,6 +172,7 @@ class GenotyperBatch {
                                            double abs_ll_converge, double frac_ll_converge, std::string& err);
 
   std::vector<SeqStutterGenotyper> loci;
+  bool keep_traced_alignments = false;   /* also build AlignmentTrace::cigar / alignment (only the visualisation reads them) */
   int64_t n_alignments = 0, n_traces = 0;
   int n_rounds = 0;
   /* wall-clock seconds by stage: construction, per-locus host decisions, trace device calls, trace stitching +

@@ -331,6 +331,7 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
  *   hap_start   genomic start of the haplotype's first block (HapBlock::start())
  *   cigar_cap   capacity of cigar_type / cigar_len; *n_cigar receives the number of runs
  *   aln_cap     capacity of alignment (NUL-terminated on return)
+ * cigar_type / cigar_len / alignment may all be NULL when only start / stop are wanted.
  * Pure host string logic; HIPSTR_ERR_BAD_ARG on inconsistent inputs (the reference dies). */
 hipstr_status_t hipstr_stitch_trace(int32_t hap_start, const char* hap_aln_to_ref, const char* read_aln_to_hap,
                                     int32_t seed_hap_pos, int32_t seed_base, const char* read_bases,
