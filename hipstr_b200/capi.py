@@ -697,9 +697,10 @@ class Genotyper:
         return dict(alignments=a.value, traces=t.value, rounds=r.value)
 
     def timing(self):
-        t = np.zeros(7)
+        t = np.zeros(9)
         self.lib.hipstr_genotyper_timing(self.h, ptr(t, c_f64p))
-        return dict(zip(("construct", "decide", "trace_device", "trace_host", "align", "posteriors", "vcf"), map(float, t)))
+        return dict(zip(("construct", "decide", "trace_device", "trace_host", "align", "posteriors", "vcf", "align_pack",
+                         "align_unpack"), map(float, t)))
 
     def phase_timing(self):
         t = np.zeros(8)

@@ -869,47 +869,147 @@ hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_
   return HIPSTR_OK;
 }
 
+namespace {
+
+/* Uninitialised buffer: std::vector would zero (and page-fault) hundreds of MB on one core before the workers fill it. */
+template <class T>
+struct RawBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  RawBuf() {}
+  RawBuf(const RawBuf&) = delete;
+  RawBuf& operator=(const RawBuf&) = delete;
+  ~RawBuf() { std::free(p); }
+  void alloc(size_t count) { std::free(p); n = count; p = static_cast<T*>(std::malloc(std::max<size_t>(count, 1) * sizeof(T))); }
+  T* data() { return p; }
+};
+
+}  // namespace
+
+/* One masked K1 + K2 + K3 call for the loci in `which`.  Packing a window of loci into the flat batch touches ~0.7 GB for
+ * 1 000 loci; it is done by all host threads at once (offsets by prefix sums first, then every locus copies its slices). */
 hipstr_status_t GenotyperBatch::run_alignments(const std::vector<int>& which, std::string& err) {
   if (which.empty()) return HIPSTR_OK;
-  PackedBatch pb;
-  PackedReads pr;
-  std::vector<SeqStutterGenotyper*> gs;
-  for (int l : which) {
-    SeqStutterGenotyper& g = loci[l];
-    pb.add(g, &g.realign_hap_, &g.realign_pool_);
-    pr.add(g);
-    if (!g.copy_read_.empty()) pr.copy_masked = true;
-    gs.push_back(&g);
-  }
-  if (pr.copy_masked)
-    for (auto g : gs) {
-      if (g->copy_read_.empty()) pr.copy_read.insert(pr.copy_read.end(), g->num_reads_, 1);
-      else pr.copy_read.insert(pr.copy_read.end(), g->copy_read_.begin(), g->copy_read_.end());
+  const double t_pack = now_s();
+  const size_t L = which.size();
+  std::vector<SeqStutterGenotyper*> gs(L);
+  for (size_t k = 0; k < L; k++) gs[k] = &loci[which[k]];
+  // prefix sums
+  std::vector<int32_t> locus_block_off(L + 1, 0), locus_pool_off(L + 1, 0), locus_read_off(L + 1, 0), locus_sample_off(L + 1, 0),
+      locus_opt_off(L + 1, 0), n_haps(L);
+  std::vector<int64_t> locus_hap_off(L + 1, 0), locus_out_off(L + 1, 0), opt_byte_off(L + 1, 0), pool_byte_off(L + 1, 0), ll_off(L + 1, 0),
+      post_off(L + 1, 0);
+  std::vector<uint8_t> haploid(L);
+  bool pool_masked = false, hap_masked = false, copy_masked = false;
+  for (size_t k = 0; k < L; k++) {
+    const SeqStutterGenotyper& g = *gs[k];
+    int opts = 0;
+    int64_t opt_bytes = 0;
+    for (const HapBlock& b : g.hap_blocks_) {
+      opts += b.num_options();
+      for (const std::string& q : b.seqs) opt_bytes += (int64_t)q.size();
     }
-  pr.size_outputs(gs);
-  hipstr_align_batch_t bt = pb.view();
+    locus_block_off[k + 1] = locus_block_off[k] + (int32_t)g.hap_blocks_.size();
+    locus_opt_off[k + 1] = locus_opt_off[k] + opts;
+    opt_byte_off[k + 1] = opt_byte_off[k] + opt_bytes;
+    locus_pool_off[k + 1] = locus_pool_off[k] + g.num_pools_;
+    pool_byte_off[k + 1] = pool_byte_off[k] + (int64_t)g.pool_bases_.size();
+    locus_hap_off[k + 1] = locus_hap_off[k] + g.num_alleles_;
+    locus_out_off[k + 1] = locus_out_off[k] + (int64_t)g.num_pools_ * g.num_alleles_;
+    locus_read_off[k + 1] = locus_read_off[k] + g.num_reads_;
+    locus_sample_off[k + 1] = locus_sample_off[k] + g.num_samples_;
+    ll_off[k + 1] = ll_off[k] + (int64_t)g.num_reads_ * g.num_alleles_;
+    post_off[k + 1] = post_off[k] + (int64_t)g.num_samples_ * g.num_alleles_ * g.num_alleles_;
+    n_haps[k] = g.num_alleles_;
+    haploid[k] = g.haploid_ ? 1 : 0;
+    for (uint8_t m : g.realign_hap_) hap_masked |= (m == 0);
+    for (uint8_t m : g.realign_pool_) pool_masked |= (m == 0);
+    copy_masked |= !g.copy_read_.empty();
+  }
+  if (pool_byte_off[L] > INT32_MAX) { err = "window too large: pooled read bytes exceed the 32-bit offsets of the batch"; return HIPSTR_ERR_BAD_ARG; }
+  const bool masked = pool_masked || hap_masked || copy_masked;   // only then must the previous likelihoods travel
+  const size_t B = locus_block_off[L], O = locus_opt_off[L], P = locus_pool_off[L], R = locus_read_off[L], S = locus_sample_off[L];
+  RawBuf<int32_t> block_period, block_opt_off, opt_seq_off, pool_seq_off, pool_seed, pool_index, sample_label, read_weight, read_seed, best;
+  RawBuf<double> block_stutter, log_p1, log_p2, read_ll, post, sample_ll, total_ll;
+  RawBuf<char> opt_seq, pool_bases, pool_quals;
+  RawBuf<uint8_t> realign_pool, realign_hap, second_mate, copy_read;
+  block_period.alloc(B); block_opt_off.alloc(B + 1); block_stutter.alloc(6 * B); opt_seq_off.alloc(O + 1); opt_seq.alloc(opt_byte_off[L]);
+  pool_seq_off.alloc(P + 1); pool_seed.alloc(P); pool_bases.alloc(pool_byte_off[L]); pool_quals.alloc(pool_byte_off[L]);
+  realign_pool.alloc(P); realign_hap.alloc(locus_hap_off[L]);
+  pool_index.alloc(R); sample_label.alloc(R); read_weight.alloc(R); second_mate.alloc(R); copy_read.alloc(R); log_p1.alloc(R); log_p2.alloc(R);
+  read_ll.alloc(ll_off[L]); read_seed.alloc(R); post.alloc(post_off[L]); sample_ll.alloc(S); best.alloc(2 * S); total_ll.alloc(L);
+  block_opt_off.p[0] = 0; opt_seq_off.p[0] = 0; pool_seq_off.p[0] = 0;
+  parallel_for(L, [&](size_t k) {
+    const SeqStutterGenotyper& g = *gs[k];
+    int32_t b = locus_block_off[k], o = locus_opt_off[k];
+    int64_t ob = opt_byte_off[k];
+    for (const HapBlock& blk : g.hap_blocks_) {
+      block_period.p[b] = blk.period;
+      std::memcpy(block_stutter.p + 6 * (size_t)b, blk.stutter, 6 * sizeof(double));
+      for (const std::string& q : blk.seqs) {
+        std::memcpy(opt_seq.p + ob, q.data(), q.size());
+        ob += (int64_t)q.size();
+        opt_seq_off.p[++o] = (int32_t)ob;
+      }
+      block_opt_off.p[++b] = o;
+    }
+    const int32_t p0 = locus_pool_off[k];
+    const int64_t pb0 = pool_byte_off[k];
+    std::memcpy(pool_bases.p + pb0, g.pool_bases_.data(), g.pool_bases_.size());
+    std::memcpy(pool_quals.p + pb0, g.pool_quals_.data(), g.pool_quals_.size());
+    for (int q = 0; q < g.num_pools_; q++) {
+      pool_seq_off.p[p0 + q + 1] = (int32_t)(pb0 + g.pool_seq_off_[q + 1]);
+      pool_seed.p[p0 + q] = g.pool_seed_[q];
+      realign_pool.p[p0 + q] = g.realign_pool_.empty() ? 1 : g.realign_pool_[q];
+    }
+    for (int h = 0; h < g.num_alleles_; h++) realign_hap.p[locus_hap_off[k] + h] = g.realign_hap_.empty() ? 1 : g.realign_hap_[h];
+    const int32_t r0 = locus_read_off[k];
+    const size_t nr = (size_t)g.num_reads_;
+    std::memcpy(pool_index.p + r0, g.pool_index_.data(), nr * sizeof(int32_t));
+    std::memcpy(sample_label.p + r0, g.sample_label_.data(), nr * sizeof(int32_t));
+    std::memcpy(read_weight.p + r0, g.read_weights_.data(), nr * sizeof(int32_t));
+    std::memcpy(second_mate.p + r0, g.second_mate_.data(), nr);
+    std::memcpy(log_p1.p + r0, g.log_p1_.data(), nr * sizeof(double));
+    std::memcpy(log_p2.p + r0, g.log_p2_.data(), nr * sizeof(double));
+    if (g.copy_read_.empty()) std::memset(copy_read.p + r0, 1, nr);
+    else std::memcpy(copy_read.p + r0, g.copy_read_.data(), nr);
+    if (masked) {   // in-place semantics of log_aln_probs_ / seed_positions_ under the masks
+      std::memcpy(read_ll.p + ll_off[k], g.log_aln_probs_.data(), (size_t)(ll_off[k + 1] - ll_off[k]) * sizeof(double));
+      std::memcpy(read_seed.p + r0, g.seed_positions_.data(), nr * sizeof(int32_t));
+    }
+  });
+  hipstr_align_batch_t bt;
+  std::memset(&bt, 0, sizeof(bt));
+  bt.n_loci = (int32_t)L; bt.n_blocks = (int32_t)B; bt.n_options = (int32_t)O; bt.n_pools = (int32_t)P; bt.n_haps = locus_hap_off[L];
+  bt.locus_block_off = locus_block_off.data(); bt.locus_pool_off = locus_pool_off.data();
+  bt.locus_hap_off = locus_hap_off.data(); bt.locus_out_off = locus_out_off.data();
+  bt.block_period = block_period.p; bt.block_opt_off = block_opt_off.p; bt.block_stutter = block_stutter.p;
+  bt.opt_seq_off = opt_seq_off.p; bt.opt_seq = opt_seq.p;
+  bt.pool_seq_off = pool_seq_off.p; bt.pool_bases = pool_bases.p; bt.pool_quals = pool_quals.p; bt.pool_seed = pool_seed.p;
+  bt.realign_pool = pool_masked ? realign_pool.p : nullptr;
+  bt.realign_hap = hap_masked ? realign_hap.p : nullptr;
   hipstr_reads_batch_t rb;
-  rb.locus_read_off = pr.locus_read_off.data();
-  rb.locus_sample_off = pr.locus_sample_off.data();
-  rb.pool_index = pr.pool_index.data();
-  rb.sample_label = pr.sample_label.data();
-  rb.second_mate = pr.second_mate.data();
-  rb.read_weight = pr.read_weight.data();
-  rb.log_p1 = pr.log_p1.data();
-  rb.log_p2 = pr.log_p2.data();
-  rb.haploid = pr.haploid.data();
-  rb.copy_read = pr.copy_masked ? pr.copy_read.data() : nullptr;
+  rb.locus_read_off = locus_read_off.data(); rb.locus_sample_off = locus_sample_off.data();
+  rb.pool_index = pool_index.p; rb.sample_label = sample_label.p; rb.second_mate = second_mate.p; rb.read_weight = read_weight.p;
+  rb.log_p1 = log_p1.p; rb.log_p2 = log_p2.p; rb.haploid = haploid.data();
+  rb.copy_read = copy_masked ? copy_read.p : nullptr;
   hipstr_genotype_out_t out;
-  out.read_ll = pr.read_ll.data();
-  out.read_seed = pr.read_seed.data();
-  out.post = pr.post.data();
-  out.sample_ll = pr.sample_ll.data();
-  out.best = pr.best.data();
-  out.total_ll = pr.total_ll.data();
+  out.read_ll = read_ll.p; out.read_seed = read_seed.p; out.post = post.p; out.sample_ll = sample_ll.p; out.best = best.p;
+  out.total_ll = total_ll.p;
+  seconds[T_ALIGN_PACK] += now_s() - t_pack;
   hipstr_status_t st = hipstr_genotype_batch_host(ctx_, &bt, &rb, &out);
   if (st != HIPSTR_OK) { err = std::string("hipstr_genotype_batch_host: ") + hipstr_last_error(ctx_); return st; }
   n_alignments += hipstr_batch_num_alignments(&bt);
-  pr.scatter_back(gs, true);
+  const double t_unpack = now_s();
+  parallel_for(L, [&](size_t k) {
+    SeqStutterGenotyper& g = *gs[k];
+    g.log_aln_probs_.assign(read_ll.p + ll_off[k], read_ll.p + ll_off[k + 1]);
+    g.seed_positions_.assign(read_seed.p + locus_read_off[k], read_seed.p + locus_read_off[k + 1]);
+    g.log_sample_posteriors_.assign(post.p + post_off[k], post.p + post_off[k + 1]);
+    g.sample_total_LLs_.assign(sample_ll.p + locus_sample_off[k], sample_ll.p + locus_sample_off[k + 1]);
+    g.optimal_haps_.assign(best.p + 2 * (size_t)locus_sample_off[k], best.p + 2 * (size_t)locus_sample_off[k + 1]);
+  });
+  seconds[T_ALIGN_UNPACK] += now_s() - t_unpack;
   return HIPSTR_OK;
 }
 
@@ -931,6 +1031,32 @@ hipstr_status_t GenotyperBatch::run_posteriors(const std::vector<int>& which, st
 hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::string& err) {
   const size_t kChunk = 1 << 17;   // traces per device call (bounds the host result buffers)
   size_t li = 0, ti = 0;           // next locus of `which`, next missing trace of that locus
+  // result buffers of one chunk, allocated once for the widest stride of the call and reused by every chunk (fresh
+  // memory would be page-faulted in again, serially, ~0.8 KB per trace)
+  size_t total = 0;
+  int32_t widest = 0;
+  for (int l : which) {
+    const SeqStutterGenotyper& g = loci[l];
+    if (g.missing_traces_.empty()) continue;
+    total += g.missing_traces_.size();
+    int32_t rd = 0, hp = 0;
+    for (int p = 0; p < g.num_pools_; p++) rd = std::max(rd, g.pool_seq_off_[p + 1] - g.pool_seq_off_[p]);
+    for (const HapBlock& b : g.hap_blocks_) {
+      size_t m = 0;
+      for (const auto& q : b.seqs) m = std::max(m, q.size());
+      hp += (int32_t)m;
+    }
+    widest = std::max(widest, rd + hp);
+  }
+  if (total == 0) { for (int l : which) { loci[l].missing_traces_.clear(); loci[l].missing_trace_read_.clear(); } return HIPSTR_OK; }
+  const int32_t stride = ((widest + 2 + 15) / 16) * 16;
+  const size_t cap = std::min(total, kChunk);
+  RawBuf<char> hap_aln;
+  RawBuf<int32_t> seed_hap_pos, stutter, span_start, span_len, flank_ins, flank_del, n_indels, indels, n_snps, snps;
+  hap_aln.alloc(cap * (size_t)stride);
+  seed_hap_pos.alloc(cap); stutter.alloc(cap * 8); span_start.alloc(cap * 8); span_len.alloc(cap * 8); flank_ins.alloc(cap);
+  flank_del.alloc(cap); n_indels.alloc(cap); indels.alloc(cap * HIPSTR_MAX_TRACE_INDELS * 2); n_snps.alloc(cap);
+  snps.alloc(cap * HIPSTR_MAX_TRACE_SNPS * 2);
   while (li < which.size()) {
     PackedBatch pb;
     std::vector<int32_t> trace_pool, trace_hap;
@@ -961,10 +1087,7 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
     }
     const size_t n = trace_pool.size();
     if (n == 0) break;
-    const int32_t stride = ((max_read + max_hap + 2 + 15) / 16) * 16;
-    std::vector<char> hap_aln(n * (size_t)stride);
-    std::vector<int32_t> seed_hap_pos(n), stutter(n * 8), span_start(n * 8), span_len(n * 8), flank_ins(n), flank_del(n), n_indels(n),
-        indels(n * HIPSTR_MAX_TRACE_INDELS * 2), n_snps(n), snps(n * HIPSTR_MAX_TRACE_SNPS * 2);
+    (void)max_read; (void)max_hap;
     hipstr_trace_out_t out;
     out.aln_stride = stride;
     out.hap_aln = hap_aln.data();
@@ -999,25 +1122,25 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
       const int nb = (int)g.hap_blocks_.size();
       const std::string read = g.pool_read(key.first);
       AlignmentTrace t;
-      t.hap_aln = std::string(&hap_aln[i * (size_t)stride]);
-      t.flank_ins_size = flank_ins[i];
-      t.flank_del_size = flank_del[i];
-      t.stutter_size.assign(stutter.begin() + i * 8, stutter.begin() + i * 8 + nb);
+      t.hap_aln = std::string(hap_aln.p + i * (size_t)stride);
+      t.flank_ins_size = flank_ins.p[i];
+      t.flank_del_size = flank_del.p[i];
+      t.stutter_size.assign(stutter.p + i * 8, stutter.p + i * 8 + nb);
       t.str_seq.assign(nb, std::string());
       t.flank_seq.assign(nb, std::string());
       for (int b = 0; b < nb; b++) {
-        const std::string span = span_len[i * 8 + b] > 0 ? read.substr(span_start[i * 8 + b], span_len[i * 8 + b]) : std::string();
+        const std::string span = span_len.p[i * 8 + b] > 0 ? read.substr(span_start.p[i * 8 + b], span_len.p[i * 8 + b]) : std::string();
         (g.hap_blocks_[b].period > 0 ? t.str_seq : t.flank_seq)[b] = span;
       }
-      for (int k = 0; k < n_indels[i]; k++)
-        t.flank_indel_data.emplace_back(indels[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2], indels[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2 + 1]);
-      for (int k = 0; k < n_snps[i]; k++)
-        t.flank_snp_data.emplace_back(snps[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2], (char)snps[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2 + 1]);
+      for (int k = 0; k < n_indels.p[i]; k++)
+        t.flank_indel_data.emplace_back(indels.p[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2], indels.p[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2 + 1]);
+      for (int k = 0; k < n_snps.p[i]; k++)
+        t.flank_snp_data.emplace_back(snps.p[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2], (char)snps.p[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2 + 1]);
       // only the span against the reference is needed by the loop and the VCF record; the CIGAR / gapped string of the
       // traced alignment (used by the reference's HTML visualisation) are built on request (keep_traced_alignments)
       int32_t n_cigar = 0;
       const bool full = keep_traced_alignments;
-      const hipstr_status_t st2 = hipstr_stitch_trace(g.hap_blocks_.front().start, g.hap_aln_info_[key.second].c_str(), t.hap_aln.c_str(), seed_hap_pos[i],
+      const hipstr_status_t st2 = hipstr_stitch_trace(g.hap_blocks_.front().start, g.hap_aln_info_[key.second].c_str(), t.hap_aln.c_str(), seed_hap_pos.p[i],
                                g.pool_seed_[key.first], read.c_str(), &t.start, &t.stop, (int32_t)ctype.size(), full ? ctype.data() : nullptr,
                                full ? clen.data() : nullptr, &n_cigar, (int32_t)aln.size(), full ? aln.data() : nullptr);
       if (st2 != HIPSTR_OK) { failed = 1; return; }
@@ -1242,9 +1365,9 @@ hipstr_status_t hipstr_genotyper_recompute_stutter_models(hipstr_genotyper_t* g,
   return HIPSTR_OK;
 }
 
-hipstr_status_t hipstr_genotyper_timing(const hipstr_genotyper_t* g, double* seconds7) {
-  if (!g || !seconds7) return HIPSTR_ERR_BAD_ARG;
-  for (int i = 0; i < hipstr::GenotyperBatch::T_COUNT; i++) seconds7[i] = g->batch.seconds[i];
+hipstr_status_t hipstr_genotyper_timing(const hipstr_genotyper_t* g, double* seconds9) {
+  if (!g || !seconds9) return HIPSTR_ERR_BAD_ARG;
+  for (int i = 0; i < hipstr::GenotyperBatch::T_COUNT; i++) seconds9[i] = g->batch.seconds[i];
   return HIPSTR_OK;
 }
 /* host seconds of the per-locus decisions summed over loci, by phase: {align-all set-up, stutter-allele discovery,

@@ -177,8 +177,8 @@ class GenotyperBatch {
   int n_rounds = 0;
   /* wall-clock seconds by stage: construction, per-locus host decisions, trace device calls, trace stitching +
    * bookkeeping, alignment calls (packing + K1/K2/K3 + unpacking), posterior calls, VCF formatting */
-  enum { T_CONSTRUCT, T_DECIDE, T_TRACE_DEVICE, T_TRACE_HOST, T_ALIGN, T_POSTERIORS, T_VCF, T_COUNT };
-  double seconds[T_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  enum { T_CONSTRUCT, T_DECIDE, T_TRACE_DEVICE, T_TRACE_HOST, T_ALIGN, T_POSTERIORS, T_VCF, T_ALIGN_PACK, T_ALIGN_UNPACK, T_COUNT };
+  double seconds[T_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   /* the last two split T_ALIGN's host share: packing, unpacking */
   hipstr_status_t run_traces(const std::vector<int>& which, std::string& err);
   /* write_vcf_record of every successfully genotyped locus (seq_stutter_genotyper.h:179-181, impl .cpp:984-1510,
    * get_alleles :691-769, reorder_alleles :673-689, compute_allele_bias :965-982): K3b marginalises the posteriors of

@@ -447,9 +447,10 @@ hipstr_status_t hipstr_genotyper_recompute_stutter_models(hipstr_genotyper_t* g,
 /* alignments (pooled read x haplotype) and traces computed so far, lockstep rounds run */
 hipstr_status_t hipstr_genotyper_stats(const hipstr_genotyper_t* g, int64_t* n_alignments, int64_t* n_traces,
                                        int32_t* n_rounds);
-/* wall-clock seconds by stage, seconds7 = {construction, per-locus host decisions, trace device calls,
- * trace stitching, alignment calls (K1+K2+K3 with packing), posterior calls, VCF formatting} */
-hipstr_status_t hipstr_genotyper_timing(const hipstr_genotyper_t* g, double* seconds7);
+/* wall-clock seconds by stage, seconds9 = {construction, per-locus host decisions, trace device calls,
+ * trace stitching, alignment calls (K1+K2+K3 with packing), posterior calls, VCF formatting, and of the
+ * alignment calls: packing the loci into one batch, unpacking the results} */
+hipstr_status_t hipstr_genotyper_timing(const hipstr_genotyper_t* g, double* seconds9);
 /* the host-decision seconds split by phase (summed over loci): {align-all set-up, stutter-allele discovery, uncalled
  * pruning, unspanned pruning, flank assembly, post-assembly pruning, done, failed} */
 hipstr_status_t hipstr_genotyper_phase_timing(const hipstr_genotyper_t* g, double* seconds8);
