@@ -212,7 +212,7 @@ __device__ void t_repeat_block(const TSide& sd, const TRep& r, const Mat M_prev,
 // of retrace (:363-571) are taken here and stored in `dec` ([row][pitch]): bits 0-1 = best of (insertion to the
 // left, deletion on the diagonal, match on the diagonal) for the match state, bit 2 = deletion state came from a
 // match, bit 3 = insertion state came from a match.  lastcol[row] = M[row][n-1] (compute_aln_logprob reads those).
-__device__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHapSide& hs, const Rows& rw, const BMat dec,
+__device__ __forceinline__ double t_fill_side(const TraceParams& P, const TSide& sd, const DevHapSide& hs, const Rows& rw, const BMat dec,
                               const Mat lastcol, const Mat match, const IMat art_size, const IMat art_pos) {
   const int n = sd.n;
   const long pitch = sd.pitch;
@@ -428,8 +428,14 @@ __global__ void __launch_bounds__(64, MIN_BLOCKS) k_trace(const TraceParams P) {
     }
     L.n = nL; L.rev = 0; L.n_read = n; L.pitch = pitchL;
     R = L; R.n = nR; R.rev = 1; R.pitch = pitchR;
-    const double edgeL = t_fill_side(P, L, hsF, rw, decL, lastL, matchq, Ls, Lp);
-    const double edgeR = t_fill_side(P, R, hsR, rw, decR, lastR, matchq, Rs, Rp);
+    // both sides through ONE inlined copy of the evaluator (a loop, not two call sites: half the code, and the
+    // instruction cache of a divergent thread-per-trace kernel is a measured stall)
+    double edge[2];
+#pragma unroll 1
+    for (int side = 0; side < 2; side++)
+      edge[side] = t_fill_side(P, side ? R : L, side ? hsR : hsF, rw, side ? decR : decL, side ? lastR : lastL, matchq,
+                               side ? Rs : Ls, side ? Rp : Lp);
+    const double edgeL = edge[0], edgeR = edge[1];
     // best seed placement (compute_aln_logprob, HapAligner.cpp:163-231)
     const uint8_t* fseq = P.hapbytes + hsF.seq_off;
     const uint8_t* frow = P.hapbytes + hsF.row_off;
@@ -502,11 +508,9 @@ __global__ void __launch_bounds__(64, MIN_BLOCKS) k_trace(const TraceParams P) {
 
 cudaError_t launch_trace(const TraceParams& p, int n_slots, cudaStream_t stream) {
   if (p.n_traces <= 0) return cudaSuccess;
-  // residency experiment hook: HIPSTR_K5_BLOCKS = 8 (128 registers), 12 (80) or 16 (64) resident CTAs per SM
-  static const int blocks = [] { const char* e = getenv("HIPSTR_K5_BLOCKS"); return e ? atoi(e) : 8; }();
-  if (blocks >= 16) k_trace<16><<<(n_slots + 63) / 64, 64, 0, stream>>>(p);
-  else if (blocks >= 12) k_trace<12><<<(n_slots + 63) / 64, 64, 0, stream>>>(p);
-  else k_trace<8><<<(n_slots + 63) / 64, 64, 0, stream>>>(p);
+  // 8 resident CTAs of 64 threads per SM (128 registers): more residency at 80 / 64 registers was measured and does
+  // not help (profiles/r1_summary.md)
+  k_trace<8><<<(n_slots + 63) / 64, 64, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
