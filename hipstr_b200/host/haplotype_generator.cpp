@@ -156,7 +156,7 @@ bool HaplotypeGenerator::add_haplotype_block(int32_t reg_start, int32_t reg_stop
     for (const ReadView& a : sample) { min_start = std::min(min_start, a.start); max_stop = std::max(max_stop, a.stop); }
   int32_t region_start = reg_start - kLeftPad, region_end = reg_stop + kRightPad;
   const std::string ref_seq = upper(chrom_seq.substr(region_start, region_end - region_start));
-  if (min_start + 5 >= region_start || max_stop - 5 <= region_end) {
+  if (min_start == INT_MAX || min_start + 5 >= region_start || max_stop - 5 <= region_end) {   // (no reads at all: no span)
     failure_msg_ = "No spanning alignments";
     return false;
   }

@@ -243,3 +243,65 @@ def test_recompute_stutter_models_matches_reference(name, kw, assemble):
     assert n_changed > 0
     g.close()
     ctx.close()
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_loop_with_empty_and_unseeded_samples():
+    """Samples without reads, a sample whose reads all lack a seed (too short to leave the repeat), and a one-read sample
+    go through the loop and the VCF writer like in the reference (NO_READS columns, untouched posteriors)."""
+    from hipstr_b200.capi import Context, Genotyper, make_locus_reads, read_locus_reads
+    from ref_genotyper import ReadsOfLocus, RefGenotyper
+    s = Synth(n_loci=2, n_samples=6, reads_per_sample=12, n_alleles=4, read_len=120, seed=141, stutter_rate=0.2)
+    reads, lro = read_locus_reads(Genotyper._reads_struct(s), s.n_loci)
+    keep, new_lro = [], [0]
+    for l in range(s.n_loci):
+        first_of_4 = True
+        for r in range(lro[l], lro[l + 1]):
+            smp = int(s.sample_label[r])
+            if smp == 2:
+                continue                                   # sample 2 has no reads at all
+            if smp == 4 and not first_of_4:
+                continue                                   # sample 4 keeps a single read
+            if smp == 4:
+                first_of_4 = False
+            start, stop, b, q, cig = reads[r]
+            if smp == 1:                                   # sample 1: reads cut down to the inside of the repeat (no seed)
+                lo = max(0, int(s.view.region_start) + 6 - start)
+                b, q = b[lo:lo + 24], q[lo:lo + 24]
+                start, stop, cig = start + lo, start + lo + len(b) - 1, [("=", len(b))]
+                if len(b) < 10 or any(t in "ID" for t, n in reads[r][4]):
+                    continue
+            keep.append((r, (start, stop, b, q, cig)))
+        new_lro.append(len(keep))
+    src = np.array([k[0] for k in keep])
+    rs = make_locus_reads(new_lro, s.locus_sample_off, [k[1] for k in keep], s.sample_label[src], src, s.log_p1[src], s.log_p2[src],
+                          s.haploid, np.zeros(len(keep)))
+    L, start, stop, period = s.n_loci, int(s.view.region_start), int(s.view.region_stop), 4
+    cl = int(s.view.chrom_len)
+    raw = C.string_at(s.view.chrom_seqs, L * cl)
+    chroms = [raw[l * cl:(l + 1) * cl] for l in range(L)]
+    ctx = Context(0)
+    g = Genotyper.from_reads(ctx, rs, L, [start] * L, [stop] * L, [period] * L, chroms)
+    ok = g.genotype(1000, 4, 0.01, True)
+    names = ["S%d" % i for i in range(6)]
+    loci = g.vcf_loci(["chrS"] * L, ["STR"] * L, [start] * L, [stop] * L, [period] * L, chroms, names * L, names)
+    records = g.write_vcf(loci, output_filters=1)
+    n_unseeded = 0
+    for l in range(L):
+        sl = slice(new_lro[l], new_lro[l + 1])
+        rd = ReadsOfLocus([k[1] for k in keep[sl]], 6, s.sample_label[src[sl]], src[sl], s.log_p1[src[sl]], s.log_p2[src[sl]], chroms[l],
+                          (start, stop), period)
+        r = RefGenotyper(rd, reassemble_flanks=True)
+        assert r.initialized and r.genotype() == bool(ok[l])
+        w, o = r.results(), g.results(l)
+        n_unseeded += int((w["seeds"] < 0).sum())
+        assert np.array_equal(o["seeds"], w["seeds"]) and np.array_equal(o["best"], w["best"])
+        assert g.blocks(l) == [b[3] for b in r.blocks()]
+        assert np.abs(o["read_ll"] - w["read_ll"]).max() <= 1e-9
+        want = r.vcf(output_filters=1).rstrip("\n")
+        assert records[l][1].replace(":-0.00:", ":0.00:") == want.replace(":-0.00:", ":0.00:")
+        assert "NO_READS" in want
+    assert n_unseeded > 0
+    g.close()
+    ctx.close()
