@@ -844,32 +844,57 @@ hipstr_status_t hipstr_nw_align_batch_host(hipstr_ctx_t* ctx, int32_t n_pairs, c
     max_read = std::max(max_read, l2);
   }
   if (ops_stride < max_ref + max_read + 1) return fail(ctx, HIPSTR_ERR_BAD_ARG, "ops_stride too small");
-  if (nw_shared_bytes(max_ref, max_read) > (size_t)227 * 1024)
-    return fail(ctx, HIPSTR_ERR_UNSUPPORTED, "window x read exceeds the shared-memory trace (227 KB)");
+  if (nw_shared_bytes(max_ref, max_read) > (size_t)200 * 1024)
+    return fail(ctx, HIPSTR_ERR_UNSUPPORTED, "window too long for the shared-memory rows");
   cudaStream_t s = ctx->stream;
   DevBuf* m = ctx->d_misc;
   DevBuf* o = ctx->d_out;
+  // one trace byte per cell, in global memory; pairs are processed in chunks of at most 2 GB of trace
+  std::vector<int64_t> trace_off((size_t)n_pairs + 1, 0);
+  for (int i = 0; i < n_pairs; i++)
+    trace_off[i + 1] = trace_off[i] + (int64_t)((ref_off[i + 1] - ref_off[i] + 15) / 16 * 16) * (read_off[i + 1] - read_off[i]);
+  const int64_t kTraceBudget = (int64_t)2 << 30;
+  int64_t widest = 0;
+  for (int first = 0; first < n_pairs;) {
+    int last = first;
+    while (last < n_pairs && trace_off[last + 1] - trace_off[first] <= kTraceBudget) last++;
+    if (last == first) return fail(ctx, HIPSTR_ERR_UNSUPPORTED, "one alignment exceeds the trace budget");
+    widest = std::max(widest, trace_off[last] - trace_off[first]);
+    first = last;
+  }
   CU(put(m[0], ref_off, (size_t)n_pairs + 1, s));
   CU(put(m[1], ref_seqs, (size_t)ref_off[n_pairs], s));
   CU(put(m[2], read_off, (size_t)n_pairs + 1, s));
   CU(put(m[3], read_seqs, (size_t)read_off[n_pairs], s));
+  CU(put(m[4], trace_off, s));
   const size_t T = (size_t)n_pairs;
   CU(o[0].reserve(T * ops_stride));
   CU(o[1].reserve(T * sizeof(int32_t)));
   CU(o[2].reserve(T * sizeof(float)));
+  CU(o[3].reserve(T * 2 * sizeof(int32_t)));
+  CU(ctx->d_last.reserve((size_t)std::max<int64_t>(widest, 16)));
   NwParams p;
   std::memset(&p, 0, sizeof(p));
-  p.n_pairs = n_pairs;
   p.ref_off = (const int32_t*)m[0].p; p.ref_seqs = (const char*)m[1].p;
   p.read_off = (const int32_t*)m[2].p; p.read_seqs = (const char*)m[3].p;
   p.use_ref_end_penalty = use_ref_end_penalty ? 1 : 0;
   p.max_ref = max_ref; p.max_read = max_read; p.ops_stride = ops_stride;
   p.out_ops = (char*)o[0].p; p.out_len = (int32_t*)o[1].p; p.out_score = (float*)o[2].p;
-  // one warp per CTA; a few waves of CTAs per SM keep the tail short
+  p.trace_off = (const int64_t*)m[4].p; p.trace = (unsigned char*)ctx->d_last.p; p.end_cell = (int32_t*)o[3].p;
   int n_sm = 148;
   CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
-  CU(launch_nw(p, n_sm * 8, s));
-  ctx->last_launches = 1;
+  int launches = 0;
+  for (int first = 0; first < n_pairs;) {
+    int last = first;
+    while (last < n_pairs && trace_off[last + 1] - trace_off[first] <= kTraceBudget) last++;
+    p.first_pair = first;
+    p.n_pairs = last - first;
+    // one warp per CTA; up to 32 of them per SM, and a few waves keep the tail short
+    CU(launch_nw(p, n_sm * 64, s));
+    launches += 2;
+    first = last;
+  }
+  ctx->last_launches = launches;
   CU(get(ctx, ops, p.out_ops, T * ops_stride));
   CU(get(ctx, ops_len, p.out_len, T));
   CU(get(ctx, score, p.out_score, T));

@@ -170,8 +170,8 @@ cudaError_t launch_trace(const TraceParams& p, int n_slots, cudaStream_t stream)
 
 /* ---- K6: batched Needleman-Wunsch (nw.cu) -------------------------------------------------- */
 struct NwParams {
-  int32_t n_pairs;
-  const int32_t* ref_off;    /* [n_pairs+1] into ref_seqs */
+  int32_t first_pair, n_pairs;  /* this launch handles pairs [first_pair, first_pair + n_pairs) */
+  const int32_t* ref_off;    /* [total pairs+1] into ref_seqs */
   const char* ref_seqs;
   const int32_t* read_off;   /* [n_pairs+1] into read_seqs */
   const char* read_seqs;
@@ -181,6 +181,9 @@ struct NwParams {
   char* out_ops;             /* [n_pairs][ops_stride] 'M' / 'D' (reference base vs gap) / 'I' (read base vs gap), NUL-terminated */
   int32_t* out_len;          /* [n_pairs] number of operations, -1 if the walk back hit an impossible cell */
   float* out_score;          /* [n_pairs] */
+  const int64_t* trace_off;  /* [total pairs+1] prefix sums of (window length rounded up to 16) x read length */
+  unsigned char* trace;      /* trace bytes of the pairs of this launch, pair p at trace_off[p] - trace_off[first_pair] */
+  int32_t* end_cell;         /* [total pairs][2] column and matrix where the alignment ends */
 };
 cudaError_t launch_nw(const NwParams& p, int max_ctas, cudaStream_t stream);
 size_t nw_shared_bytes(int max_ref, int max_read);

@@ -701,19 +701,14 @@ struct PackedReads {
     best.assign((size_t)locus_sample_off.back() * 2, 0);
     total_ll.assign(gs.size(), 0.0);
   }
-  void scatter_back(const std::vector<SeqStutterGenotyper*>& gs, bool with_ll) {
-    size_t ll_at = 0, post_at = 0;
+  void scatter_back(const std::vector<SeqStutterGenotyper*>& gs) {   // posteriors only: the likelihoods did not change
+    size_t post_at = 0;
     for (size_t k = 0; k < gs.size(); k++) {
       SeqStutterGenotyper& g = *gs[k];
-      const size_t nll = (size_t)g.num_reads_ * g.num_alleles_, npost = (size_t)g.num_samples_ * g.num_alleles_ * g.num_alleles_;
-      if (with_ll) {
-        std::copy(read_ll.begin() + ll_at, read_ll.begin() + ll_at + nll, g.log_aln_probs_.begin());
-        std::copy(read_seed.begin() + locus_read_off[k], read_seed.begin() + locus_read_off[k + 1], g.seed_positions_.begin());
-      }
+      const size_t npost = (size_t)g.num_samples_ * g.num_alleles_ * g.num_alleles_;
       g.log_sample_posteriors_.assign(post.begin() + post_at, post.begin() + post_at + npost);
       g.sample_total_LLs_.assign(sample_ll.begin() + locus_sample_off[k], sample_ll.begin() + locus_sample_off[k + 1]);
       g.optimal_haps_.assign(best.begin() + 2 * (size_t)locus_sample_off[k], best.begin() + 2 * (size_t)locus_sample_off[k + 1]);
-      ll_at += nll;
       post_at += npost;
     }
   }
@@ -1024,7 +1019,7 @@ hipstr_status_t GenotyperBatch::run_posteriors(const std::vector<int>& which, st
                                               pr.log_p2.data(), pr.sample_label.data(), pr.read_weight.data(), pr.post.data(),
                                               pr.sample_ll.data(), pr.best.data(), pr.total_ll.data());
   if (st != HIPSTR_OK) { err = std::string("hipstr_posteriors_host: ") + hipstr_last_error(ctx_); return st; }
-  pr.scatter_back(gs, false);
+  pr.scatter_back(gs);
   return HIPSTR_OK;
 }
 
@@ -1061,7 +1056,6 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
     PackedBatch pb;
     std::vector<int32_t> trace_pool, trace_hap;
     std::vector<std::pair<int, int> > owner;   // (locus, index into missing_traces_)
-    int32_t max_read = 0, max_hap = 0;
     while (li < which.size() && trace_pool.size() < kChunk) {
       SeqStutterGenotyper& g = loci[which[li]];
       if (ti >= g.missing_traces_.size()) { li++; ti = 0; continue; }
@@ -1070,14 +1064,6 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
       if (!g.missing_trace_read_.empty())
         for (size_t t = ti; t < g.missing_traces_.size() && trace_pool.size() + (t - ti) < kChunk; t++) own.push_back(g.missing_trace_read_[t]);
       pb.add(g, nullptr, nullptr, &own);
-      for (int p = 0; p < g.num_pools_; p++) max_read = std::max(max_read, g.pool_seq_off_[p + 1] - g.pool_seq_off_[p]);
-      int32_t longest = 0;
-      for (const HapBlock& b : g.hap_blocks_) {
-        size_t m = 0;
-        for (const auto& s : b.seqs) m = std::max(m, s.size());
-        longest += (int32_t)m;
-      }
-      max_hap = std::max(max_hap, longest);
       for (size_t first = ti; ti < g.missing_traces_.size() && trace_pool.size() < kChunk; ti++) {
         trace_pool.push_back(pool_base + (own.empty() ? g.missing_traces_[ti].first : g.num_pools_ + (int)(ti - first)));
         trace_hap.push_back(g.missing_traces_[ti].second);
@@ -1087,7 +1073,6 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
     }
     const size_t n = trace_pool.size();
     if (n == 0) break;
-    (void)max_read; (void)max_hap;
     hipstr_trace_out_t out;
     out.aln_stride = stride;
     out.hap_aln = hap_aln.data();

@@ -138,25 +138,23 @@ def test_host_steps_match_reference_read_by_read(kw, trim):
     assert n_realigned > 20 and n_converted > 5
 
 
-def python_loop(per_read, raw):
-    """GenotyperBamProcessor::left_align_reads' reuse-by-sequence loop over per-read (how, alignment) results."""
+def python_loop(per_read, trimmed):
+    """GenotyperBamProcessor::left_align_reads' reuse-by-sequence loop (:59-79) over the reference's per-read results;
+    trimmed[r] = (bases, qualities) of read r after TrimAlignment, the key of the reuse map."""
     out, seen = [], {}
-    for r, ((how, aln), read) in enumerate(zip(per_read, raw)):
+    for r, (how, aln) in enumerate(per_read):
         if how == -1:
             continue
-        key = trimmed_bases[r]
+        key, quals = trimmed[r]
         prev = seen.get(key)
         if prev is not None and len(prev[2]) == len(key):
-            out.append((r, (prev[0], prev[1], key.upper(), trimmed_quals[r], prev[4])))
+            out.append((r, (prev[0], prev[1], key.upper(), quals, prev[4])))
             continue
         if how == 0:
             continue
         seen[key] = aln
         out.append((r, aln))
     return out
-
-
-trimmed_bases, trimmed_quals = {}, {}
 
 
 @needs_ref
@@ -174,15 +172,10 @@ def test_batched_left_alignment_matches_reference_loop(kw):
     got, got_lro = la.reads()
     want = []
     for l in range(s.n_loci):
-        per_read, locus_raw = [], reads[lro[l]:lro[l + 1]]
-        trimmed_bases.clear()
-        trimmed_quals.clear()
-        for i, rd in enumerate(locus_raw):
-            per_read.append(ref_one(ref, rd, chroms[l], (t0, t1)))
-            # the reuse key is the trimmed read in its original case
-            trimmed = trim_like_reference(rd, t0, t1)
-            trimmed_bases[i], trimmed_quals[i] = trimmed
-        for i, aln in python_loop(per_read, locus_raw):
+        locus_raw = reads[lro[l]:lro[l + 1]]
+        per_read = [ref_one(ref, rd, chroms[l], (t0, t1)) for rd in locus_raw]
+        trimmed = [trim_like_reference(rd, t0, t1) for rd in locus_raw]   # the reuse key keeps the read's original case
+        for i, aln in python_loop(per_read, trimmed):
             want.append((lro[l] + i, aln))
     assert [int(x) for x in la.source] == [w[0] for w in want]
     assert got == [w[1] for w in want]
