@@ -164,7 +164,8 @@ def gpu_full_loop(device, synth, pipelines, gather=None, locus_base=0):
         res = {"loci_per_s": L / dt, "seconds": dt, "loci": L, "pipelines": pipelines, "loci_genotyped": sum(o[0] for o in out),
                "records": sum(o[1] for o in out), "alignments": aln, "traces": sum(o[2]["traces"] for o in out),
                "rounds": max(o[2]["rounds"] for o in out), "alignments_per_s": aln / dt,
-               "stage_seconds_summed_over_windows": stages, "host_threads": host_cores(),
+               "stage_seconds_summed_over_windows": stages,
+               "host_threads": int(os.environ.get("HIPSTR_HOST_THREADS", host_cores())),
                "what": "hipstr_genotyper_create_from_reads + genotype(1000, 4, 0.01, reassemble_flanks) + write_vcf, host buffers in, VCF text out"}
         if best is None or res["loci_per_s"] > best["loci_per_s"]:
             best = res
@@ -290,6 +291,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:   # the ranks of one box share its host cores: split them instead of oversubscribing (read by the library)
+        os.environ.setdefault("HIPSTR_HOST_THREADS", str(max(2, host_cores() // world)))
     workload = "%d synthetic loci, %d samples x %d reads, %d alleles, %d bp reads (BASELINE.json configs[1])" % (
         a.loci, a.samples, a.reads_per_sample, a.alleles, a.read_len)
     config = {"workload": workload, "loci_per_gpu": a.loci, "sharding": "independent loci per rank, NCCL gather of per-locus genotype records per step",
