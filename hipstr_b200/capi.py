@@ -740,7 +740,8 @@ class Genotyper:
         o["best"] = o["best"].reshape(S, 2)
         return o
 
-    def vcf_loci(self, chroms, names, region_start, region_stop, period, chrom_seqs, locus_sample_names, out_sample_names):
+    @staticmethod
+    def vcf_loci(chroms, names, region_start, region_stop, period, chrom_seqs, locus_sample_names, out_sample_names):
         """Build a hipstr_vcf_loci_t (lists of str / bytes per locus; sample names flattened over loci)."""
         def arr(xs):
             xs = [x if isinstance(x, bytes) else x.encode() for x in xs]
