@@ -1029,7 +1029,7 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
   // result buffers of one chunk, allocated once for the widest stride of the call and reused by every chunk (fresh
   // memory would be page-faulted in again, serially, ~0.8 KB per trace)
   size_t total = 0;
-  int32_t widest = 0;
+  int32_t widest_read = 0, widest_hap = 0;   // over ALL loci of the call: a chunk mixes loci, and the stride must hold its longest read plus its longest haplotype
   for (int l : which) {
     const SeqStutterGenotyper& g = loci[l];
     if (g.missing_traces_.empty()) continue;
@@ -1041,10 +1041,11 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
       for (const auto& q : b.seqs) m = std::max(m, q.size());
       hp += (int32_t)m;
     }
-    widest = std::max(widest, rd + hp);
+    widest_read = std::max(widest_read, rd);
+    widest_hap = std::max(widest_hap, hp);
   }
   if (total == 0) { for (int l : which) { loci[l].missing_traces_.clear(); loci[l].missing_trace_read_.clear(); } return HIPSTR_OK; }
-  const int32_t stride = ((widest + 2 + 15) / 16) * 16;
+  const int32_t stride = ((widest_read + widest_hap + 2 + 15) / 16) * 16;
   const size_t cap = std::min(total, kChunk);
   RawBuf<char> hap_aln;
   RawBuf<int32_t> seed_hap_pos, stutter, span_start, span_len, flank_ins, flank_del, n_indels, indels, n_snps, snps;

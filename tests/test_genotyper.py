@@ -305,3 +305,42 @@ def test_loop_with_empty_and_unseeded_samples():
     assert n_unseeded > 0
     g.close()
     ctx.close()
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_window_mixing_long_reads_and_long_haplotypes():
+    """One window whose loci have very different shapes -- long untrimmed reads on short repeats next to short reads on
+    long repeats: the trace buffers must hold the longest read PLUS the longest haplotype of the window, which no single
+    locus reaches (regression: found by tools/loop_stress.py)."""
+    from hipstr_b200.capi import Context, Genotyper, make_locus_reads, read_locus_reads
+    from ref_genotyper import ReadsOfLocus, RefGenotyper
+    parts = [Synth(n_loci=2, n_samples=4, reads_per_sample=8, n_alleles=3, read_len=230, seed=151, period=2, ref_copies=6, trim=0),
+             Synth(n_loci=2, n_samples=4, reads_per_sample=8, n_alleles=4, read_len=150, seed=152, period=6, ref_copies=9)]
+    reads, lro, lso, labels, chroms, regions, periods = [], [0], [0], [], [], [], []
+    for s in parts:
+        rd, off = read_locus_reads(Genotyper._reads_struct(s), s.n_loci)
+        cl = int(s.view.chrom_len)
+        raw = C.string_at(s.view.chrom_seqs, s.n_loci * cl)
+        for l in range(s.n_loci):
+            reads += rd[off[l]:off[l + 1]]
+            labels += list(s.sample_label[off[l]:off[l + 1]])
+            lro.append(len(reads))
+            lso.append(lso[-1] + 4)
+            chroms.append(raw[l * cl:(l + 1) * cl])
+            regions.append((int(s.view.region_start), int(s.view.region_stop)))
+            periods.append(int(s.cfg.period))
+    R, L = len(reads), len(chroms)
+    rs = make_locus_reads(lro, lso, reads, labels, np.arange(R), np.zeros(R), np.zeros(R), np.zeros(L, np.uint8))
+    ctx = Context(0)
+    g = Genotyper.from_reads(ctx, rs, L, [r[0] for r in regions], [r[1] for r in regions], periods, chroms)
+    ok = g.genotype(1000, 4, 0.01, True)
+    for l in range(L):
+        sl = slice(lro[l], lro[l + 1])
+        r = RefGenotyper(ReadsOfLocus(reads[sl], 4, labels[sl], np.arange(R)[sl], np.zeros(lro[l + 1] - lro[l]), np.zeros(lro[l + 1] - lro[l]),
+                                      chroms[l], regions[l], periods[l]), reassemble_flanks=True)
+        assert r.initialized and r.genotype() == bool(ok[l])
+        assert g.blocks(l) == [b[3] for b in r.blocks()]
+        assert np.array_equal(g.results(l)["best"], r.results()["best"])
+    g.close()
+    ctx.close()
