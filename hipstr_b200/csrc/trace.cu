@@ -87,24 +87,60 @@ __device__ double t_match(const TSide& sd, const TRep& r, int q) {
   return acc;
 }
 
-// Replays a position walk twice (maximum, then sum) and tracks the reference's best position
-// (StutterAlignerClass.cpp:92-95,137-140: the position counter after a step is one above the next
-// step's position, so best_pos = 1 - i == -next.pos).
+// Replays a position walk and tracks the reference's best position (StutterAlignerClass.cpp:92-95,137-140: the
+// position counter after a step is one above the next step's position, so best_pos = 1 - i == -next.pos).  The terms
+// of the walk's log-sum-exp are parked in a small per-thread array so that maximum and sum need ONE replay (the float
+// summands add exactly in a double, in any order); a walk with more terms than slots is replayed for the sum.
+#define T_WALK_SLOTS 16
 template <bool INS>
 __device__ double t_walk(const TSide& sd, const TRep& r, int prog_index, int stop, int j, int units, double lp0,
                          int tail_base, int& best_pos) {
   const int CB = HIPSTR_VAL_STRIDE * 8;
-  double mx = lp0, total = 0.0, best = lp0;
+  double mx = lp0, best = lp0;
   best_pos = 0;
-  int fin = 0;
-  for (int pass = 0; pass < 2; pass++) {
-    const DevProgEntry* e = r.progs + prog_index;
-    const double* lr = r.logrun + prog_index;
-    double lp = lp0;
-    if (pass) total = lse_term(lp0, mx);
+  double terms[T_WALK_SLOTS];
+  int n = 0;
+  const DevProgEntry* e = r.progs + prog_index;
+  const double* lr = r.logrun + prog_index;
+  double lp = lp0;
+  while (e->pos > stop) {
+    if (e->moves) {
+      // offsets are pos * CB + code * 8 (see DevProgEntry); recover the two base codes
+      const int xa = (e->off_a - e->pos * CB) / 8, xb = (e->off_b - e->pos * CB) / 8;
+      if (INS) {
+        for (int m = 0; m < units; m++) {
+          const int col = j - r.p + e->pos - m * r.p;
+          lp -= sd.emit(col, xa);
+          lp += sd.emit(col, xb);
+        }
+      } else {
+        lp -= sd.emit(j + e->pos, xa);
+        lp += sd.emit(j + e->pos, xb);
+      }
+    }
+    const double term = lp + *lr;
+    if (n < T_WALK_SLOTS) terms[n] = term;
+    n++;
+    mx = tmax(mx, term);
+    if (lp > best || (r.left_align && lp == best)) { best_pos = -(e + 1)->pos; best = lp; }
+    e++; lr++;
+  }
+  const int fin = e->pos;
+  const bool has_tail = INS ? (fin > -tail_base) : (-fin < tail_base);
+  double tail = 0.0;
+  if (has_tail) {
+    tail = __ldg(r.int_logs + (tail_base + fin)) + lp;
+    mx = tmax(mx, tail);
+  }
+  double total = lse_term(lp0, mx);
+  if (n <= T_WALK_SLOTS) {
+    for (int k = 0; k < n; k++) total += lse_term(terms[k], mx);
+  } else {   // rare: replay the walk, summing against the known maximum
+    e = r.progs + prog_index;
+    lr = r.logrun + prog_index;
+    lp = lp0;
     while (e->pos > stop) {
       if (e->moves) {
-        // offsets are pos * CB + code * 8 (see DevProgEntry); recover the two base codes
         const int xa = (e->off_a - e->pos * CB) / 8, xb = (e->off_b - e->pos * CB) / 8;
         if (INS) {
           for (int m = 0; m < units; m++) {
@@ -117,21 +153,11 @@ __device__ double t_walk(const TSide& sd, const TRep& r, int prog_index, int sto
           lp += sd.emit(j + e->pos, xb);
         }
       }
-      const double term = lp + *lr;
-      if (pass) total += lse_term(term, mx);
-      else {
-        mx = tmax(mx, term);
-        if (lp > best || (r.left_align && lp == best)) { best_pos = -(e + 1)->pos; best = lp; }
-      }
+      total += lse_term(lp + *lr, mx);
       e++; lr++;
     }
-    fin = e->pos;
-    const bool has_tail = INS ? (fin > -tail_base) : (-fin < tail_base);
-    if (has_tail) {
-      const double tail = __ldg(r.int_logs + (tail_base + fin)) + lp;
-      if (pass) total += lse_term(tail, mx); else mx = tmax(mx, tail);
-    }
   }
+  if (has_tail) total += lse_term(tail, mx);
   return lse_finish(mx, total);
 }
 
