@@ -310,6 +310,8 @@ def load():
     lib.hipstr_em_train_host.restype = C.c_int32
     lib.hipstr_em_train_host.argtypes = [vp, C.POINTER(EmBatch), C.c_int32, C.c_double, C.c_double, c_f64p, c_u8p, c_i32p,
                                          c_f64p]
+    lib.hipstr_trace_seconds.restype = None
+    lib.hipstr_trace_seconds.argtypes = [vp, c_f64p]
     lib.hipstr_last_traffic.restype = None
     lib.hipstr_last_traffic.argtypes = [vp, c_i64p, c_i64p, c_i32p]
     lib.hipstr_nw_align_batch_host.restype = C.c_int32
@@ -962,6 +964,11 @@ class Context:
         st, prm, conv, it, ll = em_train(self.lib.hipstr_em_train_host, batch, max_iter, min_abs, min_frac, self.h)
         self._check(st, "em_train_host")
         return prm, conv, it, ll
+
+    def trace_seconds(self):
+        t = np.zeros(4)
+        self.lib.hipstr_trace_seconds(self.h, ptr(t, c_f64p))
+        return dict(zip(("lower", "order_upload", "kernel", "download"), map(float, t)))
 
     def traffic(self):
         a, b, n = C.c_int64(), C.c_int64(), C.c_int32()

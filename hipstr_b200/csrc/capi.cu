@@ -2,6 +2,7 @@
  * capi.cu -- the C-ABI of include/hipstr_b200.h: context, host<->device staging, launches.
  * No CPU fallback: every compute entry point needs a context, and a context needs a GPU.
  */
+#include <chrono>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -80,6 +81,7 @@ struct hipstr_ctx {
   hipstr_dev_genotype gscratch;          // reused by hipstr_genotype_batch_host
   DevBuf d_ll, d_pos, d_misc[12], d_out[6], d_last, d_counters;
   double* d_debug = nullptr;             // test hook, see hipstr_debug_lastcols
+  double trace_seconds[4] = {0, 0, 0, 0};   // accumulated over hipstr_trace_batch_host calls: lowering, ordering + uploads, kernel, downloads
 };
 
 namespace {
@@ -382,6 +384,10 @@ hipstr_status_t hipstr_set_stream(hipstr_ctx_t* ctx, void* cuda_stream) {
 
 int64_t hipstr_batch_num_alignments(const hipstr_align_batch_t* batch) { return batch ? count_alignments(batch) : 0; }
 int32_t hipstr_last_launch_count(const hipstr_ctx_t* ctx) { return ctx ? ctx->last_launches : 0; }
+void hipstr_trace_seconds(const hipstr_ctx_t* ctx, double* seconds4) {
+  if (ctx && seconds4) for (int i = 0; i < 4; i++) seconds4[i] = ctx->trace_seconds[i];
+}
+
 void hipstr_last_traffic(const hipstr_ctx_t* ctx, int64_t* h2d, int64_t* d2h, int32_t* launches) {
   if (h2d) *h2d = ctx ? ctx->h2d_bytes : 0;
   if (d2h) *d2h = ctx ? ctx->d2h_bytes : 0;
@@ -920,12 +926,15 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   FlatBatch& f = ctx->flat;
   std::string err;
   hipstr_status_t st;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_mark = now();
   try {
     st = flatten_batch(&plain, f, err, /*fresh_rows=*/true);
   } catch (const std::bad_alloc&) {
     return fail(ctx, HIPSTR_ERR_CUDA, "out of host memory while staging the batch");
   }
   if (st != HIPSTR_OK) return fail(ctx, st, err);
+  ctx->trace_seconds[0] += now() - t_mark; t_mark = now();
   int n_max = 1, l_max = 1;
   std::vector<int32_t> block_ref_end((size_t)batch->n_blocks), locus_block0((size_t)batch->n_loci);
   for (int l = 0; l < batch->n_loci; l++) {
@@ -969,16 +978,18 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   // haplotypes still has all its seeds on one side -- its padded rows (longest left + longest right side) stay near
   // one read length instead of two.
   std::vector<int32_t> order(n_traces);
-  for (int t = 0; t < n_traces; t++) order[t] = t;
-  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-    const DevPool &pa = f.pools[trace_pool[a]], &pb = f.pools[trace_pool[b]];
-    if (pa.locus != pb.locus) return pa.locus < pb.locus;
-    const bool ha = 2 * pa.seed >= pa.len, hb = 2 * pb.seed >= pb.len;
-    if (ha != hb) return hb;
-    if (trace_hap[a] != trace_hap[b]) return trace_hap[a] < trace_hap[b];
-    if (pa.seed != pb.seed) return pa.seed < pb.seed;
-    return a < b;
-  });
+  {
+    // one 64-bit key per trace (locus | side | haplotype | seed), ties by arrival: a plain sort of pairs, no indirection
+    std::vector<std::pair<uint64_t, int32_t> > keyed((size_t)n_traces);
+    for (int t = 0; t < n_traces; t++) {
+      const DevPool& dp = f.pools[trace_pool[t]];
+      const uint64_t side = 2 * dp.seed >= dp.len ? 0 : 1;   // seeds in the right half first, like the comparator it replaces
+      keyed[t] = std::make_pair(((uint64_t)dp.locus << 42) | (side << 41) | ((uint64_t)(trace_hap[t] & 0xFFFFF) << 21) |
+                                    (uint64_t)(dp.seed & 0x1FFFFF), (int32_t)t);
+    }
+    std::sort(keyed.begin(), keyed.end());
+    for (int t = 0; t < n_traces; t++) order[t] = keyed[t].second;
+  }
   // a warp pads every lane's rows to its longest left and its longest right side: the slab holds the widest warp
   int slab_cols = 2;
   for (int t0 = 0; t0 < n_traces; t0 += 32) {
@@ -1030,7 +1041,11 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   p.out_indels = di; di += T * 2 * HIPSTR_MAX_TRACE_INDELS;
   p.out_snps = di;
   CU(cudaMemsetAsync(o[0].p, 0, T * out->aln_stride, s));
+  CU(cudaStreamSynchronize(s));
+  ctx->trace_seconds[1] += now() - t_mark; t_mark = now();
   CU(launch_trace(p, n_slots, s));
+  CU(cudaStreamSynchronize(s));
+  ctx->trace_seconds[2] += now() - t_mark; t_mark = now();
   ctx->last_launches = 1;
   CU(get(ctx, out->hap_aln, p.out_aln, T * out->aln_stride));
   CU(get(ctx, out->seed_hap_pos, p.out_seed_pos, T));
@@ -1044,6 +1059,7 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   CU(get(ctx, out->indels, p.out_indels, T * 2 * HIPSTR_MAX_TRACE_INDELS));
   CU(get(ctx, out->snps, p.out_snps, T * 2 * HIPSTR_MAX_TRACE_SNPS));
   CU(cudaStreamSynchronize(s));
+  ctx->trace_seconds[3] += now() - t_mark;
   end_call(ctx);
   return HIPSTR_OK;
 }

@@ -582,6 +582,10 @@ hipstr_status_t hipstr_vcf_writer_add_record(hipstr_vcf_writer_t* w, const char*
                                              const char* record_text);
 void            hipstr_vcf_writer_close(hipstr_vcf_writer_t* w);   /* flushes, writes the BGZF EOF block, frees */
 
+/* Wall-clock seconds this context has spent inside hipstr_trace_batch_host, by part:
+ * {host lowering of the batch, ordering + uploads, kernel K5, downloads of the results} */
+void hipstr_trace_seconds(const hipstr_ctx_t* ctx, double* seconds4);
+
 /* Accounting of the last public call on this context: bytes copied host->device and
  * device->host, and kernels launched. */
 void hipstr_last_traffic(const hipstr_ctx_t* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes,

@@ -58,4 +58,5 @@ for rep in range(3):
         print("   [%d] construct %.2f genotype %.2f vcf %.2f %s" % (k, o["construct"], o["genotype"], o["vcf"], o["stats"]))
         print("       stages:", {a: round(b, 3) for a, b in o["stages"].items()})
     if pipes == 1:
+        print("       trace call parts (cumulative over reps):", {a: round(b, 3) for a, b in ctxs[0].trace_seconds().items()})
         print("       decide by phase:", {a: round(b, 3) for a, b in out[0]["phases"].items()})
