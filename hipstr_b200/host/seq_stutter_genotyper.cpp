@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <sstream>
+#include <string_view>
 #include <thread>
 
 #include "../csrc/flatten.h"
@@ -510,6 +511,36 @@ int SeqStutterGenotyper::assemble_flanks() {
       for (const auto& f : flank_seqs)
         if (ref_seq.find(*f.first) == std::string::npos) { only_reference = false; break; }
       if (only_reference) continue;
+      {
+        // Same outcome, one step further: an edge of the graph is a (k+1)-mer; edges of the reference are never pruned
+        // and every other edge is pruned below weight max(2, ceil(0.02 * strings)) (prune_edges, debruijn_graph.cpp:47-60).
+        // If no non-reference (k+1)-mer of the sample's reads reaches that weight at k = kmer_length, pruning leaves the
+        // bare reference path -- acyclic at that k, one source-to-sink path -- and the loop below would stop at its
+        // first k with nothing to report.  Checking that needs a sort of a few hundred substrings, not a graph.
+        const int k = kmer_length;
+        int num_strings = 1;
+        std::vector<std::pair<std::string_view, int> > edges;
+        for (const auto& f : flank_seqs) {
+          if ((int)f.first->size() <= k) continue;
+          num_strings += f.second;
+          const std::string_view sv(*f.first);
+          for (size_t i = 0; i + k + 1 <= sv.size(); i++) {
+            const std::string_view e = sv.substr(i, k + 1);
+            if (ref_seq.find(e) == std::string::npos) edges.emplace_back(e, f.second);
+          }
+        }
+        const int min_weight = std::max(2, (int)std::ceil(0.02 * num_strings));
+        std::sort(edges.begin(), edges.end());
+        bool survives = false;
+        for (size_t i = 0; i < edges.size() && !survives;) {
+          size_t j = i;
+          int weight = 0;
+          while (j < edges.size() && edges[j].first == edges[i].first) weight += edges[j++].second;
+          survives = weight >= min_weight;
+          i = j;
+        }
+        if (!survives) continue;
+      }
       for (int k = kmer_length; k <= max_k; k++) {
         FlankAssembler assembler(k, ref_seq);
         for (const auto& f : flank_seqs) assembler.add_string(*f.first, 1, f.second);
