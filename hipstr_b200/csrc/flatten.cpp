@@ -251,9 +251,20 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
   int64_t total_pairs = count_alignments(b);
   out.n_alignments = total_pairs;
   std::vector<LocusInfo> loci;
-  loci.reserve((size_t)b->n_loci);
 
-  for (int l = 0; l < b->n_loci; l++) {
+  // Per-locus lowering (haplotype sequences, row classes with the reference's reuse history, repeat programs) is the
+  // serial bulk of this function; loci are independent, so chunks of loci are lowered by the host threads into private
+  // arrays with chunk-local offsets and stitched together afterwards (every cross-reference is an index, rebased once).
+  struct Lowered {
+    std::vector<DevHapSide> hapsides;
+    std::vector<uint8_t> hapbytes, hap_mask;
+    std::vector<DevBlock> blocks;
+    std::vector<DevRep> reps;
+    std::vector<DevProgEntry> progs;
+    std::vector<double> prog_logrun;
+    std::vector<int32_t> rep_tabs;
+  };
+  auto lower_locus = [b, fresh_rows](int l, Lowered& out, LocusInfo& li_out, std::string& err) -> hipstr_status_t {
     const int b0 = b->locus_block_off[l], nb = b->locus_block_off[l + 1] - b0;
     if (nb < 1 || nb > HIPSTR_MAX_BLOCKS) { err = "locus needs 1.." + std::to_string(HIPSTR_MAX_BLOCKS) + " blocks"; return HIPSTR_ERR_UNSUPPORTED; }
     if (b->block_period[b0] != 0 || b->block_period[b0 + nb - 1] != 0) {
@@ -486,7 +497,60 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     li.max_len = max_len;
     li.live_haps = H;
     if (mask) { li.live_haps = 0; for (int64_t h = 0; h < H; h++) li.live_haps += mask[h] != 0; }
-    loci.push_back(li);
+    li_out = li;
+    return HIPSTR_OK;
+  };
+  {
+    int n_threads = (int)std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("HIPSTR_HOST_THREADS")) n_threads = std::atoi(e);
+    n_threads = std::max(1, std::min(n_threads, 32));
+    if (b->n_loci < 64) n_threads = 1;
+    const int n_chunks = n_threads == 1 ? 1 : std::min(b->n_loci, n_threads * 4);
+    std::vector<Lowered> parts((size_t)n_chunks);
+    std::vector<hipstr_status_t> part_status((size_t)n_chunks, HIPSTR_OK);
+    std::vector<std::string> part_err((size_t)n_chunks);
+    loci.resize((size_t)b->n_loci);
+    auto lower_chunk = [&](int c) {
+      const int l0 = (int)((int64_t)b->n_loci * c / n_chunks), l1 = (int)((int64_t)b->n_loci * (c + 1) / n_chunks);
+      for (int l = l0; l < l1 && part_status[c] == HIPSTR_OK; l++) part_status[c] = lower_locus(l, parts[c], loci[l], part_err[c]);
+    };
+    if (n_threads == 1) lower_chunk(0);
+    else {
+      std::atomic<int> next(0);
+      auto worker = [&] { for (int c = next.fetch_add(1); c < n_chunks; c = next.fetch_add(1)) lower_chunk(c); };
+      std::vector<std::thread> workers;
+      for (int t = 1; t < n_threads; t++) workers.emplace_back(worker);
+      worker();
+      for (auto& w : workers) w.join();
+    }
+    for (int c = 0; c < n_chunks; c++)
+      if (part_status[c] != HIPSTR_OK) { err = part_err[c]; return part_status[c]; }
+    for (int c = 0; c < n_chunks; c++) {
+      Lowered& p = parts[c];
+      const int32_t side0 = (int32_t)out.hapsides.size(), byte0 = (int32_t)out.hapbytes.size(), blk0 = (int32_t)out.blocks.size(),
+                    rep0 = (int32_t)out.reps.size(), prog0 = (int32_t)out.progs.size(), tab0 = (int32_t)out.rep_tabs.size();
+      for (DevHapSide& hs : p.hapsides)
+        if (hs.len > 0) { hs.seq_off += byte0; hs.row_off += byte0; hs.blk_off += blk0; }   // (placeholders of masked haplotypes stay zero)
+      for (DevBlock& db : p.blocks)
+        if (db.rep >= 0) db.rep += rep0;
+      for (DevRep& r : p.reps) {
+        r.seq_off += byte0;
+        for (int k = 0; k <= HIPSTR_MAX_ARTIFACT_UNITS; k++) r.prog_off[k] += prog0;
+        r.diag_off += tab0;
+        r.ins_off += tab0;
+      }
+      const int l0 = (int)((int64_t)b->n_loci * c / n_chunks), l1 = (int)((int64_t)b->n_loci * (c + 1) / n_chunks);
+      for (int l = l0; l < l1; l++) loci[l].hap_rec0 += side0;
+      out.hapsides.insert(out.hapsides.end(), p.hapsides.begin(), p.hapsides.end());
+      out.hapbytes.insert(out.hapbytes.end(), p.hapbytes.begin(), p.hapbytes.end());
+      out.hap_mask.insert(out.hap_mask.end(), p.hap_mask.begin(), p.hap_mask.end());
+      out.blocks.insert(out.blocks.end(), p.blocks.begin(), p.blocks.end());
+      out.reps.insert(out.reps.end(), p.reps.begin(), p.reps.end());
+      out.progs.insert(out.progs.end(), p.progs.begin(), p.progs.end());
+      out.prog_logrun.insert(out.prog_logrun.end(), p.prog_logrun.begin(), p.prog_logrun.end());
+      out.rep_tabs.insert(out.rep_tabs.end(), p.rep_tabs.begin(), p.rep_tabs.end());
+      p = Lowered();
+    }
   }
 
   // the kernel prefetches two program entries ahead: pad the arrays
