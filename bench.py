@@ -428,10 +428,15 @@ def main():
         # page-locked arena)
         read_ll = torch.zeros(int(s.read_ll_size), dtype=torch.float64).pin_memory().numpy()
         read_seed = torch.zeros(R_tot, dtype=torch.int32).pin_memory().numpy()
+        h_post = torch.zeros(int(s.post_size), dtype=torch.float64).pin_memory().numpy()
+        h_sll = torch.zeros(S_tot, dtype=torch.float64).pin_memory().numpy()
+        h_best = torch.zeros(2 * S_tot, dtype=torch.int32).pin_memory().numpy()
+        h_tot = torch.zeros(s.n_loci, dtype=torch.float64).pin_memory().numpy()
 
         def host_step():
             return ctx.genotype_host(s.batch, reads, int(s.read_ll_size), R_tot, int(s.post_size), S_tot, s.n_loci,
-                                     read_ll=read_ll, read_seed=read_seed)
+                                     read_ll=read_ll, read_seed=read_seed, post=h_post, sample_ll=h_sll, best=h_best,
+                                     total_ll=h_tot)
         for _ in range(a.warmup):
             out = host_step()
         barrier()

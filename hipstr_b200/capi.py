@@ -902,12 +902,15 @@ class Context:
         self.lib.hipstr_free_batch(self.h, handle)
 
     def genotype_host(self, batch, reads, n_elems, n_reads, post_size, n_samples, n_loci, read_ll=None,
-                      read_seed=None):
-        """hipstr_genotype_batch_host: K1 + K2 + K3 with host buffers in and out."""
+                      read_seed=None, post=None, sample_ll=None, best=None, total_ll=None):
+        """hipstr_genotype_batch_host: K1 + K2 + K3 with host buffers in and out (caller-owned, ideally page-locked,
+        result buffers may be passed in; missing ones are allocated)."""
         out = dict(read_ll=np.zeros(n_elems, np.float64) if read_ll is None else read_ll,
                    read_seed=np.full(n_reads, -2, np.int32) if read_seed is None else read_seed,
-                   post=np.zeros(post_size, np.float64), sample_ll=np.zeros(n_samples, np.float64),
-                   best=np.zeros(2 * n_samples, np.int32), total_ll=np.zeros(n_loci, np.float64))
+                   post=np.zeros(post_size, np.float64) if post is None else post,
+                   sample_ll=np.zeros(n_samples, np.float64) if sample_ll is None else sample_ll,
+                   best=np.zeros(2 * n_samples, np.int32) if best is None else best.reshape(-1),
+                   total_ll=np.zeros(n_loci, np.float64) if total_ll is None else total_ll)
         go = GenotypeOut(*[out[k].ctypes.data for k in ("read_ll", "read_seed", "post", "sample_ll", "best", "total_ll")])
         self._check(self.lib.hipstr_genotype_batch_host(self.h, C.byref(batch), C.byref(reads), C.byref(go)),
                     "genotype_batch_host")

@@ -1002,7 +1002,11 @@ hipstr_status_t GenotyperBatch::run_alignments(const std::vector<int>& which, st
     if (masked) {   // in-place semantics of log_aln_probs_ / seed_positions_ under the masks
       std::memcpy(read_ll.p + ll_off[k], g.log_aln_probs_.data(), (size_t)(ll_off[k + 1] - ll_off[k]) * sizeof(double));
       std::memcpy(read_seed.p + r0, g.seed_positions_.data(), nr * sizeof(int32_t));
+    } else {        // results only: fault the pages in here, on all threads, not one by one under the device-to-host copy
+      for (int64_t i = ll_off[k]; i < ll_off[k + 1]; i += 512) read_ll.p[i] = 0.0;
+      for (size_t i = 0; i < nr; i += 1024) read_seed.p[r0 + i] = 0;
     }
+    for (int64_t i = post_off[k]; i < post_off[k + 1]; i += 512) post.p[i] = 0.0;
   });
   hipstr_align_batch_t bt;
   std::memset(&bt, 0, sizeof(bt));
