@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <set>
 
 namespace hipstr {
@@ -181,3 +182,34 @@ bool FlankAssembler::calc_kmer_length(const std::string& ref_seq, int min_kmer, 
 }
 
 }  // namespace hipstr
+
+/* Exported for checking on its own (include/hipstr_b200.h): the per-sample assembly step of assemble_flanks
+ * (seq_stutter_genotyper.cpp:76-97). */
+extern "C" int32_t hipstr_flank_assemble(const char* ref_seq, int32_t n_seqs, const char* const* seqs, int32_t min_kmer, int32_t max_kmer,
+                                         int32_t* k_used, int32_t max_paths, int32_t path_cap, char* paths, int32_t* weights) {
+  if (!ref_seq || (n_seqs > 0 && !seqs) || !k_used || !paths || !weights) return -2;
+  const std::string ref(ref_seq);
+  const int max_k = std::min(max_kmer, ref.empty() ? -1 : (int)ref.size() - 1);
+  int kmer_length;
+  if (!hipstr::FlankAssembler::calc_kmer_length(ref, min_kmer, max_k, kmer_length)) return -1;   // flank too repetitive
+  for (int k = kmer_length; k <= max_k; k++) {
+    hipstr::FlankAssembler assembler(k, ref);
+    for (int i = 0; i < n_seqs; i++) {
+      const std::string s(seqs[i]);
+      if (!s.empty()) assembler.add_string(s);
+    }
+    assembler.prune_edges(0.02, 2);
+    if (!assembler.has_cycles() && assembler.is_source_ok() && assembler.is_sink_ok()) {
+      std::vector<std::pair<std::string, int> > found;
+      assembler.enumerate_paths(2, max_paths, found);
+      *k_used = k;
+      for (size_t i = 0; i < found.size(); i++) {
+        if ((int32_t)found[i].first.size() + 1 > path_cap) return -2;
+        std::memcpy(paths + i * (size_t)path_cap, found[i].first.c_str(), found[i].first.size() + 1);
+        weights[i] = found[i].second;
+      }
+      return (int32_t)found.size();
+    }
+  }
+  return -3;   // cyclic for every k: the sample is marked FLANK_ASSEMBLY_CYCLIC
+}

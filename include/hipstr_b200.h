@@ -510,6 +510,16 @@ double  hipstr_fisher_two_sided(int32_t n11, int32_t n12, int32_t n21, int32_t n
 int32_t hipstr_extract_cigar(const char* cigar_type, const int32_t* cigar_len, int32_t n, int32_t cigar_start,
                              int32_t region_start, int32_t region_end, int32_t* bp_diff);
 
+/* The per-sample step of assemble_flanks (seq_stutter_genotyper.cpp:49-97) on its own: De Bruijn graph of the reference
+ * flank (weight 2) and the sample's flank sequences for the smallest k in [min_kmer, max_kmer] that leaves the
+ * reference acyclic (DebruijnGraph::calc_kmer_length) and the pruned graph acyclic with a clean source and sink, then
+ * the best-first enumeration of source-to-sink paths (debruijn_graph.cpp:151-199, min weight 2).  Returns the number of
+ * paths (sequence i at paths + i * path_cap, its bottleneck weight in weights[i]; *k_used = the k), -1 if the
+ * reference flank is too repetitive, -3 if every k is cyclic, -2 on bad arguments.  Pure host logic. */
+int32_t hipstr_flank_assemble(const char* ref_seq, int32_t n_seqs, const char* const* seqs, int32_t min_kmer,
+                              int32_t max_kmer, int32_t* k_used, int32_t max_paths, int32_t path_cap, char* paths,
+                              int32_t* weights);
+
 /* Haplotype::aln_haps_to_ref for one haplotype (SeqAlignment/Haplotype.cpp:8-86 on top of
  * NeedlemanWunsch::Align, NeedlemanWunsch.cpp:84-423): one of 'M','I','D' per alignment column
  * of alt_hap against ref_hap -- the string hipstr_stitch_trace consumes.  Pure host logic. */

@@ -34,6 +34,7 @@
 #include "region.h"
 #include "stutter_model.h"
 #include "extract_indels.h"
+#include "debruijn_graph.h"
 #include "SeqAlignment/NeedlemanWunsch.h"
 #include "SeqAlignment/AlignmentOps.h"
 #include "cephes/cephes.h"
@@ -285,6 +286,35 @@ int32_t ref_left_align_one(int32_t pos, int32_t end_pos, const char* bases, cons
   *n_out_cigar = (int32_t)out.get_cigar_list().size();
   for (int i = 0; i < *n_out_cigar; i++) { out_ctype[i] = out.get_cigar_list()[i].get_type(); out_clen[i] = out.get_cigar_list()[i].get_num(); }
   return how;
+}
+
+/* The per-sample assembly step of assemble_flanks with the reference's own DebruijnGraph (same contract as
+ * hipstr_flank_assemble). */
+int32_t ref_flank_assemble(const char* ref_seq, int32_t n_seqs, const char* const* seqs, int32_t min_kmer, int32_t max_kmer,
+                           int32_t* k_used, int32_t max_paths, int32_t path_cap, char* paths, int32_t* weights) {
+  const std::string ref(ref_seq);
+  const int max_k = std::min(max_kmer, ref.size() == 0 ? -1 : (int)ref.size() - 1);
+  int kmer_length;
+  if (!DebruijnGraph::calc_kmer_length(ref, min_kmer, max_k, kmer_length)) return -1;
+  for (int k = kmer_length; k <= max_k; k++) {
+    DebruijnGraph assembler(k, ref);
+    for (int i = 0; i < n_seqs; i++) {
+      std::string s(seqs[i]);
+      if (!s.empty()) assembler.add_string(s);
+    }
+    assembler.prune_edges(0.02, 2);
+    if (!assembler.has_cycles() && assembler.is_source_ok() && assembler.is_sink_ok()) {
+      std::vector<std::pair<std::string, int> > found;
+      assembler.enumerate_paths(2, max_paths, found);
+      *k_used = k;
+      for (size_t i = 0; i < found.size(); i++) {
+        strcpy(paths + i * (size_t)path_cap, found[i].first.c_str());
+        weights[i] = found[i].second;
+      }
+      return (int32_t)found.size();
+    }
+  }
+  return -3;
 }
 
 /* The log the reference wrote for this locus (diagnostics in test failures). */
