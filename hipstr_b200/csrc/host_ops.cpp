@@ -101,7 +101,8 @@ extern "C" hipstr_status_t hipstr_pool_reads(int32_t n_reads, const int32_t* seq
     members[it->second].push_back(r);
   }
   int32_t at = 0;
-  std::vector<char> column;
+  std::vector<signed char> column, block;
+  std::vector<uint8_t> rank;
   for (size_t p = 0; p < members.size(); p++) {
     const int32_t first = members[p][0];
     const int32_t len = seq_off[first + 1] - seq_off[first];
@@ -110,12 +111,35 @@ extern "C" hipstr_status_t hipstr_pool_reads(int32_t n_reads, const int32_t* seq
     const size_t m = members[p].size();
     if (m == 1)
       std::memcpy(pool_quals + at, quals + seq_off[first], len);
-    else {
+    else if (m <= 64) {
+      // Upper median per position by RANK: member k's byte is the median where exactly m/2 members sort before it
+      // (signed char order like std::sort, ties by member index).  Every inner loop runs along the read, over
+      // contiguous bytes, so the compiler vectorises it -- a per-position nth_element gathers one byte from each
+      // member and was the largest single cost of building a locus.
+      rank.resize((size_t)len);
+      const uint8_t want = (uint8_t)(m / 2);
+      for (size_t k = 0; k < m; k++) {
+        const signed char* qk = reinterpret_cast<const signed char*>(quals + seq_off[members[p][k]]);
+        std::fill(rank.begin(), rank.end(), (uint8_t)0);
+        for (size_t j = 0; j < m; j++) {
+          if (j == k) continue;
+          const signed char* qj = reinterpret_cast<const signed char*>(quals + seq_off[members[p][j]]);
+          uint8_t* rk = rank.data();
+          if (j < k) for (int32_t i = 0; i < len; i++) rk[i] += (uint8_t)(qj[i] <= qk[i]);
+          else for (int32_t i = 0; i < len; i++) rk[i] += (uint8_t)(qj[i] < qk[i]);
+        }
+        for (int32_t i = 0; i < len; i++)
+          if (rank[i] == want) pool_quals[at + i] = (char)qk[i];
+      }
+    } else {
+      // large pools: members copied into one block, then a selection per position
+      block.resize(m * (size_t)len);
+      for (size_t k = 0; k < m; k++) std::memcpy(block.data() + k * (size_t)len, quals + seq_off[members[p][k]], (size_t)len);
       column.resize(m);
       for (int32_t i = 0; i < len; i++) {
-        for (size_t k = 0; k < m; k++) column[k] = quals[seq_off[members[p][k]] + i];
-        std::nth_element(column.begin(), column.begin() + m / 2, column.end());  // signed char order, as std::sort
-        pool_quals[at + i] = column[m / 2];
+        for (size_t k = 0; k < m; k++) column[k] = block[k * (size_t)len + i];
+        std::nth_element(column.begin(), column.begin() + m / 2, column.end());
+        pool_quals[at + i] = (char)column[m / 2];
       }
     }
     at += len;

@@ -78,3 +78,37 @@ def test_host_ops_pool_reads():
     assert pq.raw[:4] == bytes([sorted([a, b, c])[1] for a, b, c in zip(b"!5I+", b"I5!+", b"555,")])
     assert pq.raw[4:8] == bytes([max(a, b) for a, b in zip(b"ABCD", b"DCBA")])
     assert pq.raw[8:10] == b"##"
+
+
+def test_pool_reads_median_qualities_match_sorting():
+    """Upper median per position (sorted[n/2] in signed-char order, base_quality.cpp:11-28) for pools of 1..200 members,
+    including bytes above 127 -- the rank-based path (<= 64 members) and the selection path agree with plain sorting."""
+    import numpy as np
+    from hipstr_b200.capi import c_i32p, ptr
+    lib = capi.load()
+    rng = np.random.default_rng(9)
+    for trial in range(30):
+        L = int(rng.integers(1, 130))
+        sizes = [int(x) for x in rng.choice([1, 2, 3, 4, 7, 10, 33, 64, 65, 200], int(rng.integers(1, 8)))]
+        seqs, quals = [], []
+        for p, m in enumerate(sizes):
+            seq = bytes(int(v) for v in rng.choice(list(b"ACGT"), L)) + bytes([65 + p])   # distinct per pool
+            for _ in range(m):
+                seqs.append(seq)
+                hi = 256 if trial % 3 == 0 else 127
+                quals.append(bytes(int(v) for v in rng.integers(33 if hi == 127 else 0, hi, L + 1)))
+        order = rng.permutation(len(seqs))
+        seqs, quals = [seqs[i] for i in order], [quals[i] for i in order]
+        off = np.zeros(len(seqs) + 1, np.int32)
+        off[1:] = np.cumsum([len(x) for x in seqs])
+        bases, q = b"".join(seqs), b"".join(quals)
+        pidx, first, poff = np.zeros(len(seqs), np.int32), np.zeros(len(seqs), np.int32), np.zeros(len(seqs) + 1, np.int32)
+        npools = C.c_int32()
+        pb, pq = C.create_string_buffer(len(bases)), C.create_string_buffer(len(bases))
+        st = lib.hipstr_pool_reads(len(seqs), ptr(off, c_i32p), bases, q, ptr(pidx, c_i32p), C.byref(npools), ptr(first, c_i32p),
+                                   ptr(poff, c_i32p), pb, pq)
+        assert st == 0 and npools.value == len(sizes)
+        for p in range(npools.value):
+            rows = np.array([np.frombuffer(quals[r], np.int8) for r in range(len(seqs)) if pidx[r] == p])
+            want = np.sort(rows, axis=0)[rows.shape[0] // 2].astype(np.int8).tobytes()
+            assert pq.raw[poff[p]:poff[p + 1]] == want, (trial, p, rows.shape)
