@@ -74,6 +74,61 @@ class LocusReadsStruct(C.Structure):
                 ("haploid", c_u8p), ("rev_strand", c_u8p), ("read_stop", c_i32p)]
 
 
+class SnpPhasingStruct(C.Structure):
+    """hipstr_snp_phasing_t"""
+    _fields_ = [("n_entries", C.c_int32), ("entry_aln_off", c_i32p), ("entry_snp_set", c_i32p), ("n_alns", C.c_int32),
+                ("aln_pos", c_i32p), ("aln_end", c_i32p), ("aln_seq_off", c_i32p), ("bases", C.c_void_p), ("quals", C.c_void_p),
+                ("aln_cigar_off", c_i32p), ("cigar_type", C.c_void_p), ("cigar_len", c_i32p), ("n_sets", C.c_int32),
+                ("set_off", c_i32p), ("snp_pos", C.c_void_p), ("snp_base1", C.c_void_p), ("snp_base2", C.c_void_p)]
+
+
+class SnpPhasing:
+    """Flat arrays of a hipstr_snp_phasing_t built from Python lists.
+
+    entries: [(snp_set or -1, [alignment, ...])] with alignment = (pos, end, bases, quals, [(cigar char, length), ...]);
+    sets: [[(pos, base one, base two), ...]] sorted by position."""
+
+    def __init__(self, entries, sets):
+        alns = [a for _, al in entries for a in al]
+        self.entry_aln_off = np.zeros(len(entries) + 1, np.int32)
+        self.entry_aln_off[1:] = np.cumsum([len(al) for _, al in entries])
+        self.entry_snp_set = np.array([s for s, _ in entries], np.int32).reshape(-1)
+        self.aln_pos = np.array([a[0] for a in alns], np.int32).reshape(-1)
+        self.aln_end = np.array([a[1] for a in alns], np.int32).reshape(-1)
+        self.aln_seq_off = np.zeros(len(alns) + 1, np.int32)
+        self.aln_seq_off[1:] = np.cumsum([len(a[2]) for a in alns])
+        self.bases = np.frombuffer(b"".join(_as_bytes(a[2]) for a in alns) + b"\0", np.uint8).copy()
+        self.quals = np.frombuffer(b"".join(_as_bytes(a[3]) for a in alns) + b"\0", np.uint8).copy()
+        self.aln_cigar_off = np.zeros(len(alns) + 1, np.int32)
+        self.aln_cigar_off[1:] = np.cumsum([len(a[4]) for a in alns])
+        self.cigar_type = np.frombuffer("".join(t for a in alns for t, _ in a[4]).encode() + b"\0", np.uint8).copy()
+        self.cigar_len = np.array([n for a in alns for _, n in a[4]] + [0], np.int32)
+        self.set_off = np.zeros(len(sets) + 1, np.int32)
+        self.set_off[1:] = np.cumsum([len(x) for x in sets])
+        snps = [x for st in sets for x in st]
+        self.snp_pos = np.array([x[0] for x in snps] + [0], np.uint32)
+        self.snp_base1 = np.frombuffer("".join(x[1] for x in snps).encode() + b"\0", np.uint8).copy()
+        self.snp_base2 = np.frombuffer("".join(x[2] for x in snps).encode() + b"\0", np.uint8).copy()
+        self.n_entries, self.n_alns, self.n_sets = len(entries), len(alns), len(sets)
+        self.struct = SnpPhasingStruct(
+            self.n_entries, ptr(self.entry_aln_off, c_i32p), ptr(self.entry_snp_set, c_i32p), self.n_alns,
+            ptr(self.aln_pos, c_i32p), ptr(self.aln_end, c_i32p), ptr(self.aln_seq_off, c_i32p), self.bases.ctypes.data,
+            self.quals.ctypes.data, ptr(self.aln_cigar_off, c_i32p), self.cigar_type.ctypes.data, ptr(self.cigar_len, c_i32p),
+            self.n_sets, ptr(self.set_off, c_i32p), self.snp_pos.ctypes.data, self.snp_base1.ctypes.data,
+            self.snp_base2.ctypes.data)
+
+    def run(self, fn, *handle):
+        """Calls a function with the product's signature (ctx?, batch, log_p1, log_p2, counts) -> (status, p1, p2, counts)."""
+        p1, p2 = np.zeros(max(self.n_entries, 1)), np.zeros(max(self.n_entries, 1))
+        counts = np.zeros((max(self.n_entries, 1), 4), np.int32)
+        st = fn(*handle, C.byref(self.struct), ptr(p1, c_f64p), ptr(p2, c_f64p), ptr(counts, c_i32p))
+        return st, p1[:self.n_entries], p2[:self.n_entries], counts[:self.n_entries]
+
+
+def _as_bytes(x):
+    return x if isinstance(x, (bytes, bytearray)) else x.encode("latin-1")
+
+
 class VcfLoci(C.Structure):
     """hipstr_vcf_loci_t"""
     _fields_ = [("chrom", C.POINTER(C.c_char_p)), ("name", C.POINTER(C.c_char_p)), ("region_start", c_i32p),
@@ -314,6 +369,8 @@ def load():
     lib.hipstr_trace_seconds.argtypes = [vp, c_f64p]
     lib.hipstr_last_traffic.restype = None
     lib.hipstr_last_traffic.argtypes = [vp, c_i64p, c_i64p, c_i32p]
+    lib.hipstr_snp_phasing_batch_host.restype = C.c_int32
+    lib.hipstr_snp_phasing_batch_host.argtypes = [vp, C.POINTER(SnpPhasingStruct), c_f64p, c_f64p, c_i32p]
     lib.hipstr_nw_align_batch_host.restype = C.c_int32
     lib.hipstr_nw_align_batch_host.argtypes = [vp, C.c_int32, c_i32p, C.c_char_p, c_i32p, C.c_char_p, C.c_int32, C.c_int32,
                                                C.c_void_p, c_i32p, C.POINTER(C.c_float)]
@@ -961,6 +1018,12 @@ class Context:
                     "nw_align_batch_host")
         raw = ops.reshape(n, stride)
         return [bytes(raw[i, :max(int(lens[i]), 0)]).decode() if lens[i] >= 0 else None for i in range(n)], score
+
+    def snp_phasing(self, batch):
+        """hipstr_snp_phasing_batch_host on a SnpPhasing -> (log_p1, log_p2, counts [n][4])."""
+        st, p1, p2, counts = batch.run(self.lib.hipstr_snp_phasing_batch_host, self.h)
+        self._check(st, "snp_phasing_batch_host")
+        return p1, p2, counts
 
     def em_train(self, batch, max_iter=100, min_abs=0.01, min_frac=0.001):
         """hipstr_em_train_host -> (params [L][6], converged [L], iterations [L], final LL [L])."""

@@ -909,6 +909,84 @@ hipstr_status_t hipstr_nw_align_batch_host(hipstr_ctx_t* ctx, int32_t n_pairs, c
   return HIPSTR_OK;
 }
 
+hipstr_status_t hipstr_snp_phasing_batch_host(hipstr_ctx_t* ctx, const hipstr_snp_phasing_t* b, double* log_p1, double* log_p2,
+                                              int32_t* counts) {
+  if (!ctx || !b || b->n_entries < 0 || b->n_alns < 0 || b->n_sets < 0) return HIPSTR_ERR_BAD_ARG;
+  if (b->n_entries == 0) return HIPSTR_OK;
+  if (!log_p1 || !log_p2 || !counts || !b->entry_aln_off || !b->entry_snp_set) return HIPSTR_ERR_BAD_ARG;
+  if (b->n_alns > 0 && (!b->aln_pos || !b->aln_end || !b->aln_seq_off || !b->bases || !b->quals || !b->aln_cigar_off ||
+                        !b->cigar_type || !b->cigar_len))
+    return HIPSTR_ERR_BAD_ARG;
+  if (b->n_sets > 0 && (!b->set_off || (b->set_off[b->n_sets] > 0 && (!b->snp_pos || !b->snp_base1 || !b->snp_base2))))
+    return HIPSTR_ERR_BAD_ARG;
+  CU(cudaSetDevice(ctx->device));
+  begin_call(ctx);
+  if (b->entry_aln_off[0] != 0 || b->entry_aln_off[b->n_entries] != b->n_alns)
+    return fail(ctx, HIPSTR_ERR_BAD_ARG, "entry_aln_off does not cover the alignments");
+  for (int e = 0; e < b->n_entries; e++) {
+    if (b->entry_aln_off[e + 1] < b->entry_aln_off[e]) return fail(ctx, HIPSTR_ERR_BAD_ARG, "entry_aln_off not ascending");
+    if (b->entry_snp_set[e] < -1 || b->entry_snp_set[e] >= b->n_sets) return fail(ctx, HIPSTR_ERR_BAD_ARG, "SNP set out of range");
+  }
+  for (int s = 0; s < b->n_sets; s++)
+    for (int i = b->set_off[s] + 1; i < b->set_off[s + 1]; i++)
+      if (b->snp_pos[i] <= b->snp_pos[i - 1]) return fail(ctx, HIPSTR_ERR_BAD_ARG, "SNP positions of a set must be ascending and distinct");
+  cudaStream_t s = ctx->stream;
+  DevBuf* m = ctx->d_misc;
+  DevBuf* o = ctx->d_out;
+  const size_t E = (size_t)b->n_entries, A = (size_t)b->n_alns;
+  const size_t n_snps = b->n_sets ? (size_t)b->set_off[b->n_sets] : 0;
+  const int32_t zero = 0;
+  CU(put(m[0], b->entry_aln_off, E + 1, s));
+  CU(put(m[1], b->entry_snp_set, E, s));
+  CU(put(m[2], b->aln_pos ? b->aln_pos : &zero, std::max<size_t>(A, 1), s));
+  CU(put(m[3], b->aln_end ? b->aln_end : &zero, std::max<size_t>(A, 1), s));
+  CU(put(m[4], b->aln_seq_off ? b->aln_seq_off : &zero, A ? A + 1 : 1, s));
+  const size_t n_bases = A ? (size_t)b->aln_seq_off[A] : 0, n_ops = A ? (size_t)b->aln_cigar_off[A] : 0;
+  const char pad = 0;
+  CU(put(m[5], n_bases ? b->bases : &pad, std::max<size_t>(n_bases, 1), s));
+  CU(put(m[6], n_bases ? b->quals : &pad, std::max<size_t>(n_bases, 1), s));
+  CU(put(m[7], b->aln_cigar_off ? b->aln_cigar_off : &zero, A ? A + 1 : 1, s));
+  CU(put(m[8], n_ops ? b->cigar_type : &pad, std::max<size_t>(n_ops, 1), s));
+  CU(put(m[9], n_ops ? b->cigar_len : &zero, std::max<size_t>(n_ops, 1), s));
+  CU(put(m[10], b->n_sets ? b->set_off : &zero, (size_t)b->n_sets + 1, s));
+  // the three SNP arrays share one buffer: positions, then the two allele bytes
+  std::vector<unsigned char> snps(std::max<size_t>(n_snps, 1) * 6);
+  if (n_snps) {
+    std::memcpy(snps.data(), b->snp_pos, n_snps * 4);
+    std::memcpy(snps.data() + n_snps * 4, b->snp_base1, n_snps);
+    std::memcpy(snps.data() + n_snps * 5, b->snp_base2, n_snps);
+  }
+  CU(put(m[11], snps.data(), snps.size(), s));
+  CU(o[0].reserve(E * sizeof(double)));
+  CU(o[1].reserve(E * sizeof(double)));
+  CU(o[2].reserve(E * 4 * sizeof(int32_t)));
+  SnpPhaseParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n_entries = b->n_entries;
+  p.entry_aln_off = (const int32_t*)m[0].p; p.entry_snp_set = (const int32_t*)m[1].p;
+  p.aln_pos = (const int32_t*)m[2].p; p.aln_end = (const int32_t*)m[3].p; p.aln_seq_off = (const int32_t*)m[4].p;
+  p.bases = (const char*)m[5].p; p.quals = (const char*)m[6].p;
+  p.aln_cigar_off = (const int32_t*)m[7].p; p.cigar_type = (const char*)m[8].p; p.cigar_len = (const int32_t*)m[9].p;
+  p.set_off = (const int32_t*)m[10].p;
+  p.snp_pos = (const uint32_t*)m[11].p;
+  p.snp_base1 = (const char*)m[11].p + n_snps * 4;
+  p.snp_base2 = (const char*)m[11].p + n_snps * 5;
+  p.qual_lut = ctx->d_qual_lut;
+  p.out_log_p1 = (double*)o[0].p; p.out_log_p2 = (double*)o[1].p; p.out_counts = (int32_t*)o[2].p;
+  int n_sm = 148;
+  CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+  CU(launch_snp_phase(p, n_sm, s));
+  ctx->last_launches = 1;
+  CU(get(ctx, log_p1, p.out_log_p1, E));
+  CU(get(ctx, log_p2, p.out_log_p2, E));
+  CU(get(ctx, counts, p.out_counts, E * 4));
+  CU(cudaStreamSynchronize(s));
+  end_call(ctx);
+  for (size_t e = 0; e < E; e++)
+    if (counts[4 * e + 3] != 0) return fail(ctx, HIPSTR_ERR_BAD_ARG, "an alignment's CIGAR is invalid or inconsistent with its bases");
+  return HIPSTR_OK;
+}
+
 hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch, const int32_t* block_start,
                                         int32_t n_traces, const int32_t* trace_pool, const int32_t* trace_hap,
                                         const hipstr_trace_out_t* out) {

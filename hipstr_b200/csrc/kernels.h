@@ -188,5 +188,29 @@ struct NwParams {
 cudaError_t launch_nw(const NwParams& p, int max_ctas, cudaStream_t stream);
 size_t nw_shared_bytes(int max_ref, int max_read);
 
+/* ---- K7: SNP phasing log-likelihoods (snp_phase.cu) ---------------------------------------- */
+struct SnpPhaseParams {
+  int32_t n_entries;
+  const int32_t* entry_aln_off;  /* [n_entries+1] alignments of an entry: the STR read, then its mate if any */
+  const int32_t* entry_snp_set;  /* [n_entries] SNP set of the read's sample, -1 = none (both LLs stay 0) */
+  const int32_t* aln_pos;        /* BamAlignment::Position() */
+  const int32_t* aln_end;        /* BamAlignment::GetEndPosition(), exclusive */
+  const int32_t* aln_seq_off;    /* [n_alns+1] into bases / quals */
+  const char* bases;
+  const char* quals;
+  const int32_t* aln_cigar_off;  /* [n_alns+1] into cigar_type / cigar_len */
+  const char* cigar_type;
+  const int32_t* cigar_len;
+  const int32_t* set_off;        /* [n_sets+1] into the SNP arrays; positions ascending within a set */
+  const uint32_t* snp_pos;
+  const char* snp_base1;
+  const char* snp_base2;
+  const double* qual_lut;        /* [256][2] */
+  double* out_log_p1;
+  double* out_log_p2;
+  int32_t* out_counts;           /* [n_entries][4]: haplotype-1 matches, haplotype-2 matches, mismatches, status */
+};
+cudaError_t launch_snp_phase(const SnpPhaseParams& p, int n_sm, cudaStream_t stream);
+
 }  // namespace hipstr
 #endif

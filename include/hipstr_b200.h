@@ -592,6 +592,45 @@ hipstr_status_t hipstr_vcf_writer_add_record(hipstr_vcf_writer_t* w, const char*
                                              const char* record_text);
 void            hipstr_vcf_writer_close(hipstr_vcf_writer_t* w);   /* flushes, writes the BGZF EOF block, frees */
 
+/* --- section 8(f) row 4, first slice: SNP phasing log-likelihoods (K7) ----------
+ * Replaces calc_het_snp_factors (src/snp_phasing_quality.cpp:92-120) -> add_log_phasing_probs (:65-90) ->
+ * extract_bases_and_qualities (:4-63) with SNPTree::findContained (src/snp_tree.h:114-126), as called by
+ * SNPBamProcessor::process_reads (src/snp_bam_processor.cpp:60-76), for all reads of a batch of loci in ONE
+ * launch.  These are the log_p1 / log_p2 the genotyper takes (hipstr_locus_reads_t.log_p1 / log_p2).
+ *
+ * An ENTRY is one STR read, optionally followed by its mate (the paired overload): the terms of the read's
+ * SNPs are added first, then the mate's, into the same two doubles, like the reference; results are
+ * bit-identical.  A SNP SET is the position-sorted list of one sample's phased heterozygous SNPs (what
+ * create_snp_trees puts into that sample's SNPTree); entry_snp_set = -1 for a sample without SNP
+ * information leaves both values 0 (snp_bam_processor.cpp:77-84).  Alignments carry the fields of the
+ * (possibly trimmed) BamAlignment: Position(), GetEndPosition() (exclusive), QueryBases(), Qualities(),
+ * CigarData() with the BAM operation characters M = X D I S H.
+ * counts [n_entries][4]: bases matching haplotype one, haplotype two, neither (the reference's
+ * p1_match_count / p2_match_count / mismatch_count, summed by the caller), and a status that is 0 unless
+ * the reference would have died on the entry (1 invalid CIGAR character, 2 CIGAR longer than the read,
+ * 3 CIGAR shorter than the alignment span); any non-zero status makes the call return HIPSTR_ERR_BAD_ARG. */
+typedef struct {
+  int32_t n_entries;
+  const int32_t* entry_aln_off;   /* [n_entries+1] alignments of entry e: [off[e], off[e+1]) */
+  const int32_t* entry_snp_set;   /* [n_entries] index of the sample's SNP set, or -1 */
+  int32_t n_alns;
+  const int32_t* aln_pos;         /* [n_alns] */
+  const int32_t* aln_end;         /* [n_alns] */
+  const int32_t* aln_seq_off;     /* [n_alns+1] offsets into bases / quals */
+  const char* bases;
+  const char* quals;
+  const int32_t* aln_cigar_off;   /* [n_alns+1] offsets into cigar_type / cigar_len */
+  const char* cigar_type;
+  const int32_t* cigar_len;
+  int32_t n_sets;
+  const int32_t* set_off;         /* [n_sets+1] offsets into the SNP arrays */
+  const uint32_t* snp_pos;        /* SNP::pos() (0-based), ascending and distinct within a set */
+  const char* snp_base1;          /* SNP::base_one(): allele on the sample's first haplotype */
+  const char* snp_base2;
+} hipstr_snp_phasing_t;
+hipstr_status_t hipstr_snp_phasing_batch_host(hipstr_ctx_t* ctx, const hipstr_snp_phasing_t* batch, double* log_p1,
+                                              double* log_p2, int32_t* counts);
+
 /* Wall-clock seconds this context has spent inside hipstr_trace_batch_host, by part:
  * {host lowering of the batch, ordering + uploads, kernel K5, downloads of the results} */
 void hipstr_trace_seconds(const hipstr_ctx_t* ctx, double* seconds4);

@@ -1238,3 +1238,69 @@ int32_t oracle_nw_align(const char* ref, int32_t L1, const char* read, int32_t L
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// SNP phasing log-likelihoods: checker of K7 (hipstr_snp_phasing_batch_host).
+// snp_phasing_quality.cpp:4-63 (extract_bases_and_qualities), :65-90 (add_log_phasing_probs),
+// :92-120 (calc_het_snp_factors); snp_tree.h:114-126 (findContained = SNPs with start <= pos <= stop,
+// in position order).  Two passes per alignment like the reference: first the base / quality under
+// every overlapped SNP, then the sums.
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t oracle_snp_phasing(const hipstr_snp_phasing_t* b, double* log_p1, double* log_p2, int32_t* counts) {
+  for (int e = 0; e < b->n_entries; e++) {
+    double p1 = 0.0, p2 = 0.0;
+    int32_t c1 = 0, c2 = 0, mis = 0;
+    const int set = b->entry_snp_set[e];
+    for (int a = b->entry_aln_off[e]; set >= 0 && a < b->entry_aln_off[e + 1]; a++) {
+      std::vector<int> snps;   // findContained(Position(), GetEndPosition() - 1)
+      for (int i = b->set_off[set]; i < b->set_off[set + 1]; i++)
+        if (b->snp_pos[i] >= (uint32_t)b->aln_pos[a] && b->snp_pos[i] <= (uint32_t)(b->aln_end[a] - 1)) snps.push_back(i);
+      if (snps.empty()) continue;
+      const char* seq = b->bases + b->aln_seq_off[a];
+      const char* qual = b->quals + b->aln_seq_off[a];
+      const int n_bases = b->aln_seq_off[a + 1] - b->aln_seq_off[a];
+      std::vector<char> bases, quals;
+      int32_t pos = b->aln_pos[a];
+      size_t snp_index = 0;
+      unsigned int base_index = 0;
+      int cigar_index = b->aln_cigar_off[a];
+      while (snp_index < snps.size() && cigar_index < b->aln_cigar_off[a + 1]) {
+        const uint32_t snp_pos = b->snp_pos[snps[snp_index]];
+        const int32_t len = b->cigar_len[cigar_index];
+        switch (b->cigar_type[cigar_index]) {
+          case 'M': case '=': case 'X':
+            if (snp_pos < (uint32_t)(pos + len)) {
+              const unsigned int at = snp_pos - pos + base_index;
+              if ((int)at >= n_bases) return -2;
+              bases.push_back(seq[at]);
+              quals.push_back(qual[at]);
+              snp_index++;
+            } else { pos += len; base_index += len; cigar_index++; }
+            break;
+          case 'D':
+            if (snp_pos < (uint32_t)(pos + len)) { bases.push_back('-'); quals.push_back('-'); snp_index++; }
+            else { pos += len; cigar_index++; }
+            break;
+          case 'I': base_index += len; cigar_index++; break;
+          case 'S':
+            if (snp_pos < (uint32_t)pos) { bases.push_back('-'); quals.push_back('-'); snp_index++; }
+            else { base_index += len; cigar_index++; }
+            break;
+          case 'H': cigar_index++; break;
+          default: return -1;
+        }
+      }
+      if (bases.size() != snps.size()) return -3;   // the reference's assert
+      for (size_t i = 0; i < snps.size(); i++) {
+        if (bases[i] == '-') continue;
+        const unsigned char q = (unsigned char)quals[i];
+        if (bases[i] == b->snp_base1[snps[i]]) { p1 += T().qual_correct[q]; p2 += T().qual_error[q]; c1++; }
+        else if (bases[i] == b->snp_base2[snps[i]]) { p1 += T().qual_error[q]; p2 += T().qual_correct[q]; c2++; }
+        else { p1 += T().qual_error[q]; p2 += T().qual_error[q]; mis++; }
+      }
+    }
+    log_p1[e] = p1; log_p2[e] = p2;
+    counts[4 * e] = c1; counts[4 * e + 1] = c2; counts[4 * e + 2] = mis; counts[4 * e + 3] = 0;
+  }
+  return 0;
+}

@@ -73,6 +73,10 @@ int32_t oracle_em_train(const hipstr_em_batch_t* batch, int32_t max_iter, double
                         double min_LL_frac_change, double* params_out, uint8_t* converged_out,
                         int32_t* iters_out, double* ll_out);
 
+/* calc_het_snp_factors for every entry of the batch (checker of K7); counts [n_entries][4] like the product;
+ * returns 0, or < 0 where the reference would have died. */
+int32_t oracle_snp_phasing(const hipstr_snp_phasing_t* batch, double* log_p1, double* log_p2, int32_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

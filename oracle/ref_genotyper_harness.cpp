@@ -10,9 +10,8 @@
  * member arrays the product must reproduce.  `#define private public` is only used to READ
  * members (hap_blocks_, log_aln_probs_, ...); no reference source is modified or copied.
  *
- * htslib is not built: BAM/VCF/tabix entry points that this path never reaches (ref_vcf is
- * NULL, no BAM is opened) are stubbed to abort(); kt_fisher_exact (htslib kfunc.c) and bdtr
- * (cephes) ARE reached by write_vcf_record and are compiled from the vendored C files.
+ * kt_fisher_exact (htslib kfunc.c) and bdtr (cephes), which write_vcf_record reaches, come from the
+ * vendored C files that oracle/Makefile compiles one by one (htslib 1.9 in full, see ref_bam_harness.cpp).
  */
 #include <cstdlib>
 #include <cstring>
@@ -251,7 +250,7 @@ int32_t ref_nw_align(const char* ref, int32_t L1, const char* read, int32_t L2, 
 
 /* One BAM-level alignment through the reference's left-alignment steps (genotyper_bam_processor.cpp:53-67):
  * TrimAlignment (bam_io.cpp:384-477) when do_trim, then convertAlignment for reads whose CIGAR is all M / = , else
- * realign (SeqAlignment/AlignmentOps.cpp:14-167).  The BamAlignment is assembled in memory (bam_min.c).
+ * realign (SeqAlignment/AlignmentOps.cpp:14-167).  The BamAlignment is assembled in memory.
  * Returns -1 if nothing is left after trimming, 0 if realign() failed, 1 = converted, 2 = realigned.
  * out_pos = {start, stop}; strings NUL-terminated; CIGAR in out_ctype / out_clen (*n_out_cigar runs). */
 int32_t ref_left_align_one(int32_t pos, int32_t end_pos, const char* bases, const char* quals, int32_t n_cigar,

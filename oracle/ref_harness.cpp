@@ -35,19 +35,6 @@
 
 #include "../include/hipstr_b200.h"
 
-// genotyper.cpp (get_vcf_header) pulls in FastaReader, whose only external symbols are
-// htslib's faidx entry points; the hot path never reaches them, so instead of building
-// htslib they are stubbed here (calling one aborts).
-extern "C" {
-void fai_destroy(void*) {}
-void* fai_load(const char*) { abort(); }
-int faidx_nseq(const void*) { abort(); }
-const char* faidx_iseq(const void*, int) { abort(); }
-int faidx_seq_len(const void*, const char*) { abort(); }
-char* fai_fetch(const void*, const char*, int*) { abort(); }
-char* faidx_fetch_seq(const void*, const char*, int, int, int*) { abort(); }
-}
-
 namespace {
 
 struct Init {
