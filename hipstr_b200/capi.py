@@ -129,6 +129,136 @@ def _as_bytes(x):
     return x if isinstance(x, (bytes, bytearray)) else x.encode("latin-1")
 
 
+class FilterOptions(C.Structure):
+    """hipstr_filter_options_t"""
+    _fields_ = [("max_mate_dist", C.c_int32), ("min_bp_before_indel", C.c_int32), ("min_flank", C.c_int32),
+                ("min_read_end_match", C.c_int32), ("maximal_end_match_window", C.c_int32), ("require_paired_reads", C.c_int32),
+                ("min_sum_qual_log_prob", C.c_double), ("max_total_reads", C.c_int32), ("base_qual_trim", C.c_int32),
+                ("remove_pcr_dups", C.c_int32), ("trim_adapters", C.c_int32)]
+
+
+class FilteredView(C.Structure):
+    """hipstr_filtered_view_t"""
+    _fields_ = [("n_samples", C.c_int32), ("sample_names", C.POINTER(C.c_char_p)), ("sample_entry_off", c_i32p),
+                ("entry_passes", C.c_void_p), ("aln_flag", c_i32p), ("reads", SnpPhasingStruct)]
+
+
+def _text(fn, h):
+    """Calls a *_text(handle, cap, out) function, growing the buffer to the size it asks for."""
+    cap = 1 << 16
+    while True:
+        buf = C.create_string_buffer(cap)
+        n = fn(h, cap, buf)
+        if n >= 0:
+            return buf.raw[:n].decode("latin-1")
+        if -n <= cap:
+            raise HipstrError(-2, "text call failed")
+        cap = -n
+
+
+class BamReader:
+    """hipstr_bam_reader_t: BAM files (+ .bai) read region by region, file after file."""
+
+    def __init__(self, paths):
+        self.lib, self.paths = load(), list(paths)
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        h = C.c_void_p()
+        st = self.lib.hipstr_bam_reader_open(len(paths), arr, C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "bam_reader_open: " + self.lib.hipstr_ingest_last_error().decode())
+        self.h = h
+
+    def read_groups(self):
+        """[(path, id, sample or None, library or None)]"""
+        rows = [line.split("\t") for line in _text(self.lib.hipstr_bam_reader_read_groups, self.h).splitlines()]
+        return [(r[0], r[1], None if r[2] == "-" else r[2], None if r[3] == "-" else r[3]) for r in rows]
+
+    def fetch(self, chrom, start, end):
+        h = C.c_void_p()
+        st = self.lib.hipstr_bam_reader_fetch(self.h, chrom.encode(), start, end, C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "bam_reader_fetch: " + self.lib.hipstr_ingest_last_error().decode())
+        return BamRecords(self.lib, h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hipstr_bam_reader_close(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class BamRecords:
+    """hipstr_bam_records_t"""
+
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, h
+
+    def __len__(self):
+        return self.lib.hipstr_bam_records_count(self.h)
+
+    def text(self):
+        return _text(self.lib.hipstr_bam_records_text, self.h)
+
+    def filter(self, chrom_seq, regions, rg_map, options=None, **overrides):
+        """hipstr_filter_reads; regions = [(start, stop)], rg_map = {file path + read group id: (sample, library)}."""
+        opt = options or FilterOptions()
+        if options is None:
+            self.lib.hipstr_filter_default_options(C.byref(opt))
+        for k, v in overrides.items():
+            setattr(opt, k, v)
+        starts = np.array([r[0] for r in regions], np.int32)
+        stops = np.array([r[1] for r in regions], np.int32)
+        keys = list(rg_map)
+        mk = lambda xs: (C.c_char_p * max(len(xs), 1))(*[x.encode() for x in xs])
+        h = C.c_void_p()
+        seq = chrom_seq if isinstance(chrom_seq, bytes) else chrom_seq.encode()
+        st = self.lib.hipstr_filter_reads(self.h, seq, len(regions), ptr(starts, c_i32p), ptr(stops, c_i32p), C.byref(opt), len(keys),
+                                          mk(keys), mk([rg_map[k][0] for k in keys]), mk([rg_map[k][1] for k in keys]), C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "filter_reads: " + self.lib.hipstr_ingest_last_error().decode())
+        return FilteredReads(self.lib, h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hipstr_bam_records_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class FilteredReads:
+    """hipstr_filtered_reads_t"""
+    COUNTS = ("overlapping", "hard_clipped", "has_n", "low_quality", "no_unique_mapping", "no_mate", "pcr_duplicates", "too_many_reads",
+              "passed")
+
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, h
+
+    def text(self):
+        return _text(self.lib.hipstr_filtered_reads_text, self.h)
+
+    def counts(self):
+        c = np.zeros(9, np.int32)
+        self.lib.hipstr_filtered_reads_counts(self.h, ptr(c, c_i32p))
+        return dict(zip(self.COUNTS, map(int, c)))
+
+    def view(self):
+        """FilteredView (pointers owned by this object, valid until the next view() / close())."""
+        v = FilteredView()
+        st = self.lib.hipstr_filtered_reads_view(self.h, C.byref(v))
+        if st != 0:
+            raise HipstrError(st, "filtered_reads_view")
+        return v
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hipstr_filtered_reads_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
 class VcfLoci(C.Structure):
     """hipstr_vcf_loci_t"""
     _fields_ = [("chrom", C.POINTER(C.c_char_p)), ("name", C.POINTER(C.c_char_p)), ("region_start", c_i32p),
@@ -369,6 +499,41 @@ def load():
     lib.hipstr_trace_seconds.argtypes = [vp, c_f64p]
     lib.hipstr_last_traffic.restype = None
     lib.hipstr_last_traffic.argtypes = [vp, c_i64p, c_i64p, c_i32p]
+    cpp = C.POINTER(C.c_char_p)
+    lib.hipstr_ingest_last_error.restype = C.c_char_p
+    lib.hipstr_bam_reader_open.restype = C.c_int32
+    lib.hipstr_bam_reader_open.argtypes = [C.c_int32, cpp, C.POINTER(vp)]
+    lib.hipstr_bam_reader_close.restype = None
+    lib.hipstr_bam_reader_close.argtypes = [vp]
+    lib.hipstr_bam_reader_read_groups.restype = C.c_int64
+    lib.hipstr_bam_reader_read_groups.argtypes = [vp, C.c_int64, C.c_char_p]
+    lib.hipstr_bam_reader_fetch.restype = C.c_int32
+    lib.hipstr_bam_reader_fetch.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.hipstr_bam_records_count.restype = C.c_int32
+    lib.hipstr_bam_records_count.argtypes = [vp]
+    lib.hipstr_bam_records_text.restype = C.c_int64
+    lib.hipstr_bam_records_text.argtypes = [vp, C.c_int64, C.c_char_p]
+    lib.hipstr_bam_records_free.restype = None
+    lib.hipstr_bam_records_free.argtypes = [vp]
+    lib.hipstr_filter_default_options.restype = None
+    lib.hipstr_filter_default_options.argtypes = [C.POINTER(FilterOptions)]
+    lib.hipstr_filter_reads.restype = C.c_int32
+    lib.hipstr_filter_reads.argtypes = [vp, C.c_char_p, C.c_int32, c_i32p, c_i32p, C.POINTER(FilterOptions), C.c_int32, cpp, cpp, cpp,
+                                        C.POINTER(vp)]
+    lib.hipstr_filtered_reads_counts.restype = None
+    lib.hipstr_filtered_reads_counts.argtypes = [vp, c_i32p]
+    lib.hipstr_filtered_reads_text.restype = C.c_int64
+    lib.hipstr_filtered_reads_text.argtypes = [vp, C.c_int64, C.c_char_p]
+    lib.hipstr_filtered_reads_view.restype = C.c_int32
+    lib.hipstr_filtered_reads_view.argtypes = [vp, C.POINTER(FilteredView)]
+    lib.hipstr_filtered_reads_free.restype = None
+    lib.hipstr_filtered_reads_free.argtypes = [vp]
+    lib.hipstr_trim_one.restype = C.c_int32
+    lib.hipstr_trim_one.argtypes = [C.c_int32] * 6 + [C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, c_i32p, c_i32p, C.c_char_p,
+                                    C.c_char_p, c_i32p, C.c_char_p, c_i32p]
+    lib.hipstr_alignment_filters.restype = C.c_int32
+    lib.hipstr_alignment_filters.argtypes = [C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, c_i32p, C.c_char_p,
+                                             C.c_int32, c_i32p, c_f64p]
     lib.hipstr_snp_phasing_batch_host.restype = C.c_int32
     lib.hipstr_snp_phasing_batch_host.argtypes = [vp, C.POINTER(SnpPhasingStruct), c_f64p, c_f64p, c_i32p]
     lib.hipstr_nw_align_batch_host.restype = C.c_int32
@@ -926,6 +1091,12 @@ class Context:
         if getattr(self, "h", None):
             self.lib.hipstr_destroy(self.h)
             self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
     def __del__(self):
         try:

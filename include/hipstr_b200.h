@@ -631,6 +631,83 @@ typedef struct {
 hipstr_status_t hipstr_snp_phasing_batch_host(hipstr_ctx_t* ctx, const hipstr_snp_phasing_t* batch, double* log_p1,
                                               double* log_p2, int32_t* counts);
 
+/* --- section 8(f) row 4, second slice: BAM ingestion and read filtering (host) ---
+ * Everything between the BAM files and SNPBamProcessor::process_reads for ONE region (BamProcessor::process_regions,
+ * src/bam_processor.cpp:551-607), on opaque handles:
+ *   hipstr_bam_reader_*   BamCramMultiReader(paths, "", ORDER_ALNS_BY_FILE) + SetRegion + GetNextAlignment
+ *                         (src/bam_io.{h,cpp}) for BAM files with a .bai index (BGZF, BAM and the index are decoded by
+ *                         hipstr_b200/host/bam_reader.cpp; CRAM is out of scope)
+ *   hipstr_filter_reads   BamProcessor::read_and_filter_reads (:173-474): quality trimming, adapter trimming, the N /
+ *                         base-quality / end-match / indel-distance filters, mate pairing with the unique-mapping rules
+ *                         (XA / SA / AS / XS tags), grouping by sample; then remove_pcr_duplicates
+ *                         (src/pcr_duplicates.cpp) when options.remove_pcr_dups
+ *   hipstr_filtered_reads_view   the kept reads as the flat arrays K7 takes (entries in the order of
+ *                         SNPBamProcessor::process_reads: per sample the paired STR reads, each followed by its mate,
+ *                         then the unpaired ones); entry_snp_set holds the sample index.
+ * The *_text functions print one line per alignment (for inspection and for the parity tests); they return the text
+ * length, or -(needed capacity) when cap is too small.  Errors the reference dies on return HIPSTR_ERR_BAD_ARG with
+ * the message in hipstr_ingest_last_error() (thread-local). */
+typedef struct hipstr_bam_reader hipstr_bam_reader_t;
+typedef struct hipstr_bam_records hipstr_bam_records_t;
+typedef struct hipstr_filtered_reads hipstr_filtered_reads_t;
+typedef struct {                       /* BamProcessor's public knobs (src/bam_processor.h:78-101, 164-177) */
+  int32_t max_mate_dist;               /* MAX_MATE_DIST            1000 */
+  int32_t min_bp_before_indel;         /* MIN_BP_BEFORE_INDEL      7 */
+  int32_t min_flank;                   /* MIN_FLANK                5 */
+  int32_t min_read_end_match;          /* MIN_READ_END_MATCH       10 */
+  int32_t maximal_end_match_window;    /* MAXIMAL_END_MATCH_WINDOW 15 */
+  int32_t require_paired_reads;        /* REQUIRE_PAIRED_READS     1 */
+  double  min_sum_qual_log_prob;       /* MIN_SUM_QUAL_LOG_PROB    -10 */
+  int32_t max_total_reads;             /* MAX_TOTAL_READS          1000000 */
+  int32_t base_qual_trim;              /* BASE_QUAL_TRIM           '5' (character code) */
+  int32_t remove_pcr_dups;             /* REMOVE_PCR_DUPS          1 */
+  int32_t trim_adapters;               /* AdapterTrimmer on (TruSeq + Nextera), 1 */
+} hipstr_filter_options_t;
+typedef struct {
+  int32_t n_samples;
+  const char* const* sample_names;     /* rg_names, in order of appearance */
+  const int32_t* sample_entry_off;     /* [n_samples+1] entries of sample s */
+  const char* entry_passes;            /* [n_entries] '1' if the STR read may be used to generate haplotypes (PF tag, first region) */
+  const int32_t* aln_flag;             /* [n_alns] BAM FLAG */
+  hipstr_snp_phasing_t reads;          /* SNP arrays left NULL / 0: the caller attaches its SNP sets */
+} hipstr_filtered_view_t;
+const char* hipstr_ingest_last_error(void);
+hipstr_status_t hipstr_bam_reader_open(int32_t n_files, const char* const* paths, hipstr_bam_reader_t** out);
+void hipstr_bam_reader_close(hipstr_bam_reader_t* reader);
+/* "@RG" lines of every file (BamHeader::parse_read_groups): path, ID, SM, LB per line, "-" when a tag is absent */
+int64_t hipstr_bam_reader_read_groups(const hipstr_bam_reader_t* reader, int64_t cap, char* out_text);
+/* the alignments overlapping [start, end) of `chrom`, file after file */
+hipstr_status_t hipstr_bam_reader_fetch(hipstr_bam_reader_t* reader, const char* chrom, int32_t start, int32_t end,
+                                        hipstr_bam_records_t** out);
+int32_t hipstr_bam_records_count(const hipstr_bam_records_t* records);
+int64_t hipstr_bam_records_text(const hipstr_bam_records_t* records, int64_t cap, char* out_text);
+void hipstr_bam_records_free(hipstr_bam_records_t* records);
+void hipstr_filter_default_options(hipstr_filter_options_t* options);
+/* records: hipstr_bam_reader_fetch(chrom, region start - max_mate_dist (>= 0), region stop + max_mate_dist);
+ * rg_keys[i] = file path + read group ID -> rg_samples[i] / rg_libraries[i] (what main builds from the headers) */
+hipstr_status_t hipstr_filter_reads(const hipstr_bam_records_t* records, const char* chrom_seq, int32_t n_regions,
+                                    const int32_t* region_start, const int32_t* region_stop,
+                                    const hipstr_filter_options_t* options, int32_t n_rg, const char* const* rg_keys,
+                                    const char* const* rg_samples, const char* const* rg_libraries,
+                                    hipstr_filtered_reads_t** out);
+/* counts9: reads overlapping the region, hard clipped, with an N, with low base qualities, without a unique mapping,
+ * without a mate, sets of PCR duplicates removed, TOO_MANY_READS, reads that passed */
+void hipstr_filtered_reads_counts(const hipstr_filtered_reads_t* reads, int32_t* counts9);
+int64_t hipstr_filtered_reads_text(const hipstr_filtered_reads_t* reads, int64_t cap, char* out_text);
+hipstr_status_t hipstr_filtered_reads_view(hipstr_filtered_reads_t* reads, hipstr_filtered_view_t* view);
+void hipstr_filtered_reads_free(hipstr_filtered_reads_t* reads);
+/* One alignment through one step, for checking without files: what = 0 BamAlignment::TrimLowQualityEnds((char)arg),
+ * 1 AdapterTrimmer::trim_adapters (flag decides the mate / strand), 2 TrimNumBases(arg, arg2).  out_pos = {Position(),
+ * GetEndPosition(), Length()}.  Returns 0, or -1 where the reference would have died. */
+int32_t hipstr_trim_one(int32_t what, int32_t arg, int32_t arg2, int32_t flag, int32_t pos, int32_t end_pos, const char* bases,
+                        const char* quals, int32_t n_cigar, const char* cigar_type, const int32_t* cigar_len, int32_t* out_pos,
+                        char* out_seq, char* out_qual, int32_t* n_out_cigar, char* out_ctype, int32_t* out_clen);
+/* out = {HasLargestEndMatches(aln, chrom_seq, 0, window, window), GetNumEndMatches first, second, GetEndDistToIndel first,
+ * second} (src/alignment_filters.cpp), sum_qual = BaseQuality::sum_log_prob_correct(Qualities()) */
+int32_t hipstr_alignment_filters(int32_t pos, int32_t end_pos, const char* bases, const char* quals, int32_t n_cigar,
+                                 const char* cigar_type, const int32_t* cigar_len, const char* chrom_seq, int32_t window,
+                                 int32_t* out, double* sum_qual);
+
 /* Wall-clock seconds this context has spent inside hipstr_trace_batch_host, by part:
  * {host lowering of the batch, ordering + uploads, kernel K5, downloads of the results} */
 void hipstr_trace_seconds(const hipstr_ctx_t* ctx, double* seconds4);
