@@ -975,12 +975,20 @@ hipstr_status_t hipstr_snp_phasing_batch_host(hipstr_ctx_t* ctx, const hipstr_sn
   p.out_log_p1 = (double*)o[0].p; p.out_log_p2 = (double*)o[1].p; p.out_counts = (int32_t*)o[2].p;
   int n_sm = 148;
   CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+  cudaEvent_t t0 = nullptr, t1 = nullptr;   // kernel time on the launching stream, read by hipstr_last_kernel_ms
+  if (ctx->timing) { CU(cudaEventCreate(&t0)); CU(cudaEventCreate(&t1)); CU(cudaEventRecord(t0, s)); }
   CU(launch_snp_phase(p, n_sm, s));
+  if (ctx->timing) CU(cudaEventRecord(t1, s));
   ctx->last_launches = 1;
   CU(get(ctx, log_p1, p.out_log_p1, E));
   CU(get(ctx, log_p2, p.out_log_p2, E));
   CU(get(ctx, counts, p.out_counts, E * 4));
   CU(cudaStreamSynchronize(s));
+  if (ctx->timing) {
+    CU(cudaEventElapsedTime(&ctx->last_ms, t0, t1));
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+  }
   end_call(ctx);
   for (size_t e = 0; e < E; e++)
     if (counts[4 * e + 3] != 0) return fail(ctx, HIPSTR_ERR_BAD_ARG, "an alignment's CIGAR is invalid or inconsistent with its bases");

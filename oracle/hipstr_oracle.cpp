@@ -1253,8 +1253,10 @@ extern "C" int32_t oracle_snp_phasing(const hipstr_snp_phasing_t* b, double* log
     const int set = b->entry_snp_set[e];
     for (int a = b->entry_aln_off[e]; set >= 0 && a < b->entry_aln_off[e + 1]; a++) {
       std::vector<int> snps;   // findContained(Position(), GetEndPosition() - 1)
-      for (int i = b->set_off[set]; i < b->set_off[set + 1]; i++)
-        if (b->snp_pos[i] >= (uint32_t)b->aln_pos[a] && b->snp_pos[i] <= (uint32_t)(b->aln_end[a] - 1)) snps.push_back(i);
+      const uint32_t* lo = b->snp_pos + b->set_off[set];
+      const uint32_t* hi = b->snp_pos + b->set_off[set + 1];
+      for (const uint32_t* it = std::lower_bound(lo, hi, (uint32_t)b->aln_pos[a]); it != hi && *it <= (uint32_t)(b->aln_end[a] - 1); ++it)
+        snps.push_back((int)(it - b->snp_pos));
       if (snps.empty()) continue;
       const char* seq = b->bases + b->aln_seq_off[a];
       const char* qual = b->quals + b->aln_seq_off[a];
