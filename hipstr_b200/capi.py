@@ -71,7 +71,7 @@ class LocusReadsStruct(C.Structure):
     _fields_ = [("locus_read_off", c_i32p), ("locus_sample_off", c_i32p), ("read_seq_off", c_i32p), ("bases", C.c_void_p),
                 ("quals", C.c_void_p), ("read_start", c_i32p), ("cigar_off", c_i32p), ("cigar_type", C.c_void_p),
                 ("cigar_len", c_i32p), ("sample_label", c_i32p), ("name_id", c_i32p), ("log_p1", c_f64p), ("log_p2", c_f64p),
-                ("haploid", c_u8p), ("rev_strand", c_u8p), ("read_stop", c_i32p)]
+                ("haploid", c_u8p), ("rev_strand", c_u8p), ("read_stop", c_i32p), ("use_for_haps", c_u8p)]
 
 
 class SnpPhasingStruct(C.Structure):
@@ -721,7 +721,8 @@ def blocks_batch(loci_blocks, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01)):
     return b, np.array(starts, np.int32), np.array(ends, np.int32)
 
 
-def make_locus_reads(locus_read_off, locus_sample_off, reads, sample_label, name_id, log_p1, log_p2, haploid, rev_strand=None):
+def make_locus_reads(locus_read_off, locus_sample_off, reads, sample_label, name_id, log_p1, log_p2, haploid, rev_strand=None,
+                     use_for_haps=None):
     """hipstr_locus_reads_t from Python lists: reads = [(start, stop, bases, quals, [(op, len)])] over all loci."""
     so, co = [0], [0]
     bases, quals, ctype, clen = bytearray(), bytearray(), bytearray(), []
@@ -741,11 +742,13 @@ def make_locus_reads(locus_read_off, locus_sample_off, reads, sample_label, name
                 label=np.ascontiguousarray(sample_label, np.int32), name=np.ascontiguousarray(name_id, np.int32),
                 p1=np.ascontiguousarray(log_p1, np.float64), p2=np.ascontiguousarray(log_p2, np.float64),
                 hap=np.ascontiguousarray(haploid, np.uint8),
-                rev=np.ascontiguousarray(rev_strand if rev_strand is not None else np.zeros(len(reads)), np.uint8))
+                rev=np.ascontiguousarray(rev_strand if rev_strand is not None else np.zeros(len(reads)), np.uint8),
+                use=None if use_for_haps is None else np.ascontiguousarray(use_for_haps, np.uint8))
     rs = LocusReadsStruct(ptr(keep["lro"], c_i32p), ptr(keep["lso"], c_i32p), ptr(keep["so"], c_i32p), keep["bases"].ctypes.data,
                           keep["quals"].ctypes.data, ptr(keep["start"], c_i32p), ptr(keep["co"], c_i32p), keep["ctype"].ctypes.data,
                           ptr(keep["clen"], c_i32p), ptr(keep["label"], c_i32p), ptr(keep["name"], c_i32p), ptr(keep["p1"], c_f64p),
-                          ptr(keep["p2"], c_f64p), ptr(keep["hap"], c_u8p), ptr(keep["rev"], c_u8p), ptr(keep["stop"], c_i32p))
+                          ptr(keep["p2"], c_f64p), ptr(keep["hap"], c_u8p), ptr(keep["rev"], c_u8p), ptr(keep["stop"], c_i32p),
+                          ptr(keep["use"], c_u8p))
     rs._keep = keep
     return rs
 
@@ -832,13 +835,16 @@ class Genotyper:
                                 v.log_p1, v.log_p2, v.haploid, v.read_rev_strand, v.read_stop)
 
     @classmethod
-    def from_synth_reads(cls, ctx, synth, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01), loci_range=None):
+    def from_synth_reads(cls, ctx, synth, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01), loci_range=None, use_for_haps=None):
         """The full seam-B1 constructor: haplotype blocks are generated from the reads (hipstr_genotyper_create_from_reads).
         loci_range = (first, end) restricts the batch to a window of the Synth's loci."""
         v = synth.view
         l0, l1 = loci_range if loci_range else (0, synth.n_loci)
         L = l1 - l0
         rs = cls._reads_struct(synth)
+        if use_for_haps is not None:   # [total reads] 0/1: which reads may propose candidate alleles
+            use_for_haps = np.ascontiguousarray(use_for_haps, np.uint8)
+            rs.use_for_haps = ptr(use_for_haps, c_u8p)
         if l0:   # the per-locus arrays start at the window; read-level arrays stay absolute
             step = C.sizeof(C.c_int32) * l0
             rs.locus_read_off = C.cast(C.cast(v.locus_read_off, C.c_void_p).value + step, c_i32p)
@@ -854,7 +860,7 @@ class Genotyper:
         st6 = np.tile(np.asarray(stutter, np.float64), L)
         g = cls.__new__(cls)
         g.lib, g.ctx, g.n_loci = load(), ctx, L
-        g._keep = (rs, chroms, carr, start, stop, period, st6)
+        g._keep = (rs, chroms, carr, start, stop, period, st6, use_for_haps)
         g._synth = synth
         h = C.c_void_p()
         st = g.lib.hipstr_genotyper_create_from_reads(ctx.h if ctx else None, L, ptr(start, c_i32p), ptr(stop, c_i32p),

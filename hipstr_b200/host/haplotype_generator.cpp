@@ -156,7 +156,11 @@ bool HaplotypeGenerator::add_haplotype_block(int32_t reg_start, int32_t reg_stop
     for (const ReadView& a : sample) { min_start = std::min(min_start, a.start); max_stop = std::max(max_stop, a.stop); }
   int32_t region_start = reg_start - kLeftPad, region_end = reg_stop + kRightPad;
   const std::string ref_seq = upper(chrom_seq.substr(region_start, region_end - region_start));
-  if (min_start == INT_MAX || min_start + 5 >= region_start || max_stop - 5 <= region_end) {   // (no reads at all: no span)
+  // With no alignment at all (every read of the locus failed the haplotype-generation filters) the reference's bounds stay
+  // INT_MAX / INT_MIN and its "+ 5" / "- 5" wrap around, so the test passes and the block is built from the reference
+  // allele alone; the wrap-around is reproduced here with unsigned arithmetic.
+  const int32_t lo = (int32_t)((uint32_t)min_start + 5u), hi = (int32_t)((uint32_t)max_stop - 5u);
+  if (lo >= region_start || hi <= region_end) {
     failure_msg_ = "No spanning alignments";
     return false;
   }

@@ -168,7 +168,7 @@ struct hipstr_left_aligned {
       source;
   std::vector<char> bases, quals, cigar_type;
   std::vector<double> log_p1, log_p2;
-  std::vector<uint8_t> haploid, rev_strand;
+  std::vector<uint8_t> haploid, rev_strand, use_for_haps;
   int64_t fail_count = 0, nw_alignments = 0;
 };
 
@@ -292,6 +292,7 @@ hipstr_status_t hipstr_left_align_reads_host(hipstr_ctx_t* ctx, int32_t n_loci, 
       H->log_p1.push_back(raw->log_p1[r]);
       H->log_p2.push_back(raw->log_p2[r]);
       H->rev_strand.push_back(raw->rev_strand ? raw->rev_strand[r] : 0);
+      H->use_for_haps.push_back(raw->use_for_haps ? raw->use_for_haps[r] : 1);
       H->source.push_back(r);
     }
     H->locus_read_off.push_back((int32_t)H->read_start.size());
@@ -314,6 +315,7 @@ hipstr_status_t hipstr_left_align_reads_host(hipstr_ctx_t* ctx, int32_t n_loci, 
   v.haploid = H->haploid.data();
   v.rev_strand = H->rev_strand.data();
   v.read_stop = H->read_stop.data();
+  v.use_for_haps = H->use_for_haps.data();
   *out_handle = H;
   return HIPSTR_OK;
 }

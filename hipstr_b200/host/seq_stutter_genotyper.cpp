@@ -874,7 +874,7 @@ hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_
       }
       min_start = std::min(min_start, v.start);
       max_stop = std::max(max_stop, v.stop);
-      by_sample[rd->sample_label[r]].push_back(v);
+      if (!rd->use_for_haps || rd->use_for_haps[r]) by_sample[rd->sample_label[r]].push_back(v);
     }
     g.log_ += "Generating candidate haplotypes\n";
     const std::string chrom(chrom_seq[l]);

@@ -406,6 +406,10 @@ typedef struct hipstr_locus_reads {
   const int32_t* read_stop;         /* [R] Alignment::get_stop(): HipSTR keeps the LAST aligned reference position
                                        (inclusive; AlignmentOps.cpp:56-57,106).  NULL = derived from the CIGAR as
                                        read_start + reference bases consumed - 1                              */
+  const uint8_t* use_for_haps;      /* [R] Alignment::use_for_hap_generation(0) (AlignmentData.h:116-128; set from the
+                                       "PF" tag of the read filters, genotyper_bam_processor.cpp:91-94): only these
+                                       reads propose candidate alleles in build_haplotype (seq_stutter_genotyper.cpp:
+                                       438-442); every read is still aligned and genotyped.  NULL = all reads   */
 } hipstr_locus_reads_t;
 
 typedef struct hipstr_genotyper hipstr_genotyper_t;

@@ -73,7 +73,7 @@ void* ref_sg_create(int32_t n_samples, int32_t n_reads, const int32_t* sample_la
                     const int32_t* cigar_off, const char* cigar_type, const int32_t* cigar_len, const double* log_p1,
                     const double* log_p2, const char* chrom_seq, int32_t region_start, int32_t region_stop,
                     int32_t period, const double* stutter, int32_t haploid, int32_t reassemble_flanks,
-                    const uint8_t* rev_strand) {
+                    const uint8_t* rev_strand, const uint8_t* use_for_haps) {
   ensure_init();
   RefSG* h = new RefSG();
   h->chrom_seq = chrom_seq;
@@ -98,7 +98,7 @@ void* ref_sg_create(int32_t n_samples, int32_t n_reads, const int32_t* sample_la
     }
     Alignment a(read_start[r], read_stop ? read_stop[r] : pos - 1, rev_strand != NULL && rev_strand[r] != 0, "r" + std::to_string(name_id[r]), q, seq, gapped);
     a.set_cigar_list(cig);
-    a.set_hap_gen_info(std::vector<bool>(1, true));
+    a.set_hap_gen_info(std::vector<bool>(1, use_for_haps == NULL || use_for_haps[r] != 0));
     alns.push_back(a);
     p1[sample_label[r]].push_back(log_p1[r]);
     p2[sample_label[r]].push_back(log_p2[r]);

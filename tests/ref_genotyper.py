@@ -16,7 +16,7 @@ def bind(lib):
     lib.ref_sg_create.restype = C.c_void_p
     lib.ref_sg_create.argtypes = [C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_void_p, c_i32p,
                                   C.c_void_p, c_i32p, c_f64p, c_f64p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32,
-                                  c_f64p, C.c_int32, C.c_int32, c_u8p]
+                                  c_f64p, C.c_int32, C.c_int32, c_u8p, c_u8p]
     lib.ref_sg_set_output_flags.restype = None
     lib.ref_sg_set_output_flags.argtypes = [c_i32p, C.c_double]
     for name in ("destroy",):
@@ -87,7 +87,8 @@ class LocusReads:
 class ReadsOfLocus:
     """LocusReads built from Python tuples [(start, stop, bases, quals, [(op, len)])] (e.g. left-aligned reads)."""
 
-    def __init__(self, reads, n_samples, sample_label, name_id, log_p1, log_p2, chrom_seq, region, period, haploid=0, rev_strand=None):
+    def __init__(self, reads, n_samples, sample_label, name_id, log_p1, log_p2, chrom_seq, region, period, haploid=0, rev_strand=None,
+                 use_for_haps=None):
         self.n_reads, self.n_samples = len(reads), n_samples
         so, co, bases, quals, ctype, clen = [0], [0], bytearray(), bytearray(), bytearray(), []
         for start, stop, b, q, cig in reads:
@@ -110,6 +111,7 @@ class ReadsOfLocus:
         self.log_p1, self.log_p2 = np.ascontiguousarray(log_p1, np.float64), np.ascontiguousarray(log_p2, np.float64)
         self.rev_strand = np.ascontiguousarray(rev_strand if rev_strand is not None else np.zeros(len(reads)), np.uint8)
         self.chrom_seq, self.region, self.period, self.haploid = chrom_seq, region, period, haploid
+        self.use_for_haps = None if use_for_haps is None else np.ascontiguousarray(use_for_haps, np.uint8)
 
 
 class RefGenotyper:
@@ -124,7 +126,8 @@ class RefGenotyper:
             ptr(reads.start, c_i32p), ptr(reads.stop, c_i32p), ptr(reads.seq_off, c_i32p), reads.bases.ctypes.data, reads.quals.ctypes.data,
             ptr(reads.cigar_off, c_i32p), reads.cigar_type.ctypes.data, ptr(reads.cigar_len, c_i32p),
             ptr(reads.log_p1, c_f64p), ptr(reads.log_p2, c_f64p), reads.chrom_seq, reads.region[0], reads.region[1],
-            reads.period, ptr(st, c_f64p), reads.haploid, int(reassemble_flanks), ptr(reads.rev_strand, c_u8p))
+            reads.period, ptr(st, c_f64p), reads.haploid, int(reassemble_flanks), ptr(reads.rev_strand, c_u8p),
+            ptr(getattr(reads, "use_for_haps", None), c_u8p))
         self.initialized = bool(self.lib.ref_sg_initialized(self.h))
 
     def blocks(self):

@@ -119,6 +119,38 @@ def test_constructor_matches_reference(kw):
     g.close()
 
 
+def _hap_flags(s, seed, keep=0.5):
+    """Random Alignment::use_for_hap_generation flags (what the read filters' PF tag becomes), per read of the Synth."""
+    return (np.random.default_rng(seed).random(int(s.locus_read_off[-1])) < keep).astype(np.uint8)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,keep", [(3, 0.5), (4, 0.15), (5, 0.0)])
+def test_constructor_uses_only_flagged_reads_for_haplotypes(seed, keep):
+    """Reads that failed the second set of read filters (PF tag '0') are genotyped but may not propose alleles
+    (seq_stutter_genotyper.cpp:438-442)."""
+    from hipstr_b200.capi import Genotyper
+    from ref_genotyper import LocusReads, RefGenotyper
+    s = Synth(n_loci=6, n_samples=6, reads_per_sample=10, n_alleles=6, read_len=110, seed=60 + seed, stutter_rate=0.2)
+    flags = _hap_flags(s, seed, keep)
+    g = Genotyper.from_synth_reads(None, s, use_for_haps=flags)
+    everything = Genotyper.from_synth_reads(None, s)
+    differs = 0
+    for l in range(s.n_loci):
+        reads = LocusReads(s, l)
+        reads.use_for_haps = flags[int(s.locus_read_off[l]):int(s.locus_read_off[l + 1])].copy()
+        r = RefGenotyper(reads)
+        if not r.initialized:
+            assert g.info(l)["blocks"] == 0, l
+            continue
+        assert g.blocks(l) == [b[3] for b in r.blocks()], l
+        assert g.info(l)["pools"] == r.lib.ref_sg_num_pools(r.h)
+        differs += g.blocks(l) != everything.blocks(l)
+    assert differs > 0 or keep == 0.0      # without any flagged read the reference gives up on the locus
+    g.close()
+    everything.close()
+
+
 # ---- the full loop on the GPU ---------------------------------------------------------------------------
 LOOP_CASES = [
     ("plain", dict(n_loci=3, n_samples=10, reads_per_sample=20, n_alleles=6, read_len=100, seed=5)),
@@ -144,6 +176,12 @@ LOOP_CASES = [
                               assemble=True)),
     ("assembly_stutter_and_flanks", dict(n_loci=4, n_samples=6, reads_per_sample=25, n_alleles=3, read_len=110, seed=101,
                                          stutter_rate=0.3, flank_snp_freq=0.25, assemble=True)),
+    # only part of the reads may propose candidate alleles (Alignment::use_for_hap_generation, set from the read filters):
+    # alleles seen only in unflagged reads come back through the stutter-allele rounds, or not at all
+    ("haplotypes_from_flagged_reads", dict(n_loci=5, n_samples=6, reads_per_sample=14, n_alleles=6, read_len=110, seed=141, stutter_rate=0.2,
+                                           hap_keep=0.3, assemble=True)),
+    ("haplotypes_from_no_reads", dict(n_loci=3, n_samples=5, reads_per_sample=12, n_alleles=4, read_len=110, seed=151, stutter_rate=0.2,
+                                      hap_keep=0.0)),
 ]
 
 
@@ -155,16 +193,21 @@ def test_genotype_loop_matches_reference(name, kw):
     from ref_genotyper import LocusReads, RefGenotyper
     kw = dict(kw)
     assemble, min_flank_freq = kw.pop("assemble", False), kw.pop("min_flank_freq", 0.01)
+    hap_keep = kw.pop("hap_keep", None)     # fraction of reads flagged for haplotype generation (the read filters' PF tag)
     s = Synth(**kw)
+    flags = None if hap_keep is None else _hap_flags(s, kw["seed"], hap_keep)
     refs, blocks0 = [], []
     for l in range(s.n_loci):
-        r = RefGenotyper(LocusReads(s, l), reassemble_flanks=assemble)
+        reads = LocusReads(s, l)
+        if flags is not None:
+            reads.use_for_haps = flags[int(s.locus_read_off[l]):int(s.locus_read_off[l + 1])].copy()
+        r = RefGenotyper(reads, reassemble_flanks=assemble)
         assert r.initialized
         refs.append(r)
         blocks0.append(r.blocks())     # the reference's own HaplotypeGenerator output is the common starting point
     ctx = Context(0)
     # odd cases start from the reference's blocks, even ones run the product's own haplotype generation too
-    g = Genotyper.from_synth(ctx, s, blocks0) if len(name) % 2 else Genotyper.from_synth_reads(ctx, s)
+    g = Genotyper.from_synth(ctx, s, blocks0) if len(name) % 2 and flags is None else Genotyper.from_synth_reads(ctx, s, use_for_haps=flags)
     ok = g.genotype(1000, 4, min_flank_freq, assemble)
     stats = g.stats()
     changed = rounds = 0
