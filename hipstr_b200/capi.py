@@ -140,7 +140,8 @@ class FilterOptions(C.Structure):
 class FilteredView(C.Structure):
     """hipstr_filtered_view_t"""
     _fields_ = [("n_samples", C.c_int32), ("sample_names", C.POINTER(C.c_char_p)), ("sample_entry_off", c_i32p),
-                ("entry_passes", C.c_void_p), ("aln_flag", c_i32p), ("reads", SnpPhasingStruct)]
+                ("entry_passes", C.c_void_p), ("aln_flag", c_i32p), ("entry_name_off", c_i32p), ("entry_names", C.c_void_p),
+                ("reads", SnpPhasingStruct)]
 
 
 def _text(fn, h):
@@ -250,6 +251,14 @@ class FilteredReads:
         if st != 0:
             raise HipstrError(st, "filtered_reads_view")
         return v
+
+    def entry_names(self):
+        """Read names of the STR reads, in entry order."""
+        v = self.view()
+        n = v.reads.n_entries
+        off = np.ctypeslib.as_array(v.entry_name_off, shape=(n + 1,))
+        blob = C.string_at(v.entry_names, int(off[-1])).decode("latin-1")
+        return [blob[off[i]:off[i + 1]] for i in range(n)]
 
     def close(self):
         if getattr(self, "h", None):
@@ -877,7 +886,9 @@ class Genotyper:
         chroms = [c if isinstance(c, bytes) else c.encode() for c in chrom_seqs]
         carr = (C.c_char_p * n_loci)(*chroms)
         start, stop, per = (np.ascontiguousarray(a, np.int32) for a in (region_start, region_stop, period))
-        st6 = np.tile(np.asarray(stutter, np.float64), n_loci)
+        st6 = np.asarray(stutter, np.float64)     # one model for every locus, or [n_loci][6]
+        st6 = np.tile(st6, n_loci) if st6.ndim == 1 else np.ascontiguousarray(st6.reshape(-1))
+        assert st6.size == 6 * n_loci
         g = cls.__new__(cls)
         g.lib, g.ctx, g.n_loci = load(), ctx, n_loci
         g._keep = (reads_struct, chroms, carr, start, stop, per, st6)

@@ -25,8 +25,9 @@ struct hipstr_filtered_reads {
   hipstr::FilteredReads reads;
   std::string adapter_stats;
   // flat view (hipstr_filtered_reads_view)
-  std::vector<int32_t> sample_entry_off, entry_aln_off, entry_snp_set, aln_pos, aln_end, aln_seq_off, aln_cigar_off, cigar_len, aln_flag;
-  std::string bases, quals, cigar_type, passes;
+  std::vector<int32_t> sample_entry_off, entry_aln_off, entry_snp_set, aln_pos, aln_end, aln_seq_off, aln_cigar_off, cigar_len, aln_flag,
+      entry_name_off;
+  std::string bases, quals, cigar_type, passes, entry_names;
   std::vector<const char*> sample_names;
 };
 
@@ -206,6 +207,7 @@ hipstr_status_t hipstr_filtered_reads_view(hipstr_filtered_reads_t* h, hipstr_fi
   h->sample_entry_off.assign(1, 0); h->entry_aln_off.assign(1, 0); h->aln_seq_off.assign(1, 0); h->aln_cigar_off.assign(1, 0);
   h->entry_snp_set.clear(); h->aln_pos.clear(); h->aln_end.clear(); h->cigar_len.clear(); h->aln_flag.clear();
   h->bases.clear(); h->quals.clear(); h->cigar_type.clear(); h->passes.clear(); h->sample_names.clear();
+  h->entry_names.clear(); h->entry_name_off.assign(1, 0);
   auto add = [&](const BamRecord& a) {
     h->aln_pos.push_back(a.pos);
     h->aln_end.push_back(a.end_pos);
@@ -216,8 +218,6 @@ hipstr_status_t hipstr_filtered_reads_view(hipstr_filtered_reads_t* h, hipstr_fi
     for (const auto& op : a.cigar) { h->cigar_type += op.first; h->cigar_len.push_back(op.second); }
     h->aln_cigar_off.push_back((int32_t)h->cigar_type.size());
   };
-  const size_t n_regions = r.paired.empty() ? 1 : 1;
-  (void)n_regions;
   for (size_t g = 0; g < r.rg_names.size(); g++) {
     h->sample_names.push_back(r.rg_names[g].c_str());
     // the order of SNPBamProcessor::process_reads: paired STR reads (each with its mate), then the unpaired ones
@@ -227,12 +227,16 @@ hipstr_status_t hipstr_filtered_reads_view(hipstr_filtered_reads_t* h, hipstr_fi
       h->entry_aln_off.push_back((int32_t)h->aln_pos.size());
       h->entry_snp_set.push_back((int32_t)g);
       h->passes += r.paired[g][i].passes.empty() ? '0' : r.paired[g][i].passes[0];
+      h->entry_names += r.paired[g][i].name;
+      h->entry_name_off.push_back((int32_t)h->entry_names.size());
     }
     for (size_t i = 0; i < r.unpaired[g].size(); i++) {
       add(r.unpaired[g][i]);
       h->entry_aln_off.push_back((int32_t)h->aln_pos.size());
       h->entry_snp_set.push_back((int32_t)g);
       h->passes += r.unpaired[g][i].passes.empty() ? '0' : r.unpaired[g][i].passes[0];
+      h->entry_names += r.unpaired[g][i].name;
+      h->entry_name_off.push_back((int32_t)h->entry_names.size());
     }
     h->sample_entry_off.push_back((int32_t)h->entry_snp_set.size());
   }
@@ -242,6 +246,8 @@ hipstr_status_t hipstr_filtered_reads_view(hipstr_filtered_reads_t* h, hipstr_fi
   v->sample_entry_off = h->sample_entry_off.data();
   v->entry_passes = h->passes.c_str();
   v->aln_flag = h->aln_flag.data();
+  v->entry_name_off = h->entry_name_off.data();
+  v->entry_names = h->entry_names.c_str();
   hipstr_snp_phasing_t& b = v->reads;
   std::memset(&b, 0, sizeof(b));
   b.n_entries = (int32_t)h->entry_snp_set.size();

@@ -1,0 +1,211 @@
+"""From BAM files to VCF records, a window of regions at a time: the stages of the reference's per-region driver
+(BamProcessor::process_regions, src/bam_processor.cpp:521-617 -> SNPBamProcessor::process_reads, src/snp_bam_processor.cpp:36-118 ->
+GenotyperBamProcessor::analyze_reads_and_phasing, src/genotyper_bam_processor.cpp:160-289) chained over the C-ABI:
+
+    per region   hipstr_bam_reader_fetch -> hipstr_filter_reads (+ PCR duplicates)                      host
+    per window   [hipstr_extract_cigar + hipstr_em_train_host (K4) when no default stutter model]        one launch
+                 hipstr_left_align_reads_host (K6)                                                      one launch per NW round
+                 hipstr_genotyper_create_from_reads -> genotype (K1 K2 K3 K5 in lockstep rounds) -> write_vcf (K3b K5)
+
+This module is the orchestration a caller writes; every stage is a call into libhipstr_b200.so.  Without a phased SNP VCF the
+phasing log-likelihoods are 0 for every read, as in the reference (snp_bam_processor.cpp:100-110); with SNP sets they come
+from Context.snp_phasing (K7) on FilteredReads.view().
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import BamReader, Genotyper, LeftAligned, c_i32p, make_em_batch, make_locus_reads, ptr
+
+DEFAULT_STUTTER = (0.95, 0.05, 0.05, 0.95, 0.01, 0.01)   # hipstr_main.cpp:343
+
+
+class Options:
+    """The knobs of GenotyperBamProcessor / BamProcessor that the stages read, with the reference's defaults."""
+    max_str_length = 100            # MAX_STR_LENGTH
+    min_total_reads = 100           # MIN_TOTAL_READS
+    max_total_haplotypes = 1000
+    max_flank_haplotypes = 4
+    min_flank_freq = 0.01
+    max_em_iter, abs_ll_converge, frac_ll_converge = 100, 0.01, 0.001
+    def_stutter_model = None        # six parameters, or None = learn the model with the EM stutter genotyper
+    recalc_stutter_model = False
+    haploid_chroms = ()
+    filter = None                   # dict of hipstr_filter_options_t overrides
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(type(self), k):
+                raise TypeError("unknown option " + k)
+            setattr(self, k, v)
+
+
+def read_fasta(path):
+    seqs, name = {}, None
+    with open(path) as fh:
+        for line in fh:
+            if line.startswith(">"):
+                name = line[1:].split()[0]
+                seqs[name] = []
+            elif name is not None:
+                seqs[name].append(line.strip())
+    return {k: "".join(v) for k, v in seqs.items()}
+
+
+def read_regions(path):
+    """readRegions + orderRegions (src/region.cpp:14-55): CHROM START(1-based) STOP PERIOD NCOPIES [NAME]."""
+    out = []
+    with open(path) as fh:
+        for line in fh:
+            t = line.split()
+            if len(t) < 5:
+                raise ValueError("Improperly formatted region file: " + line)
+            out.append((t[0], int(t[1]) - 1, int(t[2]), int(t[3]), t[5] if len(t) > 5 else ""))
+    return sorted(out, key=lambda r: (r[0], r[1], r[2]))
+
+
+def _extract_cigar(lib, types, lens, start, region_start, region_end):
+    bp = C.c_int32()
+    lens = np.ascontiguousarray(lens, np.int32)
+    ok = lib.hipstr_extract_cigar(types.encode(), ptr(lens, c_i32p), len(types), start, region_start, region_end, C.byref(bp))
+    return bp.value if ok else None
+
+
+def process_regions(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_options=None):
+    """Genotypes `regions` [(chrom, start, stop, period, name)] from the BAM files; returns (records, summary) with
+    records = [(chrom, pos, VCF record text)] in region order for the loci that were genotyped."""
+    opt = options or Options()
+    lib = capi.load()
+    lib.hipstr_extract_cigar.restype = C.c_int32
+    lib.hipstr_extract_cigar.argtypes = [C.c_char_p, c_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32p]
+    reader = BamReader(bam_paths)
+    rg_map, all_samples = {}, set()
+    for path, rg_id, sample, library in reader.read_groups():
+        if sample is None or library is None:
+            raise ValueError("RG in BAM header is lacking the SM or LB tag")
+        rg_map[path + rg_id] = (sample, library)
+        all_samples.add(sample)
+    out_samples = sorted(all_samples)     # samples_to_genotype_ (genotyper_bam_processor.h:181-190)
+    summary = dict(too_long=0, near_contig_end=0, too_few_reads=0, too_many_reads=0, em_failed=0, genotype_failed=0, genotyped=0)
+
+    # ---- per region: ingestion (host) ----------------------------------------------------------------------------
+    loci = []
+    filter_kw = dict(opt.filter or {})
+    max_mate_dist = filter_kw.get("max_mate_dist", 1000)
+    for chrom, start, stop, period, name in regions:
+        if stop - start > opt.max_str_length:
+            summary["too_long"] += 1
+            continue
+        seq = chrom_seqs[chrom]
+        if start < 50 or stop + 50 >= len(seq):
+            summary["near_contig_end"] += 1
+            continue
+        recs = reader.fetch(chrom, 0 if start < max_mate_dist else start - max_mate_dist, stop + max_mate_dist)
+        kept = recs.filter(seq, [(start, stop)], rg_map, **filter_kw)
+        counts = kept.counts()
+        view = kept.view()
+        b = view.reads
+        n_entries = b.n_entries
+        if n_entries < opt.min_total_reads:          # analyze_reads_and_phasing: total_reads < MIN_TOTAL_READS
+            summary["too_few_reads"] += 1
+            continue
+        if counts["too_many_reads"]:
+            summary["too_many_reads"] += 1
+            continue
+        samples = [view.sample_names[i].decode() for i in range(view.n_samples)]
+        entry_off = np.ctypeslib.as_array(view.sample_entry_off, shape=(view.n_samples + 1,)).copy()
+        aln_off = np.ctypeslib.as_array(b.entry_aln_off, shape=(n_entries + 1,))
+        seq_off = np.ctypeslib.as_array(b.aln_seq_off, shape=(b.n_alns + 1,))
+        cig_off = np.ctypeslib.as_array(b.aln_cigar_off, shape=(b.n_alns + 1,))
+        pos = np.ctypeslib.as_array(b.aln_pos, shape=(b.n_alns,))
+        end = np.ctypeslib.as_array(b.aln_end, shape=(b.n_alns,))
+        flag = np.ctypeslib.as_array(view.aln_flag, shape=(b.n_alns,))
+        bases = C.string_at(b.bases, int(seq_off[-1])).decode("latin-1")
+        quals = C.string_at(b.quals, int(seq_off[-1])).decode("latin-1")
+        ctype = C.string_at(b.cigar_type, int(cig_off[-1])).decode()
+        clen = np.ctypeslib.as_array(b.cigar_len, shape=(max(int(cig_off[-1]), 1),))
+        passes = C.string_at(view.entry_passes, n_entries)
+        names = kept.entry_names()
+        reads, labels, rev, use, name_ids, ids = [], [], [], [], [], {}
+        for s in range(view.n_samples):
+            for e in range(int(entry_off[s]), int(entry_off[s + 1])):
+                a = int(aln_off[e])                   # the STR read; its mate (if any) only matters for phasing
+                cig = [(ctype[c], int(clen[c])) for c in range(int(cig_off[a]), int(cig_off[a + 1]))]
+                reads.append((int(pos[a]), int(end[a]), bases[seq_off[a]:seq_off[a + 1]], quals[seq_off[a]:seq_off[a + 1]], cig))
+                labels.append(s)
+                rev.append(1 if flag[a] & 0x10 else 0)
+                use.append(1 if passes[e:e + 1] == b"1" else 0)
+                name_ids.append(ids.setdefault(names[e], len(ids)))
+        loci.append(dict(chrom=chrom, start=start, stop=stop, period=period, name=name, seq=seq, samples=samples, reads=reads,
+                         labels=labels, rev=rev, use=use, name_ids=name_ids, haploid=1 if chrom in opt.haploid_chroms else 0))
+
+    # ---- stutter models: the default, or one EM fit per locus, all loci in one K4 call --------------------------------
+    if opt.def_stutter_model is not None:
+        for L in loci:
+            L["stutter"] = tuple(opt.def_stutter_model)
+    elif loci:
+        lro, lso, num_bps, labels = [0], [0], [], []
+        for L in loci:
+            informative = 0
+            per_sample = [[] for _ in L["samples"]]
+            for (start, _, _, _, cig), s in zip(L["reads"], L["labels"]):
+                if informative > 10000 and not per_sample[s]:      # MAX_INF_READS is checked between samples
+                    continue
+                bp = _extract_cigar(lib, "".join(t for t, _ in cig), [n for _, n in cig], start, L["start"] - L["period"], L["stop"] + L["period"])
+                if bp is None or bp < -(L["stop"] - L["start"] + 1):
+                    continue
+                per_sample[s].append(bp)
+                informative += 1
+            L["informative"] = informative
+            for s, bps in enumerate(per_sample):
+                num_bps += bps
+                labels += [s] * len(bps)
+            lro.append(len(num_bps))
+            lso.append(lso[-1] + len(L["samples"]))
+        zeros = np.zeros(len(num_bps))
+        batch = make_em_batch(lro, lso, num_bps, labels, zeros, zeros, [L["period"] for L in loci], [0] * len(loci), [L["haploid"] for L in loci])
+        params, converged, _, _ = ctx.em_train(batch, opt.max_em_iter, opt.abs_ll_converge, opt.frac_ll_converge)
+        trained = []
+        for l, L in enumerate(loci):
+            if L["informative"] < opt.min_total_reads:
+                summary["too_few_reads"] += 1
+            elif not converged[l]:
+                summary["em_failed"] += 1
+            else:
+                L["stutter"] = tuple(float(x) for x in params[l])
+                trained.append(L)
+        loci = trained
+    if not loci:
+        return [], summary
+
+    # ---- left alignment (K6) of all loci, then the lockstep genotyper over the window -----------------------------------
+    n = len(loci)
+    read_off = np.cumsum([0] + [len(L["reads"]) for L in loci]).astype(np.int32)
+    sample_off = np.cumsum([0] + [len(L["samples"]) for L in loci]).astype(np.int32)
+    flat = lambda key: [x for L in loci for x in L[key]]
+    n_reads = int(read_off[-1])
+    raw = make_locus_reads(read_off, sample_off, flat("reads"), flat("labels"), flat("name_ids"), np.zeros(n_reads), np.zeros(n_reads),
+                           [L["haploid"] for L in loci], flat("rev"), flat("use"))
+    seqs = [L["seq"] for L in loci]
+    aligned = LeftAligned(ctx, n, raw, seqs, [L["start"] - 40 if L["start"] > 40 else 1 for L in loci], [L["stop"] + 40 for L in loci])
+    g = Genotyper.from_reads(ctx, aligned.view, n, [L["start"] for L in loci], [L["stop"] for L in loci], [L["period"] for L in loci], seqs,
+                             stutter=np.array([L["stutter"] for L in loci]))
+    ok = g.genotype(opt.max_total_haplotypes, opt.max_flank_haplotypes, opt.min_flank_freq, True)
+    if opt.recalc_stutter_model:
+        ok = g.recompute_stutter_models(opt.max_total_haplotypes, opt.max_flank_haplotypes, opt.min_flank_freq, opt.max_em_iter,
+                                        opt.abs_ll_converge, opt.frac_ll_converge)
+    vloci = g.vcf_loci([L["chrom"] for L in loci], [L["name"] for L in loci], [L["start"] for L in loci], [L["stop"] for L in loci],
+                       [L["period"] for L in loci], seqs, [s for L in loci for s in L["samples"]], out_samples)
+    records = g.write_vcf(vloci, **(vcf_options or {}))
+    out = []
+    for l, L in enumerate(loci):
+        if ok[l] and records[l] is not None:
+            out.append((L["chrom"], records[l][0], records[l][1]))
+            summary["genotyped"] += 1
+        else:
+            summary["genotype_failed"] += 1
+    summary["left_align_failed"] = int(aligned.failed)
+    g.close()
+    aligned.close()
+    return out, summary

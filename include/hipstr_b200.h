@@ -673,6 +673,8 @@ typedef struct {
   const int32_t* sample_entry_off;     /* [n_samples+1] entries of sample s */
   const char* entry_passes;            /* [n_entries] '1' if the STR read may be used to generate haplotypes (PF tag, first region) */
   const int32_t* aln_flag;             /* [n_alns] BAM FLAG */
+  const int32_t* entry_name_off;       /* [n_entries+1] into entry_names */
+  const char* entry_names;             /* BamAlignment::Name() of the STR reads (adjacent equal names = mates that both span the STR) */
   hipstr_snp_phasing_t reads;          /* SNP arrays left NULL / 0: the caller attaches its SNP sets */
 } hipstr_filtered_view_t;
 const char* hipstr_ingest_last_error(void);

@@ -20,9 +20,11 @@
 #define protected public
 #include "bam_io.h"
 #include "bam_processor.h"
+#include "genotyper_bam_processor.h"
 #undef private
 #undef protected
 #include "alignment_filters.h"
+#include "mathops.h"
 #include "base_quality.h"
 #include "pcr_duplicates.h"
 #include "region.h"
@@ -249,6 +251,41 @@ void ref_alignment_filters(int32_t pos, int32_t end_pos, const char* bases, cons
   out[3] = d.first; out[4] = d.second;
   BaseQuality base_quality;
   *sum_qual = base_quality.sum_log_prob_correct(b.Qualities());
+}
+
+/* The reference program from its BAM files to its VCF, as hipstr_main.cpp:360-555 runs it (minus option parsing): a
+ * GenotyperBamProcessor over a BamCramMultiReader, read groups taken from the BAM headers (library tag "LB"),
+ * process_regions() over the region file, finish().  No SNP VCF, no reference-panel VCF.
+ * options = {use the default stutter model 0.95/0.05/0.05/0.95/0.01/0.01 instead of EM training, MIN_TOTAL_READS,
+ *            REMOVE_PCR_DUPS, REQUIRE_PAIRED_READS, recalc_stutter_model_ (0/1), output GLs, output PLs, output FILTERS}. */
+int32_t ref_process_regions(int32_t n_files, const char* const* paths, const char* fasta_path, const char* region_path,
+                            const char* vcf_out_path, const int32_t* options) {
+  std::vector<std::string> files(paths, paths + n_files);
+  precompute_integer_logs();   // hipstr_main.cpp:352
+  GenotyperBamProcessor proc(true, options[2] != 0);
+  proc.suppress_all_logging();
+  proc.MIN_TOTAL_READS = options[1];
+  proc.REQUIRE_PAIRED_READS = options[3];
+  if (options[0]) proc.set_default_stutter_model(0.95, 0.05, 0.05, 0.95, 0.01, 0.01);
+  proc.recalc_stutter_model_ = options[4] != 0;
+  Genotyper::OUTPUT_GLS = options[5];
+  Genotyper::OUTPUT_PLS = options[6];
+  Genotyper::OUTPUT_FILTERS = options[7];
+  BamCramMultiReader reader(files, "", BamCramMultiReader::ORDER_ALNS_BY_FILE);
+  std::map<std::string, std::string> rg_to_sample, rg_to_library;
+  std::set<std::string> samples;
+  for (size_t i = 0; i < files.size(); i++) {
+    const std::vector<ReadGroup>& groups = reader.bam_header()->read_groups(i);
+    for (auto rg = groups.begin(); rg != groups.end(); ++rg) {
+      rg_to_sample[files[i] + rg->GetID()] = rg->GetSample();
+      rg_to_library[files[i] + rg->GetID()] = rg->GetLibrary();
+      samples.insert(rg->GetSample());
+    }
+  }
+  proc.set_output_str_vcf(vcf_out_path, fasta_path, "harness", samples);
+  proc.process_regions(reader, region_path, fasta_path, rg_to_sample, rg_to_library, "harness", NULL, NULL, 10000000, "");
+  proc.finish();
+  return 0;
 }
 
 }  // extern "C"

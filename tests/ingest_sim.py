@@ -18,8 +18,9 @@ def rand_seq(rng, n):
 
 
 class Scenario:
-    def __init__(self, seed, n_files=2, n_fragments=160, name_suffix=False):
+    def __init__(self, seed, n_files=2, n_fragments=160, name_suffix=False, groups=None, tag=""):
         rng = self.rng = np.random.default_rng(seed)
+        self.tag = tag
         period = int(rng.integers(2, 5))
         motif = rand_seq(rng, period)
         while len(set(motif)) == 1:
@@ -34,8 +35,8 @@ class Scenario:
         self.name_suffix = name_suffix
         self.files = []
         for f in range(n_files):
-            groups = [("f%dg%d" % (f, g), "S%d" % int(rng.integers(0, 3)), "L%d" % int(rng.integers(0, 2))) for g in range(int(rng.integers(1, 4)))]
-            self.files.append({"groups": groups, "records": []})
+            own = [("f%dg%d" % (f, g), "S%d" % int(rng.integers(0, 3)), "L%d" % int(rng.integers(0, 2))) for g in range(int(rng.integers(1, 4)))]
+            self.files.append({"groups": groups[f] if groups else own, "records": []})
         for i in range(n_fragments):
             self.fragment(i)
 
@@ -133,7 +134,7 @@ class Scenario:
         L = int(rng.integers(90, 151))
         insert = int(rng.integers(L + 5, 650))
         start = int(rng.integers(self.region[0] - 700, self.region[1] + 200))
-        name = "frag%d" % i
+        name = "%sfrag%d" % (self.tag, i)
         copies = 2 if rng.random() < 0.15 else 1          # PCR duplicates: same coordinates, another name
         for c in range(copies):
             nm = name if c == 0 else name + "dup"
@@ -167,16 +168,59 @@ class Scenario:
 
     def add(self, f, name, flag, pos, ops, rnext, pnext, seq, quals, tags):
         cigar = "".join("%d%s" % (n, c) for c, n in ops) or "*"
-        fields = [name, str(flag), "chr1", str(pos + 1), "60", cigar, rnext, str(pnext + 1), "0", seq, quals] + tags
-        self.files[f]["records"].append((pos, len(self.files[f]["records"]), "\t".join(fields)))
+        fields = [name, str(flag), "chr1", pos + 1, "60", cigar, rnext, pnext + 1, "0", seq, quals] + tags
+        self.files[f]["records"].append((pos, len(self.files[f]["records"]), fields))
 
     # ---- output ------------------------------------------------------------------------------
     def sam_text(self, f):
         head = ["@HD\tVN:1.5\tSO:coordinate", "@SQ\tSN:chr1\tLN:%d" % len(self.chrom), "@SQ\tSN:chr2\tLN:5000", "@SQ\tSN:chr1_KI1_alt\tLN:3000"]
         for g, sample, lib in self.files[f]["groups"]:
             head.append("@RG\tID:%s\tSM:%s\tLB:%s" % (g, sample, lib))
-        lines = [r[2] for r in sorted(self.files[f]["records"])]
+        lines = ["\t".join(str(x) for x in r[2]) for r in sorted(self.files[f]["records"], key=lambda r: r[:2])]
         return "\n".join(head + lines) + "\n"
 
     def rg_map(self, paths):
         return {paths[f] + g: (sample, lib) for f in range(len(self.files)) for g, sample, lib in self.files[f]["groups"]}
+
+
+class MultiScenario:
+    """Several STRs on one chromosome: independent Scenarios laid end to end (same files and read groups)."""
+
+    def __init__(self, seed, n_regions=4, n_files=2, n_fragments=220):
+        self.parts = []
+        groups = None
+        for k in range(n_regions):
+            part = Scenario(seed * 100 + k, n_files=n_files, n_fragments=n_fragments, groups=groups, tag="r%d_" % k)
+            groups = [f["groups"] for f in part.files]
+            self.parts.append(part)
+        self.offsets = np.cumsum([0] + [len(p.chrom) for p in self.parts])
+        self.chrom = "".join(p.chrom for p in self.parts)
+        self.regions = [(int(o) + p.region[0], int(o) + p.region[1], p.period) for o, p in zip(self.offsets, self.parts)]
+        self.files = self.parts[0].files
+
+    def sam_text(self, f):
+        head = ["@HD\tVN:1.5\tSO:coordinate", "@SQ\tSN:chr1\tLN:%d" % len(self.chrom), "@SQ\tSN:chr2\tLN:5000", "@SQ\tSN:chr1_KI1_alt\tLN:3000"]
+        for g, sample, lib in self.files[f]["groups"]:
+            head.append("@RG\tID:%s\tSM:%s\tLB:%s" % (g, sample, lib))
+        lines = []
+        for o, p in zip(self.offsets, self.parts):
+            for pos, idx, fields in sorted(p.files[f]["records"], key=lambda r: r[:2]):
+                x = list(fields)
+                x[3], x[7] = x[3] + int(o), x[7] + int(o) if x[6] == "=" else x[7]
+                lines.append("\t".join(str(v) for v in x))
+        return "\n".join(head + lines) + "\n"
+
+    def rg_map(self, paths):
+        return self.parts[0].rg_map(paths)
+
+    def fasta_text(self):
+        rng = np.random.default_rng(5)
+        out = []
+        for name, seq in (("chr1", self.chrom), ("chr2", rand_seq(rng, 5000)), ("chr1_KI1_alt", rand_seq(rng, 3000))):
+            out.append(">" + name)
+            out += [seq[i:i + 60] for i in range(0, len(seq), 60)]
+        return "\n".join(out) + "\n"
+
+    def region_text(self, extra=()):
+        rows = [("chr1", s + 1, e, p, (e - s) / p, "STR%d" % i) for i, (s, e, p) in enumerate(self.regions)] + list(extra)
+        return "".join("%s\t%d\t%d\t%d\t%.1f\t%s\n" % r for r in rows)
