@@ -117,6 +117,30 @@ class SnpPhasing:
             self.n_sets, ptr(self.set_off, c_i32p), self.snp_pos.ctypes.data, self.snp_base1.ctypes.data,
             self.snp_base2.ctypes.data)
 
+    @classmethod
+    def from_arrays(cls, entry_aln_off, entry_snp_set, aln_pos, aln_end, aln_seq_off, bases, quals, aln_cigar_off, cigar_type, cigar_len,
+                    set_off, snp_pos, snp_base1, snp_base2):
+        """The same batch from flat numpy arrays (bases / quals / cigar_type / snp_base* as uint8 arrays or bytes)."""
+        b = cls.__new__(cls)
+        u8 = lambda x: np.frombuffer(bytes(x) + b"\0", np.uint8).copy() if isinstance(x, (bytes, bytearray)) else np.ascontiguousarray(
+            np.concatenate([np.asarray(x, np.uint8), np.zeros(1, np.uint8)]))
+        i32 = lambda x: np.ascontiguousarray(x, np.int32)
+        b.entry_aln_off, b.entry_snp_set = i32(entry_aln_off), i32(entry_snp_set)
+        b.aln_pos, b.aln_end, b.aln_seq_off = i32(aln_pos), i32(aln_end), i32(aln_seq_off)
+        b.bases, b.quals = u8(bases), u8(quals)
+        b.aln_cigar_off, b.cigar_type = i32(aln_cigar_off), u8(cigar_type)
+        b.cigar_len = np.ascontiguousarray(np.concatenate([np.asarray(cigar_len, np.int32), np.zeros(1, np.int32)]))
+        b.set_off = i32(set_off)
+        b.snp_pos = np.ascontiguousarray(np.concatenate([np.asarray(snp_pos, np.uint32), np.zeros(1, np.uint32)]))
+        b.snp_base1, b.snp_base2 = u8(snp_base1), u8(snp_base2)
+        b.n_entries, b.n_alns, b.n_sets = len(b.entry_snp_set), len(b.aln_pos), len(b.set_off) - 1
+        b.struct = SnpPhasingStruct(
+            b.n_entries, ptr(b.entry_aln_off, c_i32p), ptr(b.entry_snp_set, c_i32p), b.n_alns, ptr(b.aln_pos, c_i32p), ptr(b.aln_end, c_i32p),
+            ptr(b.aln_seq_off, c_i32p), b.bases.ctypes.data, b.quals.ctypes.data, ptr(b.aln_cigar_off, c_i32p), b.cigar_type.ctypes.data,
+            ptr(b.cigar_len, c_i32p), b.n_sets, ptr(b.set_off, c_i32p), b.snp_pos.ctypes.data, b.snp_base1.ctypes.data,
+            b.snp_base2.ctypes.data)
+        return b
+
     def run(self, fn, *handle):
         """Calls a function with the product's signature (ctx?, batch, log_p1, log_p2, counts) -> (status, p1, p2, counts)."""
         p1, p2 = np.zeros(max(self.n_entries, 1)), np.zeros(max(self.n_entries, 1))
@@ -155,6 +179,48 @@ def _text(fn, h):
         if -n <= cap:
             raise HipstrError(-2, "text call failed")
         cap = -n
+
+
+class SnpVcf:
+    """hipstr_snp_vcf_t: a phased SNP VCF, loaded once; region queries return per-sample SNP sets for K7."""
+
+    def __init__(self, path):
+        self.lib = load()
+        h = C.c_void_p()
+        st = self.lib.hipstr_snp_vcf_open(path.encode(), C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "snp_vcf_open: " + self.lib.hipstr_snp_vcf_last_error().decode())
+        self.h = h
+        self.samples = self.lib.hipstr_snp_vcf_samples(h).decode().splitlines()
+
+    def has_chromosome(self, chrom):
+        return bool(self.lib.hipstr_snp_vcf_has_chromosome(self.h, chrom.encode()))
+
+    def region_sets(self, chrom, start, end, skip_regions=(), skip_padding=15):
+        """-> None if the chromosome is absent, else (set_off [n_samples+1], pos uint32, base1 bytes, base2 bytes) (copies)."""
+        ss = np.array([r[0] for r in skip_regions], np.int32)
+        se = np.array([r[1] for r in skip_regions], np.int32)
+        found = C.c_int32()
+        off, pos, b1, b2 = c_i32p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        st = self.lib.hipstr_snp_vcf_region_sets(self.h, chrom.encode(), start, end, len(ss), ptr(ss, c_i32p) if len(ss) else None,
+                                                 ptr(se, c_i32p) if len(se) else None, skip_padding, C.byref(found), C.byref(off),
+                                                 C.byref(pos), C.byref(b1), C.byref(b2))
+        if st != 0:
+            raise HipstrError(st, "snp_vcf_region_sets")
+        if not found.value:
+            return None
+        n = len(self.samples)
+        set_off = np.ctypeslib.as_array(off, shape=(n + 1,)).copy()
+        total = int(set_off[-1])
+        p = np.frombuffer(C.string_at(pos.value, 4 * total), np.uint32).copy() if total else np.zeros(0, np.uint32)
+        return set_off, p, C.string_at(b1.value, total), C.string_at(b2.value, total)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hipstr_snp_vcf_close(self.h)
+            self.h = None
+
+    __del__ = close
 
 
 class BamReader:
@@ -543,6 +609,20 @@ def load():
     lib.hipstr_alignment_filters.restype = C.c_int32
     lib.hipstr_alignment_filters.argtypes = [C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, c_i32p, C.c_char_p,
                                              C.c_int32, c_i32p, c_f64p]
+    lib.hipstr_snp_vcf_last_error.restype = C.c_char_p
+    lib.hipstr_snp_vcf_open.restype = C.c_int32
+    lib.hipstr_snp_vcf_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.hipstr_snp_vcf_close.restype = None
+    lib.hipstr_snp_vcf_close.argtypes = [vp]
+    lib.hipstr_snp_vcf_num_samples.restype = C.c_int32
+    lib.hipstr_snp_vcf_num_samples.argtypes = [vp]
+    lib.hipstr_snp_vcf_samples.restype = C.c_char_p
+    lib.hipstr_snp_vcf_samples.argtypes = [vp]
+    lib.hipstr_snp_vcf_has_chromosome.restype = C.c_int32
+    lib.hipstr_snp_vcf_has_chromosome.argtypes = [vp, C.c_char_p]
+    lib.hipstr_snp_vcf_region_sets.restype = C.c_int32
+    lib.hipstr_snp_vcf_region_sets.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32, c_i32p,
+                                               C.POINTER(c_i32p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.hipstr_snp_phasing_batch_host.restype = C.c_int32
     lib.hipstr_snp_phasing_batch_host.argtypes = [vp, C.POINTER(SnpPhasingStruct), c_f64p, c_f64p, c_i32p]
     lib.hipstr_nw_align_batch_host.restype = C.c_int32

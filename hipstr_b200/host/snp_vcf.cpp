@@ -1,0 +1,234 @@
+/*
+ * snp_vcf.cpp -- the phased SNP VCF behind the phasing log-likelihoods: host-side replacement of VCF::VCFReader +
+ * VCF::Variant (src/vcf_reader.{h,cpp}, over htslib's tabix / VCF code) as create_snp_trees uses them
+ * (src/snp_tree.cpp:26-108, called from SNPBamProcessor::process_reads, src/snp_bam_processor.cpp:60-64).
+ *
+ * Different design: the file (bgzipped or plain) is read ONCE; its biallelic SNPs and every sample's phased heterozygous
+ * calls are kept per chromosome, sorted by position, so the SNPs of a region are a binary search instead of a tabix
+ * query + text parse per region.  What a region query returns is what create_snp_trees puts into its per-sample SNPTrees:
+ *   records with start <= POS <= end (tabix region "chrom:start-end"), n_allele == 2 and bcf_is_snp (every allele one
+ *   character), not within `padding` of a region to skip (in_any_region, snp_tree.cpp:9-15); per sample the calls that are
+ *   not missing, phased ('|' before the second allele) and heterozygous, as SNP(POS - 1, allele[gt_a][0], allele[gt_b][0]).
+ * Pedigree-based filtering (HaplotypeTracker) is not built.  Samples whose GT is not diploid are treated as missing.
+ */
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/hipstr_b200.h"
+
+namespace {
+
+struct Site {
+  int32_t pos;        // 1-based POS
+  char ref, alt;
+  uint32_t calls;     // offset of this site's per-sample codes
+};
+struct Chrom {
+  std::vector<Site> sites;          // in file order; sorted by position on first use
+  std::vector<uint8_t> codes;       // [site][sample]: 0 unusable, 1 = 0|1 (ref on haplotype one), 2 = 1|0
+  bool sorted = false;
+};
+
+bool read_whole_file(const std::string& path, std::string& out, std::string& err) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { err = "Failed to open the VCF file " + path; return false; }
+  std::string raw;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) raw.append(buf, n);
+  fclose(f);
+  if (raw.size() < 2 || (unsigned char)raw[0] != 31 || (unsigned char)raw[1] != 139) { out.swap(raw); return true; }
+  // BGZF = concatenated gzip members
+  z_stream zs;
+  std::memset(&zs, 0, sizeof(zs));
+  if (inflateInit2(&zs, 15 + 16) != Z_OK) { err = "zlib initialisation failed"; return false; }
+  zs.next_in = (Bytef*)raw.data();
+  zs.avail_in = (uInt)raw.size();
+  std::vector<char> chunk(1 << 20);
+  while (zs.avail_in > 0) {
+    zs.next_out = (Bytef*)chunk.data();
+    zs.avail_out = (uInt)chunk.size();
+    const int rc = inflate(&zs, Z_NO_FLUSH);
+    out.append(chunk.data(), chunk.size() - zs.avail_out);
+    if (rc == Z_STREAM_END) {
+      if (zs.avail_in == 0) break;
+      if (inflateReset(&zs) != Z_OK) { inflateEnd(&zs); err = "corrupt BGZF stream in " + path; return false; }
+    } else if (rc != Z_OK) { inflateEnd(&zs); err = "corrupt BGZF stream in " + path; return false; }
+  }
+  inflateEnd(&zs);
+  return true;
+}
+
+}  // namespace
+
+struct hipstr_snp_vcf {
+  std::vector<std::string> samples;
+  std::map<std::string, Chrom> chroms;
+  std::string sample_text;
+  // result of the last region query
+  std::vector<int32_t> set_off;
+  std::vector<uint32_t> pos;
+  std::string base1, base2;
+};
+
+namespace {
+thread_local std::string g_vcf_error;
+
+bool parse(const std::string& text, hipstr_snp_vcf& v, std::string& err) {
+  size_t at = 0;
+  bool have_header = false;
+  std::vector<const char*> field;
+  while (at < text.size()) {
+    size_t eol = text.find('\n', at);
+    if (eol == std::string::npos) eol = text.size();
+    size_t len = eol - at;
+    if (len && text[at + len - 1] == '\r') len--;
+    const char* line = text.data() + at;
+    at = eol + 1;
+    if (len == 0) continue;
+    if (line[0] == '#') {
+      if (len > 6 && std::memcmp(line, "#CHROM", 6) == 0) {
+        std::string header(line, len);
+        std::stringstream ss(header);
+        std::string item;
+        int col = 0;
+        while (std::getline(ss, item, '\t'))
+          if (col++ >= 9) v.samples.push_back(item);
+        have_header = true;
+      }
+      continue;
+    }
+    if (!have_header) { err = "VCF record before the #CHROM line"; return false; }
+    // split the fixed columns; samples are scanned in place
+    const char* end = line + len;
+    const char* col[10];
+    int n_col = 0;
+    const char* p = line;
+    col[n_col++] = p;
+    while (p < end && n_col < 10) {
+      if (*p == '\t') col[n_col++] = p + 1;
+      p++;
+    }
+    if (n_col < 8) { err = "Failed to parse VCF record"; return false; }
+    auto width = [&](int c) { return (size_t)((c + 1 < n_col ? col[c + 1] - 1 : end) - col[c]); };
+    // biallelic SNP: REF and the single ALT are one character each
+    if (width(3) != 1 || width(4) != 1 || col[4][0] == '.') continue;
+    if (n_col < 10 || v.samples.empty()) continue;
+    // index of GT in FORMAT
+    int gt_index = -1, k = 0;
+    for (const char* q = col[8]; q < col[9] - 1;) {
+      const char* stop = (const char*)std::memchr(q, ':', (size_t)(col[9] - 1 - q));
+      if (!stop) stop = col[9] - 1;
+      if (stop - q == 2 && q[0] == 'G' && q[1] == 'T') { gt_index = k; break; }
+      k++;
+      q = stop + 1;
+    }
+    if (gt_index < 0) { err = "Failed to extract the genotypes from the VCF record"; return false; }
+    Chrom& c = v.chroms[std::string(col[0], width(0))];
+    Site site;
+    site.pos = (int32_t)std::strtol(col[1], nullptr, 10);
+    site.ref = col[3][0];
+    site.alt = col[4][0];
+    site.calls = (uint32_t)c.codes.size();
+    c.codes.resize(c.codes.size() + v.samples.size(), 0);
+    const char* q = col[9];
+    for (size_t s = 0; s < v.samples.size() && q <= end; s++) {
+      const char* stop = (const char*)std::memchr(q, '\t', (size_t)(end - q));
+      if (!stop) stop = end;
+      // the gt_index-th ':' separated sub-field
+      const char* g = q;
+      for (int skip = 0; skip < gt_index && g < stop; skip++) {
+        const char* colon = (const char*)std::memchr(g, ':', (size_t)(stop - g));
+        g = colon ? colon + 1 : stop;
+      }
+      const char* g_end = (const char*)std::memchr(g, ':', (size_t)(stop - g));
+      if (!g_end) g_end = stop;
+      // phased diploid call "a|b" with two different single-digit alleles of a biallelic site
+      if (g_end - g == 3 && g[1] == '|' && (g[0] == '0' || g[0] == '1') && (g[2] == '0' || g[2] == '1') && g[0] != g[2])
+        c.codes[site.calls + s] = g[0] == '0' ? 1 : 2;
+      q = stop + 1;
+    }
+    c.sites.push_back(site);
+    c.sorted = false;
+  }
+  if (!have_header) { err = "Provided VCF file is improperly formatted"; return false; }
+  return true;
+}
+}  // namespace
+
+extern "C" {
+
+const char* hipstr_snp_vcf_last_error(void) { return g_vcf_error.c_str(); }
+
+hipstr_status_t hipstr_snp_vcf_open(const char* path, hipstr_snp_vcf_t** out) {
+  if (!path || !out) return HIPSTR_ERR_BAD_ARG;
+  std::string text;
+  if (!read_whole_file(path, text, g_vcf_error)) return HIPSTR_ERR_BAD_ARG;
+  std::unique_ptr<hipstr_snp_vcf> v(new hipstr_snp_vcf());
+  if (!parse(text, *v, g_vcf_error)) return HIPSTR_ERR_BAD_ARG;
+  for (const std::string& s : v->samples) { v->sample_text += s; v->sample_text += '\n'; }
+  *out = v.release();
+  return HIPSTR_OK;
+}
+
+void hipstr_snp_vcf_close(hipstr_snp_vcf_t* v) { delete v; }
+
+int32_t hipstr_snp_vcf_num_samples(const hipstr_snp_vcf_t* v) { return v ? (int32_t)v->samples.size() : -1; }
+const char* hipstr_snp_vcf_samples(const hipstr_snp_vcf_t* v) { return v ? v->sample_text.c_str() : nullptr; }
+int32_t hipstr_snp_vcf_has_chromosome(const hipstr_snp_vcf_t* v, const char* chrom) {
+  return v && chrom && v->chroms.count(chrom) ? 1 : 0;
+}
+
+hipstr_status_t hipstr_snp_vcf_region_sets(hipstr_snp_vcf_t* v, const char* chrom, int32_t start, int32_t end, int32_t n_skip,
+                                           const int32_t* skip_start, const int32_t* skip_stop, int32_t skip_padding, int32_t* found,
+                                           const int32_t** set_off, const uint32_t** snp_pos, const char** snp_base1,
+                                           const char** snp_base2) {
+  if (!v || !chrom || !found || !set_off || !snp_pos || !snp_base1 || !snp_base2 || n_skip < 0 || (n_skip > 0 && (!skip_start || !skip_stop)))
+    return HIPSTR_ERR_BAD_ARG;
+  const size_t S = v->samples.size();
+  v->set_off.assign(S + 1, 0);
+  v->pos.clear(); v->base1.clear(); v->base2.clear();
+  *set_off = v->set_off.data();
+  auto it = v->chroms.find(chrom);
+  *found = it != v->chroms.end();      // VCFReader::set_region fails for a chromosome the index does not know
+  if (it != v->chroms.end()) {
+    Chrom& c = it->second;
+    if (!c.sorted) {
+      std::stable_sort(c.sites.begin(), c.sites.end(), [](const Site& a, const Site& b) { return a.pos < b.pos; });
+      c.sorted = true;
+    }
+    auto lo = std::lower_bound(c.sites.begin(), c.sites.end(), start, [](const Site& s, int32_t p) { return s.pos < p; });
+    auto hi = std::upper_bound(c.sites.begin(), c.sites.end(), end, [](int32_t p, const Site& s) { return p < s.pos; });
+    std::vector<const Site*> kept;
+    for (auto s = lo; s != hi; ++s) {
+      bool skip = false;
+      for (int r = 0; r < n_skip && !skip; r++) skip = s->pos >= skip_start[r] - skip_padding && s->pos <= skip_stop[r] + skip_padding;
+      if (!skip) kept.push_back(&*s);
+    }
+    for (size_t smp = 0; smp < S; smp++) {
+      for (const Site* s : kept) {
+        const uint8_t code = c.codes[s->calls + smp];
+        if (!code) continue;
+        v->pos.push_back((uint32_t)(s->pos - 1));       // VCF is 1-based, the alignments 0-based
+        v->base1 += code == 1 ? s->ref : s->alt;
+        v->base2 += code == 1 ? s->alt : s->ref;
+      }
+      v->set_off[smp + 1] = (int32_t)v->pos.size();
+    }
+  }
+  if (v->pos.empty()) v->pos.push_back(0);
+  *snp_pos = v->pos.data();
+  *snp_base1 = v->base1.c_str();
+  *snp_base2 = v->base2.c_str();
+  return HIPSTR_OK;
+}
+
+}  // extern "C"

@@ -16,7 +16,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import BamReader, Genotyper, LeftAligned, c_i32p, make_em_batch, make_locus_reads, ptr
+from .capi import BamReader, Genotyper, LeftAligned, SnpPhasing, SnpVcf, c_i32p, make_em_batch, make_locus_reads, ptr
 
 DEFAULT_STUTTER = (0.95, 0.05, 0.05, 0.95, 0.01, 0.01)   # hipstr_main.cpp:343
 
@@ -32,6 +32,9 @@ class Options:
     def_stutter_model = None        # six parameters, or None = learn the model with the EM stutter genotyper
     recalc_stutter_model = False
     haploid_chroms = ()
+    snp_vcf = None                  # path of a phased SNP VCF (bgzipped or plain): phasing log-likelihoods from K7
+    max_mate_dist = 1000            # MAX_MATE_DIST
+    skip_padding = 15               # SNPBamProcessor::SKIP_PADDING
     filter = None                   # dict of hipstr_filter_options_t overrides
 
     def __init__(self, **kw):
@@ -92,7 +95,10 @@ def process_regions(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_optio
     # ---- per region: ingestion (host) ----------------------------------------------------------------------------
     loci = []
     filter_kw = dict(opt.filter or {})
-    max_mate_dist = filter_kw.get("max_mate_dist", 1000)
+    filter_kw.setdefault("max_mate_dist", opt.max_mate_dist)
+    max_mate_dist = opt.max_mate_dist
+    snp_vcf = SnpVcf(opt.snp_vcf) if opt.snp_vcf else None
+    vcf_index = {name: i for i, name in enumerate(snp_vcf.samples)} if snp_vcf else {}
     for chrom, start, stop, period, name in regions:
         if stop - start > opt.max_str_length:
             summary["too_long"] += 1
@@ -104,6 +110,7 @@ def process_regions(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_optio
         recs = reader.fetch(chrom, 0 if start < max_mate_dist else start - max_mate_dist, stop + max_mate_dist)
         kept = recs.filter(seq, [(start, stop)], rg_map, **filter_kw)
         counts = kept.counts()
+        names = kept.entry_names()                   # (builds a view of its own: taken before the one used below)
         view = kept.view()
         b = view.reads
         n_entries = b.n_entries
@@ -126,7 +133,6 @@ def process_regions(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_optio
         ctype = C.string_at(b.cigar_type, int(cig_off[-1])).decode()
         clen = np.ctypeslib.as_array(b.cigar_len, shape=(max(int(cig_off[-1]), 1),))
         passes = C.string_at(view.entry_passes, n_entries)
-        names = kept.entry_names()
         reads, labels, rev, use, name_ids, ids = [], [], [], [], [], {}
         for s in range(view.n_samples):
             for e in range(int(entry_off[s]), int(entry_off[s + 1])):
@@ -137,34 +143,71 @@ def process_regions(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_optio
                 rev.append(1 if flag[a] & 0x10 else 0)
                 use.append(1 if passes[e:e + 1] == b"1" else 0)
                 name_ids.append(ids.setdefault(names[e], len(ids)))
-        loci.append(dict(chrom=chrom, start=start, stop=stop, period=period, name=name, seq=seq, samples=samples, reads=reads,
-                         labels=labels, rev=rev, use=use, name_ids=name_ids, haploid=1 if chrom in opt.haploid_chroms else 0))
+        L = dict(chrom=chrom, start=start, stop=stop, period=period, name=name, seq=seq, samples=samples, reads=reads,
+                 labels=labels, rev=rev, use=use, name_ids=name_ids, haploid=1 if chrom in opt.haploid_chroms else 0)
+        sets = snp_vcf.region_sets(chrom, start - max_mate_dist if start > max_mate_dist else 1, stop + max_mate_dist, [(start, stop)],
+                                   opt.skip_padding) if snp_vcf else None
+        if sets is not None:   # copies of the view (it dies with `kept`): this locus' share of the window's K7 batch
+            entry_set = np.repeat([vcf_index.get(smp, -1) for smp in samples], np.diff(entry_off))
+            L["phasing"] = dict(entry_aln_off=aln_off.copy(), entry_set=entry_set, aln_pos=pos.copy(), aln_end=end.copy(),
+                                aln_seq_off=seq_off.copy(), bases=bases.encode("latin-1"), quals=quals.encode("latin-1"),
+                                aln_cigar_off=cig_off.copy(), cigar_type=ctype.encode(), cigar_len=clen[:int(cig_off[-1])].copy(), sets=sets)
+        loci.append(L)
+
+    # ---- phasing log-likelihoods of every read of the window in ONE K7 launch ------------------------------------------
+    for L in loci:
+        L["log_p1"], L["log_p2"] = np.zeros(len(L["reads"])), np.zeros(len(L["reads"]))
+    parts = [L["phasing"] for L in loci if "phasing" in L]
+    if parts:
+        aln_shift = np.cumsum([0] + [len(p["aln_pos"]) for p in parts])
+        seq_shift = np.cumsum([0] + [len(p["bases"]) for p in parts])
+        cig_shift = np.cumsum([0] + [len(p["cigar_type"]) for p in parts])
+        set_shift = np.cumsum([0] + [len(p["sets"][0]) - 1 for p in parts])
+        snp_shift = np.cumsum([0] + [len(p["sets"][1]) for p in parts])
+        offs = lambda key, shift: np.concatenate([np.asarray(p[key])[:-1] + s for p, s in zip(parts, shift)] + [[shift[-1]]])
+        batch = SnpPhasing.from_arrays(
+            offs("entry_aln_off", aln_shift), np.concatenate([np.where(p["entry_set"] >= 0, p["entry_set"] + s, -1) for p, s in zip(parts, set_shift)]),
+            np.concatenate([p["aln_pos"] for p in parts]), np.concatenate([p["aln_end"] for p in parts]), offs("aln_seq_off", seq_shift),
+            b"".join(p["bases"] for p in parts), b"".join(p["quals"] for p in parts), offs("aln_cigar_off", cig_shift),
+            b"".join(p["cigar_type"] for p in parts), np.concatenate([p["cigar_len"] for p in parts]),
+            np.concatenate([np.asarray(p["sets"][0])[:-1] + s for p, s in zip(parts, snp_shift)] + [[snp_shift[-1]]]),
+            np.concatenate([p["sets"][1] for p in parts]), b"".join(p["sets"][2] for p in parts), b"".join(p["sets"][3] for p in parts))
+        p1, p2, counts = ctx.snp_phasing(batch)
+        at = 0
+        for L in loci:
+            if "phasing" in L:
+                n_e = len(L["reads"])
+                L["log_p1"], L["log_p2"] = p1[at:at + n_e].copy(), p2[at:at + n_e].copy()
+                at += n_e
+        summary["snp_matches"], summary["snp_mismatches"] = int(counts[:, :2].sum()), int(counts[:, 2].sum())
+        summary["phased_reads"] = int((p1 != p2).sum())
 
     # ---- stutter models: the default, or one EM fit per locus, all loci in one K4 call --------------------------------
     if opt.def_stutter_model is not None:
         for L in loci:
             L["stutter"] = tuple(opt.def_stutter_model)
     elif loci:
-        lro, lso, num_bps, labels = [0], [0], [], []
+        lro, lso, num_bps, labels, em_p1, em_p2 = [0], [0], [], [], [], []
         for L in loci:
             informative = 0
             per_sample = [[] for _ in L["samples"]]
-            for (start, _, _, _, cig), s in zip(L["reads"], L["labels"]):
+            for r, ((start, _, _, _, cig), s) in enumerate(zip(L["reads"], L["labels"])):
                 if informative > 10000 and not per_sample[s]:      # MAX_INF_READS is checked between samples
                     continue
                 bp = _extract_cigar(lib, "".join(t for t, _ in cig), [n for _, n in cig], start, L["start"] - L["period"], L["stop"] + L["period"])
                 if bp is None or bp < -(L["stop"] - L["start"] + 1):
                     continue
-                per_sample[s].append(bp)
+                per_sample[s].append((bp, L["log_p1"][r], L["log_p2"][r]))
                 informative += 1
             L["informative"] = informative
             for s, bps in enumerate(per_sample):
-                num_bps += bps
+                num_bps += [x[0] for x in bps]
+                em_p1 += [x[1] for x in bps]
+                em_p2 += [x[2] for x in bps]
                 labels += [s] * len(bps)
             lro.append(len(num_bps))
             lso.append(lso[-1] + len(L["samples"]))
-        zeros = np.zeros(len(num_bps))
-        batch = make_em_batch(lro, lso, num_bps, labels, zeros, zeros, [L["period"] for L in loci], [0] * len(loci), [L["haploid"] for L in loci])
+        batch = make_em_batch(lro, lso, num_bps, labels, em_p1, em_p2, [L["period"] for L in loci], [0] * len(loci), [L["haploid"] for L in loci])
         params, converged, _, _ = ctx.em_train(batch, opt.max_em_iter, opt.abs_ll_converge, opt.frac_ll_converge)
         trained = []
         for l, L in enumerate(loci):
@@ -184,9 +227,8 @@ def process_regions(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_optio
     read_off = np.cumsum([0] + [len(L["reads"]) for L in loci]).astype(np.int32)
     sample_off = np.cumsum([0] + [len(L["samples"]) for L in loci]).astype(np.int32)
     flat = lambda key: [x for L in loci for x in L[key]]
-    n_reads = int(read_off[-1])
-    raw = make_locus_reads(read_off, sample_off, flat("reads"), flat("labels"), flat("name_ids"), np.zeros(n_reads), np.zeros(n_reads),
-                           [L["haploid"] for L in loci], flat("rev"), flat("use"))
+    raw = make_locus_reads(read_off, sample_off, flat("reads"), flat("labels"), flat("name_ids"), np.concatenate([L["log_p1"] for L in loci]),
+                           np.concatenate([L["log_p2"] for L in loci]), [L["haploid"] for L in loci], flat("rev"), flat("use"))
     seqs = [L["seq"] for L in loci]
     aligned = LeftAligned(ctx, n, raw, seqs, [L["start"] - 40 if L["start"] > 40 else 1 for L in loci], [L["stop"] + 40 for L in loci])
     g = Genotyper.from_reads(ctx, aligned.view, n, [L["start"] for L in loci], [L["stop"] for L in loci], [L["period"] for L in loci], seqs,

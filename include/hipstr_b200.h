@@ -714,6 +714,28 @@ int32_t hipstr_alignment_filters(int32_t pos, int32_t end_pos, const char* bases
                                  const char* cigar_type, const int32_t* cigar_len, const char* chrom_seq, int32_t window,
                                  int32_t* out, double* sum_qual);
 
+/* --- section 8(f) row 4, third slice: the phased SNP VCF behind K7 (host) ---------
+ * Replaces VCF::VCFReader / VCF::Variant (src/vcf_reader.{h,cpp}) as create_snp_trees uses them (src/snp_tree.cpp:26-108):
+ * the file (bgzipped or plain text) is read once, and a region query returns, for every sample of the VCF, the SNP set
+ * create_snp_trees would put into that sample's SNPTree -- biallelic SNP records with start <= POS <= end (the tabix
+ * region "chrom:start-end"; process_reads passes region start - MAX_MATE_DIST (or 1) and region stop + MAX_MATE_DIST,
+ * src/snp_bam_processor.cpp:62), not within skip_padding (SKIP_PADDING = 15) of a region to skip, and of those the
+ * sample's phased heterozygous calls as (POS - 1, allele on haplotype one, allele on haplotype two).
+ * *found = 0 when the chromosome is not in the VCF (the reference then proceeds without SNP information).
+ * The returned arrays (n_samples + 1 offsets, then the SNPs sample after sample) are K7's set_off / snp_pos / snp_base1 /
+ * snp_base2 and stay valid until the next call on the handle.  Pedigree filtering is not built. */
+typedef struct hipstr_snp_vcf hipstr_snp_vcf_t;
+const char* hipstr_snp_vcf_last_error(void);
+hipstr_status_t hipstr_snp_vcf_open(const char* path, hipstr_snp_vcf_t** out);
+void hipstr_snp_vcf_close(hipstr_snp_vcf_t* vcf);
+int32_t hipstr_snp_vcf_num_samples(const hipstr_snp_vcf_t* vcf);
+const char* hipstr_snp_vcf_samples(const hipstr_snp_vcf_t* vcf);          /* sample names, one per line */
+int32_t hipstr_snp_vcf_has_chromosome(const hipstr_snp_vcf_t* vcf, const char* chrom);
+hipstr_status_t hipstr_snp_vcf_region_sets(hipstr_snp_vcf_t* vcf, const char* chrom, int32_t start, int32_t end, int32_t n_skip,
+                                           const int32_t* skip_start, const int32_t* skip_stop, int32_t skip_padding,
+                                           int32_t* found, const int32_t** set_off, const uint32_t** snp_pos,
+                                           const char** snp_base1, const char** snp_base2);
+
 /* Wall-clock seconds this context has spent inside hipstr_trace_batch_host, by part:
  * {host lowering of the batch, ordering + uploads, kernel K5, downloads of the results} */
 void hipstr_trace_seconds(const hipstr_ctx_t* ctx, double* seconds4);

@@ -30,6 +30,10 @@
 #include "region.h"
 #include "snp_phasing_quality.h"
 #include "snp_tree.h"
+#include "vcf_reader.h"
+extern "C" {
+#include "htslib/htslib/tbx.h"
+}
 
 namespace {
 
@@ -259,7 +263,7 @@ void ref_alignment_filters(int32_t pos, int32_t end_pos, const char* bases, cons
  * options = {use the default stutter model 0.95/0.05/0.05/0.95/0.01/0.01 instead of EM training, MIN_TOTAL_READS,
  *            REMOVE_PCR_DUPS, REQUIRE_PAIRED_READS, recalc_stutter_model_ (0/1), output GLs, output PLs, output FILTERS}. */
 int32_t ref_process_regions(int32_t n_files, const char* const* paths, const char* fasta_path, const char* region_path,
-                            const char* vcf_out_path, const int32_t* options) {
+                            const char* vcf_out_path, const int32_t* options, const char* snp_vcf_path /* NULL = none */) {
   std::vector<std::string> files(paths, paths + n_files);
   precompute_integer_logs();   // hipstr_main.cpp:352
   GenotyperBamProcessor proc(true, options[2] != 0);
@@ -282,10 +286,56 @@ int32_t ref_process_regions(int32_t n_files, const char* const* paths, const cha
       samples.insert(rg->GetSample());
     }
   }
+  if (snp_vcf_path != NULL) proc.set_input_snp_vcf(snp_vcf_path);
   proc.set_output_str_vcf(vcf_out_path, fasta_path, "harness", samples);
   proc.process_regions(reader, region_path, fasta_path, rg_to_sample, rg_to_library, "harness", NULL, NULL, 10000000, "");
   proc.finish();
   return 0;
+}
+
+/* Plain VCF text -> bgzipped VCF + tabix index with htslib (so that VCF::VCFReader can open it). */
+int32_t ref_vcf_bgzip_tabix(const char* vcf_text_path, const char* out_gz_path) {
+  FILE* in = fopen(vcf_text_path, "rb");
+  if (!in) return -1;
+  BGZF* out = bgzf_open(out_gz_path, "w");
+  if (!out) { fclose(in); return -2; }
+  char buf[1 << 16];
+  size_t n;
+  int rc = 0;
+  while ((n = fread(buf, 1, sizeof(buf), in)) > 0)
+    if (bgzf_write(out, buf, n) < 0) rc = -3;
+  fclose(in);
+  if (bgzf_close(out) < 0 && rc == 0) rc = -4;
+  if (rc == 0 && tbx_index_build(out_gz_path, 0, &tbx_conf_vcf) != 0) rc = -5;
+  return rc;
+}
+
+/* create_snp_trees (src/snp_tree.cpp:26-108, no pedigree) for one region as SNPBamProcessor::process_reads calls it
+ * (src/snp_bam_processor.cpp:62-63), dumped per VCF sample by querying each tree for everything: lines "S <sample>"
+ * followed by "pos base1 base2".  Returns the text length, -1 when create_snp_trees fails (chromosome not in the VCF). */
+int32_t ref_snp_sets(const char* snp_vcf_path, const char* chrom, int32_t region_start, int32_t region_stop, int32_t period,
+                     int32_t max_mate_dist, int32_t skip_padding, int32_t cap, char* out_text) {
+  VCF::VCFReader reader(snp_vcf_path);
+  Region region(chrom, region_start, region_stop, period);
+  std::vector<Region> skip(1, region);
+  std::vector<SNPTree*> trees;
+  std::map<std::string, unsigned int> sample_indices;
+  std::ostringstream sink, out;
+  if (!create_snp_trees(chrom, (region_start > max_mate_dist ? region_start - max_mate_dist : 1), region_stop + max_mate_dist, skip,
+                        skip_padding, &reader, NULL, sample_indices, trees, sink))
+    return -1;
+  const std::vector<std::string>& names = reader.get_samples();
+  for (size_t i = 0; i < names.size(); i++) {
+    out << "S " << names[i] << '\n';
+    std::vector<SNP> snps;
+    trees[sample_indices[names[i]]]->findContained(0, 2000000000u, snps);
+    for (size_t k = 0; k < snps.size(); k++) out << snps[k].pos() << ' ' << snps[k].base_one() << ' ' << snps[k].base_two() << '\n';
+  }
+  destroy_snp_trees(trees);
+  const std::string s = out.str();
+  if ((int32_t)s.size() + 1 > cap) return -2;
+  memcpy(out_text, s.c_str(), s.size() + 1);
+  return (int32_t)s.size();
 }
 
 }  // extern "C"

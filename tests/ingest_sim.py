@@ -224,3 +224,33 @@ class MultiScenario:
     def region_text(self, extra=()):
         rows = [("chr1", s + 1, e, p, (e - s) / p, "STR%d" % i) for i, (s, e, p) in enumerate(self.regions)] + list(extra)
         return "".join("%s\t%d\t%d\t%d\t%.1f\t%s\n" % r for r in rows)
+
+    def snp_vcf_text(self, seed=1, density=120):
+        """A phased SNP VCF over chr1 (+ one record on chr2): biallelic SNPs with 0|1, 1|0, 1|1, 0|0, 0/1, ./. and .|. calls, plus
+        indels, multi-allelic sites and sites inside / next to the STRs, for the BAM samples except one and one foreign sample."""
+        rng = np.random.default_rng(seed)
+        bam_samples = sorted({s for f in self.files for _, s, _ in f["groups"]})
+        samples = ["X9"] + (bam_samples[:-1] if len(bam_samples) > 1 else bam_samples)
+        lines = ["##fileformat=VCFv4.2", "##contig=<ID=chr1,length=%d>" % len(self.chrom), "##contig=<ID=chr2,length=5000>",
+                 '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">', '##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Depth">',
+                 "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(samples)]
+        calls = ["0|1", "1|0", "0|1", "1|0", "1|1", "0|0", "0/1", "./.", ".|.", "1/0"]
+        positions = set()
+        for start, stop, _ in self.regions:
+            positions.update(int(x) for x in rng.integers(start - 1300, stop + 1300, (stop - start + 2600) // density))
+            positions.update(range(start - 17, start - 12))          # around the skip padding
+            positions.update(range(stop + 13, stop + 18))
+        for pos in sorted(p for p in positions if 1 <= p <= len(self.chrom) - 2):
+            ref = self.chrom[pos - 1]
+            alt = "ACGT"[("ACGT".index(ref) + int(rng.integers(1, 4))) % 4]
+            r = rng.random()
+            if r < 0.06:
+                ref, alt = self.chrom[pos - 1:pos + 1], ref                      # deletion
+            elif r < 0.10:
+                alt = alt + "," + "ACGT"[("ACGT".index(ref) + 2) % 4 if alt != "ACGT"[("ACGT".index(ref) + 2) % 4] else ("ACGT".index(ref) + 1) % 4]
+            elif r < 0.13:
+                alt = ref + "T"                                                   # insertion
+            gts = [calls[int(rng.integers(0, len(calls)))] + ":%d" % int(rng.integers(1, 60)) for _ in samples]
+            lines.append("chr1\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT:DP\t%s" % (pos, ref, alt, "\t".join(gts)))
+        lines.append("chr2\t100\t.\tA\tC\t.\tPASS\t.\tGT:DP\t" + "\t".join("0|1:9" for _ in samples))
+        return "\n".join(lines) + "\n"

@@ -15,13 +15,14 @@ canon = lambda t: t.replace(":-0.00:", ":0.00:")
 
 
 def run_reference(paths, fasta, bed, out_vcf, def_stutter, min_total_reads=20, remove_dups=1, require_paired=1, recalc=0, gls=0, pls=0,
-                  filters=0):
+                  filters=0, snp_vcf=None):
     f = checkers.ref().ref_process_regions
     f.restype = C.c_int32
-    f.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32)]
+    f.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.c_char_p]
     arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
     o = np.array([def_stutter, min_total_reads, remove_dups, require_paired, recalc, gls, pls, filters], np.int32)
-    assert f(len(paths), arr, fasta.encode(), bed.encode(), out_vcf.encode(), o.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    assert f(len(paths), arr, fasta.encode(), bed.encode(), out_vcf.encode(), o.ctypes.data_as(C.POINTER(C.c_int32)),
+             snp_vcf.encode() if snp_vcf else None) == 0
     import gzip
     with gzip.open(out_vcf, "rt") as fh:       # the reference always writes BGZF (bgzfostream)
         lines = fh.read().splitlines()
@@ -52,6 +53,8 @@ def files_of(sc, tmp_path, extra_regions=()):
 @needs_ref
 @pytest.mark.parametrize("seed,def_stutter,kw", [
     (3, 1, {}),
+    (7, 1, dict(snp_vcf=1)),                      # phasing log-likelihoods from a phased SNP VCF (K7)
+    (8, 0, dict(snp_vcf=1, gls=1)),               # ... which also enter the EM stutter model
     (4, 0, {}),                                   # stutter models learned by the EM genotyper (K4)
     (5, 1, dict(require_paired=0, gls=1, pls=1, filters=1)),
     (6, 0, dict(recalc=1, remove_dups=0)),
@@ -61,8 +64,10 @@ def test_bam_to_vcf_matches_reference(seed, def_stutter, kw, tmp_path):
     sc = MultiScenario(seed, n_regions=4, n_fragments=220 if def_stutter else 600)
     extra = [("chr1", 2000, 2200, 4, 50.0, "TOO_LONG"), ("chr1", 10, 40, 3, 10.0, "CONTIG_END"), ("chr1", 7000, 7030, 3, 10.0, "NO_READS")]
     paths, fasta, bed = files_of(sc, tmp_path, extra)
-    header, want = run_reference(paths, fasta, bed, str(tmp_path / "ref.vcf"), def_stutter, **kw)
-    opt = pipeline.Options(min_total_reads=20, def_stutter_model=pipeline.DEFAULT_STUTTER if def_stutter else None,
+    kw = dict(kw)
+    snp_vcf = write_snp_vcf(sc, tmp_path, seed)[1] if kw.pop("snp_vcf", 0) else None
+    header, want = run_reference(paths, fasta, bed, str(tmp_path / "ref.vcf"), def_stutter, snp_vcf=snp_vcf, **kw)
+    opt = pipeline.Options(min_total_reads=20, snp_vcf=snp_vcf, def_stutter_model=pipeline.DEFAULT_STUTTER if def_stutter else None,
                            recalc_stutter_model=bool(kw.get("recalc", 0)),
                            filter=dict(remove_pcr_dups=kw.get("remove_dups", 1), require_paired_reads=kw.get("require_paired", 1)))
     vcf_opt = dict(output_gls=kw.get("gls", 0), output_pls=kw.get("pls", 0), output_filters=kw.get("filters", 0))
@@ -70,6 +75,51 @@ def test_bam_to_vcf_matches_reference(seed, def_stutter, kw, tmp_path):
         records, summary = pipeline.process_regions(ctx, paths, pipeline.read_fasta(fasta), pipeline.read_regions(bed), opt, vcf_opt)
     print(summary)
     assert [canon(r[2]) for r in records] == [canon(w) for w in want]
+    if snp_vcf:
+        assert summary["phased_reads"] > 20
     assert len(want) >= 2 and summary["too_long"] == 1 and summary["near_contig_end"] == 1 and summary["too_few_reads"] >= 1
     # the sample columns of the header line are the sorted sample names the records were written for
     assert header[-1].split("\t")[9:] == sorted({s for f in sc.files for _, s, _ in f["groups"]})
+
+
+def write_snp_vcf(sc, tmp_path, seed=1):
+    ref = checkers.ref()
+    ref.ref_vcf_bgzip_tabix.restype = C.c_int32
+    ref.ref_vcf_bgzip_tabix.argtypes = [C.c_char_p, C.c_char_p]
+    text, gz = str(tmp_path / "snps.vcf"), str(tmp_path / "snps.vcf.gz")
+    with open(text, "w") as fh:
+        fh.write(sc.snp_vcf_text(seed))
+    assert ref.ref_vcf_bgzip_tabix(text.encode(), gz.encode()) == 0
+    return text, gz
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [3, 4])
+def test_snp_sets_match_create_snp_trees(seed, tmp_path):
+    """hipstr_snp_vcf_region_sets against the reference's create_snp_trees over a bgzipped + tabix-indexed VCF (CPU only);
+    the product reads the bgzipped file and the plain text alike."""
+    from hipstr_b200.capi import SnpVcf
+    sc = MultiScenario(seed, n_regions=3, n_fragments=10)
+    text, gz = write_snp_vcf(sc, tmp_path, seed)
+    f = checkers.ref().ref_snp_sets
+    f.restype = C.c_int32
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_char_p]
+    total = 0
+    for path in (gz, text):
+        vcf = SnpVcf(path)
+        assert vcf.samples[0] == "X9" and vcf.has_chromosome("chr2") and not vcf.has_chromosome("chr3")
+        for start, stop, period in sc.regions + [(60, 90, 3)]:
+            for mate_dist, padding in ((1000, 15), (200, 0)):
+                buf = C.create_string_buffer(1 << 22)
+                n = f(gz.encode(), b"chr1", start, stop, period, mate_dist, padding, len(buf), buf)
+                assert n >= 0
+                got = vcf.region_sets("chr1", start - mate_dist if start > mate_dist else 1, stop + mate_dist, [(start, stop)], padding)
+                off, pos, b1, b2 = got
+                lines = []
+                for s, name in enumerate(vcf.samples):
+                    lines.append("S " + name)
+                    lines += ["%d %s %s" % (pos[k], chr(b1[k]), chr(b2[k])) for k in range(off[s], off[s + 1])]
+                assert "\n".join(lines) + "\n" == buf.raw[:n].decode(), (path, start, stop, mate_dist)
+                total += len(pos)
+        assert vcf.region_sets("chr3", 1, 1000) is None
+    assert total > 60
