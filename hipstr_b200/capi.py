@@ -161,6 +161,15 @@ class FilterOptions(C.Structure):
                 ("remove_pcr_dups", C.c_int32), ("trim_adapters", C.c_int32)]
 
 
+class PipelineOptions(C.Structure):
+    """hipstr_pipeline_options_t"""
+    _fields_ = [("filter", FilterOptions), ("max_str_length", C.c_int32), ("min_total_reads", C.c_int32), ("max_total_haplotypes", C.c_int32),
+                ("max_flank_haplotypes", C.c_int32), ("min_flank_freq", C.c_double), ("max_em_iter", C.c_int32), ("abs_ll_converge", C.c_double),
+                ("frac_ll_converge", C.c_double), ("use_def_stutter_model", C.c_int32), ("def_stutter_model", C.c_double * 6),
+                ("recalc_stutter_model", C.c_int32), ("skip_padding", C.c_int32), ("n_haploid_chroms", C.c_int32),
+                ("haploid_chroms", C.POINTER(C.c_char_p)), ("host_threads", C.c_int32)]
+
+
 class FilteredView(C.Structure):
     """hipstr_filtered_view_t"""
     _fields_ = [("n_samples", C.c_int32), ("sample_names", C.POINTER(C.c_char_p)), ("sample_entry_off", c_i32p),
@@ -609,6 +618,24 @@ def load():
     lib.hipstr_alignment_filters.restype = C.c_int32
     lib.hipstr_alignment_filters.argtypes = [C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, c_i32p, C.c_char_p,
                                              C.c_int32, c_i32p, c_f64p]
+    lib.hipstr_pipeline_default_options.restype = None
+    lib.hipstr_pipeline_default_options.argtypes = [C.POINTER(PipelineOptions)]
+    lib.hipstr_process_regions_last_error.restype = C.c_char_p
+    lib.hipstr_process_regions.restype = C.c_int32
+    lib.hipstr_process_regions.argtypes = [vp, C.c_int32, cpp, vp, C.c_int32, cpp, cpp, C.c_int32, cpp, c_i32p, c_i32p, c_i32p, cpp,
+                                           C.POINTER(PipelineOptions), C.POINTER(VcfOptions), C.POINTER(vp)]
+    lib.hipstr_region_results_count.restype = C.c_int32
+    lib.hipstr_region_results_count.argtypes = [vp]
+    lib.hipstr_region_results_status.restype = C.c_int32
+    lib.hipstr_region_results_status.argtypes = [vp, C.c_int32, c_i32p, c_i32p]
+    lib.hipstr_region_results_record.restype = C.c_char_p
+    lib.hipstr_region_results_record.argtypes = [vp, C.c_int32]
+    lib.hipstr_region_results_samples.restype = C.c_char_p
+    lib.hipstr_region_results_samples.argtypes = [vp]
+    lib.hipstr_region_results_timing.restype = None
+    lib.hipstr_region_results_timing.argtypes = [vp, c_f64p, c_i64p]
+    lib.hipstr_region_results_free.restype = None
+    lib.hipstr_region_results_free.argtypes = [vp]
     lib.hipstr_snp_vcf_last_error.restype = C.c_char_p
     lib.hipstr_snp_vcf_open.restype = C.c_int32
     lib.hipstr_snp_vcf_open.argtypes = [C.c_char_p, C.POINTER(vp)]

@@ -36,6 +36,7 @@ class Options:
     max_mate_dist = 1000            # MAX_MATE_DIST
     skip_padding = 15               # SNPBamProcessor::SKIP_PADDING
     filter = None                   # dict of hipstr_filter_options_t overrides
+    host_threads = 0                # 0 = HIPSTR_HOST_THREADS / all cores
 
     def __init__(self, **kw):
         for k, v in kw.items():
@@ -75,8 +76,63 @@ def _extract_cigar(lib, types, lens, start, region_start, region_end):
     return bp.value if ok else None
 
 
+STATUS = ("genotyped", "too_long", "near_contig_end", "too_few_reads", "too_many_reads", "em_failed", "genotype_failed", "unknown_chromosome")
+
+
 def process_regions(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_options=None):
-    """Genotypes `regions` [(chrom, start, stop, period, name)] from the BAM files; returns (records, summary) with
+    """hipstr_process_regions (hipstr_b200/host/region_driver.cpp): the whole chain in native code, one call per window.
+    Returns (records, summary) like process_regions_staged."""
+    opt = options or Options()
+    lib = capi.load()
+    po = capi.PipelineOptions()
+    lib.hipstr_pipeline_default_options(C.byref(po))
+    for k, v in (opt.filter or {}).items():
+        setattr(po.filter, k, v)
+    po.filter.max_mate_dist = opt.max_mate_dist
+    for k in ("max_str_length", "min_total_reads", "max_total_haplotypes", "max_flank_haplotypes", "min_flank_freq", "max_em_iter",
+              "abs_ll_converge", "frac_ll_converge", "skip_padding"):
+        setattr(po, k, getattr(opt, k))
+    po.recalc_stutter_model = int(bool(opt.recalc_stutter_model))
+    if opt.def_stutter_model is not None:
+        po.use_def_stutter_model = 1
+        po.def_stutter_model = (C.c_double * 6)(*opt.def_stutter_model)
+    mk = lambda xs: (C.c_char_p * max(len(xs), 1))(*[x if isinstance(x, bytes) else x.encode() for x in xs])
+    hap = mk(list(opt.haploid_chroms))
+    po.n_haploid_chroms, po.haploid_chroms = len(opt.haploid_chroms), hap
+    po.host_threads = opt.host_threads
+    vo = capi.VcfOptions()
+    lib.hipstr_vcf_default_options(C.byref(vo))
+    for k, v in (vcf_options or {}).items():
+        setattr(vo, k, v)
+    snp_vcf = SnpVcf(opt.snp_vcf) if opt.snp_vcf else None
+    names = list(chrom_seqs)
+    starts, stops, periods = (np.array([r[k] for r in regions], np.int32) for k in (1, 2, 3))
+    h = C.c_void_p()
+    st = lib.hipstr_process_regions(ctx.h, len(bam_paths), mk(bam_paths), snp_vcf.h if snp_vcf else None, len(names), mk(names),
+                                    mk([chrom_seqs[n] for n in names]), len(regions), mk([r[0] for r in regions]), ptr(starts, c_i32p),
+                                    ptr(stops, c_i32p), ptr(periods, c_i32p), mk([r[4] for r in regions]), C.byref(po), C.byref(vo), C.byref(h))
+    if st != 0:
+        raise capi.HipstrError(st, "process_regions: " + lib.hipstr_process_regions_last_error().decode())
+    summary = {k: 0 for k in STATUS}
+    records = []
+    for i, r in enumerate(regions):
+        pos = C.c_int32()
+        status = lib.hipstr_region_results_status(h, i, C.byref(pos), None)
+        summary[STATUS[status]] += 1
+        if status == 0:
+            records.append((r[0], pos.value, lib.hipstr_region_results_record(h, i).decode()))
+    sec, cnt = np.zeros(6), np.zeros(4, np.int64)
+    lib.hipstr_region_results_timing(h, ptr(sec, capi.c_f64p), ptr(cnt, capi.c_i64p))
+    summary["seconds"] = dict(zip(("ingest", "phasing", "stutter", "left_align", "genotype", "records"), (float(x) for x in sec)))
+    summary["alignments_read"], summary["reads_kept"], summary["phased_reads"], summary["left_align_failed"] = (int(x) for x in cnt)
+    summary["samples"] = lib.hipstr_region_results_samples(h).decode().splitlines()
+    lib.hipstr_region_results_free(h)
+    return records, summary
+
+
+def process_regions_staged(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_options=None):
+    """The same chain stage by stage from Python (what a caller writes against the individual entry points).
+    Genotypes `regions` [(chrom, start, stop, period, name)] from the BAM files; returns (records, summary) with
     records = [(chrom, pos, VCF record text)] in region order for the loci that were genotyped."""
     opt = options or Options()
     lib = capi.load()

@@ -736,6 +736,54 @@ hipstr_status_t hipstr_snp_vcf_region_sets(hipstr_snp_vcf_t* vcf, const char* ch
                                            int32_t* found, const int32_t** set_off, const uint32_t** snp_pos,
                                            const char** snp_base1, const char** snp_base2);
 
+/* --- the per-region driver: BAM files -> VCF records for a WINDOW of regions -----
+ * Replaces, for BAM input, BamProcessor::process_regions (src/bam_processor.cpp:521-617) -> SNPBamProcessor::process_reads
+ * (src/snp_bam_processor.cpp:36-118) -> GenotyperBamProcessor::analyze_reads_and_phasing / learn_stutter_model
+ * (src/genotyper_bam_processor.cpp:104-289) with the same decisions, re-arranged around window-sized device calls
+ * (hipstr_b200/host/region_driver.cpp): regions are read and filtered on all host threads, then ONE K7 launch (when a
+ * SNP VCF is given), ONE K4 call (unless use_def_stutter_model), the K6 left alignment of all reads and the lockstep
+ * genotyper (K1 K2 K3 K5, then K3b K5 for the records) run over all regions of the window together.
+ * Regions come in the order of the region file after orderRegions (src/region.cpp:53-55); chromosome sequences by name
+ * (upper or lower case, as FastaReader returns them).  The status of a region is 0 genotyped (record available),
+ * 1 longer than max_str_length, 2 within 50 bp of a contig end, 3 fewer than min_total_reads (informative) reads,
+ * 4 too many reads, 5 stutter model training failed, 6 genotyping failed, 7 chromosome sequence not supplied. */
+typedef struct {
+  hipstr_filter_options_t filter;      /* BamProcessor's read-filter knobs */
+  int32_t max_str_length;              /* MAX_STR_LENGTH       100 */
+  int32_t min_total_reads;             /* MIN_TOTAL_READS      100 */
+  int32_t max_total_haplotypes;        /* MAX_TOTAL_HAPLOTYPES 1000 */
+  int32_t max_flank_haplotypes;        /* MAX_FLANK_HAPLOTYPES 4 */
+  double  min_flank_freq;              /* MIN_FLANK_FREQ       0.01 */
+  int32_t max_em_iter;                 /* MAX_EM_ITER          100 */
+  double  abs_ll_converge;             /* ABS_LL_CONVERGE      0.01 */
+  double  frac_ll_converge;            /* FRAC_LL_CONVERGE     0.001 */
+  int32_t use_def_stutter_model;       /* --def-stutter-model: use def_stutter_model instead of EM training */
+  double  def_stutter_model[6];        /* 0.95 0.05 0.05 0.95 0.01 0.01 (hipstr_main.cpp:343) */
+  int32_t recalc_stutter_model;        /* recalc_stutter_model_ */
+  int32_t skip_padding;                /* SNPBamProcessor::SKIP_PADDING 15 */
+  int32_t n_haploid_chroms;            /* --haploid-chrs */
+  const char* const* haploid_chroms;
+  int32_t host_threads;                /* 0 = HIPSTR_HOST_THREADS / all cores */
+} hipstr_pipeline_options_t;
+typedef struct hipstr_region_results hipstr_region_results_t;
+void hipstr_pipeline_default_options(hipstr_pipeline_options_t* options);
+const char* hipstr_process_regions_last_error(void);
+hipstr_status_t hipstr_process_regions(hipstr_ctx_t* ctx, int32_t n_files, const char* const* bam_paths, hipstr_snp_vcf_t* snp_vcf,
+                                       int32_t n_chroms, const char* const* chrom_names, const char* const* chrom_seqs,
+                                       int32_t n_regions, const char* const* region_chrom, const int32_t* region_start,
+                                       const int32_t* region_stop, const int32_t* region_period, const char* const* region_name,
+                                       const hipstr_pipeline_options_t* options, const hipstr_vcf_options_t* vcf_options,
+                                       hipstr_region_results_t** out);
+int32_t hipstr_region_results_count(const hipstr_region_results_t* results);
+/* status of a region (see above); *pos = POS of its record, *n_reads = reads that passed the filters */
+int32_t hipstr_region_results_status(const hipstr_region_results_t* results, int32_t region, int32_t* pos, int32_t* n_reads);
+const char* hipstr_region_results_record(const hipstr_region_results_t* results, int32_t region);   /* "" unless status 0 */
+const char* hipstr_region_results_samples(const hipstr_region_results_t* results);   /* the VCF's sample columns, one per line */
+/* seconds6: ingestion (all threads, wall), SNP sets + K7, stutter models, left alignment, genotyping, records;
+ * counters4: alignments read, reads kept, reads with phase information, reads that failed to left-align */
+void hipstr_region_results_timing(const hipstr_region_results_t* results, double* seconds6, int64_t* counters4);
+void hipstr_region_results_free(hipstr_region_results_t* results);
+
 /* Wall-clock seconds this context has spent inside hipstr_trace_batch_host, by part:
  * {host lowering of the batch, ordering + uploads, kernel K5, downloads of the results} */
 void hipstr_trace_seconds(const hipstr_ctx_t* ctx, double* seconds4);

@@ -59,7 +59,8 @@ def files_of(sc, tmp_path, extra_regions=()):
     (5, 1, dict(require_paired=0, gls=1, pls=1, filters=1)),
     (6, 0, dict(recalc=1, remove_dups=0)),
 ])
-def test_bam_to_vcf_matches_reference(seed, def_stutter, kw, tmp_path):
+@pytest.mark.parametrize("driver", ["native", "staged"])
+def test_bam_to_vcf_matches_reference(seed, def_stutter, kw, driver, tmp_path):
     from hipstr_b200 import capi, pipeline
     sc = MultiScenario(seed, n_regions=4, n_fragments=220 if def_stutter else 600)
     extra = [("chr1", 2000, 2200, 4, 50.0, "TOO_LONG"), ("chr1", 10, 40, 3, 10.0, "CONTIG_END"), ("chr1", 7000, 7030, 3, 10.0, "NO_READS")]
@@ -72,7 +73,8 @@ def test_bam_to_vcf_matches_reference(seed, def_stutter, kw, tmp_path):
                            filter=dict(remove_pcr_dups=kw.get("remove_dups", 1), require_paired_reads=kw.get("require_paired", 1)))
     vcf_opt = dict(output_gls=kw.get("gls", 0), output_pls=kw.get("pls", 0), output_filters=kw.get("filters", 0))
     with capi.Context(0) as ctx:
-        records, summary = pipeline.process_regions(ctx, paths, pipeline.read_fasta(fasta), pipeline.read_regions(bed), opt, vcf_opt)
+        run = pipeline.process_regions if driver == "native" else pipeline.process_regions_staged
+        records, summary = run(ctx, paths, pipeline.read_fasta(fasta), pipeline.read_regions(bed), opt, vcf_opt)
     print(summary)
     assert [canon(r[2]) for r in records] == [canon(w) for w in want]
     if snp_vcf:
@@ -80,6 +82,8 @@ def test_bam_to_vcf_matches_reference(seed, def_stutter, kw, tmp_path):
     assert len(want) >= 2 and summary["too_long"] == 1 and summary["near_contig_end"] == 1 and summary["too_few_reads"] >= 1
     # the sample columns of the header line are the sorted sample names the records were written for
     assert header[-1].split("\t")[9:] == sorted({s for f in sc.files for _, s, _ in f["groups"]})
+    if driver == "native":
+        assert summary["samples"] == header[-1].split("\t")[9:]
 
 
 def write_snp_vcf(sc, tmp_path, seed=1):
