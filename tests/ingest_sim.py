@@ -18,7 +18,7 @@ def rand_seq(rng, n):
 
 
 class Scenario:
-    def __init__(self, seed, n_files=2, n_fragments=160, name_suffix=False, groups=None, tag=""):
+    def __init__(self, seed, n_files=2, n_fragments=160, name_suffix=False, groups=None, tag="", rgs_per_file=None):
         rng = self.rng = np.random.default_rng(seed)
         self.tag = tag
         period = int(rng.integers(2, 5))
@@ -36,6 +36,8 @@ class Scenario:
         self.files = []
         for f in range(n_files):
             own = [("f%dg%d" % (f, g), "S%d" % int(rng.integers(0, 3)), "L%d" % int(rng.integers(0, 2))) for g in range(int(rng.integers(1, 4)))]
+            if rgs_per_file:      # many samples: one per read group
+                own = [("f%dg%d" % (f, g), "S%03d" % (f * rgs_per_file + g), "L%d" % (g % 2)) for g in range(rgs_per_file)]
             self.files.append({"groups": groups[f] if groups else own, "records": []})
         for i in range(n_fragments):
             self.fragment(i)
@@ -186,13 +188,14 @@ class Scenario:
 class MultiScenario:
     """Several STRs on one chromosome: independent Scenarios laid end to end (same files and read groups)."""
 
-    def __init__(self, seed, n_regions=4, n_files=2, n_fragments=220):
+    def __init__(self, seed, n_regions=4, n_files=2, n_fragments=220, rgs_per_file=None, repeat=1):
         self.parts = []
         groups = None
         for k in range(n_regions):
-            part = Scenario(seed * 100 + k, n_files=n_files, n_fragments=n_fragments, groups=groups, tag="r%d_" % k)
+            part = Scenario(seed * 100 + k, n_files=n_files, n_fragments=n_fragments, groups=groups, tag="r%d_" % k, rgs_per_file=rgs_per_file)
             groups = [f["groups"] for f in part.files]
             self.parts.append(part)
+        self.parts = self.parts * repeat       # the same reads again further along the chromosome (cheap large inputs)
         self.offsets = np.cumsum([0] + [len(p.chrom) for p in self.parts])
         self.chrom = "".join(p.chrom for p in self.parts)
         self.regions = [(int(o) + p.region[0], int(o) + p.region[1], p.period) for o, p in zip(self.offsets, self.parts)]
