@@ -634,6 +634,8 @@ def load():
     lib.hipstr_region_results_samples.argtypes = [vp]
     lib.hipstr_region_results_timing.restype = None
     lib.hipstr_region_results_timing.argtypes = [vp, c_f64p, c_i64p]
+    lib.hipstr_region_results_genotyper_timing.restype = None
+    lib.hipstr_region_results_genotyper_timing.argtypes = [vp, c_f64p, c_i64p]
     lib.hipstr_region_results_free.restype = None
     lib.hipstr_region_results_free.argtypes = [vp]
     lib.hipstr_snp_vcf_last_error.restype = C.c_char_p

@@ -245,7 +245,7 @@ int BamFile::ref_id(const std::string& name) const {
   return -1;
 }
 
-int BamFile::read_record(BamRecord& rec) {
+int BamFile::read_record(BamRecord& rec, const int32_t* str_region) {
   unsigned char sz[4];
   const int rc = read(sz, 4);
   if (rc != 1) return rc;
@@ -265,7 +265,7 @@ int BamFile::read_record(BamRecord& rec) {
   rec.mate_ref_id = (int32_t)le32(d.data() + 20);
   rec.mate_pos = (int32_t)le32(d.data() + 24);
   const unsigned char* p = d.data() + 32;
-  rec.name.assign((const char*)p, strnlen((const char*)p, l_name));
+  const unsigned char* name_at = p;
   p += l_name;
   int32_t ref_len = 0;
   for (uint32_t c = 0; c < n_cigar; c++, p += 4) {
@@ -275,6 +275,15 @@ int BamFile::read_record(BamRecord& rec) {
     if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += (int32_t)(v >> 4);   // M D N = X consume the reference
   }
   rec.end_pos = (!(rec.flag & 0x4) && n_cigar > 0) ? pos + ref_len : pos + 1;   // bam_endpos
+  if (str_region) {   // the first two tests of read_and_filter_reads, which need none of the fields decoded below
+    if (rec.paired() && !rec.first_mate() && !rec.second_mate()) return 2;
+    if (rec.pos > str_region[1] || rec.end_pos < str_region[0]) {
+      if (!rec.paired() || rec.mate_pos == rec.pos) return 2;
+      if (rec.mate_pos > str_region[1]) return 2;
+      if (rec.mate_pos + (int32_t)l_seq + 100 < str_region[0]) return 2;
+    }
+  }
+  rec.name.assign((const char*)name_at, strnlen((const char*)name_at, l_name));
   rec.bases.resize(l_seq);
   for (uint32_t i = 0; i < l_seq; i++) rec.bases[i] = kBase[(p[i >> 1] >> ((~i & 1) << 2)) & 0xf];
   p += (l_seq + 1) / 2;
@@ -299,7 +308,8 @@ int BamFile::read_record(BamRecord& rec) {
   return 1;
 }
 
-bool BamFile::fetch(const std::string& chrom, int32_t start, int32_t end, int32_t file_index, std::vector<BamRecord>& out) {
+bool BamFile::fetch(const std::string& chrom, int32_t start, int32_t end, int32_t file_index, std::vector<BamRecord>& out,
+                    const int32_t* str_region) {
   const int tid = ref_id(chrom);
   if (tid < 0) return fail("chromosome " + chrom + " is not in the header of " + path_);
   if (start < 0) start = 0;
@@ -326,11 +336,11 @@ bool BamFile::fetch(const std::string& chrom, int32_t start, int32_t end, int32_
   for (const Chunk& c : merged) {
     if (!seek(std::max(c.beg, min_off))) return false;
     while (tell() < c.end) {
-      const int rc = read_record(rec);
+      const int rc = read_record(rec, str_region);
       if (rc < 0) return false;
       if (rc == 0) break;
       if (rec.ref_id != tid || rec.pos >= end) return true;   // coordinate-sorted: nothing further can overlap
-      if (rec.end_pos > start) {
+      if (rc == 1 && rec.end_pos > start) {
         rec.file = file_index;
         out.push_back(rec);
       }

@@ -60,8 +60,12 @@ class BamFile {
   const std::vector<uint32_t>& ref_lengths() const { return ref_lengths_; }
   const std::vector<BamReadGroup>& read_groups() const { return read_groups_; }   /* BamHeader::parse_read_groups */
   int ref_id(const std::string& name) const;
-  /* appends the records overlapping [start, end) of chromosome `chrom`, in file order */
-  bool fetch(const std::string& chrom, int32_t start, int32_t end, int32_t file_index, std::vector<BamRecord>& out);
+  /* appends the records overlapping [start, end) of chromosome `chrom`, in file order.  With `str_region` = {start, stop}
+   * of the STR group, records that read_and_filter_reads drops on sight -- paired reads that are neither first nor second
+   * mate, and reads that miss the STR whose mate cannot reach it either (src/bam_processor.cpp:191-203, decided by
+   * position, length, flag and mate position alone) -- are skipped BEFORE their name, bases, qualities and tags are decoded. */
+  bool fetch(const std::string& chrom, int32_t start, int32_t end, int32_t file_index, std::vector<BamRecord>& out,
+             const int32_t* str_region = nullptr);
 
  private:
   struct Chunk { uint64_t beg, end; };
@@ -86,7 +90,7 @@ class BamFile {
   int read(void* dst, size_t n);
   bool read_header();
   bool load_index(const std::string& path);
-  int read_record(BamRecord& rec);
+  int read_record(BamRecord& rec, const int32_t* str_region = nullptr);   /* 2 = skipped by the STR pre-filter */
 };
 
 }  // namespace hipstr

@@ -184,7 +184,9 @@ hipstr_status_t hipstr_left_align_reads_host(hipstr_ctx_t* ctx, int32_t n_loci, 
   std::vector<Trimmed> reads(R);
   std::vector<int> locus_of(R);
   std::vector<size_t> chrom_len(n_loci);
-  for (int l = 0; l < n_loci; l++) {
+  // every step below is per locus and independent: the loci of the window are spread over the host threads
+  parallel_for((size_t)n_loci, [&](size_t li) {
+    const int l = (int)li;
     chrom_len[l] = std::strlen(chrom_seq[l]);
     for (int r = raw->locus_read_off[l]; r < raw->locus_read_off[l + 1]; r++) {
       Trimmed& a = reads[r];
@@ -196,13 +198,16 @@ hipstr_status_t hipstr_left_align_reads_host(hipstr_ctx_t* ctx, int32_t n_loci, 
       for (int c = raw->cigar_off[r]; c < raw->cigar_off[r + 1]; c++) a.cigar.emplace_back(raw->cigar_type[c], raw->cigar_len[c]);
       if (trim_start && trim_stop) trim_alignment(a, trim_start[l], trim_stop[l]);
     }
-  }
+  });
   // which reads need a Needleman-Wunsch alignment: the first occurrence of every distinct sequence of a locus unless
   // its CIGAR is indel- and clip-free (round 1); later occurrences only when that first result was clipped (round 2)
   std::vector<std::map<std::string, std::vector<int> > > occurrences(n_loci);
-  for (int r = 0; r < R; r++)
-    if (!reads[r].bases.empty()) occurrences[locus_of[r]][reads[r].bases].push_back(r);
-  std::map<int, Aligned> realigned;   // read index -> result of realign()
+  parallel_for((size_t)n_loci, [&](size_t l) {
+    for (int r = raw->locus_read_off[l]; r < raw->locus_read_off[l + 1]; r++)
+      if (!reads[r].bases.empty()) occurrences[l][reads[r].bases].push_back(r);
+  });
+  std::vector<Aligned> realigned(R);          // read index -> result of realign()
+  std::vector<uint8_t> was_realigned(R, 0);
   hipstr_left_aligned* H = new hipstr_left_aligned();
   auto run_jobs = [&](const std::vector<int>& jobs) -> hipstr_status_t {
     if (jobs.empty()) return HIPSTR_OK;
@@ -233,8 +238,10 @@ hipstr_status_t hipstr_left_align_reads_host(hipstr_ctx_t* ctx, int32_t n_loci, 
                                                     stride, ops.data(), lens.data(), score.data());
     if (st != HIPSTR_OK) return st;
     H->nw_alignments += (int64_t)jobs.size();
-    for (size_t k = 0; k < jobs.size(); k++)
+    parallel_for(jobs.size(), [&](size_t k) {
       realigned[jobs[k]] = finish_realign(reads[jobs[k]], win_start[k], refs.data() + ref_off[k], &ops[k * (size_t)stride], lens[k]);
+      was_realigned[jobs[k]] = 1;
+    });
     return HIPSTR_OK;
   };
   std::vector<int> jobs;
@@ -246,20 +253,27 @@ hipstr_status_t hipstr_left_align_reads_host(hipstr_ctx_t* ctx, int32_t n_loci, 
   jobs.clear();
   for (int l = 0; l < n_loci; l++)
     for (const auto& kv : occurrences[l]) {
-      auto first = realigned.find(kv.second[0]);
-      if (first == realigned.end() || !first->second.ok || first->second.bases.size() == kv.first.size()) continue;
+      const int first = kv.second[0];
+      if (!was_realigned[first] || !realigned[first].ok || realigned[first].bases.size() == kv.first.size()) continue;
       for (size_t k = 1; k < kv.second.size(); k++)
         if (!matches_reference(reads[kv.second[k]])) jobs.push_back(kv.second[k]);
     }
   st = run_jobs(jobs);
   if (st != HIPSTR_OK) { delete H; return st; }
 
-  // the reference's loop, read by read (genotyper_bam_processor.cpp:50-93)
-  H->locus_read_off.push_back(0);
-  H->locus_sample_off.assign(raw->locus_sample_off, raw->locus_sample_off + n_loci + 1);
-  H->read_seq_off.push_back(0);
-  H->cigar_off.push_back(0);
-  for (int l = 0; l < n_loci; l++) {
+  // the reference's loop, read by read (genotyper_bam_processor.cpp:50-93), one locus per task; the per-locus pieces are
+  // then laid end to end
+  struct Piece {
+    std::vector<int32_t> seq_len, read_start, read_stop, cigar_n, cigar_len, sample_label, name_id, source;
+    std::vector<char> bases, quals, cigar_type;
+    std::vector<double> log_p1, log_p2;
+    std::vector<uint8_t> rev_strand, use_for_haps;
+    int64_t failed = 0;
+  };
+  std::vector<Piece> pieces(n_loci);
+  parallel_for((size_t)n_loci, [&](size_t li) {
+    const int l = (int)li;
+    Piece& P = pieces[l];
     std::map<std::string, Aligned> seq_to_aln;   // the alignment every later read with this sequence reuses
     for (int r = raw->locus_read_off[l]; r < raw->locus_read_off[l + 1]; r++) {
       const Trimmed& a = reads[r];
@@ -274,27 +288,41 @@ hipstr_status_t hipstr_left_align_reads_host(hipstr_ctx_t* ctx, int32_t n_loci, 
       } else {
         if (matches_reference(a)) result = convert_alignment(a, chrom_seq[l]);
         else {
-          auto it = realigned.find(r);
-          if (it == realigned.end() || !it->second.ok) { H->fail_count++; continue; }
-          result = it->second;
+          if (!was_realigned[r] || !realigned[r].ok) { P.failed++; continue; }
+          result = realigned[r];
         }
         seq_to_aln[a.bases] = result;
       }
-      H->bases.insert(H->bases.end(), result.bases.begin(), result.bases.end());
-      H->quals.insert(H->quals.end(), result.quals.begin(), result.quals.end());
-      H->read_seq_off.push_back((int32_t)H->bases.size());
-      H->read_start.push_back(result.start);
-      H->read_stop.push_back(result.stop);
-      for (const auto& op : result.cigar) { H->cigar_type.push_back(op.first); H->cigar_len.push_back(op.second); }
-      H->cigar_off.push_back((int32_t)H->cigar_type.size());
-      H->sample_label.push_back(raw->sample_label[r]);
-      H->name_id.push_back(raw->name_id[r]);
-      H->log_p1.push_back(raw->log_p1[r]);
-      H->log_p2.push_back(raw->log_p2[r]);
-      H->rev_strand.push_back(raw->rev_strand ? raw->rev_strand[r] : 0);
-      H->use_for_haps.push_back(raw->use_for_haps ? raw->use_for_haps[r] : 1);
-      H->source.push_back(r);
+      P.bases.insert(P.bases.end(), result.bases.begin(), result.bases.end());
+      P.quals.insert(P.quals.end(), result.quals.begin(), result.quals.end());
+      P.seq_len.push_back((int32_t)result.bases.size());
+      P.read_start.push_back(result.start);
+      P.read_stop.push_back(result.stop);
+      for (const auto& op : result.cigar) { P.cigar_type.push_back(op.first); P.cigar_len.push_back(op.second); }
+      P.cigar_n.push_back((int32_t)result.cigar.size());
+      P.sample_label.push_back(raw->sample_label[r]);
+      P.name_id.push_back(raw->name_id[r]);
+      P.log_p1.push_back(raw->log_p1[r]);
+      P.log_p2.push_back(raw->log_p2[r]);
+      P.rev_strand.push_back(raw->rev_strand ? raw->rev_strand[r] : 0);
+      P.use_for_haps.push_back(raw->use_for_haps ? raw->use_for_haps[r] : 1);
+      P.source.push_back(r);
     }
+  });
+  H->locus_read_off.push_back(0);
+  H->locus_sample_off.assign(raw->locus_sample_off, raw->locus_sample_off + n_loci + 1);
+  H->read_seq_off.push_back(0);
+  H->cigar_off.push_back(0);
+  auto append = [](auto& dst, const auto& src) { dst.insert(dst.end(), src.begin(), src.end()); };
+  for (int l = 0; l < n_loci; l++) {
+    const Piece& P = pieces[l];
+    for (int32_t n : P.seq_len) H->read_seq_off.push_back(H->read_seq_off.back() + n);
+    for (int32_t n : P.cigar_n) H->cigar_off.push_back(H->cigar_off.back() + n);
+    append(H->bases, P.bases); append(H->quals, P.quals); append(H->cigar_type, P.cigar_type); append(H->cigar_len, P.cigar_len);
+    append(H->read_start, P.read_start); append(H->read_stop, P.read_stop); append(H->sample_label, P.sample_label);
+    append(H->name_id, P.name_id); append(H->log_p1, P.log_p1); append(H->log_p2, P.log_p2); append(H->rev_strand, P.rev_strand);
+    append(H->use_for_haps, P.use_for_haps); append(H->source, P.source);
+    H->fail_count += P.failed;
     H->locus_read_off.push_back((int32_t)H->read_start.size());
     H->haploid.push_back(raw->haploid ? raw->haploid[l] : 0);
   }

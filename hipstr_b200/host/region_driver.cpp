@@ -53,6 +53,8 @@ struct hipstr_region_results {
   std::vector<std::string> samples;
   std::string sample_text;
   double seconds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double genotyper_seconds[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // hipstr_genotyper_timing of the window
+  int64_t genotyper_stats[3] = {0, 0, 0};                       // alignments, traces, rounds
   int64_t counters[4] = {0, 0, 0, 0};   // alignments read, reads kept, reads with phase information, left-alignment failures
 };
 
@@ -149,8 +151,10 @@ hipstr_status_t hipstr_process_regions(hipstr_ctx_t* ctx, int32_t n_files, const
           }
         std::vector<BamRecord> records;
         const int32_t dist = opt->filter.max_mate_dist;
+        const int32_t str_region[2] = {start, stop};
         for (size_t f = 0; f < files.size(); f++)
-          if (!files[f]->fetch(region_chrom[i], start < dist ? 0 : start - dist, stop + dist, (int32_t)f, records)) throw hipstr::FilterError(files[f]->error());
+          if (!files[f]->fetch(region_chrom[i], start < dist ? 0 : start - dist, stop + dist, (int32_t)f, records, str_region))
+            throw hipstr::FilterError(files[f]->error());
         n_records += (int64_t)records.size();
         std::unique_ptr<Locus> L(new Locus());
         L->region = i;
@@ -250,7 +254,9 @@ hipstr_status_t hipstr_process_regions(hipstr_ctx_t* ctx, int32_t n_files, const
       b.snp_base1 = base1.c_str(); b.snp_base2 = base2.c_str();
       std::vector<double> p1(entry_set.size()), p2(entry_set.size());
       std::vector<int32_t> counts(entry_set.size() * 4);
+      R->seconds[6] = now_s() - t;           // SNP sets + packing the reads of the window
       hipstr_status_t st = hipstr_snp_phasing_batch_host(ctx, &b, p1.data(), p2.data(), counts.data());
+      R->seconds[7] = now_s() - t - R->seconds[6];   // the K7 call (uploads, launch, downloads)
       if (st != HIPSTR_OK) { g_driver_error = hipstr_last_error(ctx); return st; }
       for (size_t e = 0; e < entry_owner.size(); e++) {
         entry_owner[e].first->log_p1[entry_owner[e].second] = p1[e];
@@ -409,6 +415,12 @@ hipstr_status_t hipstr_process_regions(hipstr_ctx_t* ctx, int32_t n_files, const
     else res.status = GENOTYPING_FAILED;
   }
   R->seconds[5] = now_s() - t;
+  hipstr_genotyper_timing(g, R->genotyper_seconds);
+  {
+    int32_t rounds = 0;
+    hipstr_genotyper_stats(g, &R->genotyper_stats[0], &R->genotyper_stats[1], &rounds);
+    R->genotyper_stats[2] = rounds;
+  }
   hipstr_genotyper_destroy(g);
   hipstr_left_aligned_free(aligned);
   *out = R.release();
@@ -426,10 +438,15 @@ const char* hipstr_region_results_record(const hipstr_region_results_t* r, int32
   return r && region >= 0 && region < (int32_t)r->regions.size() ? r->regions[region].text.c_str() : nullptr;
 }
 const char* hipstr_region_results_samples(const hipstr_region_results_t* r) { return r ? r->sample_text.c_str() : nullptr; }
-void hipstr_region_results_timing(const hipstr_region_results_t* r, double* seconds6, int64_t* counters4) {
+void hipstr_region_results_timing(const hipstr_region_results_t* r, double* seconds6 /* [8] */, int64_t* counters4) {
   if (!r) return;
-  if (seconds6) std::memcpy(seconds6, r->seconds, 6 * sizeof(double));
+  if (seconds6) std::memcpy(seconds6, r->seconds, 8 * sizeof(double));
   if (counters4) std::memcpy(counters4, r->counters, 4 * sizeof(int64_t));
+}
+void hipstr_region_results_genotyper_timing(const hipstr_region_results_t* r, double* seconds9, int64_t* stats3) {
+  if (!r) return;
+  if (seconds9) std::memcpy(seconds9, r->genotyper_seconds, sizeof(r->genotyper_seconds));
+  if (stats3) std::memcpy(stats3, r->genotyper_stats, sizeof(r->genotyper_stats));
 }
 void hipstr_region_results_free(hipstr_region_results_t* r) { delete r; }
 

@@ -121,10 +121,15 @@ def process_regions(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_optio
         summary[STATUS[status]] += 1
         if status == 0:
             records.append((r[0], pos.value, lib.hipstr_region_results_record(h, i).decode()))
-    sec, cnt = np.zeros(6), np.zeros(4, np.int64)
+    sec, cnt = np.zeros(8), np.zeros(4, np.int64)
     lib.hipstr_region_results_timing(h, ptr(sec, capi.c_f64p), ptr(cnt, capi.c_i64p))
-    summary["seconds"] = dict(zip(("ingest", "phasing", "stutter", "left_align", "genotype", "records"), (float(x) for x in sec)))
+    summary["seconds"] = dict(zip(("ingest", "phasing", "stutter", "left_align", "genotype", "records", "phasing_pack", "phasing_k7_call"), (float(x) for x in sec)))
     summary["alignments_read"], summary["reads_kept"], summary["phased_reads"], summary["left_align_failed"] = (int(x) for x in cnt)
+    gsec, gst = np.zeros(9), np.zeros(3, np.int64)
+    lib.hipstr_region_results_genotyper_timing(h, ptr(gsec, capi.c_f64p), ptr(gst, capi.c_i64p))
+    summary["genotyper_seconds"] = dict(zip(("construct", "decide", "trace_device", "trace_host", "align", "posteriors", "vcf", "align_pack",
+                                             "align_unpack"), (round(float(x), 4) for x in gsec)))
+    summary["alignments"], summary["traces"], summary["rounds"] = (int(x) for x in gst)
     summary["samples"] = lib.hipstr_region_results_samples(h).decode().splitlines()
     lib.hipstr_region_results_free(h)
     return records, summary

@@ -779,9 +779,12 @@ int32_t hipstr_region_results_count(const hipstr_region_results_t* results);
 int32_t hipstr_region_results_status(const hipstr_region_results_t* results, int32_t region, int32_t* pos, int32_t* n_reads);
 const char* hipstr_region_results_record(const hipstr_region_results_t* results, int32_t region);   /* "" unless status 0 */
 const char* hipstr_region_results_samples(const hipstr_region_results_t* results);   /* the VCF's sample columns, one per line */
-/* seconds6: ingestion (all threads, wall), SNP sets + K7, stutter models, left alignment, genotyping, records;
+/* seconds8: ingestion (all threads, wall), SNP sets + K7, stutter models, left alignment, genotyping, records, and of the
+ * second: packing the window's reads and SNP sets, the K7 call itself;
  * counters4: alignments read, reads kept, reads with phase information, reads that failed to left-align */
-void hipstr_region_results_timing(const hipstr_region_results_t* results, double* seconds6, int64_t* counters4);
+void hipstr_region_results_timing(const hipstr_region_results_t* results, double* seconds8, int64_t* counters4);
+/* hipstr_genotyper_timing / hipstr_genotyper_stats of the window's genotyper: seconds9 as there, stats3 = alignments, traces, rounds */
+void hipstr_region_results_genotyper_timing(const hipstr_region_results_t* results, double* seconds9, int64_t* stats3);
 void hipstr_region_results_free(hipstr_region_results_t* results);
 
 /* Wall-clock seconds this context has spent inside hipstr_trace_batch_host, by part:
