@@ -251,7 +251,8 @@ int BamFile::read_record(BamRecord& rec, const int32_t* str_region) {
   if (rc != 1) return rc;
   const uint32_t block_size = le32(sz);
   if (block_size < 32) { fail("invalid record in " + path_); return -1; }
-  std::vector<unsigned char> d(block_size);
+  std::vector<unsigned char>& d = record_;   // reused from record to record
+  if (d.size() < block_size) d.resize(block_size);
   if (read(d.data(), block_size) != 1) { fail("truncated record in " + path_); return -1; }
   const int32_t ref = (int32_t)le32(d.data()), pos = (int32_t)le32(d.data() + 4);
   const uint32_t l_name = d[8], n_cigar = le16(d.data() + 12), l_seq = le32(d.data() + 16);
@@ -342,7 +343,7 @@ bool BamFile::fetch(const std::string& chrom, int32_t start, int32_t end, int32_
       if (rec.ref_id != tid || rec.pos >= end) return true;   // coordinate-sorted: nothing further can overlap
       if (rc == 1 && rec.end_pos > start) {
         rec.file = file_index;
-        out.push_back(rec);
+        out.push_back(std::move(rec));
       }
     }
   }

@@ -81,6 +81,7 @@ class BamFile {
   uint64_t next_addr_ = 0;             /* file offset of the block after it */
   std::vector<unsigned char> block_;
   size_t block_at_ = 0;
+  std::vector<unsigned char> record_;  /* the bytes of the record being decoded */
 
   bool fail(const std::string& why) { error_ = why; return false; }
   bool load_block(uint64_t addr);
