@@ -232,6 +232,27 @@ class SnpVcf:
     __del__ = close
 
 
+def vcf_header(reference_path, full_command, contigs, samples, **options):
+    """hipstr_vcf_header: contigs = [(name, length)] in FASTA order; options override hipstr_vcf_default_options."""
+    lib = load()
+    opt = VcfOptions()
+    lib.hipstr_vcf_default_options(C.byref(opt))
+    for k, v in options.items():
+        setattr(opt, k, v)
+    mk = lambda xs: (C.c_char_p * max(len(xs), 1))(*[x.encode() for x in xs])
+    lens = np.array([c[1] for c in contigs] + [0], np.int64)
+    cap = 1 << 16
+    while True:
+        buf = C.create_string_buffer(cap)
+        n = lib.hipstr_vcf_header(reference_path.encode(), full_command.encode(), len(contigs), mk([c[0] for c in contigs]), ptr(lens, c_i64p),
+                                  len(samples), mk(list(samples)), C.byref(opt), cap, buf)
+        if n > 0:
+            return buf.raw[:n].decode()
+        if n == 0:
+            raise HipstrError(-2, "vcf_header")
+        cap = -n
+
+
 class BamReader:
     """hipstr_bam_reader_t: BAM files (+ .bai) read region by region, file after file."""
 
@@ -618,6 +639,9 @@ def load():
     lib.hipstr_alignment_filters.restype = C.c_int32
     lib.hipstr_alignment_filters.argtypes = [C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, c_i32p, C.c_char_p,
                                              C.c_int32, c_i32p, c_f64p]
+    lib.hipstr_vcf_header.restype = C.c_int64
+    lib.hipstr_vcf_header.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, cpp, c_i64p, C.c_int32, cpp, C.POINTER(VcfOptions), C.c_int64,
+                                      C.c_char_p]
     lib.hipstr_pipeline_default_options.restype = None
     lib.hipstr_pipeline_default_options.argtypes = [C.POINTER(PipelineOptions)]
     lib.hipstr_process_regions_last_error.restype = C.c_char_p

@@ -589,3 +589,94 @@ hipstr_status_t hipstr_genotyper_emit_records(const hipstr_genotyper_t* g, const
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// The VCF header (Genotyper::get_vcf_header, src/genotyper.cpp:253-331): the field dictionary of the records that
+// format_record writes, as a table.  The texts are part of the file format the reference emits.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct FieldDef { const char* id; const char* number; const char* type; const char* text; };
+const FieldDef kInfoFields[] = {
+    {"INFRAME_PGEOM", "1", "Float", "Parameter for in-frame geometric step size distribution"},
+    {"INFRAME_UP", "1", "Float", "Probability that stutter causes an in-frame increase in obs. STR size"},
+    {"INFRAME_DOWN", "1", "Float", "Probability that stutter causes an in-frame decrease in obs. STR size"},
+    {"OUTFRAME_PGEOM", "1", "Float", "Parameter for out-of-frame geometric step size distribution"},
+    {"OUTFRAME_UP", "1", "Float", "Probability that stutter causes an out-of-frame increase in read's STR size"},
+    {"OUTFRAME_DOWN", "1", "Float", "Probability that stutter causes an out-of-frame decrease in read's STR size"},
+    {"BPDIFFS", "A", "Integer", "Base pair difference of each alternate allele from the reference allele"},
+    {"START", "1", "Integer", "Inclusive start coodinate for the repetitive portion of the reference allele"},
+    {"END", "1", "Integer", "Inclusive end coordinate for the repetitive portion of the reference allele"},
+    {"PERIOD", "1", "Integer", "Length of STR motif"},
+    {"AN", "1", "Integer", "Total number of alleles in called genotypes"},
+    {"REFAC", "1", "Integer", "Reference allele count"},
+    {"AC", "A", "Integer", "Alternate allele counts"},
+    {"NSKIP", "1", "Integer", "Number of samples not genotyped due to various issues"},
+    {"NFILT", "1", "Integer", "Number of samples whose genotypes were filtered due to various issues"},
+    {"DP", "1", "Integer", "Total number of valid reads used to genotype all samples"},
+    {"DSNP", "1", "Integer", "Total number of reads with SNP phasing information"},
+    {"DSTUTTER", "1", "Integer", "Total number of reads with a stutter indel in the STR region"},
+    {"DFLANKINDEL", "1", "Integer", "Total number of reads with an indel in the regions flanking the STR"},
+};
+const FieldDef kHaplotypeInfoFields[] = {
+    {"LFLANKS", ".", "String", "Comma-separated sequence(s) of flank to the  left of the repeat. Only output if 1 or more non-ref  left flanks were detected"},
+    {"RFLANKS", ".", "String", "Comma-separated sequence(s) of flank to the right of the repeat. Only output if 1 or more non-ref right flanks were detected"},
+};
+const char kBiasTail[] = "where 0 is no bias and more negative values are increasingly biased. For homozygous genotypes, this can be negative if the haplotypes are heterozygous";
+const FieldDef kFormatFields[] = {
+    {"GT", "1", "String", "Genotype"},
+    {"GB", "1", "String", "Base pair differences of genotype from reference"},
+    {"Q", "1", "Float", "Posterior probability of unphased genotype"},
+    {"PQ", "1", "Float", "Posterior probability of phased genotype"},
+    {"DP", "1", "Integer", "Number of valid reads used for sample's genotype"},
+    {"DSNP", "1", "Integer", "Number of reads with SNP phasing information"},
+    {"PSNP", "1", "String", "Number of reads with SNPs supporting each haploid genotype"},
+    {"PDP", "1", "String", "Fractional reads supporting each haploid genotype"},
+    {"GLDIFF", "1", "Float", "Difference in likelihood between the reported and next best genotypes"},
+    {"DSTUTTER", "1", "Integer", "Number of reads with a stutter indel in the STR region"},
+    {"DFLANKINDEL", "1", "Integer", "Number of reads with an indel in the regions flanking the STR"},
+    {"AB", "1", "Float", "log10 of the allele bias pvalue, "},       // + kBiasTail
+    {"FS", "1", "Float", "log10 of the strand bias pvalue from Fisher's exact test, "},
+    {"DAB", "1", "Integer", "Number of reads used in the AB and FS calculations"},
+};
+const FieldDef kHaplotypeFormatFields[] = {
+    {"HQ", "1", "Float", "Posterior probability of unphased haplotypes. Only output if 1 or more non-ref flanks were detected"},
+    {"PHQ", "1", "Float", "Posterior probability of   phased haplotypes. Only output if 1 or more non-ref flanks were detected"},
+    {"LFGT", "1", "String", "Genotype of  left flank with corresponding sequences reported in LFLANKS. Only output if 1 or more non-ref  left flanks were detected"},
+    {"RFGT", "1", "String", "Genotype of right flank with corresponding sequences reported in RFLANKS. Only output if 1 or more non-ref right flanks were detected"},
+};
+void put_field(std::ostringstream& out, const char* kind, const FieldDef& f, const char* tail = "") {
+  out << "##" << kind << "=<ID=" << f.id << ",Number=" << f.number << ",Type=" << f.type << ",Description=\"" << f.text << tail << "\">\n";
+}
+}  // namespace
+
+extern "C" int64_t hipstr_vcf_header(const char* reference_path, const char* full_command, int32_t n_contigs, const char* const* contig_names,
+                                     const int64_t* contig_lengths, int32_t n_samples, const char* const* sample_names,
+                                     const hipstr_vcf_options_t* o, int64_t cap, char* out_text) {
+  if (!reference_path || !full_command || n_contigs < 0 || n_samples < 0 || !o || (n_contigs > 0 && (!contig_names || !contig_lengths)) ||
+      (n_samples > 0 && !sample_names))
+    return 0;
+  std::ostringstream out;
+  out << "##fileformat=VCFv4.1\n##command=" << full_command << "\n##reference=" << reference_path << "\n";
+  for (int c = 0; c < n_contigs; c++) out << "##contig=<ID=" << contig_names[c] << ",length=" << contig_lengths[c] << ">\n";
+  for (const FieldDef& f : kInfoFields) put_field(out, "INFO", f);
+  if (o->output_haplotype_data)
+    for (const FieldDef& f : kHaplotypeInfoFields) put_field(out, "INFO", f);
+  for (const FieldDef& f : kFormatFields) put_field(out, "FORMAT", f, (std::strcmp(f.id, "AB") == 0 || std::strcmp(f.id, "FS") == 0) ? kBiasTail : "");
+  if (o->output_haplotype_data)
+    for (const FieldDef& f : kHaplotypeFormatFields) put_field(out, "FORMAT", f);
+  if (o->output_allreads) put_field(out, "FORMAT", FieldDef{"ALLREADS", "1", "String", "Base pair difference observed in each read's Needleman-Wunsch alignment"});
+  if (o->output_mallreads)
+    put_field(out, "FORMAT", FieldDef{"MALLREADS", "1", "String", "Maximum likelihood bp diff in each read based on haplotype alignments for reads that span the repeat region by at least 5 base pairs"});
+  if (o->output_gls) put_field(out, "FORMAT", FieldDef{"GL", "G", "Float", "log10 genotype likelihoods"});
+  if (o->output_pls) put_field(out, "FORMAT", FieldDef{"PL", "G", "Integer", "Phred-scaled genotype likelihoods"});
+  if (o->output_phased_gls)
+    put_field(out, "FORMAT", FieldDef{"PHASEDGL", ".", "Float", "log10 genotype likelihood for each phased genotype. Value for phased genotype X|Y is stored at a 0-based index of X*A + Y, where A is the number of alleles. Not applicable to haploid genotypes"});
+  if (o->output_filters) put_field(out, "FORMAT", FieldDef{"FILTER", "1", "String", "Reason for filtering the current call, or PASS if the call was not filtered"});
+  out << "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT";
+  for (int s = 0; s < n_samples; s++) out << "\t" << sample_names[s];
+  out << "\n";
+  const std::string text = out.str();
+  if (!out_text || (int64_t)text.size() + 1 > cap) return -(int64_t)text.size() - 1;
+  std::memcpy(out_text, text.c_str(), text.size() + 1);
+  return (int64_t)text.size();
+}

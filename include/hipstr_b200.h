@@ -586,6 +586,12 @@ int32_t hipstr_left_align_one(int32_t pos, int32_t end_pos, const char* bases, c
  * arrive grouped.  A path ending in ".gz" is written as BGZF (what the reference's
  * bgzfostream produces), anything else as plain text.  The C++ class with the reference's
  * method names is hipstr::VCFWriter (hipstr_b200/host/vcf_writer.h). */
+/* Genotyper::get_vcf_header (src/genotyper.cpp:253-331): the header text of the STR VCF for these options -- file format,
+ * ##command, ##reference, one ##contig line per FASTA sequence (FastaReader::write_all_contigs_to_vcf), the INFO / FORMAT
+ * dictionary and the #CHROM line with the sample columns.  Returns the text length, or -(needed capacity). */
+int64_t hipstr_vcf_header(const char* reference_path, const char* full_command, int32_t n_contigs, const char* const* contig_names,
+                          const int64_t* contig_lengths, int32_t n_samples, const char* const* sample_names,
+                          const hipstr_vcf_options_t* options, int64_t cap, char* out_text);
 typedef struct hipstr_vcf_writer hipstr_vcf_writer_t;
 /* feed the records of hipstr_genotyper_write_vcf to a writer, in locus order (VCFWriter::add_vcf_record) */
 hipstr_status_t hipstr_genotyper_emit_records(const hipstr_genotyper_t* g, const hipstr_vcf_loci_t* loci,

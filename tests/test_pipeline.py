@@ -127,3 +127,21 @@ def test_snp_sets_match_create_snp_trees(seed, tmp_path):
                 total += len(pos)
         assert vcf.region_sets("chr3", 1, 1000) is None
     assert total > 60
+
+
+@needs_ref
+@pytest.mark.parametrize("flags", [dict(), dict(gls=1, pls=1, filters=1)])
+def test_vcf_header_matches_reference(flags, tmp_path):
+    """hipstr_vcf_header against the header the reference program writes (Genotyper::get_vcf_header through
+    GenotyperBamProcessor::init_output_vcf); an empty region file, so no GPU is involved."""
+    from hipstr_b200 import capi
+    sc = MultiScenario(9, n_regions=1, n_fragments=5)
+    paths, fasta, bed = files_of(sc, tmp_path)
+    open(bed, "w").close()
+    header, records = run_reference(paths, fasta, bed, str(tmp_path / "ref.vcf"), 1, **flags)
+    assert not records
+    contigs = [("chr1", len(sc.chrom)), ("chr2", 5000), ("chr1_KI1_alt", 3000)]
+    samples = sorted({s for f in sc.files for _, s, _ in f["groups"]})
+    got = capi.vcf_header(fasta, "harness", contigs, samples, output_gls=flags.get("gls", 0), output_pls=flags.get("pls", 0),
+                          output_filters=flags.get("filters", 0))
+    assert got == "\n".join(header) + "\n"
