@@ -312,3 +312,20 @@ def process_regions_staged(ctx, bam_paths, chrom_seqs, regions, options=None, vc
     g.close()
     aligned.close()
     return out, summary
+
+
+def write_vcf_file(path, header_text, records):
+    """The records of process_regions through hipstr::VCFWriter (vcf_writer.h: POS-ordered heap; BGZF when the path ends in
+    .gz, as the reference always writes) -- VCFWriter::open / write_header / add_vcf_record / close."""
+    lib = capi.load()
+    w = lib.hipstr_vcf_writer_open(path.encode())
+    if not w:
+        raise IOError("cannot create " + path)
+    try:
+        if lib.hipstr_vcf_writer_header(w, header_text.encode()) != 0:
+            raise IOError("writing the header of %s failed" % path)
+        for chrom, pos, text in records:
+            if lib.hipstr_vcf_writer_add_record(w, chrom.encode(), pos, text.encode()) != 0:
+                raise IOError("writing a record of %s failed" % path)
+    finally:
+        lib.hipstr_vcf_writer_close(w)

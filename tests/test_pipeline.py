@@ -84,6 +84,13 @@ def test_bam_to_vcf_matches_reference(seed, def_stutter, kw, driver, tmp_path):
     assert header[-1].split("\t")[9:] == sorted({s for f in sc.files for _, s, _ in f["groups"]})
     if driver == "native":
         assert summary["samples"] == header[-1].split("\t")[9:]
+        # the whole FILE: header + records through hipstr::VCFWriter (BGZF), against the reference program's output file
+        import gzip
+        contigs = [("chr1", len(sc.chrom)), ("chr2", 5000), ("chr1_KI1_alt", 3000)]
+        out_path = str(tmp_path / "ours.vcf.gz")
+        pipeline.write_vcf_file(out_path, capi.vcf_header(fasta, "harness", contigs, summary["samples"], **vcf_opt), records)
+        with gzip.open(out_path, "rt") as a, gzip.open(str(tmp_path / "ref.vcf"), "rt") as b:
+            assert canon(a.read()) == canon(b.read())
 
 
 def write_snp_vcf(sc, tmp_path, seed=1):
