@@ -43,6 +43,28 @@ struct Locus {
   bool has_model = false;
 };
 
+/* alignments of one region packed into flat arrays (built per region on the host threads, then concatenated) */
+struct AlnPiece {
+  std::vector<int32_t> pos, end, seq_len, cigar_n, cigar_len, group_n;
+  std::string bases, quals, cigar_type;
+  void add(const BamRecord& a) {
+    pos.push_back(a.pos); end.push_back(a.end_pos);
+    bases += a.bases; quals += a.quals;
+    seq_len.push_back((int32_t)a.bases.size());
+    for (const auto& op : a.cigar) { cigar_type += op.first; cigar_len.push_back(op.second); }
+    cigar_n.push_back((int32_t)a.cigar.size());
+  }
+  void append_to(std::vector<int32_t>& all_pos, std::vector<int32_t>& all_end, std::vector<int32_t>& seq_off, std::string& all_bases,
+                 std::string& all_quals, std::vector<int32_t>& cigar_off, std::string& all_types, std::vector<int32_t>& all_lens) const {
+    all_pos.insert(all_pos.end(), pos.begin(), pos.end());
+    all_end.insert(all_end.end(), end.begin(), end.end());
+    for (int32_t n : seq_len) seq_off.push_back(seq_off.back() + n);
+    for (int32_t n : cigar_n) cigar_off.push_back(cigar_off.back() + n);
+    all_bases += bases; all_quals += quals; all_types += cigar_type;
+    all_lens.insert(all_lens.end(), cigar_len.begin(), cigar_len.end());
+  }
+};
+
 thread_local std::string g_driver_error;
 
 }  // namespace
@@ -212,15 +234,11 @@ hipstr_status_t hipstr_process_regions(hipstr_ctx_t* ctx, int32_t n_files, const
     std::vector<uint32_t> snp_pos;
     std::string bases, quals, cigar_type, base1, base2;
     std::vector<std::pair<Locus*, size_t> > entry_owner;
-    auto add = [&](const BamRecord& a) {
-      aln_pos.push_back(a.pos); aln_end.push_back(a.end_pos);
-      bases += a.bases; quals += a.quals;
-      aln_seq_off.push_back((int32_t)bases.size());
-      for (const auto& op : a.cigar) { cigar_type += op.first; cigar_len.push_back(op.second); }
-      aln_cigar_off.push_back((int32_t)cigar_type.size());
-    };
-    for (Locus* L : loci) {
-      const int i = L->region;
+    // the SNP sets of every region (binary searches on the loaded VCF; the handle's result buffers are not shared)
+    struct Sets { bool found = false; std::vector<int32_t> off; std::vector<uint32_t> pos; std::string b1, b2; };
+    std::vector<Sets> sets(loci.size());
+    for (size_t l = 0; l < loci.size(); l++) {
+      const int i = loci[l]->region;
       const int32_t start = region_start[i], stop = region_stop[i], dist = opt->filter.max_mate_dist;
       int32_t found = 0;
       const int32_t* off; const uint32_t* pos; const char* b1; const char* b2;
@@ -228,19 +246,42 @@ hipstr_status_t hipstr_process_regions(hipstr_ctx_t* ctx, int32_t n_files, const
                                                       opt->skip_padding, &found, &off, &pos, &b1, &b2);
       if (st != HIPSTR_OK) return st;
       if (!found) continue;    // chromosome not in the VCF: no SNP information for this region
-      const int32_t set_base = (int32_t)set_off.size() - 1, snp_base = (int32_t)snp_pos.size();
-      for (int s = 0; s < n_vcf; s++) set_off.push_back(snp_base + off[s + 1]);
-      snp_pos.insert(snp_pos.end(), pos, pos + off[n_vcf]);
-      base1.append(b1, (size_t)off[n_vcf]);
-      base2.append(b2, (size_t)off[n_vcf]);
-      for (size_t r = 0; r < L->reads.size(); r++) {
-        add(*L->reads[r]);
-        if (L->mates[r]) add(*L->mates[r]);
-        entry_aln_off.push_back((int32_t)aln_pos.size());
-        auto vi = vcf_index.find(L->kept.rg_names[L->label[r]]);
-        entry_set.push_back(vi == vcf_index.end() ? -1 : set_base + vi->second);
-        entry_owner.emplace_back(L, r);
+      sets[l].found = true;
+      sets[l].off.assign(off, off + n_vcf + 1);
+      sets[l].pos.assign(pos, pos + off[n_vcf]);
+      sets[l].b1.assign(b1, (size_t)off[n_vcf]);
+      sets[l].b2.assign(b2, (size_t)off[n_vcf]);
+    }
+    // the reads (+ mates) of every region, packed per region on the host threads and then laid end to end
+    std::vector<AlnPiece> pieces(loci.size());
+    std::vector<std::vector<int32_t> > piece_sets(loci.size());
+    hipstr::parallel_for(loci.size(), [&](size_t l) {
+      if (!sets[l].found) return;
+      const Locus* L = loci[l];
+      std::vector<int32_t> sample_set(L->kept.rg_names.size());
+      for (size_t g = 0; g < sample_set.size(); g++) {
+        auto vi = vcf_index.find(L->kept.rg_names[g]);
+        sample_set[g] = vi == vcf_index.end() ? -1 : vi->second;
       }
+      for (size_t r = 0; r < L->reads.size(); r++) {
+        pieces[l].add(*L->reads[r]);
+        if (L->mates[r]) pieces[l].add(*L->mates[r]);
+        pieces[l].group_n.push_back(L->mates[r] ? 2 : 1);
+        piece_sets[l].push_back(sample_set[L->label[r]]);
+      }
+    });
+    for (size_t l = 0; l < loci.size(); l++) {
+      if (!sets[l].found) continue;
+      const int32_t set_base = (int32_t)set_off.size() - 1, snp_base = (int32_t)snp_pos.size();
+      for (int sm = 0; sm < n_vcf; sm++) set_off.push_back(snp_base + sets[l].off[sm + 1]);
+      snp_pos.insert(snp_pos.end(), sets[l].pos.begin(), sets[l].pos.end());
+      base1 += sets[l].b1;
+      base2 += sets[l].b2;
+      const AlnPiece& P = pieces[l];
+      for (int32_t n : P.group_n) entry_aln_off.push_back(entry_aln_off.back() + n);
+      for (int32_t v : piece_sets[l]) entry_set.push_back(v < 0 ? -1 : set_base + v);
+      P.append_to(aln_pos, aln_end, aln_seq_off, bases, quals, aln_cigar_off, cigar_type, cigar_len);
+      for (size_t r = 0; r < loci[l]->reads.size(); r++) entry_owner.emplace_back(loci[l], r);
     }
     if (!entry_set.empty()) {
       cigar_len.push_back(0);
@@ -336,23 +377,31 @@ hipstr_status_t hipstr_process_regions(hipstr_ctx_t* ctx, int32_t n_files, const
   std::vector<double> p1, p2, stutter;
   std::vector<uint8_t> haploid, rev, use;
   std::vector<const char*> seq_ptr, chrom_ptr, name_ptr, sample_ptr, out_sample_ptr;
-  for (Locus* L : loci) {
-    const int i = L->region;
-    std::map<std::string, int32_t> ids;
+  struct RawPiece { AlnPiece alns; std::vector<int32_t> name_id; std::vector<uint8_t> rev, use; };
+  std::vector<RawPiece> raw_pieces(loci.size());
+  hipstr::parallel_for(loci.size(), [&](size_t l) {
+    const Locus* L = loci[l];
+    RawPiece& P = raw_pieces[l];
+    std::map<std::string, int32_t> ids;      // equal names on adjacent reads = mates that both span the STR
     for (size_t r = 0; r < L->reads.size(); r++) {
       const BamRecord& a = *L->reads[r];
-      read_start.push_back(a.pos);
-      read_stop.push_back(a.end_pos);
-      bases += a.bases; quals += a.quals;
-      seq_off.push_back((int32_t)bases.size());
-      for (const auto& op : a.cigar) { cigar_type += op.first; cigar_len.push_back(op.second); }
-      cigar_off.push_back((int32_t)cigar_type.size());
-      label.push_back(L->label[r]);
-      name_id.push_back(ids.insert(std::make_pair(a.name, (int32_t)ids.size())).first->second);
-      p1.push_back(L->log_p1[r]); p2.push_back(L->log_p2[r]);
-      rev.push_back(a.reverse() ? 1 : 0);
-      use.push_back(!a.passes.empty() && a.passes[0] == '1' ? 1 : 0);
+      P.alns.add(a);
+      P.name_id.push_back(ids.insert(std::make_pair(a.name, (int32_t)ids.size())).first->second);
+      P.rev.push_back(a.reverse() ? 1 : 0);
+      P.use.push_back(!a.passes.empty() && a.passes[0] == '1' ? 1 : 0);
     }
+  });
+  for (size_t l = 0; l < loci.size(); l++) {
+    const Locus* L = loci[l];
+    const int i = L->region;
+    const RawPiece& P = raw_pieces[l];
+    P.alns.append_to(read_start, read_stop, seq_off, bases, quals, cigar_off, cigar_type, cigar_len);
+    label.insert(label.end(), L->label.begin(), L->label.end());
+    name_id.insert(name_id.end(), P.name_id.begin(), P.name_id.end());
+    p1.insert(p1.end(), L->log_p1.begin(), L->log_p1.end());
+    p2.insert(p2.end(), L->log_p2.begin(), L->log_p2.end());
+    rev.insert(rev.end(), P.rev.begin(), P.rev.end());
+    use.insert(use.end(), P.use.begin(), P.use.end());
     lro.push_back((int32_t)read_start.size());
     lso.push_back(lso.back() + (int32_t)L->kept.rg_names.size());
     haploid.push_back(is_haploid(region_chrom[i]) ? 1 : 0);
