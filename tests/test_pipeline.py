@@ -152,3 +152,19 @@ def test_vcf_header_matches_reference(flags, tmp_path):
     got = capi.vcf_header(fasta, "harness", contigs, samples, output_gls=flags.get("gls", 0), output_pls=flags.get("pls", 0),
                           output_filters=flags.get("filters", 0))
     assert got == "\n".join(header) + "\n"
+
+
+def test_process_regions_needs_a_device():
+    """No CPU path: without a context the driver refuses (HIPSTR_ERR_NO_DEVICE), and bad arguments are rejected."""
+    from hipstr_b200 import capi
+    lib = capi.load()
+    po, vo = capi.PipelineOptions(), capi.VcfOptions()
+    lib.hipstr_pipeline_default_options(C.byref(po))
+    lib.hipstr_vcf_default_options(C.byref(vo))
+    assert (po.max_str_length, po.min_total_reads, po.filter.max_mate_dist, po.skip_padding) == (100, 100, 1000, 15)
+    assert list(po.def_stutter_model) == [0.95, 0.05, 0.05, 0.95, 0.01, 0.01]
+    h = C.c_void_p()
+    mk = lambda xs: (C.c_char_p * len(xs))(*[x.encode() for x in xs])
+    st = lib.hipstr_process_regions(None, 1, mk(["x.bam"]), None, 1, mk(["chr1"]), mk(["ACGT"]), 0, None, None, None, None, None, C.byref(po),
+                                    C.byref(vo), C.byref(h))
+    assert capi.STATUS[st] == "NO_DEVICE" and not h.value
