@@ -13,7 +13,8 @@ namespace hipstr {
 
 namespace {
 
-inline char low(char c) { return (char)std::tolower((unsigned char)c); }
+/* tolower() of the "C" locale, which is what the reference's comparisons run under, without the library call per character */
+inline char low(char c) { return (c >= 'A' && c <= 'Z') ? (char)(c + ('a' - 'A')) : c; }
 
 /* number of leading characters of `pattern` equal (ignoring case) to text[at...] */
 int prefix_matches(const std::string& pattern, const std::string& text, int at) {
