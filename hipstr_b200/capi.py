@@ -167,7 +167,7 @@ class PipelineOptions(C.Structure):
                 ("max_flank_haplotypes", C.c_int32), ("min_flank_freq", C.c_double), ("max_em_iter", C.c_int32), ("abs_ll_converge", C.c_double),
                 ("frac_ll_converge", C.c_double), ("use_def_stutter_model", C.c_int32), ("def_stutter_model", C.c_double * 6),
                 ("recalc_stutter_model", C.c_int32), ("skip_padding", C.c_int32), ("n_haploid_chroms", C.c_int32),
-                ("haploid_chroms", C.POINTER(C.c_char_p)), ("host_threads", C.c_int32)]
+                ("haploid_chroms", C.POINTER(C.c_char_p)), ("host_threads", C.c_int32), ("bams_from_10x", C.c_int32)]
 
 
 class FilteredView(C.Structure):

@@ -221,8 +221,22 @@ hipstr_status_t hipstr_process_regions(hipstr_ctx_t* ctx, int32_t n_files, const
   for (Locus* L : loci) R->counters[1] += (int64_t)L->reads.size();
   R->seconds[0] = now_s() - t; t = now_s();
 
-  // ---- phasing log-likelihoods: every read (+ mate) of the window in ONE K7 launch -----------------------------------
-  if (snp_vcf && !loci.empty()) {
+  // ---- phasing log-likelihoods: from the 10X haplotype tags, or every read (+ mate) of the window in ONE K7 launch --------
+  if (opt->bams_from_10x) {   // process_10x_reads: the pair's HP tag decides; mates that disagree (or lack it) carry no information
+    for (Locus* L : loci)
+      for (size_t r = 0; r < L->reads.size(); r++) {
+        int64_t hap = L->reads[r]->has_hp ? L->reads[r]->hp : -1;
+        if (L->mates[r]) {
+          const int64_t mate_hap = L->mates[r]->has_hp ? L->mates[r]->hp : -1;
+          if (mate_hap != hap) hap = -1;
+        }
+        if (hap == -1) continue;
+        if (hap != 1 && hap != 2) { g_driver_error = "HP tag of " + L->reads[r]->name + " is neither 1 nor 2"; return HIPSTR_ERR_BAD_ARG; }
+        L->log_p1[r] = hap == 1 ? -0.01 : -1000.0;     // FROM_HAP_LL / OTHER_HAP_LL (snp_bam_processor.h:17-18)
+        L->log_p2[r] = hap == 2 ? -0.01 : -1000.0;
+        R->counters[2]++;
+      }
+  } else if (snp_vcf && !loci.empty()) {
     const int32_t n_vcf = hipstr_snp_vcf_num_samples(snp_vcf);
     std::map<std::string, int> vcf_index;
     {

@@ -37,6 +37,7 @@ class Options:
     skip_padding = 15               # SNPBamProcessor::SKIP_PADDING
     filter = None                   # dict of hipstr_filter_options_t overrides
     host_threads = 0                # 0 = HIPSTR_HOST_THREADS / all cores
+    bams_from_10x = False           # phasing from the reads' HP tags (native driver only)
 
     def __init__(self, **kw):
         for k, v in kw.items():
@@ -100,6 +101,7 @@ def process_regions(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_optio
     hap = mk(list(opt.haploid_chroms))
     po.n_haploid_chroms, po.haploid_chroms = len(opt.haploid_chroms), hap
     po.host_threads = opt.host_threads
+    po.bams_from_10x = int(bool(opt.bams_from_10x))
     vo = capi.VcfOptions()
     lib.hipstr_vcf_default_options(C.byref(vo))
     for k, v in (vcf_options or {}).items():

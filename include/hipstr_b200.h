@@ -770,6 +770,8 @@ typedef struct {
   int32_t n_haploid_chroms;            /* --haploid-chrs */
   const char* const* haploid_chroms;
   int32_t host_threads;                /* 0 = HIPSTR_HOST_THREADS / all cores */
+  int32_t bams_from_10x;               /* --10x-bams: phasing from the reads' HP tags (SNPBamProcessor::process_10x_reads,
+                                          src/snp_bam_processor.cpp:140-200) instead of a SNP VCF */
 } hipstr_pipeline_options_t;
 typedef struct hipstr_region_results hipstr_region_results_t;
 void hipstr_pipeline_default_options(hipstr_pipeline_options_t* options);

@@ -262,7 +262,7 @@ void ref_alignment_filters(int32_t pos, int32_t end_pos, const char* bases, cons
  * process_regions() over the region file, finish().  No SNP VCF, no reference-panel VCF.
  * options = {use the default stutter model 0.95/0.05/0.05/0.95/0.01/0.01 instead of EM training, MIN_TOTAL_READS,
  *            REMOVE_PCR_DUPS, REQUIRE_PAIRED_READS, recalc_stutter_model_ (0/1), output GLs, output PLs, output FILTERS,
- *            treat chr1 as haploid (--haploid-chrs chr1)}. */
+ *            treat chr1 as haploid (--haploid-chrs chr1), BAMs carry 10X haplotype tags (--10x-bams)}. */
 int32_t ref_process_regions(int32_t n_files, const char* const* paths, const char* fasta_path, const char* region_path,
                             const char* vcf_out_path, const int32_t* options, const char* snp_vcf_path /* NULL = none */) {
   std::vector<std::string> files(paths, paths + n_files);
@@ -277,6 +277,7 @@ int32_t ref_process_regions(int32_t n_files, const char* const* paths, const cha
   Genotyper::OUTPUT_PLS = options[6];
   Genotyper::OUTPUT_FILTERS = options[7];
   if (options[8]) proc.add_haploid_chrom("chr1");
+  if (options[9]) proc.use_10x_bam_tags();
   BamCramMultiReader reader(files, "", BamCramMultiReader::ORDER_ALNS_BY_FILE);
   std::map<std::string, std::string> rg_to_sample, rg_to_library;
   std::set<std::string> samples;

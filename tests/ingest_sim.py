@@ -18,8 +18,9 @@ def rand_seq(rng, n):
 
 
 class Scenario:
-    def __init__(self, seed, n_files=2, n_fragments=160, name_suffix=False, groups=None, tag="", rgs_per_file=None):
+    def __init__(self, seed, n_files=2, n_fragments=160, name_suffix=False, groups=None, tag="", rgs_per_file=None, hp_tags=False):
         rng = self.rng = np.random.default_rng(seed)
+        self.hp_tags = hp_tags
         self.tag = tag
         period = int(rng.integers(2, 5))
         motif = rand_seq(rng, period)
@@ -112,6 +113,12 @@ class Scenario:
     def tags(self, rg, ops):
         rng = self.rng
         t = ["RG:Z:" + rg]
+        if getattr(self, "hp", None):          # 10X haplotype tag of the fragment; a few reads lack it or disagree with their mate
+            r = rng.random()
+            if r < 0.85:
+                t.append("HP:i:%d" % self.hp)
+            elif r < 0.92:
+                t.append("HP:i:%d" % (3 - self.hp))
         if rng.random() < 0.5:
             a = int(rng.integers(60, 150)); t += ["AS:i:%d" % a, "XS:i:%d" % max(0, a - int(rng.integers(0, 40)))]
         r = rng.random()
@@ -137,6 +144,8 @@ class Scenario:
         insert = int(rng.integers(L + 5, 650))
         start = int(rng.integers(self.region[0] - 700, self.region[1] + 200))
         name = "%sfrag%d" % (self.tag, i)
+        if getattr(self, "hp_tags", False):
+            self.hp = int(rng.integers(1, 3)) if rng.random() < 0.8 else None
         copies = 2 if rng.random() < 0.15 else 1          # PCR duplicates: same coordinates, another name
         for c in range(copies):
             nm = name if c == 0 else name + "dup"
@@ -188,11 +197,11 @@ class Scenario:
 class MultiScenario:
     """Several STRs on one chromosome: independent Scenarios laid end to end (same files and read groups)."""
 
-    def __init__(self, seed, n_regions=4, n_files=2, n_fragments=220, rgs_per_file=None, repeat=1):
+    def __init__(self, seed, n_regions=4, n_files=2, n_fragments=220, rgs_per_file=None, repeat=1, hp_tags=False):
         self.parts = []
         groups = None
         for k in range(n_regions):
-            part = Scenario(seed * 100 + k, n_files=n_files, n_fragments=n_fragments, groups=groups, tag="r%d_" % k, rgs_per_file=rgs_per_file)
+            part = Scenario(seed * 100 + k, n_files=n_files, n_fragments=n_fragments, groups=groups, tag="r%d_" % k, rgs_per_file=rgs_per_file, hp_tags=hp_tags)
             groups = [f["groups"] for f in part.files]
             self.parts.append(part)
         self.parts = self.parts * repeat       # the same reads again further along the chromosome (cheap large inputs)

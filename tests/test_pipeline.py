@@ -15,12 +15,12 @@ canon = lambda t: t.replace(":-0.00:", ":0.00:")
 
 
 def run_reference(paths, fasta, bed, out_vcf, def_stutter, min_total_reads=20, remove_dups=1, require_paired=1, recalc=0, gls=0, pls=0,
-                  filters=0, snp_vcf=None, haploid=0):
+                  filters=0, snp_vcf=None, haploid=0, tenx=0):
     f = checkers.ref().ref_process_regions
     f.restype = C.c_int32
     f.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.c_char_p]
     arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
-    o = np.array([def_stutter, min_total_reads, remove_dups, require_paired, recalc, gls, pls, filters, haploid], np.int32)
+    o = np.array([def_stutter, min_total_reads, remove_dups, require_paired, recalc, gls, pls, filters, haploid, tenx], np.int32)
     assert f(len(paths), arr, fasta.encode(), bed.encode(), out_vcf.encode(), o.ctypes.data_as(C.POINTER(C.c_int32)),
              snp_vcf.encode() if snp_vcf else None) == 0
     import gzip
@@ -59,18 +59,21 @@ def files_of(sc, tmp_path, extra_regions=()):
     (5, 1, dict(require_paired=0, gls=1, pls=1, filters=1)),
     (6, 0, dict(recalc=1, remove_dups=0)),
     (9, 0, dict(haploid=1, snp_vcf=1)),           # --haploid-chrs chr1
+    (10, 0, dict(tenx=1)),                        # --10x-bams: phasing from the HP tags (native driver only)
 ])
 @pytest.mark.parametrize("driver", ["native", "staged"])
 def test_bam_to_vcf_matches_reference(seed, def_stutter, kw, driver, tmp_path):
     from hipstr_b200 import capi, pipeline
-    sc = MultiScenario(seed, n_regions=4, n_fragments=220 if def_stutter else 600)
+    if kw.get("tenx") and driver == "staged":
+        pytest.skip("the stage-by-stage Python chain does not read HP tags")
+    sc = MultiScenario(seed, n_regions=4, n_fragments=220 if def_stutter else 600, hp_tags=bool(kw.get("tenx")))
     extra = [("chr1", 2000, 2200, 4, 50.0, "TOO_LONG"), ("chr1", 10, 40, 3, 10.0, "CONTIG_END"), ("chr1", 7000, 7030, 3, 10.0, "NO_READS")]
     paths, fasta, bed = files_of(sc, tmp_path, extra)
     kw = dict(kw)
     snp_vcf = write_snp_vcf(sc, tmp_path, seed)[1] if kw.pop("snp_vcf", 0) else None
     header, want = run_reference(paths, fasta, bed, str(tmp_path / "ref.vcf"), def_stutter, snp_vcf=snp_vcf, **kw)
     opt = pipeline.Options(min_total_reads=20, snp_vcf=snp_vcf, def_stutter_model=pipeline.DEFAULT_STUTTER if def_stutter else None,
-                           recalc_stutter_model=bool(kw.get("recalc", 0)), haploid_chroms=("chr1",) if kw.get("haploid") else (),
+                           recalc_stutter_model=bool(kw.get("recalc", 0)), haploid_chroms=("chr1",) if kw.get("haploid") else (), bams_from_10x=bool(kw.get("tenx")),
                            filter=dict(remove_pcr_dups=kw.get("remove_dups", 1), require_paired_reads=kw.get("require_paired", 1)))
     vcf_opt = dict(output_gls=kw.get("gls", 0), output_pls=kw.get("pls", 0), output_filters=kw.get("filters", 0))
     with capi.Context(0) as ctx:
