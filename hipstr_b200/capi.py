@@ -642,6 +642,9 @@ def load():
     lib.hipstr_vcf_header.restype = C.c_int64
     lib.hipstr_vcf_header.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, cpp, c_i64p, C.c_int32, cpp, C.POINTER(VcfOptions), C.c_int64,
                                       C.c_char_p]
+    lib.hipstr_genotyper_create_with_ref_alleles.restype = C.c_int32
+    lib.hipstr_genotyper_create_with_ref_alleles.argtypes = [vp, C.c_int32, c_i32p, c_i32p, c_i32p, cpp, c_f64p, C.POINTER(LocusReadsStruct),
+                                                             c_i32p, c_i32p, cpp, C.POINTER(vp)]
     lib.hipstr_pipeline_default_options.restype = None
     lib.hipstr_pipeline_default_options.argtypes = [C.POINTER(PipelineOptions)]
     lib.hipstr_process_regions_last_error.restype = C.c_char_p
@@ -977,7 +980,8 @@ class Genotyper:
                                 v.log_p1, v.log_p2, v.haploid, v.read_rev_strand, v.read_stop)
 
     @classmethod
-    def from_synth_reads(cls, ctx, synth, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01), loci_range=None, use_for_haps=None):
+    def from_synth_reads(cls, ctx, synth, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01), loci_range=None, use_for_haps=None,
+                         ref_alleles=None):
         """The full seam-B1 constructor: haplotype blocks are generated from the reads (hipstr_genotyper_create_from_reads).
         loci_range = (first, end) restricts the batch to a window of the Synth's loci."""
         v = synth.view
@@ -1005,8 +1009,18 @@ class Genotyper:
         g._keep = (rs, chroms, carr, start, stop, period, st6, use_for_haps)
         g._synth = synth
         h = C.c_void_p()
-        st = g.lib.hipstr_genotyper_create_from_reads(ctx.h if ctx else None, L, ptr(start, c_i32p), ptr(stop, c_i32p),
-                                                      ptr(period, c_i32p), carr, ptr(st6, c_f64p), C.byref(rs), C.byref(h))
+        if ref_alleles is not None:   # [(pos or -1, [allele, ...])] per locus: the --ref-vcf reference panel
+            apos = np.array([a[0] for a in ref_alleles], np.int32)
+            aoff = np.cumsum([0] + [len(a[1]) for a in ref_alleles]).astype(np.int32)
+            flat = [x.encode() for a in ref_alleles for x in a[1]]
+            aarr = (C.c_char_p * max(len(flat), 1))(*flat)
+            g._keep += (apos, aoff, flat, aarr)
+            st = g.lib.hipstr_genotyper_create_with_ref_alleles(ctx.h if ctx else None, L, ptr(start, c_i32p), ptr(stop, c_i32p), ptr(period, c_i32p),
+                                                                carr, ptr(st6, c_f64p), C.byref(rs), ptr(apos, c_i32p), ptr(aoff, c_i32p), aarr,
+                                                                C.byref(h))
+        else:
+            st = g.lib.hipstr_genotyper_create_from_reads(ctx.h if ctx else None, L, ptr(start, c_i32p), ptr(stop, c_i32p),
+                                                          ptr(period, c_i32p), carr, ptr(st6, c_f64p), C.byref(rs), C.byref(h))
         if st != 0:
             raise HipstrError(st, "genotyper_create_from_reads")
         g.h = h

@@ -180,6 +180,32 @@ bool HaplotypeGenerator::add_haplotype_block(int32_t reg_start, int32_t reg_stop
   return true;
 }
 
+bool HaplotypeGenerator::add_vcf_haplotype_block(int32_t pos, int32_t period, const std::string& chrom_seq,
+                                                 const std::vector<std::string>& vcf_alleles, const double* stutter) {
+  if (vcf_alleles.empty()) { failure_msg_ = "no alleles in the reference VCF record"; return false; }
+  const int32_t region_start = pos, region_end = pos + (int32_t)vcf_alleles[0].size();
+  if (region_start < kRefFlankLen || region_end + kRefFlankLen >= (int64_t)chrom_seq.size()) {
+    failure_msg_ = "Haplotype blocks are too near to the chromosome ends";
+    return false;
+  }
+  if (upper(vcf_alleles[0]) != upper(chrom_seq.substr(region_start, region_end - region_start))) {
+    failure_msg_ = "the reference allele of the VCF record does not match the chromosome sequence";   // an assert in the reference
+    return false;
+  }
+  if (!hap_blocks_.empty() && region_start < hap_blocks_.back().end + kMinBlockSpacing) {
+    failure_msg_ = "Haplotype blocks are too near to one another";
+    return false;
+  }
+  HapBlock block;
+  block.start = region_start;
+  block.end = region_end;
+  block.period = period;
+  std::memcpy(block.stutter, stutter, sizeof(block.stutter));
+  for (const std::string& a : vcf_alleles) block.seqs.push_back(upper(a));
+  hap_blocks_.push_back(block);
+  return true;
+}
+
 bool HaplotypeGenerator::fuse_haplotype_blocks(const std::string& chrom_seq) {
   if (hap_blocks_.empty()) { failure_msg_ = "no haplotype blocks were added"; return false; }
   // flanks of at most kRefFlankLen bp, at least 10 bp, no longer than the reads reach

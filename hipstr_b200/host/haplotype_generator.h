@@ -33,6 +33,9 @@ class HaplotypeGenerator {
   /* add_haplotype_block (HaplotypeGenerator.cpp:274-329); reads grouped by sample */
   bool add_haplotype_block(int32_t region_start, int32_t region_stop, int32_t period, const std::string& chrom_seq,
                            const std::vector<std::vector<ReadView> >& alignments, const double* stutter);
+  /* add_vcf_haplotype_block (:256-284): the alleles come from a reference panel instead of the reads */
+  bool add_vcf_haplotype_block(int32_t pos, int32_t period, const std::string& chrom_seq, const std::vector<std::string>& vcf_alleles,
+                               const double* stutter);
   bool fuse_haplotype_blocks(const std::string& chrom_seq);   /* :331-366 */
   const std::string& failure_msg() const { return failure_msg_; }
   const std::vector<HapBlock>& get_haplotype_blocks() const { return hap_blocks_; }

@@ -383,7 +383,8 @@ SeqStutterGenotyper::Request SeqStutterGenotyper::advance() {
         log_aln_probs_.assign((size_t)num_reads_ * num_alleles_, 0.0);
         log_sample_posteriors_.assign((size_t)num_samples_ * num_alleles_ * num_alleles_, 0.0);
         log_ += "Aligning reads to each candidate haplotype\n";
-        phase_ = STUTTER_ALLELES;
+        // with a reference panel the allele set is fixed: no stutter-allele discovery, no pruning (seq_stutter_genotyper.cpp:641-665)
+        phase_ = fixed_alleles_ ? (reassemble_flanks_ ? ASSEMBLE_FLANKS : DONE) : STUTTER_ALLELES;
         rounds_++;
         return NEED_ALIGNMENT;
       case STUTTER_ALLELES: {   // id_and_align_to_stutter_alleles, seq_stutter_genotyper.cpp:570-601
@@ -444,7 +445,7 @@ SeqStutterGenotyper::Request SeqStutterGenotyper::advance() {
         const int outcome = assemble_flanks();
         if (outcome < 0) { phase_ = FAILED; return NONE; }
         if (outcome == 0) { phase_ = DONE; break; }
-        phase_ = ASSEMBLE_PRUNE;
+        phase_ = fixed_alleles_ ? DONE : ASSEMBLE_PRUNE;   // (:204: uncalled alleles are only removed without a reference panel)
         rounds_++;
         return NEED_ALIGNMENT;
       }
@@ -844,7 +845,8 @@ hipstr_status_t GenotyperBatch::add_loci(const hipstr_align_batch_t* bt, const i
 
 hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_t* region_start, const int32_t* region_stop,
                                                     const int32_t* period, const char* const* chrom_seq, const double* stutter,
-                                                    const hipstr_locus_reads_t* rd, std::string& err) {
+                                                    const hipstr_locus_reads_t* rd, std::string& err, const int32_t* allele_pos,
+                                                    const int32_t* allele_off, const char* const* alleles) {
   if (!region_start || !region_stop || !period || !chrom_seq || !stutter || !rd) { err = "null argument"; return HIPSTR_ERR_BAD_ARG; }
   const size_t base = loci.size();
   loci.resize(base + n_loci);
@@ -879,8 +881,20 @@ hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_
     g.log_ += "Generating candidate haplotypes\n";
     const std::string chrom(chrom_seq[l]);
     HaplotypeGenerator generator(min_start, max_stop);
-    if (generator.add_haplotype_block(region_start[l], region_stop[l], period[l], chrom, by_sample, stutter + 6 * (size_t)l) &&
-        generator.fuse_haplotype_blocks(chrom)) {
+    bool added;
+    if (allele_pos) {   // ref_vcf != NULL (seq_stutter_genotyper.cpp:445-459): the alleles of the reference panel's record
+      g.fixed_alleles_ = true;
+      std::vector<std::string> vcf_alleles;
+      for (int a = allele_off[l]; a < allele_off[l + 1]; a++) vcf_alleles.push_back(alleles[a]);
+      if (allele_pos[l] < 0 || vcf_alleles.empty()) {
+        g.log_ += "Haplotype construction failed: The alleles could not be extracted from the reference VCF\n";
+        g.phase_ = SeqStutterGenotyper::FAILED;
+        status[li] = init_reads(g, rd, l, errors[li]);
+        return;
+      }
+      added = generator.add_vcf_haplotype_block(allele_pos[l], period[l], chrom, vcf_alleles, stutter + 6 * (size_t)l);
+    } else added = generator.add_haplotype_block(region_start[l], region_stop[l], period[l], chrom, by_sample, stutter + 6 * (size_t)l);
+    if (added && generator.fuse_haplotype_blocks(chrom)) {
       g.hap_blocks_ = generator.get_haplotype_blocks();
       g.num_alleles_ = 1;
       for (const HapBlock& b : g.hap_blocks_) g.num_alleles_ *= b.num_options();
@@ -1354,6 +1368,21 @@ hipstr_status_t hipstr_genotyper_create_from_reads(hipstr_ctx_t* ctx, int32_t n_
   hipstr_genotyper* g = new hipstr_genotyper(ctx);
   const double t0 = hipstr::now_s();
   hipstr_status_t st = g->batch.add_loci_from_reads(n_loci, region_start, region_stop, period, chrom_seq, stutter, reads, g->last_error);
+  g->batch.seconds[hipstr::GenotyperBatch::T_CONSTRUCT] += hipstr::now_s() - t0;
+  if (st != HIPSTR_OK) { delete g; return st; }
+  *out = g;
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_genotyper_create_with_ref_alleles(hipstr_ctx_t* ctx, int32_t n_loci, const int32_t* region_start,
+                                                         const int32_t* region_stop, const int32_t* period, const char* const* chrom_seq,
+                                                         const double* stutter, const hipstr_locus_reads_t* reads, const int32_t* allele_pos,
+                                                         const int32_t* allele_off, const char* const* alleles, hipstr_genotyper_t** out) {
+  if (!out || n_loci < 0 || !allele_pos || !allele_off || (allele_off[n_loci] > 0 && !alleles)) return HIPSTR_ERR_BAD_ARG;
+  hipstr_genotyper* g = new hipstr_genotyper(ctx);
+  const double t0 = hipstr::now_s();
+  hipstr_status_t st = g->batch.add_loci_from_reads(n_loci, region_start, region_stop, period, chrom_seq, stutter, reads, g->last_error, allele_pos,
+                                                    allele_off, alleles);
   g->batch.seconds[hipstr::GenotyperBatch::T_CONSTRUCT] += hipstr::now_s() - t0;
   if (st != HIPSTR_OK) { delete g; return st; }
   *out = g;

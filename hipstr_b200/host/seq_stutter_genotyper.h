@@ -123,6 +123,7 @@ class SeqStutterGenotyper {
   int max_total_haplotypes_ = 1000, max_flank_haplotypes_ = 4;
   double min_flank_freq_ = 0.01;
   bool reassemble_flanks_ = false;
+  bool fixed_alleles_ = false;   /* ref_vcf_ != NULL: the alleles come from a reference panel and are never added to or pruned */
   /* pending device work */
   std::vector<uint8_t> realign_hap_, realign_pool_, copy_read_;   /* masks of the pending alignment */
   std::vector<std::pair<int, int> > missing_traces_;
@@ -159,7 +160,8 @@ class GenotyperBatch {
    * locus, then init().  A locus whose haplotype construction fails stays uninitialised (genotype() = false). */
   hipstr_status_t add_loci_from_reads(int32_t n_loci, const int32_t* region_start, const int32_t* region_stop,
                                       const int32_t* period, const char* const* chrom_seq, const double* stutter,
-                                      const hipstr_locus_reads_t* reads, std::string& err);
+                                      const hipstr_locus_reads_t* reads, std::string& err, const int32_t* allele_pos = nullptr,
+                                      const int32_t* allele_off = nullptr, const char* const* alleles = nullptr);
   /* genotype() of every locus (.cpp:603-671), lockstep rounds. */
   hipstr_status_t genotype(int max_total_haplotypes, int max_flank_haplotypes, double min_flank_freq, bool reassemble_flanks,
                            std::string& err);

@@ -430,6 +430,18 @@ hipstr_status_t hipstr_genotyper_create_from_reads(hipstr_ctx_t* ctx, int32_t n_
                                                    const int32_t* region_stop, const int32_t* period,
                                                    const char* const* chrom_seq, const double* stutter,
                                                    const hipstr_locus_reads_t* reads, hipstr_genotyper_t** out);
+/* The same constructor with ref_vcf != NULL (the --ref-vcf reference panel, seq_stutter_genotyper.cpp:445-459): the
+ * alleles of locus l are alleles[allele_off[l] .. allele_off[l+1]) starting at allele_pos[l] (0-based; what
+ * read_vcf_alleles returns, src/vcf_input.cpp:21-50; allele 0 must equal the chromosome there), entered through
+ * HaplotypeGenerator::add_vcf_haplotype_block (HaplotypeGenerator.cpp:256-284).  allele_pos[l] < 0 = the record could not
+ * be read: the locus fails like in the reference.  genotype() then keeps the allele set fixed -- no stutter-allele
+ * discovery and no pruning (:641-665, :204); flank assembly still runs. */
+hipstr_status_t hipstr_genotyper_create_with_ref_alleles(hipstr_ctx_t* ctx, int32_t n_loci, const int32_t* region_start,
+                                                         const int32_t* region_stop, const int32_t* period,
+                                                         const char* const* chrom_seq, const double* stutter,
+                                                         const hipstr_locus_reads_t* reads, const int32_t* allele_pos,
+                                                         const int32_t* allele_off, const char* const* alleles,
+                                                         hipstr_genotyper_t** out);
 void            hipstr_genotyper_destroy(hipstr_genotyper_t* g);
 const char*     hipstr_genotyper_last_error(const hipstr_genotyper_t* g);
 /* genotype(max_total_haplotypes, max_flank_haplotypes, min_flank_freq) of every locus

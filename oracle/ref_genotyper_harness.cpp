@@ -31,6 +31,7 @@
 #include "SeqAlignment/RepeatBlock.h"
 #include "mathops.h"
 #include "region.h"
+#include "vcf_reader.h"
 #include "stutter_model.h"
 #include "extract_indels.h"
 #include "debruijn_graph.h"
@@ -55,8 +56,10 @@ struct RefSG {
   std::string chrom_seq;
   std::ostringstream log;
   int n_reads = 0;
+  VCF::VCFReader* ref_vcf = NULL;
   ~RefSG() {
     delete g;
+    delete ref_vcf;
     for (auto m : models) delete m;
   }
 };
@@ -73,7 +76,7 @@ void* ref_sg_create(int32_t n_samples, int32_t n_reads, const int32_t* sample_la
                     const int32_t* cigar_off, const char* cigar_type, const int32_t* cigar_len, const double* log_p1,
                     const double* log_p2, const char* chrom_seq, int32_t region_start, int32_t region_stop,
                     int32_t period, const double* stutter, int32_t haploid, int32_t reassemble_flanks,
-                    const uint8_t* rev_strand, const uint8_t* use_for_haps) {
+                    const uint8_t* rev_strand, const uint8_t* use_for_haps, const char* ref_vcf_path /* NULL = no reference panel */) {
   ensure_init();
   RefSG* h = new RefSG();
   h->chrom_seq = chrom_seq;
@@ -106,8 +109,9 @@ void* ref_sg_create(int32_t n_samples, int32_t n_reads, const int32_t* sample_la
   Region region("chrS", region_start, region_stop, period, "STR");
   RegionGroup group(region);
   h->models.push_back(new StutterModel(stutter[0], stutter[1], stutter[2], stutter[3], stutter[4], stutter[5], period));
+  if (ref_vcf_path != NULL) h->ref_vcf = new VCF::VCFReader(ref_vcf_path);
   h->g = new SeqStutterGenotyper(group, haploid != 0, reassemble_flanks != 0, alns, p1, p2, h->names, h->chrom_seq,
-                                 h->models, NULL, h->log);
+                                 h->models, h->ref_vcf, h->log);
   return h;
 }
 

@@ -16,7 +16,7 @@ def bind(lib):
     lib.ref_sg_create.restype = C.c_void_p
     lib.ref_sg_create.argtypes = [C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_void_p, c_i32p,
                                   C.c_void_p, c_i32p, c_f64p, c_f64p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32,
-                                  c_f64p, C.c_int32, C.c_int32, c_u8p, c_u8p]
+                                  c_f64p, C.c_int32, C.c_int32, c_u8p, c_u8p, C.c_char_p]
     lib.ref_sg_set_output_flags.restype = None
     lib.ref_sg_set_output_flags.argtypes = [c_i32p, C.c_double]
     for name in ("destroy",):
@@ -117,7 +117,7 @@ class ReadsOfLocus:
 class RefGenotyper:
     """One reference SeqStutterGenotyper object."""
 
-    def __init__(self, reads, stutter=DEF_STUTTER, reassemble_flanks=False):
+    def __init__(self, reads, stutter=DEF_STUTTER, reassemble_flanks=False, ref_vcf=None):
         self.lib = bind(checkers.ref())
         self.reads = reads
         st = np.asarray(stutter, np.float64)
@@ -127,7 +127,7 @@ class RefGenotyper:
             ptr(reads.cigar_off, c_i32p), reads.cigar_type.ctypes.data, ptr(reads.cigar_len, c_i32p),
             ptr(reads.log_p1, c_f64p), ptr(reads.log_p2, c_f64p), reads.chrom_seq, reads.region[0], reads.region[1],
             reads.period, ptr(st, c_f64p), reads.haploid, int(reassemble_flanks), ptr(reads.rev_strand, c_u8p),
-            ptr(getattr(reads, "use_for_haps", None), c_u8p))
+            ptr(getattr(reads, "use_for_haps", None), c_u8p), ref_vcf.encode() if ref_vcf else None)
         self.initialized = bool(self.lib.ref_sg_initialized(self.h))
 
     def blocks(self):

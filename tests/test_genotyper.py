@@ -387,3 +387,78 @@ def test_window_mixing_long_reads_and_long_haplotypes():
         assert np.array_equal(g.results(l)["best"], r.results()["best"])
     g.close()
     ctx.close()
+
+
+# ---- the reference-panel path (--ref-vcf): alleles from a VCF record, never added to or pruned ---------------------------
+def _panel(s, l, tmp_path, n_alt=3):
+    """A one-record STR VCF for locus l (bgzipped + tabix-indexed by htslib through the harness): the reference allele padded by
+    2 bp / 1 bp, alternates that add or drop repeat units.  Returns (path, pos, alleles)."""
+    from ref_genotyper import LocusReads
+    reads = LocusReads(s, l)
+    chrom = reads.chrom_seq.decode()
+    start, stop = reads.region
+    period = reads.period
+    pos = start - 2
+    ref = chrom[pos:stop + 1]
+    unit = chrom[start:start + period]
+    alts = [ref[:2] + unit * k + ref[2:] for k in range(1, n_alt)] + [ref[:2] + ref[2 + period:]]
+    text = ("##fileformat=VCFv4.2\n##contig=<ID=chrS,length=%d>\n" % len(chrom)
+            + '##INFO=<ID=START,Number=1,Type=Integer,Description="s">\n##INFO=<ID=END,Number=1,Type=Integer,Description="e">\n'
+            + '##FORMAT=<ID=GT,Number=1,Type=String,Description="g">\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tX\n'
+            + "chrS\t%d\t.\t%s\t%s\t.\t.\tSTART=%d;END=%d\tGT\t0/1\n" % (pos + 1, ref, ",".join(alts), start + 1, stop))
+    plain, gz = str(tmp_path / ("panel%d.vcf" % l)), str(tmp_path / ("panel%d.vcf.gz" % l))
+    with open(plain, "w") as fh:
+        fh.write(text)
+    lib = checkers.ref()
+    lib.ref_vcf_bgzip_tabix.restype = C.c_int32
+    lib.ref_vcf_bgzip_tabix.argtypes = [C.c_char_p, C.c_char_p]
+    assert lib.ref_vcf_bgzip_tabix(plain.encode(), gz.encode()) == 0
+    return gz, pos, [ref] + alts
+
+
+@needs_ref
+def test_constructor_with_reference_panel(tmp_path):
+    from hipstr_b200.capi import Genotyper
+    from ref_genotyper import LocusReads, RefGenotyper
+    s = Synth(n_loci=3, n_samples=5, reads_per_sample=10, n_alleles=4, read_len=110, seed=171, stutter_rate=0.2)
+    panels = [_panel(s, l, tmp_path) for l in range(s.n_loci)]
+    g = Genotyper.from_synth_reads(None, s, ref_alleles=[(p[1], p[2]) for p in panels[:-1]] + [(-1, [])])
+    for l in range(s.n_loci - 1):
+        r = RefGenotyper(LocusReads(s, l), ref_vcf=panels[l][0])
+        assert r.initialized
+        assert g.blocks(l) == [b[3] for b in r.blocks()], l
+        assert [x for x in g.blocks(l) if len(x) > 1][0] == [a.upper() for a in panels[l][2]]
+    assert g.info(s.n_loci - 1)["blocks"] == 0      # "alleles could not be extracted": the locus fails
+    g.close()
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("assemble", [False, True])
+def test_genotype_loop_with_reference_panel(assemble, tmp_path):
+    from hipstr_b200.capi import Context, Genotyper
+    from ref_genotyper import LocusReads, RefGenotyper
+    s = Synth(n_loci=4, n_samples=6, reads_per_sample=14, n_alleles=5, read_len=110, seed=181, stutter_rate=0.25,
+              flank_snp_freq=0.3 if assemble else 0.0)
+    panels = [_panel(s, l, tmp_path) for l in range(s.n_loci)]
+    ctx = Context(0)
+    g = Genotyper.from_synth_reads(ctx, s, ref_alleles=[(p[1], p[2]) for p in panels])
+    ok = g.genotype(1000, 4, 0.01, assemble)
+    names = ["S%d" % i for i in range(6)]
+    cl = int(s.view.chrom_len)
+    raw = C.string_at(s.view.chrom_seqs, s.n_loci * cl)
+    loci = g.vcf_loci(["chrS"] * s.n_loci, ["STR"] * s.n_loci, [s.view.region_start] * s.n_loci, [s.view.region_stop] * s.n_loci,
+                      [int(s.cfg.period) or 4] * s.n_loci, [raw[l * cl:(l + 1) * cl] for l in range(s.n_loci)], names * s.n_loci, names)
+    records = g.write_vcf(loci)
+    canon = lambda t: t.replace(":-0.00:", ":0.00:")
+    for l in range(s.n_loci):
+        r = RefGenotyper(LocusReads(s, l), reassemble_flanks=assemble, ref_vcf=panels[l][0])
+        assert r.genotype(1000, 4, 0.01) == bool(ok[l])
+        assert g.blocks(l) == [b[3] for b in r.blocks()], l
+        w, o = r.results(), g.results(l)
+        assert np.array_equal(o["best"], w["best"]) and np.abs(o["read_ll"] - w["read_ll"]).max() <= 1e-9
+        assert canon(records[l][1]) == canon(r.vcf().rstrip("\n")), l
+        # the panel's alleles all survive: nothing is pruned with a reference panel
+        assert [a.upper() for a in panels[l][2]] in g.blocks(l)
+    g.close()
+    ctx.close()
