@@ -167,7 +167,8 @@ class PipelineOptions(C.Structure):
                 ("max_flank_haplotypes", C.c_int32), ("min_flank_freq", C.c_double), ("max_em_iter", C.c_int32), ("abs_ll_converge", C.c_double),
                 ("frac_ll_converge", C.c_double), ("use_def_stutter_model", C.c_int32), ("def_stutter_model", C.c_double * 6),
                 ("recalc_stutter_model", C.c_int32), ("skip_padding", C.c_int32), ("n_haploid_chroms", C.c_int32),
-                ("haploid_chroms", C.POINTER(C.c_char_p)), ("host_threads", C.c_int32), ("bams_from_10x", C.c_int32)]
+                ("haploid_chroms", C.POINTER(C.c_char_p)), ("host_threads", C.c_int32), ("bams_from_10x", C.c_int32),
+                ("ref_vcf", C.c_void_p)]
 
 
 class FilteredView(C.Structure):
@@ -251,6 +252,32 @@ def vcf_header(reference_path, full_command, contigs, samples, **options):
         if n == 0:
             raise HipstrError(-2, "vcf_header")
         cap = -n
+
+
+class StrVcf:
+    """hipstr_str_vcf_t: a reference panel of STR genotypes (--ref-vcf)."""
+
+    def __init__(self, path):
+        self.lib = load()
+        h = C.c_void_p()
+        st = self.lib.hipstr_str_vcf_open(path.encode(), C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "str_vcf_open: " + self.lib.hipstr_snp_vcf_last_error().decode())
+        self.h = h
+
+    def alleles(self, chrom, region_start, region_stop):
+        """read_vcf_alleles -> (pos, [alleles]) or None"""
+        pos, n, text = C.c_int32(), C.c_int32(), C.c_char_p()
+        if self.lib.hipstr_str_vcf_alleles(self.h, chrom.encode(), region_start, region_stop, C.byref(pos), C.byref(n), C.byref(text)) != 1:
+            return None
+        return pos.value, text.value.decode().splitlines()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hipstr_str_vcf_close(self.h)
+            self.h = None
+
+    __del__ = close
 
 
 class BamReader:
@@ -645,6 +672,12 @@ def load():
     lib.hipstr_genotyper_create_with_ref_alleles.restype = C.c_int32
     lib.hipstr_genotyper_create_with_ref_alleles.argtypes = [vp, C.c_int32, c_i32p, c_i32p, c_i32p, cpp, c_f64p, C.POINTER(LocusReadsStruct),
                                                              c_i32p, c_i32p, cpp, C.POINTER(vp)]
+    lib.hipstr_str_vcf_open.restype = C.c_int32
+    lib.hipstr_str_vcf_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.hipstr_str_vcf_close.restype = None
+    lib.hipstr_str_vcf_close.argtypes = [vp]
+    lib.hipstr_str_vcf_alleles.restype = C.c_int32
+    lib.hipstr_str_vcf_alleles.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, c_i32p, c_i32p, C.POINTER(C.c_char_p)]
     lib.hipstr_pipeline_default_options.restype = None
     lib.hipstr_pipeline_default_options.argtypes = [C.POINTER(PipelineOptions)]
     lib.hipstr_process_regions_last_error.restype = C.c_char_p

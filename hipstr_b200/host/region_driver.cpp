@@ -444,8 +444,27 @@ hipstr_status_t hipstr_process_regions(hipstr_ctx_t* ctx, int32_t n_files, const
   R->seconds[3] = now_s() - t; t = now_s();
 
   hipstr_genotyper_t* g = nullptr;
-  st = hipstr_genotyper_create_from_reads(ctx, n, starts.data(), stops.data(), periods.data(), seq_ptr.data(), stutter.data(),
-                                          hipstr_left_aligned_reads(aligned), &g);
+  if (opt->ref_vcf) {   // the alleles of the reference panel's record for every region (read_vcf_alleles)
+    std::vector<int32_t> allele_pos(n, -1), allele_off(1, 0);
+    std::vector<std::string> allele_text;
+    for (int32_t l = 0; l < n; l++) {
+      int32_t pos = -1, count = 0;
+      const char* text = nullptr;
+      if (hipstr_str_vcf_alleles(opt->ref_vcf, chrom_ptr[l], starts[l], stops[l], &pos, &count, &text) == 1) {
+        allele_pos[l] = pos;
+        const std::string all(text);
+        for (size_t at = 0; at < all.size();) { const size_t eol = all.find('\n', at); allele_text.push_back(all.substr(at, eol - at)); at = eol + 1; }
+      }
+      allele_off.push_back((int32_t)allele_text.size());
+    }
+    std::vector<const char*> allele_ptr;
+    for (const std::string& a : allele_text) allele_ptr.push_back(a.c_str());
+    allele_ptr.push_back("");
+    st = hipstr_genotyper_create_with_ref_alleles(ctx, n, starts.data(), stops.data(), periods.data(), seq_ptr.data(), stutter.data(),
+                                                  hipstr_left_aligned_reads(aligned), allele_pos.data(), allele_off.data(), allele_ptr.data(), &g);
+  } else
+    st = hipstr_genotyper_create_from_reads(ctx, n, starts.data(), stops.data(), periods.data(), seq_ptr.data(), stutter.data(),
+                                            hipstr_left_aligned_reads(aligned), &g);
   if (st != HIPSTR_OK) { hipstr_left_aligned_free(aligned); g_driver_error = "constructing the genotypers failed"; return st; }
   std::vector<uint8_t> ok(n, 0);
   st = hipstr_genotyper_genotype(g, opt->max_total_haplotypes, opt->max_flank_haplotypes, opt->min_flank_freq, 1, ok.data());

@@ -232,3 +232,97 @@ hipstr_status_t hipstr_snp_vcf_region_sets(hipstr_snp_vcf_t* v, const char* chro
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// The reference panel (--ref-vcf): the STR record of a region, read_vcf_alleles (src/vcf_input.cpp:21-50).
+// ---------------------------------------------------------------------------------------------
+struct hipstr_str_vcf {
+  struct Record { int32_t pos; int32_t ref_len; bool has_span; int32_t start, end; std::vector<std::string> alleles; };
+  std::map<std::string, std::vector<Record> > chroms;   // file order
+  std::string result;
+};
+
+namespace {
+bool info_int(const std::string& info, const char* key, int32_t& value) {   // KEY=<int> among the ';' separated INFO entries
+  const size_t klen = std::strlen(key);
+  size_t at = 0;
+  while (at <= info.size()) {
+    size_t stop = info.find(';', at);
+    if (stop == std::string::npos) stop = info.size();
+    if (stop - at > klen && info.compare(at, klen, key) == 0 && info[at + klen] == '=') {
+      value = (int32_t)std::strtol(info.c_str() + at + klen + 1, nullptr, 10);
+      return true;
+    }
+    at = stop + 1;
+  }
+  return false;
+}
+}  // namespace
+
+extern "C" {
+
+hipstr_status_t hipstr_str_vcf_open(const char* path, hipstr_str_vcf_t** out) {
+  if (!path || !out) return HIPSTR_ERR_BAD_ARG;
+  std::string text;
+  if (!read_whole_file(path, text, g_vcf_error)) return HIPSTR_ERR_BAD_ARG;
+  std::unique_ptr<hipstr_str_vcf> v(new hipstr_str_vcf());
+  std::stringstream ss(text);
+  std::string line;
+  while (std::getline(ss, line)) {
+    if (line.empty() || line[0] == '#') continue;
+    std::vector<std::string> f;
+    size_t at = 0;
+    for (int c = 0; c < 8; c++) {
+      const size_t tab = line.find('\t', at);
+      f.push_back(line.substr(at, tab == std::string::npos ? std::string::npos : tab - at));
+      if (tab == std::string::npos) break;
+      at = tab + 1;
+    }
+    if (f.size() < 8) { g_vcf_error = "Failed to parse VCF record"; return HIPSTR_ERR_BAD_ARG; }
+    hipstr_str_vcf::Record r;
+    r.pos = (int32_t)std::strtol(f[1].c_str(), nullptr, 10);
+    r.ref_len = (int32_t)f[3].size();
+    r.alleles.push_back(f[3]);
+    if (f[4] != ".") {
+      std::stringstream alts(f[4]);
+      std::string a;
+      while (std::getline(alts, a, ',')) r.alleles.push_back(a);
+    }
+    const bool has_start = info_int(f[7], "START", r.start), has_end = info_int(f[7], "END", r.end);
+    r.has_span = has_start && has_end;
+    v->chroms[f[0]].push_back(r);
+  }
+  *out = v.release();
+  return HIPSTR_OK;
+}
+
+void hipstr_str_vcf_close(hipstr_str_vcf_t* v) { delete v; }
+
+int32_t hipstr_str_vcf_alleles(hipstr_str_vcf_t* v, const char* chrom, int32_t region_start, int32_t region_stop, int32_t* pos,
+                               int32_t* n_alleles, const char** alleles_text) {
+  if (!v || !chrom || !pos || !n_alleles || !alleles_text) return -1;
+  *pos = -1;
+  *n_alleles = 0;
+  v->result.clear();
+  *alleles_text = v->result.c_str();
+  auto it = v->chroms.find(chrom);
+  if (it == v->chroms.end()) return 0;
+  const int32_t pad = 50;   // vcf_input.cpp:19
+  const int32_t pad_start = region_start < pad ? 0 : region_start - pad;
+  const int32_t beg = pad_start > 0 ? pad_start - 1 : 0, end = region_stop + pad;   // the tabix region "chrom:pad_start-end"
+  for (const hipstr_str_vcf::Record& r : it->second) {
+    if (!(r.pos - 1 < end && r.pos - 1 + r.ref_len > beg)) continue;
+    if (!r.has_span) continue;          // not an STR record
+    if (r.start == region_start + 1 && r.end == region_stop) {
+      *pos = r.pos - 1;
+      *n_alleles = (int32_t)r.alleles.size();
+      for (const std::string& a : r.alleles) { v->result += a; v->result += '\n'; }
+      *alleles_text = v->result.c_str();
+      return 1;
+    }
+    if (r.pos > region_start + pad) break;
+  }
+  return 0;
+}
+
+}  // extern "C"

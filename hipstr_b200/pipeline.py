@@ -38,6 +38,7 @@ class Options:
     filter = None                   # dict of hipstr_filter_options_t overrides
     host_threads = 0                # 0 = HIPSTR_HOST_THREADS / all cores
     bams_from_10x = False           # phasing from the reads' HP tags (native driver only)
+    ref_vcf = None                  # path of a reference panel of STR genotypes (--ref-vcf; native driver only)
 
     def __init__(self, **kw):
         for k, v in kw.items():
@@ -102,6 +103,8 @@ def process_regions(ctx, bam_paths, chrom_seqs, regions, options=None, vcf_optio
     po.n_haploid_chroms, po.haploid_chroms = len(opt.haploid_chroms), hap
     po.host_threads = opt.host_threads
     po.bams_from_10x = int(bool(opt.bams_from_10x))
+    panel = capi.StrVcf(opt.ref_vcf) if opt.ref_vcf else None
+    po.ref_vcf = panel.h if panel else None
     vo = capi.VcfOptions()
     lib.hipstr_vcf_default_options(C.byref(vo))
     for k, v in (vcf_options or {}).items():

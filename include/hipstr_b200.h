@@ -754,6 +754,15 @@ hipstr_status_t hipstr_snp_vcf_region_sets(hipstr_snp_vcf_t* vcf, const char* ch
                                            int32_t* found, const int32_t** set_off, const uint32_t** snp_pos,
                                            const char** snp_base1, const char** snp_base2);
 
+/* The reference panel (--ref-vcf): read_vcf_alleles (src/vcf_input.cpp:21-50) -- among the records overlapping the region
+ * padded by 50 bp, the first whose INFO START / END equal region start + 1 / region stop gives *pos (0-based POS) and the
+ * alleles (REF first, one per line in *alleles_text, valid until the next call); returns 1, or 0 when there is none. */
+typedef struct hipstr_str_vcf hipstr_str_vcf_t;
+hipstr_status_t hipstr_str_vcf_open(const char* path, hipstr_str_vcf_t** out);
+void hipstr_str_vcf_close(hipstr_str_vcf_t* vcf);
+int32_t hipstr_str_vcf_alleles(hipstr_str_vcf_t* vcf, const char* chrom, int32_t region_start, int32_t region_stop, int32_t* pos,
+                               int32_t* n_alleles, const char** alleles_text);
+
 /* --- the per-region driver: BAM files -> VCF records for a WINDOW of regions -----
  * Replaces, for BAM input, BamProcessor::process_regions (src/bam_processor.cpp:521-617) -> SNPBamProcessor::process_reads
  * (src/snp_bam_processor.cpp:36-118) -> GenotyperBamProcessor::analyze_reads_and_phasing / learn_stutter_model
@@ -784,6 +793,8 @@ typedef struct {
   int32_t host_threads;                /* 0 = HIPSTR_HOST_THREADS / all cores */
   int32_t bams_from_10x;               /* --10x-bams: phasing from the reads' HP tags (SNPBamProcessor::process_10x_reads,
                                           src/snp_bam_processor.cpp:140-200) instead of a SNP VCF */
+  struct hipstr_str_vcf* ref_vcf;      /* --ref-vcf: genotype the alleles of this reference panel (hipstr_str_vcf_open) instead of
+                                          alleles found in the reads; NULL = none */
 } hipstr_pipeline_options_t;
 typedef struct hipstr_region_results hipstr_region_results_t;
 void hipstr_pipeline_default_options(hipstr_pipeline_options_t* options);

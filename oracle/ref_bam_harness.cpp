@@ -31,6 +31,7 @@
 #include "snp_phasing_quality.h"
 #include "snp_tree.h"
 #include "vcf_reader.h"
+#include "vcf_input.h"
 extern "C" {
 #include "htslib/htslib/tbx.h"
 }
@@ -264,7 +265,8 @@ void ref_alignment_filters(int32_t pos, int32_t end_pos, const char* bases, cons
  *            REMOVE_PCR_DUPS, REQUIRE_PAIRED_READS, recalc_stutter_model_ (0/1), output GLs, output PLs, output FILTERS,
  *            treat chr1 as haploid (--haploid-chrs chr1), BAMs carry 10X haplotype tags (--10x-bams)}. */
 int32_t ref_process_regions(int32_t n_files, const char* const* paths, const char* fasta_path, const char* region_path,
-                            const char* vcf_out_path, const int32_t* options, const char* snp_vcf_path /* NULL = none */) {
+                            const char* vcf_out_path, const int32_t* options, const char* snp_vcf_path /* NULL = none */,
+                            const char* ref_vcf_path /* NULL = none */) {
   std::vector<std::string> files(paths, paths + n_files);
   precompute_integer_logs();   // hipstr_main.cpp:352
   GenotyperBamProcessor proc(true, options[2] != 0);
@@ -290,6 +292,7 @@ int32_t ref_process_regions(int32_t n_files, const char* const* paths, const cha
     }
   }
   if (snp_vcf_path != NULL) proc.set_input_snp_vcf(snp_vcf_path);
+  if (ref_vcf_path != NULL) proc.set_ref_vcf(ref_vcf_path);
   proc.set_output_str_vcf(vcf_out_path, fasta_path, "harness", samples);
   proc.process_regions(reader, region_path, fasta_path, rg_to_sample, rg_to_library, "harness", NULL, NULL, 10000000, "");
   proc.finish();
@@ -339,6 +342,20 @@ int32_t ref_snp_sets(const char* snp_vcf_path, const char* chrom, int32_t region
   if ((int32_t)s.size() + 1 > cap) return -2;
   memcpy(out_text, s.c_str(), s.size() + 1);
   return (int32_t)s.size();
+}
+
+/* read_vcf_alleles (src/vcf_input.cpp:21-50) on a bgzipped + tabix-indexed panel: returns 1 and pos / the alleles (one per line), or 0. */
+int32_t ref_read_vcf_alleles(const char* vcf_path, const char* chrom, int32_t region_start, int32_t region_stop, int32_t period, int32_t* pos,
+                             int32_t cap, char* out_text) {
+  VCF::VCFReader reader(vcf_path);
+  Region region(chrom, region_start, region_stop, period);
+  std::vector<std::string> alleles;
+  if (!read_vcf_alleles(&reader, region, alleles, *pos)) return 0;
+  std::string s;
+  for (size_t i = 0; i < alleles.size(); i++) { s += alleles[i]; s += '\n'; }
+  if ((int32_t)s.size() + 1 > cap) return -2;
+  memcpy(out_text, s.c_str(), s.size() + 1);
+  return 1;
 }
 
 }  // extern "C"

@@ -15,14 +15,14 @@ canon = lambda t: t.replace(":-0.00:", ":0.00:")
 
 
 def run_reference(paths, fasta, bed, out_vcf, def_stutter, min_total_reads=20, remove_dups=1, require_paired=1, recalc=0, gls=0, pls=0,
-                  filters=0, snp_vcf=None, haploid=0, tenx=0):
+                  filters=0, snp_vcf=None, haploid=0, tenx=0, ref_vcf=None):
     f = checkers.ref().ref_process_regions
     f.restype = C.c_int32
-    f.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.c_char_p]
+    f.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.c_char_p, C.c_char_p]
     arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
     o = np.array([def_stutter, min_total_reads, remove_dups, require_paired, recalc, gls, pls, filters, haploid, tenx], np.int32)
     assert f(len(paths), arr, fasta.encode(), bed.encode(), out_vcf.encode(), o.ctypes.data_as(C.POINTER(C.c_int32)),
-             snp_vcf.encode() if snp_vcf else None) == 0
+             snp_vcf.encode() if snp_vcf else None, ref_vcf.encode() if ref_vcf else None) == 0
     import gzip
     with gzip.open(out_vcf, "rt") as fh:       # the reference always writes BGZF (bgzfostream)
         lines = fh.read().splitlines()
@@ -172,3 +172,65 @@ def test_process_regions_needs_a_device():
     st = lib.hipstr_process_regions(None, 1, mk(["x.bam"]), None, 1, mk(["chr1"]), mk(["ACGT"]), 0, None, None, None, None, None, C.byref(po),
                                     C.byref(vo), C.byref(h))
     assert capi.STATUS[st] == "NO_DEVICE" and not h.value
+
+
+def _panel_from_reference(sc, paths, fasta, bed, tmp_path):
+    """A reference panel = the reference program's own STR VCF of these files (EM-trained models), re-indexed with tabix."""
+    import gzip
+    run_reference(paths, fasta, bed, str(tmp_path / "panel_src.vcf"), 0)
+    text = str(tmp_path / "panel.vcf")
+    with gzip.open(str(tmp_path / "panel_src.vcf"), "rt") as src, open(text, "w") as dst:
+        dst.write(src.read())
+    gz = str(tmp_path / "panel.vcf.gz")
+    ref = checkers.ref()
+    ref.ref_vcf_bgzip_tabix.restype = C.c_int32
+    ref.ref_vcf_bgzip_tabix.argtypes = [C.c_char_p, C.c_char_p]
+    assert ref.ref_vcf_bgzip_tabix(text.encode(), gz.encode()) == 0
+    return gz
+
+
+@needs_ref
+def test_reference_panel_alleles_match_read_vcf_alleles(tmp_path):
+    """hipstr_str_vcf_alleles against read_vcf_alleles (src/vcf_input.cpp) on the reference program's own output (CPU only)."""
+    from hipstr_b200.capi import StrVcf
+    sc = MultiScenario(12, n_regions=4, n_fragments=600)
+    paths, fasta, bed = files_of(sc, tmp_path)
+    gz = _panel_from_reference(sc, paths, fasta, bed, tmp_path)
+    f = checkers.ref().ref_read_vcf_alleles
+    f.restype = C.c_int32
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_char_p]
+    panel = StrVcf(gz)
+    found = 0
+    queries = [(s, e, p) for s, e, p in sc.regions] + [(s + 1, e, p) for s, e, p in sc.regions] + [(100, 130, 3), (sc.regions[0][0] - 60, sc.regions[0][0] - 30, 2)]
+    for start, stop, period in queries:
+        pos, buf = C.c_int32(), C.create_string_buffer(1 << 16)
+        rc = f(gz.encode(), b"chr1", start, stop, period, C.byref(pos), len(buf), buf)
+        got = panel.alleles("chr1", start, stop)
+        if rc == 1:
+            assert got == (pos.value, buf.value.decode().splitlines()), (start, stop)
+            found += 1
+        else:
+            assert got is None, (start, stop)
+    assert found >= 3
+    assert panel.alleles("chr7", 100, 130) is None
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_bam_to_vcf_with_reference_panel(tmp_path):
+    """--ref-vcf: the alleles of a reference panel are genotyped instead of alleles found in the reads."""
+    from hipstr_b200 import capi, pipeline
+    sc = MultiScenario(12, n_regions=4, n_fragments=600)
+    paths, fasta, bed = files_of(sc, tmp_path)
+    gz = _panel_from_reference(sc, paths, fasta, bed, tmp_path)
+    s1, e1, p1 = sc.regions[1]
+    sc.regions[1] = (s1 + 1, e1, p1)          # the panel has no record with these coordinates: the locus must fail in both
+    with open(bed, "w") as fh:
+        fh.write(sc.region_text())
+    header, want = run_reference(paths, fasta, bed, str(tmp_path / "ref.vcf"), 0, ref_vcf=gz)
+    opt = pipeline.Options(min_total_reads=20, ref_vcf=gz)
+    with capi.Context(0) as ctx:
+        records, summary = pipeline.process_regions(ctx, paths, pipeline.read_fasta(fasta), pipeline.read_regions(bed), opt)
+    print(summary)
+    assert [canon(r[2]) for r in records] == [canon(w) for w in want] and len(want) == 3
+    assert summary["genotype_failed"] == 1
