@@ -276,6 +276,7 @@ int BamFile::read_record(BamRecord& rec, const int32_t* str_region) {
     if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += (int32_t)(v >> 4);   // M D N = X consume the reference
   }
   rec.end_pos = (!(rec.flag & 0x4) && n_cigar > 0) ? pos + ref_len : pos + 1;   // bam_endpos
+  if (l_seq == 0) rec.cigar.clear();   // BamAlignment::ExtractSequenceFields returns before the CIGAR when there is no sequence (bam_io.cpp:15-19)
   if (str_region) {   // the first two tests of read_and_filter_reads, which need none of the fields decoded below
     if (rec.paired() && !rec.first_mate() && !rec.second_mate()) return 2;
     if (rec.pos > str_region[1] || rec.end_pos < str_region[0]) {

@@ -304,3 +304,41 @@ def test_golden_bam_fixture():
     filtered = recs.filter(meta["chrom"], [tuple(meta["region"])], rg_map)
     with open(os.path.join(GOLDEN, "ingest_f0.filtered.txt")) as fh:
         assert filtered.text() == fh.read()
+
+
+@needs_ref
+def test_bam_decoding_edge_cases(tmp_path):
+    """Records htslib accepts that the simulator never writes: no sequence / no qualities, IUPAC codes (which the reference
+    maps to blanks), every CIGAR operation, unmapped reads placed at their mate, all auxiliary value types, small integer types
+    for AS / XS, a second chromosome."""
+    head = ["@HD\tVN:1.5\tSO:coordinate", "@SQ\tSN:chr1\tLN:100000", "@SQ\tSN:chr2\tLN:5000", "@RG\tID:g\tSM:s\tLB:l", "@RG\tID:h\tSM:t"]
+    recs = [
+        ("plain", 99, "chr1", 1000, 60, "10M", "=", 1200, 210, "ACGTACGTAC", "IIIIIIIIII", ["RG:Z:g", "AS:i:10", "XS:i:3"]),
+        ("noseq", 0, "chr1", 1001, 0, "5M", "*", 0, 0, "*", "*", ["RG:Z:g"]),
+        ("noqual", 16, "chr1", 1002, 30, "4M", "*", 0, 0, "ACGT", "*", ["RG:Z:h", "XA:Z:chr2,+100,4M,0;"]),
+        ("iupac", 0, "chr1", 1003, 30, "8M", "*", 0, 0, "ACRYKMNT", "!#5?IJ~~", ["RG:Z:g", "NM:i:2", "MD:Z:8"]),
+        ("ops", 0, "chr1", 1004, 30, "2H3S4M2I3D5N2=1X1P2M4S", "*", 0, 0, "A" * 18, "I" * 18, ["RG:Z:g", "SA:Z:chr2,5,+,3S4M,60,0;"]),
+        ("unmapped_mate", 69, "chr1", 1005, 0, "*", "=", 1005, 0, "ACGTAC", "IIIIII", ["RG:Z:g"]),
+        ("tags", 0, "chr1", 1006, 30, "6M", "*", 0, 0, "ACGTAC", "IIIIII",
+         ["XA:Z:chr1,-90,6M,1;chr2,+7,6M,0;", "AS:i:200", "XS:i:-3", "RG:Z:h", "ZF:f:1.5", "ZA:A:x", "ZB:B:c,1,-2,3", "ZS:B:S,1,2", "ZI:B:i,70000", "ZH:H:1AE3", "HP:i:2"]),
+        ("big_as", 0, "chr1", 1007, 30, "6M", "*", 0, 0, "ACGTAC", "IIIIII", ["AS:i:70000", "XS:i:300", "RG:Z:g"]),
+        ("long_" + "n" * 200, 147, "chr1", 1200, 60, "10M", "=", 1000, -210, "ACGTACGTAC", "IIIIIIIIII", ["RG:Z:g"]),
+        ("far", 0, "chr1", 90000, 60, "10M", "*", 0, 0, "ACGTACGTAC", "IIIIIIIIII", ["RG:Z:g"]),
+        ("other", 0, "chr2", 100, 60, "10M", "chr1", 1000, 0, "ACGTACGTAC", "IIIIIIIIII", ["RG:Z:g"]),
+    ]
+    sam = tmp_path / "edge.sam"
+    with open(sam, "w") as fh:
+        fh.write("\n".join(head) + "\n")
+        for r in recs:
+            fh.write("\t".join([r[0], str(r[1]), r[2], str(r[3]), str(r[4]), r[5], r[6], str(r[7]), str(r[8]), r[9], r[10]] + r[11]) + "\n")
+    bam = str(tmp_path / "edge.bam")
+    ref = checkers.ref()
+    ref.ref_sam_to_bam.restype = C.c_int32
+    ref.ref_sam_to_bam.argtypes = [C.c_char_p, C.c_char_p]
+    assert ref.ref_sam_to_bam(str(sam).encode(), bam.encode()) == 0
+    reader = capi.BamReader([bam])
+    for chrom, start, end in (("chr1", 0, 100000), ("chr1", 990, 1010), ("chr1", 1004, 1005), ("chr1", 1011, 1013), ("chr1", 1016, 1019),
+                              ("chr1", 89990, 90001), ("chr2", 0, 5000), ("chr1", 50000, 60000)):
+        assert reader.fetch(chrom, start, end).text() == ref_region_reads([bam], chrom, start, end), (chrom, start, end)
+    assert len(reader.fetch("chr1", 0, 100000)) == 10
+    assert reader.read_groups() == [(bam, "g", "s", "l"), (bam, "h", "t", None)]
