@@ -119,8 +119,10 @@ bool parse(const std::string& text, hipstr_snp_vcf& v, std::string& err) {
     }
     if (n_col < 8) { err = "Failed to parse VCF record"; return false; }
     auto width = [&](int c) { return (size_t)((c + 1 < n_col ? col[c + 1] - 1 : end) - col[c]); };
-    // biallelic SNP: REF and the single ALT are one character each
-    if (width(3) != 1 || width(4) != 1 || col[4][0] == '.') continue;
+    // biallelic SNP (n_allele == 2 && bcf_is_snp): REF and the single ALT are one character each; like htslib, mpileup's
+    // symbolic <X> / <*> alternates count as SNPs too (their "base" is then the '<' the reference takes from allele[0])
+    const bool symbolic = width(4) == 3 && col[4][0] == '<' && (col[4][1] == 'X' || col[4][1] == '*') && col[4][2] == '>';
+    if (width(3) != 1 || !(symbolic || (width(4) == 1 && col[4][0] != '.'))) continue;
     if (n_col < 10 || v.samples.empty()) continue;
     // index of GT in FORMAT
     int gt_index = -1, k = 0;

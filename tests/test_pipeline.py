@@ -234,3 +234,47 @@ def test_bam_to_vcf_with_reference_panel(tmp_path):
     print(summary)
     assert [canon(r[2]) for r in records] == [canon(w) for w in want] and len(want) == 3
     assert summary["genotype_failed"] == 1
+
+
+@needs_ref
+def test_snp_vcf_edge_cases_match_create_snp_trees(tmp_path):
+    """Records the simulator never writes: GT not first in FORMAT, spanning-deletion and symbolic alternates (which htslib counts
+    as SNPs), haploid and missing calls, a multi-base REF, no FORMAT column data beyond GT."""
+    from hipstr_b200.capi import SnpVcf
+    head = ["##fileformat=VCFv4.2", "##contig=<ID=chr1,length=100000>", '##FORMAT=<ID=GT,Number=1,Type=String,Description="g">',
+            '##FORMAT=<ID=DP,Number=1,Type=Integer,Description="d">', '##INFO=<ID=AF,Number=A,Type=Float,Description="a">',
+            "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\tC"]
+    rows = [
+        (5000, "A", "C", "GT", ["0|1", "1|0", "1|1"]),
+        (5010, "G", "T", "DP:GT", ["5:0|1", "7:1|0", "9:0/1"]),
+        (5020, "C", "*", "GT", ["0|1", "0|1", "0|0"]),
+        (5030, "T", "<X>", "GT:DP", ["0|1:3", "1|0:4", ".|.:0"]),
+        (5040, "AC", "A", "GT", ["0|1", "0|1", "0|1"]),
+        (5050, "A", "C,G", "GT", ["0|1", "1|2", "0|2"]),
+        (5060, "G", "A", "GT", ["0|1", ".", "./."]),
+        (5070, "T", "A", "GT", ["1|0", "0|1", "1|0"]),
+        (5080, "C", ".", "GT", ["0|0", "0|0", "0|0"]),
+        (5090, "a", "g", "GT", ["0|1", "1|0", "0|1"]),
+    ]
+    text = "\n".join(head + ["chr1\t%d\trs%d\t%s\t%s\t50\tPASS\tAF=0.5\t%s\t%s" % (p, p, r, a, f, "\t".join(g)) for p, r, a, f, g in rows]) + "\n"
+    plain, gz = str(tmp_path / "edge.vcf"), str(tmp_path / "edge.vcf.gz")
+    with open(plain, "w") as fh:
+        fh.write(text)
+    ref = checkers.ref()
+    ref.ref_vcf_bgzip_tabix.restype = C.c_int32
+    ref.ref_vcf_bgzip_tabix.argtypes = [C.c_char_p, C.c_char_p]
+    assert ref.ref_vcf_bgzip_tabix(plain.encode(), gz.encode()) == 0
+    f = ref.ref_snp_sets
+    f.restype = C.c_int32
+    f.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_char_p]
+    vcf = SnpVcf(gz)
+    for start, stop in ((5200, 5230), (4900, 4930), (5044, 5048)):
+        buf = C.create_string_buffer(1 << 16)
+        n = f(gz.encode(), b"chr1", start, stop, 3, 1000, 15, len(buf), buf)
+        assert n >= 0
+        off, pos, b1, b2 = vcf.region_sets("chr1", start - 1000, stop + 1000, [(start, stop)], 15)
+        lines = []
+        for s, name in enumerate(vcf.samples):
+            lines.append("S " + name)
+            lines += ["%d %s %s" % (pos[k], chr(b1[k]), chr(b2[k])) for k in range(off[s], off[s + 1])]
+        assert "\n".join(lines) + "\n" == buf.raw[:n].decode(), (start, stop)
