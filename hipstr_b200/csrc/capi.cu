@@ -37,6 +37,9 @@ struct DevBuf {
 
 struct hipstr_dev_batch {
   DevBuf pools, bases, quals, hapsides, hapbytes, blocks, reps, progs, logrun, tabs, mask, jobs[kNumColVariants];
+  DevBuf slot_reps, stut_jobs, pool_t_off;      // K1a: stutter-table slots, jobs, slab offsets
+  std::vector<FlatBatch::Chunk> chunks;         // pool ranges whose stutter tables fit the table buffer
+  int32_t stut_n_max = 16;
   int32_t n_jobs[kNumColVariants];
   int32_t n_max[kNumColVariants], l_max[kNumColVariants];
   int64_t n_out = 0, n_alignments = 0;
@@ -44,6 +47,7 @@ struct hipstr_dev_batch {
   void release() {
     pools.release(); bases.release(); quals.release(); hapsides.release(); hapbytes.release();
     blocks.release(); reps.release(); progs.release(); logrun.release(); tabs.release(); mask.release();
+    slot_reps.release(); stut_jobs.release(); pool_t_off.release();
     for (auto& j : jobs) j.release();
   }
 };
@@ -80,6 +84,8 @@ struct hipstr_ctx {
   hipstr_dev_batch scratch;              // reused by hipstr_align_batch_host
   hipstr_dev_genotype gscratch;          // reused by hipstr_genotype_batch_host
   DevBuf d_ll, d_pos, d_misc[12], d_out[6], d_last, d_counters;
+  DevBuf d_stut;                         // stutter tables of the chunk in flight (K1a -> K1b)
+  float last_stutter_ms = 0.f;           // of the timed align call: K1a's share
   double* d_debug = nullptr;             // test hook, see hipstr_debug_lastcols
   double trace_seconds[4] = {0, 0, 0, 0};   // accumulated over hipstr_trace_batch_host calls: lowering, ordering + uploads, kernel, downloads
 };
@@ -148,6 +154,11 @@ hipstr_status_t stage(hipstr_ctx* ctx, const hipstr_align_batch_t* batch, hipstr
   CU(put(d.logrun, f.prog_logrun, s));
   CU(put(d.tabs, f.rep_tabs, s));
   CU(put(d.mask, f.hap_mask, s));
+  CU(put(d.slot_reps, f.slot_reps, s));
+  CU(put(d.stut_jobs, f.stut_jobs, s));
+  CU(put(d.pool_t_off, f.pool_t_off, s));
+  d.chunks = f.chunks;
+  d.stut_n_max = f.stut_n_max;
   for (int v = 0; v < kNumColVariants; v++) {
     CU(put(d.jobs[v], f.jobs[v], s));
     d.n_jobs[v] = (int32_t)f.jobs[v].size();
@@ -184,19 +195,48 @@ hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll
   int l_all = 2;
   for (int v = 0; v < kNumColVariants; v++) if (d.n_jobs[v]) l_all = std::max(l_all, d.l_max[v]);
   CU(ctx->d_last.reserve((size_t)HIPSTR_MAX_ALIGN_CTAS * HIPSTR_WARPS_PER_CTA * 2 * l_all * sizeof(double)));
-  CU(ctx->d_counters.reserve(kNumColVariants * sizeof(int32_t)));
-  CU(cudaMemsetAsync(ctx->d_counters.p, 0, kNumColVariants * sizeof(int32_t), ctx->stream));
+  // one job counter per launch: K1a + up to kNumColVariants K1b launches per chunk
+  const size_t n_counters = std::max<size_t>(1, d.chunks.size()) * (kNumColVariants + 1);
+  CU(ctx->d_counters.reserve(n_counters * sizeof(int32_t)));
+  CU(cudaMemsetAsync(ctx->d_counters.p, 0, n_counters * sizeof(int32_t), ctx->stream));
+  int64_t t_max = 2;
+  for (const FlatBatch::Chunk& ck : d.chunks) t_max = std::max(t_max, ck.t_doubles);
+  CU(ctx->d_stut.reserve((size_t)t_max * sizeof(double)));
   p.last_scratch = (double*)ctx->d_last.p;
-  for (int v = kNumColVariants - 1; v >= 0; v--) {   // longest reads first
-    if (d.n_jobs[v] == 0) continue;
-    p.jobs = (const DevJob*)d.jobs[v].p;
-    p.n_jobs = d.n_jobs[v];
-    p.n_max = d.n_max[v];
-    p.l_max = l_all;
-    p.debug_out = ctx->d_debug;
-    p.job_counter = (int32_t*)ctx->d_counters.p + v;
-    CU(launch_align(v, p, HIPSTR_MAX_ALIGN_CTAS, ctx->stream, nullptr));
-    ctx->last_launches++;
+  p.stut = (const double*)ctx->d_stut.p;
+  p.pool_t_off = (const int64_t*)d.pool_t_off.p;
+  p.l_max = l_all;
+  p.debug_out = ctx->d_debug;
+  StutParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.n_max = d.stut_n_max;
+  sp.pools = p.pools; sp.bases = p.bases; sp.quals = p.quals;
+  sp.slot_reps = (const DevSlotReps*)d.slot_reps.p;
+  sp.reps = p.reps; sp.progs = p.progs; sp.prog_logrun = p.prog_logrun; sp.rep_tabs = p.rep_tabs;
+  sp.qual_lut = p.qual_lut; sp.int_logs = p.int_logs;
+  sp.pool_t_off = p.pool_t_off;
+  sp.stut = (double*)ctx->d_stut.p;
+  for (size_t c = 0; c < d.chunks.size(); c++) {
+    const FlatBatch::Chunk& ck = d.chunks[c];
+    int32_t* counters = (int32_t*)ctx->d_counters.p + c * (kNumColVariants + 1);
+    // K1a: the stutter tables of the chunk's (read, allele) pairs; K1b of the same chunk follows on the stream and the
+    // next chunk's K1a, which overwrites the buffer, follows that
+    if (ck.stut_job1 > ck.stut_job0) {
+      sp.jobs = (const DevStutJob*)d.stut_jobs.p + ck.stut_job0;
+      sp.n_jobs = ck.stut_job1 - ck.stut_job0;
+      sp.job_counter = counters + kNumColVariants;
+      CU(launch_stutter(sp, ctx->stream));
+      ctx->last_launches++;
+    }
+    for (int v = kNumColVariants - 1; v >= 0; v--) {   // longest reads first
+      if (ck.job1[v] == ck.job0[v]) continue;
+      p.jobs = (const DevJob*)d.jobs[v].p + ck.job0[v];
+      p.n_jobs = ck.job1[v] - ck.job0[v];
+      p.n_max = d.n_max[v];
+      p.job_counter = counters + v;
+      CU(launch_align(v, p, HIPSTR_MAX_ALIGN_CTAS, ctx->stream, nullptr));
+      ctx->last_launches++;
+    }
   }
   return HIPSTR_OK;
 }
@@ -362,6 +402,7 @@ void hipstr_destroy(hipstr_ctx_t* ctx) {
   ctx->d_pos.release();
   ctx->d_last.release();
   ctx->d_counters.release();
+  ctx->d_stut.release();
   for (auto& b : ctx->d_misc) b.release();
   for (auto& b : ctx->d_out) b.release();
   for (auto& ev : ctx->pending) for (auto& e : ev.e) cudaEventDestroy(e);
@@ -929,7 +970,7 @@ hipstr_status_t hipstr_snp_phasing_batch_host(hipstr_ctx_t* ctx, const hipstr_sn
   }
   for (int s = 0; s < b->n_sets; s++)
     for (int i = b->set_off[s] + 1; i < b->set_off[s + 1]; i++)
-      if (b->snp_pos[i] <= b->snp_pos[i - 1]) return fail(ctx, HIPSTR_ERR_BAD_ARG, "SNP positions of a set must be ascending and distinct");
+      if (b->snp_pos[i] < b->snp_pos[i - 1]) return fail(ctx, HIPSTR_ERR_BAD_ARG, "SNP positions of a set must be non-decreasing");
   cudaStream_t s = ctx->stream;
   DevBuf* m = ctx->d_misc;
   DevBuf* o = ctx->d_out;

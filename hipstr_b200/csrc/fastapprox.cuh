@@ -65,6 +65,14 @@ __device__ __forceinline__ double lse_term(double v, double mx) {
   const double diff = v - mx;
   return diff > HIPSTR_LOG_THRESH ? (double)coarse_exp(__double2float_rn(diff)) : 0.0;
 }
+// the same term when the caller has no use for the clamp of fasterpow2: diff > log(0.001) keeps 1.4427 * diff far
+// above -126, so the clamp never fires and the results are identical
+__device__ __forceinline__ double lse_term_near(double v, double mx) {
+  const double diff = v - mx;
+  const float x = __fmul_rn(1.442695040f, __double2float_rn(diff));
+  const float e = __uint_as_float(__float2uint_rz(__fmul_rn(8388608.0f, __fadd_rn(x, 126.94269504f))));
+  return diff > HIPSTR_LOG_THRESH ? (double)e : 0.0;
+}
 __device__ __forceinline__ double lse_finish(double mx, double total) {
   return mx + (double)coarse_log(__double2float_rn(total));
 }

@@ -45,6 +45,8 @@ void FlatBatch::clear() {
   pools.clear(); bases.clear(); quals.clear();
   hapsides.clear(); hapbytes.clear(); blocks.clear(); reps.clear(); progs.clear(); prog_logrun.clear(); rep_tabs.clear(); hap_mask.clear();
   for (auto& j : jobs) j.clear();
+  slot_reps.clear(); stut_jobs.clear(); pool_t_off.clear(); chunks.clear();
+  stut_n_max = 16;
   n_out = n_alignments = 0;
 }
 
@@ -163,7 +165,7 @@ int pick_variant(int n_left, int n_right) {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-struct LocusInfo { int32_t hap_rec0, H, max_len; int64_t live_haps; };
+struct LocusInfo { int32_t hap_rec0, H, max_len; int64_t live_haps; int32_t slot0, n_slots; };
 // Bases travel to the device as codes 0..4.  The reference compares raw characters
 // (HapAligner.cpp:115,149); restricted to the alphabet ACGTN that is the same relation.
 // (A,C,T,G) = (c >> 1) & 3, which the bulk converter below computes without a table; N = 4.
@@ -219,6 +221,12 @@ inline unsigned convert_bases(const unsigned char* __restrict src, char* __restr
 
 }  // namespace
 
+int64_t stutter_table_budget_doubles() {
+  int64_t mb = 6144;
+  if (const char* e = std::getenv("HIPSTR_T_BUDGET_MB")) mb = std::max<int64_t>(1, std::atoll(e));
+  return mb * (1 << 20) / 8;
+}
+
 int64_t count_alignments(const hipstr_align_batch_t* b) {
   int64_t total = 0;
   for (int l = 0; l < b->n_loci; l++) {
@@ -263,6 +271,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     std::vector<DevProgEntry> progs;
     std::vector<double> prog_logrun;
     std::vector<int32_t> rep_tabs;
+    std::vector<DevSlotReps> slot_reps;
   };
   auto lower_locus = [b, fresh_rows](int l, Lowered& out, LocusInfo& li_out, std::string& err) -> hipstr_status_t {
     const int b0 = b->locus_block_off[l], nb = b->locus_block_off[l + 1] - b0;
@@ -407,6 +416,9 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
 
     // ---- haplotypes: oriented sequences + row classes with the reference's reuse history ----
     const int hap_rec0 = (int)out.hapsides.size();
+    const int slot0 = (int)out.slot_reps.size();
+    std::vector<std::vector<int> > slot_of(nb);   // [block][option] -> table slot of the locus, assigned at first use by a live haplotype
+    for (int k = 0; k < nb; k++) slot_of[k].assign(n_opts[k], -1);
     std::vector<int32_t> cur(nb), prev(nb);
     std::vector<std::vector<uint8_t> > cached[2];   // [side][oriented block] -> classes of its rows
     cached[0].resize(nb); cached[1].resize(nb);
@@ -448,6 +460,18 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
         for (int k = 0; k < nb; k++) {
           const int n = (int)opt[k]->seq[side].size();
           DevBlock db = {row, n, period[k] > 0 ? opt[k]->rep[side] : -1, 0};
+          if (period[k] > 0) {
+            const int src = side == 0 ? k : nb - 1 - k;
+            int& slot = slot_of[src][cur[src]];
+            if (slot < 0) {
+              slot = (int)out.slot_reps.size() - slot0;
+              DevSlotReps sr = {opt[k]->rep[side == 0 ? 0 : 1], 0};
+              sr.rep_fwd = blk[src].opts[cur[src]].rep[0];
+              sr.rep_rev = blk[src].opts[cur[src]].rep[1];
+              out.slot_reps.push_back(sr);
+            }
+            db.tslot = slot;
+          }
           out.blocks.push_back(db);
           if (period[k] > 0) {
             if (first_repeat_row < 0) { first_repeat_row = row; hs.first_rep = k; }
@@ -497,6 +521,8 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     li.max_len = max_len;
     li.live_haps = H;
     if (mask) { li.live_haps = 0; for (int64_t h = 0; h < H; h++) li.live_haps += mask[h] != 0; }
+    li.slot0 = slot0;
+    li.n_slots = (int32_t)out.slot_reps.size() - slot0;
     li_out = li;
     return HIPSTR_OK;
   };
@@ -528,7 +554,8 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     for (int c = 0; c < n_chunks; c++) {
       Lowered& p = parts[c];
       const int32_t side0 = (int32_t)out.hapsides.size(), byte0 = (int32_t)out.hapbytes.size(), blk0 = (int32_t)out.blocks.size(),
-                    rep0 = (int32_t)out.reps.size(), prog0 = (int32_t)out.progs.size(), tab0 = (int32_t)out.rep_tabs.size();
+                    rep0 = (int32_t)out.reps.size(), prog0 = (int32_t)out.progs.size(), tab0 = (int32_t)out.rep_tabs.size(),
+                    slots0 = (int32_t)out.slot_reps.size();
       for (DevHapSide& hs : p.hapsides)
         if (hs.len > 0) { hs.seq_off += byte0; hs.row_off += byte0; hs.blk_off += blk0; }   // (placeholders of masked haplotypes stay zero)
       for (DevBlock& db : p.blocks)
@@ -540,7 +567,9 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
         r.ins_off += tab0;
       }
       const int l0 = (int)((int64_t)b->n_loci * c / n_chunks), l1 = (int)((int64_t)b->n_loci * (c + 1) / n_chunks);
-      for (int l = l0; l < l1; l++) loci[l].hap_rec0 += side0;
+      for (int l = l0; l < l1; l++) { loci[l].hap_rec0 += side0; loci[l].slot0 += slots0; }
+      for (DevSlotReps& sr : p.slot_reps) { sr.rep_fwd += rep0; sr.rep_rev += rep0; }
+      out.slot_reps.insert(out.slot_reps.end(), p.slot_reps.begin(), p.slot_reps.end());
       out.hapsides.insert(out.hapsides.end(), p.hapsides.begin(), p.hapsides.end());
       out.hapbytes.insert(out.hapbytes.end(), p.hapbytes.begin(), p.hapbytes.end());
       out.hap_mask.insert(out.hap_mask.end(), p.hap_mask.begin(), p.hap_mask.end());
@@ -634,7 +663,11 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
 
   // ---- jobs ----
   // Split a pool's haplotypes over several warps only when the batch is too small to fill the GPU.
-  size_t count[kNumColVariants] = {0};
+  // Jobs are emitted in pool order, so a chunk of pools (stutter tables within the budget) is a contiguous range of
+  // every job list.
+  const int64_t budget = stutter_table_budget_doubles();
+  out.pool_t_off.resize((size_t)n_pools);
+  size_t count[kNumColVariants] = {0}, n_stut = 0;
   for (int l = 0; l < b->n_loci; l++) {
     const LocusInfo& li = loci[l];
     int chunk = li.H;
@@ -645,23 +678,50 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
       if (v == 255) continue;
       if (v == 254) { count[0]++; continue; }
       count[v] += per_pool;
-      out.n_max[v] = std::max(out.n_max[v], round_up(b->pool_seq_off[p + 1] - b->pool_seq_off[p], 4));
+      n_stut += (size_t)(li.n_slots + HIPSTR_STUT_SLOTS_PER_JOB - 1) / HIPSTR_STUT_SLOTS_PER_JOB;
+      const int len = b->pool_seq_off[p + 1] - b->pool_seq_off[p];
+      out.n_max[v] = std::max(out.n_max[v], round_up(len, 4));
       out.l_max[v] = std::max(out.l_max[v], round_up(li.max_len, 2));
+      out.stut_n_max = std::max(out.stut_n_max, round_up(len, 16));
     }
   }
-  size_t at[kNumColVariants];
+  size_t at[kNumColVariants], at_stut = 0;
   for (int v = 0; v < kNumColVariants; v++) { out.jobs[v].resize(count[v]); at[v] = 0; }
+  out.stut_jobs.resize(n_stut);
+  FlatBatch::Chunk ck;
+  auto open_chunk = [&] {
+    ck.stut_job0 = (int32_t)at_stut;
+    for (int v = 0; v < kNumColVariants; v++) ck.job0[v] = (int32_t)at[v];
+    ck.t_doubles = 0;
+  };
+  auto close_chunk = [&] {
+    ck.stut_job1 = (int32_t)at_stut;
+    bool any = ck.stut_job1 > ck.stut_job0;
+    for (int v = 0; v < kNumColVariants; v++) { ck.job1[v] = (int32_t)at[v]; any |= ck.job1[v] > ck.job0[v]; }
+    if (any) out.chunks.push_back(ck);
+  };
+  open_chunk();
   for (int l = 0; l < b->n_loci; l++) {
     const LocusInfo& li = loci[l];
     int chunk = li.H;
     if (total_pairs > 0 && total_pairs / li.H < 16384) chunk = (int)std::max<int64_t>(1, std::min<int64_t>(li.H, total_pairs / 16384));
     for (int p = b->locus_pool_off[l]; p < b->locus_pool_off[l + 1]; p++) {
       const uint8_t v = pool_variant[p];
+      out.pool_t_off[p] = 0;
       if (v == 255) continue;
       if (v == 254) {   // HapAligner.cpp:333-337: LL 0 for every haplotype, mask ignored
         DevJob j = {p, 0, li.H, 0};
         out.jobs[0][at[0]++] = j;
         continue;
+      }
+      const int len = b->pool_seq_off[p + 1] - b->pool_seq_off[p];
+      const int64_t need = (int64_t)li.n_slots * HIPSTR_NUM_ARTIFACTS * hipstr_t_pitch(len);
+      if (ck.t_doubles > 0 && ck.t_doubles + need > budget) { close_chunk(); open_chunk(); }
+      out.pool_t_off[p] = ck.t_doubles;
+      ck.t_doubles += need;
+      for (int s0 = 0; s0 < li.n_slots; s0 += HIPSTR_STUT_SLOTS_PER_JOB) {
+        DevStutJob sj = {p, li.slot0 + s0, std::min(HIPSTR_STUT_SLOTS_PER_JOB, li.n_slots - s0), s0};
+        out.stut_jobs[at_stut++] = sj;
       }
       for (int h0 = 0; h0 < li.H; h0 += chunk) {
         DevJob j = {p, h0, std::min(li.H, h0 + chunk), 0};
@@ -669,6 +729,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
       }
     }
   }
+  close_chunk();
   return HIPSTR_OK;
 }
 

@@ -82,6 +82,19 @@ struct FlatBatch {
   HostBuf<DevJob> jobs[kNumColVariants];
   int32_t n_max[kNumColVariants];            /* per variant: max read length (padded) */
   int32_t l_max[kNumColVariants];            /* per variant: max haplotype length (padded) */
+  /* K1a (stutter tables): the (repeat block, allele) slots of every locus, one job per (pooled read, up to
+   * HIPSTR_STUT_SLOTS_PER_JOB slots), and the slab offset of every pool inside its chunk's table buffer.  A chunk is a
+   * range of pools whose tables fit the budget: K1a then K1b run chunk by chunk over the same buffer. */
+  std::vector<DevSlotReps> slot_reps;
+  HostBuf<DevStutJob> stut_jobs;
+  HostBuf<int64_t> pool_t_off;
+  struct Chunk {
+    int32_t stut_job0, stut_job1;
+    int32_t job0[kNumColVariants], job1[kNumColVariants];
+    int64_t t_doubles;
+  };
+  std::vector<Chunk> chunks;
+  int32_t stut_n_max = 16;                   /* longest read with a K1a job (padded to 16) */
   int64_t n_out = 0;
   int64_t n_alignments = 0;
   void clear();
@@ -92,6 +105,8 @@ struct FlatBatch {
  * trace_optimal_aln sees: the haplotype is fixed, nothing is reused) instead of replaying the
  * reuse history of a process_reads run. */
 hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std::string& err, bool fresh_rows = false);
+/* Doubles of stutter table one chunk may hold (HIPSTR_T_BUDGET_MB, default 6144 MB). */
+int64_t stutter_table_budget_doubles();
 int64_t count_alignments(const hipstr_align_batch_t* b);
 
 /* Per-block option index of haplotype `hap`: closed form of the reflected mixed-radix Gray

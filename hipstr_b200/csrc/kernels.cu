@@ -27,285 +27,37 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/hipstr_b200.h"
 #include "fastapprox.cuh"
+#include "kcommon.cuh"
 #include "kernels.h"
 #include "layout.h"
 
 namespace hipstr {
 
-#define FULL 0xffffffffu
-#define IMPOSSIBLE (-1000000000.0)            /* HapAligner.cpp:20 */
 #define LOG_INS_TO_INS (-1.0)                 /* AlignmentModel.h:7 */
 #define LOG_INS_TO_MATCH (-0.4586751453870818910216436) /* AlignmentModel.h:8 */
 #define LOG_DEL_TO_DEL (-1.0)                 /* AlignmentModel.h:9 */
 #define LOG_DEL_TO_MATCH (-0.4586751453870818910216436) /* AlignmentModel.h:10 */
 
 __device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(FULL, v, 1); }
-__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
-
-// ------------------------------------------------------------------------------------------
-// Repeat-block evaluator: one (read side, repeat allele).  Everything is anchored at the right
-// ends like the reference: column q of the side pairs with allele base B-1 when it is the last
-// base of the block.  Bases are 0..4 codes (A,C,G,T,N); val[q*5 + x] is the emission
-// log-likelihood of read column q against haplotype base x (log_correct if equal, else
-// log_error), so an emission is ONE shared-memory load.
-// ------------------------------------------------------------------------------------------
-// Shared-memory accesses of the evaluator use explicit 32-bit shared-window addresses: the compiler
-// otherwise rebuilds the generic->shared base (S2UR/ULEA) inside the hot loop.
-__device__ __forceinline__ double lds_f64(unsigned addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
-  asm volatile("st.shared.f64 [%0], %1;" :: "r"(addr), "d"(v));
-}
-
-#define HIPSTR_COL_BYTES (HIPSTR_VAL_STRIDE * 8)
-
-// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) of a pooled read's packed bases + qualities ------
-// One elected lane arms an mbarrier with the byte count and issues the two bulk copies; the warp
-// then waits on the barrier's phase.  Sources are 16-byte aligned and padded by the host lowering.
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" :: "r"(bar), "r"(parity) : "memory");
-}
-
-struct RepCtx {
-  const uint8_t* s;          // oriented allele base codes (global, read-only)
-  const DevProgEntry* progs;
-  const double* prog_logrun;
-  const int32_t* diag;       // global: byte offsets of the right-anchored diagonal (see DevRep)
-  const int32_t* ins_tab;    // global: byte offsets of the periodic-copy sum
-  const DevRep* rep;
-  const double* int_logs;    // global
-  unsigned val;              // shared address: emission table of this side, column q at val + q*COL_BYTES
-  const uint8_t* code;       // shared: read base codes of this side
-  const double* match;       // shared: match_probs_ by side column
-  unsigned terms;            // shared address: this lane's term cache, slot s at terms + 256*s
-  int B, p, n_side;
-};
-
-#define HIPSTR_TERM_SLOTS 8    /* terms of one fast_log_sum_exp call kept in shared memory per lane ... */
-#define HIPSTR_TERM_EXTRA 8    /* ... and in a per-thread local array (L1) when a walk has more */
-
-// match_probs_[q] of StutterAlignerClass::load_read (StutterAlignerClass.cpp:12-53).
-__device__ __forceinline__ double rep_match_prob(const RepCtx& c, int q) {
-  const int terms = min(q + 1, c.B);
-  const unsigned col = c.val + q * HIPSTR_COL_BYTES;
-  double acc = 0.0;
-#pragma unroll 4
-  for (int t = 0; t < terms; t++) acc += lds_f64(col + __ldg(c.diag + t));
-  return acc;
-}
-
-// Replays one position walk for read column j (see DevProgEntry) and returns
-// fast_log_sum_exp(vector) of its terms (mathops.cpp:97-106).
-//   INS: align_pcr_insertion_reverse (StutterAlignerClass.cpp:59-104), `units` copies inserted, a
-//        moving step touches the `units` read bases upstream of the position;
-//   else align_pcr_deletion_reverse (:106-150), a moving step touches one read base.
-// Terms are parked in shared memory (they are few: the walk collapses runs of equivalent
-// positions) so maximum and sum need ONE pass; a longer walk falls back to a second pass.
-template <bool INS>
-__device__ __forceinline__ double rep_walk(const RepCtx& c, int prog_index, int stop, int j, int units, double lp0,
-                                           int tail_base) {
-  const DevProgEntry* prog = c.progs + prog_index;
-  const double* lr = c.prog_logrun + prog_index;
-  const unsigned col = c.val + (INS ? (j - c.p) : j) * HIPSTR_COL_BYTES;
-  const int stride = c.p * HIPSTR_COL_BYTES;
-  double lp = lp0, mx = lp0;
-  double extra[HIPSTR_TERM_EXTRA];
-  int n = 1;
-  sts_f64(c.terms, lp0);
-  // two steps are always in flight ahead of the one being applied (every walk ends with a terminal
-  // entry and the program array is padded, so reading two entries past the end of a walk is safe)
-  int4 cur = __ldg(reinterpret_cast<const int4*>(prog));
-  double cur_lr = __ldg(lr);
-  int4 nx1 = __ldg(reinterpret_cast<const int4*>(prog + 1));
-  double nx1_lr = __ldg(lr + 1);
-  prog += 2; lr += 2;
-  // deletion walks: the pair of emissions of the NEXT step is loaded while this step's adds run
-  double pa = 0.0, pb = 0.0;
-  if (!INS && cur.w && cur.x > stop) { pa = lds_f64(col + cur.y); pb = lds_f64(col + cur.z); }
-  while (cur.x > stop) {
-    const int4 nx2 = __ldg(reinterpret_cast<const int4*>(prog++));
-    const double nx2_lr = __ldg(lr++);
-    if (INS) {
-      if (cur.w) {
-        unsigned a = col + cur.y, b = col + cur.z;
-        for (int m = 0; m < units; m++, a -= stride, b -= stride) {
-          lp -= lds_f64(a);
-          lp += lds_f64(b);
-        }
-      }
-    } else {
-      const double va = pa, vb = pb;
-      if (nx1.w && nx1.x > stop) { pa = lds_f64(col + nx1.y); pb = lds_f64(col + nx1.z); }
-      if (cur.w) { lp -= va; lp += vb; }
-    }
-    const double term = lp + cur_lr;
-    if (n < HIPSTR_TERM_SLOTS) sts_f64(c.terms + 256 * n, term);
-    else if (n < HIPSTR_TERM_SLOTS + HIPSTR_TERM_EXTRA) extra[n - HIPSTR_TERM_SLOTS] = term;
-    n++;
-    mx = dmax(mx, term);
-    cur = nx1; cur_lr = nx1_lr;
-    nx1 = nx2; nx1_lr = nx2_lr;
-  }
-  double tail = 0.0;
-  const bool has_tail = INS ? (cur.x > -tail_base) : (-cur.x < tail_base);
-  if (has_tail) {
-    tail = __ldg(c.int_logs + (tail_base + cur.x)) + lp;
-    mx = dmax(mx, tail);
-  }
-  double total = has_tail ? lse_term(tail, mx) : 0.0;
-  if (n <= HIPSTR_TERM_SLOTS + HIPSTR_TERM_EXTRA) {
-    // the cached terms are independent: load them all, then evaluate (the sum of the float results
-    // in a double is exact in any order, see the header of this file)
-    double tv[HIPSTR_TERM_SLOTS];
-#pragma unroll
-    for (int s = 0; s < HIPSTR_TERM_SLOTS; s++) tv[s] = s < n ? lds_f64(c.terms + 256 * s) : -1.0e300;
-    double part[2] = {0.0, 0.0};
-#pragma unroll
-    for (int s = 0; s < HIPSTR_TERM_SLOTS; s++) part[s & 1] += lse_term(tv[s], mx);
-    total += part[0] + part[1];
-    for (int s = HIPSTR_TERM_SLOTS; s < n; s++) total += lse_term(extra[s - HIPSTR_TERM_SLOTS], mx);
-    return lse_finish(mx, total);
-  }
-  // rare: more terms than slots -> replay the walk, summing against the known maximum
-  lp = lp0;
-  total += lse_term(lp0, mx);
-  prog -= (n - 1) + 2;
-  lr -= (n - 1) + 2;
-  cur = __ldg(reinterpret_cast<const int4*>(prog));
-  cur_lr = __ldg(lr);
-  while (cur.x > stop) {
-    const int4 nxt = __ldg(reinterpret_cast<const int4*>(++prog));
-    const double nxt_lr = __ldg(++lr);
-    if (cur.w) {
-      unsigned a = col + cur.y, b = col + cur.z;
-      if (INS) {
-        for (int m = 0; m < units; m++, a -= stride, b -= stride) {
-          lp -= lds_f64(a);
-          lp += lds_f64(b);
-        }
-      } else {
-        lp -= lds_f64(a);
-        lp += lds_f64(b);
-      }
-    }
-    total += lse_term(lp + cur_lr, mx);
-    cur = nxt;
-    cur_lr = nxt_lr;
-  }
-  return lse_finish(mx, total);
-}
-
-// One column of the repeat block's last row: HapAligner.cpp:76-100.  The 13 artifact sizes are
-// evaluated by two rolled loops (deletions, insertions) so the evaluator code exists once; their
-// results wait in a small per-thread array for the final log-sum-exp.
-__device__ __forceinline__ double rep_column(const RepCtx& c, const double* prev_row, int j) {
-  const int B = c.B, p = c.p;
-  const DevRep* rep = c.rep;
-  const unsigned colj = c.val + j * HIPSTR_COL_BYTES;
-  double probs[HIPSTR_NUM_ARTIFACTS];
-#pragma unroll 1
-  for (int k = HIPSTR_MAX_ARTIFACT_UNITS; k >= 1; k--) {   // deletions of k units
-    const int D = -k * p;
-    const int base_len = min(B + D, j + 1);
-    double v = IMPOSSIBLE;
-    if (base_len >= 0) {
-      double lp0 = -__ldg(c.int_logs + (B + D + 1));
-      const int q = j - D;   // read column |D| bases to the right of j
-      if (q <= c.n_side - 1) {
-        // match_probs_[q] - del_probs_[q][k-1]; the deletion prefix table entry is the first
-        // k*period terms of the same right-anchored sum, recomputed here instead of stored
-        double pre = 0.0;
-        const unsigned colq = c.val + q * HIPSTR_COL_BYTES;
-#pragma unroll 4
-        for (int t = 0; t < -D; t++) pre += lds_f64(colq + __ldg(c.diag + t));
-        lp0 += c.match[q] - pre;
-      } else {
-        // read base j-t against allele base B-1-(t-D): entry t-D of the same diagonal, seen from column j
-        const unsigned cold = colj - D * HIPSTR_COL_BYTES;
-#pragma unroll 4
-        for (int t = 0; t < base_len; t++) lp0 += lds_f64(cold + __ldg(c.diag + (t - D)));
-      }
-      const double pr = rep_walk<false>(c, __ldg(rep->prog_off + k), -base_len, j, k, lp0, B + D);
-      const double pre_row = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
-      v = __ldg(rep->art + (HIPSTR_MAX_ARTIFACT_UNITS - k)) + pr + pre_row;
-    }
-    probs[HIPSTR_MAX_ARTIFACT_UNITS - k] = v;
-  }
-  {
-    const int base_len = min(B, j + 1);
-    const double pre_row = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
-    probs[HIPSTR_MAX_ARTIFACT_UNITS] = __ldg(rep->art + HIPSTR_MAX_ARTIFACT_UNITS) + c.match[j] + pre_row;
-  }
-  double ins_acc = 0.0;    // ins_probs_ running sum (StutterAlignerClass.cpp:38-51)
-  int ins_t = 0;
-  const double ins_prior = -__ldg(c.int_logs + (B + 1));
-  const int ins_prog = __ldg(rep->prog_off);
-#pragma unroll 1
-  for (int k = 1; k <= HIPSTR_MAX_ARTIFACT_UNITS; k++) {    // insertions of k units
-    const int D = k * p;
-    const int base_len = min(B + D, j + 1);
-    // extend the periodic-copy sum to k copies (at most j+1 read bases exist)
-    const int upto = min(D, j + 1);
-    for (; ins_t < upto; ins_t++) {
-      const int off = __ldg(c.ins_tab + ins_t);
-      ins_acc += lds_f64(off != -1 ? colj + off : colj - ins_t * HIPSTR_COL_BYTES + 8 * c.code[j - ins_t]);
-    }
-    double lp0 = ins_prior + ins_acc;
-    lp0 += (base_len > D) ? c.match[j - D] : 0.0;
-    const int stop = -min(max(0, base_len - D), B);
-    const double pr = rep_walk<true>(c, ins_prog, stop, j, k, lp0, B);
-    const double pre_row = (j - base_len < 0) ? 0.0 : prev_row[j - base_len];
-    probs[HIPSTR_MAX_ARTIFACT_UNITS + k] = __ldg(rep->art + HIPSTR_MAX_ARTIFACT_UNITS + k) + pr + pre_row;
-  }
-  double mx = probs[0];
-#pragma unroll 1
-  for (int a = 1; a < HIPSTR_NUM_ARTIFACTS; a++) mx = dmax(mx, probs[a]);
-  double total = 0.0;
-#pragma unroll 1
-  for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) total += lse_term(probs[a], mx);
-  return lse_finish(mx, total);
-}
 
 // ------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t align_smem_doubles(int n_max, int l_max) {
-  // val[5N] run/rowout[N] rowbuf[N] match[N] terms[32*SLOTS] raw bases/quals, mbarrier, code[N bytes]
+  // run[N] rowout[N] rowbuf[N] + 2 x raw[2][round16(N)] bytes (double-buffered bulk-copy landing zones) + two mbarriers
   (void)l_max;
-  // + 2 x raw[2][round16(N)] bytes (double-buffered bulk-copy landing zones) + two mbarriers
   const size_t n16 = ((size_t)n_max + 15) / 16 * 16;
-  const size_t d = (size_t)(HIPSTR_VAL_STRIDE + 3) * n_max + 32 * HIPSTR_TERM_SLOTS + 4 * n16 / 8 + 2 + (n_max + 7) / 8;
+  const size_t d = 3 * (size_t)n16 + 4 * n16 / 8 + 2;
   return (d + 1) / 2 * 2;   // keep every warp's slab 16-byte aligned
 }
 size_t align_smem_bytes(int n_max, int l_max) { return align_smem_doubles(n_max, l_max) * 8 * HIPSTR_WARPS_PER_CTA; }
 
-template <int C>
-__global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <= 8 ? 12 : 8)) / HIPSTR_WARPS_PER_CTA) k_align(const AlignParams P) {
+template <int C, int MINB>
+__global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const AlignParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -316,7 +68,7 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
   // Persistent warps: every warp pulls (pooled read, haplotype range) jobs from a global counter.
   const int N16 = (N + 15) / 16 * 16;
   double* wbase0 = reinterpret_cast<double*>(smem_raw) + (size_t)wib * align_smem_doubles(N, L);
-  uint8_t* s_raw0 = reinterpret_cast<uint8_t*>(wbase0 + (HIPSTR_VAL_STRIDE + 3) * (size_t)N + 32 * HIPSTR_TERM_SLOTS);
+  uint8_t* s_raw0 = reinterpret_cast<uint8_t*>(wbase0 + 3 * (size_t)N16);
   const unsigned raw_addr = (unsigned)__cvta_generic_to_shared(s_raw0);
   const unsigned bar_addr = raw_addr + 4 * N16;   // two 8-byte mbarriers after the two zones
   if (lane == 0) { mbar_init(bar_addr, 1); mbar_init(bar_addr + 8, 1); }
@@ -375,35 +127,19 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
   }
 
   double* wbase = reinterpret_cast<double*>(smem_raw) + (size_t)wib * align_smem_doubles(N, L);
-  double* s_val = wbase;               // [column g][5]: emission of column g against base code x
-  double* s_run = s_val + HIPSTR_VAL_STRIDE * N;
-  double* s_rowbuf = s_run + N;
-  double* s_rowout = s_run;            // aliases s_run (dead once the running sums are in registers)
-  double* s_match = s_rowbuf + N;
-  double* s_terms = s_match + N;
-  uint8_t* s_code = s_raw0 + 4 * N16 + 16;   // after the landing zones and the mbarriers
+  double* s_run = wbase;               // running sums of log_correct (row 0 of every haplotype starts from them)
+  double* s_rowbuf = s_run + N16;      // the row above a repeat block
+  double* s_rowout = s_rowbuf + N16;   // the repeat block's output row / the parked deletion row
 
   const int n = pool.len, seed = pool.seed;
   const int nL = seed, nR = n - seed - 1;
-  // Stage the read in SIDE order: columns 0..nL-1 are read bases 0..seed-1 (left of the seed, aligned
-  // to the forward haplotype), columns nL..n-2 are read bases n-1..seed+1 (right of the seed,
-  // reversed, aligned to the reversed haplotype), HapAligner.cpp:579-585,606-609.
-  // The packed bases and qualities arrived by TMA bulk copy in the landing zone (waited for above);
-  // every lane expands its read positions into the emission table.
-  for (int i = lane; i < n; i += 32) {
-    if (i == seed) continue;
-    const int g = i < seed ? i : nL + (n - 1 - i);
-    const uint8_t q = s_rawq[i];
-    const uint8_t x = s_rawb[i];
-    const double ok = __ldg(P.qual_lut + 2 * q), bad = __ldg(P.qual_lut + 2 * q + 1);
-    s_code[g] = x;
-#pragma unroll
-    for (int y = 0; y < 5; y++) s_val[g * HIPSTR_VAL_STRIDE + y] = (y == x) ? ok : bad;
-  }
+  // Columns are in SIDE order: columns 0..nL-1 of the left side are read bases 0..seed-1 (aligned to the forward
+  // haplotype), columns 0..nR-1 of the right side are read bases n-1..seed+1 (reversed, aligned to the reversed
+  // haplotype), HapAligner.cpp:579-585,606-609.  The packed bases and qualities arrived by TMA bulk copy in the
+  // landing zone (waited for above).
   const uint8_t seed_code = s_rawb[seed];
   const uint8_t seed_q = s_rawq[seed];
   const double seed_ok = __ldg(P.qual_lut + 2 * seed_q), seed_bad = __ldg(P.qual_lut + 2 * seed_q + 1);
-  __syncwarp();
   // running sums of log_correct from each read end towards the seed (row 0 of either matrix,
   // HapAligner.cpp:33-42); strictly sequential adds, one lane per side
   double edge = 0.0;
@@ -414,7 +150,7 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
 #pragma unroll 4
     for (int j = 0; j < cnt; j++) {
       s_run[g0 + j] = acc;
-      acc += s_val[(g0 + j) * HIPSTR_VAL_STRIDE + s_code[g0 + j]];
+      acc += __ldg(P.qual_lut + 2 * s_rawq[lane ? n - 1 - j : j]);
     }
     edge = acc;
   }
@@ -430,27 +166,23 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
   const int gbase = side ? nL : 0;
   const int j0 = k * C;
 
+  // per-column constants stay in registers for the whole job: base code, log P(correct), log P(error)
   double lc[C], lw[C], Mp[C], Dp[C];
   uint8_t bs[C];
 #pragma unroll
   for (int cc = 0; cc < C; cc++) {
     const int j = j0 + cc;
     const bool ok = lane_on && j < ncol;
-    const int g = ok ? gbase + j : 0;
-    const uint8_t x = s_code[g];
-    bs[cc] = x;
-    lc[cc] = s_val[g * HIPSTR_VAL_STRIDE + x];
-    lw[cc] = s_val[g * HIPSTR_VAL_STRIDE + (x == 0 ? 1 : 0)];
+    const int i = ok ? (side ? n - 1 - j : j) : 0;
+    const uint8_t q = s_rawq[i];
+    bs[cc] = s_rawb[i];
+    lc[cc] = __ldg(P.qual_lut + 2 * q);
+    lw[cc] = __ldg(P.qual_lut + 2 * q + 1);
   }
   const int last_cc = (lane_on && ncol - 1 >= j0 && ncol - 1 < j0 + C) ? ncol - 1 - j0 : -1;
-  // the running sums of this lane's columns stay in registers for the whole job; their shared-memory
-  // staging area is reused as the repeat block's output row
-  double runv[C];
-#pragma unroll
-  for (int cc = 0; cc < C; cc++) runv[cc] = (lane_on && j0 + cc < ncol) ? s_run[gbase + j0 + cc] : 0.0;
   __syncwarp();
-  const unsigned val_addr = (unsigned)__cvta_generic_to_shared(s_val);
-  const unsigned terms_addr = (unsigned)__cvta_generic_to_shared(s_terms + lane);
+  const int t_pitch = hipstr_t_pitch(n);
+  const double* t_pool = P.stut + P.pool_t_off[job.pool];
 
   int cached_class = -1;   // seg1_class of the rows before the first repeat block that this lane's
                            // side currently holds in s_rowbuf / s_last (from an earlier haplotype)
@@ -478,7 +210,7 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
 #pragma unroll
       for (int cc = 0; cc < C; cc++) {
         const int j = j0 + cc;
-        Mp[cc] = (bs[cc] == fc ? lc[cc] : lw[cc]) + runv[cc];
+        Mp[cc] = (bs[cc] == fc ? lc[cc] : lw[cc]) + ((lane_on && j < ncol) ? s_run[gbase + j] : 0.0);
         Dp[cc] = IMPOSSIBLE;
         if (cc == last_cc) s_last[side * L] = Mp[cc];
       }
@@ -546,47 +278,44 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
             }
         }
         __syncwarp();
-        // pass 1: match_probs_ of every column of the sides that are in a repeat block
+        // every column of a side that is in a repeat block: fold the stutter tables of K1a with the row above
+        // (HapAligner.cpp:84-100): probs[D] = T[D][column] + M[row above][j - base_len], then the 13-term log-sum-exp
         for (int g = lane; g < n - 1; g += 32) {
           const int gs = g >= nL;
           const DevBlock& gb = gs ? blkR : blkF;
           if (gb.rep < 0) continue;
           const DevRep* rep = P.reps + gb.rep;
-          RepCtx c;
-          c.s = P.hapbytes + rep->seq_off; c.progs = P.progs; c.prog_logrun = P.prog_logrun; c.rep = rep;
-          c.diag = P.rep_tabs + rep->diag_off; c.ins_tab = P.rep_tabs + rep->ins_off; c.int_logs = P.int_logs;
-          c.val = val_addr + (gs ? nL : 0) * HIPSTR_COL_BYTES; c.code = s_code + (gs ? nL : 0); c.match = s_match + (gs ? nL : 0);
-          c.terms = terms_addr;
-          c.B = rep->len; c.p = rep->period; c.n_side = gs ? nR : nL;
-          s_match[g] = rep_match_prob(c, g - (gs ? nL : 0));
+          const int B = __ldg(&rep->len), p = __ldg(&rep->period);
+          const int j = g - (gs ? nL : 0);
+          const double* tcol = t_pool + (size_t)gb.tslot * HIPSTR_NUM_ARTIFACTS * t_pitch + g;
+          const double* prev = s_rowbuf + (gs ? nL : 0);
+          double probs[HIPSTR_NUM_ARTIFACTS];
+#pragma unroll
+          for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) {
+            const int BD = B + (a - HIPSTR_MAX_ARTIFACT_UNITS) * p;
+            const int base_len = min(BD, j + 1);
+            double v = IMPOSSIBLE;
+            if (BD >= 0) {
+              const double pre_row = (j - base_len < 0) ? 0.0 : prev[j - base_len];
+              v = __ldg(tcol + a * t_pitch) + pre_row;
+            }
+            probs[a] = v;
+          }
+          double mx = probs[0];
+#pragma unroll
+          for (int a = 1; a < HIPSTR_NUM_ARTIFACTS; a++) mx = dmax(mx, probs[a]);
+          double total = 0.0;
+#pragma unroll
+          for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) total += lse_term(probs[a], mx);
+          s_rowout[g] = lse_finish(mx, total);
         }
         __syncwarp();
-        // pass 2: the 13 artifact sizes of every column
-        for (int g = lane; g < n - 1; g += 32) {
-          const int gs = g >= nL;
-          const DevBlock& gb = gs ? blkR : blkF;
-          if (gb.rep < 0) continue;
-          const DevRep* rep = P.reps + gb.rep;
-          RepCtx c;
-          c.s = P.hapbytes + rep->seq_off; c.progs = P.progs; c.prog_logrun = P.prog_logrun; c.rep = rep;
-          c.diag = P.rep_tabs + rep->diag_off; c.ins_tab = P.rep_tabs + rep->ins_off; c.int_logs = P.int_logs;
-          c.val = val_addr + (gs ? nL : 0) * HIPSTR_COL_BYTES; c.code = s_code + (gs ? nL : 0); c.match = s_match + (gs ? nL : 0);
-          c.terms = terms_addr;
-          c.B = rep->len; c.p = rep->period; c.n_side = gs ? nR : nL;
-          s_rowout[g] = rep_column(c, s_rowbuf + (gs ? nL : 0), g - (gs ? nL : 0));
-        }
-        __syncwarp();
-        // every lane re-reads its column constants: nothing of the flank state has to stay in
-        // registers across the evaluator above
+        // back to registers
 #pragma unroll
         for (int cc = 0; cc < C; cc++) {
           const int j = j0 + cc;
           const bool ok = lane_on && j < ncol;
           const int g = ok ? gbase + j : 0;
-          const uint8_t x = s_code[g];
-          bs[cc] = x;
-          lc[cc] = s_val[g * HIPSTR_VAL_STRIDE + x];
-          lw[cc] = s_val[g * HIPSTR_VAL_STRIDE + (x == 0 ? 1 : 0)];
           if (blk.rep >= 0) {
             Mp[cc] = ok ? s_rowout[g] : 0.0;
             Dp[cc] = IMPOSSIBLE;
@@ -661,10 +390,10 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, (C <= 5 ? 16 : (C <
   }   // next job
 }
 
-template <int C>
+template <int C, int MINB>
 static cudaError_t launch_align_c(const AlignParams& p, int max_ctas, cudaStream_t stream, int* grid_out) {
   const size_t smem = align_smem_bytes(p.n_max, p.l_max);
-  cudaError_t e = cudaFuncSetAttribute(k_align<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_align<C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   static int sms = 0;
   if (!sms) {
@@ -673,7 +402,7 @@ static cudaError_t launch_align_c(const AlignParams& p, int max_ctas, cudaStream
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align<C>, 32 * HIPSTR_WARPS_PER_CTA, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align<C, MINB>, 32 * HIPSTR_WARPS_PER_CTA, smem);
   if (e != cudaSuccess) return e;
   // persistent grid: exactly as many CTAs as can be resident (a multiple of the SM count)
   const int jobs_ctas = (p.n_jobs + HIPSTR_WARPS_PER_CTA - 1) / HIPSTR_WARPS_PER_CTA;
@@ -681,21 +410,23 @@ static cudaError_t launch_align_c(const AlignParams& p, int max_ctas, cudaStream
   if (grid > jobs_ctas) grid = jobs_ctas;
   if (grid > max_ctas) grid = max_ctas;
   if (grid_out) *grid_out = grid;
-  k_align<C><<<grid, 32 * HIPSTR_WARPS_PER_CTA, smem, stream>>>(p);
+  k_align<C, MINB><<<grid, 32 * HIPSTR_WARPS_PER_CTA, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_align(int variant, const AlignParams& p, int max_ctas, cudaStream_t stream, int* grid_out) {
   if (p.n_jobs <= 0) return cudaSuccess;
+  // tuning switch: HIPSTR_ALIGN_WARPS=20 caps the short-read variants at 96 registers (20 one-warp CTAs per SM)
+  static const int dense = [] { const char* e = getenv("HIPSTR_ALIGN_WARPS"); return e && atoi(e) >= 20; }();
   switch (variant) {
-    case 0: return launch_align_c<2>(p, max_ctas, stream, grid_out);
-    case 1: return launch_align_c<3>(p, max_ctas, stream, grid_out);
-    case 2: return launch_align_c<4>(p, max_ctas, stream, grid_out);
-    case 3: return launch_align_c<5>(p, max_ctas, stream, grid_out);
-    case 4: return launch_align_c<6>(p, max_ctas, stream, grid_out);
-    case 5: return launch_align_c<8>(p, max_ctas, stream, grid_out);
-    case 6: return launch_align_c<12>(p, max_ctas, stream, grid_out);
-    case 7: return launch_align_c<16>(p, max_ctas, stream, grid_out);
+    case 0: return dense ? launch_align_c<2, 20>(p, max_ctas, stream, grid_out) : launch_align_c<2, 16>(p, max_ctas, stream, grid_out);
+    case 1: return dense ? launch_align_c<3, 20>(p, max_ctas, stream, grid_out) : launch_align_c<3, 16>(p, max_ctas, stream, grid_out);
+    case 2: return dense ? launch_align_c<4, 20>(p, max_ctas, stream, grid_out) : launch_align_c<4, 16>(p, max_ctas, stream, grid_out);
+    case 3: return dense ? launch_align_c<5, 20>(p, max_ctas, stream, grid_out) : launch_align_c<5, 16>(p, max_ctas, stream, grid_out);
+    case 4: return launch_align_c<6, 12>(p, max_ctas, stream, grid_out);
+    case 5: return launch_align_c<8, 12>(p, max_ctas, stream, grid_out);
+    case 6: return launch_align_c<12, 8>(p, max_ctas, stream, grid_out);
+    case 7: return launch_align_c<16, 8>(p, max_ctas, stream, grid_out);
   }
   return cudaErrorInvalidValue;
 }

@@ -12,6 +12,9 @@ namespace hipstr {
 #define HIPSTR_MAX_ALIGN_CTAS 8192
 cudaError_t launch_align(int variant, const AlignParams& p, int max_ctas, cudaStream_t stream, int* grid_out);
 size_t align_smem_bytes(int n_max, int l_max);
+/* K1a: stutter tables of (pooled read, repeat allele) pairs (stutter.cu); runs before launch_align on the same stream. */
+cudaError_t launch_stutter(const StutParams& p, cudaStream_t stream);
+size_t stutter_smem_bytes(int n_max);
 
 /* K2: pool -> read scatter + mate merge (seq_stutter_genotyper.cpp:530-564). */
 struct ScatterParams {

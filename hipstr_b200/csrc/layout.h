@@ -23,6 +23,11 @@
 #define HIPSTR_B200_LAYOUT_H_
 
 #include <stdint.h>
+#ifdef __CUDACC__
+#define HIPSTR_HD __host__ __device__
+#else
+#define HIPSTR_HD
+#endif
 
 #define HIPSTR_WARPS_PER_CTA 1
 #define HIPSTR_MAX_BLOCKS 8          /* haplotype blocks per locus handled by the kernel */
@@ -58,7 +63,7 @@ struct DevBlock {         /* 16 B */
   int32_t row_start;      /* first haplotype row of the block in this orientation */
   int32_t len;
   int32_t rep;            /* index into reps, or -1 for a flank block */
-  int32_t pad;
+  int32_t tslot;          /* repeat block: slot of this (block, allele) in the stutter tables of its locus (K1a) */
 };
 
 /* One step of a repeat-block "program": the position walk of align_pcr_insertion_reverse /
@@ -95,6 +100,23 @@ struct DevRep {           /* 168 B */
   double  art[13];        /* log_prob_pcr_artifact for D = -6p .. +6p */
 };
 
+/* K1a work item: the stutter tables of one pooled read against a range of (repeat block, allele) slots of its locus.
+ * A slot pairs the forward-oriented DevRep (read bases left of the seed) with the reversed one (right of the seed). */
+struct DevStutJob {       /* 16 B */
+  int32_t pool;
+  int32_t slot0;          /* first entry of slot_reps */
+  int32_t n_slots;
+  int32_t tslot0;         /* table slot of slot0 within the pool's slab of the stutter tables */
+};
+struct DevSlotReps { int32_t rep_fwd, rep_rev; };
+
+/* Stutter tables T (K1a -> K1b), per pooled read a slab at pool_t_off[pool] (in doubles):
+ *     T[tslot][artifact 0..12][column g],  g = side-order column (left of the seed 0..nL-1, then right nL..n-2),
+ * row pitch = hipstr_t_pitch(len).  T = log_prob_pcr_artifact + align_stutter_region_reverse for the read prefix
+ * ending at column g (HapAligner.cpp:84-87 without pre_prob); it depends only on (read, allele), not on the flanks. */
+#define HIPSTR_STUT_SLOTS_PER_JOB 8
+static inline HIPSTR_HD int32_t hipstr_t_pitch(int32_t read_len) { return (read_len + 1) & ~1; }
+
 struct DevJob {           /* 16 B */
   int32_t pool;
   int32_t h0, h1;         /* haplotype range [h0, h1) of the pool's locus */
@@ -125,6 +147,27 @@ struct AlignParams {
   double* debug_out;         /* may be NULL: [2][l_max] last-column M values of job 0's last haplotype */
   int32_t* job_counter;      /* zeroed before the launch: persistent warps pull jobs from it */
   double* last_scratch;      /* [resident warps][2][l_max] last-column slabs */
+  const double* stut;        /* stutter tables of this launch's pools (K1a output) */
+  const int64_t* pool_t_off; /* [n_pools] offset of the pool's slab in stut, in doubles */
+};
+
+struct StutParams {          /* K1a */
+  const DevStutJob* jobs;
+  int32_t n_jobs;
+  int32_t n_max;             /* longest read of the launch, multiple of 16 */
+  const DevPool* pools;
+  const char* bases;
+  const char* quals;
+  const DevSlotReps* slot_reps;
+  const DevRep* reps;
+  const DevProgEntry* progs;
+  const double* prog_logrun;
+  const int32_t* rep_tabs;
+  const double* qual_lut;
+  const double* int_logs;
+  const int64_t* pool_t_off;
+  double* stut;
+  int32_t* job_counter;
 };
 
 #endif

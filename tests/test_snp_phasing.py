@@ -103,6 +103,25 @@ def test_reference_tree_with_many_snps_is_a_range_query():
     assert np.array_equal(counts[:, 0] + counts[:, 1], rc[:, 0]) and np.array_equal(counts[:, 2], rc[:, 1])
 
 
+def duplicate_pos_batch():
+    """Two VCF rows at one POS (a multi-allelic site split by `bcftools norm -m-`): 1|0 on one row, 0|1 on the other.
+    create_snp_trees emits both SNPs; the set stays small so that the reference's std::sort keeps their order."""
+    read = (100, 120, "ACGTACGTACGTACGTACGT", b"5" * 20, [("M", 20)])
+    mate = (300, 310, "TTTTTTTTTT", b"I" * 10, [("M", 10)])
+    sets = [[(103, "T", "G"), (108, "A", "C"), (108, "C", "A"), (108, "G", "T"), (115, "T", "A"), (304, "T", "A"), (304, "A", "T")]]
+    return SnpPhasing([(0, [read, mate]), (0, [read])], sets)
+
+
+@needs_ref
+def test_duplicate_snp_positions_match_reference():
+    batch = duplicate_pos_batch()
+    p1, p2, counts = run_oracle(batch)
+    r1, r2, rc = run_ref(batch)
+    assert same_bits(p1, r1) and same_bits(p2, r2)
+    assert np.array_equal(counts[:, 0] + counts[:, 1], rc[:, 0]) and np.array_equal(counts[:, 2], rc[:, 1])
+    assert counts[0].tolist()[:3] == [4, 2, 1]
+
+
 def test_oracle_hand_case():
     """One read 10M2D5M1I4M at 100 with SNPs under a match, inside the deletion, after the insertion and in the mate."""
     read = (100, 121, "ACGTACGTACGTACGTACGT", b"5" * 20, [("M", 10), ("D", 2), ("M", 5), ("I", 1), ("M", 4)])
@@ -126,6 +145,15 @@ def test_kernel_matches_oracle(seed, n):
     with capi.Context() as ctx:
         p1, p2, counts = ctx.snp_phasing(batch)
         assert ctx.traffic()[2] == 1
+    o1, o2, oc = run_oracle(batch)
+    assert same_bits(p1, o1) and same_bits(p2, o2) and np.array_equal(counts, oc)
+
+
+@pytest.mark.gpu
+def test_kernel_duplicate_snp_positions():
+    batch = duplicate_pos_batch()
+    with capi.Context() as ctx:
+        p1, p2, counts = ctx.snp_phasing(batch)
     o1, o2, oc = run_oracle(batch)
     assert same_bits(p1, o1) and same_bits(p2, o2) and np.array_equal(counts, oc)
 
