@@ -85,6 +85,7 @@ struct hipstr_ctx {
   hipstr_dev_genotype gscratch;          // reused by hipstr_genotype_batch_host
   DevBuf d_ll, d_pos, d_misc[12], d_out[6], d_last, d_counters;
   DevBuf d_stut;                         // stutter tables of the chunk in flight (K1a -> K1b)
+  DevBuf d_stut_pos, d_dec, d_art, d_job_t_off[kNumColVariants];   // K5 forward pass -> walk back
   float last_stutter_ms = 0.f;           // of the timed align call: K1a's share
   double* d_debug = nullptr;             // test hook, see hipstr_debug_lastcols
   double trace_seconds[4] = {0, 0, 0, 0};   // accumulated over hipstr_trace_batch_host calls: lowering, ordering + uploads, kernel, downloads
@@ -402,7 +403,8 @@ void hipstr_destroy(hipstr_ctx_t* ctx) {
   ctx->d_pos.release();
   ctx->d_last.release();
   ctx->d_counters.release();
-  ctx->d_stut.release();
+  ctx->d_stut.release(); ctx->d_stut_pos.release(); ctx->d_dec.release(); ctx->d_art.release();
+  for (auto& b : ctx->d_job_t_off) b.release();
   for (auto& b : ctx->d_misc) b.release();
   for (auto& b : ctx->d_out) b.release();
   for (auto& ev : ctx->pending) for (auto& e : ev.e) cudaEventDestroy(e);
@@ -1092,6 +1094,8 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   CU(put(d.reps, f.reps, s));
   CU(put(d.progs, f.progs, s));
   CU(put(d.logrun, f.prog_logrun, s));
+  CU(put(d.tabs, f.rep_tabs, s));
+  CU(put(d.slot_reps, f.slot_reps, s));
   DevBuf* m = ctx->d_misc;
   DevBuf* o = ctx->d_out;
   CU(put(m[0], trace_pool, (size_t)n_traces, s));
@@ -1099,62 +1103,77 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   CU(put(m[2], block_start, (size_t)batch->n_blocks, s));
   CU(put(m[3], block_ref_end, s));
   CU(put(m[4], locus_block0, s));
-  // Lanes of a warp run in step when they trace against the same haplotype with the seed at a similar place (same
-  // blocks, same repeat programs, same column counts): process the traces sorted by (locus, seed in the left / right
-  // half of the read, haplotype, seed).  The half comes before the haplotype so that a warp that straddles two
-  // haplotypes still has all its seeds on one side -- its padded rows (longest left + longest right side) stay near
-  // one read length instead of two.
-  std::vector<int32_t> order(n_traces);
+  // The forward pass is the alignment kernel pair in TRACE mode: one K1b job per trace = (pool, ONE haplotype), bucketed
+  // by columns per lane like the alignment jobs, and one K1a job per (trace, repeat block of its haplotype).  Every
+  // trace owns a slab of stutter tables (one per repeat block), of predecessor bytes and of artifact tables.
+  std::vector<DevJob> jobs[kNumColVariants];
+  std::vector<int64_t> job_t_off[kNumColVariants], stut_t_off, dec_off((size_t)n_traces), art_off((size_t)n_traces);
+  std::vector<DevStutJob> stut_jobs;
+  int64_t t_doubles = 0, dec_bytes = 0, art_ints = 0;
+  int stut_n_max = 16, n_max_v[kNumColVariants], l_all = 2;
+  for (int v = 0; v < kNumColVariants; v++) n_max_v[v] = 16;
   {
-    // one 64-bit key per trace (locus | side | haplotype | seed), ties by arrival: a plain sort of pairs, no indirection
-    std::vector<std::pair<uint64_t, int32_t> > keyed((size_t)n_traces);
+    const std::vector<int32_t>& locus_slot0 = f.locus_slot0;   // DevBlock::tslot is local to the locus
     for (int t = 0; t < n_traces; t++) {
       const DevPool& dp = f.pools[trace_pool[t]];
-      const uint64_t side = 2 * dp.seed >= dp.len ? 0 : 1;   // seeds in the right half first, like the comparator it replaces
-      keyed[t] = std::make_pair(((uint64_t)dp.locus << 42) | (side << 41) | ((uint64_t)(trace_hap[t] & 0xFFFFF) << 21) |
-                                    (uint64_t)(dp.seed & 0x1FFFFF), (int32_t)t);
+      const DevHapSide& hs = f.hapsides[dp.hap_rec0 + 2 * trace_hap[t]];
+      int v = -1;
+      for (int c = 0; c < kNumColVariants && v < 0; c++) {
+        const int C = kColVariants[c];
+        if ((dp.seed + C - 1) / C + (dp.len - dp.seed - 1 + C - 1) / C <= 32) v = c;
+      }
+      if (v < 0) return fail(ctx, HIPSTR_ERR_UNSUPPORTED, "read longer than the kernel's limit");
+      const int pitch = hipstr_t_pitch(dp.len);
+      int n_rep = 0;
+      for (int b = 0; b < hs.n_blocks; b++) {
+        const DevBlock& db = f.blocks[hs.blk_off + b];
+        if (db.rep < 0) continue;
+        DevStutJob sj = {trace_pool[t], locus_slot0[dp.locus] + db.tslot, 1, n_rep};
+        stut_jobs.push_back(sj);
+        stut_t_off.push_back(t_doubles);
+        n_rep++;
+      }
+      DevJob j = {trace_pool[t], trace_hap[t], trace_hap[t] + 1, t};
+      jobs[v].push_back(j);
+      job_t_off[v].push_back(t_doubles);
+      t_doubles += (int64_t)std::max(n_rep, 1) * HIPSTR_NUM_ARTIFACTS * pitch;
+      dec_off[t] = dec_bytes;
+      dec_bytes += (int64_t)hs.len * (dp.len - 1);
+      art_off[t] = art_ints;
+      art_ints += (int64_t)2 * hs.n_blocks * (dp.len - 1);
+      stut_n_max = std::max(stut_n_max, (dp.len + 15) / 16 * 16);
+      n_max_v[v] = std::max(n_max_v[v], (dp.len + 3) / 4 * 4);
+      l_all = std::max(l_all, (hs.len + 1) / 2 * 2);
     }
-    std::sort(keyed.begin(), keyed.end());
-    for (int t = 0; t < n_traces; t++) order[t] = keyed[t].second;
   }
-  // a warp pads every lane's rows to its longest left and its longest right side: the slab holds the widest warp
-  int slab_cols = 2;
-  for (int t0 = 0; t0 < n_traces; t0 += 32) {
-    int left = 0, right = 0;
-    for (int t = t0; t < std::min(n_traces, t0 + 32); t++) {
-      const DevPool& dp = f.pools[trace_pool[order[t]]];
-      left = std::max(left, dp.seed);
-      right = std::max(right, dp.len - dp.seed - 1);
-    }
-    slab_cols = std::max(slab_cols, left + right);
-  }
-  CU(put(m[6], order, s));
-  TraceParams p;
-  std::memset(&p, 0, sizeof(p));
-  // two rolling rows of M / I / D, last columns of both sides, the emission table of the read
-  p.slab_doubles = (int64_t)7 * slab_cols + 2 * l_max + 6 * (int64_t)n_max;   // (+ one row of match_probs_)
-  p.dec_bytes = (int64_t)slab_cols * l_max;                // one predecessor-choice byte per cell of both sides
-  p.art_ints = (int64_t)2 * slab_cols * HIPSTR_MAX_BLOCKS;
-  // threads in flight: each owns ~25 KB; at most 131072 of them and at most 8 GB per context
-  const int64_t per_thread = p.slab_doubles * (int64_t)sizeof(double) + p.dec_bytes + p.art_ints * (int64_t)sizeof(int32_t);
-  const int by_budget = (int)std::max<int64_t>(64, ((int64_t)8 << 30) / per_thread / 64 * 64);
-  const int n_slots = std::min((std::min(n_traces, 131072) + 63) / 64 * 64, by_budget);
-  CU(ctx->d_last.reserve((size_t)n_slots * p.slab_doubles * sizeof(double)));
-  CU(m[5].reserve((size_t)n_slots * p.art_ints * sizeof(int32_t)));
-  CU(m[7].reserve((size_t)n_slots * p.dec_bytes));
+  CU(put(m[5], stut_jobs, s));
+  CU(put(m[6], stut_t_off, s));
+  CU(put(m[7], dec_off, s));
+  CU(put(m[8], art_off, s));
+  CU(ctx->d_stut.reserve((size_t)std::max<int64_t>(t_doubles, 2) * sizeof(double)));
+  CU(ctx->d_stut_pos.reserve((size_t)std::max<int64_t>(t_doubles, 2) * sizeof(int32_t)));
+  CU(ctx->d_dec.reserve((size_t)std::max<int64_t>(dec_bytes, 16)));
+  CU(ctx->d_art.reserve((size_t)std::max<int64_t>(art_ints, 4) * sizeof(int32_t)));
+  CU(ctx->d_last.reserve((size_t)HIPSTR_MAX_ALIGN_CTAS * HIPSTR_WARPS_PER_CTA * 2 * l_all * sizeof(double)));
+  CU(ctx->d_counters.reserve((kNumColVariants + 1) * sizeof(int32_t)));
+  CU(cudaMemsetAsync(ctx->d_counters.p, 0, (kNumColVariants + 1) * sizeof(int32_t), s));
   const size_t T = (size_t)n_traces;
   CU(o[0].reserve(T * out->aln_stride));
   CU(o[1].reserve(T * (1 + 3 * HIPSTR_MAX_BLOCKS_PER_LOCUS + 4 + 2 * HIPSTR_MAX_TRACE_INDELS + 2 * HIPSTR_MAX_TRACE_SNPS) * sizeof(int32_t)));
+  CU(o[2].reserve(T * sizeof(int32_t)));
   int32_t* di = (int32_t*)o[1].p;
+  TraceWalkParams p;
+  std::memset(&p, 0, sizeof(p));
   p.n_traces = n_traces;
-  p.trace_pool = (const int32_t*)m[0].p; p.trace_hap = (const int32_t*)m[1].p; p.trace_order = (const int32_t*)m[6].p;
+  p.trace_pool = (const int32_t*)m[0].p; p.trace_hap = (const int32_t*)m[1].p;
   p.pools = (const DevPool*)d.pools.p; p.bases = (const char*)d.bases.p; p.quals = (const char*)d.quals.p;
   p.hapsides = (const DevHapSide*)d.hapsides.p; p.hapbytes = (const uint8_t*)d.hapbytes.p;
-  p.blocks = (const DevBlock*)d.blocks.p; p.reps = (const DevRep*)d.reps.p;
-  p.progs = (const DevProgEntry*)d.progs.p; p.prog_logrun = (const double*)d.logrun.p;
-  p.qual_lut = ctx->d_qual_lut; p.trans = ctx->d_trans; p.int_logs = ctx->d_int_logs;
+  p.blocks = (const DevBlock*)d.blocks.p;
+  p.qual_lut = ctx->d_qual_lut;
   p.block_start = (const int32_t*)m[2].p; p.block_ref_end = (const int32_t*)m[3].p; p.locus_block0 = (const int32_t*)m[4].p;
-  p.slab = (double*)ctx->d_last.p; p.art_slab = (int32_t*)m[5].p; p.dec_slab = (unsigned char*)m[7].p;
+  p.dec = (const unsigned char*)ctx->d_dec.p; p.dec_off = (const int64_t*)m[7].p;
+  p.art = (const int32_t*)ctx->d_art.p; p.art_off = (const int64_t*)m[8].p;
+  p.seed_pos = (const int32_t*)o[2].p;
   p.aln_stride = out->aln_stride;
   p.out_aln = (char*)o[0].p;
   p.out_seed_pos = di; di += T;
@@ -1168,12 +1187,45 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   p.out_indels = di; di += T * 2 * HIPSTR_MAX_TRACE_INDELS;
   p.out_snps = di;
   CU(cudaMemsetAsync(o[0].p, 0, T * out->aln_stride, s));
+  // K1a in TRACE mode: tables + best artifact positions
+  StutParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.jobs = (const DevStutJob*)m[5].p; sp.n_jobs = (int32_t)stut_jobs.size(); sp.n_max = stut_n_max;
+  sp.pools = p.pools; sp.bases = p.bases; sp.quals = p.quals;
+  sp.slot_reps = (const DevSlotReps*)d.slot_reps.p; sp.reps = (const DevRep*)d.reps.p;
+  sp.progs = (const DevProgEntry*)d.progs.p; sp.prog_logrun = (const double*)d.logrun.p; sp.rep_tabs = (const int32_t*)d.tabs.p;
+  sp.qual_lut = ctx->d_qual_lut; sp.int_logs = ctx->d_int_logs;
+  sp.stut = (double*)ctx->d_stut.p; sp.stut_pos = (int32_t*)ctx->d_stut_pos.p;
+  sp.job_t_off = (const int64_t*)m[6].p;
+  sp.job_counter = (int32_t*)ctx->d_counters.p + kNumColVariants;
+  // K1b in TRACE mode
+  AlignParams ap;
+  std::memset(&ap, 0, sizeof(ap));
+  ap.pools = p.pools; ap.bases = p.bases; ap.quals = p.quals; ap.hapsides = p.hapsides; ap.hapbytes = p.hapbytes;
+  ap.blocks = p.blocks; ap.reps = sp.reps; ap.progs = sp.progs; ap.prog_logrun = sp.prog_logrun; ap.rep_tabs = sp.rep_tabs;
+  ap.qual_lut = ctx->d_qual_lut; ap.trans = ctx->d_trans; ap.int_logs = ctx->d_int_logs;
+  ap.l_max = l_all; ap.last_scratch = (double*)ctx->d_last.p;
+  ap.stut = (const double*)ctx->d_stut.p; ap.stut_pos = (const int32_t*)ctx->d_stut_pos.p;
+  ap.dec = (unsigned char*)ctx->d_dec.p; ap.dec_off = p.dec_off; ap.art = (int32_t*)ctx->d_art.p; ap.art_off = p.art_off;
+  ap.trace_seed_pos = (int32_t*)o[2].p;
   CU(cudaStreamSynchronize(s));
   ctx->trace_seconds[1] += now() - t_mark; t_mark = now();
-  CU(launch_trace(p, n_slots, s));
+  ctx->last_launches = 0;
+  if (sp.n_jobs > 0) { CU(launch_stutter(sp, s)); ctx->last_launches++; }
+  for (int v = kNumColVariants - 1; v >= 0; v--) {
+    if (jobs[v].empty()) continue;
+    CU(put(d.jobs[v], jobs[v], s));
+    CU(put(ctx->d_job_t_off[v], job_t_off[v], s));
+    ap.jobs = (const DevJob*)d.jobs[v].p; ap.n_jobs = (int32_t)jobs[v].size(); ap.n_max = n_max_v[v];
+    ap.job_t_off = (const int64_t*)ctx->d_job_t_off[v].p;
+    ap.job_counter = (int32_t*)ctx->d_counters.p + v;
+    CU(launch_trace_forward(v, ap, HIPSTR_MAX_ALIGN_CTAS, s));
+    ctx->last_launches++;
+  }
+  CU(launch_trace_walk(p, s));
+  ctx->last_launches++;
   CU(cudaStreamSynchronize(s));
   ctx->trace_seconds[2] += now() - t_mark; t_mark = now();
-  ctx->last_launches = 1;
   CU(get(ctx, out->hap_aln, p.out_aln, T * out->aln_stride));
   CU(get(ctx, out->seed_hap_pos, p.out_seed_pos, T));
   CU(get(ctx, out->stutter_size, p.out_stutter, T * HIPSTR_MAX_BLOCKS_PER_LOCUS));

@@ -45,7 +45,7 @@ void FlatBatch::clear() {
   pools.clear(); bases.clear(); quals.clear();
   hapsides.clear(); hapbytes.clear(); blocks.clear(); reps.clear(); progs.clear(); prog_logrun.clear(); rep_tabs.clear(); hap_mask.clear();
   for (auto& j : jobs) j.clear();
-  slot_reps.clear(); stut_jobs.clear(); pool_t_off.clear(); chunks.clear();
+  slot_reps.clear(); locus_slot0.clear(); stut_jobs.clear(); pool_t_off.clear(); chunks.clear();
   stut_n_max = 16;
   n_out = n_alignments = 0;
 }
@@ -660,6 +660,9 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     case HIPSTR_ERR_INVALID_SEED: err = "invalid alignment seed"; return HIPSTR_ERR_INVALID_SEED;
     default: err = "read longer than the kernel's limit"; return HIPSTR_ERR_UNSUPPORTED;
   }
+
+  out.locus_slot0.resize((size_t)b->n_loci);
+  for (int l = 0; l < b->n_loci; l++) out.locus_slot0[l] = loci[l].slot0;
 
   // ---- jobs ----
   // Split a pool's haplotypes over several warps only when the batch is too small to fill the GPU.

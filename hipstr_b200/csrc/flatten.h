@@ -86,6 +86,7 @@ struct FlatBatch {
    * HIPSTR_STUT_SLOTS_PER_JOB slots), and the slab offset of every pool inside its chunk's table buffer.  A chunk is a
    * range of pools whose tables fit the budget: K1a then K1b run chunk by chunk over the same buffer. */
   std::vector<DevSlotReps> slot_reps;
+  std::vector<int32_t> locus_slot0;          /* [n_loci] first entry of slot_reps of the locus */
   HostBuf<DevStutJob> stut_jobs;
   HostBuf<int64_t> pool_t_off;
   struct Chunk {

@@ -52,6 +52,22 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "DONE_%=:\n"
       "}\n" :: "r"(bar), "r"(parity) : "memory");
 }
+// The predecessor choices of HapAligner::retrace (HapAligner.cpp:345-361): within TRACE_LL_TOL = 0.001 the left side of
+// the seed prefers the later candidate, the right side (aligned reversed) the earlier one.
+#define HIPSTR_TRACE_TOL 0.001
+__device__ __forceinline__ int pick3(bool rev, double v1, double v2, double v3) {
+  if (!rev) {
+    if (v1 > v2 + HIPSTR_TRACE_TOL) return v1 > v3 + HIPSTR_TRACE_TOL ? 0 : 2;
+    return v2 > v3 + HIPSTR_TRACE_TOL ? 1 : 2;
+  }
+  if (v3 > v2 + HIPSTR_TRACE_TOL) return v3 > v1 + HIPSTR_TRACE_TOL ? 2 : 0;
+  return v2 > v1 + HIPSTR_TRACE_TOL ? 1 : 0;
+}
+__device__ __forceinline__ int pick2(bool rev, double v1, double v2) {
+  if (!rev) return v1 > v2 + HIPSTR_TRACE_TOL ? 0 : 1;
+  return v2 > v1 + HIPSTR_TRACE_TOL ? 1 : 0;
+}
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace hipstr

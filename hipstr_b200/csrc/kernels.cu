@@ -56,7 +56,13 @@ __host__ __device__ inline size_t align_smem_doubles(int n_max, int l_max) {
 }
 size_t align_smem_bytes(int n_max, int l_max) { return align_smem_doubles(n_max, l_max) * 8 * HIPSTR_WARPS_PER_CTA; }
 
-template <int C, int MINB>
+// TRACE = the forward pass of K5 (HapAligner::trace_optimal_aln, HapAligner.cpp:711-722 -> process_read(retrace_aln)):
+// one job per trace = (pooled read, ONE haplotype).  The reference keeps the three full matrices and re-derives the best
+// predecessor of every cell it visits walking back; those choices only depend on values at hand when the cell is
+// computed, so they are taken HERE (same tolerance and side-dependent preferences, kcommon.cuh pick2 / pick3) and stored
+// as one byte per flank cell, plus the best artifact size / position of every repeat-block column; k_trace_walk
+// (trace.cu) then follows the bytes.
+template <int C, int MINB, bool TRACE>
 __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const AlignParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -182,12 +188,14 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const
   const int last_cc = (lane_on && ncol - 1 >= j0 && ncol - 1 < j0 + C) ? ncol - 1 - j0 : -1;
   __syncwarp();
   const int t_pitch = hipstr_t_pitch(n);
-  const double* t_pool = P.stut + P.pool_t_off[job.pool];
+  const int64_t t_off = TRACE ? P.job_t_off[my_job] : P.pool_t_off[job.pool];
+  const double* t_pool = P.stut + t_off;
+  const int tr = job.pad;   // TRACE: the trace this job computes
 
   // The stutter tables come from HBM (K1a wrote them a moment ago): ask L2 for the tables of a haplotype one
   // haplotype ahead of their use, 128 bytes per lane and request, so that the 13 loads per column find them on chip.
   auto prefetch_tables = [&](int h) {
-    if (h >= job.h1 || (P.hap_mask && !P.hap_mask[(pool.hap_rec0 >> 1) + h])) return;
+    if (TRACE || h >= job.h1 || (P.hap_mask && !P.hap_mask[(pool.hap_rec0 >> 1) + h])) return;
     const DevHapSide hp = P.hapsides[pool.hap_rec0 + 2 * h];
     for (int b = 0; b < hp.n_blocks; b++) {
       const DevBlock blk = P.blocks[hp.blk_off + b];
@@ -212,6 +220,8 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const
     const uint8_t* rows = P.hapbytes + hs.row_off;
     const int nb = hsF.n_blocks;
     const int hlen = hsF.len;
+    unsigned char* dec_side = TRACE ? P.dec + P.dec_off[tr] + (side ? (size_t)hlen * nL : 0) : nullptr;
+    int32_t* art_base = TRACE ? P.art + P.art_off[tr] : nullptr;   // sizes [2 sides][blocks][n_side], then positions
 
     // Rows before the first repeat block depend only on the read and on seg1_class: when the
     // previous haplotype of this job had the same class they are still in shared memory (the row
@@ -271,6 +281,14 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const
                   In = IMPOSSIBLE;
                   Dn = IMPOSSIBLE;
                 }
+                if (TRACE && j0 + cc < ncol) {   // what retrace would choose standing on this cell, from the very values it would read
+                  const bool rev = side != 0;
+                  const int choice = col0 ? (pick2(rev, Dup + LOG_DEL_TO_DEL, Mup + LOG_DEL_TO_MATCH) << 2)
+                                          : (pick3(rev, Ileft + m2i, Ddiag + m2d, Mdiag + m2m) |
+                                             (pick2(rev, Dup + LOG_DEL_TO_DEL, Mup + LOG_DEL_TO_MATCH) << 2) |
+                                             (pick2(rev, Ileft + LOG_INS_TO_INS, Mdiag + LOG_INS_TO_MATCH) << 3));
+                  dec_side[(size_t)row * ncol + j0 + cc] = (unsigned char)choice;
+                }
                 Mdiag = Mup; Ddiag = Dup; Ileft = In;
                 Mp[cc] = Mn; Dp[cc] = Dn;
                 if (cc == last_cc) s_last[side * L + row] = Mn;
@@ -303,7 +321,13 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const
           const DevRep* rep = P.reps + gb.rep;
           const int B = __ldg(&rep->len), p = __ldg(&rep->period);
           const int j = g - (gs ? nL : 0);
-          const double* tcol = t_pool + (size_t)gb.tslot * HIPSTR_NUM_ARTIFACTS * t_pitch + g;
+          int tslot = gb.tslot;
+          if (TRACE) {   // the trace's slab holds one table per repeat block of the haplotype, in forward block order
+            const int fb = gs ? nb - 1 - b : b;
+            tslot = 0;
+            for (int x = 0; x < fb; x++) tslot += P.blocks[hsF.blk_off + x].rep >= 0;
+          }
+          const double* tcol = t_pool + (size_t)tslot * HIPSTR_NUM_ARTIFACTS * t_pitch + g;
           const double* prev = s_rowbuf + (gs ? nL : 0);
           double probs[HIPSTR_NUM_ARTIFACTS];
 #pragma unroll
@@ -324,6 +348,18 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const
 #pragma unroll
           for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) total += lse_term(probs[a], mx);
           s_rowout[g] = lse_finish(mx, total);
+          if (TRACE) {   // HapAligner.cpp:79-97: the first strictly best artifact size and its position
+            double best = IMPOSSIBLE;
+            int best_a = -1;
+#pragma unroll
+            for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++)
+              if (probs[a] > best) { best = probs[a]; best_a = a; }
+            const int n_side_g = gs ? nR : nL;
+            int32_t* sizes = art_base + (gs ? nb * nL : 0) + b * n_side_g;
+            int32_t* poss = sizes + nb * (nL + nR);
+            sizes[j] = best_a < 0 ? -10000 : (best_a - HIPSTR_MAX_ARTIFACT_UNITS) * p;
+            poss[j] = best_a < 0 ? 0 : __ldg(P.stut_pos + t_off + (size_t)tslot * HIPSTR_NUM_ARTIFACTS * t_pitch + g + (size_t)best_a * t_pitch);
+          }
         }
         __syncwarp();
         // back to registers
@@ -394,8 +430,12 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
       if (lane == 0) {
-        out[h] = lse_finish(vmax, total);
-        if (P.pos_out) P.pos_out[pool.out_off + h] = vrank == 0 ? 0 : (vrank == 1 ? hlen - 1 : vrank - 1);
+        const int seed_pos = vrank == 0 ? 0 : (vrank == 1 ? hlen - 1 : vrank - 1);
+        if (TRACE) P.trace_seed_pos[tr] = seed_pos;
+        else {
+          out[h] = lse_finish(vmax, total);
+          if (P.pos_out) P.pos_out[pool.out_off + h] = seed_pos;
+        }
       }
       if (P.debug_out && my_job == 0 && h == job.h1 - 1)
         for (int i = lane; i < 2 * L; i += 32) P.debug_out[i] = (i % L) < hlen ? s_last[i] : 0.0;
@@ -406,10 +446,10 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const
   }   // next job
 }
 
-template <int C, int MINB>
+template <int C, int MINB, bool TRACE = false>
 static cudaError_t launch_align_c(const AlignParams& p, int max_ctas, cudaStream_t stream, int* grid_out) {
   const size_t smem = align_smem_bytes(p.n_max, p.l_max);
-  cudaError_t e = cudaFuncSetAttribute(k_align<C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_align<C, MINB, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   static int sms = 0;
   if (!sms) {
@@ -418,7 +458,7 @@ static cudaError_t launch_align_c(const AlignParams& p, int max_ctas, cudaStream
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align<C, MINB>, 32 * HIPSTR_WARPS_PER_CTA, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align<C, MINB, TRACE>, 32 * HIPSTR_WARPS_PER_CTA, smem);
   if (e != cudaSuccess) return e;
   // persistent grid: exactly as many CTAs as can be resident (a multiple of the SM count)
   const int jobs_ctas = (p.n_jobs + HIPSTR_WARPS_PER_CTA - 1) / HIPSTR_WARPS_PER_CTA;
@@ -426,7 +466,7 @@ static cudaError_t launch_align_c(const AlignParams& p, int max_ctas, cudaStream
   if (grid > jobs_ctas) grid = jobs_ctas;
   if (grid > max_ctas) grid = max_ctas;
   if (grid_out) *grid_out = grid;
-  k_align<C, MINB><<<grid, 32 * HIPSTR_WARPS_PER_CTA, smem, stream>>>(p);
+  k_align<C, MINB, TRACE><<<grid, 32 * HIPSTR_WARPS_PER_CTA, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -443,6 +483,21 @@ cudaError_t launch_align(int variant, const AlignParams& p, int max_ctas, cudaSt
     case 5: return launch_align_c<8, 12>(p, max_ctas, stream, grid_out);
     case 6: return launch_align_c<12, 8>(p, max_ctas, stream, grid_out);
     case 7: return launch_align_c<16, 8>(p, max_ctas, stream, grid_out);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_trace_forward(int variant, const AlignParams& p, int max_ctas, cudaStream_t stream) {
+  if (p.n_jobs <= 0) return cudaSuccess;
+  switch (variant) {
+    case 0: return launch_align_c<2, 16, true>(p, max_ctas, stream, nullptr);
+    case 1: return launch_align_c<3, 16, true>(p, max_ctas, stream, nullptr);
+    case 2: return launch_align_c<4, 16, true>(p, max_ctas, stream, nullptr);
+    case 3: return launch_align_c<5, 16, true>(p, max_ctas, stream, nullptr);
+    case 4: return launch_align_c<6, 12, true>(p, max_ctas, stream, nullptr);
+    case 5: return launch_align_c<8, 12, true>(p, max_ctas, stream, nullptr);
+    case 6: return launch_align_c<12, 8, true>(p, max_ctas, stream, nullptr);
+    case 7: return launch_align_c<16, 8, true>(p, max_ctas, stream, nullptr);
   }
   return cudaErrorInvalidValue;
 }

@@ -137,39 +137,33 @@ struct EmParams {
 cudaError_t launch_em(const EmParams& p, int max_alleles, cudaStream_t stream);
 
 /* K5: alignment traceback (trace.cu), one thread per (pooled read, haplotype) trace. */
-struct TraceParams {
+struct TraceWalkParams {
   int32_t n_traces;
   const int32_t* trace_pool;     /* global pool index */
   const int32_t* trace_hap;      /* haplotype index local to the pool's locus */
-  const int32_t* trace_order;    /* [n_traces] processing order: lane i of the k-th group of 32 handles trace_order[32 k + i] */
   const DevPool* pools;
   const char* bases;
   const char* quals;
   const DevHapSide* hapsides;
   const uint8_t* hapbytes;
   const DevBlock* blocks;
-  const DevRep* reps;
-  const DevProgEntry* progs;
-  const double* prog_logrun;
   const double* qual_lut;
-  const double* trans;
-  const double* int_logs;
   const int32_t* block_start;    /* [n_blocks] genomic start of every block */
   const int32_t* block_ref_end;  /* [n_blocks] start + length of the reference allele */
   const int32_t* locus_block0;   /* [n_loci] first block of the locus */
-  double* slab;                  /* [n_slots][slab_doubles] rolling rows + last columns */
-  int64_t slab_doubles;
-  unsigned char* dec_slab;       /* [n_slots][dec_bytes] predecessor choices, one byte per cell */
-  int64_t dec_bytes;
-  int32_t* art_slab;             /* [n_slots][art_ints] best artifact size / position tables */
-  int64_t art_ints;
+  /* what the forward pass (k_align<.., TRACE>) left, see AlignParams */
+  const unsigned char* dec; const int64_t* dec_off;
+  const int32_t* art; const int64_t* art_off;
+  const int32_t* seed_pos;
   int32_t aln_stride;
   char* out_aln;
   int32_t* out_seed_pos; int32_t* out_stutter; int32_t* out_span_start; int32_t* out_span_len;
   int32_t* out_flank_ins; int32_t* out_flank_del; int32_t* out_n_indels; int32_t* out_indels;
   int32_t* out_n_snps; int32_t* out_snps;
 };
-cudaError_t launch_trace(const TraceParams& p, int n_slots, cudaStream_t stream);
+/* K5: forward pass (one warp per trace, kernels.cu) and walk back (one thread per trace, trace.cu) */
+cudaError_t launch_trace_forward(int variant, const AlignParams& p, int max_ctas, cudaStream_t stream);
+cudaError_t launch_trace_walk(const TraceWalkParams& p, cudaStream_t stream);
 
 /* ---- K6: batched Needleman-Wunsch (nw.cu) -------------------------------------------------- */
 struct NwParams {

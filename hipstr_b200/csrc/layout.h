@@ -149,6 +149,14 @@ struct AlignParams {
   double* last_scratch;      /* [resident warps][2][l_max] last-column slabs */
   const double* stut;        /* stutter tables of this launch's pools (K1a output) */
   const int64_t* pool_t_off; /* [n_pools] offset of the pool's slab in stut, in doubles */
+  /* ---- traces (K5 forward pass, k_align<.., TRACE = true>): one job per trace = (pool, ONE haplotype), job.pad = trace ---- */
+  const int64_t* job_t_off;  /* [n_jobs of the launch] slab of the trace in stut / stut_pos (slot = ordinal of the repeat block) */
+  const int32_t* stut_pos;   /* best artifact position of every table entry (K1a, TRACE) */
+  unsigned char* dec;        /* predecessor choices, one byte per flank cell: left side [hap rows][nL] then right side [hap rows][nR] */
+  const int64_t* dec_off;    /* [n_traces] */
+  int32_t* art;              /* per trace: best artifact size [2 sides][blocks][n_side], then position, same shape */
+  const int64_t* art_off;    /* [n_traces] */
+  int32_t* trace_seed_pos;   /* [n_traces] haplotype position of the seed base */
 };
 
 struct StutParams {          /* K1a */
@@ -168,6 +176,9 @@ struct StutParams {          /* K1a */
   const int64_t* pool_t_off;
   double* stut;
   int32_t* job_counter;
+  /* traces (K5): one table slab per JOB instead of per pool, and the best artifact position of every walk */
+  const int64_t* job_t_off;  /* NULL for alignment */
+  int32_t* stut_pos;         /* NULL for alignment; parallel to stut */
 };
 
 #endif

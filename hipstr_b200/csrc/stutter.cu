@@ -73,15 +73,19 @@ __device__ __forceinline__ void stut_move(double& lp, unsigned col, const int4& 
 // The whole warp is on the same (side, allele, artifact size): program entries, the `moves` branch and the loop
 // bound are uniform; a lane only differs in where its read prefix ends (`stop`).  Terms wait in shared memory for the
 // maximum; a walk with more terms than slots is replayed for the ones that did not fit.
-template <bool INS>
+// TRACE also tracks the reference's best artifact position (StutterAlignerClass.cpp:92-95,137-140: the position counter
+// after a step is one above the next step's position, so best_pos = 1 - i == -next.pos).
+template <bool INS, bool TRACE>
 __device__ __forceinline__ double stut_walk(const StutCtx& c, int prog_index, int stop, int j, int units, double lp0,
-                                            int tail_base) {
+                                            int tail_base, int& best_pos) {
   const int4* prog = reinterpret_cast<const int4*>(c.progs + prog_index);
   const double* lr = c.logrun + prog_index;
   const unsigned col = c.val + (INS ? (j - c.p) : j) * HIPSTR_COL_BYTES;
   const int stride = c.p * HIPSTR_COL_BYTES;
   const int warp_stop = __reduce_min_sync(FULL, stop);
-  double lp = lp0, mx = lp0;
+  double lp = lp0, mx = lp0, best = lp0;
+  best_pos = 0;
+  const bool left_align = TRACE && __ldg(&c.rep->left_align) != 0;
   sts_f64(c.terms, lp0);
   int cnt = 0, s = 0;
   unsigned slot = c.terms;
@@ -96,6 +100,7 @@ __device__ __forceinline__ double stut_walk(const StutCtx& c, int prog_index, in
       if (s + 1 < STUT_TERM_SLOTS) sts_f64(slot + STUT_TERM_STRIDE, term);
       mx = dmax(mx, term);
       cnt++;
+      if (TRACE && (lp > best || (left_align && lp == best))) { best_pos = -e1.x; best = lp; }
     }
     if (e1.x <= warp_stop) { s += 1; break; }
     if (e1.x > stop) {
@@ -104,6 +109,7 @@ __device__ __forceinline__ double stut_walk(const StutCtx& c, int prog_index, in
       if (s + 2 < STUT_TERM_SLOTS) sts_f64(slot + 2 * STUT_TERM_STRIDE, term);
       mx = dmax(mx, term);
       cnt++;
+      if (TRACE && (lp > best || (left_align && lp == best))) { best_pos = -__ldg(&prog[s + 2].x); best = lp; }
     }
     s += 2;
     slot += 2 * STUT_TERM_STRIDE;
@@ -138,7 +144,8 @@ __device__ __forceinline__ double stut_walk(const StutCtx& c, int prog_index, in
 // The 13 table entries of one read column (HapAligner.cpp:76-100 without pre_prob).  On entry the deletion rows of
 // the table hold what pass 1 left there: match_probs_[q] - del_probs_[q][k-1] for q = j + k*period inside the read, or
 // the whole first term (prior included) where the read ends before q.
-__device__ __forceinline__ void stut_column(const StutCtx& c, int j, bool live, double* tcol, int pitch) {
+template <bool TRACE>
+__device__ __forceinline__ void stut_column(const StutCtx& c, int j, bool live, double* tcol, int32_t* pcol, int pitch) {
   const int B = c.B, p = c.p;
   const DevRep* rep = c.rep;
   const unsigned colj = c.val + j * HIPSTR_COL_BYTES;
@@ -150,10 +157,13 @@ __device__ __forceinline__ void stut_column(const StutCtx& c, int j, bool live, 
     double* cell = tcol + (HIPSTR_MAX_ARTIFACT_UNITS - k) * pitch;
     const double v = *cell;
     const double lp0 = (j - D <= c.n_side - 1) ? -__ldg(c.int_logs + (B + D + 1)) + v : v;
-    const double pr = stut_walk<false>(c, __ldg(rep->prog_off + k), -base_len, j, k, lp0, B + D);
+    int pos;
+    const double pr = stut_walk<false, TRACE>(c, __ldg(rep->prog_off + k), -base_len, j, k, lp0, B + D, pos);
     if (live) *cell = __ldg(rep->art + (HIPSTR_MAX_ARTIFACT_UNITS - k)) + pr;
+    if (TRACE && live) pcol[(HIPSTR_MAX_ARTIFACT_UNITS - k) * pitch] = pos;
   }
   if (live) tcol[HIPSTR_MAX_ARTIFACT_UNITS * pitch] = __ldg(rep->art + HIPSTR_MAX_ARTIFACT_UNITS) + c.match[j];
+  if (TRACE && live) pcol[HIPSTR_MAX_ARTIFACT_UNITS * pitch] = -1;
   double ins_acc = 0.0;    // ins_probs_ running sum (StutterAlignerClass.cpp:38-51)
   int ins_t = 0;
   const double ins_prior = -__ldg(c.int_logs + (B + 1));
@@ -171,8 +181,10 @@ __device__ __forceinline__ void stut_column(const StutCtx& c, int j, bool live, 
     lp0 += (base_len > D) ? c.match[j - D] : 0.0;
     const int stop = -min(max(0, base_len - D), B);
     __syncwarp();
-    const double pr = stut_walk<true>(c, ins_prog, stop, j, k, lp0, B);
+    int pos;
+    const double pr = stut_walk<true, TRACE>(c, ins_prog, stop, j, k, lp0, B, pos);
     if (live) tcol[(HIPSTR_MAX_ARTIFACT_UNITS + k) * pitch] = __ldg(rep->art + HIPSTR_MAX_ARTIFACT_UNITS + k) + pr;
+    if (TRACE && live) pcol[(HIPSTR_MAX_ARTIFACT_UNITS + k) * pitch] = pos;
   }
 }
 
@@ -189,6 +201,7 @@ size_t stutter_smem_bytes(int n_max) { return stut_smem_bytes_hd(n_max); }
 #ifndef STUT_MIN_CTAS
 #define STUT_MIN_CTAS 7
 #endif
+template <bool TRACE>
 __global__ void __launch_bounds__(STUT_THREADS, STUT_MIN_CTAS) k_stutter(const StutParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -252,7 +265,9 @@ __global__ void __launch_bounds__(STUT_THREADS, STUT_MIN_CTAS) k_stutter(const S
     }
     __syncthreads();
     const int pitch = hipstr_t_pitch(n);
-    double* tpool = P.stut + P.pool_t_off[job.pool];
+    // alignment: one slab per pooled read; traces: one slab per job (a trace reads one haplotype)
+    const int64_t t_off = P.job_t_off ? P.job_t_off[job_id] : P.pool_t_off[job.pool];
+    double* tpool = P.stut + t_off;
     const int n_tasks = 2 * job.n_slots;
     for (;;) {
       int task = 0;
@@ -265,6 +280,7 @@ __global__ void __launch_bounds__(STUT_THREADS, STUT_MIN_CTAS) k_stutter(const S
       const int n_side = side ? nR : nL;
       const int gbase = side ? nL : 0;
       double* tside = tpool + (size_t)(job.tslot0 + s) * HIPSTR_NUM_ARTIFACTS * pitch + gbase;
+      int32_t* pside = TRACE ? P.stut_pos + t_off + (size_t)(job.tslot0 + s) * HIPSTR_NUM_ARTIFACTS * pitch + gbase : nullptr;
       const DevRep* rep = P.reps + (side ? sr.rep_rev : sr.rep_fwd);
       StutCtx c;
       c.progs = P.progs; c.logrun = P.prog_logrun; c.rep = rep; c.int_logs = P.int_logs;
@@ -323,7 +339,7 @@ __global__ void __launch_bounds__(STUT_THREADS, STUT_MIN_CTAS) k_stutter(const S
         const bool live = jq < n_side;
         const int j = live ? jq : n_side - 1;   // idle lanes shadow the side's last column (the warp stays converged)
         __syncwarp();
-        stut_column(c, j, live, tside + j, pitch);
+        stut_column<TRACE>(c, j, live, tside + j, TRACE ? pside + j : nullptr, pitch);
       }
       __syncwarp();   // the next task overwrites this warp's tables
     }
@@ -332,10 +348,10 @@ __global__ void __launch_bounds__(STUT_THREADS, STUT_MIN_CTAS) k_stutter(const S
   }
 }
 
-cudaError_t launch_stutter(const StutParams& p, cudaStream_t stream) {
-  if (p.n_jobs <= 0) return cudaSuccess;
+template <bool TRACE>
+static cudaError_t launch_stutter_t(const StutParams& p, cudaStream_t stream) {
   const size_t smem = stut_smem_bytes_hd(p.n_max);
-  cudaError_t e = cudaFuncSetAttribute(k_stutter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_stutter<TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   static int sms = 0;
   if (!sms) {
@@ -344,13 +360,18 @@ cudaError_t launch_stutter(const StutParams& p, cudaStream_t stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stutter, STUT_THREADS, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stutter<TRACE>, STUT_THREADS, smem);
   if (e != cudaSuccess) return e;
   // persistent grid: exactly as many CTAs as can be resident (a multiple of the SM count)
   int grid = sms * (per_sm > 0 ? per_sm : 1);
   if (grid > p.n_jobs) grid = p.n_jobs;
-  k_stutter<<<grid, STUT_THREADS, smem, stream>>>(p);
+  k_stutter<TRACE><<<grid, STUT_THREADS, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_stutter(const StutParams& p, cudaStream_t stream) {
+  if (p.n_jobs <= 0) return cudaSuccess;
+  return p.stut_pos ? launch_stutter_t<true>(p, stream) : launch_stutter_t<false>(p, stream);
 }
 
 }  // namespace hipstr
