@@ -553,6 +553,7 @@ def bind_align_abi(lib, prefix):
 
 _lib = None
 _synth = None
+NEXT_WINDOW_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p)
 
 
 def load():
@@ -772,6 +773,26 @@ def load():
     lib.hipstr_genotyper_locus_log.argtypes = [vp, C.c_int32, C.c_void_p, C.c_int32]
     lib.hipstr_collect_timing.restype = C.c_int32
     lib.hipstr_collect_timing.argtypes = [vp, c_f64p, c_f64p, c_i32p]
+    lib.hipstr_multi_create.restype = C.c_int32
+    lib.hipstr_multi_create.argtypes = [C.c_int32, c_i32p, C.c_int32, C.POINTER(vp)]
+    lib.hipstr_multi_destroy.restype = None
+    lib.hipstr_multi_destroy.argtypes = [vp]
+    lib.hipstr_multi_last_error.restype = C.c_char_p
+    lib.hipstr_multi_last_error.argtypes = [vp]
+    lib.hipstr_multi_num_workers.restype = C.c_int32
+    lib.hipstr_multi_num_workers.argtypes = [vp]
+    lib.hipstr_multi_num_windows.restype = C.c_int32
+    lib.hipstr_multi_num_windows.argtypes = [C.c_int32, C.c_int32]
+    lib.hipstr_multi_window_order.restype = C.c_int32
+    lib.hipstr_multi_window_order.argtypes = [C.c_int32, C.c_int32, c_i32p, c_i32p]
+    lib.hipstr_multi_genotype.restype = C.c_int32
+    lib.hipstr_multi_genotype.argtypes = [vp, C.c_int32, c_i32p, c_i32p, c_i32p, C.POINTER(C.c_char_p), c_f64p, C.POINTER(LocusReadsStruct),
+                                          C.POINTER(VcfLoci), C.POINTER(VcfOptions), C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                          NEXT_WINDOW_FN, vp, c_u8p]
+    lib.hipstr_multi_locus_record.restype = C.c_int32
+    lib.hipstr_multi_locus_record.argtypes = [vp, C.c_int32, c_i32p, vp, C.c_int32]
+    lib.hipstr_multi_stats.restype = C.c_int32
+    lib.hipstr_multi_stats.argtypes = [vp, c_i64p, c_i64p, c_f64p, c_i32p, c_f64p]
     _lib = lib
     return lib
 
@@ -1267,6 +1288,82 @@ class BatchBuilder:
         b._keep = keep
         b.n_out = int(loo[-1])
         return b
+
+
+class MultiGenotyper:
+    """hipstr_multi_t: the locus list of seam B1 dealt window by window to worker threads, one per (device, pipeline)."""
+
+    STAGES = ("construct", "decide", "trace_device", "trace_host", "align", "posteriors", "vcf", "align_pack", "align_unpack")
+
+    def __init__(self, devices=(0,), pipelines=2):
+        self.lib = load()
+        dev = np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        st = self.lib.hipstr_multi_create(len(dev), ptr(dev, c_i32p), pipelines, C.byref(h))
+        if st != 0:
+            raise HipstrError(st, "hipstr_multi_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.hipstr_multi_destroy(self.h)
+            self.h = None
+
+    def window_order(self, synth, window_loci):
+        n = self.lib.hipstr_multi_num_windows(synth.n_loci, window_loci)
+        order = np.zeros(n, np.int32)
+        st = self.lib.hipstr_multi_window_order(synth.n_loci, window_loci, synth.view.locus_read_off, ptr(order, c_i32p))
+        if st != 0:
+            raise HipstrError(st, "hipstr_multi_window_order")
+        return order
+
+    def genotype_synth(self, synth, vcf_loci, window_loci, stutter=(0.95, 0.05, 0.05, 0.95, 0.01, 0.01), next_window=None,
+                       max_total_haplotypes=1000, max_flank_haplotypes=4, min_flank_freq=0.01, **options):
+        """create_from_reads -> genotype(flank assembly on) -> write_vcf for every locus of a Synth.  next_window = a
+        Python callable returning the next position in the dealing order (a dealer shared with other processes), or None
+        for the handle's own counter.  Returns (locus_ok, [(pos, text) or None per locus])."""
+        v = synth.view
+        L = synth.n_loci
+        rs = Genotyper._reads_struct(synth)
+        cl = int(v.chrom_len)
+        raw = C.string_at(v.chrom_seqs, L * cl)
+        chroms = [raw[l * cl:(l + 1) * cl] for l in range(L)]
+        carr = (C.c_char_p * L)(*chroms)
+        start = np.full(L, int(v.region_start), np.int32)
+        stop = np.full(L, int(v.region_stop), np.int32)
+        period = np.full(L, int(synth.cfg.period) or 4, np.int32)
+        st6 = np.tile(np.asarray(stutter, np.float64), L)
+        opt = VcfOptions()
+        self.lib.hipstr_vcf_default_options(C.byref(opt))
+        for k, val in options.items():
+            setattr(opt, k, val)
+        ok = np.zeros(L, np.uint8)
+        cb = NEXT_WINDOW_FN(lambda user: int(next_window())) if next_window is not None else C.cast(None, NEXT_WINDOW_FN)
+        st = self.lib.hipstr_multi_genotype(self.h, L, ptr(start, c_i32p), ptr(stop, c_i32p), ptr(period, c_i32p), carr, ptr(st6, c_f64p),
+                                            C.byref(rs), C.byref(vcf_loci), C.byref(opt), max_total_haplotypes, max_flank_haplotypes,
+                                            min_flank_freq, window_loci, cb, None, ptr(ok, c_u8p))
+        if st != 0:
+            raise HipstrError(st, "hipstr_multi_genotype: " + (self.lib.hipstr_multi_last_error(self.h) or b"").decode())
+        return ok, self.records(L)
+
+    def records(self, n_loci):
+        out = []
+        buf = np.zeros(1 << 22, np.uint8)
+        for l in range(n_loci):
+            pos = C.c_int32()
+            n = self.lib.hipstr_multi_locus_record(self.h, l, C.byref(pos), buf.ctypes.data, len(buf))
+            if n < 0:
+                raise HipstrError(3, "record of locus %d needs %d bytes" % (l, -n))
+            out.append((pos.value, bytes(buf[:n]).decode()) if n > 0 else None)
+        return out
+
+    def stats(self):
+        nw = self.lib.hipstr_multi_num_workers(self.h)
+        a, t = C.c_int64(), C.c_int64()
+        sec, win, busy = np.zeros(9), np.zeros(nw, np.int32), np.zeros(nw)
+        self.lib.hipstr_multi_stats(self.h, C.byref(a), C.byref(t), ptr(sec, c_f64p), ptr(win, c_i32p), ptr(busy, c_f64p))
+        return {"alignments": a.value, "traces": t.value, "stage_seconds": dict(zip(self.STAGES, [round(float(x), 4) for x in sec])),
+                "windows_per_worker": win.tolist(), "busy_seconds_per_worker": [round(float(x), 3) for x in busy]}
 
 
 class Context:

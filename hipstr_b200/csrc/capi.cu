@@ -8,8 +8,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/hipstr_b200.h"
@@ -117,13 +121,55 @@ cudaError_t put(DevBuf& d, const std::vector<T>& v, cudaStream_t s) { return put
 template <class T>
 cudaError_t put(DevBuf& d, const HostBuf<T>& v, cudaStream_t s) { return put(d, v.data(), v.size(), s); }
 
-// page-locked staging for flatten.cpp's big arrays
+// Page-locked staging for the big host arrays (flatten.cpp's packed batch, the loop's packing / result buffers):
+// H2D / D2H copies then run at full PCIe speed and truly asynchronously.  cudaHostAlloc costs milliseconds, and the loop
+// asks for the same few sizes every round, so freed blocks are kept in a size-sorted cache and handed out again
+// (best fit, at most twice the request); the cache is capped, the excess goes back to the driver.
+struct PinnedCache {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  std::unordered_map<void*, size_t> size_of;
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCached = (size_t)8 << 30;
+};
+PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }
 void* pinned_alloc(size_t bytes) {
+  PinnedCache& c = pinned_cache();
+  if (bytes == 0) bytes = 16;
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.free_blocks.lower_bound(bytes);
+    if (it != c.free_blocks.end() && it->first <= 2 * bytes + 4096) {
+      void* p = it->second;
+      c.cached_bytes -= it->first;
+      c.free_blocks.erase(it);
+      return p;
+    }
+  }
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.size_of[p] = bytes;
   return p;
 }
-void pinned_free(void* p) { cudaFreeHost(p); }
+void pinned_free(void* p) {
+  if (!p) return;
+  PinnedCache& c = pinned_cache();
+  size_t bytes = 0;
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.size_of.find(p);
+    if (it == c.size_of.end()) { std::free(p); return; }   // allocated with malloc before a context existed
+    bytes = it->second;
+    if (c.cached_bytes + bytes <= PinnedCache::kMaxCached) {
+      c.free_blocks.emplace(bytes, p);
+      c.cached_bytes += bytes;
+      return;
+    }
+    c.size_of.erase(it);
+  }
+  cudaFreeHost(p);
+}
 void begin_call(hipstr_ctx* c) { g_h2d = 0; c->h2d_bytes = c->d2h_bytes = 0; c->last_launches = 0; }
 void end_call(hipstr_ctx* c) { c->h2d_bytes = g_h2d; }
 template <class T>

@@ -41,6 +41,17 @@ void* host_alloc(size_t bytes) {
 }
 void host_free(void* p) { if (g_free) g_free(p); else std::free(p); }
 
+namespace { thread_local int t_thread_cap = 0; }
+void set_host_thread_budget(int n) { t_thread_cap = n > 0 ? n : 0; }
+int host_thread_budget() {
+  static const int n = [] {
+    const char* env = std::getenv("HIPSTR_HOST_THREADS");
+    const int t = env ? std::atoi(env) : (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(t, 32));
+  }();
+  return t_thread_cap > 0 ? std::min(n, t_thread_cap) : n;
+}
+
 void FlatBatch::clear() {
   pools.clear(); bases.clear(); quals.clear();
   hapsides.clear(); hapbytes.clear(); blocks.clear(); reps.clear(); progs.clear(); prog_logrun.clear(); rep_tabs.clear(); hap_mask.clear();
@@ -527,9 +538,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     return HIPSTR_OK;
   };
   {
-    int n_threads = (int)std::thread::hardware_concurrency();
-    if (const char* e = std::getenv("HIPSTR_HOST_THREADS")) n_threads = std::atoi(e);
-    n_threads = std::max(1, std::min(n_threads, 32));
+    int n_threads = host_thread_budget();
     if (b->n_loci < 64) n_threads = 1;
     const int n_chunks = n_threads == 1 ? 1 : std::min(b->n_loci, n_threads * 4);
     std::vector<Lowered> parts((size_t)n_chunks);
@@ -636,9 +645,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
       }
     }
   };
-  int n_threads = (int)std::thread::hardware_concurrency();
-  if (const char* e = std::getenv("HIPSTR_HOST_THREADS")) n_threads = std::atoi(e);
-  n_threads = std::max(1, std::min(n_threads, 32));
+  int n_threads = host_thread_budget();
   if (n_pools < 20000) n_threads = 1;
   if (n_threads == 1) fill(0, b->n_loci);
   else {

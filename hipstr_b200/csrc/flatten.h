@@ -101,6 +101,11 @@ struct FlatBatch {
   void clear();
 };
 
+/* Host threads a call may use: HIPSTR_HOST_THREADS or the hardware concurrency (at most 32), capped by the calling
+ * thread's own budget when one was set (the multi-GPU driver splits the cores between its window workers). */
+int host_thread_budget();
+void set_host_thread_budget(int n);   /* for the calling thread; 0 = no cap */
+
 /* Returns HIPSTR_OK or an error with a message. */
 /* fresh_rows: give every haplotype the homopolymer classes of a from-scratch alignment (what
  * trace_optimal_aln sees: the haplotype is fixed, nothing is reused) instead of replaying the

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <string_view>
 #include <unordered_map>
 #include <vector>
 
@@ -86,64 +87,70 @@ extern "C" hipstr_status_t hipstr_pool_reads(int32_t n_reads, const int32_t* seq
   if (n_reads > 0 && (!seq_off || !bases || !quals || !pool_index || !pool_first_read || !pool_seq_off ||
                       !pool_bases || !pool_quals))
     return HIPSTR_ERR_BAD_ARG;
-  std::unordered_map<std::string, int32_t> by_seq;
+  // keys are views into the caller's bases: no per-read string allocations
+  std::unordered_map<std::string_view, int32_t> by_seq;
   by_seq.reserve((size_t)n_reads * 2);
-  std::vector<std::vector<int32_t> > members;
+  std::vector<int32_t> next_member((size_t)n_reads, -1), last_member, count;   // members of a pool as a linked list in read order
   for (int32_t r = 0; r < n_reads; r++) {
-    std::string key(bases + seq_off[r], bases + seq_off[r + 1]);
+    const std::string_view key(bases + seq_off[r], (size_t)(seq_off[r + 1] - seq_off[r]));
     auto it = by_seq.find(key);
     if (it == by_seq.end()) {
-      it = by_seq.emplace(std::move(key), (int32_t)members.size()).first;
-      pool_first_read[members.size()] = r;
-      members.emplace_back();
+      it = by_seq.emplace(key, (int32_t)last_member.size()).first;
+      pool_first_read[last_member.size()] = r;
+      last_member.push_back(r);
+      count.push_back(1);
+    } else {
+      next_member[last_member[it->second]] = r;
+      last_member[it->second] = r;
+      count[it->second]++;
     }
     pool_index[r] = it->second;
-    members[it->second].push_back(r);
   }
   int32_t at = 0;
-  std::vector<signed char> column, block;
-  std::vector<uint8_t> rank;
-  for (size_t p = 0; p < members.size(); p++) {
-    const int32_t first = members[p][0];
+  std::vector<const unsigned char*> rows;
+  uint16_t hist[256];
+  std::memset(hist, 0, sizeof(hist));
+  for (size_t p = 0; p < last_member.size(); p++) {
+    const int32_t first = pool_first_read[p];
     const int32_t len = seq_off[first + 1] - seq_off[first];
     pool_seq_off[p] = at;
     std::memcpy(pool_bases + at, bases + seq_off[first], len);
-    const size_t m = members[p].size();
+    const size_t m = (size_t)count[p];
     if (m == 1)
       std::memcpy(pool_quals + at, quals + seq_off[first], len);
-    else if (m <= 64) {
-      // Upper median per position by RANK: member k's byte is the median where exactly m/2 members sort before it
-      // (signed char order like std::sort, ties by member index).  Every inner loop runs along the read, over
-      // contiguous bytes, so the compiler vectorises it -- a per-position nth_element gathers one byte from each
-      // member and was the largest single cost of building a locus.
-      rank.resize((size_t)len);
-      const uint8_t want = (uint8_t)(m / 2);
-      for (size_t k = 0; k < m; k++) {
-        const signed char* qk = reinterpret_cast<const signed char*>(quals + seq_off[members[p][k]]);
-        std::fill(rank.begin(), rank.end(), (uint8_t)0);
-        for (size_t j = 0; j < m; j++) {
-          if (j == k) continue;
-          const signed char* qj = reinterpret_cast<const signed char*>(quals + seq_off[members[p][j]]);
-          uint8_t* rk = rank.data();
-          if (j < k) for (int32_t i = 0; i < len; i++) rk[i] += (uint8_t)(qj[i] <= qk[i]);
-          else for (int32_t i = 0; i < len; i++) rk[i] += (uint8_t)(qj[i] < qk[i]);
-        }
-        for (int32_t i = 0; i < len; i++)
-          if (rank[i] == want) pool_quals[at + i] = (char)qk[i];
-      }
+    else if (m == 2) {
+      // upper median of two = the larger byte in signed char order (std::sort on chars, base_quality.cpp:11-28)
+      const signed char* a = reinterpret_cast<const signed char*>(quals + seq_off[first]);
+      const signed char* b = reinterpret_cast<const signed char*>(quals + seq_off[next_member[first]]);
+      for (int32_t i = 0; i < len; i++) pool_quals[at + i] = (char)(a[i] > b[i] ? a[i] : b[i]);
     } else {
-      // large pools: members copied into one block, then a selection per position
-      block.resize(m * (size_t)len);
-      for (size_t k = 0; k < m; k++) std::memcpy(block.data() + k * (size_t)len, quals + seq_off[members[p][k]], (size_t)len);
-      column.resize(m);
+      // Upper median per position (sorted[m / 2] in signed char order) by counting: m increments of a 256-bin histogram
+      // indexed by (byte ^ 0x80) -- which turns signed order into unsigned order -- then a scan of the occupied range.
+      rows.clear();
+      for (int32_t r = first; r >= 0; r = next_member[r]) rows.push_back(reinterpret_cast<const unsigned char*>(quals + seq_off[r]));
+      const uint32_t want = (uint32_t)(m / 2);
       for (int32_t i = 0; i < len; i++) {
-        for (size_t k = 0; k < m; k++) column[k] = block[k * (size_t)len + i];
-        std::nth_element(column.begin(), column.begin() + m / 2, column.end());
-        pool_quals[at + i] = (char)column[m / 2];
+        unsigned lo = 255, hi = 0;
+        for (size_t k = 0; k < m; k++) {
+          const unsigned v = rows[k][i] ^ 0x80u;
+          hist[v]++;
+          lo = v < lo ? v : lo;
+          hi = v > hi ? v : hi;
+        }
+        uint32_t seen = 0;
+        unsigned med = hi;
+        bool found = false;
+        for (unsigned v = lo; v <= hi; v++) {
+          seen += hist[v];
+          if (!found && seen > want) { med = v; found = true; }
+          hist[v] = 0;
+        }
+        pool_quals[at + i] = (char)(med ^ 0x80u);
       }
     }
     at += len;
   }
+  const std::vector<int32_t>& members = last_member;
   pool_seq_off[members.size()] = at;
   *n_pools = (int32_t)members.size();
   return HIPSTR_OK;

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstring>
 #include <set>
+#include <unordered_set>
 #include <atomic>
 #include <cstdlib>
 #include <sstream>
@@ -25,14 +26,7 @@ namespace hipstr {
 namespace {
 
 }  // namespace
-int host_threads() {
-  static const int n = [] {
-    const char* env = std::getenv("HIPSTR_HOST_THREADS");
-    int t = env ? std::atoi(env) : (int)std::thread::hardware_concurrency();
-    return std::max(1, std::min(t, 32));
-  }();
-  return n;
-}
+int host_threads() { return host_thread_budget(); }
 void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
   const size_t workers = std::min<size_t>((size_t)host_threads(), n);
   if (workers <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
@@ -238,11 +232,12 @@ int SeqStutterGenotyper::best_hap_of_read(int r) const {
 bool SeqStutterGenotyper::collect_missing_traces() {
   missing_traces_.clear();
   missing_trace_read_.clear();
-  std::set<std::pair<int, int> > wanted;
+  std::unordered_set<uint64_t> wanted;
   for (int r = 0; r < num_reads_; r++) {
     if (seed_positions_[r] < 0) continue;
     std::pair<int, int> key(pool_index_[r], best_hap_of_read(r));
-    if (trace_cache_.count(key) == 0 && wanted.insert(key).second) missing_traces_.push_back(key);
+    if (trace_cache_.count(key) == 0 && wanted.insert(((uint64_t)(uint32_t)key.first << 32) | (uint32_t)key.second).second)
+      missing_traces_.push_back(key);
   }
   return missing_traces_.empty();
 }
@@ -354,7 +349,8 @@ bool SeqStutterGenotyper::add_and_remove_alleles(const std::vector<std::vector<i
     for (int j = 0; j < old_H; j++)
       if (allele_mapping[j] != -1) fixed[(size_t)r * new_H + allele_mapping[j]] = log_aln_probs_[(size_t)r * old_H + j];
   log_aln_probs_.swap(fixed);
-  std::map<std::pair<int, int>, AlignmentTrace> remapped;
+  TraceCache remapped;
+  remapped.reserve(trace_cache_.size());
   for (auto& kv : trace_cache_) {
     const int h = allele_mapping[kv.first.second];
     if (h != -1) remapped[std::make_pair(kv.first.first, h)] = std::move(kv.second);
@@ -702,50 +698,6 @@ struct PackedBatch {
   }
 };
 
-/* The read-level arrays (hipstr_reads_batch_t) of a list of loci plus the in/out result buffers. */
-struct PackedReads {
-  std::vector<int32_t> locus_read_off{0}, locus_sample_off{0}, pool_index, sample_label, read_weight, n_haps;
-  std::vector<uint8_t> second_mate, haploid, copy_read;
-  std::vector<double> log_p1, log_p2;
-  bool copy_masked = false;
-  std::vector<double> read_ll, post, sample_ll, total_ll;
-  std::vector<int32_t> read_seed, best;
-
-  void add(const SeqStutterGenotyper& g) {
-    pool_index.insert(pool_index.end(), g.pool_index_.begin(), g.pool_index_.end());
-    sample_label.insert(sample_label.end(), g.sample_label_.begin(), g.sample_label_.end());
-    read_weight.insert(read_weight.end(), g.read_weights_.begin(), g.read_weights_.end());
-    second_mate.insert(second_mate.end(), g.second_mate_.begin(), g.second_mate_.end());
-    log_p1.insert(log_p1.end(), g.log_p1_.begin(), g.log_p1_.end());
-    log_p2.insert(log_p2.end(), g.log_p2_.begin(), g.log_p2_.end());
-    haploid.push_back(g.haploid_ ? 1 : 0);
-    n_haps.push_back(g.num_alleles_);
-    locus_read_off.push_back((int32_t)pool_index.size());
-    locus_sample_off.push_back(locus_sample_off.back() + g.num_samples_);
-    read_ll.insert(read_ll.end(), g.log_aln_probs_.begin(), g.log_aln_probs_.end());
-    read_seed.insert(read_seed.end(), g.seed_positions_.begin(), g.seed_positions_.end());
-  }
-  void size_outputs(const std::vector<SeqStutterGenotyper*>& gs) {
-    size_t post_size = 0;
-    for (auto g : gs) post_size += (size_t)g->num_samples_ * g->num_alleles_ * g->num_alleles_;
-    post.assign(post_size, 0.0);
-    sample_ll.assign(locus_sample_off.back(), 0.0);
-    best.assign((size_t)locus_sample_off.back() * 2, 0);
-    total_ll.assign(gs.size(), 0.0);
-  }
-  void scatter_back(const std::vector<SeqStutterGenotyper*>& gs) {   // posteriors only: the likelihoods did not change
-    size_t post_at = 0;
-    for (size_t k = 0; k < gs.size(); k++) {
-      SeqStutterGenotyper& g = *gs[k];
-      const size_t npost = (size_t)g.num_samples_ * g.num_alleles_ * g.num_alleles_;
-      g.log_sample_posteriors_.assign(post.begin() + post_at, post.begin() + post_at + npost);
-      g.sample_total_LLs_.assign(sample_ll.begin() + locus_sample_off[k], sample_ll.begin() + locus_sample_off[k + 1]);
-      g.optimal_haps_.assign(best.begin() + 2 * (size_t)locus_sample_off[k], best.begin() + 2 * (size_t)locus_sample_off[k + 1]);
-      post_at += npost;
-    }
-  }
-};
-
 }  // namespace
 
 hipstr_status_t GenotyperBatch::init_reads(SeqStutterGenotyper& g, const hipstr_locus_reads_t* rd, int l, std::string& err) {
@@ -911,7 +863,9 @@ hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_
 
 namespace {
 
-/* Uninitialised buffer: std::vector would zero (and page-fault) hundreds of MB on one core before the workers fill it. */
+/* Uninitialised buffer from the pluggable host allocator (flatten.h): page-locked through the C-ABI layer's block cache
+ * when a context exists, so the copies to and from the device run at PCIe speed; std::vector would also zero (and
+ * page-fault) hundreds of MB on one core before the workers fill it. */
 template <class T>
 struct RawBuf {
   T* p = nullptr;
@@ -919,8 +873,8 @@ struct RawBuf {
   RawBuf() {}
   RawBuf(const RawBuf&) = delete;
   RawBuf& operator=(const RawBuf&) = delete;
-  ~RawBuf() { std::free(p); }
-  void alloc(size_t count) { std::free(p); n = count; p = static_cast<T*>(std::malloc(std::max<size_t>(count, 1) * sizeof(T))); }
+  ~RawBuf() { if (p) host_free(p); }
+  void alloc(size_t count) { if (p) host_free(p); n = count; p = static_cast<T*>(host_alloc(std::max<size_t>(count, 1) * sizeof(T))); }
   T* data() { return p; }
 };
 
@@ -1057,18 +1011,50 @@ hipstr_status_t GenotyperBatch::run_alignments(const std::vector<int>& which, st
   return HIPSTR_OK;
 }
 
+/* One K3 call for the loci in `which` (loci that only lost alleles: the likelihoods are unchanged, only the posteriors are
+ * recomputed).  Packed by all host threads into page-locked buffers like run_alignments. */
 hipstr_status_t GenotyperBatch::run_posteriors(const std::vector<int>& which, std::string& err) {
   if (which.empty()) return HIPSTR_OK;
-  PackedReads pr;
-  std::vector<SeqStutterGenotyper*> gs;
-  for (int l : which) { pr.add(loci[l]); gs.push_back(&loci[l]); }
-  pr.size_outputs(gs);
-  hipstr_status_t st = hipstr_posteriors_host(ctx_, (int32_t)gs.size(), pr.locus_read_off.data(), pr.locus_sample_off.data(),
-                                              pr.n_haps.data(), pr.haploid.data(), pr.read_ll.data(), pr.log_p1.data(),
-                                              pr.log_p2.data(), pr.sample_label.data(), pr.read_weight.data(), pr.post.data(),
-                                              pr.sample_ll.data(), pr.best.data(), pr.total_ll.data());
+  const size_t L = which.size();
+  std::vector<SeqStutterGenotyper*> gs(L);
+  for (size_t k = 0; k < L; k++) gs[k] = &loci[which[k]];
+  std::vector<int32_t> locus_read_off(L + 1, 0), locus_sample_off(L + 1, 0), n_haps(L);
+  std::vector<int64_t> ll_off(L + 1, 0), post_off(L + 1, 0);
+  std::vector<uint8_t> haploid(L);
+  for (size_t k = 0; k < L; k++) {
+    const SeqStutterGenotyper& g = *gs[k];
+    locus_read_off[k + 1] = locus_read_off[k] + g.num_reads_;
+    locus_sample_off[k + 1] = locus_sample_off[k] + g.num_samples_;
+    ll_off[k + 1] = ll_off[k] + (int64_t)g.num_reads_ * g.num_alleles_;
+    post_off[k + 1] = post_off[k] + (int64_t)g.num_samples_ * g.num_alleles_ * g.num_alleles_;
+    n_haps[k] = g.num_alleles_;
+    haploid[k] = g.haploid_ ? 1 : 0;
+  }
+  const size_t R = locus_read_off[L], S = locus_sample_off[L];
+  RawBuf<int32_t> sample_label, read_weight, best;
+  RawBuf<double> log_p1, log_p2, read_ll, post, sample_ll, total_ll;
+  sample_label.alloc(R); read_weight.alloc(R); log_p1.alloc(R); log_p2.alloc(R); read_ll.alloc(ll_off[L]);
+  post.alloc(post_off[L]); sample_ll.alloc(S); best.alloc(2 * S); total_ll.alloc(L);
+  parallel_for(L, [&](size_t k) {
+    const SeqStutterGenotyper& g = *gs[k];
+    const int32_t r0 = locus_read_off[k];
+    const size_t nr = (size_t)g.num_reads_;
+    std::memcpy(sample_label.p + r0, g.sample_label_.data(), nr * sizeof(int32_t));
+    std::memcpy(read_weight.p + r0, g.read_weights_.data(), nr * sizeof(int32_t));
+    std::memcpy(log_p1.p + r0, g.log_p1_.data(), nr * sizeof(double));
+    std::memcpy(log_p2.p + r0, g.log_p2_.data(), nr * sizeof(double));
+    std::memcpy(read_ll.p + ll_off[k], g.log_aln_probs_.data(), (size_t)(ll_off[k + 1] - ll_off[k]) * sizeof(double));
+  });
+  hipstr_status_t st = hipstr_posteriors_host(ctx_, (int32_t)L, locus_read_off.data(), locus_sample_off.data(), n_haps.data(),
+                                              haploid.data(), read_ll.p, log_p1.p, log_p2.p, sample_label.p, read_weight.p, post.p,
+                                              sample_ll.p, best.p, total_ll.p);
   if (st != HIPSTR_OK) { err = std::string("hipstr_posteriors_host: ") + hipstr_last_error(ctx_); return st; }
-  pr.scatter_back(gs);
+  parallel_for(L, [&](size_t k) {
+    SeqStutterGenotyper& g = *gs[k];
+    g.log_sample_posteriors_.assign(post.p + post_off[k], post.p + post_off[k + 1]);
+    g.sample_total_LLs_.assign(sample_ll.p + locus_sample_off[k], sample_ll.p + locus_sample_off[k + 1]);
+    g.optimal_haps_.assign(best.p + 2 * (size_t)locus_sample_off[k], best.p + 2 * (size_t)locus_sample_off[k + 1]);
+  });
   return HIPSTR_OK;
 }
 

@@ -21,6 +21,7 @@
 
 #include <functional>
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -62,6 +63,33 @@ struct AlignmentTrace {
 std::string hap_aln_to_ref(const std::string& ref_hap, const std::string& alt_hap, int32_t first_block_start,
                            int32_t repeat_block_start);
 
+/* trace_cache_ (seq_stutter_genotyper.h:61 of the reference: std::map<std::pair<int,int>, AlignmentTrace*>): (pooled read,
+ * haplotype) -> trace.  Every decision of the loop looks its reads up here, ~10 lookups per read and round, so the map is
+ * a hash over one 64-bit key with the traces in a flat vector instead of a red-black tree of pairs. */
+class TraceCache {
+ public:
+  typedef std::pair<int, int> Key;
+  size_t count(const Key& k) const { return index_.count(pack(k)); }
+  const AlignmentTrace& at(const Key& k) const { return items_[index_.at(pack(k))].second; }
+  AlignmentTrace& operator[](const Key& k) {
+    auto it = index_.find(pack(k));
+    if (it != index_.end()) return items_[it->second].second;
+    index_.emplace(pack(k), (int32_t)items_.size());
+    items_.emplace_back(k, AlignmentTrace());
+    return items_.back().second;
+  }
+  void clear() { index_.clear(); items_.clear(); }
+  void swap(TraceCache& o) { index_.swap(o.index_); items_.swap(o.items_); }
+  size_t size() const { return items_.size(); }
+  void reserve(size_t n) { index_.reserve(n); items_.reserve(n); }
+  std::vector<std::pair<Key, AlignmentTrace> >::iterator begin() { return items_.begin(); }
+  std::vector<std::pair<Key, AlignmentTrace> >::iterator end() { return items_.end(); }
+ private:
+  static uint64_t pack(const Key& k) { return ((uint64_t)(uint32_t)k.first << 32) | (uint32_t)k.second; }
+  std::unordered_map<uint64_t, int32_t> index_;
+  std::vector<std::pair<Key, AlignmentTrace> > items_;
+};
+
 class GenotyperBatch;
 double now_s();   /* steady clock, seconds */
 /* Runs fn(i) for i in [0, n) on the host cores (std::thread, dynamic scheduling).  The per-locus host logic of the
@@ -98,7 +126,7 @@ class SeqStutterGenotyper {
   std::vector<double> sample_total_LLs_;       /* [S] */
   std::vector<int32_t> optimal_haps_;          /* [S][2] get_optimal_haplotypes */
   std::vector<std::string> call_sample_;       /* non-empty = sample not genotyped, with the reason */
-  std::map<std::pair<int, int>, AlignmentTrace> trace_cache_;   /* (pool, haplotype) -> trace */
+  TraceCache trace_cache_;                     /* (pool, haplotype) -> trace */
   std::string log_;
   std::string vcf_record_;                     /* text of the last write_vcf_record */
   int32_t vcf_pos_ = 0;                        /* its POS */

@@ -516,6 +516,47 @@ hipstr_status_t hipstr_genotyper_write_vcf(hipstr_genotyper_t* g, const hipstr_v
 /* the record of one locus (empty when the locus produced none); returns its length or -needed */
 int32_t         hipstr_genotyper_locus_record(const hipstr_genotyper_t* g, int32_t locus, int32_t* pos, char* out, int32_t cap);
 
+/* --- the locus list of seam B1 on every GPU of the box, from C++ ------------------
+ * Replaces the region loop of BamProcessor::process_regions (src/bam_processor.cpp:550-617) around
+ * GenotyperBamProcessor::analyze_reads_and_phasing (src/genotyper_bam_processor.cpp:229-246: constructor, genotype(),
+ * write_vcf_record per locus) for a whole list of loci.  The list is cut into windows of `window_loci` consecutive
+ * loci; one worker thread per (device, pipeline) owns a context on its device and pulls the next window when it has
+ * finished one, heaviest windows (most reads) first, so no static split has to guess the cost of a locus.  Several
+ * pipelines per device overlap the host stages of one window with the device stages of another.  There is no exchange
+ * between devices; the records are kept per locus and read back in locus order, the order VCFWriter::add_vcf_record
+ * needs (src/vcf_writer.h:33-35).
+ *   devices [n_devices]       CUDA device ordinals; pipelines_per_device 1..8 (2-3 keep one GPU busy)
+ *   next_window / user        NULL = the handle's own counter.  Otherwise the dealer: returns the next position in the
+ *                             dealing order (0, 1, 2, ...; anything outside [0, windows) stops the worker) -- lets the
+ *                             workers of several PROCESSES (one per GPU under torchrun) share one locus list through a
+ *                             counter of their own (hipstr_multi_window_order is a pure function of the inputs).
+ *   locus_ok [n_loci]         genotype()'s return value per locus (0 for windows another process took); may be NULL
+ * Arguments otherwise as hipstr_genotyper_create_from_reads / _genotype (reassemble_flanks = 1) / _write_vcf. */
+typedef struct hipstr_multi hipstr_multi_t;
+typedef struct hipstr_vcf_writer hipstr_vcf_writer_t;   /* seam B5, declared below */
+typedef int32_t (*hipstr_next_window_fn)(void* user);
+hipstr_status_t hipstr_multi_create(int32_t n_devices, const int32_t* devices, int32_t pipelines_per_device, hipstr_multi_t** out);
+void            hipstr_multi_destroy(hipstr_multi_t* m);
+const char*     hipstr_multi_last_error(const hipstr_multi_t* m);
+int32_t         hipstr_multi_num_workers(const hipstr_multi_t* m);
+int32_t         hipstr_multi_num_windows(int32_t n_loci, int32_t window_loci);
+/* order [windows]: the window dealt at position k (heaviest first; cost = reads of the window) */
+hipstr_status_t hipstr_multi_window_order(int32_t n_loci, int32_t window_loci, const int32_t* locus_read_off, int32_t* order);
+hipstr_status_t hipstr_multi_genotype(hipstr_multi_t* m, int32_t n_loci, const int32_t* region_start, const int32_t* region_stop,
+                                      const int32_t* period, const char* const* chrom_seq, const double* stutter,
+                                      const hipstr_locus_reads_t* reads, const hipstr_vcf_loci_t* vcf_loci,
+                                      const hipstr_vcf_options_t* vcf_options, int32_t max_total_haplotypes,
+                                      int32_t max_flank_haplotypes, double min_flank_freq, int32_t window_loci,
+                                      hipstr_next_window_fn next_window, void* next_window_user, uint8_t* locus_ok);
+/* the record of one locus (empty when the locus produced none or another process took its window); returns its length or -needed */
+int32_t         hipstr_multi_locus_record(const hipstr_multi_t* m, int32_t locus, int32_t* pos, char* out, int32_t cap);
+/* feed the records to a writer in locus order (VCFWriter::add_vcf_record) */
+hipstr_status_t hipstr_multi_emit_records(const hipstr_multi_t* m, const hipstr_vcf_loci_t* loci, hipstr_vcf_writer_t* w);
+/* alignments / traces computed, stage seconds summed over windows (layout of hipstr_genotyper_timing), and per worker
+ * (device-major, pipeline-minor) the windows it processed and the seconds it was busy; any pointer may be NULL */
+hipstr_status_t hipstr_multi_stats(const hipstr_multi_t* m, int64_t* n_alignments, int64_t* n_traces, double* seconds9,
+                                   int32_t* windows_per_worker, double* busy_seconds_per_worker);
+
 /* Pure host arithmetic of write_vcf_record, exported so that it can be checked on its own:
  *   hipstr_allele_bias       compute_allele_bias (seq_stutter_genotyper.cpp:965-982): log10 of the two-sided
  *                            binomial p-value of the read split (the reference uses cephes bdtr, lib/cephes/bdtr.c)
