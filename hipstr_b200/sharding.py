@@ -76,3 +76,29 @@ def write_records(merged, writer_handle, lib):
         st = lib.hipstr_vcf_writer_add_record(writer_handle, chrom.encode(), pos, text.encode())
         if st != 0:
             raise RuntimeError("hipstr_vcf_writer_add_record failed with status %d" % st)
+
+
+def lpt_assign(costs, world):
+    """Cost-aware static sharding: longest-processing-time-first assignment of units (loci or windows)
+    with the given costs to `world` ranks.  Returns rank_of[unit].  Deterministic, so every rank computes the same map."""
+    import heapq
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    heap = [(0, r) for r in range(world)]
+    rank_of = [0] * len(costs)
+    for i in order:
+        load, r = heapq.heappop(heap)
+        rank_of[i] = r
+        heapq.heappush(heap, (load + costs[i], r))
+    return rank_of
+
+
+class StoreDealer:
+    """Dynamic window dealing across the ranks of a torch.distributed job: one atomic counter in the rendezvous store
+    (TCPStore.add).  Passed as hipstr_multi_genotype's next_window callback, so a rank pulls the next window of the
+    SHARED locus list the moment one of its pipelines is free -- no static split, no data-path collective."""
+
+    def __init__(self, store, key):
+        self.store, self.key = store, key
+
+    def __call__(self):
+        return int(self.store.add(self.key, 1)) - 1

@@ -130,3 +130,55 @@ def test_vcf_records_gathered_to_rank0_in_locus_order(tmp_path, world):
     mp.spawn(_record_worker, args=(world, _free_port(), n_loci, sharded), nprocs=world, join=True)
     assert open(sharded).read() == open(single).read()
     assert open(single).read().count("\n") == n_loci + 1
+
+
+def _loop_worker(rank, world, port, n_loci, out_path):
+    """bench.py's N>1 loop on CPU: every rank drives the C++ multi-GPU driver (over the host simulation), the ranks share
+    ONE locus list through a counter in the rendezvous store, rank 0 gathers the VCF records over gloo."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from hipstr_b200 import capi
+    capi._lib, capi.LIB_PATH = None, os.path.join(ROOT, "tests", "hostsim", "libhipstr_hostsim.so")
+    from hipstr_b200.sharding import StoreDealer, gather_vcf_records
+    import test_hostsim
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["HIPSTR_HOST_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s = test_hostsim.synth(n_loci, 91)   # the same list on every rank
+    m = capi.MultiGenotyper(devices=(0,), pipelines=2)
+    dealer = StoreDealer(dist.distributed_c10d._get_default_store(), "loop_test")
+    ok, rec = m.genotype_synth(s, test_hostsim.vcf_loci(s), 2, next_window=dealer)
+    windows = sum(m.stats()["windows_per_worker"])
+    m.close()
+    merged = gather_vcf_records([(l, "chrS", r[0], r[1]) for l, r in enumerate(rec) if r is not None])
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([windows], dtype=torch.int64))
+    if rank == 0:
+        import json
+        json.dump({"records": merged, "windows": [int(c.item()) for c in counts]}, open(out_path, "w"))
+    dist.destroy_process_group()
+
+
+def test_shared_list_loop_two_ranks(tmp_path):
+    """World size 2: windows are dealt dynamically from one shared list, every window exactly once, and the records rank 0
+    holds after the gather equal the single-process result in locus order."""
+    import json
+    import subprocess
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostsim")], check=True)
+    n_loci = 9
+    out = str(tmp_path / "loop.json")
+    mp.spawn(_loop_worker, args=(2, _free_port(), n_loci, out), nprocs=2, join=True)
+    got = json.load(open(out))
+    assert sum(got["windows"]) == 5
+    # the single-process result, through the same host simulation
+    code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from hipstr_b200 import capi\n"
+            "capi.LIB_PATH = %r\n"
+            "import test_hostsim\n"
+            "s = test_hostsim.synth(%d, 91)\n"
+            "ok, rec = test_hostsim.single_context_records(s)\n"
+            "print(json.dumps([[l, 'chrS', r[0], r[1]] for l, r in enumerate(rec) if r is not None]))\n"
+            % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "hostsim", "libhipstr_hostsim.so"), n_loci))
+    want = json.loads(subprocess.run([sys.executable, "-c", code], check=True, capture_output=True, text=True).stdout.splitlines()[-1])
+    assert got["records"] == want and len(want) > 0

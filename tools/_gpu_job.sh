@@ -1,6 +1,4 @@
 set -x
 mkdir -p gpurun_out/r2
-timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/r2/gpu_all1.log 2>&1
-tail -8 gpurun_out/r2/gpu_all1.log
-python tools/loop_time.py 200 8 1 0.05 1 > gpurun_out/r2/loop_v2.log 2>&1
-tail -7 gpurun_out/r2/loop_v2.log
+python bench.py --steps 5 --warmup 3 > gpurun_out/r2/bench_n1_a.json 2> gpurun_out/r2/bench_n1_a.err; tail -c 600 gpurun_out/r2/bench_n1_a.err
+python bench.py --workload cfg4_em --loci 500 --steps 3 --warmup 3 > gpurun_out/r2/bench_em.json 2> gpurun_out/r2/bench_em.err; tail -c 400 gpurun_out/r2/bench_em.err
