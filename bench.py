@@ -279,6 +279,10 @@ def gpu_full_loop(device, synth, pipelines, window, reps, world=1, rank=0, dist=
         merged = mine
         if world > 1:   # the one collective: finished records to rank 0
             merged = gather_vcf_records(mine, device=torch_dev)
+            import torch
+            ok_all = torch.from_numpy(ok.astype(np.int32)).to(torch_dev)   # a locus is genotyped by the rank that took its window
+            dist.all_reduce(ok_all, op=dist.ReduceOp.MAX)
+            ok = ok_all.cpu().numpy().astype(np.uint8)
             barrier()
             n_merged = len(merged) if merged is not None else 0
             dt = max_over_ranks(time.perf_counter() - t0)

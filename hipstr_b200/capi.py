@@ -464,6 +464,30 @@ def trace_batch(fn, batch, block_start, trace_pool, trace_hap, aln_stride=1024, 
     return st, o
 
 
+def trace_flank_lists(lib, batch, block_start, pool, hap, hap_aln, seed_hap_pos, stutter_size, cap=4096, name="hipstr_trace_flank_lists"):
+    """The complete flank indel / SNP lists of one trace (hipstr_trace_flank_lists, or the reference harness's
+    ref_trace_lists when name says so).  Returns (indels [n][2], snps [n][2])."""
+    bs = np.ascontiguousarray(block_start, np.int32)
+    ind, snp = np.zeros(2 * cap, np.int32), np.zeros(2 * cap, np.int32)
+    ni, ns = C.c_int32(), C.c_int32()
+    f = getattr(lib, name)
+    f.restype = C.c_int32
+    if name == "hipstr_trace_flank_lists":
+        ss = np.ascontiguousarray(stutter_size, np.int32)
+        f.argtypes = [C.POINTER(AlignBatch), c_i32p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, c_i32p, C.c_char_p, C.c_int32,
+                      c_i32p, c_i32p, C.c_int32, c_i32p, c_i32p]
+        st = f(C.byref(batch), ptr(bs, c_i32p), int(pool), int(hap), hap_aln.encode(), int(seed_hap_pos), ptr(ss, c_i32p), None, cap,
+               C.byref(ni), ptr(ind, c_i32p), cap, C.byref(ns), ptr(snp, c_i32p))
+    else:
+        f.argtypes = [C.POINTER(AlignBatch), c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32, c_i32p, c_i32p]
+        st = f(C.byref(batch), ptr(bs, c_i32p), int(pool), int(hap), cap, C.byref(ni), ptr(ind, c_i32p), cap, C.byref(ns), ptr(snp, c_i32p))
+    if st != 0:
+        raise HipstrError(st, name)
+    if ni.value > cap or ns.value > cap:   # too few slots: the counts are the true ones, ask again with room for them
+        return trace_flank_lists(lib, batch, block_start, pool, hap, hap_aln, seed_hap_pos, stutter_size, max(ni.value, ns.value), name)
+    return ind[:2 * ni.value].reshape(-1, 2).copy(), snp[:2 * ns.value].reshape(-1, 2).copy()
+
+
 EXTRACT_ARGTYPES = [C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_u8p, c_f64p, c_f64p, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p,
                     c_f64p, c_f64p, c_f64p, c_f64p, c_i32p]
 
@@ -622,6 +646,8 @@ def load():
     lib.hipstr_vcf_writer_add_record.argtypes = [vp, C.c_char_p, C.c_int32, C.c_char_p]
     lib.hipstr_vcf_writer_close.restype = None
     lib.hipstr_vcf_writer_close.argtypes = [vp]
+    lib.hipstr_vcf_writer_finish.restype = C.c_int32
+    lib.hipstr_vcf_writer_finish.argtypes = [vp]
     lib.hipstr_stitch_trace.restype = C.c_int32
     lib.hipstr_stitch_trace.argtypes = [C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, c_i32p, c_i32p,
                                         C.c_int32, C.c_char_p, c_i32p, c_i32p, C.c_int32, C.c_char_p]

@@ -145,7 +145,7 @@ void HaplotypeGenerator::gen_candidate_seqs(const std::string& ref_seq, int idea
   trim(ideal_min_length, region_start, region_end, sequences);
 }
 
-bool HaplotypeGenerator::add_haplotype_block(int32_t reg_start, int32_t reg_stop, int32_t period, const std::string& chrom_seq,
+bool HaplotypeGenerator::add_haplotype_block(int32_t reg_start, int32_t reg_stop, int32_t period, std::string_view chrom_seq,
                                              const std::vector<std::vector<ReadView> >& alignments, const double* stutter) {
   if (reg_start < kRefFlankLen + kLeftPad || reg_stop + kRefFlankLen + kRightPad > (int64_t)chrom_seq.size()) {
     failure_msg_ = "Haplotype blocks are too near to the chromosome ends";
@@ -155,7 +155,7 @@ bool HaplotypeGenerator::add_haplotype_block(int32_t reg_start, int32_t reg_stop
   for (const auto& sample : alignments)
     for (const ReadView& a : sample) { min_start = std::min(min_start, a.start); max_stop = std::max(max_stop, a.stop); }
   int32_t region_start = reg_start - kLeftPad, region_end = reg_stop + kRightPad;
-  const std::string ref_seq = upper(chrom_seq.substr(region_start, region_end - region_start));
+  const std::string ref_seq = upper(std::string(chrom_seq.substr(region_start, region_end - region_start)));
   // With no alignment at all (every read of the locus failed the haplotype-generation filters) the reference's bounds stay
   // INT_MAX / INT_MIN and its "+ 5" / "- 5" wrap around, so the test passes and the block is built from the reference
   // allele alone; the wrap-around is reproduced here with unsigned arithmetic.
@@ -180,7 +180,7 @@ bool HaplotypeGenerator::add_haplotype_block(int32_t reg_start, int32_t reg_stop
   return true;
 }
 
-bool HaplotypeGenerator::add_vcf_haplotype_block(int32_t pos, int32_t period, const std::string& chrom_seq,
+bool HaplotypeGenerator::add_vcf_haplotype_block(int32_t pos, int32_t period, std::string_view chrom_seq,
                                                  const std::vector<std::string>& vcf_alleles, const double* stutter) {
   if (vcf_alleles.empty()) { failure_msg_ = "no alleles in the reference VCF record"; return false; }
   const int32_t region_start = pos, region_end = pos + (int32_t)vcf_alleles[0].size();
@@ -188,7 +188,7 @@ bool HaplotypeGenerator::add_vcf_haplotype_block(int32_t pos, int32_t period, co
     failure_msg_ = "Haplotype blocks are too near to the chromosome ends";
     return false;
   }
-  if (upper(vcf_alleles[0]) != upper(chrom_seq.substr(region_start, region_end - region_start))) {
+  if (upper(vcf_alleles[0]) != upper(std::string(chrom_seq.substr(region_start, region_end - region_start)))) {
     failure_msg_ = "the reference allele of the VCF record does not match the chromosome sequence";   // an assert in the reference
     return false;
   }
@@ -206,7 +206,7 @@ bool HaplotypeGenerator::add_vcf_haplotype_block(int32_t pos, int32_t period, co
   return true;
 }
 
-bool HaplotypeGenerator::fuse_haplotype_blocks(const std::string& chrom_seq) {
+bool HaplotypeGenerator::fuse_haplotype_blocks(std::string_view chrom_seq) {
   if (hap_blocks_.empty()) { failure_msg_ = "no haplotype blocks were added"; return false; }
   // flanks of at most kRefFlankLen bp, at least 10 bp, no longer than the reads reach
   const int32_t min_start = std::min(hap_blocks_.front().start - 10, std::max(hap_blocks_.front().start - kRefFlankLen, min_aln_start_));
@@ -217,7 +217,7 @@ bool HaplotypeGenerator::fuse_haplotype_blocks(const std::string& chrom_seq) {
     HapBlock b;
     b.start = from;
     b.end = to;
-    b.seqs.push_back(upper(chrom_seq.substr(from, to - from)));
+    b.seqs.push_back(upper(std::string(chrom_seq.substr(from, to - from))));
     return b;
   };
   for (const HapBlock& b : hap_blocks_) {

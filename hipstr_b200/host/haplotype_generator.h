@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <string_view>
 #include <vector>
 
 #include "seq_stutter_genotyper.h"
@@ -31,12 +32,12 @@ class HaplotypeGenerator {
  public:
   HaplotypeGenerator(int32_t min_aln_start, int32_t max_aln_stop) : min_aln_start_(min_aln_start), max_aln_stop_(max_aln_stop) {}
   /* add_haplotype_block (HaplotypeGenerator.cpp:274-329); reads grouped by sample */
-  bool add_haplotype_block(int32_t region_start, int32_t region_stop, int32_t period, const std::string& chrom_seq,
+  bool add_haplotype_block(int32_t region_start, int32_t region_stop, int32_t period, std::string_view chrom_seq,
                            const std::vector<std::vector<ReadView> >& alignments, const double* stutter);
   /* add_vcf_haplotype_block (:256-284): the alleles come from a reference panel instead of the reads */
-  bool add_vcf_haplotype_block(int32_t pos, int32_t period, const std::string& chrom_seq, const std::vector<std::string>& vcf_alleles,
+  bool add_vcf_haplotype_block(int32_t pos, int32_t period, std::string_view chrom_seq, const std::vector<std::string>& vcf_alleles,
                                const double* stutter);
-  bool fuse_haplotype_blocks(const std::string& chrom_seq);   /* :331-366 */
+  bool fuse_haplotype_blocks(std::string_view chrom_seq);   /* :331-366 */
   const std::string& failure_msg() const { return failure_msg_; }
   const std::vector<HapBlock>& get_haplotype_blocks() const { return hap_blocks_; }
 

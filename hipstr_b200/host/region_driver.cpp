@@ -147,7 +147,12 @@ hipstr_status_t hipstr_process_regions(hipstr_ctx_t* ctx, int32_t n_files, const
   };
   std::map<std::string, int> chrom_index;
   std::vector<std::string> seqs(n_chroms);
-  for (int c = 0; c < n_chroms; c++) { chrom_index[chrom_names[c]] = c; seqs[c] = chrom_seqs[c]; }
+  for (int c = 0; c < n_chroms; c++) chrom_index[chrom_names[c]] = c;
+  // only the chromosomes this window's regions name are materialised (a caller passes the whole genome on every window)
+  for (int i = 0; i < n_regions; i++) {
+    auto ci = chrom_index.find(region_chrom[i]);
+    if (ci != chrom_index.end() && seqs[ci->second].empty() && chrom_seqs[ci->second]) seqs[ci->second] = chrom_seqs[ci->second];
+  }
 
   // ---- per region, on all host threads: region query, read filters, mate pairing, PCR duplicates -----------------
   std::vector<std::unique_ptr<Locus> > slots(n_regions);

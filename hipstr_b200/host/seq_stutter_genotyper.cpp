@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstring>
 #include <set>
+#include <unordered_map>
 #include <unordered_set>
 #include <atomic>
 #include <cstdlib>
@@ -474,7 +475,10 @@ int SeqStutterGenotyper::assemble_flanks() {
   std::vector<int> first_read(num_samples_ + 1, num_reads_);
   for (int r = num_reads_ - 1; r >= 0; r--) first_read[sample_label_[r]] = r;
   for (int s = num_samples_ - 1; s >= 0; s--) first_read[s] = std::min(first_read[s], first_read[s + 1]);
-
+  // the trace of every read against its best haplotype, looked up once for both flanks
+  std::vector<const AlignmentTrace*> read_trace(num_reads_, nullptr);
+  for (int r = 0; r < num_reads_; r++)
+    if (seed_positions_[r] >= 0) read_trace[r] = &trace_cache_.at(std::make_pair(pool_index_[r], best_hap_of_read(r)));
   for (int flank = 0; flank < 2; flank++) {
     const int block_index = flank == 0 ? 0 : (int)hap_blocks_.size() - 1;
     const std::string& ref_seq = hap_blocks_[block_index].seqs[0];
@@ -483,48 +487,71 @@ int SeqStutterGenotyper::assemble_flanks() {
     int kmer_length;
     if (!FlankAssembler::calc_kmer_length(ref_seq, kMinKmer, max_k, kmer_length)) return -1;
 
+    // Per DISTINCT flank sequence of the locus (the same few strings come back in every sample): is it a substring of the
+    // reference flank, and which of its (k+1)-mers at k = kmer_length are not reference edges.  Every read is looked up
+    // once; the per-sample work below only touches these records.
+    struct FlankInfo {
+      const std::string* seq = nullptr;
+      bool in_reference = false;
+      std::vector<std::string_view> nonref_edges;
+      int stamp = -1, count = 0;   // sample that saw it last, reads of that sample carrying it
+    };
+    std::unordered_map<std::string_view, FlankInfo> flank_info;
+    std::vector<FlankInfo*> read_info(num_reads_, nullptr);
+    for (int r = 0; r < num_reads_; r++) {
+      if (!read_trace[r]) continue;
+      const std::string& seq = read_trace[r]->flank_seq[block_index];
+      if (seq.empty()) continue;
+      const std::string_view sv(seq);
+      auto it = flank_info.find(sv);
+      if (it == flank_info.end()) {
+        FlankInfo fi;
+        fi.seq = &seq;
+        fi.in_reference = ref_seq.find(sv) != std::string::npos;
+        if (!fi.in_reference)
+          for (size_t c = 0; c + kmer_length + 1 <= sv.size(); c++) {
+            const std::string_view e = sv.substr(c, kmer_length + 1);
+            if (ref_seq.find(e) == std::string::npos) fi.nonref_edges.push_back(e);
+          }
+        it = flank_info.emplace(sv, std::move(fi)).first;
+      }
+      read_info[r] = &it->second;
+    }
     std::map<std::string, int> haplotype_indexes;           // alternate flank -> index
     std::vector<std::vector<int> > haplotype_to_sample;     // samples supporting each alternate flank
     std::vector<std::pair<std::string, int> > assembly_data;
+    std::vector<FlankInfo*> flank_seqs;                     // the sample's distinct flank sequences in read order
+    std::vector<std::pair<std::string_view, int> > edges;
     for (int s = 0; s < num_samples_; s++) {
       if (!call_sample_[s].empty()) continue;
       assembly_data.clear();
       bool acyclic = false;
       // the sample's flank sequences in read order, identical ones counted once (same graph, fewer k-mer walks)
-      std::vector<std::pair<const std::string*, int> > flank_seqs;
+      flank_seqs.clear();
+      bool only_reference = true;
       for (int r = first_read[s]; r < first_read[s + 1]; r++) {
-        if (seed_positions_[r] < 0) continue;
-        const std::string& seq = trace_cache_.at(std::make_pair(pool_index_[r], best_hap_of_read(r))).flank_seq[block_index];
-        if (seq.empty()) continue;
-        bool seen = false;
-        for (auto& f : flank_seqs)
-          if (*f.first == seq) { f.second++; seen = true; break; }
-        if (!seen) flank_seqs.emplace_back(&seq, 1);
+        FlankInfo* fi = read_info[r];
+        if (!fi) continue;
+        if (fi->stamp != s) { fi->stamp = s; fi->count = 0; flank_seqs.push_back(fi); only_reference &= fi->in_reference; }
+        fi->count++;
       }
       // Reads that only repeat (part of) the reference flank add weight to reference edges and nothing else: the graph
       // is the reference path, acyclic at kmer_length by construction, with exactly one source-to-sink path -- the
       // outcome "no alternate flank" is known without building it.
-      bool only_reference = true;
-      for (const auto& f : flank_seqs)
-        if (ref_seq.find(*f.first) == std::string::npos) { only_reference = false; break; }
       if (only_reference) continue;
       {
         // Same outcome, one step further: an edge of the graph is a (k+1)-mer; edges of the reference are never pruned
         // and every other edge is pruned below weight max(2, ceil(0.02 * strings)) (prune_edges, debruijn_graph.cpp:47-60).
         // If no non-reference (k+1)-mer of the sample's reads reaches that weight at k = kmer_length, pruning leaves the
         // bare reference path -- acyclic at that k, one source-to-sink path -- and the loop below would stop at its
-        // first k with nothing to report.  Checking that needs a sort of a few hundred substrings, not a graph.
+        // first k with nothing to report.  Checking that needs a sort of a few substrings, not a graph.
         const int k = kmer_length;
         int num_strings = 1;
-        std::vector<std::pair<std::string_view, int> > edges;
-        for (const auto& f : flank_seqs) {
-          if ((int)f.first->size() <= k) continue;
-          num_strings += f.second;
-          const std::string_view sv(*f.first);
-          for (size_t i = 0; i + k + 1 <= sv.size(); i++) {
-            const std::string_view e = sv.substr(i, k + 1);
-            if (ref_seq.find(e) == std::string::npos) edges.emplace_back(e, f.second);
-          }
+        edges.clear();
+        for (const FlankInfo* fi : flank_seqs) {
+          if ((int)fi->seq->size() <= k) continue;
+          num_strings += fi->count;
+          for (const std::string_view& e : fi->nonref_edges) edges.emplace_back(e, fi->count);
         }
         const int min_weight = std::max(2, (int)std::ceil(0.02 * num_strings));
         std::sort(edges.begin(), edges.end());
@@ -540,7 +567,7 @@ int SeqStutterGenotyper::assemble_flanks() {
       }
       for (int k = kmer_length; k <= max_k; k++) {
         FlankAssembler assembler(k, ref_seq);
-        for (const auto& f : flank_seqs) assembler.add_string(*f.first, 1, f.second);
+        for (const FlankInfo* fi : flank_seqs) assembler.add_string(*fi->seq, 1, fi->count);
         assembler.prune_edges(0.02, 2);
         if (!assembler.has_cycles() && assembler.is_source_ok() && assembler.is_sink_ok()) {
           acyclic = true;
@@ -805,6 +832,18 @@ hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_
   std::vector<hipstr_status_t> status(n_loci, HIPSTR_OK);
   std::vector<std::string> errors(n_loci);
   host_tables();
+  // Loci of one chromosome share its sequence: the length is measured once per distinct pointer and the sequence is used
+  // in place (a copy per locus would move the whole chromosome -- hundreds of MB -- for every locus).
+  std::vector<size_t> chrom_len(n_loci, 0);
+  {
+    std::unordered_map<const char*, size_t> seen;
+    for (int l = 0; l < n_loci; l++) {
+      if (!chrom_seq[l]) { err = "null chromosome sequence"; return HIPSTR_ERR_BAD_ARG; }
+      auto it = seen.find(chrom_seq[l]);
+      if (it == seen.end()) it = seen.emplace(chrom_seq[l], std::strlen(chrom_seq[l])).first;
+      chrom_len[l] = it->second;
+    }
+  }
   parallel_for(n_loci, [&](size_t li) {
     const int l = (int)li;
     SeqStutterGenotyper& g = loci[base + li];
@@ -831,7 +870,7 @@ hipstr_status_t GenotyperBatch::add_loci_from_reads(int32_t n_loci, const int32_
       if (!rd->use_for_haps || rd->use_for_haps[r]) by_sample[rd->sample_label[r]].push_back(v);
     }
     g.log_ += "Generating candidate haplotypes\n";
-    const std::string chrom(chrom_seq[l]);
+    const std::string_view chrom(chrom_seq[l], chrom_len[li]);
     HaplotypeGenerator generator(min_start, max_stop);
     bool added;
     if (allele_pos) {   // ref_vcf != NULL (seq_stutter_genotyper.cpp:445-459): the alleles of the reference panel's record
@@ -1153,10 +1192,23 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
         const std::string span = span_len.p[i * 8 + b] > 0 ? read.substr(span_start.p[i * 8 + b], span_len.p[i * 8 + b]) : std::string();
         (g.hap_blocks_[b].period > 0 ? t.str_seq : t.flank_seq)[b] = span;
       }
-      for (int k = 0; k < n_indels.p[i]; k++)
-        t.flank_indel_data.emplace_back(indels.p[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2], indels.p[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2 + 1]);
-      for (int k = 0; k < n_snps.p[i]; k++)
-        t.flank_snp_data.emplace_back(snps.p[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2], (char)snps.p[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2 + 1]);
+      if (n_indels.p[i] > HIPSTR_MAX_TRACE_INDELS || n_snps.p[i] > HIPSTR_MAX_TRACE_SNPS) {
+        // more flank indels / SNPs than the fixed slots of the device call hold (a chimeric or mismapped read): the counts
+        // are the true ones, the complete lists are rebuilt on the host from the trace's operation string
+        std::vector<int32_t> all_indels(2 * (size_t)std::max(n_indels.p[i], 1)), all_snps(2 * (size_t)std::max(n_snps.p[i], 1));
+        int32_t ni = 0, ns = 0;
+        const hipstr_status_t st3 = hipstr_trace_flank_lists(&bt, pb.block_start.data(), trace_pool[i], trace_hap[i], t.hap_aln.c_str(),
+                                                             seed_hap_pos.p[i], stutter.p + i * 8, nullptr, n_indels.p[i], &ni,
+                                                             all_indels.data(), n_snps.p[i], &ns, all_snps.data());
+        if (st3 != HIPSTR_OK || ni != n_indels.p[i] || ns != n_snps.p[i]) { failed = 1; return; }
+        for (int k = 0; k < ni; k++) t.flank_indel_data.emplace_back(all_indels[2 * (size_t)k], all_indels[2 * (size_t)k + 1]);
+        for (int k = 0; k < ns; k++) t.flank_snp_data.emplace_back(all_snps[2 * (size_t)k], (char)all_snps[2 * (size_t)k + 1]);
+      } else {
+        for (int k = 0; k < n_indels.p[i]; k++)
+          t.flank_indel_data.emplace_back(indels.p[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2], indels.p[(i * HIPSTR_MAX_TRACE_INDELS + k) * 2 + 1]);
+        for (int k = 0; k < n_snps.p[i]; k++)
+          t.flank_snp_data.emplace_back(snps.p[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2], (char)snps.p[(i * HIPSTR_MAX_TRACE_SNPS + k) * 2 + 1]);
+      }
       // only the span against the reference is needed by the loop and the VCF record; the CIGAR / gapped string of the
       // traced alignment (used by the reference's HTML visualisation) are built on request (keep_traced_alignments)
       int32_t n_cigar = 0;

@@ -29,7 +29,7 @@ namespace {
 struct Site {
   int32_t pos;        // 1-based POS
   char ref, alt;
-  uint32_t calls;     // offset of this site's per-sample codes
+  size_t calls;       // offset of this site's per-sample codes (sites x samples exceeds 32 bits on large panels)
 };
 struct Chrom {
   std::vector<Site> sites;          // in file order; sorted by position on first use
@@ -37,35 +37,100 @@ struct Chrom {
   bool sorted = false;
 };
 
-bool read_whole_file(const std::string& path, std::string& out, std::string& err) {
-  FILE* f = fopen(path.c_str(), "rb");
-  if (!f) { err = "Failed to open the VCF file " + path; return false; }
-  std::string raw;
-  char buf[1 << 16];
-  size_t n;
-  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) raw.append(buf, n);
-  fclose(f);
-  if (raw.size() < 2 || (unsigned char)raw[0] != 31 || (unsigned char)raw[1] != 139) { out.swap(raw); return true; }
-  // BGZF = concatenated gzip members
-  z_stream zs;
-  std::memset(&zs, 0, sizeof(zs));
-  if (inflateInit2(&zs, 15 + 16) != Z_OK) { err = "zlib initialisation failed"; return false; }
-  zs.next_in = (Bytef*)raw.data();
-  zs.avail_in = (uInt)raw.size();
-  std::vector<char> chunk(1 << 20);
-  while (zs.avail_in > 0) {
-    zs.next_out = (Bytef*)chunk.data();
-    zs.avail_out = (uInt)chunk.size();
-    const int rc = inflate(&zs, Z_NO_FLUSH);
-    out.append(chunk.data(), chunk.size() - zs.avail_out);
-    if (rc == Z_STREAM_END) {
-      if (zs.avail_in == 0) break;
-      if (inflateReset(&zs) != Z_OK) { inflateEnd(&zs); err = "corrupt BGZF stream in " + path; return false; }
-    } else if (rc != Z_OK) { inflateEnd(&zs); err = "corrupt BGZF stream in " + path; return false; }
+/* Streams a plain or BGZF / gzip text file line by line: the file is read and inflated in bounded chunks (1 MiB of
+ * compressed input, 4 MiB of text at a time), so memory stays proportional to the PARSED data, a file of any size works
+ * (zlib's 32-bit avail_in is fed in pieces), and a stream that ends inside a gzip member is an error instead of a
+ * silently shorter file. */
+class LineStream {
+ public:
+  LineStream(const std::string& path, std::string& err) : err_(err), in_(1 << 20), out_(4 << 20) {
+    f_ = fopen(path.c_str(), "rb");
+    if (!f_) { err_ = "Failed to open the VCF file " + path; failed_ = true; return; }
+    path_ = path;
+    const size_t n = fread(in_.data(), 1, in_.size(), f_);
+    in_len_ = n;
+    gz_ = n >= 2 && (unsigned char)in_[0] == 31 && (unsigned char)in_[1] == 139;
+    if (gz_) {
+      std::memset(&zs_, 0, sizeof(zs_));
+      if (inflateInit2(&zs_, 15 + 16) != Z_OK) { err_ = "zlib initialisation failed"; failed_ = true; return; }
+      zs_.next_in = (Bytef*)in_.data();
+      zs_.avail_in = (uInt)in_len_;
+      z_open_ = true;
+    }
   }
-  inflateEnd(&zs);
-  return true;
-}
+  ~LineStream() {
+    if (z_open_) inflateEnd(&zs_);
+    if (f_) fclose(f_);
+  }
+  bool failed() const { return failed_; }
+  /* next line without its terminator; false at the end of the file or on error (check failed()) */
+  bool next(const char*& line, size_t& len) {
+    for (;;) {
+      const char* base = text_.data() + text_at_;
+      const char* nl = (const char*)std::memchr(base, '\n', text_.size() - text_at_);
+      if (nl) {
+        line = base;
+        len = (size_t)(nl - base);
+        text_at_ += len + 1;
+        if (len && line[len - 1] == '\r') len--;
+        return true;
+      }
+      if (eof_) {
+        if (text_at_ < text_.size()) {   // last line without a newline
+          line = base;
+          len = text_.size() - text_at_;
+          text_at_ = text_.size();
+          if (len && line[len - 1] == '\r') len--;
+          return true;
+        }
+        return false;
+      }
+      text_.erase(0, text_at_);   // keep the partial line, fetch more
+      text_at_ = 0;
+      if (!fill()) return false;
+    }
+  }
+
+ private:
+  bool fill() {
+    if (!gz_) {
+      if (in_len_ == 0) { eof_ = true; return true; }
+      text_.append(in_.data(), in_len_);
+      in_len_ = fread(in_.data(), 1, in_.size(), f_);
+      if (in_len_ == 0) eof_ = true;
+      return true;
+    }
+    // BGZF = concatenated gzip members
+    for (;;) {
+      if (zs_.avail_in == 0) {
+        const size_t n = fread(in_.data(), 1, in_.size(), f_);
+        if (n == 0) {
+          if (mid_member_) { err_ = "truncated BGZF stream in " + path_; failed_ = true; return false; }
+          eof_ = true;
+          return true;
+        }
+        zs_.next_in = (Bytef*)in_.data();
+        zs_.avail_in = (uInt)n;
+      }
+      zs_.next_out = (Bytef*)out_.data();
+      zs_.avail_out = (uInt)out_.size();
+      const int rc = inflate(&zs_, Z_NO_FLUSH);
+      const size_t got = out_.size() - zs_.avail_out;
+      if (rc != Z_OK && rc != Z_STREAM_END && rc != Z_BUF_ERROR) { err_ = "corrupt BGZF stream in " + path_; failed_ = true; return false; }
+      mid_member_ = rc != Z_STREAM_END;
+      if (rc == Z_STREAM_END && inflateReset(&zs_) != Z_OK) { err_ = "corrupt BGZF stream in " + path_; failed_ = true; return false; }
+      if (got) { text_.append(out_.data(), got); return true; }
+      if (rc == Z_BUF_ERROR && zs_.avail_in != 0) { err_ = "corrupt BGZF stream in " + path_; failed_ = true; return false; }
+    }
+  }
+  std::string& err_;
+  std::string path_, text_;
+  size_t text_at_ = 0, in_len_ = 0;
+  std::vector<char> in_, out_;
+  FILE* f_ = nullptr;
+  z_stream zs_;
+  bool gz_ = false, z_open_ = false, eof_ = false, failed_ = false, mid_member_ = false;
+};
 
 }  // namespace
 
@@ -82,17 +147,11 @@ struct hipstr_snp_vcf {
 namespace {
 thread_local std::string g_vcf_error;
 
-bool parse(const std::string& text, hipstr_snp_vcf& v, std::string& err) {
-  size_t at = 0;
+bool parse(LineStream& in, hipstr_snp_vcf& v, std::string& err) {
   bool have_header = false;
-  std::vector<const char*> field;
-  while (at < text.size()) {
-    size_t eol = text.find('\n', at);
-    if (eol == std::string::npos) eol = text.size();
-    size_t len = eol - at;
-    if (len && text[at + len - 1] == '\r') len--;
-    const char* line = text.data() + at;
-    at = eol + 1;
+  const char* line;
+  size_t len;
+  while (in.next(line, len)) {
     if (len == 0) continue;
     if (line[0] == '#') {
       if (len > 6 && std::memcmp(line, "#CHROM", 6) == 0) {
@@ -139,7 +198,7 @@ bool parse(const std::string& text, hipstr_snp_vcf& v, std::string& err) {
     site.pos = (int32_t)std::strtol(col[1], nullptr, 10);
     site.ref = col[3][0];
     site.alt = col[4][0];
-    site.calls = (uint32_t)c.codes.size();
+    site.calls = c.codes.size();
     c.codes.resize(c.codes.size() + v.samples.size(), 0);
     const char* q = col[9];
     for (size_t s = 0; s < v.samples.size() && q <= end; s++) {
@@ -161,6 +220,7 @@ bool parse(const std::string& text, hipstr_snp_vcf& v, std::string& err) {
     c.sites.push_back(site);
     c.sorted = false;
   }
+  if (in.failed()) return false;
   if (!have_header) { err = "Provided VCF file is improperly formatted"; return false; }
   return true;
 }
@@ -172,10 +232,10 @@ const char* hipstr_snp_vcf_last_error(void) { return g_vcf_error.c_str(); }
 
 hipstr_status_t hipstr_snp_vcf_open(const char* path, hipstr_snp_vcf_t** out) {
   if (!path || !out) return HIPSTR_ERR_BAD_ARG;
-  std::string text;
-  if (!read_whole_file(path, text, g_vcf_error)) return HIPSTR_ERR_BAD_ARG;
+  LineStream in(path, g_vcf_error);
+  if (in.failed()) return HIPSTR_ERR_BAD_ARG;
   std::unique_ptr<hipstr_snp_vcf> v(new hipstr_snp_vcf());
-  if (!parse(text, *v, g_vcf_error)) return HIPSTR_ERR_BAD_ARG;
+  if (!parse(in, *v, g_vcf_error)) return HIPSTR_ERR_BAD_ARG;
   for (const std::string& s : v->samples) { v->sample_text += s; v->sample_text += '\n'; }
   *out = v.release();
   return HIPSTR_OK;
@@ -265,12 +325,13 @@ extern "C" {
 
 hipstr_status_t hipstr_str_vcf_open(const char* path, hipstr_str_vcf_t** out) {
   if (!path || !out) return HIPSTR_ERR_BAD_ARG;
-  std::string text;
-  if (!read_whole_file(path, text, g_vcf_error)) return HIPSTR_ERR_BAD_ARG;
+  LineStream in(path, g_vcf_error);
+  if (in.failed()) return HIPSTR_ERR_BAD_ARG;
   std::unique_ptr<hipstr_str_vcf> v(new hipstr_str_vcf());
-  std::stringstream ss(text);
-  std::string line;
-  while (std::getline(ss, line)) {
+  const char* raw;
+  size_t raw_len;
+  while (in.next(raw, raw_len)) {
+    const std::string line(raw, raw_len);
     if (line.empty() || line[0] == '#') continue;
     std::vector<std::string> f;
     size_t at = 0;
@@ -294,6 +355,7 @@ hipstr_status_t hipstr_str_vcf_open(const char* path, hipstr_str_vcf_t** out) {
     r.has_span = has_start && has_end;
     v->chroms[f[0]].push_back(r);
   }
+  if (in.failed()) return HIPSTR_ERR_BAD_ARG;
   *out = v.release();
   return HIPSTR_OK;
 }

@@ -15,7 +15,7 @@ const unsigned char kBgzfEof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff,
                                     0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 }
 
-VCFWriter::VCFWriter() : fp_(nullptr), open_(false), bgzf_(false), max_record_pad_(50) {}
+VCFWriter::VCFWriter() : fp_(nullptr), open_(false), bgzf_(false), io_ok_(true), max_record_pad_(50) {}
 VCFWriter::~VCFWriter() { close(); }
 
 bool VCFWriter::open(const std::string& vcf_file) {
@@ -24,6 +24,7 @@ bool VCFWriter::open(const std::string& vcf_file) {
   if (!fp_) return false;
   bgzf_ = vcf_file.size() >= 3 && vcf_file.compare(vcf_file.size() - 3, 3, ".gz") == 0;
   open_ = true;
+  io_ok_ = true;
   chrom_.clear();
   return true;
 }
@@ -33,13 +34,13 @@ void VCFWriter::flush_block() {
   // one gzip member: header with the BC subfield, raw deflate payload, CRC32 + ISIZE
   z_stream zs;
   std::memset(&zs, 0, sizeof(zs));
-  deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+  if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { io_ok_ = false; block_.clear(); return; }
   std::vector<unsigned char> out(deflateBound(&zs, block_.size()) + 64);
   zs.next_in = block_.data();
   zs.avail_in = (uInt)block_.size();
   zs.next_out = out.data() + 18;
   zs.avail_out = (uInt)(out.size() - 18);
-  deflate(&zs, Z_FINISH);
+  if (deflate(&zs, Z_FINISH) != Z_STREAM_END) io_ok_ = false;
   const size_t clen = zs.total_out;
   deflateEnd(&zs);
   const unsigned char head[18] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0, 0};
@@ -53,12 +54,12 @@ void VCFWriter::flush_block() {
     out[18 + clen + k] = (unsigned char)(crc >> (8 * k));
     out[18 + clen + 4 + k] = (unsigned char)(isize >> (8 * k));
   }
-  std::fwrite(out.data(), 1, total, fp_);
+  if (std::fwrite(out.data(), 1, total, fp_) != total) io_ok_ = false;   // full disk, closed pipe, ...
   block_.clear();
 }
 
 void VCFWriter::emit(const std::string& s) {
-  if (!bgzf_) { std::fwrite(s.data(), 1, s.size(), fp_); return; }
+  if (!bgzf_) { if (std::fwrite(s.data(), 1, s.size(), fp_) != s.size()) io_ok_ = false; return; }
   size_t at = 0;
   while (at < s.size()) {
     const size_t take = std::min(s.size() - at, kBgzfBlock - block_.size());
@@ -71,7 +72,7 @@ void VCFWriter::emit(const std::string& s) {
 bool VCFWriter::write_header(const std::string& header_text) {
   if (!open_) return false;
   emit(header_text);
-  return true;
+  return io_ok_;
 }
 
 void VCFWriter::write_all_records() {
@@ -106,19 +107,20 @@ bool VCFWriter::add_vcf_record(const std::string& chrom, int32_t record_pos, con
   }
   heap_.push_back(new Record{record_pos, record_text});
   std::push_heap(heap_.begin(), heap_.end(), later);
-  return true;
+  return io_ok_;   // false once any write failed: the file on disk is incomplete
 }
 
-void VCFWriter::close() {
-  if (!open_) return;
+bool VCFWriter::close() {
+  if (!open_) return io_ok_;
   write_all_records();
   if (bgzf_) {
     flush_block();
-    std::fwrite(kBgzfEof, 1, sizeof(kBgzfEof), fp_);
+    if (std::fwrite(kBgzfEof, 1, sizeof(kBgzfEof), fp_) != sizeof(kBgzfEof)) io_ok_ = false;
   }
-  std::fclose(fp_);
+  if (std::fclose(fp_) != 0) io_ok_ = false;   // buffered data that could not be written shows up here
   fp_ = nullptr;
   open_ = false;
+  return io_ok_;
 }
 
 }  // namespace hipstr
@@ -139,10 +141,12 @@ hipstr_status_t hipstr_vcf_writer_add_record(hipstr_vcf_writer_t* w, const char*
   if (!w || !chrom || !text) return HIPSTR_ERR_BAD_ARG;
   return reinterpret_cast<hipstr::VCFWriter*>(w)->add_vcf_record(chrom, pos, text) ? HIPSTR_OK : HIPSTR_ERR_BAD_ARG;
 }
-void hipstr_vcf_writer_close(hipstr_vcf_writer_t* w) {
-  if (!w) return;
+void hipstr_vcf_writer_close(hipstr_vcf_writer_t* w) { hipstr_vcf_writer_finish(w); }
+hipstr_status_t hipstr_vcf_writer_finish(hipstr_vcf_writer_t* w) {
+  if (!w) return HIPSTR_ERR_BAD_ARG;
   hipstr::VCFWriter* p = reinterpret_cast<hipstr::VCFWriter*>(w);
-  p->close();
+  const bool ok = p->close();
   delete p;
+  return ok ? HIPSTR_OK : HIPSTR_ERR_BAD_ARG;
 }
 }

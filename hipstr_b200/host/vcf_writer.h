@@ -28,8 +28,8 @@ class VCFWriter {
   bool is_open() const { return open_; }
   bool open(const std::string& vcf_file);                 // false if the file cannot be created
   bool write_header(const std::string& header_text);      // false if not open
-  bool add_vcf_record(const std::string& chrom, int32_t record_pos, const std::string& record_text);
-  void close();
+  bool add_vcf_record(const std::string& chrom, int32_t record_pos, const std::string& record_text);   // false once a write failed
+  bool close();                                           // false if any write, the compression or fclose failed
 
  private:
   struct Record { int32_t pos; std::string text; };
@@ -39,7 +39,7 @@ class VCFWriter {
   void flush_block();
 
   std::FILE* fp_;
-  bool open_, bgzf_;
+  bool open_, bgzf_, io_ok_;
   std::string chrom_;
   std::vector<Record*> heap_;
   std::vector<unsigned char> block_;     // uncompressed bytes waiting for the next BGZF block

@@ -310,16 +310,32 @@ typedef struct hipstr_trace_out {
   int32_t* span_len;      /* [n_traces][8] per block: its length (0 = empty)                       */
   int32_t* flank_ins;     /* [n_traces] flank_ins_size()                                           */
   int32_t* flank_del;     /* [n_traces] flank_del_size()                                           */
-  int32_t* n_indels;      /* [n_traces] entries of flank_indel_data(), in the reference's order    */
-  int32_t* indels;        /* [n_traces][16][2] (position, size)                                    */
-  int32_t* n_snps;        /* [n_traces] entries of flank_snp_data()                                */
-  int32_t* snps;          /* [n_traces][32][2] (position, read base character)                     */
+  int32_t* n_indels;      /* [n_traces] entries of flank_indel_data(), in the reference's order: the TRUE count */
+  int32_t* indels;        /* [n_traces][16][2] (position, size): the first min(n_indels, 16) entries; a trace
+                             with more gets its full lists from hipstr_trace_flank_lists                       */
+  int32_t* n_snps;        /* [n_traces] entries of flank_snp_data(): the TRUE count                */
+  int32_t* snps;          /* [n_traces][32][2] (position, read base character): the first min(n_snps, 32)      */
 } hipstr_trace_out_t;
 
 hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_batch_t* batch,
                                         const int32_t* block_start, int32_t n_traces,
                                         const int32_t* trace_pool, const int32_t* trace_hap,
                                         const hipstr_trace_out_t* out);
+
+/* The COMPLETE flank indel / flank SNP lists of one trace (AlignmentTrace::flank_indel_data / flank_snp_data,
+ * SeqAlignment/AlignmentTraceback.h:29-33).  hipstr_trace_batch_host returns these lists in fixed-size slots
+ * (HIPSTR_MAX_TRACE_INDELS / HIPSTR_MAX_TRACE_SNPS entries per trace) next to the TRUE counts n_indels / n_snps; when
+ * a count exceeds its slot -- a chimeric or mismapped read -- only the first entries were stored, and the caller gets the
+ * whole lists here, rebuilt on the host from the trace's operation string (the accounting half of HapAligner::retrace,
+ * HapAligner.cpp:363-571, driven by the operations K5 chose), identical to the reference's.
+ *   batch / block_start / pool / hap   as passed to hipstr_trace_batch_host (hap local to the pool's locus)
+ *   hap_aln, seed_hap_pos, stutter_size [8]   that trace's outputs
+ *   own_quals   NULL = the pool's qualities; else the qualities the trace was computed with (a read traced with its own)
+ *   indels [cap_indels][2] (position, size), snps [cap_snps][2] (position, base character); *n_* = the true counts */
+hipstr_status_t hipstr_trace_flank_lists(const hipstr_align_batch_t* batch, const int32_t* block_start, int32_t pool, int32_t hap,
+                                         const char* hap_aln, int32_t seed_hap_pos, const int32_t* stutter_size,
+                                         const char* own_quals, int32_t cap_indels, int32_t* n_indels, int32_t* indels,
+                                         int32_t cap_snps, int32_t* n_snps, int32_t* snps);
 
 /* --- a16 (host part): trace -> alignment against the reference genome ---------
  * Replaces stitch_alignment_trace + stitch (SeqAlignment/AlignmentTraceback.cpp:5-144), the
@@ -654,6 +670,9 @@ hipstr_status_t hipstr_vcf_writer_header(hipstr_vcf_writer_t* w, const char* hea
 hipstr_status_t hipstr_vcf_writer_add_record(hipstr_vcf_writer_t* w, const char* chrom, int32_t pos,
                                              const char* record_text);
 void            hipstr_vcf_writer_close(hipstr_vcf_writer_t* w);   /* flushes, writes the BGZF EOF block, frees */
+/* the same with the outcome: HIPSTR_ERR_BAD_ARG if any write, the compression or the final fclose failed (full disk,
+ * closed pipe) -- the file on disk is then incomplete; _header / _add_record report a failed write the same way */
+hipstr_status_t hipstr_vcf_writer_finish(hipstr_vcf_writer_t* w);
 
 /* --- section 8(f) row 4, first slice: SNP phasing log-likelihoods (K7) ----------
  * Replaces calc_het_snp_factors (src/snp_phasing_quality.cpp:92-120) -> add_log_phasing_probs (:65-90) ->

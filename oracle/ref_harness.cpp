@@ -282,6 +282,38 @@ int32_t ref_trace_batch(const hipstr_align_batch_t* bt, const int32_t* block_sta
   return HIPSTR_OK;
 }
 
+// The COMPLETE flank_indel_data() / flank_snp_data() vectors of one trace (the batch entry above truncates them to the
+// fixed slots of hipstr_trace_out_t): checker of hipstr_trace_flank_lists.
+int32_t ref_trace_lists(const hipstr_align_batch_t* bt, const int32_t* block_start, int32_t pool, int32_t hap, int32_t cap_indels,
+                        int32_t* n_indels, int32_t* indels, int32_t cap_snps, int32_t* n_snps, int32_t* snps) {
+  ensure_init();
+  BaseQuality base_quality;
+  int l = 0;
+  while (!(pool >= bt->locus_pool_off[l] && pool < bt->locus_pool_off[l + 1])) l++;
+  const int b0 = bt->locus_block_off[l], nb = bt->locus_block_off[l + 1] - b0;
+  std::vector<int32_t> starts(nb), ends(nb);
+  for (int b = 0; b < nb; b++) {
+    const int o0 = bt->block_opt_off[b0 + b];
+    starts[b] = block_start[b0 + b];
+    ends[b] = starts[b] + (bt->opt_seq_off[o0 + 1] - bt->opt_seq_off[o0]);
+  }
+  RefLocus rl(bt, l, starts.data(), ends.data());
+  std::vector<bool> mask(rl.hap->num_combs(), true);
+  HapAligner aligner(rl.hap, mask);
+  const int s0 = bt->pool_seq_off[pool], s1 = bt->pool_seq_off[pool + 1];
+  Alignment aln(0, 0, false, "READPOOL", std::string(bt->pool_quals + s0, bt->pool_quals + s1),
+                std::string(bt->pool_bases + s0, bt->pool_bases + s1), "");
+  AlignmentTrace* trace = aligner.trace_optimal_aln(aln, bt->pool_seed[pool], hap, &base_quality);
+  const auto& ind = trace->flank_indel_data();
+  const auto& snp = trace->flank_snp_data();
+  *n_indels = (int32_t)ind.size();
+  *n_snps = (int32_t)snp.size();
+  for (int k = 0; k < (int)ind.size() && k < cap_indels; k++) { indels[2 * k] = ind[k].first; indels[2 * k + 1] = ind[k].second; }
+  for (int k = 0; k < (int)snp.size() && k < cap_snps; k++) { snps[2 * k] = snp[k].first; snps[2 * k + 1] = (int)snp[k].second; }
+  delete trace;
+  return HIPSTR_OK;
+}
+
 // The reference's own stitched alignment of a trace (AlignmentTrace::traced_aln) together with the two inputs
 // stitch_alignment_trace gets: hap_aln_to_ref = Haplotype::get_aln_info() of the traced haplotype (computed by the
 // reference's Needleman-Wunsch in the Haplotype constructor) and the read-vs-haplotype string.

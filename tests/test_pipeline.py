@@ -141,6 +141,31 @@ def test_snp_sets_match_create_snp_trees(seed, tmp_path):
 
 
 @needs_ref
+def test_snp_vcf_stream_errors(tmp_path):
+    """The SNP VCF is streamed in bounded chunks: a BGZF file cut inside a block is an error (not a silently shorter panel),
+    a file cut BETWEEN blocks parses, and a plain file without a final newline keeps its last record."""
+    from hipstr_b200.capi import SnpVcf
+    sc = MultiScenario(5, n_regions=2, n_fragments=8)
+    text, gz = write_snp_vcf(sc, tmp_path, 5)
+    raw = open(gz, "rb").read()
+    cut = str(tmp_path / "cut.vcf.gz")
+    with open(cut, "wb") as fh:
+        fh.write(raw[:len(raw) // 2 if len(raw) > 200 else len(raw) - 10])
+    with pytest.raises(Exception):
+        SnpVcf(cut)
+    whole = str(tmp_path / "no_eof_block.vcf.gz")     # the 28-byte BGZF end-of-file block removed: still whole gzip members
+    with open(whole, "wb") as fh:
+        fh.write(raw[:-28])
+    full, part = SnpVcf(gz), SnpVcf(whole)
+    assert part.samples == full.samples
+    bare = str(tmp_path / "bare.vcf")
+    with open(bare, "w") as fh:
+        fh.write(open(text).read().rstrip("\n"))
+    a, b = SnpVcf(text).region_sets("chr1", 1, 100000), SnpVcf(bare).region_sets("chr1", 1, 100000)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[1]) > 0
+
+
+@needs_ref
 @pytest.mark.parametrize("flags", [dict(), dict(gls=1, pls=1, filters=1)])
 def test_vcf_header_matches_reference(flags, tmp_path):
     """hipstr_vcf_header against the header the reference program writes (Genotyper::get_vcf_header through

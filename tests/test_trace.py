@@ -147,3 +147,74 @@ def test_stitch_trace_matches_reference(case):
         assert (start, stop, cigar, aln) == (a.value, b.value, b3.value.decode(), b4.value.decode()), i
         n_checked += 1
     assert n_checked >= 10
+
+
+# ---- complete flank lists (hipstr_trace_flank_lists): fixed-size slots of K5 vs reads with more entries ----------
+def noisy_flank_traces(seed=5):
+    """Reads with dozens of confident flank mismatches and a few flank indels over a 330-bp flank (what a chimeric or
+    mismapped read looks like).  The model lets a read hang off the haplotype ends for free, so the best path clips such a
+    read instead of paying for its mismatches: the fixed slots of K5 (16 indels, 32 SNPs) are not reachable through a
+    maximum-likelihood path on real flank lengths -- the case checks that the lists stay identical to the reference's."""
+    rng = np.random.default_rng(seed)
+    left = "".join("ACGT"[i] for i in rng.integers(0, 4, 330))
+    right = "".join("ACGT"[i] for i in rng.integers(0, 4, 60))
+    blocks = [(0, [left]), (2, ["AC" * 8, "AC" * 9]), (0, [right])]
+    hap = left + "AC" * 8 + right
+    reads = []
+    for k in range(6):
+        rd = list(hap)
+        for i in range(4 + k, 320, 9):
+            rd[i] = "ACGT"[("ACGT".index(rd[i]) + 1 + k % 3) % 4]
+        if k >= 3:                       # and a few flank indels
+            del rd[len(hap) - 20]
+            rd.insert(100, "G")
+        rd = "".join(rd)
+        reads.append((rd, "9" * len(rd), len(rd) - 25))    # seed in the right flank: the left side spans the repeat and the long flank
+    b = BatchBuilder().add_locus(blocks, reads).build()
+    pools = np.arange(len(reads), dtype=np.int32)
+    haps = np.array([0, 1, 0, 1, 0, 1], np.int32)
+    return b, pools, haps
+
+
+@pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libhipstr_ref.so not built")
+@pytest.mark.parametrize("case", ALL[:6] + [("noisy", None)], ids=lambda c: str(c[1]))
+def test_flank_lists_match_reference(case):
+    """hipstr_trace_flank_lists rebuilds the reference's complete flank_indel_data / flank_snp_data from a trace's operation
+    string -- also for reads with more entries than the fixed slots hold."""
+    from hipstr_b200 import capi
+    from hipstr_b200.capi import MAX_TRACE_SNPS, trace_flank_lists
+    if case[0] == "noisy":
+        batch, pools, haps = noisy_flank_traces()
+    else:
+        keep, batch, pools, haps, _ = _load(case)   # `keep` owns the batch's memory
+    bs = block_starts(batch)
+    st, o = trace_batch(_fn(checkers.oracle(), "oracle_trace_batch"), batch, bs, pools, haps, aln_stride=2048)
+    assert st == 0
+    lib = capi.load()
+    for i in range(len(pools)):
+        ind, snp = trace_flank_lists(lib, batch, bs, pools[i], haps[i], o["hap_aln"][i], o["seed_hap_pos"][i], o["stutter_size"][i])
+        rind, rsnp = trace_flank_lists(checkers.ref(), batch, bs, pools[i], haps[i], None, None, None, name="ref_trace_lists")
+        assert np.array_equal(ind, rind) and np.array_equal(snp, rsnp), i
+        assert len(ind) == o["n_indels"][i] and len(snp) == o["n_snps"][i]
+        # a caller with too few slots gets the TRUE counts and the first entries (the contract of the fixed-size K5 outputs)
+        if len(snp) + len(ind) > 0:
+            ind1, snp1 = trace_flank_lists(lib, batch, bs, pools[i], haps[i], o["hap_aln"][i], o["seed_hap_pos"][i], o["stutter_size"][i], cap=1)
+            assert np.array_equal(ind1, ind) and np.array_equal(snp1, snp)
+
+
+@pytest.mark.gpu
+def test_gpu_trace_counts_beyond_slots():
+    """K5 on reads full of flank mismatches: counts, slots and the host rebuild of the complete lists agree."""
+    from hipstr_b200.capi import Context, MAX_TRACE_SNPS, trace_flank_lists
+    batch, pools, haps = noisy_flank_traces()
+    bs = block_starts(batch)
+    st, o = trace_batch(_fn(checkers.oracle(), "oracle_trace_batch"), batch, bs, pools, haps, aln_stride=2048)
+    ctx = Context(0)
+    g = ctx.trace(batch, bs, pools, haps)
+    assert g["hap_aln"] == o["hap_aln"]
+    for k in KEYS:
+        assert np.array_equal(g[k], o[k]), k
+    for i in range(len(pools)):
+        ind, snp = trace_flank_lists(ctx.lib, batch, bs, pools[i], haps[i], g["hap_aln"][i], g["seed_hap_pos"][i], g["stutter_size"][i])
+        assert len(snp) == g["n_snps"][i] and np.array_equal(snp[:MAX_TRACE_SNPS], g["snps"][i][:min(len(snp), MAX_TRACE_SNPS)])
+    ctx.close()

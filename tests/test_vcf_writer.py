@@ -4,6 +4,7 @@ import heapq
 import struct
 
 import numpy as np
+import pytest
 
 from hipstr_b200 import capi
 
@@ -97,3 +98,19 @@ def test_misuse_is_reported_not_fatal(tmp_path):
     lib = capi.load()
     assert not lib.hipstr_vcf_writer_open(str(tmp_path / "no_such_dir" / "x.vcf").encode())
     assert lib.hipstr_vcf_writer_add_record(None, b"chr1", 1, b"x") == 3
+
+
+def test_writer_reports_io_failure():
+    """A write that fails (here: /dev/full, the kernel's always-full device) is reported by the call that hits it or by
+    finish(), instead of leaving a silently truncated file."""
+    import os
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    from hipstr_b200 import capi
+    lib = capi.load()
+    w = lib.hipstr_vcf_writer_open(b"/dev/full")
+    assert w
+    lib.hipstr_vcf_writer_header(w, b"##fileformat=VCFv4.2\n" * 4000)
+    for k in range(2000):
+        lib.hipstr_vcf_writer_add_record(w, b"chr1", 100 + 60 * k, b"chr1\t%d\t.\tA\tC" % (100 + 60 * k))
+    assert lib.hipstr_vcf_writer_finish(w) != 0

@@ -1,4 +1,6 @@
 set -x
 mkdir -p gpurun_out/r2
-python bench.py --steps 5 --warmup 3 > gpurun_out/r2/bench_n1_a.json 2> gpurun_out/r2/bench_n1_a.err; tail -c 600 gpurun_out/r2/bench_n1_a.err
-python bench.py --workload cfg4_em --loci 500 --steps 3 --warmup 3 > gpurun_out/r2/bench_em.json 2> gpurun_out/r2/bench_em.err; tail -c 400 gpurun_out/r2/bench_em.err
+nproc
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r2/bench_n2_a.json 2> gpurun_out/r2/bench_n2_a.err; tail -c 300 gpurun_out/r2/bench_n2_a.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload loop --loci 2000 > gpurun_out/r2/bench_loop_n2.json 2> gpurun_out/r2/bench_loop_n2.err; tail -c 300 gpurun_out/r2/bench_loop_n2.err
+python bench.py --workload loop --loci 2000 > gpurun_out/r2/bench_loop_n1_2000.json 2> gpurun_out/r2/bench_loop_n1_2000.err; tail -c 300 gpurun_out/r2/bench_loop_n1_2000.err
