@@ -96,3 +96,33 @@ def test_properties_at_scale():
     truth = np.sort(np.ctypeslib.as_array(s.view.true_gt, shape=(S, 2)), axis=1)
     assert (np.sort(out1["best"], axis=1) == truth).all(axis=1).mean() > 0.85
     ctx.close()
+
+
+@pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libhipstr_ref.so not built")
+@pytest.mark.parametrize("name,kw", [
+    ("configs[2]: 100 samples x 30 reads, 16 alleles", dict(n_loci=3, n_samples=100, reads_per_sample=30, n_alleles=16, read_len=150, seed=3000)),
+    ("configs[3]: 500 samples x 5 reads, 32 alleles", dict(n_loci=3, n_samples=500, reads_per_sample=5, n_alleles=32, read_len=150, seed=4000)),
+])
+def test_full_shapes_against_reference(name, kw):
+    """K1 (+ K2 + K3) at the FULL per-locus shapes of BASELINE.json configs[2] and configs[3], three loci each, against the
+    compiled, unmodified reference (HapAligner::process_reads + Genotyper::calc_log_sample_posteriors): LLs within the
+    north-star tolerance 1e-4 -- and, as everywhere so far, bit-equal -- best diplotypes identical."""
+    s = Synth(**kw)
+    ref = checkers.ref()
+    want = checkers.align(ref, "ref_", s.batch, s.n_out)
+    ctx = Context(0)
+    got = ctx.align_host(s.batch, s.n_out)
+    d = np.abs(got - want)
+    print("[%s] %d alignments, max|diff| %.3g, not bit-equal %d" % (name, got.size, d.max(), int((got != want).sum())))
+    assert d.max() <= 1e-4 and d.max() <= 1e-9
+    # the genotype posteriors on top of them
+    reads = s.reads_batch()
+    S, R = int(s.locus_sample_off[-1]), int(s.n_reads)
+    out = ctx.genotype_host(s.batch, reads, int(s.read_ll_size), R, int(s.post_size), S, s.n_loci)
+    ctx.close()
+    read_ll = np.concatenate([want[s.locus_out_off[l]:s.locus_out_off[l + 1]].reshape(-1, int(s.n_haps[l]))
+                              [s.pool_index[s.locus_read_off[l]:s.locus_read_off[l + 1]]].ravel() for l in range(s.n_loci)])
+    post, sll, best, tot = checkers.posteriors(ref, "ref_", s.locus_read_off, s.locus_sample_off, s.n_haps, s.haploid, read_ll, s.log_p1,
+                                               s.log_p2, s.sample_label, s.read_weight)
+    assert np.array_equal(out["best"].reshape(-1, 2), best.reshape(-1, 2))
+    assert np.abs(out["post"] - post).max() <= 1e-9 and np.abs(out["total_ll"] - tot).max() <= 1e-6
