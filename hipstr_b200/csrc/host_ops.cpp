@@ -108,6 +108,7 @@ extern "C" hipstr_status_t hipstr_pool_reads(int32_t n_reads, const int32_t* seq
   }
   int32_t at = 0;
   std::vector<const unsigned char*> rows;
+  std::vector<unsigned char> work;
   uint16_t hist[256];
   std::memset(hist, 0, sizeof(hist));
   for (size_t p = 0; p < last_member.size(); p++) {
@@ -123,6 +124,30 @@ extern "C" hipstr_status_t hipstr_pool_reads(int32_t n_reads, const int32_t* seq
       const signed char* a = reinterpret_cast<const signed char*>(quals + seq_off[first]);
       const signed char* b = reinterpret_cast<const signed char*>(quals + seq_off[next_member[first]]);
       for (int32_t i = 0; i < len; i++) pool_quals[at + i] = (char)(a[i] > b[i] ? a[i] : b[i]);
+    } else if (m <= 24) {
+      // Upper median per position (sorted[m / 2] in signed char order) of a few rows: an odd-even transposition network
+      // over whole rows -- every compare-exchange is an elementwise min / max of two byte rows, which the compiler turns
+      // into vector instructions.  (byte ^ 0x80) turns signed order into unsigned order.
+      const size_t pitch = ((size_t)len + 63) & ~(size_t)63;
+      work.resize(m * pitch);
+      size_t k = 0;
+      for (int32_t r = first; r >= 0; r = next_member[r], k++) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(quals + seq_off[r]);
+        unsigned char* dst = work.data() + k * pitch;
+        for (int32_t i = 0; i < len; i++) dst[i] = src[i] ^ 0x80u;
+      }
+      for (size_t pass = 0; pass < m; pass++)
+        for (size_t a = pass & 1; a + 1 < m; a += 2) {
+          unsigned char* __restrict lo = work.data() + a * pitch;
+          unsigned char* __restrict hi = lo + pitch;
+          for (int32_t i = 0; i < len; i++) {
+            const unsigned char x = lo[i], y = hi[i];
+            lo[i] = x < y ? x : y;
+            hi[i] = x < y ? y : x;
+          }
+        }
+      const unsigned char* med = work.data() + (m / 2) * pitch;
+      for (int32_t i = 0; i < len; i++) pool_quals[at + i] = (char)(med[i] ^ 0x80u);
     } else {
       // Upper median per position (sorted[m / 2] in signed char order) by counting: m increments of a 256-bin histogram
       // indexed by (byte ^ 0x80) -- which turns signed order into unsigned order -- then a scan of the occupied range.
@@ -187,6 +212,34 @@ bool compose(const std::string& hap, const std::string& read, long h, long r, in
   return true;
 }
 
+// The same walk when only the reference span is wanted: the number of reference-consuming operations ('M' / 'D') it
+// would emit, no string built.  Returns -1 on an inconsistent pair.
+long compose_span(const char* hap, long hap_n, const char* read, long read_n, long h, long r, int step) {
+  long span = 0;
+  while (r >= 0 && r < read_n) {
+    const char rc = read[r];
+    if (rc == 'S') { r += step; continue; }
+    if (h < 0 || h >= hap_n) return -1;
+    const char hc = hap[h];
+    if (hc == 'D') {
+      span++;
+      if (rc == 'I') r += step;
+      h += step;
+    } else if (rc == 'I') r += step;
+    else if (rc == 'D') {
+      if (hc == 'M') span++;
+      else if (hc != 'I') return -1;
+      r += step; h += step;
+    } else if (rc == 'M') {
+      if (hc == 'M') span++;
+      else if (hc != 'I') return -1;
+      r += step; h += step;
+    } else
+      return -1;
+  }
+  return span;
+}
+
 }  // namespace
 
 extern "C" hipstr_status_t hipstr_stitch_trace(int32_t hap_start, const char* hap_aln_to_ref, const char* read_aln_to_hap,
@@ -195,6 +248,29 @@ extern "C" hipstr_status_t hipstr_stitch_trace(int32_t hap_start, const char* ha
                                                int32_t* cigar_len, int32_t* n_cigar, int32_t aln_cap, char* alignment) {
   if (!hap_aln_to_ref || !read_aln_to_hap || !read_bases || !start || !stop || !n_cigar) return HIPSTR_ERR_BAD_ARG;
   const bool want_strings = cigar_type && cigar_len && alignment;   // NULL = only the span is wanted
+  if (!want_strings) {
+    const char *hap = hap_aln_to_ref, *read = read_aln_to_hap;
+    const long hap_n = (long)std::strlen(hap), read_n = (long)std::strlen(read);
+    long hcol = 0, remaining = seed_hap_pos;
+    int32_t seed_pos = hap_start;
+    for (; remaining > 0 && hcol < hap_n; hcol++) {
+      remaining -= hap[hcol] != 'D';
+      seed_pos += hap[hcol] != 'I';
+    }
+    while (hcol < hap_n && hap[hcol] == 'D') hcol++;
+    if (hcol == hap_n) return HIPSTR_ERR_BAD_ARG;
+    long rcol = 0;
+    for (remaining = seed_base; remaining > 0 && rcol < read_n; rcol++) remaining -= read[rcol] != 'D';
+    while (rcol < read_n && read[rcol] == 'D') rcol++;
+    if (rcol == read_n) return HIPSTR_ERR_BAD_ARG;
+    const long left = compose_span(hap, hap_n, read, read_n, hcol - 1, rcol - 1, -1);
+    const long right = compose_span(hap, hap_n, read, read_n, hcol + 1, rcol + 1, 1);
+    if (left < 0 || right < 0) return HIPSTR_ERR_BAD_ARG;
+    *start = seed_pos - (int32_t)left;
+    *stop = seed_pos + (int32_t)right;
+    *n_cigar = 0;
+    return HIPSTR_OK;
+  }
   const std::string hap(hap_aln_to_ref), read(read_aln_to_hap);
   // column of the haplotype-vs-reference alignment that holds haplotype base seed_hap_pos, and its coordinate
   long hcol = 0, remaining = seed_hap_pos;

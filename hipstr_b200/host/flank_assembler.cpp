@@ -36,10 +36,10 @@ void FlankAssembler::increment_edge(std::string_view from, std::string_view to, 
   arriving_[d].push_back(id);
 }
 
-void FlankAssembler::add_string(const std::string& seq, int weight, int copies) {
+void FlankAssembler::add_string(std::string_view seq, int weight, int copies) {
   if ((int)seq.size() <= k_) return;
   num_strings_ += copies;
-  const std::string_view s(seq);
+  const std::string_view s = seq;
   for (size_t i = 1; i + k_ <= seq.size(); i++) increment_edge(s.substr(i - 1, k_), s.substr(i, k_), weight * copies);
 }
 

@@ -26,7 +26,7 @@ class FlankAssembler {
   /* DebruijnGraph(k, ref_seq): the reference path enters with weight 2 and its edges are never pruned. */
   FlankAssembler(int k, const std::string& ref_seq);
   /* debruijn_graph.cpp:31-45; `copies` identical strings at once (same graph as adding them one by one) */
-  void add_string(const std::string& seq, int weight = 1, int copies = 1);
+  void add_string(std::string_view seq, int weight = 1, int copies = 1);
   void prune_edges(double min_edge_freq, int min_weight);         /* :47-60, 62-121 */
   bool has_cycles() const;                                        /* directed_graph.cpp:29-64 */
   bool is_source_ok();                                            /* debruijn_graph.cpp:12-15 */

@@ -23,7 +23,9 @@ bool by_length_then_sequence(const std::string& a, const std::string& b) {
 
 bool HaplotypeGenerator::extract_sequence(const ReadView& aln, int32_t region_start, int32_t region_end, std::string& seq) {
   if (aln.start >= region_start || aln.stop <= region_end) return false;
-  std::string out;
+  std::string& out = seq;   // built in place: the caller reuses one buffer for all its reads
+  out.clear();
+  auto done = [&] { for (char& ch : out) ch = (char)std::toupper((unsigned char)ch); return true; };
   int32_t pos = aln.start;   // reference coordinate of the next unconsumed base of the current element
   int read_at = 0;           // next unconsumed read base
   for (int c = 0; c < aln.n_cigar; c++) {
@@ -31,9 +33,9 @@ bool HaplotypeGenerator::extract_sequence(const ReadView& aln, int32_t region_st
     const int len = aln.cigar_len[c];
     int used = 0;
     while (used < len) {
-      if (pos > region_end) { seq = upper(out); return true; }
+      if (pos > region_end) return done();
       if (pos == region_end) {
-        if (type != 'I') { seq = upper(out); return true; }
+        if (type != 'I') return done();
         out.append(aln.bases + read_at, len);   // an insertion flush with the region's end still belongs to it
         read_at += len;
         used = len;
@@ -111,8 +113,8 @@ void HaplotypeGenerator::gen_candidate_seqs(const std::string& ref_seq, int idea
   for (const std::vector<ReadView>& sample : alignments) {
     int samp_reads = 0;
     std::map<std::string, int> counts;
+    std::string sub;
     for (const ReadView& aln : sample) {
-      std::string sub;
       if (extract_sequence(aln, region_start, region_end, sub)) {
         read_counts[sub]++;
         counts[sub]++;

@@ -126,54 +126,50 @@ HapBlock HapBlock::remove_alleles(const std::vector<int>& allele_indices) const 
   return out;
 }
 
-bool AlignmentTrace::has_stutter() const {
-  for (int32_t s : stutter_size)
-    if (s != HIPSTR_NO_STR_DATA && s != 0) return true;
-  return false;
-}
-int AlignmentTrace::total_stutter_size() const {
-  int total = 0;
-  for (int32_t s : stutter_size)
-    if (s != HIPSTR_NO_STR_DATA) total += s;
-  return total;
-}
-
 std::string hap_aln_to_ref(const std::string& ref_hap, const std::string& alt_hap, int32_t first_block_start,
                            int32_t repeat_block_start) {
   const int L1 = (int)ref_hap.size(), L2 = (int)alt_hap.size(), W = L1 + 1;
   const size_t cells = (size_t)W * (L2 + 1);
-  // M: bases paired; X: reference base against a gap; Y: alternate base against a gap
-  std::vector<float> M(cells), X(cells), Y(cells);
-  std::vector<int8_t> tM(cells, -1), tX(cells, -1), tY(cells, -1);
-  M[0] = 0.0f; X[0] = -kLarge; Y[0] = -kLarge;
-  for (int j = 1; j <= L1; j++) { X[j] = -kGapOpen - (j - 1) * kGapExtend; tX[j] = 1; Y[j] = -kLarge; M[j] = -kLarge; }
+  // M: bases paired; X: reference base against a gap; Y: alternate base against a gap.  Only two rows of scores are live;
+  // the three predecessor choices of a cell share one byte (2 bits each: M, X, Y from the low bits up).
+  static thread_local std::vector<float> score;
+  static thread_local std::vector<uint8_t> from;
+  static thread_local std::vector<int8_t> rc, ac;
+  score.resize(6 * (size_t)W);
+  from.resize(cells);
+  rc.resize(L1); ac.resize(L2);
+  float *pM = score.data(), *pX = pM + W, *pY = pX + W, *cM = pY + W, *cX = cM + W, *cY = cX + W;
+  pM[0] = 0.0f; pX[0] = -kLarge; pY[0] = -kLarge;
+  for (int j = 1; j <= L1; j++) { pX[j] = -kGapOpen - (j - 1) * kGapExtend; pY[j] = -kLarge; pM[j] = -kLarge; }
+  for (int j = 0; j < L1; j++) rc[j] = (int8_t)base_code(ref_hap[j]);
+  for (int i = 0; i < L2; i++) ac[i] = (int8_t)base_code(alt_hap[i]);
   for (int i = 1; i <= L2; i++) {
-    const size_t c = (size_t)i * W;
-    Y[c] = -kGapOpen - (i - 1) * kGapExtend; tY[c] = 2; X[c] = -kLarge; M[c] = -kLarge;
-  }
-  std::vector<int> rc(L1), ac(L2);
-  for (int j = 0; j < L1; j++) rc[j] = base_code(ref_hap[j]);
-  for (int i = 0; i < L2; i++) ac[i] = base_code(alt_hap[i]);
-  for (int i = 1; i <= L2; i++)
+    uint8_t* frow = from.data() + (size_t)i * W;
+    cY[0] = -kGapOpen - (i - 1) * kGapExtend; cX[0] = -kLarge; cM[0] = -kLarge;
+    frow[0] = (uint8_t)(2 << 4);
+    const int a = ac[i - 1];
     for (int j = 1; j <= L1; j++) {
-      const size_t here = (size_t)i * W + j, diag = here - W - 1, left = here - 1, up = here - W;
-      M[here] = pick3(M[diag], X[diag], Y[diag], &tM[here]) + pair_score(rc[j - 1], ac[i - 1]);
-      X[here] = pick3(M[left] - kGapOpen, X[left] - kGapExtend, Y[left] - kGapOpen, &tX[here]);
-      Y[here] = pick3(M[up] - kGapOpen, X[up] - kGapOpen, Y[up] - kGapExtend, &tY[here]);
+      int8_t wM, wX, wY;
+      cM[j] = pick3(pM[j - 1], pX[j - 1], pY[j - 1], &wM) + pair_score(rc[j - 1], a);
+      cX[j] = pick3(cM[j - 1] - kGapOpen, cX[j - 1] - kGapExtend, cY[j - 1] - kGapOpen, &wX);
+      cY[j] = pick3(pM[j] - kGapOpen, pX[j] - kGapOpen, pY[j] - kGapExtend, &wY);
+      frow[j] = (uint8_t)(wM | (wX << 2) | (wY << 4));
     }
+    std::swap(pM, cM); std::swap(pX, cX); std::swap(pY, cY);
+  }
   // end-to-end alignment: stop in the corner (findOptimalStopEndPenalty)
-  const size_t corner = cells - 1;
   int kind = 0;
-  float best = M[corner];
-  if (X[corner] > best) { best = X[corner]; kind = 1; }
-  if (Y[corner] > best) { best = Y[corner]; kind = 2; }
+  float best = pM[L1];
+  if (pX[L1] > best) { best = pX[L1]; kind = 1; }
+  if (pY[L1] > best) { best = pY[L1]; kind = 2; }
   std::string ref_row, alt_row;   // built back to front
+  ref_row.reserve((size_t)L1 + L2); alt_row.reserve((size_t)L1 + L2);
   int row = L2, col = L1;
   while (row > 0) {
-    const size_t here = (size_t)row * W + col;
-    if (kind == 0 && col > 0) { ref_row += ref_hap[col - 1]; alt_row += alt_hap[row - 1]; kind = tM[here]; row--; col--; }
-    else if (kind == 1 && col > 0) { ref_row += ref_hap[col - 1]; alt_row += '-'; kind = tX[here]; col--; }
-    else if (kind == 2) { ref_row += '-'; alt_row += alt_hap[row - 1]; kind = tY[here]; row--; }
+    const uint8_t f = from[(size_t)row * W + col];
+    if (kind == 0 && col > 0) { ref_row += ref_hap[col - 1]; alt_row += alt_hap[row - 1]; kind = f & 3; row--; col--; }
+    else if (kind == 1 && col > 0) { ref_row += ref_hap[col - 1]; alt_row += '-'; kind = (f >> 2) & 3; col--; }
+    else if (kind == 2) { ref_row += '-'; alt_row += alt_hap[row - 1]; kind = (f >> 4) & 3; row--; }
     else return std::string();   // the reference dies here ("Invalid matrix type")
   }
   for (; col > 0; col--) { ref_row += ref_hap[col - 1]; alt_row += '-'; }
@@ -251,7 +247,7 @@ void SeqStutterGenotyper::get_stutter_candidate_alleles(int block_index, std::ve
     if (seed_positions_[r] < 0) continue;
     const AlignmentTrace& trace = trace_cache_.at(std::make_pair(pool_index_[r], best_hap_of_read(r)));
     if (trace.start < block.start && trace.stop > block.end) {
-      if (trace.stutter_size[block_index] != 0) sample_stutter_counts[sample_label_[r]][trace.str_seq[block_index]]++;
+      if (trace.stutter_size[block_index] != 0) sample_stutter_counts[sample_label_[r]][std::string(trace.str_seq(block_index))]++;
       sample_counts[sample_label_[r]]++;
     }
   }
@@ -491,7 +487,7 @@ int SeqStutterGenotyper::assemble_flanks() {
     // reference flank, and which of its (k+1)-mers at k = kmer_length are not reference edges.  Every read is looked up
     // once; the per-sample work below only touches these records.
     struct FlankInfo {
-      const std::string* seq = nullptr;
+      std::string_view seq;
       bool in_reference = false;
       std::vector<std::string_view> nonref_edges;
       int stamp = -1, count = 0;   // sample that saw it last, reads of that sample carrying it
@@ -500,13 +496,12 @@ int SeqStutterGenotyper::assemble_flanks() {
     std::vector<FlankInfo*> read_info(num_reads_, nullptr);
     for (int r = 0; r < num_reads_; r++) {
       if (!read_trace[r]) continue;
-      const std::string& seq = read_trace[r]->flank_seq[block_index];
-      if (seq.empty()) continue;
-      const std::string_view sv(seq);
+      const std::string_view sv = read_trace[r]->flank_seq(block_index);
+      if (sv.empty()) continue;
       auto it = flank_info.find(sv);
       if (it == flank_info.end()) {
         FlankInfo fi;
-        fi.seq = &seq;
+        fi.seq = sv;
         fi.in_reference = ref_seq.find(sv) != std::string::npos;
         if (!fi.in_reference)
           for (size_t c = 0; c + kmer_length + 1 <= sv.size(); c++) {
@@ -549,7 +544,7 @@ int SeqStutterGenotyper::assemble_flanks() {
         int num_strings = 1;
         edges.clear();
         for (const FlankInfo* fi : flank_seqs) {
-          if ((int)fi->seq->size() <= k) continue;
+          if ((int)fi->seq.size() <= k) continue;
           num_strings += fi->count;
           for (const std::string_view& e : fi->nonref_edges) edges.emplace_back(e, fi->count);
         }
@@ -567,7 +562,7 @@ int SeqStutterGenotyper::assemble_flanks() {
       }
       for (int k = kmer_length; k <= max_k; k++) {
         FlankAssembler assembler(k, ref_seq);
-        for (const FlankInfo* fi : flank_seqs) assembler.add_string(*fi->seq, 1, fi->count);
+        for (const FlankInfo* fi : flank_seqs) assembler.add_string(fi->seq, 1, fi->count);
         assembler.prune_edges(0.02, 2);
         if (!assembler.has_cycles() && assembler.is_source_ok() && assembler.is_sink_ok()) {
           acyclic = true;
@@ -1134,6 +1129,7 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
     while (li < which.size() && trace_pool.size() < kChunk) {
       SeqStutterGenotyper& g = loci[which[li]];
       if (ti >= g.missing_traces_.size()) { li++; ti = 0; continue; }
+      if (ti == 0) g.trace_cache_.reserve(g.trace_cache_.size() + g.missing_traces_.size());
       const int32_t pool_base = (int32_t)pb.pool_seed.size();
       std::vector<int> own;   // reads traced with their own qualities become extra pools of this locus
       if (!g.missing_trace_read_.empty())
@@ -1180,24 +1176,23 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
       SeqStutterGenotyper& g = loci[owner[i].first];
       const std::pair<int, int> key = g.missing_traces_[owner[i].second];
       const int nb = (int)g.hap_blocks_.size();
-      const std::string read = g.pool_read(key.first);
-      AlignmentTrace t;
-      t.hap_aln = std::string(hap_aln.p + i * (size_t)stride);
+      const std::string_view read = g.pool_read_view(key.first);
+      AlignmentTrace& t = g.trace_cache_[key];
+      t = AlignmentTrace();
+      const char* ops = hap_aln.p + i * (size_t)stride;   // read-vs-haplotype operations, NUL-terminated
       t.flank_ins_size = flank_ins.p[i];
       t.flank_del_size = flank_del.p[i];
-      t.stutter_size.assign(stutter.p + i * 8, stutter.p + i * 8 + nb);
-      t.str_seq.assign(nb, std::string());
-      t.flank_seq.assign(nb, std::string());
+      t.num_blocks = nb;
       for (int b = 0; b < nb; b++) {
-        const std::string span = span_len.p[i * 8 + b] > 0 ? read.substr(span_start.p[i * 8 + b], span_len.p[i * 8 + b]) : std::string();
-        (g.hap_blocks_[b].period > 0 ? t.str_seq : t.flank_seq)[b] = span;
+        t.stutter_size[b] = stutter.p[i * 8 + b];
+        t.block_seq[b] = span_len.p[i * 8 + b] > 0 ? read.substr(span_start.p[i * 8 + b], span_len.p[i * 8 + b]) : std::string_view();
       }
       if (n_indels.p[i] > HIPSTR_MAX_TRACE_INDELS || n_snps.p[i] > HIPSTR_MAX_TRACE_SNPS) {
         // more flank indels / SNPs than the fixed slots of the device call hold (a chimeric or mismapped read): the counts
         // are the true ones, the complete lists are rebuilt on the host from the trace's operation string
         std::vector<int32_t> all_indels(2 * (size_t)std::max(n_indels.p[i], 1)), all_snps(2 * (size_t)std::max(n_snps.p[i], 1));
         int32_t ni = 0, ns = 0;
-        const hipstr_status_t st3 = hipstr_trace_flank_lists(&bt, pb.block_start.data(), trace_pool[i], trace_hap[i], t.hap_aln.c_str(),
+        const hipstr_status_t st3 = hipstr_trace_flank_lists(&bt, pb.block_start.data(), trace_pool[i], trace_hap[i], ops,
                                                              seed_hap_pos.p[i], stutter.p + i * 8, nullptr, n_indels.p[i], &ni,
                                                              all_indels.data(), n_snps.p[i], &ns, all_snps.data());
         if (st3 != HIPSTR_OK || ni != n_indels.p[i] || ns != n_snps.p[i]) { failed = 1; return; }
@@ -1213,8 +1208,8 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
       // traced alignment (used by the reference's HTML visualisation) are built on request (keep_traced_alignments)
       int32_t n_cigar = 0;
       const bool full = keep_traced_alignments;
-      const hipstr_status_t st2 = hipstr_stitch_trace(g.hap_blocks_.front().start, g.hap_aln_info_[key.second].c_str(), t.hap_aln.c_str(), seed_hap_pos.p[i],
-                               g.pool_seed_[key.first], read.c_str(), &t.start, &t.stop, (int32_t)ctype.size(), full ? ctype.data() : nullptr,
+      const hipstr_status_t st2 = hipstr_stitch_trace(g.hap_blocks_.front().start, g.hap_aln_info_[key.second].c_str(), ops, seed_hap_pos.p[i],
+                               g.pool_seed_[key.first], full ? std::string(read).c_str() : "", &t.start, &t.stop, (int32_t)ctype.size(), full ? ctype.data() : nullptr,
                                full ? clen.data() : nullptr, &n_cigar, (int32_t)aln.size(), full ? aln.data() : nullptr);
       if (st2 != HIPSTR_OK) { failed = 1; return; }
       if (full) {
@@ -1222,8 +1217,8 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
         for (int k = 0; k < n_cigar; k++) cig << clen[k] << ctype[k];
         t.cigar = cig.str();
         t.alignment = std::string(aln.data());
+        t.hap_aln = ops;
       }
-      g.trace_cache_[key] = std::move(t);
       }
     });
     if (failed) { err = "hipstr_stitch_trace failed"; return HIPSTR_ERR_BAD_ARG; }
@@ -1324,7 +1319,7 @@ hipstr_status_t GenotyperBatch::recompute_stutter_models(int max_total_haplotype
         if (g.seed_positions_[r] < 0) continue;
         const AlignmentTrace& t = g.trace_cache_.at(std::make_pair(g.pool_index_[r], g.best_hap_of_read(r)));
         if (!(t.start < block.start && t.stop > block.end)) continue;
-        num_bps.push_back((int32_t)t.str_seq[b].size() + t.stutter_size[b]);
+        num_bps.push_back((int32_t)t.str_seq(b).size() + t.stutter_size[b]);
         labels.push_back(g.sample_label_[r]);
         p1.push_back(g.log_p1_[r]);
         p2.push_back(g.log_p2_[r]);

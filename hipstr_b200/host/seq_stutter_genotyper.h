@@ -23,6 +23,7 @@
 #include <map>
 #include <unordered_map>
 #include <string>
+#include <string_view>
 #include <utility>
 #include <vector>
 
@@ -43,17 +44,33 @@ struct HapBlock {
 
 /* What the control loop and the VCF writer read off an AlignmentTrace (AlignmentTraceback.h:9-117). */
 struct AlignmentTrace {
-  std::string hap_aln;                              /* hap_aln(): read vs haplotype operations */
+  std::string hap_aln;                              /* hap_aln(): read vs haplotype operations (kept when keep_traced_alignments) */
   int32_t start = 0, stop = 0;                      /* traced_aln().get_start() / get_stop() */
   std::string cigar;                                /* traced_aln().getCigarString()   (filled when keep_traced_alignments) */
   std::string alignment;                            /* traced_aln().get_alignment()    (filled when keep_traced_alignments) */
   int32_t flank_ins_size = 0, flank_del_size = 0;
-  std::vector<int32_t> stutter_size;                /* per block; HIPSTR_NO_STR_DATA where no STR data */
-  std::vector<std::string> str_seq, flank_seq;      /* per block */
+  /* Per block, in fixed slots (a locus has at most HIPSTR_MAX_BLOCKS_PER_LOCUS blocks): a trace is built for every
+   * (pooled read, haplotype) the loop looks at, ~1000 per locus, so it owns no per-block heap storage. */
+  int32_t num_blocks = 0;
+  int32_t stutter_size[HIPSTR_MAX_BLOCKS_PER_LOCUS] = {};   /* HIPSTR_NO_STR_DATA where no STR data */
+  /* the read bases aligned to the block: str_seq() of a repeat block, flank_seq() of a flank block -- views into the
+   * locus' pooled read bases (SeqStutterGenotyper::pool_bases_), valid while the locus lives */
+  std::string_view block_seq[HIPSTR_MAX_BLOCKS_PER_LOCUS];
+  std::string_view str_seq(int block) const { return block_seq[block]; }
+  std::string_view flank_seq(int block) const { return block_seq[block]; }
   std::vector<std::pair<int32_t, int32_t> > flank_indel_data;
   std::vector<std::pair<int32_t, char> > flank_snp_data;
-  bool has_stutter() const;
-  int total_stutter_size() const;
+  bool has_stutter() const {
+    for (int b = 0; b < num_blocks; b++)
+      if (stutter_size[b] != HIPSTR_NO_STR_DATA && stutter_size[b] != 0) return true;
+    return false;
+  }
+  int total_stutter_size() const {
+    int total = 0;
+    for (int b = 0; b < num_blocks; b++)
+      if (stutter_size[b] != HIPSTR_NO_STR_DATA) total += stutter_size[b];
+    return total;
+  }
 };
 
 /* Haplotype::aln_haps_to_ref for one haplotype (SeqAlignment/Haplotype.cpp:8-86): global affine-gap
@@ -142,6 +159,9 @@ class SeqStutterGenotyper {
   Phase phase() const { return phase_; }
   bool succeeded() const { return phase_ == DONE; }
   std::string pool_read(int pool) const { return pool_bases_.substr(pool_seq_off_[pool], pool_seq_off_[pool + 1] - pool_seq_off_[pool]); }
+  std::string_view pool_read_view(int pool) const {
+    return std::string_view(pool_bases_).substr(pool_seq_off_[pool], pool_seq_off_[pool + 1] - pool_seq_off_[pool]);
+  }
   void haps_to_alleles(int block_index, std::vector<int>& allele_indices) const;   /* .cpp:219-227 */
   std::string hap_seq(int hap) const;
 

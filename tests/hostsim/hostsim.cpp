@@ -7,6 +7,8 @@
  * a GPU (`-m "not gpu"` tests, gprof).  It is linked only into tests/hostsim/libhipstr_hostsim.so; the product
  * (hipstr_b200/libhipstr_b200.so) has no such path and fails with HIPSTR_ERR_NO_DEVICE without a GPU.
  */
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,6 +18,32 @@
 #include "../../oracle/hipstr_oracle.h"
 
 struct hipstr_ctx { std::string last_error; double trace_seconds[4] = {0, 0, 0, 0}; };
+
+/* Record / replay of the simulated device calls, for profiling the HOST side alone: with HIPSTR_SIM_RECORD=<file> every
+ * call appends its outputs to the file; with HIPSTR_SIM_REPLAY=<file> the same sequence of calls (same inputs, ONE host
+ * thread, one window at a time) gets the recorded outputs back without running the oracle; the tape rewinds at its end. */
+namespace {
+struct Tape {
+  FILE* f = nullptr;
+  bool replay = false;
+  Tape() {
+    if (const char* p = std::getenv("HIPSTR_SIM_REPLAY")) { f = std::fopen(p, "rb"); replay = true; }
+    else if (const char* q = std::getenv("HIPSTR_SIM_RECORD")) f = std::fopen(q, "wb");
+  }
+  bool playing() {
+    if (!(f && replay)) return false;
+    const int c = std::fgetc(f);
+    if (c == EOF) std::rewind(f); else std::ungetc(c, f);
+    return true;
+  }
+  template <class T> void io(T* p, size_t n) {
+    if (!f || !p || n == 0) return;
+    if (replay) { if (std::fread(p, sizeof(T), n, f) != n) { std::fprintf(stderr, "hostsim: tape does not match the calls\n"); std::abort(); } }
+    else std::fwrite(p, sizeof(T), n, f);
+  }
+};
+Tape& tape() { static Tape t; return t; }
+}  // namespace
 
 extern "C" {
 
@@ -55,14 +83,32 @@ hipstr_status_t hipstr_posteriors_host(hipstr_ctx_t*, int32_t n_loci, const int3
                                        const uint8_t* haploid, const double* read_ll, const double* p1, const double* p2,
                                        const int32_t* label, const int32_t* weight, double* post, double* sll, int32_t* best,
                                        double* tot) {
-  return oracle_posteriors(n_loci, lro, lso, n_haps, haploid, read_ll, p1, p2, label, weight, post, sll, best, tot) == 0
-             ? HIPSTR_OK : HIPSTR_ERR_BAD_ARG;
+  size_t n_post = 0;
+  for (int l = 0; l < n_loci; l++) n_post += (size_t)(lso[l + 1] - lso[l]) * n_haps[l] * n_haps[l];
+  const size_t S = n_loci ? (size_t)lso[n_loci] : 0;
+  auto io = [&] { tape().io(post, n_post); tape().io(sll, S); tape().io(best, 2 * S); tape().io(tot, (size_t)n_loci); };
+  if (tape().playing()) { io(); return HIPSTR_OK; }
+  const int rc = oracle_posteriors(n_loci, lro, lso, n_haps, haploid, read_ll, p1, p2, label, weight, post, sll, best, tot);
+  io();
+  return rc == 0 ? HIPSTR_OK : HIPSTR_ERR_BAD_ARG;
 }
 /* K1 + K2 + K3 of a batch (seq_stutter_genotyper.cpp:519-568,638-639), masks with the in-place semantics of the product */
 hipstr_status_t hipstr_genotype_batch_host(hipstr_ctx_t* c, const hipstr_align_batch_t* b, const hipstr_reads_batch_t* r,
                                            const hipstr_genotype_out_t* o) {
   if (!c || !b || !r || !o || !o->read_ll || !o->post || !o->sample_ll) return HIPSTR_ERR_BAD_ARG;
   const int L = b->n_loci;
+  size_t n_ll = 0, n_post = 0;
+  for (int l = 0; l < L; l++) {
+    const size_t H = (size_t)(b->locus_hap_off[l + 1] - b->locus_hap_off[l]);
+    n_ll += (size_t)(r->locus_read_off[l + 1] - r->locus_read_off[l]) * H;
+    n_post += (size_t)(r->locus_sample_off[l + 1] - r->locus_sample_off[l]) * H * H;
+  }
+  const size_t n_r = L ? (size_t)r->locus_read_off[L] : 0, n_s = L ? (size_t)r->locus_sample_off[L] : 0;
+  auto io = [&] {
+    tape().io(o->read_ll, n_ll); tape().io(o->read_seed, n_r); tape().io(o->post, n_post); tape().io(o->sample_ll, n_s);
+    tape().io(o->best, 2 * n_s); tape().io(o->total_ll, (size_t)L);
+  };
+  if (tape().playing()) { io(); return HIPSTR_OK; }
   std::vector<double> pool_ll((size_t)(L ? b->locus_out_off[L] : 0), 0.0);
   if (oracle_align_batch(b, pool_ll.data(), nullptr) != 0) { c->last_error = "oracle_align_batch failed"; return HIPSTR_ERR_BAD_ARG; }
   std::vector<int32_t> n_haps((size_t)L);
@@ -83,21 +129,46 @@ hipstr_status_t hipstr_genotype_batch_host(hipstr_ctx_t* c, const hipstr_align_b
       return HIPSTR_ERR_BAD_ARG;
     ll_at += (int64_t)R * H;
   }
-  return oracle_posteriors(L, r->locus_read_off, r->locus_sample_off, n_haps.data(), r->haploid, o->read_ll, r->log_p1, r->log_p2,
-                           r->sample_label, r->read_weight, o->post, o->sample_ll, o->best, o->total_ll) == 0
-             ? HIPSTR_OK : HIPSTR_ERR_BAD_ARG;
+  const int rc = oracle_posteriors(L, r->locus_read_off, r->locus_sample_off, n_haps.data(), r->haploid, o->read_ll, r->log_p1, r->log_p2,
+                                   r->sample_label, r->read_weight, o->post, o->sample_ll, o->best, o->total_ll);
+  io();
+  return rc == 0 ? HIPSTR_OK : HIPSTR_ERR_BAD_ARG;
 }
 hipstr_status_t hipstr_extract_genotypes_host(hipstr_ctx_t*, int32_t n_loci, const int32_t* lso, const int32_t* n_haps,
                                               const int32_t* n_variants, const int32_t* h2a, const uint8_t* haploid, const double* post,
                                               const double* sll, int32_t* best_hap, int32_t* best_gt, double* lp, double* lu, double* hlp,
                                               double* hlu, double* gl, double* pgl, double* gl_diff, int32_t* pl) {
-  return oracle_extract_genotypes(n_loci, lso, n_haps, n_variants, h2a, haploid, post, sll, best_hap, best_gt, lp, lu, hlp, hlu, gl, pgl,
-                                  gl_diff, pl) == 0 ? HIPSTR_OK : HIPSTR_ERR_BAD_ARG;
+  size_t n_gl = 0, n_pgl = 0;
+  for (int l = 0; l < n_loci; l++) {
+    const size_t S = (size_t)(lso[l + 1] - lso[l]), V = (size_t)n_variants[l];
+    n_gl += S * (haploid[l] ? V : V * (V + 1) / 2);
+    n_pgl += S * (haploid[l] ? V : V * V);
+  }
+  const size_t S = n_loci ? (size_t)lso[n_loci] : 0;
+  auto io = [&] {
+    tape().io(best_hap, 2 * S); tape().io(best_gt, 2 * S); tape().io(lp, S); tape().io(lu, S); tape().io(hlp, S); tape().io(hlu, S);
+    tape().io(gl, n_gl); tape().io(pgl, n_pgl); tape().io(gl_diff, S); tape().io(pl, n_gl);
+  };
+  if (tape().playing()) { io(); return HIPSTR_OK; }
+  const int rc = oracle_extract_genotypes(n_loci, lso, n_haps, n_variants, h2a, haploid, post, sll, best_hap, best_gt, lp, lu, hlp, hlu, gl,
+                                          pgl, gl_diff, pl);
+  io();
+  return rc == 0 ? HIPSTR_OK : HIPSTR_ERR_BAD_ARG;
 }
 hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t*, const hipstr_align_batch_t* b, const int32_t* block_start, int32_t n,
                                         const int32_t* tp, const int32_t* th, const hipstr_trace_out_t* out) {
   if (n == 0) return HIPSTR_OK;
-  return oracle_trace_batch(b, block_start, n, tp, th, out) == 0 ? HIPSTR_OK : HIPSTR_ERR_BAD_ARG;
+  const size_t T = (size_t)n;
+  auto io = [&] {
+    tape().io(out->hap_aln, T * (size_t)out->aln_stride); tape().io(out->seed_hap_pos, T); tape().io(out->stutter_size, 8 * T);
+    tape().io(out->span_start, 8 * T); tape().io(out->span_len, 8 * T); tape().io(out->flank_ins, T); tape().io(out->flank_del, T);
+    tape().io(out->n_indels, T); tape().io(out->indels, T * 2 * HIPSTR_MAX_TRACE_INDELS); tape().io(out->n_snps, T);
+    tape().io(out->snps, T * 2 * HIPSTR_MAX_TRACE_SNPS);
+  };
+  if (tape().playing()) { io(); return HIPSTR_OK; }
+  const int rc = oracle_trace_batch(b, block_start, n, tp, th, out);
+  io();
+  return rc == 0 ? HIPSTR_OK : HIPSTR_ERR_BAD_ARG;
 }
 hipstr_status_t hipstr_em_train_host(hipstr_ctx_t*, const hipstr_em_batch_t* b, int32_t max_iter, double a, double f, double* params,
                                      uint8_t* conv, int32_t* iters, double* ll) {

@@ -89,7 +89,7 @@ def test_pool_reads_median_qualities_match_sorting():
     rng = np.random.default_rng(9)
     for trial in range(30):
         L = int(rng.integers(1, 130))
-        sizes = [int(x) for x in rng.choice([1, 2, 3, 4, 7, 10, 33, 64, 65, 200], int(rng.integers(1, 8)))]
+        sizes = [int(x) for x in rng.choice([1, 2, 3, 4, 7, 10, 24, 25, 33, 64, 65, 200], int(rng.integers(1, 8)))]
         seqs, quals = [], []
         for p, m in enumerate(sizes):
             seq = bytes(int(v) for v in rng.choice(list(b"ACGT"), L)) + bytes([65 + p])   # distinct per pool

@@ -9,7 +9,7 @@ import pytest
 
 import cases
 import checkers
-from hipstr_b200.capi import MAX_BLOCKS, AlignBatch, BatchBuilder, TraceOut, c_i32p, trace_batch
+from hipstr_b200.capi import MAX_BLOCKS, AlignBatch, BatchBuilder, TraceOut, c_i32p, load, trace_batch
 
 KEYS = ("stutter_size", "span_start", "span_len", "flank_ins", "flank_del", "n_indels", "indels", "n_snps", "snps")
 
@@ -145,6 +145,12 @@ def test_stitch_trace_matches_reference(case):
                                                    int(seeds[pools[i]]), reads[i])
         assert st == 0
         assert (start, stop, cigar, aln) == (a.value, b.value, b3.value.decode(), b4.value.decode()), i
+        # the span-only form (no CIGAR / alignment buffers) the loop uses
+        lib = load()
+        s2, e2, n2 = C.c_int32(), C.c_int32(), C.c_int32(-1)
+        st = lib.hipstr_stitch_trace(hap_start, b1.value, o["hap_aln"][i].encode(), int(o["seed_hap_pos"][i]), int(seeds[pools[i]]),
+                                     reads[i].encode(), C.byref(s2), C.byref(e2), 0, None, None, C.byref(n2), 0, None)
+        assert (st, s2.value, e2.value, n2.value) == (0, a.value, b.value, 0), i
         n_checked += 1
     assert n_checked >= 10
 
