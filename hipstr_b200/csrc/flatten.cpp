@@ -23,6 +23,13 @@
 #include <map>
 #include <new>
 #include <thread>
+#include <chrono>
+#include <functional>
+#include <pthread.h>
+#include <mutex>
+#include <memory>
+#include <deque>
+#include <condition_variable>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
@@ -50,6 +57,73 @@ int host_thread_budget() {
     return std::max(1, std::min(t, 32));
   }();
   return t_thread_cap > 0 ? std::min(n, t_thread_cap) : n;
+}
+
+/* ---- the host thread pool ---------------------------------------------------------------------------------------- */
+namespace {
+struct PoolJob {
+  const std::function<void(size_t)>* fn;
+  size_t n;
+  std::atomic<size_t> next{0}, done{0};
+  void work() {
+    size_t mine = 0;
+    for (size_t i = next.fetch_add(1, std::memory_order_relaxed); i < n; i = next.fetch_add(1, std::memory_order_relaxed)) { (*fn)(i); mine++; }
+    if (mine) done.fetch_add(mine, std::memory_order_release);
+  }
+};
+struct ThreadPool {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::shared_ptr<PoolJob> > tickets;   // one entry per helper a job asked for
+  int n_threads = 0;
+  void loop() {
+    for (;;) {
+      std::shared_ptr<PoolJob> job;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !tickets.empty(); });
+        job = std::move(tickets.front());
+        tickets.pop_front();
+      }
+      job->work();   // a ticket taken after the job ran dry finds next >= n and never touches fn
+    }
+  }
+  void grow(int want) {   // under mu
+    for (; n_threads < want; n_threads++) std::thread([this] { loop(); }).detach();
+  }
+};
+ThreadPool* g_pool = nullptr;   // leaked on purpose: its parked threads outlive static destruction
+std::once_flag g_pool_once;
+ThreadPool& thread_pool() {
+  std::call_once(g_pool_once, [] {
+    g_pool = new ThreadPool();
+    // a forked child has none of the parked threads: it starts over with an empty pool
+    pthread_atfork(nullptr, nullptr, [] { g_pool = new ThreadPool(); });
+  });
+  return *g_pool;
+}
+}  // namespace
+
+void parallel_run(size_t n, int workers, const std::function<void(size_t)>& fn) {
+  if (workers > (int)n) workers = (int)n;
+  if (workers <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+  auto job = std::make_shared<PoolJob>();
+  job->fn = &fn;
+  job->n = n;
+  ThreadPool& pool = thread_pool();
+  {
+    std::lock_guard<std::mutex> lk(pool.mu);
+    const int hw = std::max(2, std::min((int)std::thread::hardware_concurrency(), 256));
+    pool.grow(std::min(hw, std::max(pool.n_threads, (int)pool.tickets.size() + workers - 1)));
+    for (int w = 1; w < workers; w++) pool.tickets.push_back(job);
+  }
+  if (workers == 2) pool.cv.notify_one(); else pool.cv.notify_all();
+  job->work();
+  // every index is claimed; wait for the helpers still inside fn
+  for (int spins = 0; job->done.load(std::memory_order_acquire) < n; spins++) {
+    if (spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(20));
+    else if (spins > 64) std::this_thread::yield();
+  }
 }
 
 void FlatBatch::clear() {
@@ -551,12 +625,7 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     };
     if (n_threads == 1) lower_chunk(0);
     else {
-      std::atomic<int> next(0);
-      auto worker = [&] { for (int c = next.fetch_add(1); c < n_chunks; c = next.fetch_add(1)) lower_chunk(c); };
-      std::vector<std::thread> workers;
-      for (int t = 1; t < n_threads; t++) workers.emplace_back(worker);
-      worker();
-      for (auto& w : workers) w.join();
+      parallel_run((size_t)n_chunks, n_threads, [&](size_t c) { lower_chunk((int)c); });
     }
     for (int c = 0; c < n_chunks; c++)
       if (part_status[c] != HIPSTR_OK) { err = part_err[c]; return part_status[c]; }
@@ -649,17 +718,17 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
   if (n_pools < 20000) n_threads = 1;
   if (n_threads == 1) fill(0, b->n_loci);
   else {
-    std::vector<std::thread> workers;
+    std::vector<std::pair<int, int> > ranges;
     int l0 = 0;
     for (int t = 0; t < n_threads; t++) {   // split by pool count, not locus count
       const int64_t target = (int64_t)n_pools * (t + 1) / n_threads;
       int l1 = l0;
       while (l1 < b->n_loci && b->locus_pool_off[l1 + 1] <= target) l1++;
       if (t == n_threads - 1) l1 = b->n_loci;
-      if (l1 > l0) workers.emplace_back(fill, l0, l1);
+      if (l1 > l0) ranges.emplace_back(l0, l1);
       l0 = l1;
     }
-    for (auto& w : workers) w.join();
+    parallel_run(ranges.size(), n_threads, [&](size_t i) { fill(ranges[i].first, ranges[i].second); });
   }
   switch (status.load()) {
     case HIPSTR_OK: break;

@@ -7,6 +7,7 @@
 
 #include <cstring>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "../../include/hipstr_b200.h"
@@ -105,6 +106,10 @@ struct FlatBatch {
  * thread's own budget when one was set (the multi-GPU driver splits the cores between its window workers). */
 int host_thread_budget();
 void set_host_thread_budget(int n);   /* for the calling thread; 0 = no cap */
+/* Runs fn(i) for i in [0, n): the caller plus up to workers - 1 threads of one process-wide pool of parked threads
+ * (created on first use, never per call -- a window of the loop issues ~50 of these).  Indices are handed out one at a
+ * time; returns when every fn(i) has returned.  Safe to call from several threads at once and from inside fn. */
+void parallel_run(size_t n, int workers, const std::function<void(size_t)>& fn);
 
 /* Returns HIPSTR_OK or an error with a message. */
 /* fresh_rows: give every haplotype the homopolymer classes of a from-scratch alignment (what

@@ -28,16 +28,7 @@ namespace {
 
 }  // namespace
 int host_threads() { return host_thread_budget(); }
-void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
-  const size_t workers = std::min<size_t>((size_t)host_threads(), n);
-  if (workers <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
-  std::atomic<size_t> next(0);
-  auto body = [&] { for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); };
-  std::vector<std::thread> pool;
-  for (size_t w = 1; w < workers; w++) pool.emplace_back(body);
-  body();
-  for (std::thread& t : pool) t.join();
-}
+void parallel_for(size_t n, const std::function<void(size_t)>& fn) { parallel_run(n, host_threads(), fn); }
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 namespace {
 
