@@ -17,6 +17,7 @@
 #include <sstream>
 #include <string_view>
 #include <thread>
+#include <emmintrin.h>
 
 #include "../csrc/flatten.h"
 #include "flank_assembler.h"
@@ -117,35 +118,78 @@ HapBlock HapBlock::remove_alleles(const std::vector<int>& allele_indices) const 
   return out;
 }
 
+/* Four cells of the three-way choice above: the value, and which matrix it came from (0, 1, 2) as an integer vector. */
+inline __m128 blend4(__m128 mask, __m128 a, __m128 b) { return _mm_or_ps(_mm_and_ps(mask, a), _mm_andnot_ps(mask, b)); }
+inline __m128 pick3x4(__m128 s1, __m128 s2, __m128 s3, __m128i* which) {
+  const __m128 second = _mm_cmpgt_ps(s2, s1);
+  const __m128 a = blend4(second, s2, s1);
+  const __m128 third = _mm_or_ps(_mm_cmpgt_ps(s3, a), _mm_and_ps(second, _mm_cmpeq_ps(s3, a)));   // ties: third over second, first over third
+  const __m128i t = _mm_castps_si128(third);
+  *which = _mm_or_si128(_mm_and_si128(t, _mm_set1_epi32(2)), _mm_andnot_si128(t, _mm_and_si128(_mm_castps_si128(second), _mm_set1_epi32(1))));
+  return blend4(third, s3, a);
+}
+
 std::string hap_aln_to_ref(const std::string& ref_hap, const std::string& alt_hap, int32_t first_block_start,
                            int32_t repeat_block_start) {
   const int L1 = (int)ref_hap.size(), L2 = (int)alt_hap.size(), W = L1 + 1;
+  const int P = ((W + 3) & ~3) + 8;   // pitch of the work rows: whole vectors plus slack for the shifted loads
   const size_t cells = (size_t)W * (L2 + 1);
   // M: bases paired; X: reference base against a gap; Y: alternate base against a gap.  Only two rows of scores are live;
   // the three predecessor choices of a cell share one byte (2 bits each: M, X, Y from the low bits up).
-  static thread_local std::vector<float> score;
+  //
+  // A row is computed four cells at a time (SSE2, part of x86-64).  M and Y only look at the row above.  X looks at its
+  // left neighbour, X[j] = max(M[j-1] - open, Y[j-1] - open, X[j-1] - extend), which in the frame X[j] + j * extend is a
+  // running maximum of t[j] = max(M[j-1], Y[j-1]) - open + j * extend: one scalar max per cell.  Every score is a multiple
+  // of 1/8 far below 2^21, so binary32 arithmetic is exact here and the re-association changes no value; the predecessor
+  // choices, ties included, are then taken cell by cell from the finished values exactly as pick3 takes them.
+  static thread_local std::vector<float> work;
+  static thread_local std::vector<int32_t> choice;
   static thread_local std::vector<uint8_t> from;
-  static thread_local std::vector<int8_t> rc, ac;
-  score.resize(6 * (size_t)W);
-  from.resize(cells);
-  rc.resize(L1); ac.resize(L2);
-  float *pM = score.data(), *pX = pM + W, *pY = pX + W, *cM = pY + W, *cX = cM + W, *cY = cX + W;
+  work.assign((size_t)P * 13, 0.0f);
+  choice.assign((size_t)P * 2, 0);
+  from.resize(cells + 16);
+  float *pM = work.data(), *pX = pM + P, *pY = pX + P, *cM = pY + P, *cX = cM + P, *cY = cX + P;
+  float *sub = cY + P;                      // [5][P]: pair score of alternate base code a against reference base j-1
+  float *t = sub + 5 * (size_t)P, *ramp = t + P;   // ramp[j] = j * extend
+  int32_t *wM = choice.data(), *wY = wM + P;
   pM[0] = 0.0f; pX[0] = -kLarge; pY[0] = -kLarge;
   for (int j = 1; j <= L1; j++) { pX[j] = -kGapOpen - (j - 1) * kGapExtend; pY[j] = -kLarge; pM[j] = -kLarge; }
-  for (int j = 0; j < L1; j++) rc[j] = (int8_t)base_code(ref_hap[j]);
-  for (int i = 0; i < L2; i++) ac[i] = (int8_t)base_code(alt_hap[i]);
+  for (int j = 1; j <= L1; j++) {
+    const int r = base_code(ref_hap[j - 1]);
+    for (int a = 0; a < 5; a++) sub[(size_t)a * P + j] = pair_score(r, a);
+  }
+  for (int j = 0; j < P; j++) ramp[j] = j * kGapExtend;
+  const __m128 open = _mm_set1_ps(kGapOpen), extend = _mm_set1_ps(kGapExtend);
   for (int i = 1; i <= L2; i++) {
     uint8_t* frow = from.data() + (size_t)i * W;
     cY[0] = -kGapOpen - (i - 1) * kGapExtend; cX[0] = -kLarge; cM[0] = -kLarge;
-    frow[0] = (uint8_t)(2 << 4);
-    const int a = ac[i - 1];
-    for (int j = 1; j <= L1; j++) {
-      int8_t wM, wX, wY;
-      cM[j] = pick3(pM[j - 1], pX[j - 1], pY[j - 1], &wM) + pair_score(rc[j - 1], a);
-      cX[j] = pick3(cM[j - 1] - kGapOpen, cX[j - 1] - kGapExtend, cY[j - 1] - kGapOpen, &wX);
-      cY[j] = pick3(pM[j] - kGapOpen, pX[j] - kGapOpen, pY[j] - kGapExtend, &wY);
-      frow[j] = (uint8_t)(wM | (wX << 2) | (wY << 4));
+    const float* srow = sub + (size_t)base_code(alt_hap[i - 1]) * P;
+    for (int j = 1; j <= L1; j += 4) {
+      __m128i wm, wy;
+      const __m128 m = pick3x4(_mm_loadu_ps(pM + j - 1), _mm_loadu_ps(pX + j - 1), _mm_loadu_ps(pY + j - 1), &wm);
+      const __m128 y = pick3x4(_mm_sub_ps(_mm_loadu_ps(pM + j), open), _mm_sub_ps(_mm_loadu_ps(pX + j), open),
+                               _mm_sub_ps(_mm_loadu_ps(pY + j), extend), &wy);
+      _mm_storeu_ps(cM + j, _mm_add_ps(m, _mm_loadu_ps(srow + j)));
+      _mm_storeu_ps(cY + j, y);
+      _mm_storeu_si128(reinterpret_cast<__m128i*>(wM + j), wm);
+      _mm_storeu_si128(reinterpret_cast<__m128i*>(wY + j), wy);
     }
+    for (int j = 1; j <= L1; j += 4) {
+      const __m128 s1 = _mm_sub_ps(_mm_loadu_ps(cM + j - 1), open), s3 = _mm_sub_ps(_mm_loadu_ps(cY + j - 1), open);
+      _mm_storeu_ps(t + j, _mm_add_ps(_mm_max_ps(s1, s3), _mm_loadu_ps(ramp + j)));
+    }
+    float run = cX[0];
+    for (int j = 1; j <= L1; j++) { run = run > t[j] ? run : t[j]; cX[j] = run - ramp[j]; }
+    for (int j = 1; j <= L1; j += 4) {
+      __m128i wx;
+      (void)pick3x4(_mm_sub_ps(_mm_loadu_ps(cM + j - 1), open), _mm_sub_ps(_mm_loadu_ps(cX + j - 1), extend),
+                    _mm_sub_ps(_mm_loadu_ps(cY + j - 1), open), &wx);
+      const __m128i f = _mm_or_si128(_mm_or_si128(_mm_loadu_si128(reinterpret_cast<const __m128i*>(wM + j)), _mm_slli_epi32(wx, 2)),
+                                     _mm_slli_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i*>(wY + j)), 4));
+      const int32_t four = _mm_cvtsi128_si32(_mm_packus_epi16(_mm_packs_epi32(f, f), _mm_setzero_si128()));
+      std::memcpy(frow + j, &four, 4);   // may spill up to 3 bytes into the next row, which is written after this one
+    }
+    frow[0] = (uint8_t)(2 << 4);
     std::swap(pM, cM); std::swap(pX, cX); std::swap(pY, cY);
   }
   // end-to-end alignment: stop in the corner (findOptimalStopEndPenalty)
@@ -463,9 +507,9 @@ int SeqStutterGenotyper::assemble_flanks() {
   for (int r = num_reads_ - 1; r >= 0; r--) first_read[sample_label_[r]] = r;
   for (int s = num_samples_ - 1; s >= 0; s--) first_read[s] = std::min(first_read[s], first_read[s + 1]);
   // the trace of every read against its best haplotype, looked up once for both flanks
-  std::vector<const AlignmentTrace*> read_trace(num_reads_, nullptr);
+  std::vector<int32_t> read_trace(num_reads_, -1);   // slot in trace_cache_: reads of one pool share their trace
   for (int r = 0; r < num_reads_; r++)
-    if (seed_positions_[r] >= 0) read_trace[r] = &trace_cache_.at(std::make_pair(pool_index_[r], best_hap_of_read(r)));
+    if (seed_positions_[r] >= 0) read_trace[r] = trace_cache_.slot_of(std::make_pair(pool_index_[r], best_hap_of_read(r)));
   for (int flank = 0; flank < 2; flank++) {
     const int block_index = flank == 0 ? 0 : (int)hap_blocks_.size() - 1;
     const std::string& ref_seq = hap_blocks_[block_index].seqs[0];
@@ -480,14 +524,18 @@ int SeqStutterGenotyper::assemble_flanks() {
     struct FlankInfo {
       std::string_view seq;
       bool in_reference = false;
-      std::vector<std::string_view> nonref_edges;
+      std::vector<int> nonref_edges;   // ids (below) of its (k+1)-mers that are not reference edges, one per occurrence
       int stamp = -1, count = 0;   // sample that saw it last, reads of that sample carrying it
     };
     std::unordered_map<std::string_view, FlankInfo> flank_info;
-    std::vector<FlankInfo*> read_info(num_reads_, nullptr);
+    std::unordered_map<std::string_view, int> edge_id;   // the locus' distinct non-reference (k+1)-mers
+    std::vector<FlankInfo*> read_info(num_reads_, nullptr), trace_info(trace_cache_.size(), nullptr);
+    std::vector<uint8_t> trace_seen(trace_cache_.size(), 0);
     for (int r = 0; r < num_reads_; r++) {
-      if (!read_trace[r]) continue;
-      const std::string_view sv = read_trace[r]->flank_seq(block_index);
+      if (read_trace[r] < 0) continue;
+      if (trace_seen[read_trace[r]]) { read_info[r] = trace_info[read_trace[r]]; continue; }
+      trace_seen[read_trace[r]] = 1;
+      const std::string_view sv = trace_cache_.in_slot(read_trace[r]).flank_seq(block_index);
       if (sv.empty()) continue;
       auto it = flank_info.find(sv);
       if (it == flank_info.end()) {
@@ -497,17 +545,17 @@ int SeqStutterGenotyper::assemble_flanks() {
         if (!fi.in_reference)
           for (size_t c = 0; c + kmer_length + 1 <= sv.size(); c++) {
             const std::string_view e = sv.substr(c, kmer_length + 1);
-            if (ref_seq.find(e) == std::string::npos) fi.nonref_edges.push_back(e);
+            if (ref_seq.find(e) == std::string::npos) fi.nonref_edges.push_back(edge_id.emplace(e, (int)edge_id.size()).first->second);
           }
         it = flank_info.emplace(sv, std::move(fi)).first;
       }
-      read_info[r] = &it->second;
+      read_info[r] = trace_info[read_trace[r]] = &it->second;
     }
     std::map<std::string, int> haplotype_indexes;           // alternate flank -> index
     std::vector<std::vector<int> > haplotype_to_sample;     // samples supporting each alternate flank
     std::vector<std::pair<std::string, int> > assembly_data;
     std::vector<FlankInfo*> flank_seqs;                     // the sample's distinct flank sequences in read order
-    std::vector<std::pair<std::string_view, int> > edges;
+    std::vector<int> edge_weight(edge_id.size(), 0), edge_stamp(edge_id.size(), -1);
     for (int s = 0; s < num_samples_; s++) {
       if (!call_sample_[s].empty()) continue;
       assembly_data.clear();
@@ -530,25 +578,20 @@ int SeqStutterGenotyper::assemble_flanks() {
         // and every other edge is pruned below weight max(2, ceil(0.02 * strings)) (prune_edges, debruijn_graph.cpp:47-60).
         // If no non-reference (k+1)-mer of the sample's reads reaches that weight at k = kmer_length, pruning leaves the
         // bare reference path -- acyclic at that k, one source-to-sink path -- and the loop below would stop at its
-        // first k with nothing to report.  Checking that needs a sort of a few substrings, not a graph.
+        // first k with nothing to report.  Checking that needs a tally over the interned (k+1)-mers, not a graph.
         const int k = kmer_length;
-        int num_strings = 1;
-        edges.clear();
+        int num_strings = 1, heaviest = 0;
         for (const FlankInfo* fi : flank_seqs) {
           if ((int)fi->seq.size() <= k) continue;
           num_strings += fi->count;
-          for (const std::string_view& e : fi->nonref_edges) edges.emplace_back(e, fi->count);
+          for (const int e : fi->nonref_edges) {
+            if (edge_stamp[e] != s) { edge_stamp[e] = s; edge_weight[e] = 0; }
+            edge_weight[e] += fi->count;
+            heaviest = std::max(heaviest, edge_weight[e]);   // weights only grow: the last maximum is the final one
+          }
         }
         const int min_weight = std::max(2, (int)std::ceil(0.02 * num_strings));
-        std::sort(edges.begin(), edges.end());
-        bool survives = false;
-        for (size_t i = 0; i < edges.size() && !survives;) {
-          size_t j = i;
-          int weight = 0;
-          while (j < edges.size() && edges[j].first == edges[i].first) weight += edges[j++].second;
-          survives = weight >= min_weight;
-          i = j;
-        }
+        const bool survives = heaviest >= min_weight;
         if (!survives) continue;
       }
       for (int k = kmer_length; k <= max_k; k++) {

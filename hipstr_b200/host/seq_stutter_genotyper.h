@@ -88,6 +88,8 @@ class TraceCache {
   typedef std::pair<int, int> Key;
   size_t count(const Key& k) const { return index_.count(pack(k)); }
   const AlignmentTrace& at(const Key& k) const { return items_[index_.at(pack(k))].second; }
+  int32_t slot_of(const Key& k) const { return index_.at(pack(k)); }            /* position in insertion order */
+  const AlignmentTrace& in_slot(int32_t i) const { return items_[i].second; }
   AlignmentTrace& operator[](const Key& k) {
     auto it = index_.find(pack(k));
     if (it != index_.end()) return items_[it->second].second;
