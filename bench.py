@@ -467,7 +467,7 @@ def main():
     ap.add_argument("--reads-per-sample", type=int, default=30)
     ap.add_argument("--alleles", type=int, default=8)
     ap.add_argument("--read-len", type=int, default=150)
-    ap.add_argument("--loop-loci", type=int, default=0, help="loci of the shared list of full_loop (default: --loci at N=1, 2000 at N>1)")
+    ap.add_argument("--loop-loci", type=int, default=0, help="loci of the shared list of full_loop (default: --loci at N=1, 1000 per GPU at N>1: enough windows for every pipeline)")
     ap.add_argument("--pipelines", type=int, default=4)
     ap.add_argument("--window", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -524,7 +524,7 @@ def main():
     s = hb.Synth(n_loci=a.loci, n_samples=a.samples, reads_per_sample=a.reads_per_sample, n_alleles=a.alleles,
                  read_len=a.read_len, seed=2000 + (0 if loop_only else rank))
     # the loop's shared list: the same loci on every rank (windows are dealt dynamically, any rank may get any window)
-    loop_loci = a.loop_loci or (a.loci if (world == 1 or loop_only) else 2000)
+    loop_loci = a.loop_loci or (a.loci if (world == 1 or loop_only) else max(2000, 1000 * world))
     s_loop = s if (world == 1 or loop_only) and loop_loci == a.loci else None
     if s_loop is None and not a.no_full_loop:
         s_loop = hb.Synth(n_loci=loop_loci, n_samples=a.samples, reads_per_sample=a.reads_per_sample, n_alleles=a.alleles,

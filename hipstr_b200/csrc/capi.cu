@@ -40,7 +40,7 @@ struct DevBuf {
 };
 
 struct hipstr_dev_batch {
-  DevBuf pools, bases, quals, hapsides, hapbytes, blocks, reps, progs, logrun, tabs, mask, jobs[kNumColVariants];
+  DevBuf pools, bases, quals, hapsides, hapbytes, blocks, reps, progs, tabs, mask, jobs[kNumColVariants];
   DevBuf slot_reps, stut_jobs, pool_t_off;      // K1a: stutter-table slots, jobs, slab offsets
   std::vector<FlatBatch::Chunk> chunks;         // pool ranges whose stutter tables fit the table buffer
   int32_t stut_n_max = 16;
@@ -50,7 +50,7 @@ struct hipstr_dev_batch {
   bool has_mask = false;
   void release() {
     pools.release(); bases.release(); quals.release(); hapsides.release(); hapbytes.release();
-    blocks.release(); reps.release(); progs.release(); logrun.release(); tabs.release(); mask.release();
+    blocks.release(); reps.release(); progs.release(); tabs.release(); mask.release();
     slot_reps.release(); stut_jobs.release(); pool_t_off.release();
     for (auto& j : jobs) j.release();
   }
@@ -198,7 +198,6 @@ hipstr_status_t stage(hipstr_ctx* ctx, const hipstr_align_batch_t* batch, hipstr
   CU(put(d.blocks, f.blocks, s));
   CU(put(d.reps, f.reps, s));
   CU(put(d.progs, f.progs, s));
-  CU(put(d.logrun, f.prog_logrun, s));
   CU(put(d.tabs, f.rep_tabs, s));
   CU(put(d.mask, f.hap_mask, s));
   CU(put(d.slot_reps, f.slot_reps, s));
@@ -231,7 +230,6 @@ hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll
   p.blocks = (const DevBlock*)d.blocks.p;
   p.reps = (const DevRep*)d.reps.p;
   p.progs = (const DevProgEntry*)d.progs.p;
-  p.prog_logrun = (const double*)d.logrun.p;
   p.rep_tabs = (const int32_t*)d.tabs.p;
   p.hap_mask = d.has_mask ? (const uint8_t*)d.mask.p : nullptr;
   p.qual_lut = ctx->d_qual_lut;
@@ -259,7 +257,7 @@ hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll
   sp.n_max = d.stut_n_max;
   sp.pools = p.pools; sp.bases = p.bases; sp.quals = p.quals;
   sp.slot_reps = (const DevSlotReps*)d.slot_reps.p;
-  sp.reps = p.reps; sp.progs = p.progs; sp.prog_logrun = p.prog_logrun; sp.rep_tabs = p.rep_tabs;
+  sp.reps = p.reps; sp.progs = p.progs; sp.rep_tabs = p.rep_tabs;
   sp.qual_lut = p.qual_lut; sp.int_logs = p.int_logs;
   sp.pool_t_off = p.pool_t_off;
   sp.stut = (double*)ctx->d_stut.p;
@@ -1139,7 +1137,6 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   CU(put(d.blocks, f.blocks, s));
   CU(put(d.reps, f.reps, s));
   CU(put(d.progs, f.progs, s));
-  CU(put(d.logrun, f.prog_logrun, s));
   CU(put(d.tabs, f.rep_tabs, s));
   CU(put(d.slot_reps, f.slot_reps, s));
   DevBuf* m = ctx->d_misc;
@@ -1239,7 +1236,7 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   sp.jobs = (const DevStutJob*)m[5].p; sp.n_jobs = (int32_t)stut_jobs.size(); sp.n_max = stut_n_max;
   sp.pools = p.pools; sp.bases = p.bases; sp.quals = p.quals;
   sp.slot_reps = (const DevSlotReps*)d.slot_reps.p; sp.reps = (const DevRep*)d.reps.p;
-  sp.progs = (const DevProgEntry*)d.progs.p; sp.prog_logrun = (const double*)d.logrun.p; sp.rep_tabs = (const int32_t*)d.tabs.p;
+  sp.progs = (const DevProgEntry*)d.progs.p; sp.rep_tabs = (const int32_t*)d.tabs.p;
   sp.qual_lut = ctx->d_qual_lut; sp.int_logs = ctx->d_int_logs;
   sp.stut = (double*)ctx->d_stut.p; sp.stut_pos = (int32_t*)ctx->d_stut_pos.p;
   sp.job_t_off = (const int64_t*)m[6].p;
@@ -1248,7 +1245,7 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   AlignParams ap;
   std::memset(&ap, 0, sizeof(ap));
   ap.pools = p.pools; ap.bases = p.bases; ap.quals = p.quals; ap.hapsides = p.hapsides; ap.hapbytes = p.hapbytes;
-  ap.blocks = p.blocks; ap.reps = sp.reps; ap.progs = sp.progs; ap.prog_logrun = sp.prog_logrun; ap.rep_tabs = sp.rep_tabs;
+  ap.blocks = p.blocks; ap.reps = sp.reps; ap.progs = sp.progs; ap.rep_tabs = sp.rep_tabs;
   ap.qual_lut = ctx->d_qual_lut; ap.trans = ctx->d_trans; ap.int_logs = ctx->d_int_logs;
   ap.l_max = l_all; ap.last_scratch = (double*)ctx->d_last.p;
   ap.stut = (const double*)ctx->d_stut.p; ap.stut_pos = (const int32_t*)ctx->d_stut_pos.p;

@@ -73,6 +73,17 @@ __device__ __forceinline__ double lse_term_near(double v, double mx) {
   const float e = __uint_as_float(__float2uint_rz(__fmul_rn(8388608.0f, __fadd_rn(x, 126.94269504f))));
   return diff > HIPSTR_LOG_THRESH ? (double)e : 0.0;
 }
+// ... and when the caller also knows whether the slot holds a term at all: one 32-bit select on the float instead of
+// two 64-bit ones ((double)0.0f is +0.0, so the sum sees the same addend)
+__device__ __forceinline__ double lse_term_masked(double v, double mx, bool valid) {
+  const double diff = v - mx;
+  const float x = __fmul_rn(1.442695040f, __double2float_rn(diff));
+  const unsigned bits = __float2uint_rz(__fmul_rn(8388608.0f, __fadd_rn(x, 126.94269504f)));
+  unsigned kept;
+  asm("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %4, 0;\n\tsetp.gt.and.f64 p, %2, %3, q;\n\tselp.b32 %0, %1, 0, p;\n\t}"
+      : "=r"(kept) : "r"(bits), "d"(diff), "d"(HIPSTR_LOG_THRESH), "r"((int)valid));
+  return (double)__uint_as_float(kept);
+}
 __device__ __forceinline__ double lse_finish(double mx, double total) {
   return mx + (double)coarse_log(__double2float_rn(total));
 }

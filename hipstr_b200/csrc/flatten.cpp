@@ -128,7 +128,7 @@ void parallel_run(size_t n, int workers, const std::function<void(size_t)>& fn) 
 
 void FlatBatch::clear() {
   pools.clear(); bases.clear(); quals.clear();
-  hapsides.clear(); hapbytes.clear(); blocks.clear(); reps.clear(); progs.clear(); prog_logrun.clear(); rep_tabs.clear(); hap_mask.clear();
+  hapsides.clear(); hapbytes.clear(); blocks.clear(); reps.clear(); progs.clear(); rep_tabs.clear(); hap_mask.clear();
   for (auto& j : jobs) j.clear();
   slot_reps.clear(); locus_slot0.clear(); stut_jobs.clear(); pool_t_off.clear(); chunks.clear();
   stut_n_max = 16;
@@ -354,7 +354,6 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
     std::vector<DevBlock> blocks;
     std::vector<DevRep> reps;
     std::vector<DevProgEntry> progs;
-    std::vector<double> prog_logrun;
     std::vector<int32_t> rep_tabs;
     std::vector<DevSlotReps> slot_reps;
   };
@@ -433,9 +432,12 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
               for (int i = k2 * p; i < B; i++) runs[k2 - 1][i] = sq[i - k2 * p] != sq[i] ? 0 : 1 + runs[k2 - 1][i - 1];
             const int VB = HIPSTR_VAL_STRIDE * 8;   // bytes per read column of the emission table
             auto emit_entry = [&](int pos, int off_a, int off_b, int moves, double logrun) {
-              DevProgEntry e = {pos, off_a, off_b, moves};
+              DevProgEntry e;
+              e.pos = pos;
+              e.moves = moves;
+              if (moves) { e.off_a = off_a; e.off_b = off_b; }
+              else e.logrun = logrun;
               out.progs.push_back(e);
-              out.prog_logrun.push_back(logrun);
             };
             const int zero = 0;
             const HostTables& T = host_tables();
@@ -654,14 +656,17 @@ hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std
       out.blocks.insert(out.blocks.end(), p.blocks.begin(), p.blocks.end());
       out.reps.insert(out.reps.end(), p.reps.begin(), p.reps.end());
       out.progs.insert(out.progs.end(), p.progs.begin(), p.progs.end());
-      out.prog_logrun.insert(out.prog_logrun.end(), p.prog_logrun.begin(), p.prog_logrun.end());
       out.rep_tabs.insert(out.rep_tabs.end(), p.rep_tabs.begin(), p.rep_tabs.end());
       p = Lowered();
     }
   }
 
   // the kernel prefetches two program entries ahead: pad the arrays
-  for (int k = 0; k < 2; k++) { DevProgEntry e = {-(1 << 30), 0, 0, 0}; out.progs.push_back(e); out.prog_logrun.push_back(0.0); }
+  for (int k = 0; k < 2; k++) {
+    DevProgEntry e;
+    e.pos = -(1 << 30); e.moves = 0; e.logrun = 0.0;
+    out.progs.push_back(e);
+  }
 
   // ---- pooled reads: offsets (serial prefix), then a threaded fill of the big byte arrays ----
   const int n_pools = b->n_pools;

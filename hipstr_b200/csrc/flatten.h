@@ -77,7 +77,6 @@ struct FlatBatch {
   std::vector<DevBlock> blocks;
   std::vector<DevRep> reps;
   std::vector<DevProgEntry> progs;
-  std::vector<double> prog_logrun;
   std::vector<int32_t> rep_tabs;
   std::vector<uint8_t> hap_mask;             /* empty = all haplotypes */
   HostBuf<DevJob> jobs[kNumColVariants];

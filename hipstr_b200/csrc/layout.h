@@ -72,18 +72,23 @@ struct DevBlock {         /* 16 B */
  * every read column replays it: no data-dependent pointer chasing on the device, and the next
  * step can be prefetched while the current one is applied.
  *
- * Every step has the same shape:
- *     if (moves) lp = (lp - val[col + off_a]) + val[col + off_b];   term = lp + logrun
- * where val is the per-read emission table with HIPSTR_VAL_STRIDE doubles per read column (base
- * codes 0..4) and logrun = 0.0 unless the step is a collapsed run (x + 0.0 is exact).  Offsets are
- * BYTES relative to the table entry of the column the walk started at (insertion walks: relative
- * to column j - period, the first base an inserted copy overwrites). */
+ * A step is one of two things, told apart by `moves` (uniform across the warp that replays the walk):
+ *     moves != 0:  lp = (lp - val[col + off_a]) + val[col + off_b];   term = lp
+ *     moves == 0:  term = lp + logrun      -- a run of positions that all share lp, collapsed by the reference into one
+ *                                             term with int_log(run length) added; logrun = 0.0 where nothing is added
+ * where val is the per-read emission table with HIPSTR_VAL_STRIDE doubles per read column (base codes 0..4).  A step
+ * never does both, so the two offsets and the double share the same 8 bytes and a step is ONE 16-byte load.  Offsets
+ * are BYTES relative to the table entry of the column the walk started at (insertion walks: relative to column
+ * j - period, the first base an inserted copy overwrites). */
 #define HIPSTR_VAL_STRIDE 5   /* odd stride in 8-byte words: consecutive columns fall in distinct banks */
 struct DevProgEntry {     /* 16 B */
   int32_t pos;            /* artifact position i (<= 0, offset from the right end of the block); the
                              terminal entry of a walk holds the position where the walk stops */
-  int32_t off_a, off_b;   /* byte offsets into val of the emission to remove / to add */
   int32_t moves;          /* 1 if the step changes lp (insertions repeat it once per inserted copy) */
+  union {
+    struct { int32_t off_a, off_b; };   /* moves != 0: byte offsets into val of the emission to remove / to add */
+    double logrun;                      /* moves == 0: added to lp for this step's term */
+  };
 };
 
 struct DevRep {           /* 168 B */
@@ -92,7 +97,7 @@ struct DevRep {           /* 168 B */
   int32_t period;
   int32_t n_del;          /* StutterAlignerClass num_deletions_ */
   int32_t left_align;     /* !reversed (RepeatBlock.h:28,41); only the traceback uses it */
-  int32_t prog_off[7];    /* into progs / prog_logrun: [0] insertion walk (lag = period), [k] deletion of k units */
+  int32_t prog_off[7];    /* into progs: [0] insertion walk (lag = period), [k] deletion of k units */
   int32_t diag_off;       /* into rep_tabs: B byte offsets of the right-anchored diagonal,
                              entry t = emission of column q - t against allele base B-1-t, relative to column q */
   int32_t ins_off;        /* into rep_tabs: 6*period byte offsets of the periodic-copy sum
@@ -136,7 +141,6 @@ struct AlignParams {
   const DevBlock* blocks;
   const DevRep* reps;
   const DevProgEntry* progs;
-  const double* prog_logrun;   /* parallel to progs: int_log(run length) of a collapsed step, else 0.0 */
   const int32_t* rep_tabs;
   const uint8_t* hap_mask;   /* per global hap index; NULL = all */
   const double* qual_lut;    /* [256][2]: log_correct, log_error by quality byte */
@@ -169,7 +173,6 @@ struct StutParams {          /* K1a */
   const DevSlotReps* slot_reps;
   const DevRep* reps;
   const DevProgEntry* progs;
-  const double* prog_logrun;
   const int32_t* rep_tabs;
   const double* qual_lut;
   const double* int_logs;

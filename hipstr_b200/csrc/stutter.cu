@@ -37,12 +37,13 @@ namespace hipstr {
 
 #define STUT_THREADS 128
 #define STUT_WARPS (STUT_THREADS / 32)
+#ifndef STUT_TERM_SLOTS
 #define STUT_TERM_SLOTS 16                      /* terms of one walk kept in shared memory per lane */
+#endif
 #define STUT_TERM_STRIDE 256                    /* bytes between two slots of one lane (32 lanes x 8) */
 
 struct StutCtx {
   const DevProgEntry* progs;
-  const double* logrun;
   const int32_t* diag;       // byte offsets of the right-anchored diagonal (DevRep::diag_off)
   const int32_t* ins_tab;    // byte offsets of the periodic-copy sum (DevRep::ins_off)
   const DevRep* rep;
@@ -54,18 +55,31 @@ struct StutCtx {
   int B, p, n_side;
 };
 
-// one step of a walk's chain: lp = (lp - val[col + off_a]) + val[col + off_b], `units` times for insertions
+// One step of a walk (layout.h DevProgEntry as int4: x = pos, y = moves, then z / w = the two offsets or the double):
+// either lp = (lp - val[col + off_a]) + val[col + off_b], `units` times for insertions, and the term is lp itself, or
+// the term is lp + logrun.  `moves` is the same for the whole warp.  The term goes to its shared-memory slot (when the
+// walk still has one) and into the running maximum; both arms do that themselves so that neither copies a double.
 template <bool INS>
-__device__ __forceinline__ void stut_move(double& lp, unsigned col, const int4& e, int units, int stride) {
-  if (INS) {
-    unsigned a = col + e.y, b = col + e.z;
-    for (int m = 0; m < units; m++, a -= stride, b -= stride) {
-      lp -= lds_f64(a);
-      lp += lds_f64(b);
+__device__ __forceinline__ void stut_step(double& lp, double& mx, unsigned col, const int4& e, int units, int stride, bool keep,
+                                          unsigned slot) {
+  if (e.y) {
+    if (INS) {
+      unsigned a = col + e.z, b = col + e.w;
+#pragma unroll 2
+      for (int m = 0; m < units; m++, a -= stride, b -= stride) {
+        lp -= lds_f64(a);
+        lp += lds_f64(b);
+      }
+    } else {
+      lp -= lds_f64(col + e.z);
+      lp += lds_f64(col + e.w);
     }
+    if (keep) sts_f64(slot, lp);
+    mx = dmax(mx, lp);
   } else {
-    lp -= lds_f64(col + e.y);
-    lp += lds_f64(col + e.z);
+    const double term = lp + __hiloint2double(e.w, e.z);
+    if (keep) sts_f64(slot, term);
+    mx = dmax(mx, term);
   }
 }
 
@@ -79,7 +93,6 @@ template <bool INS, bool TRACE>
 __device__ __forceinline__ double stut_walk(const StutCtx& c, int prog_index, int stop, int j, int units, double lp0,
                                             int tail_base, int& best_pos) {
   const int4* prog = reinterpret_cast<const int4*>(c.progs + prog_index);
-  const double* lr = c.logrun + prog_index;
   const unsigned col = c.val + (INS ? (j - c.p) : j) * HIPSTR_COL_BYTES;
   const int stride = c.p * HIPSTR_COL_BYTES;
   const int warp_stop = __reduce_min_sync(FULL, stop);
@@ -89,29 +102,24 @@ __device__ __forceinline__ double stut_walk(const StutCtx& c, int prog_index, in
   sts_f64(c.terms, lp0);
   int cnt = 0, s = 0;
   unsigned slot = c.terms;
+  const int4* pe = prog;
   // two entries per trip: no register shuffling for the look-ahead, half the loop overhead
   for (;;) {
-    const int4 e0 = __ldg(prog + s), e1 = __ldg(prog + s + 1);
-    const double r0 = __ldg(lr + s), r1 = __ldg(lr + s + 1);
+    const int4 e0 = __ldg(pe), e1 = __ldg(pe + 1);
     if (e0.x <= warp_stop) break;
     if (e0.x > stop) {
-      if (e0.w) stut_move<INS>(lp, col, e0, units, stride);
-      const double term = lp + r0;
-      if (s + 1 < STUT_TERM_SLOTS) sts_f64(slot + STUT_TERM_STRIDE, term);
-      mx = dmax(mx, term);
+      stut_step<INS>(lp, mx, col, e0, units, stride, s + 1 < STUT_TERM_SLOTS, slot + STUT_TERM_STRIDE);
       cnt++;
       if (TRACE && (lp > best || (left_align && lp == best))) { best_pos = -e1.x; best = lp; }
     }
     if (e1.x <= warp_stop) { s += 1; break; }
     if (e1.x > stop) {
-      if (e1.w) stut_move<INS>(lp, col, e1, units, stride);
-      const double term = lp + r1;
-      if (s + 2 < STUT_TERM_SLOTS) sts_f64(slot + 2 * STUT_TERM_STRIDE, term);
-      mx = dmax(mx, term);
+      stut_step<INS>(lp, mx, col, e1, units, stride, s + 2 < STUT_TERM_SLOTS, slot + 2 * STUT_TERM_STRIDE);
       cnt++;
-      if (TRACE && (lp > best || (left_align && lp == best))) { best_pos = -__ldg(&prog[s + 2].x); best = lp; }
+      if (TRACE && (lp > best || (left_align && lp == best))) { best_pos = -__ldg(&pe[2].x); best = lp; }
     }
     s += 2;
+    pe += 2;
     slot += 2 * STUT_TERM_STRIDE;
   }
   // the entry this lane stopped at tells how many artifact positions are left (they all share lp)
@@ -126,21 +134,20 @@ __device__ __forceinline__ double stut_walk(const StutCtx& c, int prog_index, in
   const int n = cnt + 1;                                  // cached terms of this lane (slot 0 = lp0)
   const int n_warp = min(s + 1, STUT_TERM_SLOTS);
   slot = c.terms;
-  for (int t = 0; t < n_warp; t++, slot += STUT_TERM_STRIDE) {   // branch-free: a slot this lane did not fill counts as -inf
-    const double v = lds_f64(slot);
-    total += lse_term_near(t < n ? v : -1.0e300, mx);
-  }
+#pragma unroll 4
+  for (int t = 0; t < n_warp; t++, slot += STUT_TERM_STRIDE)     // branch-free: a slot this lane did not fill adds 0
+    total += lse_term_masked(lds_f64(slot), mx, t < n);
   if (n > STUT_TERM_SLOTS) {   // rare: a walk longer than the cache -> replay it for the terms that did not fit
     lp = lp0;
     for (int t = 0; t < cnt; t++) {
       const int4 e = __ldg(prog + t);
-      if (e.w) stut_move<INS>(lp, col, e, units, stride);
-      if (t + 1 >= STUT_TERM_SLOTS) total += lse_term_near(lp + __ldg(lr + t), mx);
+      double term = lp + __hiloint2double(e.w, e.z), unused = 0.0;
+      if (e.y) { stut_step<INS>(lp, unused, col, e, units, stride, false, 0); term = lp; }
+      if (t + 1 >= STUT_TERM_SLOTS) total += lse_term_near(term, mx);
     }
   }
   return lse_finish(mx, total);
 }
-
 // The 13 table entries of one read column (HapAligner.cpp:76-100 without pre_prob).  On entry the deletion rows of
 // the table hold what pass 1 left there: match_probs_[q] - del_probs_[q][k-1] for q = j + k*period inside the read, or
 // the whole first term (prior included) where the read ends before q.
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(STUT_THREADS, STUT_MIN_CTAS) k_stutter(const S
       int32_t* pside = TRACE ? P.stut_pos + t_off + (size_t)(job.tslot0 + s) * HIPSTR_NUM_ARTIFACTS * pitch + gbase : nullptr;
       const DevRep* rep = P.reps + (side ? sr.rep_rev : sr.rep_fwd);
       StutCtx c;
-      c.progs = P.progs; c.logrun = P.prog_logrun; c.rep = rep; c.int_logs = P.int_logs;
+      c.progs = P.progs; c.rep = rep; c.int_logs = P.int_logs;
       c.diag = P.rep_tabs + __ldg(&rep->diag_off); c.ins_tab = P.rep_tabs + __ldg(&rep->ins_off);
       c.val = val_addr + gbase * HIPSTR_COL_BYTES; c.code = s_code + gbase; c.match = s_match;
       c.terms = terms_addr;

@@ -1,8 +1,10 @@
 set -x
-mkdir -p gpurun_out/r2b
-nproc
-timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/r2b/gpu_all.log 2>&1
-tail -6 gpurun_out/r2b/gpu_all.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2b/smoke.log 2>&1; tail -2 gpurun_out/r2b/smoke.log
-python bench.py --workload loop --loci 2000 --steps 3 --warmup 3 > gpurun_out/r2b/loop_n1.json 2> gpurun_out/r2b/loop_n1.err; tail -c 400 gpurun_out/r2b/loop_n1.err; cat gpurun_out/r2b/loop_n1.json
-python bench.py > gpurun_out/r2b/bench_default.json 2> gpurun_out/r2b/bench_default.err; tail -c 300 gpurun_out/r2b/bench_default.err; cat gpurun_out/r2b/bench_default.json
+mkdir -p gpurun_out/r2d
+cp hipstr_b200/libhipstr_b200.so /tmp/lib_keep.so
+for v in base s18 s20 i4 kl1 base; do
+  cp tools/_variants/libhipstr_b200_$v.so hipstr_b200/libhipstr_b200.so
+  echo "== $v" >> gpurun_out/r2d/variants3.log
+  python tools/quick_time.py 200 8 4 2>&1 | grep "run 3\|checksum" >> gpurun_out/r2d/variants3.log
+done
+cp /tmp/lib_keep.so hipstr_b200/libhipstr_b200.so
+cat gpurun_out/r2d/variants3.log
