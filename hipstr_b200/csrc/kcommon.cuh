@@ -13,6 +13,13 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 
 // Shared-memory accesses of the hot loops use explicit 32-bit shared-window addresses: the compiler
 // otherwise rebuilds the generic->shared base (S2UR/ULEA) inside the loop.
+// a >= 0 ? x : y as one select the compiler cannot turn back into a branch around the code that computes x (it otherwise
+// sinks the loads feeding x into that branch, where each waits for the previous one's consumer)
+__device__ __forceinline__ double select_if_nonneg(int a, double x, double y) {
+  double v;
+  asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\tselp.f64 %0, %2, %3, p;\n\t}" : "=d"(v) : "r"(a), "d"(x), "d"(y));
+  return v;
+}
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));

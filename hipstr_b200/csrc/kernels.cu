@@ -27,6 +27,8 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 #include <stdlib.h>
 
 #include "../../include/hipstr_b200.h"
@@ -259,40 +261,47 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const
           for (int t = 0; t < steps; t++) {
             const double rI = shfl_up_d(pubI), rM = shfl_up_d(pubM), rD = shfl_up_d(pubD);
             const int r = t - k;
-            if (flank_on && r >= 0 && r < nrows) {
-              const int row = r0 + r;
+            const bool live = flank_on && r >= 0 && r < nrows;
+            const int row = r0 + r;
+            const uint8_t info = live ? __ldg(rows + row) : 0;
+            // the first row after a repeat block is a different recurrence (HapAligner.cpp:129-139); one row per side and
+            // haplotype is such a row, so the cells carry its selects only in the steps where some lane stands on one
+            const bool some_after = __any_sync(FULL, (info & HIPSTR_ROW_AFTER_REPEAT) != 0);
+            if (live) {
               const uint8_t hc = __ldg(seq + row);
-              const uint8_t info = __ldg(rows + row);
               const int hp = info & 15;
               const bool after = (info & HIPSTR_ROW_AFTER_REPEAT) != 0;
               const double m2m = __ldg(P.trans + hp), m2i = __ldg(P.trans + 16 + hp), m2d = __ldg(P.trans + 32 + hp);
               double Ileft = rI, Mdiag = Mlp, Ddiag = Dlp;
+              auto cells = [&](auto with_after) {
 #pragma unroll
-              for (int cc = 0; cc < C; cc++) {
-                const double e = bs[cc] == hc ? lc[cc] : lw[cc];
-                const double Mup = Mp[cc], Dup = Dp[cc];
-                const bool col0 = (cc == 0) && (k == 0);
-                double Mn = e + dmax(Ileft + m2i, dmax(Mdiag + m2m, Ddiag + m2d));
-                double In = lc[cc] + dmax(Mdiag + LOG_INS_TO_MATCH, Ileft + LOG_INS_TO_INS);
-                double Dn = dmax(Mup + LOG_DEL_TO_MATCH, Dup + LOG_DEL_TO_DEL);
-                if (col0) { Mn = e; In = lc[cc]; }
-                if (after) {   // first row after a repeat block (HapAligner.cpp:129-139)
-                  Mn = col0 ? e : e + Mdiag;
-                  In = IMPOSSIBLE;
-                  Dn = IMPOSSIBLE;
+                for (int cc = 0; cc < C; cc++) {
+                  const double e = bs[cc] == hc ? lc[cc] : lw[cc];
+                  const double Mup = Mp[cc], Dup = Dp[cc];
+                  const bool col0 = (cc == 0) && (k == 0);
+                  double Mn = e + dmax(Ileft + m2i, dmax(Mdiag + m2m, Ddiag + m2d));
+                  double In = lc[cc] + dmax(Mdiag + LOG_INS_TO_MATCH, Ileft + LOG_INS_TO_INS);
+                  double Dn = dmax(Mup + LOG_DEL_TO_MATCH, Dup + LOG_DEL_TO_DEL);
+                  if (col0) { Mn = e; In = lc[cc]; }
+                  if (decltype(with_after)::value && after) {
+                    Mn = col0 ? e : e + Mdiag;
+                    In = IMPOSSIBLE;
+                    Dn = IMPOSSIBLE;
+                  }
+                  if (TRACE && j0 + cc < ncol) {   // what retrace would choose standing on this cell, from the very values it would read
+                    const bool rev = side != 0;
+                    const int choice = col0 ? (pick2(rev, Dup + LOG_DEL_TO_DEL, Mup + LOG_DEL_TO_MATCH) << 2)
+                                            : (pick3(rev, Ileft + m2i, Ddiag + m2d, Mdiag + m2m) |
+                                               (pick2(rev, Dup + LOG_DEL_TO_DEL, Mup + LOG_DEL_TO_MATCH) << 2) |
+                                               (pick2(rev, Ileft + LOG_INS_TO_INS, Mdiag + LOG_INS_TO_MATCH) << 3));
+                    dec_side[(size_t)row * ncol + j0 + cc] = (unsigned char)choice;
+                  }
+                  Mdiag = Mup; Ddiag = Dup; Ileft = In;
+                  Mp[cc] = Mn; Dp[cc] = Dn;
+                  if (cc == last_cc) s_last[side * L + row] = Mn;
                 }
-                if (TRACE && j0 + cc < ncol) {   // what retrace would choose standing on this cell, from the very values it would read
-                  const bool rev = side != 0;
-                  const int choice = col0 ? (pick2(rev, Dup + LOG_DEL_TO_DEL, Mup + LOG_DEL_TO_MATCH) << 2)
-                                          : (pick3(rev, Ileft + m2i, Ddiag + m2d, Mdiag + m2m) |
-                                             (pick2(rev, Dup + LOG_DEL_TO_DEL, Mup + LOG_DEL_TO_MATCH) << 2) |
-                                             (pick2(rev, Ileft + LOG_INS_TO_INS, Mdiag + LOG_INS_TO_MATCH) << 3));
-                  dec_side[(size_t)row * ncol + j0 + cc] = (unsigned char)choice;
-                }
-                Mdiag = Mup; Ddiag = Dup; Ileft = In;
-                Mp[cc] = Mn; Dp[cc] = Dn;
-                if (cc == last_cc) s_last[side * L + row] = Mn;
-              }
+              };
+              if (some_after) cells(std::true_type()); else cells(std::false_type());
               Mlp = rM; Dlp = rD;
               pubM = Mp[C - 1]; pubI = Ileft; pubD = Dp[C - 1];
             }
@@ -329,17 +338,17 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const
           }
           const double* tcol = t_pool + (size_t)tslot * HIPSTR_NUM_ARTIFACTS * t_pitch + g;
           const double* prev = s_rowbuf + (gs ? nL : 0);
+          // all 13 table loads first, with nothing between them that waits for one: they are in flight together.  The
+          // entries of impossible sizes are allocated but never written (K1a skips them); they are loaded and dropped.
           double probs[HIPSTR_NUM_ARTIFACTS];
+#pragma unroll
+          for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) probs[a] = __ldg(tcol + a * t_pitch);
 #pragma unroll
           for (int a = 0; a < HIPSTR_NUM_ARTIFACTS; a++) {
             const int BD = B + (a - HIPSTR_MAX_ARTIFACT_UNITS) * p;
-            const int base_len = min(BD, j + 1);
-            double v = IMPOSSIBLE;
-            if (BD >= 0) {
-              const double pre_row = (j - base_len < 0) ? 0.0 : prev[j - base_len];
-              v = __ldg(tcol + a * t_pitch) + pre_row;
-            }
-            probs[a] = v;
+            const int from = j - min(BD, j + 1);                   // column of the row above the block this size continues from
+            const double above = prev[max(from, 0)];
+            probs[a] = select_if_nonneg(BD, probs[a] + select_if_nonneg(from, above, 0.0), IMPOSSIBLE);
           }
           double mx = probs[0];
 #pragma unroll
