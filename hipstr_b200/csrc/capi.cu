@@ -88,9 +88,10 @@ struct hipstr_ctx {
   hipstr_dev_batch scratch;              // reused by hipstr_align_batch_host
   hipstr_dev_genotype gscratch;          // reused by hipstr_genotype_batch_host
   DevBuf d_ll, d_pos, d_misc[12], d_out[6], d_last, d_counters;
-  DevBuf d_stut;                         // stutter tables of the chunk in flight (K1a -> K1b)
+  DevBuf d_stut, d_stut2;                // stutter tables of the chunks in flight (K1a -> K1b), two alternating buffers
+  cudaStream_t table_stream = nullptr;   // K1a of chunk c+1 runs here while K1b of chunk c drains on `stream`
+  cudaEvent_t ev_tables[2] = {nullptr, nullptr}, ev_folded[2] = {nullptr, nullptr}, ev_inputs = nullptr;
   DevBuf d_stut_pos, d_dec, d_art, d_job_t_off[kNumColVariants];   // K5 forward pass -> walk back
-  float last_stutter_ms = 0.f;           // of the timed align call: K1a's share
   double* d_debug = nullptr;             // test hook, see hipstr_debug_lastcols
   double trace_seconds[4] = {0, 0, 0, 0};   // accumulated over hipstr_trace_batch_host calls: lowering, ordering + uploads, kernel, downloads
 };
@@ -247,8 +248,12 @@ hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll
   int64_t t_max = 2;
   for (const FlatBatch::Chunk& ck : d.chunks) t_max = std::max(t_max, ck.t_doubles);
   CU(ctx->d_stut.reserve((size_t)t_max * sizeof(double)));
+  // With more than one chunk the tables alternate between two buffers and K1a runs on its own stream: the tables of
+  // chunk c+1 are computed while K1b of chunk c drains, so no launch ends on a GPU that is emptying.
+  const bool overlap = d.chunks.size() > 1;
+  if (overlap) CU(ctx->d_stut2.reserve((size_t)t_max * sizeof(double)));
+  double* const tables[2] = {(double*)ctx->d_stut.p, overlap ? (double*)ctx->d_stut2.p : (double*)ctx->d_stut.p};
   p.last_scratch = (double*)ctx->d_last.p;
-  p.stut = (const double*)ctx->d_stut.p;
   p.pool_t_off = (const int64_t*)d.pool_t_off.p;
   p.l_max = l_all;
   p.debug_out = ctx->d_debug;
@@ -260,19 +265,30 @@ hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll
   sp.reps = p.reps; sp.progs = p.progs; sp.rep_tabs = p.rep_tabs;
   sp.qual_lut = p.qual_lut; sp.int_logs = p.int_logs;
   sp.pool_t_off = p.pool_t_off;
-  sp.stut = (double*)ctx->d_stut.p;
+  cudaStream_t table_stream = overlap ? ctx->table_stream : ctx->stream;
+  if (overlap) {   // the uploads and the counter reset above are on `stream`
+    CU(cudaEventRecord(ctx->ev_inputs, ctx->stream));
+    CU(cudaStreamWaitEvent(table_stream, ctx->ev_inputs, 0));
+  }
   for (size_t c = 0; c < d.chunks.size(); c++) {
     const FlatBatch::Chunk& ck = d.chunks[c];
+    const int buf = (int)(c & 1);
     int32_t* counters = (int32_t*)ctx->d_counters.p + c * (kNumColVariants + 1);
-    // K1a: the stutter tables of the chunk's (read, allele) pairs; K1b of the same chunk follows on the stream and the
-    // next chunk's K1a, which overwrites the buffer, follows that
+    // K1a: the stutter tables of the chunk's (read, allele) pairs, once K1b of the chunk that used this buffer is done
+    if (overlap && c >= 2) CU(cudaStreamWaitEvent(table_stream, ctx->ev_folded[buf], 0));
     if (ck.stut_job1 > ck.stut_job0) {
       sp.jobs = (const DevStutJob*)d.stut_jobs.p + ck.stut_job0;
       sp.n_jobs = ck.stut_job1 - ck.stut_job0;
       sp.job_counter = counters + kNumColVariants;
-      CU(launch_stutter(sp, ctx->stream));
+      sp.stut = tables[buf];
+      CU(launch_stutter(sp, table_stream));
       ctx->last_launches++;
     }
+    if (overlap) {
+      CU(cudaEventRecord(ctx->ev_tables[buf], table_stream));
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_tables[buf], 0));
+    }
+    p.stut = tables[buf];
     for (int v = kNumColVariants - 1; v >= 0; v--) {   // longest reads first
       if (ck.job1[v] == ck.job0[v]) continue;
       p.jobs = (const DevJob*)d.jobs[v].p + ck.job0[v];
@@ -282,6 +298,7 @@ hipstr_status_t run_align(hipstr_ctx* ctx, const hipstr_dev_batch& d, double* ll
       CU(launch_align(v, p, HIPSTR_MAX_ALIGN_CTAS, ctx->stream, nullptr));
       ctx->last_launches++;
     }
+    if (overlap) CU(cudaEventRecord(ctx->ev_folded[buf], ctx->stream));
   }
   return HIPSTR_OK;
 }
@@ -426,6 +443,9 @@ hipstr_status_t hipstr_create(int device, hipstr_ctx_t** out_ctx) {
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   ctx->stream = ctx->own_stream;
+  if ((e = cudaStreamCreateWithFlags(&ctx->table_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  for (cudaEvent_t* ev : {&ctx->ev_tables[0], &ctx->ev_tables[1], &ctx->ev_folded[0], &ctx->ev_folded[1], &ctx->ev_inputs})
+    if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
   const HostTables& T = host_tables();
   if ((e = cudaMalloc(&ctx->d_qual_lut, sizeof(T.qual_lut))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->d_trans, sizeof(T.trans))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -441,6 +461,10 @@ void hipstr_destroy(hipstr_ctx_t* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  if (ctx->table_stream) { cudaStreamSynchronize(ctx->table_stream); cudaStreamDestroy(ctx->table_stream); }
+  for (cudaEvent_t ev : {ctx->ev_tables[0], ctx->ev_tables[1], ctx->ev_folded[0], ctx->ev_folded[1], ctx->ev_inputs})
+    if (ev) cudaEventDestroy(ev);
+  ctx->d_stut2.release();
   ctx->scratch.release();
   ctx->gscratch.release();
   ctx->d_ll.release();

@@ -307,7 +307,7 @@ inline unsigned convert_bases(const unsigned char* __restrict src, char* __restr
 }  // namespace
 
 int64_t stutter_table_budget_doubles() {
-  int64_t mb = 6144;
+  int64_t mb = 16384;
   if (const char* e = std::getenv("HIPSTR_T_BUDGET_MB")) mb = std::max<int64_t>(1, std::atoll(e));
   return mb * (1 << 20) / 8;
 }

@@ -115,7 +115,7 @@ void parallel_run(size_t n, int workers, const std::function<void(size_t)>& fn);
  * trace_optimal_aln sees: the haplotype is fixed, nothing is reused) instead of replaying the
  * reuse history of a process_reads run. */
 hipstr_status_t flatten_batch(const hipstr_align_batch_t* b, FlatBatch& out, std::string& err, bool fresh_rows = false);
-/* Doubles of stutter table one chunk may hold (HIPSTR_T_BUDGET_MB, default 6144 MB). */
+/* Doubles of stutter table one chunk may hold (HIPSTR_T_BUDGET_MB, default 16384 MB of the 180 GB; the device keeps two such buffers when a batch has several chunks). */
 int64_t stutter_table_budget_doubles();
 int64_t count_alignments(const hipstr_align_batch_t* b);
 

@@ -56,6 +56,32 @@ def test_fuzz_batch_against_oracle(seed, long_reads):
     assert d.max() <= 1e-9
 
 
+@pytest.mark.parametrize("budget_mb", [1, 3])
+def test_fuzz_batch_in_many_chunks(budget_mb, monkeypatch):
+    """The same kind of batch with the stutter-table budget forced down to a few megabytes: the tables are computed chunk by
+    chunk into two alternating buffers, K1a of a chunk on its own stream while K1b of the previous chunk drains
+    (capi.cu run_align).  Results must not depend on the chunking."""
+    rng = np.random.default_rng(11)
+    bb = BatchBuilder()
+    for _ in range(60):
+        blocks, reads = random_locus(rng, False)
+        bb.add_locus(blocks, reads)
+    b = bb.build()
+    want, wpos = checkers.align(checkers.oracle(), "oracle_", b, b.n_out, want_pos=True, fill=3.5)
+    ctx = Context(0)
+    whole = ctx.align_host(b, b.n_out, ll=np.full(b.n_out, 3.5))
+    n_whole = ctx.lib.hipstr_last_launch_count(ctx.h)
+    monkeypatch.setenv("HIPSTR_T_BUDGET_MB", str(budget_mb))
+    for rep in range(3):   # repeated calls reuse the two buffers and their events
+        got = ctx.align_host(b, b.n_out, ll=np.full(b.n_out, 3.5))
+        assert np.array_equal(got, whole)
+    n_chunked = ctx.lib.hipstr_last_launch_count(ctx.h)
+    ctx.close()
+    print("[chunks] %d alignments: %d launches in one chunk, %d with a %d MB budget" % (got.size, n_whole, n_chunked, budget_mb))
+    assert n_chunked >= 3 * n_whole > 0
+    assert np.abs(got - want).max() <= 1e-9
+
+
 def test_properties_at_scale():
     """BASELINE configs[1] shape at 120 loci (1 M alignments; the oracle would need minutes): size-independent checks."""
     s = Synth(n_loci=120, n_samples=100, reads_per_sample=30, n_alleles=8, read_len=150, seed=2000)

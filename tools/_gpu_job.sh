@@ -1,10 +1,9 @@
 set -x
-mkdir -p gpurun_out/r2f
-cp hipstr_b200/libhipstr_b200.so /tmp/lib_keep.so
-for v in nosplit split splittr splittrah splitah nosplit; do
-  cp tools/_variants/libhipstr_b200_$v.so hipstr_b200/libhipstr_b200.so
-  echo "== $v" >> gpurun_out/r2f/variants.log
-  python tools/quick_time.py 200 8 5 2>&1 | grep "run 2\|run 3\|run 4\|checksum" >> gpurun_out/r2f/variants.log
+mkdir -p gpurun_out/r2j
+timeout 900 python -m pytest tests/test_gpu_fuzz.py -x -q -m gpu -s 2>&1 | tail -15 > gpurun_out/r2j/fuzz.log; cat gpurun_out/r2j/fuzz.log
+for mb in 8192 4096 16384; do
+  echo "== budget $mb" >> gpurun_out/r2j/budget.log
+  HIPSTR_T_BUDGET_MB=$mb python tools/quick_time.py 200 8 4 2>&1 | grep "run 3\|checksum" >> gpurun_out/r2j/budget.log
 done
-cp /tmp/lib_keep.so hipstr_b200/libhipstr_b200.so
-cat gpurun_out/r2f/variants.log
+cat gpurun_out/r2j/budget.log
+python tools/trace_time.py 2>&1 | tail -4

@@ -20,3 +20,15 @@ for rep in range(2):
     dt = time.perf_counter() - t
     print("K5: %d traces in %.1f ms -> %.2f M traces/s (host buffers, end to end); stutter!=0 in %d" %
           (len(pools), dt * 1e3, len(pools) / dt / 1e6, int(((out["stutter_size"][:, 1] != 0)).sum())))
+# small-batch latency: what one locus of the loop asks for between two rounds (a batch of ONE locus)
+s1 = hb.Synth(n_loci=1, n_samples=100, reads_per_sample=30, n_alleles=8, read_len=150, seed=2001)
+pools1 = np.nonzero(s1.pool_seed >= 0)[0].astype(np.int32)
+haps1 = rng.integers(0, 8, len(pools1)).astype(np.int32)
+bs1 = block_starts(s1.batch)
+for n_small in (16, 64, 256):
+    ctx.trace(s1.batch, bs1, pools1[:n_small], haps1[:n_small])
+    t = time.perf_counter()
+    for _ in range(50):
+        ctx.trace(s1.batch, bs1, pools1[:n_small], haps1[:n_small])
+    print("K5 small batch: %d traces of one locus, %.3f ms per call (host buffers in, host buffers out, includes the ctypes wrapper)" %
+          (n_small, (time.perf_counter() - t) / 50 * 1e3))
