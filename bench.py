@@ -292,6 +292,8 @@ def gpu_full_loop(device, synth, pipelines, window, reps, world=1, rank=0, dist=
         res = {"loci_per_s": L / dt, "seconds": dt, "loci": L, "n_gpus": world, "pipelines_per_gpu": pipelines, "window_loci": window,
                "scaling": "strong: one shared locus list, windows dealt dynamically" + (" to the ranks through the rendezvous store" if world > 1 else " to the pipelines"),
                "records_on_rank0": n_merged, "alignments_this_rank": st["alignments"], "traces_this_rank": st["traces"],
+               "h2d_bytes_this_rank": st["h2d_bytes"], "d2h_bytes_this_rank": st["d2h_bytes"], "gpu_launches_this_rank": st["gpu_launches"],
+               "read_bytes_of_the_list": 2 * int(np.ctypeslib.as_array(synth.view.read_seq_off, shape=(int(synth.n_reads) + 1,))[-1]),
                "windows_per_worker_this_rank": st["windows_per_worker"], "stage_seconds_summed_over_windows_this_rank": st["stage_seconds"],
                "host_threads": int(os.environ.get("HIPSTR_HOST_THREADS", host_cores())),
                "what": "hipstr_multi_genotype: create_from_reads + genotype(1000, 4, 0.01, reassemble_flanks) + write_vcf per window, host buffers in, VCF text out",
@@ -608,9 +610,10 @@ def main():
                   "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                   "config": {"workload": "%d synthetic loci, %d samples x %d reads, %d alleles, %d bp reads; one shared list, windows of %d loci dealt dynamically"
                                          % (loop_loci, a.samples, a.reads_per_sample, a.alleles, a.read_len, a.window)},
-                  "e2e": {"value": fl["loci_per_s"], "unit": "loci/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-                          "note": "the loop's inputs are host buffers and its output is VCF text: value is already end to end"},
-                  "gpu_launches": None, "cpu_baseline": cpu_baseline, "clocks": clocks.summary() if clocks else None, "full_loop": fl})
+                  "e2e": {"value": fl["loci_per_s"], "unit": "loci/s", "h2d_bytes_per_step": fl["h2d_bytes_this_rank"],
+                          "d2h_bytes_per_step": fl["d2h_bytes_this_rank"],
+                          "note": "the loop's inputs are host buffers and its output is VCF text: value is already end to end; bytes and launches are rank 0's share"},
+                  "gpu_launches": fl["gpu_launches_this_rank"], "cpu_baseline": cpu_baseline, "clocks": clocks.summary() if clocks else None, "full_loop": fl})
         if world > 1:
             dist.destroy_process_group()
         return

@@ -819,6 +819,8 @@ def load():
     lib.hipstr_multi_locus_record.argtypes = [vp, C.c_int32, c_i32p, vp, C.c_int32]
     lib.hipstr_multi_stats.restype = C.c_int32
     lib.hipstr_multi_stats.argtypes = [vp, c_i64p, c_i64p, c_f64p, c_i32p, c_f64p]
+    lib.hipstr_multi_traffic.restype = C.c_int32
+    lib.hipstr_multi_traffic.argtypes = [vp, c_i64p, c_i64p, c_i64p]
     _lib = lib
     return lib
 
@@ -1388,8 +1390,11 @@ class MultiGenotyper:
         a, t = C.c_int64(), C.c_int64()
         sec, win, busy = np.zeros(9), np.zeros(nw, np.int32), np.zeros(nw)
         self.lib.hipstr_multi_stats(self.h, C.byref(a), C.byref(t), ptr(sec, c_f64p), ptr(win, c_i32p), ptr(busy, c_f64p))
+        h2d, d2h, nl = C.c_int64(), C.c_int64(), C.c_int64()
+        self.lib.hipstr_multi_traffic(self.h, C.byref(h2d), C.byref(d2h), C.byref(nl))
         return {"alignments": a.value, "traces": t.value, "stage_seconds": dict(zip(self.STAGES, [round(float(x), 4) for x in sec])),
-                "windows_per_worker": win.tolist(), "busy_seconds_per_worker": [round(float(x), 3) for x in busy]}
+                "windows_per_worker": win.tolist(), "busy_seconds_per_worker": [round(float(x), 3) for x in busy],
+                "h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "gpu_launches": nl.value}
 
 
 class Context:

@@ -26,8 +26,7 @@ int FlankAssembler::node(std::string_view kmer) {
   return id;
 }
 
-void FlankAssembler::increment_edge(std::string_view from, std::string_view to, int delta) {
-  const int s = node(from), d = node(to);
+void FlankAssembler::increment_edge(int s, int d, int delta) {
   for (int e : arriving_[d])
     if (edges_[e].source == s) { edges_[e].weight += delta; return; }
   const int id = (int)edges_.size();
@@ -39,8 +38,13 @@ void FlankAssembler::increment_edge(std::string_view from, std::string_view to, 
 void FlankAssembler::add_string(std::string_view seq, int weight, int copies) {
   if ((int)seq.size() <= k_) return;
   num_strings_ += copies;
-  const std::string_view s = seq;
-  for (size_t i = 1; i + k_ <= seq.size(); i++) increment_edge(s.substr(i - 1, k_), s.substr(i, k_), weight * copies);
+  // consecutive edges share a node: every k-mer is looked up once (nodes are still created source first, in string order)
+  int from = node(seq.substr(0, k_));
+  for (size_t i = 1; i + k_ <= seq.size(); i++) {
+    const int to = node(seq.substr(i, k_));
+    increment_edge(from, to, weight * copies);
+    from = to;
+  }
 }
 
 void FlankAssembler::prune_edges(double min_edge_freq, int min_weight) {

@@ -47,7 +47,7 @@ class FlankAssembler {
   std::vector<std::vector<int> > arriving_, departing_;   /* node id -> edge ids, insertion order */
 
   int node(std::string_view kmer);                /* get_node: creates the node when absent */
-  void increment_edge(std::string_view from, std::string_view to, int delta);
+  void increment_edge(int from_node, int to_node, int delta);
   void alt_kmer_nodes(std::string kmer, bool source, bool sink, std::vector<int>& nodes);
 };
 

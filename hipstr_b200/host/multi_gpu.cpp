@@ -39,7 +39,7 @@ struct hipstr_multi {
   std::vector<int32_t> windows_done;          // per worker
   std::vector<double> busy_seconds;           // per worker
   double seconds[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  int64_t n_alignments = 0, n_traces = 0;
+  int64_t n_alignments = 0, n_traces = 0, h2d_bytes = 0, d2h_bytes = 0, gpu_launches = 0;
   std::string last_error;
 };
 
@@ -122,7 +122,7 @@ hipstr_status_t hipstr_multi_genotype(hipstr_multi_t* m, int32_t n_loci, const i
   m->windows_done.assign((size_t)n_workers, 0);
   m->busy_seconds.assign((size_t)n_workers, 0.0);
   std::fill(m->seconds, m->seconds + 9, 0.0);
-  m->n_alignments = m->n_traces = 0;
+  m->n_alignments = m->n_traces = m->h2d_bytes = m->d2h_bytes = m->gpu_launches = 0;
   if (locus_ok) std::memset(locus_ok, 0, (size_t)n_loci);
   std::atomic<int32_t> counter(0);
   std::atomic<int> failed(0);
@@ -175,6 +175,7 @@ hipstr_status_t hipstr_multi_genotype(hipstr_multi_t* m, int32_t n_loci, const i
         for (int i = 0; i < 9; i++) m->seconds[i] += g->batch.seconds[i];
         m->n_alignments += g->batch.n_alignments;
         m->n_traces += g->batch.n_traces;
+        m->h2d_bytes += g->batch.h2d_bytes; m->d2h_bytes += g->batch.d2h_bytes; m->gpu_launches += g->batch.gpu_launches;
         m->window_owner[(size_t)win] = w;
         m->windows_done[(size_t)w]++;
         m->busy_seconds[(size_t)w] += hipstr::now_s() - t0;
@@ -217,6 +218,14 @@ hipstr_status_t hipstr_multi_stats(const hipstr_multi_t* m, int64_t* n_alignment
   if (seconds9) std::copy(m->seconds, m->seconds + 9, seconds9);
   if (windows_per_worker) std::copy(m->windows_done.begin(), m->windows_done.end(), windows_per_worker);
   if (busy_seconds_per_worker) std::copy(m->busy_seconds.begin(), m->busy_seconds.end(), busy_seconds_per_worker);
+  return HIPSTR_OK;
+}
+
+hipstr_status_t hipstr_multi_traffic(const hipstr_multi_t* m, int64_t* h2d_bytes, int64_t* d2h_bytes, int64_t* gpu_launches) {
+  if (!m) return HIPSTR_ERR_BAD_ARG;
+  if (h2d_bytes) *h2d_bytes = m->h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = m->d2h_bytes;
+  if (gpu_launches) *gpu_launches = m->gpu_launches;
   return HIPSTR_OK;
 }
 

@@ -30,6 +30,12 @@ namespace {
 }  // namespace
 int host_threads() { return host_thread_budget(); }
 void parallel_for(size_t n, const std::function<void(size_t)>& fn) { parallel_run(n, host_threads(), fn); }
+void GenotyperBatch::account_device_call() {
+  int64_t h2d = 0, d2h = 0;
+  int32_t launches = 0;
+  hipstr_last_traffic(ctx_, &h2d, &d2h, &launches);
+  h2d_bytes += h2d; d2h_bytes += d2h; gpu_launches += launches;
+}
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 namespace {
 
@@ -1064,6 +1070,7 @@ hipstr_status_t GenotyperBatch::run_alignments(const std::vector<int>& which, st
   out.total_ll = total_ll.p;
   seconds[T_ALIGN_PACK] += now_s() - t_pack;
   hipstr_status_t st = hipstr_genotype_batch_host(ctx_, &bt, &rb, &out);
+  account_device_call();
   if (st != HIPSTR_OK) { err = std::string("hipstr_genotype_batch_host: ") + hipstr_last_error(ctx_); return st; }
   n_alignments += hipstr_batch_num_alignments(&bt);
   const double t_unpack = now_s();
@@ -1116,6 +1123,7 @@ hipstr_status_t GenotyperBatch::run_posteriors(const std::vector<int>& which, st
   hipstr_status_t st = hipstr_posteriors_host(ctx_, (int32_t)L, locus_read_off.data(), locus_sample_off.data(), n_haps.data(),
                                               haploid.data(), read_ll.p, log_p1.p, log_p2.p, sample_label.p, read_weight.p, post.p,
                                               sample_ll.p, best.p, total_ll.p);
+  account_device_call();
   if (st != HIPSTR_OK) { err = std::string("hipstr_posteriors_host: ") + hipstr_last_error(ctx_); return st; }
   parallel_for(L, [&](size_t k) {
     SeqStutterGenotyper& g = *gs[k];
@@ -1194,6 +1202,7 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
     hipstr_align_batch_t bt = pb.view();
     const double t_dev = now_s();
     hipstr_status_t st = hipstr_trace_batch_host(ctx_, &bt, pb.block_start.data(), (int32_t)n, trace_pool.data(), trace_hap.data(), &out);
+    account_device_call();
     seconds[T_TRACE_DEVICE] += now_s() - t_dev;
     if (st != HIPSTR_OK) { err = std::string("hipstr_trace_batch_host: ") + hipstr_last_error(ctx_); return st; }
     n_traces += (int64_t)n;
@@ -1382,6 +1391,7 @@ hipstr_status_t GenotyperBatch::recompute_stutter_models(int max_total_haplotype
   std::vector<int32_t> iters(problem.size());
   st = hipstr_em_train_host(ctx_, &em, max_em_iter, abs_ll_converge, frac_ll_converge, params.data(), converged.data(), iters.data(),
                             ll.data());
+  account_device_call();
   if (st != HIPSTR_OK) { err = std::string("hipstr_em_train_host: ") + hipstr_last_error(ctx_); return st; }
   for (size_t k = 0; k < problem.size(); k++) {
     SeqStutterGenotyper& g = loci[problem[k].first];

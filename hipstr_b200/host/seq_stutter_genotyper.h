@@ -226,6 +226,8 @@ class GenotyperBatch {
   std::vector<SeqStutterGenotyper> loci;
   bool keep_traced_alignments = false;   /* also build AlignmentTrace::cigar / alignment (only the visualisation reads them) */
   int64_t n_alignments = 0, n_traces = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0, gpu_launches = 0;   /* summed over every device call of the loop (hipstr_last_traffic) */
+  void account_device_call();
   int n_rounds = 0;
   /* wall-clock seconds by stage: construction, per-locus host decisions, trace device calls, trace stitching +
    * bookkeeping, alignment calls (packing + K1/K2/K3 + unpacking), posterior calls, VCF formatting */

@@ -512,6 +512,7 @@ hipstr_status_t GenotyperBatch::write_vcf_records(const hipstr_vcf_loci_t* regio
                                                      hap_to_allele.data(), haploid.data(), post.data(), sample_ll.data(), best_hap.data(),
                                                      best_gt.data(), log_phased.data(), log_unphased.data(), hap_log_phased.data(),
                                                      hap_log_unphased.data(), gl.data(), phased_gl.data(), gl_diff.data(), pl.data());
+  account_device_call();
   if (st != HIPSTR_OK) { err = std::string("hipstr_extract_genotypes_host: ") + hipstr_last_error(ctx_); return st; }
   // traces of the reads against the haplotype their strand assignment picks
   parallel_for(which.size(), [&](size_t k) { loci[which[k]].vcf_prepare(&best_hap[2 * (size_t)locus_sample_off[k]]); });

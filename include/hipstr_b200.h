@@ -572,6 +572,9 @@ hipstr_status_t hipstr_multi_emit_records(const hipstr_multi_t* m, const hipstr_
  * (device-major, pipeline-minor) the windows it processed and the seconds it was busy; any pointer may be NULL */
 hipstr_status_t hipstr_multi_stats(const hipstr_multi_t* m, int64_t* n_alignments, int64_t* n_traces, double* seconds9,
                                    int32_t* windows_per_worker, double* busy_seconds_per_worker);
+/* host->device and device->host bytes and kernel launches of the last hipstr_multi_genotype call, summed over every device
+ * call of every window (each window's reads, haplotypes and results cross the bus per round: see DESIGN.md 7) */
+hipstr_status_t hipstr_multi_traffic(const hipstr_multi_t* m, int64_t* h2d_bytes, int64_t* d2h_bytes, int64_t* gpu_launches);
 
 /* Pure host arithmetic of write_vcf_record, exported so that it can be checked on its own:
  *   hipstr_allele_bias       compute_allele_bias (seq_stutter_genotyper.cpp:965-982): log10 of the two-sided
