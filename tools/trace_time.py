@@ -15,9 +15,13 @@ ctx = hb.Context(0)
 bs = block_starts(s.batch)
 ctx.trace(s.batch, bs, pools[:64], haps[:64])
 for rep in range(2):
+    before = np.array(list(ctx.trace_seconds().values()))
     t = time.perf_counter()
     out = ctx.trace(s.batch, bs, pools, haps)
     dt = time.perf_counter() - t
+    inside = np.array(list(ctx.trace_seconds().values())) - before
+    print("    inside hipstr_trace_batch_host: lowering %.1f ms, ordering + uploads %.1f ms, kernels %.1f ms, downloads %.1f ms -> %.2f M traces/s "
+          "(the rest of the wall time is this script's ctypes / numpy wrapper)" % (*(1e3 * inside), len(pools) / max(inside.sum(), 1e-9) / 1e6))
     print("K5: %d traces in %.1f ms -> %.2f M traces/s (host buffers, end to end); stutter!=0 in %d" %
           (len(pools), dt * 1e3, len(pools) / dt / 1e6, int(((out["stutter_size"][:, 1] != 0)).sum())))
 # small-batch latency: what one locus of the loop asks for between two rounds (a batch of ONE locus)
