@@ -256,25 +256,40 @@ def loop_vcf_loci(synth):
                               [raw[l * cl:(l + 1) * cl] for l in range(L)], names * L, names)
 
 
-def gpu_full_loop(device, synth, pipelines, window, reps, world=1, rank=0, dist=None, torch_dev=None, barrier=None,
+def gpu_full_loop(device, segments, pipelines, window, reps, world=1, rank=0, dist=None, torch_dev=None, barrier=None,
                   max_over_ranks=None):
     """Seam B1 end to end: hipstr_multi_genotype (create_from_reads -> genotype(flank assembly) -> write_vcf per window).
-    One shared locus list; at N>1 the ranks pull windows from one counter in the rendezvous store (dynamic dealing, strong
-    scaling) and the finished VCF records are gathered to rank 0 over NCCL inside the timed region."""
+    One shared locus list (handed over in `segments`, see main); at N>1 the ranks pull windows from one counter in the
+    rendezvous store (dynamic dealing, strong scaling) and the finished VCF records are gathered to rank 0 over NCCL inside
+    the timed region."""
     from hipstr_b200.capi import MultiGenotyper
     from hipstr_b200.sharding import StoreDealer, gather_vcf_records
-    L = synth.n_loci
-    vl = loop_vcf_loci(synth)   # inputs of write_vcf_record are host buffers the caller owns, like the reads
+    L = sum(sg.n_loci for sg in segments)
+    base = np.concatenate([[0], np.cumsum([sg.n_loci for sg in segments])]).astype(int)
+    vls = [loop_vcf_loci(sg) for sg in segments]   # inputs of write_vcf_record are host buffers the caller owns, like the reads
+    read_bytes = sum(2 * int(np.ctypeslib.as_array(sg.view.read_seq_off, shape=(int(sg.n_reads) + 1,))[-1]) for sg in segments)
     m = MultiGenotyper(devices=[device], pipelines=pipelines)
     store = dist.distributed_c10d._get_default_store() if world > 1 else None
     best = None
     for rep in range(reps):   # the first pass warms the allocations (device buffers, page-locked block cache)
-        dealer = StoreDealer(store, "hipstr_loop_%d" % rep) if world > 1 else None
         if barrier:
             barrier()
         t0 = time.perf_counter()
-        ok, rec = m.genotype_synth(synth, vl, window, next_window=dealer)
-        mine = [(l, "chrS", r[0], r[1]) for l, r in enumerate(rec) if r is not None]
+        mine, oks, st = [], [], None
+        for k, (sg, vl) in enumerate(zip(segments, vls)):
+            dealer = StoreDealer(store, "hipstr_loop_%d_%d" % (rep, k)) if world > 1 else None
+            ok_k, rec = m.genotype_synth(sg, vl, window, next_window=dealer)
+            mine += [(int(base[k]) + l, "chrS", r[0], r[1]) for l, r in enumerate(rec) if r is not None]
+            oks.append(ok_k)
+            sk = m.stats()   # per call: summed over the segments here
+            if st is None:
+                st = sk
+            else:
+                for key in ("alignments", "traces", "h2d_bytes", "d2h_bytes", "gpu_launches"):
+                    st[key] += sk[key]
+                st["stage_seconds"] = {n: round(st["stage_seconds"][n] + v, 4) for n, v in sk["stage_seconds"].items()}
+                st["windows_per_worker"] = [x + y for x, y in zip(st["windows_per_worker"], sk["windows_per_worker"])]
+        ok = np.concatenate(oks)
         n_merged = len(mine)
         merged = mine
         if world > 1:   # the one collective: finished records to rank 0
@@ -288,12 +303,12 @@ def gpu_full_loop(device, synth, pipelines, window, reps, world=1, rank=0, dist=
             dt = max_over_ranks(time.perf_counter() - t0)
         else:
             dt = time.perf_counter() - t0
-        st = m.stats()
-        res = {"loci_per_s": L / dt, "seconds": dt, "loci": L, "n_gpus": world, "pipelines_per_gpu": pipelines, "window_loci": window,
+        res = {"loci_per_s": L / dt, "seconds": dt, "loci": L, "segments": [int(sg.n_loci) for sg in segments], "n_gpus": world,
+               "pipelines_per_gpu": pipelines, "window_loci": window,
                "scaling": "strong: one shared locus list, windows dealt dynamically" + (" to the ranks through the rendezvous store" if world > 1 else " to the pipelines"),
                "records_on_rank0": n_merged, "alignments_this_rank": st["alignments"], "traces_this_rank": st["traces"],
                "h2d_bytes_this_rank": st["h2d_bytes"], "d2h_bytes_this_rank": st["d2h_bytes"], "gpu_launches_this_rank": st["gpu_launches"],
-               "read_bytes_of_the_list": 2 * int(np.ctypeslib.as_array(synth.view.read_seq_off, shape=(int(synth.n_reads) + 1,))[-1]),
+               "read_bytes_of_the_list": read_bytes,
                "windows_per_worker_this_rank": st["windows_per_worker"], "stage_seconds_summed_over_windows_this_rank": st["stage_seconds"],
                "host_threads": int(os.environ.get("HIPSTR_HOST_THREADS", host_cores())),
                "what": "hipstr_multi_genotype: create_from_reads + genotype(1000, 4, 0.01, reassemble_flanks) + write_vcf per window, host buffers in, VCF text out",
@@ -523,14 +538,27 @@ def main():
 
     loop_only = a.workload == "loop"
     t_gen = time.time()
-    s = hb.Synth(n_loci=a.loci, n_samples=a.samples, reads_per_sample=a.reads_per_sample, n_alleles=a.alleles,
-                 read_len=a.read_len, seed=2000 + (0 if loop_only else rank))
     # the loop's shared list: the same loci on every rank (windows are dealt dynamically, any rank may get any window)
     loop_loci = a.loop_loci or (a.loci if (world == 1 or loop_only) else max(2000, 1000 * world))
-    s_loop = s if (world == 1 or loop_only) and loop_loci == a.loci else None
-    if s_loop is None and not a.no_full_loop:
-        s_loop = hb.Synth(n_loci=loop_loci, n_samples=a.samples, reads_per_sample=a.reads_per_sample, n_alleles=a.alleles,
-                          read_len=a.read_len, seed=2000)
+    # The C-ABI's read offsets are 32-bit (hipstr_locus_reads_t): a list whose read bytes pass ~1.5 GB is handed over in
+    # segments, each one hipstr_multi_genotype call with its own dealer (configs[2], 10 000 loci x 3 000 reads x 150 bp = 4.5 GB)
+    seg_loci = max(a.window, int(1.5e9 / max(1, a.samples * a.reads_per_sample * a.read_len)) // a.window * a.window)
+    seg_sizes = [min(seg_loci, loop_loci - k) for k in range(0, loop_loci, seg_loci)]
+    if not loop_only and a.loci > seg_loci:
+        raise SystemExit("bench.py: --loci %d passes the 32-bit read offsets of one batch (at most %d loci of this shape)" % (a.loci, seg_loci))
+    s = hb.Synth(n_loci=seg_sizes[0] if loop_only else a.loci, n_samples=a.samples, reads_per_sample=a.reads_per_sample,
+                 n_alleles=a.alleles, read_len=a.read_len, seed=2000 + (0 if loop_only else rank))
+    if (world == 1 or loop_only) and loop_loci == a.loci and len(seg_sizes) == 1:
+        loop_segments = [s]
+    elif loop_only:
+        loop_segments = [s] + [hb.Synth(n_loci=n, n_samples=a.samples, reads_per_sample=a.reads_per_sample, n_alleles=a.alleles,
+                                        read_len=a.read_len, seed=2000 + 7919 * k) for k, n in enumerate(seg_sizes) if k > 0]
+    elif a.no_full_loop:
+        loop_segments = []
+    else:
+        loop_segments = [hb.Synth(n_loci=n, n_samples=a.samples, reads_per_sample=a.reads_per_sample, n_alleles=a.alleles,
+                                  read_len=a.read_len, seed=2000 + 7919 * k) for k, n in enumerate(seg_sizes)]
+    s_loop = loop_segments[0] if loop_segments else None   # the reference check samples its loci from the first segment
     t_gen = time.time() - t_gen
     alg_bytes, n_aln, cells = algorithmic_bytes(s)
 
@@ -590,8 +618,8 @@ def main():
     def run_loop():
         if clocks:
             clocks.on = True
-        fl = gpu_full_loop(local, s_loop, a.pipelines, a.window, 3, world=world, rank=rank, dist=dist, torch_dev=dev, barrier=barrier,
-                           max_over_ranks=max_over_ranks)
+        fl = gpu_full_loop(local, loop_segments, a.pipelines, a.window, 3, world=world, rank=rank, dist=dist, torch_dev=dev,
+                           barrier=barrier, max_over_ranks=max_over_ranks)
         if clocks:
             clocks.on = False
         if rank == 0 and ref_records:

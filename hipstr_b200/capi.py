@@ -857,6 +857,8 @@ class Synth:
         self.cfg = SynthCfg(n_loci, n_samples, reads_per_sample, n_alleles, read_len, trim, period, ref_copies, seed,
                             stutter_rate, sub_rate, mate_rate, flank_snp_freq, haploid)
         self._h = lib.hipstr_synth_create(C.byref(self.cfg))
+        if not self._h:
+            raise HipstrError(3, "hipstr_synth_create: the reads of %d loci do not fit the 32-bit offsets of one batch" % n_loci)
         self.view = lib.hipstr_synth_view(self._h).contents
         v, b = self.view, self.view.batch
         self.batch = b

@@ -13,6 +13,7 @@
  */
 #include "hipstr_synth.h"
 
+#include <climits>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -233,6 +234,8 @@ extern "C" hipstr_synth_t* hipstr_synth_create(const hipstr_synth_cfg_t* cfg_in)
       S->read_bp_diff.push_back(reads[r].bp_diff);
       S->read_bases.insert(S->read_bases.end(), reads[r].seq.begin(), reads[r].seq.end());
       S->read_quals.insert(S->read_quals.end(), reads[r].qual.begin(), reads[r].qual.end());
+      // offsets of the C-ABI are 32-bit: a request that does not fit is refused (callers split their locus lists)
+      if (S->read_bases.size() > (size_t)INT32_MAX) { delete S; return nullptr; }
       S->read_seq_off.push_back((int32_t)S->read_bases.size());
       S->read_start.push_back(reads[r].start);
       {
