@@ -91,6 +91,8 @@ struct hipstr_ctx {
   DevBuf d_stut, d_stut2;                // stutter tables of the chunks in flight (K1a -> K1b), two alternating buffers
   cudaStream_t table_stream = nullptr;   // K1a of chunk c+1 runs here while K1b of chunk c drains on `stream`
   cudaEvent_t ev_tables[2] = {nullptr, nullptr}, ev_folded[2] = {nullptr, nullptr}, ev_inputs = nullptr;
+  cudaEvent_t ev_wait = nullptr;         // cudaEventBlockingSync: host waits sleep instead of spinning (see wait_stream)
+  bool sleeping_waits = true;
   DevBuf d_stut_pos, d_dec, d_art, d_job_t_off[kNumColVariants];   // K5 forward pass -> walk back
   double* d_debug = nullptr;             // test hook, see hipstr_debug_lastcols
   double trace_seconds[4] = {0, 0, 0, 0};   // accumulated over hipstr_trace_batch_host calls: lowering, ordering + uploads, kernel, downloads
@@ -101,6 +103,16 @@ namespace {
 hipstr_status_t fail(hipstr_ctx* c, hipstr_status_t st, const std::string& msg) {
   if (c) c->last_error = msg;
   return st;
+}
+
+// Host wait for everything queued on `s`.  cudaStreamSynchronize spins on a core; the loop runs several pipelines per GPU and
+// several GPUs per box on the same cores, where a spinning wait takes a core away from another pipeline's host work, so the
+// wait goes through an event created with cudaEventBlockingSync (the thread sleeps).  HIPSTR_SPIN_WAITS=1 restores spinning.
+cudaError_t wait_stream(hipstr_ctx* ctx, cudaStream_t s) {
+  if (!ctx->sleeping_waits || !ctx->ev_wait) return cudaStreamSynchronize(s);
+  cudaError_t e = cudaEventRecord(ctx->ev_wait, s);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ctx->ev_wait);
 }
 #define CU(call)                                                                               \
   do {                                                                                         \
@@ -216,7 +228,7 @@ hipstr_status_t stage(hipstr_ctx* ctx, const hipstr_align_batch_t* batch, hipstr
   d.n_alignments = f.n_alignments;
   d.has_mask = !f.hap_mask.empty();
   // the staging buffers are reused by the next call: the copies above must have completed
-  CU(cudaStreamSynchronize(s));
+  CU(wait_stream(ctx, s));
   return HIPSTR_OK;
 }
 
@@ -376,7 +388,7 @@ hipstr_status_t stage_reads(hipstr_ctx* ctx, const hipstr_align_batch_t* b, cons
   CU(put(g.read_weight, r->read_weight, (size_t)R, s));
   CU(put(g.log_p1, r->log_p1, (size_t)R, s));
   CU(put(g.log_p2, r->log_p2, (size_t)R, s));
-  CU(cudaStreamSynchronize(s));   // `loci` / `samples` are locals
+  CU(wait_stream(ctx, s));   // `loci` / `samples` are locals
   g.n_loci = n_loci; g.n_samples = S; g.n_reads = R; g.n_elems = elem; g.post_size = post;
   g.has_copy_read = r->copy_read != nullptr;
   g.masked = r->copy_read || b->realign_pool || b->realign_hap;
@@ -446,6 +458,8 @@ hipstr_status_t hipstr_create(int device, hipstr_ctx_t** out_ctx) {
   if ((e = cudaStreamCreateWithFlags(&ctx->table_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   for (cudaEvent_t* ev : {&ctx->ev_tables[0], &ctx->ev_tables[1], &ctx->ev_folded[0], &ctx->ev_folded[1], &ctx->ev_inputs})
     if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_wait, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) return bail("event", e);
+  if (const char* spin = std::getenv("HIPSTR_SPIN_WAITS")) ctx->sleeping_waits = std::atoi(spin) == 0;
   const HostTables& T = host_tables();
   if ((e = cudaMalloc(&ctx->d_qual_lut, sizeof(T.qual_lut))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->d_trans, sizeof(T.trans))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -462,7 +476,7 @@ void hipstr_destroy(hipstr_ctx_t* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   if (ctx->table_stream) { cudaStreamSynchronize(ctx->table_stream); cudaStreamDestroy(ctx->table_stream); }
-  for (cudaEvent_t ev : {ctx->ev_tables[0], ctx->ev_tables[1], ctx->ev_folded[0], ctx->ev_folded[1], ctx->ev_inputs})
+  for (cudaEvent_t ev : {ctx->ev_tables[0], ctx->ev_tables[1], ctx->ev_folded[0], ctx->ev_folded[1], ctx->ev_inputs, ctx->ev_wait})
     if (ev) cudaEventDestroy(ev);
   ctx->d_stut2.release();
   ctx->scratch.release();
@@ -516,7 +530,7 @@ float hipstr_last_kernel_ms(const hipstr_ctx_t* ctx) { return ctx ? ctx->last_ms
 hipstr_status_t hipstr_collect_timing(hipstr_ctx_t* ctx, double* k1_ms, double* rest_ms, int32_t* n_calls) {
   if (!ctx) return HIPSTR_ERR_BAD_ARG;
   CU(cudaSetDevice(ctx->device));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(wait_stream(ctx, ctx->stream));
   double a = 0, b = 0;
   for (auto& ev : ctx->pending) {
     float t0 = 0, t1 = 0;
@@ -583,7 +597,7 @@ hipstr_status_t hipstr_align_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   if (st != HIPSTR_OK) return st;
   CU(get(ctx, ll_out, ctx->d_ll.p, n));
   if (seed_hap_pos) CU(get(ctx, seed_hap_pos, ctx->d_pos.p, n));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(wait_stream(ctx, ctx->stream));
   end_call(ctx);
   return HIPSTR_OK;
 }
@@ -663,7 +677,7 @@ hipstr_status_t hipstr_genotype_batch_host(hipstr_ctx_t* ctx, const hipstr_align
   CU(get(ctx, o->sample_ll, d[3].p, (size_t)g.n_samples));
   if (o->best) CU(get(ctx, o->best, d[4].p, (size_t)g.n_samples * 2));
   if (o->total_ll) CU(get(ctx, o->total_ll, d[5].p, (size_t)g.n_loci));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(wait_stream(ctx, ctx->stream));
   end_call(ctx);
   return HIPSTR_OK;
 }
@@ -703,7 +717,7 @@ hipstr_status_t hipstr_scatter_pool_lls_host(hipstr_ctx_t* ctx, int32_t n_reads,
   ctx->last_launches = 1;
   CU(get(ctx, read_ll, m[3].p, (size_t)n_reads * n_haps));
   if (read_seed) CU(get(ctx, read_seed, m[7].p, (size_t)n_reads));
-  CU(cudaStreamSynchronize(s));
+  CU(wait_stream(ctx, s));
   end_call(ctx);
   return HIPSTR_OK;
 }
@@ -772,7 +786,7 @@ hipstr_status_t hipstr_posteriors_host(hipstr_ctx_t* ctx, int32_t n_loci, const 
   CU(get(ctx, sample_ll_out, m[7].p, (size_t)S));
   if (best_out) CU(get(ctx, best_out, m[8].p, (size_t)S * 2));
   if (total_ll_out) CU(get(ctx, total_ll_out, m[9].p, (size_t)n_loci));
-  CU(cudaStreamSynchronize(s));
+  CU(wait_stream(ctx, s));
   end_call(ctx);
   return HIPSTR_OK;
 }
@@ -870,7 +884,7 @@ hipstr_status_t hipstr_em_train_host(hipstr_ctx_t* ctx, const hipstr_em_batch_t*
   CU(get(ctx, converged_out, o[3].p, (size_t)n_loci));
   if (iters_out) CU(get(ctx, iters_out, o[4].p, (size_t)n_loci));
   if (ll_out) CU(get(ctx, ll_out, o[5].p, (size_t)n_loci));
-  CU(cudaStreamSynchronize(st));
+  CU(wait_stream(ctx, st));
   end_call(ctx);
   return HIPSTR_OK;
 }
@@ -940,7 +954,7 @@ hipstr_status_t hipstr_extract_genotypes_host(hipstr_ctx_t* ctx, int32_t n_loci,
   CU(get(ctx, gl, p.gl, (size_t)gl_off));
   CU(get(ctx, phased_gl, p.phased_gl, (size_t)pgl_off));
   CU(get(ctx, pl, p.pl, (size_t)gl_off));
-  CU(cudaStreamSynchronize(st));
+  CU(wait_stream(ctx, st));
   end_call(ctx);
   return HIPSTR_OK;
 }
@@ -1015,7 +1029,7 @@ hipstr_status_t hipstr_nw_align_batch_host(hipstr_ctx_t* ctx, int32_t n_pairs, c
   CU(get(ctx, ops, p.out_ops, T * ops_stride));
   CU(get(ctx, ops_len, p.out_len, T));
   CU(get(ctx, score, p.out_score, T));
-  CU(cudaStreamSynchronize(s));
+  CU(wait_stream(ctx, s));
   end_call(ctx);
   return HIPSTR_OK;
 }
@@ -1094,7 +1108,7 @@ hipstr_status_t hipstr_snp_phasing_batch_host(hipstr_ctx_t* ctx, const hipstr_sn
   CU(get(ctx, log_p1, p.out_log_p1, E));
   CU(get(ctx, log_p2, p.out_log_p2, E));
   CU(get(ctx, counts, p.out_counts, E * 4));
-  CU(cudaStreamSynchronize(s));
+  CU(wait_stream(ctx, s));
   if (ctx->timing) {
     CU(cudaEventElapsedTime(&ctx->last_ms, t0, t1));
     cudaEventDestroy(t0);
@@ -1275,7 +1289,7 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   ap.stut = (const double*)ctx->d_stut.p; ap.stut_pos = (const int32_t*)ctx->d_stut_pos.p;
   ap.dec = (unsigned char*)ctx->d_dec.p; ap.dec_off = p.dec_off; ap.art = (int32_t*)ctx->d_art.p; ap.art_off = p.art_off;
   ap.trace_seed_pos = (int32_t*)o[2].p;
-  CU(cudaStreamSynchronize(s));
+  CU(wait_stream(ctx, s));
   ctx->trace_seconds[1] += now() - t_mark; t_mark = now();
   ctx->last_launches = 0;
   if (sp.n_jobs > 0) { CU(launch_stutter(sp, s)); ctx->last_launches++; }
@@ -1291,7 +1305,7 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   }
   CU(launch_trace_walk(p, s));
   ctx->last_launches++;
-  CU(cudaStreamSynchronize(s));
+  CU(wait_stream(ctx, s));
   ctx->trace_seconds[2] += now() - t_mark; t_mark = now();
   CU(get(ctx, out->hap_aln, p.out_aln, T * out->aln_stride));
   CU(get(ctx, out->seed_hap_pos, p.out_seed_pos, T));
@@ -1304,7 +1318,7 @@ hipstr_status_t hipstr_trace_batch_host(hipstr_ctx_t* ctx, const hipstr_align_ba
   CU(get(ctx, out->n_snps, p.out_n_snps, T));
   CU(get(ctx, out->indels, p.out_indels, T * 2 * HIPSTR_MAX_TRACE_INDELS));
   CU(get(ctx, out->snps, p.out_snps, T * 2 * HIPSTR_MAX_TRACE_SNPS));
-  CU(cudaStreamSynchronize(s));
+  CU(wait_stream(ctx, s));
   ctx->trace_seconds[3] += now() - t_mark;
   end_call(ctx);
   return HIPSTR_OK;
