@@ -485,7 +485,7 @@ def main():
     ap.add_argument("--alleles", type=int, default=8)
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--loop-loci", type=int, default=0, help="loci of the shared list of full_loop (default: --loci at N=1, 1000 per GPU at N>1: enough windows for every pipeline)")
-    ap.add_argument("--pipelines", type=int, default=4)
+    ap.add_argument("--pipelines", type=int, default=0, help="window pipelines per GPU (default: 4; twice the host threads of a rank, at most 8, when a rank has fewer than 8 threads)")
     ap.add_argument("--window", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -497,6 +497,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:   # the ranks of one box share its host cores: split them instead of oversubscribing (read by the library)
         os.environ.setdefault("HIPSTR_HOST_THREADS", str(max(2, host_cores() // world)))
+    if a.pipelines <= 0:
+        # With few host threads per GPU (8 GPUs on 32 cores) a pipeline is one thread, and it sleeps while its device call runs:
+        # twice as many pipelines as threads keep the cores busy (measured on 4 cores per rank: 4 pipelines 970-1 000 loci/s,
+        # 6: 1 120, 8: 1 135); with 12-16 threads per GPU four pipelines of 3-4 threads are best
+        threads = int(os.environ.get("HIPSTR_HOST_THREADS", host_cores()))
+        a.pipelines = 4 if threads >= 8 else max(4, min(8, 2 * threads))
     if a.impl == "ours" and a.workload == "cfg4_em":
         if rank == 0:
             workload_cfg4_em(a, rank, world, local)
