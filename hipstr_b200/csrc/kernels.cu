@@ -458,14 +458,9 @@ __global__ void __launch_bounds__(32 * HIPSTR_WARPS_PER_CTA, MINB) k_align(const
 template <int C, int MINB, bool TRACE = false>
 static cudaError_t launch_align_c(const AlignParams& p, int max_ctas, cudaStream_t stream, int* grid_out) {
   const size_t smem = align_smem_bytes(p.n_max, p.l_max);
-  cudaError_t e = cudaFuncSetAttribute(k_align<C, MINB, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void*>(&k_align<C, MINB, TRACE>));
   if (e != cudaSuccess) return e;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = sm_count_of_current_device();
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align<C, MINB, TRACE>, 32 * HIPSTR_WARPS_PER_CTA, smem);
   if (e != cudaSuccess) return e;
@@ -1052,7 +1047,7 @@ __global__ void __launch_bounds__(EM_THREADS) k_em_train(const EmParams P) {
 cudaError_t launch_em(const EmParams& p, int max_alleles, cudaStream_t stream) {
   if (p.n_loci <= 0) return cudaSuccess;
   const size_t smem = ((size_t)max_alleles * max_alleles + 2 * (size_t)max_alleles + 7 * EM_WARPS + 7) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(k_em_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void*>(&k_em_train));
   if (e != cudaSuccess) return e;
   k_em_train<<<p.n_loci, EM_THREADS, smem, stream>>>(p);
   return cudaGetLastError();

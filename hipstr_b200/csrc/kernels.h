@@ -210,4 +210,42 @@ struct SnpPhaseParams {
 cudaError_t launch_snp_phase(const SnpPhaseParams& p, int n_sm, cudaStream_t stream);
 
 }  // namespace hipstr
+
+/* Launch helpers shared by the .cu files.  Several host threads (the pipelines of hipstr_multi_*) launch the same kernels with
+ * different shared-memory sizes at the same time: setting cudaFuncAttributeMaxDynamicSharedMemorySize to the size of ONE launch
+ * right before it races with the others (a launch then fails with "invalid argument" when another thread has just lowered the
+ * limit).  The limit is therefore raised ONCE per (kernel, device) to the device's opt-in maximum; what a launch actually gets
+ * is still its own `smem` argument. */
+#ifdef __CUDACC__
+#include <mutex>
+#include <set>
+#include <utility>
+namespace hipstr {
+inline cudaError_t allow_max_dynamic_smem(const void* kernel) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int> > done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count(std::make_pair(kernel, dev))) return cudaSuccess;
+  int optin = 0;
+  if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
+  done.insert(std::make_pair(kernel, dev));
+  return cudaSuccess;
+}
+inline int sm_count_of_current_device() {
+  static std::mutex mu;
+  static int count[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
+  if (!count[dev]) cudaDeviceGetAttribute(&count[dev], cudaDevAttrMultiProcessorCount, dev);
+  return count[dev];
+}
+}  // namespace hipstr
+#endif
+
 #endif

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(128) k_nw_walk(const NwParams P) {
 cudaError_t launch_nw(const NwParams& p, int max_ctas, cudaStream_t stream) {
   if (p.n_pairs <= 0) return cudaSuccess;
   const size_t smem = nw_shared_bytes(p.max_ref, p.max_read);
-  cudaError_t e = cudaFuncSetAttribute(k_nw_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void*>(&k_nw_fill));
   if (e != cudaSuccess) return e;
   const int grid = p.n_pairs < max_ctas ? p.n_pairs : max_ctas;
   k_nw_fill<<<grid, 32, smem, stream>>>(p);

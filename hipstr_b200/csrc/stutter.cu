@@ -358,14 +358,9 @@ __global__ void __launch_bounds__(STUT_THREADS, STUT_MIN_CTAS) k_stutter(const S
 template <bool TRACE>
 static cudaError_t launch_stutter_t(const StutParams& p, cudaStream_t stream) {
   const size_t smem = stut_smem_bytes_hd(p.n_max);
-  cudaError_t e = cudaFuncSetAttribute(k_stutter<TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void*>(&k_stutter<TRACE>));
   if (e != cudaSuccess) return e;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = sm_count_of_current_device();
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stutter<TRACE>, STUT_THREADS, smem);
   if (e != cudaSuccess) return e;
