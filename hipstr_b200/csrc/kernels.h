@@ -231,7 +231,10 @@ inline cudaError_t allow_max_dynamic_smem(const void* kernel) {
   if (done.count(std::make_pair(kernel, dev))) return cudaSuccess;
   int optin = 0;
   if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return e;
+  cudaFuncAttributes attr;
+  if ((e = cudaFuncGetAttributes(&attr, kernel)) != cudaSuccess) return e;
+  const int room = optin - (int)attr.sharedSizeBytes;   // the opt-in maximum covers static + dynamic shared memory
+  if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, room)) != cudaSuccess) return e;
   done.insert(std::make_pair(kernel, dev));
   return cudaSuccess;
 }

@@ -82,6 +82,47 @@ def test_fuzz_batch_in_many_chunks(budget_mb, monkeypatch):
     assert np.abs(got - want).max() <= 1e-9
 
 
+def test_concurrent_contexts_with_different_read_lengths():
+    """Four host threads, each with its own context, align batches whose reads differ in length (different shared-memory
+    sizes of the same kernels) at the same time, as the pipelines of hipstr_multi_* do: every call succeeds and returns
+    what the same batch returns alone.  (Setting a kernel's dynamic shared-memory limit per launch raced here.)"""
+    import threading
+    batches = []
+    for t, long_reads in enumerate([False, True, False, True]):
+        rng = np.random.default_rng(100 + t)
+        bb = BatchBuilder()
+        for _ in range(12):
+            blocks, reads = random_locus(rng, long_reads)
+            bb.add_locus(blocks, reads)
+        batches.append(bb.build())
+    alone = []
+    for b in batches:
+        ctx = Context(0)
+        alone.append(ctx.align_host(b, b.n_out, ll=np.full(b.n_out, 3.5)))
+        ctx.close()
+    errors, results = [], [None] * len(batches)
+
+    def work(i):
+        try:
+            ctx = Context(0)
+            for rep in range(40):
+                got = ctx.align_host(batches[i], batches[i].n_out, ll=np.full(batches[i].n_out, 3.5))
+                if not np.array_equal(got, alone[i]):
+                    raise AssertionError("thread %d, call %d: results differ from the batch run alone" % (i, rep))
+            ctx.close()
+            results[i] = True
+        except Exception as e:   # noqa: BLE001 -- reported below
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(batches))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert all(results)
+
+
 def test_properties_at_scale():
     """BASELINE configs[1] shape at 120 loci (1 M alignments; the oracle would need minutes): size-independent checks."""
     s = Synth(n_loci=120, n_samples=100, reads_per_sample=30, n_alleles=8, read_len=150, seed=2000)

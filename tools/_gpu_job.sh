@@ -1,8 +1,7 @@
 set -x
-mkdir -p gpurun_out/r2q
-timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/r2q/gpu_all.log 2>&1
-tail -4 gpurun_out/r2q/gpu_all.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2q/smoke.log 2>&1; tail -2 gpurun_out/r2q/smoke.log
-python bench.py > gpurun_out/r2q/bench_default.json 2> gpurun_out/r2q/bench_default.err; tail -c 300 gpurun_out/r2q/bench_default.err; cut -c1-330 gpurun_out/r2q/bench_default.json
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2q/bench_reference.json 2> gpurun_out/r2q/bench_reference.err; cut -c1-400 gpurun_out/r2q/bench_reference.json
-python tools/trace_time.py 2>&1 | tail -3
+mkdir -p gpurun_out/r2t
+timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/r2t/gpu_all.log 2>&1
+tail -5 gpurun_out/r2t/gpu_all.log
+python bench.py > gpurun_out/r2t/bench_default.json 2> gpurun_out/r2t/bench_default.err; tail -c 300 gpurun_out/r2t/bench_default.err; cut -c1-200 gpurun_out/r2t/bench_default.json
+python bench.py --workload cfg4_em --loci 1000 --steps 3 --warmup 3 > gpurun_out/r2t/bench_em.json 2> gpurun_out/r2t/bench_em.err; tail -c 300 gpurun_out/r2t/bench_em.err; cut -c1-300 gpurun_out/r2t/bench_em.json
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
