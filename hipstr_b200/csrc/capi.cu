@@ -107,11 +107,17 @@ hipstr_status_t fail(hipstr_ctx* c, hipstr_status_t st, const std::string& msg) 
 
 // Host wait for everything queued on `s`.  cudaStreamSynchronize spins on a core; the loop runs several pipelines per GPU and
 // several GPUs per box on the same cores, where a spinning wait takes a core away from another pipeline's host work, so the
-// wait goes through an event created with cudaEventBlockingSync (the thread sleeps).  HIPSTR_SPIN_WAITS=1 restores spinning.
+// wait goes through an event created with cudaEventBlockingSync (the thread sleeps) -- after polling for 150 us first, which
+// keeps the latency of small calls (a few traces of one locus) where it was.  HIPSTR_SPIN_WAITS=1 restores spinning.
 cudaError_t wait_stream(hipstr_ctx* ctx, cudaStream_t s) {
   if (!ctx->sleeping_waits || !ctx->ev_wait) return cudaStreamSynchronize(s);
   cudaError_t e = cudaEventRecord(ctx->ev_wait, s);
   if (e != cudaSuccess) return e;
+  const auto t0 = std::chrono::steady_clock::now();
+  while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(150)) {
+    e = cudaEventQuery(ctx->ev_wait);
+    if (e != cudaErrorNotReady) return e;   // done (cudaSuccess) or failed
+  }
   return cudaEventSynchronize(ctx->ev_wait);
 }
 #define CU(call)                                                                               \
