@@ -25,7 +25,8 @@ bool HaplotypeGenerator::extract_sequence(const ReadView& aln, int32_t region_st
   if (aln.start >= region_start || aln.stop <= region_end) return false;
   std::string& out = seq;   // built in place: the caller reuses one buffer for all its reads
   out.clear();
-  auto done = [&] { for (char& ch : out) ch = (char)std::toupper((unsigned char)ch); return true; };
+  // read bases are ASCII: upper-casing without the locale-aware call per character
+  auto done = [&] { for (char& ch : out) ch = (ch >= 'a' && ch <= 'z') ? (char)(ch - 32) : ch; return true; };
   int32_t pos = aln.start;   // reference coordinate of the next unconsumed base of the current element
   int read_at = 0;           // next unconsumed read base
   for (int c = 0; c < aln.n_cigar; c++) {
@@ -110,19 +111,23 @@ void HaplotypeGenerator::gen_candidate_seqs(const std::string& ref_seq, int idea
   std::map<std::string, double> sample_counts;   // sum over samples of the fraction of the sample's reads
   std::map<std::string, int> read_counts, must_inc;
   int tot_reads = 0, tot_samples = 0;
+  std::vector<std::pair<std::string, int> > counts;
+  std::string sub;
   for (const std::vector<ReadView>& sample : alignments) {
     int samp_reads = 0;
-    std::map<std::string, int> counts;
-    std::string sub;
+    counts.clear();   // a sample carries a handful of distinct sequences: a flat list beats a tree of strings
     for (const ReadView& aln : sample) {
       if (extract_sequence(aln, region_start, region_end, sub)) {
-        read_counts[sub]++;
-        counts[sub]++;
+        size_t k = 0;
+        while (k < counts.size() && counts[k].first != sub) k++;
+        if (k == counts.size()) counts.emplace_back(sub, 0);
+        counts[k].second++;
         tot_reads++;
         samp_reads++;
       }
     }
     for (const auto& kv : counts) {   // alleles one sample supports strongly on its own
+      read_counts[kv.first] += kv.second;
       if (kv.second >= kMinReadsStrongSample && kv.second >= kMinFracStrongSample * samp_reads) must_inc[kv.first]++;
       sample_counts[kv.first] += kv.second * 1.0 / samp_reads;
     }

@@ -535,6 +535,8 @@ int SeqStutterGenotyper::assemble_flanks() {
     };
     std::unordered_map<std::string_view, FlankInfo> flank_info;
     std::unordered_map<std::string_view, int> edge_id;   // the locus' distinct non-reference (k+1)-mers
+    std::unordered_set<std::string_view> ref_edges;      // the reference flank's (k+1)-mers
+    for (size_t c = 0; c + kmer_length + 1 <= ref_seq.size(); c++) ref_edges.insert(std::string_view(ref_seq).substr(c, kmer_length + 1));
     std::vector<FlankInfo*> read_info(num_reads_, nullptr), trace_info(trace_cache_.size(), nullptr);
     std::vector<uint8_t> trace_seen(trace_cache_.size(), 0);
     for (int r = 0; r < num_reads_; r++) {
@@ -551,7 +553,7 @@ int SeqStutterGenotyper::assemble_flanks() {
         if (!fi.in_reference)
           for (size_t c = 0; c + kmer_length + 1 <= sv.size(); c++) {
             const std::string_view e = sv.substr(c, kmer_length + 1);
-            if (ref_seq.find(e) == std::string::npos) fi.nonref_edges.push_back(edge_id.emplace(e, (int)edge_id.size()).first->second);
+            if (!ref_edges.count(e)) fi.nonref_edges.push_back(edge_id.emplace(e, (int)edge_id.size()).first->second);
           }
         it = flank_info.emplace(sv, std::move(fi)).first;
       }

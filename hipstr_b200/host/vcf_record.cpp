@@ -87,7 +87,19 @@ bool extract_cigar(const char* type, const int32_t* len, int n, int cigar_start,
   return true;
 }
 
-double log_binomial(int n, int k) { return (k == 0 || n == k) ? 0.0 : std::lgamma(n + 1.0) - std::lgamma(k + 1.0) - std::lgamma(n - k + 1.0); }
+/* lgamma(n + 1) for read counts: the very values std::lgamma returns, computed once (three calls per binomial coefficient and a
+ * few dozen coefficients per sample were 2 % of the loop's host time) */
+double lgamma_of_count_plus_one(int n) {
+  static const std::vector<double> table = [] {
+    std::vector<double> t(4096);
+    for (int i = 0; i < (int)t.size(); i++) t[i] = std::lgamma(i + 1.0);
+    return t;
+  }();
+  return (n >= 0 && n < (int)table.size()) ? table[n] : std::lgamma(n + 1.0);
+}
+double log_binomial(int n, int k) {
+  return (k == 0 || n == k) ? 0.0 : lgamma_of_count_plus_one(n) - lgamma_of_count_plus_one(k) - lgamma_of_count_plus_one(n - k);
+}
 
 /* log10 of the two-sided binomial p-value for the read split between the two haplotypes
  * (compute_allele_bias, seq_stutter_genotyper.cpp:965-982; the reference takes the CDF from cephes' bdtr). */
