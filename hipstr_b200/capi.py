@@ -648,6 +648,10 @@ def load():
     lib.hipstr_vcf_writer_close.argtypes = [vp]
     lib.hipstr_vcf_writer_finish.restype = C.c_int32
     lib.hipstr_vcf_writer_finish.argtypes = [vp]
+    lib.hipstr_hap_aln_index.restype = C.c_int32
+    lib.hipstr_hap_aln_index.argtypes = [C.c_char_p, C.c_int32, c_i32p]
+    lib.hipstr_trace_span.restype = C.c_int32
+    lib.hipstr_trace_span.argtypes = [C.c_int32, C.c_char_p, C.c_int32, c_i32p, C.c_char_p, C.c_int32, C.c_int32, c_i32p, c_i32p]
     lib.hipstr_stitch_trace.restype = C.c_int32
     lib.hipstr_stitch_trace.argtypes = [C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, c_i32p, c_i32p,
                                         C.c_int32, C.c_char_p, c_i32p, c_i32p, C.c_int32, C.c_char_p]

@@ -242,6 +242,80 @@ long compose_span(const char* hap, long hap_n, const char* read, long read_n, lo
 
 }  // namespace
 
+extern "C" hipstr_status_t hipstr_hap_aln_index(const char* hap, int32_t n, int32_t* index) {
+  if (!hap || n < 0 || !index) return HIPSTR_ERR_BAD_ARG;
+  int32_t *non_d = index, *non_i = index + (n + 1), *col_of = index + 2 * (n + 1);
+  non_d[0] = non_i[0] = 0;
+  for (int32_t c = 0; c < n; c++) {
+    if (hap[c] != 'M' && hap[c] != 'I' && hap[c] != 'D') return HIPSTR_ERR_BAD_ARG;
+    if (hap[c] != 'D') col_of[non_d[c]] = c;
+    non_d[c + 1] = non_d[c] + (hap[c] != 'D');
+    non_i[c + 1] = non_i[c] + (hap[c] != 'I');
+  }
+  for (int32_t k = non_d[n]; k <= n; k++) col_of[k] = n;   // "no such operation"
+  return HIPSTR_OK;
+}
+
+extern "C" hipstr_status_t hipstr_trace_span(int32_t hap_start, const char* hap, int32_t hap_n, const int32_t* index,
+                                             const char* read, int32_t seed_hap_pos, int32_t seed_base, int32_t* start,
+                                             int32_t* stop) {
+  if (!hap || !index || !read || !start || !stop || hap_n < 0) return HIPSTR_ERR_BAD_ARG;
+  const int32_t *non_d = index, *non_i = index + (hap_n + 1), *col_of = index + 2 * (hap_n + 1);
+  // the seed's column in the haplotype string: after seed_hap_pos non-'D' operations, then over any 'D's
+  if (seed_hap_pos < 0 || seed_hap_pos >= non_d[hap_n]) {
+    // fewer haplotype bases than the seed position (or a negative one): let the stepping form decide
+    int32_t n_cigar = 0;
+    return hipstr_stitch_trace(hap_start, hap, read, seed_hap_pos, seed_base, "", start, stop, 0, nullptr, nullptr, &n_cigar, 0, nullptr);
+  }
+  const long first = seed_hap_pos == 0 ? 0 : col_of[seed_hap_pos - 1] + 1;   // where the counting loop of the stepping form stops
+  const int32_t seed_pos = hap_start + non_i[first];
+  const long hcol = col_of[seed_hap_pos];
+  // one pass over the read's operations: the seed's column, the outermost aligned ('M' / 'D') operation on either side and
+  // how many there are; anything but M, I, D, S goes to the stepping form
+  long read_n = 0, rcol = -1, remaining = seed_base, r_lo = -1, r_hi = -1, n_left = 0, n_right = 0;
+  bool odd = false;
+  for (; read[read_n]; read_n++) {
+    const char c = read[read_n];
+    odd |= !(c == 'M' || c == 'I' || c == 'D' || c == 'S');
+    if (rcol < 0) {
+      if (remaining > 0) remaining -= c != 'D';
+      else if (c != 'D') rcol = read_n;
+    }
+  }
+  if (rcol < 0 || odd || seed_base < 0) {
+    int32_t n_cigar = 0;
+    return hipstr_stitch_trace(hap_start, hap, read, seed_hap_pos, seed_base, "", start, stop, 0, nullptr, nullptr, &n_cigar, 0, nullptr);
+  }
+  for (long r = 0; r < rcol; r++)
+    if (read[r] == 'M' || read[r] == 'D') { if (r_lo < 0) r_lo = r; n_left++; }
+  for (long r = rcol + 1; r < read_n; r++)
+    if (read[r] == 'M' || read[r] == 'D') { r_hi = r; n_right++; }
+  // left of the seed: the n_left aligned operations consume the n_left non-'D' columns before the seed's and every 'D' between
+  long span_left = 0, h = hcol - 1, r = rcol - 1;
+  if (n_left > 0) {
+    if (n_left > non_d[hcol]) return HIPSTR_ERR_BAD_ARG;
+    const long p = col_of[non_d[hcol] - n_left];
+    span_left = non_i[hcol] - non_i[p];
+    h = p - 1;
+    r = r_lo - 1;
+  }
+  const long tail_left = compose_span(hap, hap_n, read, read_n, h, r, -1);
+  long span_right = 0;
+  h = hcol + 1; r = rcol + 1;
+  if (n_right > 0) {
+    if (n_right > non_d[hap_n] - non_d[hcol + 1]) return HIPSTR_ERR_BAD_ARG;
+    const long p = col_of[non_d[hcol + 1] + n_right - 1];
+    span_right = non_i[p + 1] - non_i[hcol + 1];
+    h = p + 1;
+    r = r_hi + 1;
+  }
+  const long tail_right = compose_span(hap, hap_n, read, read_n, h, r, 1);
+  if (tail_left < 0 || tail_right < 0) return HIPSTR_ERR_BAD_ARG;
+  *start = seed_pos - (int32_t)(span_left + tail_left);
+  *stop = seed_pos + (int32_t)(span_right + tail_right);
+  return HIPSTR_OK;
+}
+
 extern "C" hipstr_status_t hipstr_stitch_trace(int32_t hap_start, const char* hap_aln_to_ref, const char* read_aln_to_hap,
                                                int32_t seed_hap_pos, int32_t seed_base, const char* read_bases,
                                                int32_t* start, int32_t* stop, int32_t cigar_cap, char* cigar_type,

@@ -258,6 +258,12 @@ void SeqStutterGenotyper::rebuild_hap_aln_info(const std::map<std::string, std::
     }
     hap_aln_info_[h] = hap_aln_to_ref(ref, seq, first, rep);
   }
+  hap_aln_index_.assign(num_alleles_, std::vector<int32_t>());
+  for (int h = 0; h < num_alleles_; h++) {
+    hap_aln_index_[h].resize(3 * (hap_aln_info_[h].size() + 1));
+    if (hipstr_hap_aln_index(hap_aln_info_[h].c_str(), (int32_t)hap_aln_info_[h].size(), hap_aln_index_[h].data()) != HIPSTR_OK)
+      hap_aln_index_[h].clear();   // an empty string ("Invalid matrix type") or one with other operations: the stepping form
+  }
 }
 
 int SeqStutterGenotyper::best_hap_of_read(int r) const {
@@ -1253,9 +1259,16 @@ hipstr_status_t GenotyperBatch::run_traces(const std::vector<int>& which, std::s
       // traced alignment (used by the reference's HTML visualisation) are built on request (keep_traced_alignments)
       int32_t n_cigar = 0;
       const bool full = keep_traced_alignments;
-      const hipstr_status_t st2 = hipstr_stitch_trace(g.hap_blocks_.front().start, g.hap_aln_info_[key.second].c_str(), ops, seed_hap_pos.p[i],
-                               g.pool_seed_[key.first], full ? std::string(read).c_str() : "", &t.start, &t.stop, (int32_t)ctype.size(), full ? ctype.data() : nullptr,
-                               full ? clen.data() : nullptr, &n_cigar, (int32_t)aln.size(), full ? aln.data() : nullptr);
+      const std::string& to_ref = g.hap_aln_info_[key.second];
+      const std::vector<int32_t>& to_ref_index = g.hap_aln_index_[key.second];
+      const hipstr_status_t st2 =
+          (!full && !to_ref_index.empty())
+              ? hipstr_trace_span(g.hap_blocks_.front().start, to_ref.c_str(), (int32_t)to_ref.size(), to_ref_index.data(), ops,
+                                  seed_hap_pos.p[i], g.pool_seed_[key.first], &t.start, &t.stop)
+              : hipstr_stitch_trace(g.hap_blocks_.front().start, to_ref.c_str(), ops, seed_hap_pos.p[i], g.pool_seed_[key.first],
+                                    full ? std::string(read).c_str() : "", &t.start, &t.stop, (int32_t)ctype.size(),
+                                    full ? ctype.data() : nullptr, full ? clen.data() : nullptr, &n_cigar, (int32_t)aln.size(),
+                                    full ? aln.data() : nullptr);
       if (st2 != HIPSTR_OK) { failed = 1; return; }
       if (full) {
         std::ostringstream cig;

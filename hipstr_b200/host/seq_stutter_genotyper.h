@@ -126,6 +126,7 @@ class SeqStutterGenotyper {
   int num_samples_ = 0, num_reads_ = 0, num_alleles_ = 0;   /* num_alleles_ = number of haplotypes */
   std::vector<HapBlock> hap_blocks_;
   std::vector<std::string> hap_aln_info_;                    /* per haplotype, Haplotype::get_aln_info */
+  std::vector<std::vector<int32_t> > hap_aln_index_;         /* per haplotype, hipstr_hap_aln_index of the string above */
   /* reads (sample-major) */
   std::vector<int32_t> sample_label_, pool_index_, read_weights_, seed_positions_;
   std::vector<uint8_t> second_mate_;

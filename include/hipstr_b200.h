@@ -354,6 +354,17 @@ hipstr_status_t hipstr_stitch_trace(int32_t hap_start, const char* hap_aln_to_re
                                     int32_t* start, int32_t* stop, int32_t cigar_cap, char* cigar_type,
                                     int32_t* cigar_len, int32_t* n_cigar, int32_t aln_cap, char* alignment);
 
+/* The span of hipstr_stitch_trace (start / stop only) for MANY traces against the same haplotype: the haplotype's operation
+ * string is indexed once (hipstr_hap_aln_index: three int32 tables of hap_aln_len + 1 entries each -- non-'D' columns before a
+ * column, non-'I' columns before a column, column of the k-th non-'D' operation), and a trace then jumps over the part of the
+ * walk that consumes haplotype bases instead of stepping through it; only the operations of the read beyond its outermost
+ * aligned base on either side are stepped through.  Same results and status as hipstr_stitch_trace with NULL string buffers
+ * (tests/test_trace.py compares them on random operation strings).  index must hold 3 * (hap_aln_len + 1) entries. */
+hipstr_status_t hipstr_hap_aln_index(const char* hap_aln_to_ref, int32_t hap_aln_len, int32_t* index);
+hipstr_status_t hipstr_trace_span(int32_t hap_start, const char* hap_aln_to_ref, int32_t hap_aln_len, const int32_t* index,
+                                  const char* read_aln_to_hap, int32_t seed_hap_pos, int32_t seed_base, int32_t* start,
+                                  int32_t* stop);
+
 /* --- a17 / seam B4: EM stutter-model learner (kernel K4) --------------------
  * Replaces EMStutterGenotyper(...) + train(...) + get_stutter_model()
  * (em_stutter_genotyper.h:50-117, em_stutter_genotyper.cpp:10-226) for a batch of

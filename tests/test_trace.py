@@ -151,8 +151,75 @@ def test_stitch_trace_matches_reference(case):
         st = lib.hipstr_stitch_trace(hap_start, b1.value, o["hap_aln"][i].encode(), int(o["seed_hap_pos"][i]), int(seeds[pools[i]]),
                                      reads[i].encode(), C.byref(s2), C.byref(e2), 0, None, None, C.byref(n2), 0, None)
         assert (st, s2.value, e2.value, n2.value) == (0, a.value, b.value, 0), i
+        # ... and the indexed form (hipstr_hap_aln_index + hipstr_trace_span)
+        index = np.zeros(3 * (len(b1.value) + 1), np.int32)
+        assert lib.hipstr_hap_aln_index(b1.value, len(b1.value), index.ctypes.data_as(c_i32p)) == 0
+        s3, e3 = C.c_int32(), C.c_int32()
+        st = lib.hipstr_trace_span(hap_start, b1.value, len(b1.value), index.ctypes.data_as(c_i32p), o["hap_aln"][i].encode(),
+                                   int(o["seed_hap_pos"][i]), int(seeds[pools[i]]), C.byref(s3), C.byref(e3))
+        assert (st, s3.value, e3.value) == (0, a.value, b.value), i
         n_checked += 1
     assert n_checked >= 10
+
+
+def test_indexed_trace_span_equals_the_stepping_form():
+    """hipstr_trace_span (jumps over the aligned part of the walk through an index of the haplotype's operation string) against
+    hipstr_stitch_trace without string buffers (steps through both strings) on random operation strings: haplotype strings
+    over M / I / D with runs of D, read strings over M / I / D / S with clipped and inserted ends, seeds anywhere (also beyond
+    either string), an occasional foreign character.  Status, start and stop must agree in every case."""
+    lib = load()
+    rng = np.random.default_rng(12)
+    n_ok = n_bad = 0
+    for trial in range(6000):
+        n_h = int(rng.integers(1, 60))
+        hap = "".join(rng.choice(list("MMMMMMIDD"), n_h))
+        if trial % 2 == 0:   # anything against anything: mostly inconsistent pairs
+            n_r = int(rng.integers(1, 50))
+            core = "".join(rng.choice(list("MMMMMMMIDD"), n_r))
+            read = "".join(rng.choice(list("SI"), int(rng.integers(0, 4)))) + core + "".join(rng.choice(list("IS"), int(rng.integers(0, 4))))
+            seed_hap_pos = int(rng.integers(-1, n_h + 2))
+            seed_base = int(rng.integers(-1, len(read) + 2))
+        else:                # a read laid over a stretch of the haplotype's bases, seeded on one of its matches
+            n_bases = sum(c != "D" for c in hap)
+            x0 = int(rng.integers(0, max(1, n_bases)))
+            x1 = int(rng.integers(x0, n_bases + 1))
+            ops = []
+            for _ in range(x0, x1):
+                if rng.random() < 0.06:
+                    ops.append("I")
+                ops.append("M" if rng.random() < 0.88 else "D")
+            head = "".join(rng.choice(list("SI"), int(rng.integers(0, 3))))
+            read = head + "".join(ops) + "".join(rng.choice(list("IS"), int(rng.integers(0, 3))))
+            matches = [k for k, c in enumerate(ops) if c == "M"]
+            if matches:
+                j = int(rng.choice(matches))
+                seed_hap_pos = x0 + sum(c != "I" for c in ops[:j])
+                seed_base = len(head) + sum(c != "D" for c in ops[:j])
+            else:
+                seed_hap_pos, seed_base = x0, len(head)
+        if trial % 97 == 0 and read:
+            k = int(rng.integers(0, len(read)))
+            read = read[:k] + "X" + read[k + 1:]
+        if not read:
+            read = "S"
+        hap_start = int(rng.integers(0, 1000))
+        a, b, n = C.c_int32(-7), C.c_int32(-7), C.c_int32(-1)
+        st1 = lib.hipstr_stitch_trace(hap_start, hap.encode(), read.encode(), seed_hap_pos, seed_base, b"", C.byref(a), C.byref(b), 0,
+                                      None, None, C.byref(n), 0, None)
+        index = np.zeros(3 * (n_h + 1), np.int32)
+        assert lib.hipstr_hap_aln_index(hap.encode(), n_h, index.ctypes.data_as(c_i32p)) == 0
+        c, d = C.c_int32(-7), C.c_int32(-7)
+        st2 = lib.hipstr_trace_span(hap_start, hap.encode(), n_h, index.ctypes.data_as(c_i32p), read.encode(), seed_hap_pos, seed_base,
+                                    C.byref(c), C.byref(d))
+        assert st1 == st2, (trial, hap, read, seed_hap_pos, seed_base, st1, st2)
+        if st1 == 0:
+            assert (a.value, b.value) == (c.value, d.value), (trial, hap, read, seed_hap_pos, seed_base)
+            n_ok += 1
+        else:
+            n_bad += 1
+    assert n_ok > 1500 and n_bad > 300, (n_ok, n_bad)
+    index = np.zeros(12, np.int32)
+    assert lib.hipstr_hap_aln_index(b"MXM", 3, index.ctypes.data_as(c_i32p)) != 0   # only M / I / D can be indexed
 
 
 # ---- complete flank lists (hipstr_trace_flank_lists): fixed-size slots of K5 vs reads with more entries ----------
