@@ -142,7 +142,9 @@ hipstr_status_t hipstr_filter_reads(const hipstr_bam_records_t* recs, const char
   }
   std::unique_ptr<hipstr_filtered_reads> h(new hipstr_filtered_reads());
   try {
-    filter.run(recs->records, recs->ref_names, recs->file_names, chrom_seq, regions, rg_to_sample, h->reads);
+    // a view, not a std::string: the chromosome is not copied per call
+    filter.run(recs->records, recs->ref_names, recs->file_names, std::string_view(chrom_seq, std::strlen(chrom_seq)), regions, rg_to_sample,
+               h->reads);
     if (filter.options.remove_pcr_dups) hipstr::ReadFilter::remove_pcr_duplicates(rg_to_library, recs->file_names, h->reads);
   } catch (const std::exception& e) {
     g_error = e.what();
@@ -274,7 +276,7 @@ int32_t hipstr_alignment_filters(int32_t pos, int32_t end_pos, const char* bases
   if (!bases || !quals || (n_cigar > 0 && (!cigar_type || !cigar_len)) || !chrom_seq || !out || !sum_qual) return -2;
   BamRecord a;
   fill_record(a, 0, pos, end_pos, bases, quals, n_cigar, cigar_type, cigar_len);
-  const std::string ref(chrom_seq);
+  const std::string_view ref(chrom_seq, std::strlen(chrom_seq));
   try {
     out[0] = hipstr::filters::has_largest_end_matches(a, ref, 0, window, window) ? 1 : 0;
     const std::pair<int, int> m = hipstr::filters::num_end_matches(a, ref, 0);

@@ -184,10 +184,19 @@ hipstr_status_t hipstr_left_align_reads_host(hipstr_ctx_t* ctx, int32_t n_loci, 
   std::vector<Trimmed> reads(R);
   std::vector<int> locus_of(R);
   std::vector<size_t> chrom_len(n_loci);
+  {
+    // one strlen per distinct chromosome of the window, not one per locus (a chromosome is up to 250 MB)
+    std::map<const char*, size_t> length_of;
+    for (int l = 0; l < n_loci; l++) {
+      if (!chrom_seq[l]) return HIPSTR_ERR_BAD_ARG;
+      auto it = length_of.find(chrom_seq[l]);
+      if (it == length_of.end()) it = length_of.emplace(chrom_seq[l], std::strlen(chrom_seq[l])).first;
+      chrom_len[l] = it->second;
+    }
+  }
   // every step below is per locus and independent: the loci of the window are spread over the host threads
   parallel_for((size_t)n_loci, [&](size_t li) {
     const int l = (int)li;
-    chrom_len[l] = std::strlen(chrom_seq[l]);
     for (int r = raw->locus_read_off[l]; r < raw->locus_read_off[l + 1]; r++) {
       Trimmed& a = reads[r];
       locus_of[r] = l;

@@ -17,13 +17,13 @@ namespace {
 inline char low(char c) { return (c >= 'A' && c <= 'Z') ? (char)(c + ('a' - 'A')) : c; }
 
 /* number of leading characters of `pattern` equal (ignoring case) to text[at...] */
-int prefix_matches(const std::string& pattern, const std::string& text, int at) {
+int prefix_matches(std::string_view pattern, std::string_view text, int at) {
   int n = 0;
   while (n < (int)pattern.size() && at + n < (int)text.size() && low(pattern[n]) == low(text[at + n])) n++;
   return n;
 }
 /* number of trailing characters of `pattern` equal (ignoring case) to text[...at], read backwards from `at` */
-int suffix_matches(const std::string& pattern, const std::string& text, int at) {
+int suffix_matches(std::string_view pattern, std::string_view text, int at) {
   int n = 0;
   while (n < (int)pattern.size() && at - n >= 0 && low(pattern[pattern.size() - 1 - n]) == low(text[at - n])) n++;
   return n;
@@ -259,7 +259,7 @@ std::pair<int, int> end_dist_to_indel(const BamRecord& a) {
   return std::make_pair(dist_to_indel(a.cigar.begin(), a.cigar.end()), dist_to_indel(a.cigar.rbegin(), a.cigar.rend()));
 }
 
-std::pair<int, int> num_end_matches(const BamRecord& a, const std::string& ref, int ref_seq_start) {
+std::pair<int, int> num_end_matches(const BamRecord& a, std::string_view ref, int ref_seq_start) {
   if (a.pos < ref_seq_start) return std::make_pair(-1, -1);
   size_t read_index = 0, ref_index = (size_t)(a.pos - ref_seq_start);
   auto it = a.cigar.begin();
@@ -297,7 +297,7 @@ std::pair<int, int> num_end_matches(const BamRecord& a, const std::string& ref, 
   return in_head ? std::make_pair(run, run) : std::make_pair(head, run);
 }
 
-bool has_largest_end_matches(const BamRecord& a, const std::string& ref, int ref_seq_start, int max_external, int max_internal) {
+bool has_largest_end_matches(const BamRecord& a, std::string_view ref, int ref_seq_start, int max_external, int max_internal) {
   // GetUnclippedInfo: the aligned part of the read and its first / last reference coordinate
   int32_t start = a.pos, last = a.pos - 1;
   bool leading = true;
@@ -411,7 +411,7 @@ void ReadFilter::valid_pairings(const BamRecord& a1, const BamRecord& a2, const 
 // read_and_filter_reads (bam_processor.cpp:173-474)
 // ---------------------------------------------------------------------------------------------
 void ReadFilter::run(const std::vector<BamRecord>& records, const std::vector<std::string>& ref_names, const std::vector<std::string>& file_names,
-                     const std::string& chrom_seq, const std::vector<std::pair<int32_t, int32_t> >& regions,
+                     std::string_view chrom_seq, const std::vector<std::pair<int32_t, int32_t> >& regions,
                      const std::map<std::string, std::string>& rg_to_sample, FilteredReads& out) {
   if (regions.empty()) throw FilterError("no region given");
   int32_t group_start = INT_MAX, group_stop = INT_MIN;

@@ -18,6 +18,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <string_view>
 #include <utility>
 #include <vector>
 
@@ -51,8 +52,8 @@ class AdapterTrimmer {
 
 namespace filters {
 std::pair<int, int> end_dist_to_indel(const BamRecord& a);
-std::pair<int, int> num_end_matches(const BamRecord& a, const std::string& ref_seq, int ref_seq_start);
-bool has_largest_end_matches(const BamRecord& a, const std::string& ref_seq, int ref_seq_start, int max_external, int max_internal);
+std::pair<int, int> num_end_matches(const BamRecord& a, std::string_view ref_seq, int ref_seq_start);
+bool has_largest_end_matches(const BamRecord& a, std::string_view ref_seq, int ref_seq_start, int max_external, int max_internal);
 double sum_log_prob_correct(const std::string& quals);
 }  // namespace filters
 
@@ -89,7 +90,7 @@ class ReadFilter {
   /* records: the reader's stream for the padded region, files one after the other; ref_names / file_names resolve
    * ref_id / file; regions: [start, stop) of every STR of the group; rg_to_sample keys are file name + read group id. */
   void run(const std::vector<BamRecord>& records, const std::vector<std::string>& ref_names, const std::vector<std::string>& file_names,
-           const std::string& chrom_seq, const std::vector<std::pair<int32_t, int32_t> >& regions,
+           std::string_view chrom_seq, const std::vector<std::pair<int32_t, int32_t> >& regions,
            const std::map<std::string, std::string>& rg_to_sample, FilteredReads& out);
   /* remove_pcr_duplicates (pcr_duplicates.cpp:19-94); returns the number of duplicate sets removed */
   static int32_t remove_pcr_duplicates(const std::map<std::string, std::string>& rg_to_library, const std::vector<std::string>& file_names,

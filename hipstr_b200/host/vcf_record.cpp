@@ -136,7 +136,7 @@ double fisher_two_sided(int n11, int n12, int n21, int n22) {
 /* Alleles of the STR block as the VCF reports them: trimmed to the region where all alleles agree, padded back with
  * reference sequence, one base added on the left when an allele would be empty or start differently
  * (get_alleles, seq_stutter_genotyper.cpp:691-769). */
-std::pair<int, int> get_alleles(const HapBlock& block, int32_t region_start, int32_t region_stop, const std::string& chrom_seq,
+std::pair<int, int> get_alleles(const HapBlock& block, int32_t region_start, int32_t region_stop, std::string_view chrom_seq,
                                 int32_t& pos, std::vector<std::string>& alleles) {
   alleles = block.seqs;
   int32_t left_trim = 0, start = block.start;
@@ -162,8 +162,8 @@ std::pair<int, int> get_alleles(const HapBlock& block, int32_t region_start, int
   }
   end -= right_trim;
   for (std::string& a : alleles) a = a.substr(0, a.size() - right_trim);
-  std::string left_flank = start >= region_start ? upper(chrom_seq.substr(region_start, start - region_start)) : "";
-  const std::string right_flank = end <= region_stop ? upper(chrom_seq.substr(end, region_stop - end)) : "";
+  std::string left_flank = start >= region_start ? upper(std::string(chrom_seq.substr(region_start, start - region_start))) : "";
+  const std::string right_flank = end <= region_stop ? upper(std::string(chrom_seq.substr(end, region_stop - end))) : "";
   pos = std::min(region_start, start);
   left_trim -= (int32_t)left_flank.size();
   right_trim -= (int32_t)right_flank.size();
@@ -174,7 +174,7 @@ std::pair<int, int> get_alleles(const HapBlock& block, int32_t region_start, int
     if (pad_left) {
       pos -= 1;
       left_trim -= 1;
-      left_flank = upper(chrom_seq.substr(pos, 1));
+      left_flank = upper(std::string(chrom_seq.substr(pos, 1)));
     }
   }
   for (std::string& a : alleles) a = left_flank + a + right_flank;
@@ -233,7 +233,7 @@ void SeqStutterGenotyper::vcf_prepare(const int32_t* best_hap) {
 namespace {
 
 void format_record(SeqStutterGenotyper& g, const LocusGenotypes& k3b, const std::string& chrom, const std::string& name,
-                   int32_t region_start, int32_t region_stop, int32_t period, const std::string& chrom_seq,
+                   int32_t region_start, int32_t region_stop, int32_t period, std::string_view chrom_seq,
                    const std::vector<std::string>& locus_names, const std::vector<std::string>& out_names,
                    const hipstr_vcf_options_t& opt) {
   const int S = g.num_samples_, nb = (int)g.hap_blocks_.size();
@@ -530,6 +530,18 @@ hipstr_status_t GenotyperBatch::write_vcf_records(const hipstr_vcf_loci_t* regio
   parallel_for(which.size(), [&](size_t k) { loci[which[k]].vcf_prepare(&best_hap[2 * (size_t)locus_sample_off[k]]); });
   st = run_traces(which, err);
   if (st != HIPSTR_OK) return st;
+  // a view of every locus' chromosome (the C-ABI hands NUL-terminated sequences: one strlen per distinct chromosome, and no
+  // copy -- a std::string parameter here copied the whole chromosome for every record)
+  std::vector<std::string_view> chrom_of(which.size());
+  {
+    std::map<const char*, size_t> length_of;
+    for (size_t k = 0; k < which.size(); k++) {
+      const char* c = regions->chrom_seq[which[k]];
+      auto it = length_of.find(c);
+      if (it == length_of.end()) it = length_of.emplace(c, c ? std::strlen(c) : 0).first;
+      chrom_of[k] = std::string_view(c ? c : "", it->second);
+    }
+  }
   parallel_for(which.size(), [&](size_t k) {
     const int l = which[k];
     SeqStutterGenotyper& g = loci[l];
@@ -546,7 +558,7 @@ hipstr_status_t GenotyperBatch::write_vcf_records(const hipstr_vcf_loci_t* regio
     for (int s = 0; s < g.num_samples_; s++) locus_names.push_back(regions->locus_sample_names[sample_base[l] + s]);
     for (int s = 0; s < regions->n_out_samples; s++) out_names.push_back(regions->out_sample_names[s]);
     format_record(g, v, regions->chrom[l], regions->name && regions->name[l] ? regions->name[l] : "", regions->region_start[l],
-                  regions->region_stop[l], regions->period[l], regions->chrom_seq[l], locus_names, out_names, *options);
+                  regions->region_stop[l], regions->period[l], chrom_of[k], locus_names, out_names, *options);
   });
   seconds[T_VCF] += (now_s() - t_begin) - (seconds[T_TRACE_DEVICE] - other0);
   return HIPSTR_OK;
