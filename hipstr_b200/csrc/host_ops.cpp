@@ -109,7 +109,7 @@ extern "C" hipstr_status_t hipstr_pool_reads(int32_t n_reads, const int32_t* seq
   int32_t at = 0;
   std::vector<const unsigned char*> rows;
   std::vector<unsigned char> work;
-  uint16_t hist[256];
+  uint32_t hist[256];   // a pool can hold more than 65 535 reads (amplicon data)
   std::memset(hist, 0, sizeof(hist));
   for (size_t p = 0; p < last_member.size(); p++) {
     const int32_t first = pool_first_read[p];
