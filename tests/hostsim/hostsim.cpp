@@ -192,3 +192,33 @@ hipstr_status_t hipstr_snp_phasing_batch_host(hipstr_ctx_t*, const hipstr_snp_ph
 }
 
 }  // extern "C"
+
+/* Test hook for the product's host thread pool (hipstr::parallel_run, csrc/flatten.cpp): `callers` threads call it at the same
+ * time, each `rounds` times over `n` indices with `workers` workers, and every index calls it again from inside (nested use,
+ * as the loop does when a per-locus step lowers a batch).  Returns the number of wrong sums (0 = every index ran exactly once). */
+#include <atomic>
+#include <thread>
+extern "C" int64_t hostsim_exercise_thread_pool(int32_t callers, int32_t rounds, int32_t n, int32_t workers) {
+  std::atomic<int64_t> wrong(0);
+  auto one_caller = [&](int c) {
+    for (int r = 0; r < rounds; r++) {
+      std::vector<std::atomic<int32_t> > hits((size_t)n);
+      for (auto& h : hits) h = 0;
+      std::atomic<int64_t> inner_total(0);
+      hipstr::parallel_run((size_t)n, workers, [&](size_t i) {
+        hits[i]++;
+        std::atomic<int64_t> inner(0);
+        hipstr::parallel_run(4, 2, [&](size_t k) { inner += (int64_t)(k + 1); });   // 1 + 2 + 3 + 4
+        inner_total += inner.load();
+      });
+      for (auto& h : hits) wrong += h.load() != 1;
+      wrong += inner_total.load() != 10 * (int64_t)n;
+      (void)c;
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int c = 0; c < callers; c++) threads.emplace_back(one_caller, c);
+  for (auto& t : threads) t.join();
+  return wrong.load();
+}
+

@@ -131,3 +131,28 @@ def test_multi_shared_dealer_across_handles(sim):
     assert ((results[0][0] | results[1][0]) == ok1).all()
     for h in handles:
         h.close()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")   # forking with parked threads is the point
+def test_host_thread_pool_under_concurrent_and_nested_use():
+    """hipstr::parallel_run (one process-wide pool of parked threads behind every parallel loop of the host side): eight callers
+    at once, 200 rounds each, nested calls from inside every index; every index runs exactly once and nothing deadlocks.  Then
+    the same from a forked child (a fork keeps none of the parked threads: the child starts a pool of its own)."""
+    lib = C.CDLL(HOSTSIM)
+    f = lib.hostsim_exercise_thread_pool
+    f.restype = C.c_int64
+    f.argtypes = [C.c_int32] * 4
+    assert f(8, 200, 37, 5) == 0
+    assert f(1, 50, 1, 4) == 0          # fewer indices than workers
+    assert f(3, 20, 1000, 16) == 0
+    pid = os.fork()
+    if pid == 0:
+        try:
+            ok = f(4, 50, 37, 5) == 0
+        except BaseException:
+            ok = False
+        os._exit(0 if ok else 1)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+
