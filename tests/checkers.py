@@ -80,3 +80,19 @@ def posteriors(lib, prefix, locus_read_off, locus_sample_off, n_haps, haploid, r
         ptr(read_weight, c_i32p), ptr(post, c_f64p), ptr(sample_ll, c_f64p), ptr(best, c_i32p), ptr(total, c_f64p))
     assert st == 0, st
     return post, sample_ll, best.reshape(-1, 2), total
+
+
+def build_hostsim():
+    """Builds tests/hostsim/libhipstr_hostsim.so (make decides whether anything is stale) under a file lock: several test
+    modules need it and pytest-xdist runs them in different processes."""
+    import fcntl
+    import subprocess
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "hostsim")
+    with open(os.path.join(d, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            subprocess.run(["make", "-s", "-C", d], check=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return os.path.join(d, "libhipstr_hostsim.so")
+

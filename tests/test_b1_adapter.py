@@ -71,7 +71,7 @@ def run(lib, tmp_path, seed):
 @needs
 @pytest.mark.parametrize("seed", [7, 19])
 def test_b1_adapter_over_host_simulation(tmp_path, seed):
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostsim")], check=True)
+    checkers.build_hostsim()
     run(os.path.join(ROOT, "tests", "hostsim", "libhipstr_hostsim.so"), tmp_path, seed)
 
 

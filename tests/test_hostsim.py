@@ -23,7 +23,7 @@ needs_ref = pytest.mark.skipif(checkers.ref() is None, reason="oracle/_ref/libhi
 @pytest.fixture(scope="module")
 def sim():
     """capi bound to the host simulation for the duration of this module."""
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostsim")], check=True)
+    checkers.build_hostsim()
     saved = (capi._lib, capi.LIB_PATH)
     capi._lib, capi.LIB_PATH = None, HOSTSIM
     try:

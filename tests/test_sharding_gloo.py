@@ -165,7 +165,8 @@ def test_shared_list_loop_two_ranks(tmp_path):
     holds after the gather equal the single-process result in locus order."""
     import json
     import subprocess
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostsim")], check=True)
+    import checkers
+    checkers.build_hostsim()
     n_loci = 9
     out = str(tmp_path / "loop.json")
     mp.spawn(_loop_worker, args=(2, _free_port(), n_loci, out), nprocs=2, join=True)
